@@ -1,0 +1,73 @@
+"""numpy mirrors of the C records of include/gf2_abi.h (aligned structured dtypes: arrays of these can be handed to
+the C ABI as-is) and ctypes mirrors of the option/summary structs."""
+import ctypes as C
+import numpy as np
+
+MAX_FRAMES = 11
+MAX_LANDMARKS = 1000
+MAX_PRIOR_DIM = 96
+
+OBS = np.dtype([("x", "f4"), ("y", "f4"), ("vx", "f4"), ("vy", "f4")], align=True)
+IMU_SAMPLE = np.dtype([("dt", "f8"), ("acc", "f8", 3), ("gyr", "f8", 3)], align=True)
+WHEEL_SAMPLE = np.dtype([("dt", "f8"), ("vel", "f8", 3), ("gyr", "f8", 3)], align=True)
+IMU_PREINT = np.dtype([("sum_dt", "f8"), ("delta_p", "f8", 3), ("delta_q", "f8", 4), ("delta_v", "f8", 3),
+                       ("lin_ba", "f8", 3), ("lin_bg", "f8", 3), ("jacobian", "f8", 225), ("covariance", "f8", 225),
+                       ("valid", "i4"), ("pad_", "i4")], align=True)
+WHEEL_PREINT = np.dtype([("sum_dt", "f8"), ("delta_p", "f8", 3), ("delta_q", "f8", 4),
+                         ("lin_sx", "f8"), ("lin_sy", "f8"), ("lin_sw", "f8"), ("lin_td", "f8"),
+                         ("lin_vel", "f8", 3), ("lin_gyr", "f8", 3), ("vel_1", "f8", 3), ("gyr_1", "f8", 3),
+                         ("jacobian", "f8", 18), ("covariance", "f8", 36), ("valid", "i4"), ("pad_", "i4")], align=True)
+PLANE = np.dtype([("p_body", "f8", 3), ("normal", "f8", 3), ("offset", "f8"), ("weight", "f8"),
+                  ("frame", "i4"), ("pad_", "i4")], align=True)
+PRIOR_BLOCK = np.dtype([("kind", "i4"), ("index", "i4"), ("offset", "i4"), ("pad_", "i4"), ("x0", "f8", 9)], align=True)
+
+BLK_POSE, BLK_SPEEDBIAS, BLK_EX_POSE, BLK_TD, BLK_EX_WHEEL, BLK_SX, BLK_SY, BLK_SW, BLK_TD_WHEEL = range(9)
+CONST_EX_POSE, CONST_TD, CONST_EX_WHEEL, CONST_WHEEL_INTRINSIC, CONST_TD_WHEEL = 1, 2, 4, 8, 16
+CONST_ALL_CALIB = 31
+TERM_NAMES = ["no_convergence", "function_tol", "gradient_tol", "parameter_tol", "min_radius", "failure"]
+LK_USE_INITIAL_FLOW = 4
+
+
+class SolverCfg(C.Structure):
+    _fields_ = [("device", C.c_int32), ("max_windows", C.c_int32), ("n_frames", C.c_int32),
+                ("max_landmarks", C.c_int32), ("max_obs", C.c_int32), ("max_planes", C.c_int32),
+                ("max_imu_samples", C.c_int32), ("max_wheel_samples", C.c_int32), ("use_wheel", C.c_int32),
+                ("reserved_", C.c_int32 * 7)]
+
+
+class SolveOpts(C.Structure):
+    _fields_ = [("max_iterations", C.c_int32), ("const_mask", C.c_uint32), ("huber_delta", C.c_double),
+                ("sqrt_info_px", C.c_double), ("g_norm", C.c_double), ("lidar_sqrt_info", C.c_double),
+                ("max_time_s", C.c_double), ("initial_radius", C.c_double), ("function_tolerance", C.c_double),
+                ("gradient_tolerance", C.c_double), ("parameter_tolerance", C.c_double), ("reserved_", C.c_double * 6)]
+
+
+def default_opts(max_iterations=8, const_mask=CONST_ALL_CALIB, g_norm=9.7944, lidar_sqrt_info=31.622776601683793):
+    """NUM_ITERATIONS = 8, Huber(1.0), sqrt_info = FOCAL_LENGTH/1.5 = 400, g_norm of m3dgr.yaml:117,
+    lidar sqrt_info = sqrt(1/0.001) (LIO/liw/lio/lidarodom.cpp:10,13)."""
+    o = SolveOpts()
+    o.max_iterations = max_iterations
+    o.const_mask = const_mask
+    o.huber_delta = 1.0
+    o.sqrt_info_px = 400.0
+    o.g_norm = g_norm
+    o.lidar_sqrt_info = lidar_sqrt_info
+    return o
+
+
+SUMMARY = np.dtype([("initial_cost", "f8"), ("final_cost", "f8"), ("iterations", "i4"), ("successful_steps", "i4"),
+                    ("termination", "i4"), ("pad_", "i4")], align=True)
+
+
+class TrackerCfg(C.Structure):
+    _fields_ = [("device", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("max_pts", C.c_int32),
+                ("win", C.c_int32), ("max_level", C.c_int32), ("max_iters", C.c_int32), ("max_streams", C.c_int32),
+                ("eps", C.c_double), ("min_eig", C.c_double)]
+
+
+def ptr(a, ctype=C.c_void_p):
+    """pointer to a C-contiguous numpy array (or None)"""
+    if a is None:
+        return None
+    assert a.flags["C_CONTIGUOUS"], "array must be C-contiguous"
+    return a.ctypes.data_as(ctype)

@@ -1,0 +1,255 @@
+"""Synthetic sliding windows in the reference's packed wire layout.
+
+Pure numpy, deterministic (seed = 20250925 + config_id*1000 + window_id). Produces RAW sensor samples and
+observations; IMU/wheel preintegration records are made from them either by the product (device kernel, bench)
+or by the oracle (CPU tests) — this module contains no solver arithmetic.
+
+Camera: GF/config/realsense/color.yaml (fx 607.80, fy 607.84, cx 328.80, cy 245.53, 640x480, no distortion);
+extrinsic body_T_cam0 and IMU noise: GF/config/realsense/m3dgr.yaml:44-51,113-117; wheel noise :121-123.
+"""
+import numpy as np
+from . import abi
+
+FX, FY, CX, CY = 607.79772949218, 607.83526613281, 328.79772949218, 245.53321838378
+W_IMG, H_IMG = 640, 480
+BODY_T_CAM0 = np.array([[0.99957087, 0.00215313, 0.02921355, 0.03668114],
+                        [-0.00192891, 0.99996848, -0.00770122, -0.00477653],
+                        [-0.02922921, 0.00764156, 0.99954353, 0.0316039],
+                        [0., 0., 0., 1.]])
+ACC_N, GYR_N, ACC_W, GYR_W, G_NORM = 1.2374091609523514e-02, 3.0032654435730201e-03, 1.9218003442176448e-04, 5.4692100664858005e-05, 9.7944
+WHEEL_VEL_N, WHEEL_GYR_N = 0.01, 0.004
+BASE_SEED = 20250925
+
+
+def quat_from_R(R):
+    """Eigen Quaterniond(Matrix3d) — returns [x y z w]; batched over leading dims."""
+    R = np.asarray(R)
+    t = np.trace(R, axis1=-2, axis2=-1)
+    q = np.zeros(R.shape[:-2] + (4,))
+    flat_R = R.reshape(-1, 3, 3); flat_q = q.reshape(-1, 4); flat_t = np.atleast_1d(t).reshape(-1)
+    for n in range(flat_R.shape[0]):
+        m = flat_R[n]; tt = flat_t[n]
+        if tt > 0:
+            s = np.sqrt(tt + 1.0); w = 0.5 * s; s = 0.5 / s
+            flat_q[n] = [(m[2, 1] - m[1, 2]) * s, (m[0, 2] - m[2, 0]) * s, (m[1, 0] - m[0, 1]) * s, w]
+        else:
+            i = 0
+            if m[1, 1] > m[0, 0]: i = 1
+            if m[2, 2] > m[i, i]: i = 2
+            j = (i + 1) % 3; k = (j + 1) % 3
+            s = np.sqrt(m[i, i] - m[j, j] - m[k, k] + 1.0)
+            v = np.zeros(3); v[i] = 0.5 * s; s = 0.5 / s
+            w = (m[k, j] - m[j, k]) * s; v[j] = (m[j, i] + m[i, j]) * s; v[k] = (m[k, i] + m[i, k]) * s
+            flat_q[n] = [v[0], v[1], v[2], w]
+    return q
+
+
+def R_from_quat(q):
+    """[x y z w] -> rotation matrix (Eigen toRotationMatrix), batched."""
+    q = np.asarray(q); x, y, z, w = q[..., 0], q[..., 1], q[..., 2], q[..., 3]
+    R = np.empty(q.shape[:-1] + (3, 3))
+    R[..., 0, 0] = 1 - 2 * (y * y + z * z); R[..., 0, 1] = 2 * (x * y - z * w); R[..., 0, 2] = 2 * (x * z + y * w)
+    R[..., 1, 0] = 2 * (x * y + z * w); R[..., 1, 1] = 1 - 2 * (x * x + z * z); R[..., 1, 2] = 2 * (y * z - x * w)
+    R[..., 2, 0] = 2 * (x * z - y * w); R[..., 2, 1] = 2 * (y * z + x * w); R[..., 2, 2] = 1 - 2 * (x * x + y * y)
+    return R
+
+
+def so3_exp(v):
+    v = np.asarray(v); th = np.linalg.norm(v, axis=-1)[..., None, None]
+    K = np.zeros(v.shape[:-1] + (3, 3))
+    K[..., 0, 1] = -v[..., 2]; K[..., 0, 2] = v[..., 1]; K[..., 1, 0] = v[..., 2]
+    K[..., 1, 2] = -v[..., 0]; K[..., 2, 0] = -v[..., 1]; K[..., 2, 1] = v[..., 0]
+    th_safe = np.where(th < 1e-12, 1.0, th)
+    a = np.where(th < 1e-12, 1.0, np.sin(th_safe) / th_safe)
+    b = np.where(th < 1e-12, 0.5, (1 - np.cos(th_safe)) / th_safe ** 2)
+    return np.eye(3) + a * K + b * (K @ K)
+
+
+def _heading_R(psi):
+    """Body frame of a camera-like IMU: x right, y down, z forward; world z up. Columns = body axes in world."""
+    c, s = np.cos(psi), np.sin(psi)
+    R = np.zeros(np.shape(psi) + (3, 3))
+    R[..., 0, 0] = s; R[..., 1, 0] = -c          # right
+    R[..., 2, 1] = -1.0                          # down
+    R[..., 0, 2] = c; R[..., 1, 2] = s           # forward
+    return R
+
+
+def make_windows(n_windows, config_id=2, n_landmarks=1000, n_frames=11, wheel=False, n_planes=0, first_window=0,
+                 sorted_landmarks=True, prior="anchor", speed=1.0, yaw_rate=0.2, frame_dt=0.1, imu_hz=200, wheel_hz=50,
+                 pixel_noise=0.5, max_landmarks=None, max_obs=None):
+    """Return a dict of window-major arrays for `n_windows` windows (W10-F1000 when n_landmarks = 1000).
+
+    Landmark l starts in frame s_l = l mod 8 (track length n_frames - s_l, observed in every later frame). With
+    sorted_landmarks the table is ordered by start frame (the reference's f_manager.feature list order is
+    non-decreasing in start_frame because features are appended when first seen, feature_manager.cpp:67-88).
+    """
+    F = n_frames
+    L = n_landmarks
+    start = (np.arange(L) % 8).astype(np.int32)
+    if F < 11:
+        start = np.minimum(start, max(F - 4, 0)).astype(np.int32)
+    if sorted_landmarks:
+        start = np.sort(start, kind="stable")
+    tlen = (F - start).astype(np.int32)
+    n_obs = int(tlen.sum())
+    Lmax = max_landmarks or L
+    Omax = max_obs or n_obs
+    n_imu = int(round(frame_dt * imu_hz))
+    n_whl = int(round(frame_dt * wheel_hz))
+    Ric = BODY_T_CAM0[:3, :3]; tic = BODY_T_CAM0[:3, 3]
+    qic = quat_from_R(Ric)
+
+    out = {
+        "n_frames": F, "max_landmarks": Lmax, "max_obs": Omax, "n_imu_samples": n_imu, "n_wheel_samples": n_whl,
+        "para_pose": np.zeros((n_windows, F, 7)), "para_speedbias": np.zeros((n_windows, F, 9)),
+        "ex_pose": np.tile(np.concatenate([tic, qic]), (n_windows, 1)), "td": np.zeros(n_windows),
+        "n_landmarks": np.full(n_windows, L, np.int32), "inv_depth": np.zeros((n_windows, Lmax)),
+        "start_frame": np.zeros((n_windows, Lmax), np.int32), "track_len": np.zeros((n_windows, Lmax), np.int32),
+        "fixed": np.zeros((n_windows, Lmax), np.uint8), "obs": np.zeros((n_windows, Omax), abi.OBS),
+        "frame_td": np.zeros((n_windows, F)),
+        "imu_samples": np.zeros((n_windows, F - 1, n_imu), abi.IMU_SAMPLE), "imu_n": np.full((n_windows, F - 1), n_imu, np.int32),
+        "imu_first": np.zeros((n_windows, F - 1, 6)), "imu_lin_bias": np.zeros((n_windows, F - 1, 6)),
+        "imu_noise": np.array([ACC_N, GYR_N, ACC_W, GYR_W]),
+        "gt_pose": np.zeros((n_windows, F, 7)), "gt_speedbias": np.zeros((n_windows, F, 9)), "gt_inv_depth": np.zeros((n_windows, Lmax)),
+        "use_wheel": bool(wheel), "max_planes": int(n_planes),
+    }
+    out["start_frame"][:, :L] = start; out["track_len"][:, :L] = tlen
+    if wheel:
+        # wheel frame == body frame rotated so that wheel x is forward: body_T_wheel of m3dgr.yaml:66-76 is specific to
+        # that robot; the synthetic robot uses R_io mapping wheel (x fwd, y left, z up) into the body (x right, y down, z fwd)
+        Rio = np.array([[0., -1., 0.], [0., 0., -1.], [1., 0., 0.]]); tio = np.array([0.0, 0.05, -0.1])
+        out["ex_pose_wheel"] = np.tile(np.concatenate([tio, quat_from_R(Rio)]), (n_windows, 1))
+        out["sxsysw"] = np.ones((n_windows, 3)); out["td_wheel"] = np.zeros(n_windows)
+        out["wheel_samples"] = np.zeros((n_windows, F - 1, n_whl), abi.WHEEL_SAMPLE)
+        out["wheel_n"] = np.full((n_windows, F - 1), n_whl, np.int32)
+        out["wheel_first"] = np.zeros((n_windows, F - 1, 6)); out["wheel_lin"] = np.tile(np.array([1., 1., 1., 0.]), (n_windows, F - 1, 1))
+        out["wheel_noise"] = np.array([WHEEL_VEL_N, WHEEL_GYR_N])
+    if n_planes:
+        out["n_planes"] = np.full(n_windows, n_planes, np.int32)
+        out["planes"] = np.zeros((n_windows, n_planes), abi.PLANE)
+    P = abi.MAX_PRIOR_DIM
+    out["prior_rows"] = np.zeros(n_windows, np.int32); out["prior_nblocks"] = np.zeros(n_windows, np.int32)
+    out["prior_J0"] = np.zeros((n_windows, P, P)); out["prior_r0"] = np.zeros((n_windows, P))
+    out["prior_blocks"] = np.zeros((n_windows, 2 * F + 8), abi.PRIOR_BLOCK)
+
+    obs_begin = np.concatenate([[0], np.cumsum(tlen)[:-1]])
+    lm_of_obs = np.repeat(np.arange(L), tlen)
+    k_of_obs = np.arange(n_obs) - obs_begin[lm_of_obs]
+    for wi in range(n_windows):
+        rng = np.random.Generator(np.random.PCG64(BASE_SEED + config_id * 1000 + first_window + wi))
+        psi0 = rng.uniform(-np.pi, np.pi)
+        p0 = rng.uniform(-5, 5, 3); p0[2] = rng.uniform(0.2, 0.6)
+        ba = np.array([0.02, -0.01, 0.015]) * rng.uniform(0.5, 1.5); bg = np.array([0.002, -0.001, 0.0015]) * rng.uniform(0.5, 1.5)
+        # --- ground-truth trajectory at IMU rate, frames every n_imu samples; one extra frame before frame 0 for velocities
+        dt = 1.0 / imu_hz
+        t_imu = np.arange(-n_imu, (F - 1) * n_imu + 1) * dt
+        psi = psi0 + yaw_rate * t_imu
+        if abs(yaw_rate) > 1e-12:
+            px = p0[0] + speed / yaw_rate * (np.sin(psi) - np.sin(psi0)); py = p0[1] - speed / yaw_rate * (np.cos(psi) - np.cos(psi0))
+        else:
+            px = p0[0] + speed * np.cos(psi0) * t_imu; py = p0[1] + speed * np.sin(psi0) * t_imu
+        pos = np.stack([px, py, np.full_like(px, p0[2])], -1)
+        vel = np.stack([speed * np.cos(psi), speed * np.sin(psi), np.zeros_like(psi)], -1)
+        acc_w = np.stack([-speed * yaw_rate * np.sin(psi), speed * yaw_rate * np.cos(psi), np.zeros_like(psi)], -1)
+        Rwb = _heading_R(psi)
+        acc_b = np.einsum("nji,nj->ni", Rwb, acc_w + np.array([0, 0, G_NORM])) + ba + rng.normal(0, ACC_N, acc_w.shape)
+        gyr_b = np.tile(np.array([0.0, -yaw_rate, 0.0]), (len(psi), 1)) + bg + rng.normal(0, GYR_N, acc_w.shape)
+        fidx = n_imu + np.arange(F) * n_imu  # index of frame k in the IMU timeline
+        for k in range(F - 1):
+            s0 = fidx[k]
+            smp = out["imu_samples"][wi, k]
+            smp["dt"] = dt; smp["acc"] = acc_b[s0 + 1:s0 + 1 + n_imu]; smp["gyr"] = gyr_b[s0 + 1:s0 + 1 + n_imu]
+            out["imu_first"][wi, k, :3] = acc_b[s0]; out["imu_first"][wi, k, 3:] = gyr_b[s0]
+        gtR = Rwb[fidx]; gtp = pos[fidx]; gtv = vel[fidx]
+        out["gt_pose"][wi, :, :3] = gtp; out["gt_pose"][wi, :, 3:] = quat_from_R(gtR)
+        out["gt_speedbias"][wi, :, :3] = gtv; out["gt_speedbias"][wi, :, 3:6] = ba; out["gt_speedbias"][wi, :, 6:] = bg
+        # camera poses for frames -1..F-1 (frame -1 only for the velocity of frame-0 observations)
+        fall = np.concatenate([[0], fidx])
+        Rwc = Rwb[fall] @ Ric; twc = pos[fall] + np.einsum("nij,j->ni", Rwb[fall], tic)
+        # --- landmarks: uniform pixel x depth in the host camera frustum, visible in every frame of the track
+        Xw = np.zeros((L, 3)); need = np.arange(L)
+        for _ in range(200):
+            if len(need) == 0: break
+            u = rng.uniform(20, W_IMG - 20, len(need)); v = rng.uniform(20, H_IMG - 20, len(need)); d = rng.uniform(3.0, 15.0, len(need))
+            pc = np.stack([(u - CX) / FX * d, (v - CY) / FY * d, d], -1)
+            s = start[need] + 1
+            cand = np.einsum("nij,nj->ni", Rwc[s], pc) + twc[s]
+            ok = np.ones(len(need), bool)
+            for f in range(1, F + 1):
+                pcf = np.einsum("ji,nj->ni", Rwc[f], cand - twc[f])
+                uu = FX * pcf[:, 0] / pcf[:, 2] + CX; vv = FY * pcf[:, 1] / pcf[:, 2] + CY
+                vis = (pcf[:, 2] > 0.5) & (uu > 2) & (uu < W_IMG - 2) & (vv > 2) & (vv < H_IMG - 2)
+                ok &= vis | (f < s)
+            Xw[need[ok]] = cand[ok]; need = need[~ok]
+        assert len(need) == 0, "landmark sampling failed"
+        # --- observations (normalised plane) in every frame incl. the pre-window frame, + pixel noise, fp32
+        pcs = np.einsum("fji,flj->fli", Rwc, Xw[None] - twc[:, None])          # [F+1][L][3]
+        xn = pcs[..., :2] / pcs[..., 2:3]
+        xn = xn + rng.normal(0, pixel_noise, xn.shape) / np.array([FX, FY])
+        xn32 = xn.astype(np.float32)
+        o = out["obs"][wi]
+        fr = start[lm_of_obs] + k_of_obs
+        cur = xn32[fr + 1, lm_of_obs]; prv = xn32[fr, lm_of_obs]
+        vel32 = np.where((k_of_obs > 0)[:, None], (cur - prv) / np.float32(frame_dt), np.float32(0)).astype(np.float32)
+        o["x"][:n_obs] = cur[:, 0]; o["y"][:n_obs] = cur[:, 1]   # new points get velocity 0 (feature_tracker.cpp:840-846)
+        o["vx"][:n_obs] = vel32[:, 0]; o["vy"][:n_obs] = vel32[:, 1]
+        true_depth = pcs[start + 1, np.arange(L), 2]
+        out["gt_inv_depth"][wi, :L] = 1.0 / true_depth
+        out["inv_depth"][wi, :L] = (1.0 / true_depth) * (1.0 + rng.normal(0, 0.1, L))
+        # --- initial states: ground truth perturbed (5 cm, 1 deg, 0.05 m/s); biases start at 0 = linearisation point
+        dR = so3_exp(rng.normal(0, np.deg2rad(1.0), (F, 3)))
+        out["para_pose"][wi, :, :3] = gtp + rng.normal(0, 0.05, (F, 3))
+        out["para_pose"][wi, :, 3:] = quat_from_R(gtR @ dR)
+        out["para_speedbias"][wi, :, :3] = gtv + rng.normal(0, 0.05, (F, 3))
+        # --- wheel odometry samples (wheel frame velocity along wheel x, yaw rate about wheel z)
+        if wheel:
+            n_sub = imu_hz // wheel_hz
+            for k in range(F - 1):
+                s0 = fidx[k]
+                ws = out["wheel_samples"][wi, k]
+                ws["dt"] = 1.0 / wheel_hz
+                vel_o = np.zeros((n_whl + 1, 3)); vel_o[:, 0] = speed; gyr_o = np.zeros((n_whl + 1, 3)); gyr_o[:, 2] = yaw_rate
+                vel_o += rng.normal(0, WHEEL_VEL_N, vel_o.shape); gyr_o += rng.normal(0, WHEEL_GYR_N, gyr_o.shape)
+                ws["vel"] = vel_o[1:]; ws["gyr"] = gyr_o[1:]
+                out["wheel_first"][wi, k, :3] = vel_o[0]; out["wheel_first"][wi, k, 3:] = gyr_o[0]
+        # --- LiDAR plane factors: points on 6 random planes seen from each frame 1..F-1 (config 4)
+        if n_planes:
+            per = n_planes // (F - 1)
+            pl = out["planes"][wi]
+            nrm = rng.normal(0, 1, (6, 3)); nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+            off = -np.einsum("ij,ij->i", nrm, gtp.mean(0) + nrm * rng.uniform(3, 10, (6, 1)))  # plane through a point 3..10 m away
+            idx = 0
+            for f in range(1, F):
+                cnt = per if f < F - 1 else n_planes - per * (F - 2)
+                which = rng.integers(0, 6, cnt)
+                # random world points, projected onto their plane, + 2 cm noise along the normal, into the body frame
+                pw = gtp[f] + rng.uniform(-8, 8, (cnt, 3))
+                dist = np.einsum("ij,ij->i", nrm[which], pw) + off[which]
+                pw = pw - dist[:, None] * nrm[which] + rng.normal(0, 0.02, (cnt, 1)) * nrm[which]
+                pb = np.einsum("ji,nj->ni", gtR[f], pw - gtp[f])
+                pl["p_body"][idx:idx + cnt] = pb; pl["normal"][idx:idx + cnt] = nrm[which]; pl["offset"][idx:idx + cnt] = off[which]
+                pl["weight"][idx:idx + cnt] = 1.0; pl["frame"][idx:idx + cnt] = f
+                idx += cnt
+        # --- prior
+        if prior == "anchor":  # identity-information anchor on frame 0's pose (6 rows), SURVEY 8(d) config 2
+            out["prior_rows"][wi] = 6; out["prior_nblocks"][wi] = 1
+            out["prior_J0"][wi, :6, :6] = np.eye(6)
+            blk = out["prior_blocks"][wi, 0]
+            blk["kind"] = abi.BLK_POSE; blk["index"] = 0; blk["offset"] = 0; blk["x0"][:7] = out["para_pose"][wi, 0]
+        elif prior == "dense":  # marginalization-shaped prior over poses 0..F-2 and speed-bias 0 (n = 6(F-1)+9)
+            n = 6 * (F - 1) + 9
+            A = rng.normal(0, 1, (n, n)) * 0.3 + np.diag(rng.uniform(5, 50, n))
+            out["prior_rows"][wi] = n; out["prior_nblocks"][wi] = F
+            out["prior_J0"][wi, :n, :n] = np.triu(A)
+            out["prior_r0"][wi, :n] = rng.normal(0, 0.05, n)
+            off_c = 0
+            for b in range(F - 1):
+                blk = out["prior_blocks"][wi, b]
+                blk["kind"] = abi.BLK_POSE; blk["index"] = b; blk["offset"] = off_c; blk["x0"][:7] = out["para_pose"][wi, b]
+                off_c += 6
+                if b == 0:
+                    blk = out["prior_blocks"][wi, F - 1]
+                    blk["kind"] = abi.BLK_SPEEDBIAS; blk["index"] = 0; blk["offset"] = 6 * (F - 1); blk["x0"][:9] = out["para_speedbias"][wi, 0]
+            # keep block list ordered: poses first then speed-bias (any order is valid)
+    return out

@@ -1,0 +1,334 @@
+/*
+ * gf2_abi.h — C ABI of the B200-native sliding-window solver and KLT tracker that replace
+ * the arithmetic of Ground-Fusion++'s Estimator::optimization() and
+ * FeatureTracker::trackImage().
+ *
+ * Citations use the abbreviations of SURVEY.md:
+ *   VE/  = Ground-Fusion++/vins_estimator/src/      LIO/ = Ground-Fusion++/lio/src/
+ *
+ * What this boundary replaces (the reference has no FFI; its "plug-in" interface is the
+ * ceres::CostFunction::Evaluate API driven by ceres::Solve):
+ *   - gf2_solver_*  : the ceres::Problem build + ceres::Solve call of
+ *                     Estimator::optimization()            VE/estimator/estimator.cpp:2951-3392
+ *   - gf2_set_*     : the wire layout of vector2double()   VE/estimator/estimator.cpp:2337-2414
+ *   - gf2_get_*     : the inverse, double2vector()'s input VE/estimator/estimator.cpp:2501-2630
+ *   - gf2_imu_preintegrate / gf2_wheel_preintegrate :
+ *                     IntegrationBase::push_back chain     VE/factor/integration_base.h:39-167
+ *                     WheelIntegrationBase::push_back      VE/factor/wheel_integration_base.h:41-178
+ *   - gf2_marginalize: MarginalizationInfo::preMarginalize/marginalize
+ *                                                          VE/factor/marginalization_factor.cpp:119-308
+ *   - gf2_tracker_* : cv::calcOpticalFlowPyrLK call sites  VE/featureTracker/feature_tracker.cpp:122,132,135,141
+ *
+ * Conventions: plain C, opaque handles, caller-owned HOST buffers, int status (0 = OK,
+ * negative = error), no exceptions cross the boundary, gf2_last_error() returns the message
+ * of the last failure on the calling thread. Calls are thread-safe per handle, not across
+ * handles sharing one. Every quaternion is stored [x y z w] (Eigen coeffs order, the order of
+ * para_Pose[i][3..6], VE/estimator/estimator.cpp:2345-2348). Every matrix is row-major unless
+ * stated. All batched arrays are window-major: element (w, ...) lives at w * stride + ....
+ *
+ * There is NO CPU fallback behind this ABI: every entry point that computes runs CUDA kernels
+ * on the handle's device and fails with GF2_ERR_CUDA if no device is usable.
+ */
+#ifndef GF2_ABI_H_
+#define GF2_ABI_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GF2_ABI_VERSION 1
+
+/* WINDOW_SIZE + 1 and NUM_OF_F of VE/estimator/parameters.h:24-25 */
+#define GF2_MAX_FRAMES 11
+#define GF2_MAX_LANDMARKS 1000
+#define GF2_MAX_PRIOR_DIM 96
+
+enum {
+  GF2_OK = 0,
+  GF2_ERR_INVALID = -1,     /* bad argument / out of capacity */
+  GF2_ERR_CUDA = -2,        /* CUDA runtime failure or no device */
+  GF2_ERR_UNSUPPORTED = -3, /* feature named by the ABI but not built yet */
+  GF2_ERR_NCCL = -4
+};
+
+/* ---------------------------------------------------------------- records */
+
+/* One feature observation. The reference stores cv::Point2f values widened to double
+ * (VE/featureTracker/feature_tracker.cpp:326-339; FeaturePerFrame VE/estimator/feature_manager.h:33-43):
+ * x,y = undistorted normalised image point (z = 1 implied), vx,vy = its velocity. fp32 is lossless. */
+typedef struct gf2_obs {
+  float x, y, vx, vy;
+} gf2_obs;
+
+/* One raw IMU sample fed to IntegrationBase::push_back (VE/factor/integration_base.h:39). */
+typedef struct gf2_imu_sample {
+  double dt;
+  double acc[3];
+  double gyr[3];
+} gf2_imu_sample;
+
+/* State of an IntegrationBase after its last push_back (members at
+ * VE/factor/integration_base.h:197-217). jacobian/covariance are 15x15 row-major in the order
+ * O_P=0, O_R=3, O_V=6, O_BA=9, O_BG=12 (VE/estimator/parameters.h enum StateOrder). */
+typedef struct gf2_imu_preint {
+  double sum_dt;
+  double delta_p[3];
+  double delta_q[4]; /* x y z w */
+  double delta_v[3];
+  double lin_ba[3];
+  double lin_bg[3];
+  double jacobian[225];
+  double covariance[225];
+  int32_t valid; /* 0: factor skipped (the reference skips sum_dt > 10, estimator.cpp:3175) */
+  int32_t pad_;
+} gf2_imu_preint;
+
+/* One raw wheel-odometry sample fed to WheelIntegrationBase::push_back
+ * (VE/factor/wheel_integration_base.h:41). */
+typedef struct gf2_wheel_sample {
+  double dt;
+  double vel[3];
+  double gyr[3];
+} gf2_wheel_sample;
+
+/* State of a WheelIntegrationBase (members at VE/factor/wheel_integration_base.h:221-244).
+ * jacobian is 6x3 row-major (rows O_P=0..2, O_R=3..5; cols sx, sy, sw); covariance 6x6. */
+typedef struct gf2_wheel_preint {
+  double sum_dt;
+  double delta_p[3];
+  double delta_q[4]; /* x y z w */
+  double lin_sx, lin_sy, lin_sw, lin_td;
+  double lin_vel[3], lin_gyr[3]; /* linearized_vel / linearized_gyr: first sample of the interval */
+  double vel_1[3], gyr_1[3];     /* last sample of the interval */
+  double jacobian[18];
+  double covariance[36];
+  int32_t valid;
+  int32_t pad_;
+} gf2_wheel_preint;
+
+/* One LiDAR point-to-plane factor, LidarPlaneNormFactor (LIO/liw/lidarFactor.cpp:13-50), attached
+ * to the window pose of `frame` (synthetic composition of BASELINE.json config 4).
+ * residual = sqrt_info * weight * (normal . (R p_body + t) + offset). */
+typedef struct gf2_plane {
+  double p_body[3];
+  double normal[3];
+  double offset;
+  double weight;
+  int32_t frame;
+  int32_t pad_;
+} gf2_plane;
+
+/* Parameter-block kinds a marginalization prior can keep
+ * (last_marginalization_parameter_blocks, VE/estimator/estimator.cpp:3561-3595). */
+enum {
+  GF2_BLK_POSE = 0,      /* para_Pose[index]        size 7 / local 6 */
+  GF2_BLK_SPEEDBIAS = 1, /* para_SpeedBias[index]   size 9 */
+  GF2_BLK_EX_POSE = 2,   /* para_Ex_Pose[0]         size 7 / local 6 */
+  GF2_BLK_TD = 3,        /* para_Td[0]              size 1 */
+  GF2_BLK_EX_WHEEL = 4,  /* para_Ex_Pose_wheel[0]   size 7 / local 6 */
+  GF2_BLK_SX = 5,
+  GF2_BLK_SY = 6,
+  GF2_BLK_SW = 7,
+  GF2_BLK_TD_WHEEL = 8
+};
+
+/* One kept block of a MarginalizationInfo: keep_block_size / keep_block_idx / keep_block_data
+ * (VE/factor/marginalization_factor.h:74-76). `offset` = keep_block_idx - m. */
+typedef struct gf2_prior_block {
+  int32_t kind;
+  int32_t index;  /* frame index for POSE / SPEEDBIAS, else 0 */
+  int32_t offset; /* first column of this block in linearized_jacobians */
+  int32_t pad_;
+  double x0[9]; /* linearisation point, global size (7, 9 or 1 used) */
+} gf2_prior_block;
+
+/* Bits of gf2_solve_opts.const_mask: blocks held constant by SetParameterBlockConstant
+ * (VE/estimator/estimator.cpp:3051-3060, 3093-3117, 3158-3161). Frame poses and speed-biases are
+ * always free (the "stationary" freeze at :3294-3307 makes the solve a no-op; callers skip it). */
+enum {
+  GF2_CONST_EX_POSE = 1,
+  GF2_CONST_TD = 2,
+  GF2_CONST_EX_WHEEL = 4,
+  GF2_CONST_WHEEL_INTRINSIC = 8, /* sx, sy, sw together, as the reference does */
+  GF2_CONST_TD_WHEEL = 16
+};
+
+typedef struct gf2_solver gf2_solver;
+
+typedef struct gf2_solver_cfg {
+  int32_t device;        /* CUDA device ordinal */
+  int32_t max_windows;   /* batch capacity B */
+  int32_t n_frames;      /* frame_count + 1, <= GF2_MAX_FRAMES */
+  int32_t max_landmarks; /* per window, <= GF2_MAX_LANDMARKS */
+  int32_t max_obs;       /* per window: sum over landmarks of track length (host obs included) */
+  int32_t max_planes;    /* per window LiDAR plane factors (0 = none) */
+  int32_t max_imu_samples;   /* per interval, for gf2_imu_preintegrate (0 = records only) */
+  int32_t max_wheel_samples; /* per interval */
+  int32_t use_wheel;     /* allocate wheel factor storage */
+  int32_t reserved_[7];
+} gf2_solver_cfg;
+
+/* Options of one solve = the ceres::Solver::Options the reference sets (estimator.cpp:3364-3376)
+ * plus the static members it configures elsewhere. */
+typedef struct gf2_solve_opts {
+  int32_t max_iterations;  /* NUM_ITERATIONS; Ceres counts attempted steps */
+  uint32_t const_mask;     /* GF2_CONST_* */
+  double huber_delta;      /* HuberLoss(1.0), estimator.cpp:2959 */
+  double sqrt_info_px;     /* ProjectionTwoFrameOneCamFactor::sqrt_info = FOCAL_LENGTH/1.5 * I (estimator.cpp:193) */
+  double g_norm;           /* G = (0,0,g_norm), parameters.cpp:223 */
+  double lidar_sqrt_info;  /* LidarPlaneNormFactor::sqrt_info = sqrt(1/laser_point_cov) (lidarodom.cpp:10,13) */
+  double max_time_s;       /* must be 0: the wall-clock cap is machine dependent and is NOT reproduced */
+  /* Ceres 1.14 trust-region defaults; 0 selects the default */
+  double initial_radius;       /* 1e4 */
+  double function_tolerance;   /* 1e-6 */
+  double gradient_tolerance;   /* 1e-10 */
+  double parameter_tolerance;  /* 1e-8 */
+  double reserved_[6];
+} gf2_solve_opts;
+
+enum { /* gf2_solve_summary.termination */
+  GF2_TERM_NO_CONVERGENCE = 0, /* iteration budget exhausted */
+  GF2_TERM_FUNCTION_TOL = 1,
+  GF2_TERM_GRADIENT_TOL = 2,
+  GF2_TERM_PARAMETER_TOL = 3,
+  GF2_TERM_MIN_RADIUS = 4,
+  GF2_TERM_FAILURE = 5
+};
+
+typedef struct gf2_solve_summary {
+  double initial_cost;
+  double final_cost;
+  int32_t iterations;       /* attempted trust-region steps */
+  int32_t successful_steps;
+  int32_t termination;
+  int32_t pad_;
+} gf2_solve_summary;
+
+/* ---------------------------------------------------------------- solver */
+
+const char* gf2_last_error(void);
+int gf2_abi_version(void);
+/* number of usable CUDA devices (0 on a CPU-only box); never fails */
+int gf2_device_count(void);
+
+int gf2_solver_create(const gf2_solver_cfg* cfg, gf2_solver** out);
+void gf2_solver_destroy(gf2_solver* h);
+
+/* Packed states of windows [first, first+n): para_Pose [n][F][7], para_SpeedBias [n][F][9],
+ * para_Ex_Pose[0] [n][7], para_Td [n], and (wheel) para_Ex_Pose_wheel [n][7], sx/sy/sw [n][3],
+ * para_Td_wheel [n]. Wheel pointers may be NULL when the solver was created with use_wheel = 0. */
+int gf2_set_states(gf2_solver* h, int first, int n, const double* para_pose, const double* para_speedbias,
+                   const double* ex_pose, const double* td, const double* ex_pose_wheel,
+                   const double* sxsysw, const double* td_wheel);
+
+/* Landmark table in f_manager.feature list order restricted to used_num >= 4
+ * (getDepthVector order, VE/estimator/feature_manager.cpp:286-302):
+ *   n_landmarks [n]; inv_depth [n][max_landmarks] (para_Feature); start_frame [n][max_landmarks];
+ *   track_len [n][max_landmarks] (feature_per_frame.size(), >= 2 here; the reference requires >= 4);
+ *   fixed [n][max_landmarks] (estimate_flag == 1 -> SetParameterBlockConstant, estimator.cpp:3352).
+ * Observations [n][max_obs], landmark-major: landmark l owns records obs_begin(l) .. +track_len(l),
+ * obs_begin = exclusive prefix sum of track_len; record k is the observation in frame
+ * start_frame + k (k = 0 is the host observation pts_i). frame_td [n][F] is cur_td of the frame
+ * (FeaturePerFrame::cur_td, VE/estimator/feature_manager.cpp:69). */
+int gf2_set_landmarks(gf2_solver* h, int first, int n, const int32_t* n_landmarks, const double* inv_depth,
+                      const int32_t* start_frame, const int32_t* track_len, const uint8_t* fixed,
+                      const gf2_obs* obs, const double* frame_td);
+
+/* IMU factors: record k of a window links frames k and k+1 ([n][F-1]). */
+int gf2_set_imu(gf2_solver* h, int first, int n, const gf2_imu_preint* preint);
+/* Same from raw samples, preintegrated on the device: samples [n][F-1][max_imu_samples],
+ * n_samples [n][F-1], first sample acc_0/gyr_0 [n][F-1][6] (acc then gyr), linearisation biases
+ * lin_bias [n][F-1][6] (ba then bg), noise = {ACC_N, GYR_N, ACC_W, GYR_W}. */
+int gf2_imu_preintegrate(gf2_solver* h, int first, int n, const gf2_imu_sample* samples,
+                         const int32_t* n_samples, const double* first_sample, const double* lin_bias,
+                         const double noise[4]);
+/* Read back the device-side preintegration records ([n][F-1]). */
+int gf2_get_imu(gf2_solver* h, int first, int n, gf2_imu_preint* preint);
+
+int gf2_set_wheel(gf2_solver* h, int first, int n, const gf2_wheel_preint* preint);
+
+/* Marginalization prior per window: n_rows [n] (0 = no prior), J0 [n][P][P] with
+ * P = GF2_MAX_PRIOR_DIM (row r, column c at r*P + c; rows/cols >= n_rows ignored),
+ * r0 [n][P], n_blocks [n], blocks [n][2*F+8]. */
+int gf2_set_prior(gf2_solver* h, int first, int n, const int32_t* n_rows, const double* J0, const double* r0,
+                  const int32_t* n_blocks, const gf2_prior_block* blocks);
+
+/* LiDAR plane factors: n_planes [n], planes [n][max_planes] sorted or not by frame. */
+int gf2_set_planes(gf2_solver* h, int first, int n, const int32_t* n_planes, const gf2_plane* planes);
+
+/* Solve windows [first, first+n) (ceres::Solve with DENSE_SCHUR + traditional DOGLEG semantics).
+ * Synchronous. summaries may be NULL. */
+int gf2_solve(gf2_solver* h, int first, int n, const gf2_solve_opts* opts, gf2_solve_summary* summaries);
+
+/* One linearisation only (residuals, Jacobians, Schur): fills the reduced system of each window.
+ * Used by parity tests and by the roofline measurement. reduced_dim = gf2_reduced_dim(). */
+int gf2_linearize(gf2_solver* h, int first, int n, const gf2_solve_opts* opts);
+int gf2_reduced_dim(gf2_solver* h, const gf2_solve_opts* opts);
+/* Reduced camera system of the last linearisation: S [n][D][D] (full symmetric, row-major, WITHOUT
+ * the mu*diag regularisation), g [n][D] (reduced gradient J^T r after eliminating landmarks),
+ * cost [n] = 0.5 * sum rho(|r|^2). Tangent order: per frame [pose 6 | speed-bias 9], then the free
+ * blocks among ex-pose 6, td 1, ex-wheel 6, sx sy sw 3, td-wheel 1. */
+int gf2_get_reduced_system(gf2_solver* h, int first, int n, double* S, double* g, double* cost);
+
+int gf2_get_states(gf2_solver* h, int first, int n, double* para_pose, double* para_speedbias, double* ex_pose,
+                   double* td, double* ex_pose_wheel, double* sxsysw, double* td_wheel);
+int gf2_get_landmarks(gf2_solver* h, int first, int n, double* inv_depth);
+
+/* Multi-GPU, factor-sharded mode: every rank holds the same windows' states, a
+ * disjoint subset of the landmarks/planes; the reduced system is summed with one ncclAllReduce per
+ * linearisation. nccl_unique_id points at an ncclUniqueId (128 bytes) produced by rank 0. */
+int gf2_comm_init(gf2_solver* h, int rank, int nranks, const void* nccl_unique_id);
+int gf2_comm_unique_id(void* out_128_bytes);
+
+/* Device-time of the phases of the last gf2_solve / gf2_linearize on this handle, in milliseconds,
+ * measured with CUDA events on the handle's stream: [0] total, [1] linearise kernels (sum),
+ * [2] reduced solve kernels, [3] back-substitution + candidate evaluation kernels, [4] number of
+ * kernel launches, [5] number of linearise launches. */
+int gf2_last_timing(gf2_solver* h, double out[8]);
+
+/* ---------------------------------------------------------------- tracker */
+
+typedef struct gf2_tracker gf2_tracker;
+
+typedef struct gf2_tracker_cfg {
+  int32_t device;
+  int32_t width, height; /* COL, ROW */
+  int32_t max_pts;       /* MAX_CNT upper bound */
+  int32_t win;           /* 21 */
+  int32_t max_level;     /* capacity: 3 */
+  int32_t max_iters;     /* 30 */
+  int32_t max_streams;   /* independent image streams tracked per call (batch), >= 1 */
+  double eps;            /* 0.01 */
+  double min_eig;        /* 1e-4 */
+} gf2_tracker_cfg;
+
+enum { GF2_LK_USE_INITIAL_FLOW = 4 /* cv::OPTFLOW_USE_INITIAL_FLOW */ };
+
+int gf2_tracker_create(const gf2_tracker_cfg* cfg, gf2_tracker** out);
+void gf2_tracker_destroy(gf2_tracker* h);
+
+/* cv::calcOpticalFlowPyrLK(prev, cur, prev_pts, cur_pts, status, err, Size(win,win), max_level,
+ * TermCriteria(COUNT+EPS, max_iters, eps), flags, min_eig) for `n_streams` independent image pairs.
+ * prev/cur: [n_streams] images of height*stride bytes (u8); prev may be NULL to reuse the pyramid
+ * kept from the previous call's `cur` of the same stream (the reference's prev_img = cur_img,
+ * feature_tracker.cpp:307). pts: [n_streams][max_pts][2] float; n_pts [n_streams]. */
+int gf2_tracker_track(gf2_tracker* h, int n_streams, const uint8_t* prev, const uint8_t* cur, size_t stride,
+                      const int32_t* n_pts, const float* prev_pts, float* cur_pts, uint8_t* status, float* err,
+                      int flags, int max_level);
+
+/* The forward + backward check of trackImage (feature_tracker.cpp:135-153) fused: forward LK at
+ * max_level, reverse LK at level 1 with initial flow, status &= (reverse ok && round trip <= 0.5 px).
+ * Outputs cur_pts and the combined status. */
+int gf2_tracker_track_fb(gf2_tracker* h, int n_streams, const uint8_t* prev, const uint8_t* cur, size_t stride,
+                         const int32_t* n_pts, const float* prev_pts, float* cur_pts, uint8_t* status,
+                         int max_level);
+
+int gf2_tracker_last_timing(gf2_tracker* h, double out[8]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GF2_ABI_H_ */

@@ -1,0 +1,148 @@
+"""TEST INFRASTRUCTURE — ctypes binding of oracle/_build/libgf2_oracle.so (the CPU restatement of the reference
+path). Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this."""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "_build", "libgf2_oracle.so")
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", HERE])
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        build()
+    return C.CDLL(LIB_PATH)
+
+
+lib = _load()
+
+
+class Window(C.Structure):
+    _fields_ = [("n_frames", C.c_int32), ("n_landmarks", C.c_int32), ("n_planes", C.c_int32), ("prior_rows", C.c_int32),
+                ("prior_nblocks", C.c_int32), ("use_wheel", C.c_int32)] + [(n, C.c_void_p) for n in (
+                    "para_pose", "para_speedbias", "ex_pose", "td", "ex_pose_wheel", "sxsysw", "td_wheel", "inv_depth",
+                    "start_frame", "track_len", "fixed", "obs", "frame_td", "imu", "wheel", "prior_J0", "prior_r0",
+                    "prior_blocks", "planes")]
+
+
+class Batch(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("n_windows", "n_frames", "max_landmarks", "max_obs", "max_planes", "use_wheel")] + \
+               [(n, C.c_void_p) for n in ("para_pose", "para_speedbias", "ex_pose", "td", "ex_pose_wheel", "sxsysw", "td_wheel",
+                                          "inv_depth", "n_landmarks", "start_frame", "track_len", "fixed", "obs", "frame_td",
+                                          "imu", "wheel", "prior_rows", "prior_J0", "prior_r0", "prior_nblocks", "prior_blocks",
+                                          "n_planes", "planes")]
+
+
+assert lib.gf2o_sizeof(4) == C.sizeof(Window) and lib.gf2o_sizeof(5) == C.sizeof(Batch)
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def make_batch(w, keep):
+    """Batch struct over the arrays of a synth window dict `w` (arrays must stay alive: stored in `keep`)."""
+    b = Batch()
+    n = w["para_pose"].shape[0]
+    b.n_windows = n; b.n_frames = w["n_frames"]; b.max_landmarks = w["max_landmarks"]; b.max_obs = w["max_obs"]
+    b.max_planes = w.get("max_planes", 0); b.use_wheel = 1 if w.get("use_wheel") else 0
+    for name in ("para_pose", "para_speedbias", "ex_pose", "td", "ex_pose_wheel", "sxsysw", "td_wheel", "inv_depth",
+                 "n_landmarks", "start_frame", "track_len", "fixed", "obs", "frame_td", "imu", "wheel", "prior_rows",
+                 "prior_J0", "prior_r0", "prior_nblocks", "prior_blocks", "n_planes", "planes"):
+        a = w.get(name)
+        if a is not None:
+            a = np.ascontiguousarray(a); w[name] = a; keep.append(a)
+        setattr(b, name, _p(a))
+    return b
+
+
+def solve_batch(w, opts, n_threads=1):
+    """Solve every window of `w` in place (states, inverse depths); returns the summaries array."""
+    from gf2_loader import load
+    abi = load().abi
+    keep = []
+    b = make_batch(w, keep)
+    n = b.n_windows
+    summ = np.zeros(n, abi.SUMMARY)
+    lib.gf2o_solve_batch(C.byref(b), C.byref(opts), _p(summ), int(n_threads))
+    return summ
+
+
+def solve_window_trace(w, i, opts):
+    from gf2_loader import load
+    abi = load().abi
+    keep = []
+    b = make_batch(w, keep)
+    win = Window()
+    lib.gf2o_batch_window(C.byref(b), int(i), C.byref(win))
+    summ = np.zeros(1, abi.SUMMARY)
+    trace = np.zeros((opts.max_iterations, 6))
+    lib.gf2o_solve_window(C.byref(win), C.byref(opts), _p(summ), _p(trace))
+    return summ[0], trace
+
+
+def linearize_window(w, i, opts, max_dim=256):
+    keep = []
+    b = make_batch(w, keep)
+    win = Window()
+    lib.gf2o_batch_window(C.byref(b), int(i), C.byref(win))
+    S = np.zeros((max_dim, max_dim)); g = np.zeros(max_dim); cost = C.c_double(0)
+    L = int(w["n_landmarks"][i])
+    ete = np.zeros(L + 1); etr = np.zeros(L + 1)
+    D = lib.gf2o_linearize_window(C.byref(win), C.byref(opts), max_dim, _p(S), _p(g), C.byref(cost), _p(ete), _p(etr))
+    assert D > 0
+    S = S.reshape(-1)[:D * D].reshape(D, D).copy()
+    return S, g[:D].copy(), cost.value, ete, etr
+
+
+def factor_eval(kind, consts, params, extra=None, want_jac=True):
+    sizes = {0: (2, [7, 7, 7, 1, 1]), 1: (15, [7, 9, 7, 9]), 2: (6, [7, 7, 7, 1, 1, 1, 1]), 3: (1, [3, 4]), 4: (1, [3, 4, 3, 4]), 5: (1, [7])}[kind]
+    nres, blocks = sizes
+    params = np.ascontiguousarray(params, dtype=np.float64)
+    assert params.size == sum(blocks)
+    res = np.zeros(nres); jac = np.zeros(nres * sum(blocks))
+    consts = np.ascontiguousarray(consts)
+    ex = np.ascontiguousarray(extra if extra is not None else [0.0], dtype=np.float64)
+    lib.gf2o_factor_eval(int(kind), _p(consts), _p(ex), _p(params), _p(res), _p(jac) if want_jac else None)
+    out = []; o = 0
+    for s in blocks:
+        out.append(jac[o:o + nres * s].reshape(nres, s).copy()); o += nres * s
+    return res, out
+
+
+def imu_preintegrate(w):
+    """Fill w['imu'] ([n][F-1] IMU_PREINT) from the raw samples with the restated IntegrationBase."""
+    from gf2_loader import load
+    abi = load().abi
+    n, Fm1 = w["imu_n"].shape
+    rec = np.zeros((n, Fm1), abi.IMU_PREINT)
+    noise = np.ascontiguousarray(w["imu_noise"], dtype=np.float64)
+    for i in range(n):
+        for k in range(Fm1):
+            smp = np.ascontiguousarray(w["imu_samples"][i, k]); first = np.ascontiguousarray(w["imu_first"][i, k]); lb = np.ascontiguousarray(w["imu_lin_bias"][i, k])
+            one = np.zeros(1, abi.IMU_PREINT)
+            lib.gf2o_imu_preintegrate(_p(smp), int(w["imu_n"][i, k]), _p(first), _p(lb), _p(noise), _p(one))
+            rec[i, k] = one[0]
+    w["imu"] = rec
+    return rec
+
+
+def wheel_preintegrate(w):
+    from gf2_loader import load
+    abi = load().abi
+    n, Fm1 = w["wheel_n"].shape
+    rec = np.zeros((n, Fm1), abi.WHEEL_PREINT)
+    noise = np.ascontiguousarray(w["wheel_noise"], dtype=np.float64)
+    for i in range(n):
+        for k in range(Fm1):
+            smp = np.ascontiguousarray(w["wheel_samples"][i, k]); first = np.ascontiguousarray(w["wheel_first"][i, k]); lin = np.ascontiguousarray(w["wheel_lin"][i, k])
+            one = np.zeros(1, abi.WHEEL_PREINT)
+            lib.gf2o_wheel_preintegrate(_p(smp), int(w["wheel_n"][i, k]), _p(first), _p(lin), _p(noise), _p(one))
+            rec[i, k] = one[0]
+    w["wheel"] = rec
+    return rec
