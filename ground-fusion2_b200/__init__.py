@@ -1,4 +1,198 @@
 """gf2_b200 — host-side Python mirror of the C ABI in include/gf2_abi.h (ctypes over libgf2_b200.so).
-The CUDA library is loaded lazily by `lib()`; there is no CPU fallback: without the built extension every
-compute entry point raises."""
+
+The library holds only hand-written sm_100a kernels; there is NO CPU fallback: if the shared library is missing or
+no CUDA device is present, every compute entry point raises."""
+import ctypes as C
+import os
+
+import numpy as np
+
 from . import abi  # noqa: F401
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgf2_b200.so")
+_lib = None
+
+
+class Gf2Error(RuntimeError):
+    pass
+
+
+def lib():
+    """Load libgf2_b200.so (built in-tree by build.py / __graft_entry__.build())."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise Gf2Error(f"{LIB_PATH} is missing: run `python __graft_entry__.py build` (the CUDA extension is the only "
+                           "implementation; there is no CPU fallback)")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.gf2_last_error.restype = C.c_char_p
+        _lib.gf2_host_alloc.restype = C.c_void_p
+        _lib.gf2_host_alloc.argtypes = [C.c_size_t]
+        _lib.gf2_host_free.argtypes = [C.c_void_p]
+    return _lib
+
+
+ABI_SYMBOLS = [
+    "gf2_last_error", "gf2_abi_version", "gf2_device_count", "gf2_solver_create", "gf2_solver_destroy", "gf2_set_states",
+    "gf2_solver_set_stream", "gf2_snapshot_states", "gf2_restore_states", "gf2_host_alloc", "gf2_host_free",
+    "gf2_imu_preintegrate_resident",
+    "gf2_set_landmarks", "gf2_set_imu", "gf2_imu_preintegrate", "gf2_get_imu", "gf2_set_wheel", "gf2_set_prior",
+    "gf2_set_planes", "gf2_solve", "gf2_linearize", "gf2_reduced_dim", "gf2_get_reduced_system", "gf2_get_states",
+    "gf2_get_landmarks", "gf2_comm_init", "gf2_comm_unique_id", "gf2_last_timing", "gf2_tracker_create",
+    "gf2_tracker_destroy", "gf2_tracker_track", "gf2_tracker_track_fb", "gf2_tracker_last_timing",
+]
+
+
+def _check(rc):
+    if rc != 0:
+        raise Gf2Error(f"gf2 error {rc}: {lib().gf2_last_error().decode()}")
+
+
+def device_count():
+    return lib().gf2_device_count()
+
+
+def pinned_empty(shape, dtype):
+    """numpy array backed by cudaHostAlloc'ed (pinned) memory, for full-speed H2D/D2H through the ABI."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    p = lib().gf2_host_alloc(max(n, 1))
+    if not p:
+        raise Gf2Error("cudaHostAlloc failed")
+    buf = (C.c_char * max(n, 1)).from_address(p)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    return arr
+
+
+_p = abi.ptr
+
+
+class Solver:
+    """Batched sliding-window solver: the ceres::Solve call of Estimator::optimization() for `max_windows` windows."""
+
+    def __init__(self, max_windows, n_frames=11, max_landmarks=1000, max_obs=7500, max_planes=0, max_imu_samples=0,
+                 use_wheel=False, device=0):
+        cfg = abi.SolverCfg()
+        cfg.device = device; cfg.max_windows = max_windows; cfg.n_frames = n_frames; cfg.max_landmarks = max_landmarks
+        cfg.max_obs = max_obs; cfg.max_planes = max_planes; cfg.max_imu_samples = max_imu_samples
+        cfg.use_wheel = 1 if use_wheel else 0
+        self.cfg = cfg
+        self.h = C.c_void_p()
+        _check(lib().gf2_solver_create(C.byref(cfg), C.byref(self.h)))
+        self.B, self.F, self.Lm, self.Om = max_windows, n_frames, max_landmarks, max_obs
+
+    def close(self):
+        if self.h:
+            lib().gf2_solver_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- uploads (arrays are window-major, see include/gf2_abi.h)
+    def set_states(self, w, first=0, n=None):
+        n = n if n is not None else w["para_pose"].shape[0]
+        _check(lib().gf2_set_states(self.h, first, n, _p(w["para_pose"]), _p(w["para_speedbias"]), _p(w["ex_pose"]), _p(w["td"]),
+                                    _p(w.get("ex_pose_wheel")), _p(w.get("sxsysw")), _p(w.get("td_wheel"))))
+
+    def set_landmarks(self, w, first=0, n=None):
+        n = n if n is not None else w["para_pose"].shape[0]
+        assert w["inv_depth"].shape[1] == self.Lm and w["obs"].shape[1] == self.Om, "array strides must equal the solver capacities"
+        _check(lib().gf2_set_landmarks(self.h, first, n, _p(w["n_landmarks"]), _p(w["inv_depth"]), _p(w["start_frame"]),
+                                       _p(w["track_len"]), _p(w["fixed"]), _p(w["obs"]), _p(w["frame_td"])))
+
+    def set_imu(self, rec, first=0):
+        _check(lib().gf2_set_imu(self.h, first, rec.shape[0], _p(rec)))
+
+    def imu_preintegrate(self, w, first=0):
+        n = w["imu_n"].shape[0]
+        noise = np.ascontiguousarray(w["imu_noise"], dtype=np.float64)
+        _check(lib().gf2_imu_preintegrate(self.h, first, n, _p(w["imu_samples"]), _p(w["imu_n"]), _p(w["imu_first"]),
+                                          _p(w["imu_lin_bias"]), _p(noise)))
+
+    def imu_preintegrate_resident(self, noise, n=None, first=0):
+        noise = np.ascontiguousarray(noise, dtype=np.float64)
+        _check(lib().gf2_imu_preintegrate_resident(self.h, first, n if n is not None else self.B, _p(noise)))
+
+    def set_stream(self, cuda_stream_ptr):
+        _check(lib().gf2_solver_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
+
+    def snapshot(self, n=None, first=0):
+        _check(lib().gf2_snapshot_states(self.h, first, n if n is not None else self.B))
+
+    def restore(self, n=None, first=0):
+        _check(lib().gf2_restore_states(self.h, first, n if n is not None else self.B))
+
+    def get_imu(self, n, first=0):
+        rec = np.zeros((n, self.F - 1), abi.IMU_PREINT)
+        _check(lib().gf2_get_imu(self.h, first, n, _p(rec)))
+        return rec
+
+    def set_wheel(self, rec, first=0):
+        _check(lib().gf2_set_wheel(self.h, first, rec.shape[0], _p(rec)))
+
+    def set_prior(self, w, first=0):
+        n = w["prior_rows"].shape[0]
+        _check(lib().gf2_set_prior(self.h, first, n, _p(w["prior_rows"]), _p(w["prior_J0"]), _p(w["prior_r0"]),
+                                   _p(w["prior_nblocks"]), _p(w["prior_blocks"])))
+
+    def set_planes(self, w, first=0):
+        _check(lib().gf2_set_planes(self.h, first, w["n_planes"].shape[0], _p(w["n_planes"]), _p(w["planes"])))
+
+    def upload(self, w, first=0, preintegrate="auto"):
+        """Everything a synth window dict holds. preintegrate: 'device' (raw samples -> kernel), 'records' (w['imu'])."""
+        self.set_states(w, first)
+        self.set_landmarks(w, first)
+        if preintegrate == "auto":
+            preintegrate = "records" if "imu" in w else "device"
+        if preintegrate == "device":
+            self.imu_preintegrate(w, first)
+        else:
+            self.set_imu(w["imu"], first)
+        if w.get("use_wheel") and "wheel" in w:
+            self.set_wheel(w["wheel"], first)
+        self.set_prior(w, first)
+        if w.get("max_planes", 0) > 0:
+            self.set_planes(w, first)
+
+    # ---- compute
+    def solve(self, opts, n=None, first=0, summaries=None):
+        n = n if n is not None else self.B
+        if summaries is None:
+            summaries = np.zeros(n, abi.SUMMARY)
+        _check(lib().gf2_solve(self.h, first, n, C.byref(opts), _p(summaries)))
+        return summaries
+
+    def linearize(self, opts, n=None, first=0):
+        n = n if n is not None else self.B
+        _check(lib().gf2_linearize(self.h, first, n, C.byref(opts)))
+        D = lib().gf2_reduced_dim(self.h, C.byref(opts))
+        S = np.zeros((n, D, D)); g = np.zeros((n, D)); cost = np.zeros(n)
+        _check(lib().gf2_get_reduced_system(self.h, first, n, _p(S), _p(g), _p(cost)))
+        return S, g, cost
+
+    def get_states(self, n=None, first=0, out=None):
+        n = n if n is not None else self.B
+        o = out if out is not None else {}
+        o.setdefault("para_pose", np.zeros((n, self.F, 7))); o.setdefault("para_speedbias", np.zeros((n, self.F, 9)))
+        o.setdefault("ex_pose", np.zeros((n, 7))); o.setdefault("td", np.zeros(n))
+        if self.cfg.use_wheel:
+            o.setdefault("ex_pose_wheel", np.zeros((n, 7))); o.setdefault("sxsysw", np.zeros((n, 3))); o.setdefault("td_wheel", np.zeros(n))
+        _check(lib().gf2_get_states(self.h, first, n, _p(o["para_pose"]), _p(o["para_speedbias"]), _p(o["ex_pose"]), _p(o["td"]),
+                                    _p(o.get("ex_pose_wheel")), _p(o.get("sxsysw")), _p(o.get("td_wheel"))))
+        return o
+
+    def get_landmarks(self, n=None, first=0, out=None):
+        n = n if n is not None else self.B
+        d = out if out is not None else np.zeros((n, self.Lm))
+        _check(lib().gf2_get_landmarks(self.h, first, n, _p(d)))
+        return d
+
+    def last_timing(self):
+        t = np.zeros(8)
+        _check(lib().gf2_last_timing(self.h, _p(t)))
+        return {"total_ms": t[0], "linearize_ms": t[1], "solve_ms": t[2], "step_ms": t[3], "launches": int(t[4]), "linearize_launches": int(t[5]), "prepare_ms": t[6]}

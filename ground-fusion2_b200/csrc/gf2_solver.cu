@@ -1,0 +1,509 @@
+// gf2_solver.cu — C-ABI entry points of the batched sliding-window solver (include/gf2_abi.h) and the host-side
+// orchestration: device memory, H2D/D2H of the reference's packed arrays, the trust-region kernel sequence and its
+// CUDA-event timing. No CPU fallback: every compute call launches kernels on the handle's device.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include "gf2_solver_kernels2.cuh"
+#include "gf2_common.h"
+
+using namespace gf2;
+
+namespace gf2 {
+
+// ------------------------------------------------------------------------------------------------ preintegration
+// IntegrationBase::push_back chain (VE/factor/integration_base.h:39-167): mid-point integration with 15x15 jacobian and
+// covariance propagation. One thread per interval; F and V are built explicitly and the sparse products are dense loops.
+__global__ void k_imu_preintegrate(int n_intervals, int max_samples, const gf2_imu_sample* samples, const int32_t* n_samples,
+                                   const double* first, const double* lin_bias, double acc_n, double gyr_n, double acc_w, double gyr_w,
+                                   gf2_imu_preint* out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_intervals) return;
+  const gf2_imu_sample* smp = samples + (size_t)idx * max_samples;
+  V3 acc_0 = ld3(first + 6 * idx), gyr_0 = ld3(first + 6 * idx + 3);
+  const V3 ba = ld3(lin_bias + 6 * idx), bg = ld3(lin_bias + 6 * idx + 3);
+  V3 dp = mk3(0, 0, 0), dv = mk3(0, 0, 0); Q4 dq; dq.x = dq.y = dq.z = 0; dq.w = 1;
+  double Jm[225], C[225], Fm[225], T[225], V[270];
+  for (int i = 0; i < 225; i++) { Jm[i] = 0; C[i] = 0; }
+  for (int i = 0; i < 15; i++) Jm[i * 16] = 1.0;
+  double sum_dt = 0;
+  const double nz[18] = {acc_n * acc_n, acc_n * acc_n, acc_n * acc_n, gyr_n * gyr_n, gyr_n * gyr_n, gyr_n * gyr_n,
+                         acc_n * acc_n, acc_n * acc_n, acc_n * acc_n, gyr_n * gyr_n, gyr_n * gyr_n, gyr_n * gyr_n,
+                         acc_w * acc_w, acc_w * acc_w, acc_w * acc_w, gyr_w * gyr_w, gyr_w * gyr_w, gyr_w * gyr_w};
+  const int ns = n_samples[idx];
+  for (int s = 0; s < ns; s++) {
+    const double dt = smp[s].dt;
+    const V3 acc_1 = ld3(smp[s].acc), gyr_1 = ld3(smp[s].gyr);
+    // midPointIntegration, integration_base.h:72-81
+    const V3 un_acc_0 = qrot(dq, acc_0 - ba);
+    const V3 un_gyr = 0.5 * (gyr_0 + gyr_1) - bg;
+    Q4 hq; hq.w = 1; hq.x = un_gyr.x * dt / 2; hq.y = un_gyr.y * dt / 2; hq.z = un_gyr.z * dt / 2;
+    const Q4 rq = qmul(dq, hq);
+    const V3 un_acc_1 = qrot(rq, acc_1 - ba);
+    const V3 un_acc = 0.5 * (un_acc_0 + un_acc_1);
+    const V3 rp = dp + dt * dv + (0.5 * dt * dt) * un_acc;
+    const V3 rv = dv + dt * un_acc;
+    // jacobian / covariance, integration_base.h:83-135
+    const M3 R_w_x = skew(un_gyr), R_a_0_x = skew(acc_0 - ba), R_a_1_x = skew(acc_1 - ba);
+    const M3 dR = toR(dq), rR = toR(rq), I = eye3();
+    const M3 IwR = sub(I, scale(R_w_x, dt));
+    for (int i = 0; i < 225; i++) Fm[i] = 0;
+    for (int i = 0; i < 270; i++) V[i] = 0;
+    const M3 rRa1 = mul(rR, R_a_1_x);
+    put3(Fm, 15, 0, 0, I, 1.0);
+    put3(Fm, 15, 0, 3, add(scale(mul(dR, R_a_0_x), -0.25 * dt * dt), scale(mul(rRa1, IwR), -0.25 * dt * dt)), 1.0);
+    put3(Fm, 15, 0, 6, I, dt);
+    put3(Fm, 15, 0, 9, add(dR, rR), -0.25 * dt * dt);
+    put3(Fm, 15, 0, 12, rRa1, -0.25 * dt * dt * -dt);
+    put3(Fm, 15, 3, 3, IwR, 1.0);
+    put3(Fm, 15, 3, 12, I, -dt);
+    put3(Fm, 15, 6, 3, add(scale(mul(dR, R_a_0_x), -0.5 * dt), scale(mul(rRa1, IwR), -0.5 * dt)), 1.0);
+    put3(Fm, 15, 6, 6, I, 1.0);
+    put3(Fm, 15, 6, 9, add(dR, rR), -0.5 * dt);
+    put3(Fm, 15, 6, 12, rRa1, -0.5 * dt * -dt);
+    put3(Fm, 15, 9, 9, I, 1.0);
+    put3(Fm, 15, 12, 12, I, 1.0);
+    put3(V, 18, 0, 0, dR, 0.25 * dt * dt);
+    put3(V, 18, 0, 3, rRa1, -0.25 * dt * dt * 0.5 * dt);
+    put3(V, 18, 0, 6, rR, 0.25 * dt * dt);
+    put3(V, 18, 0, 9, rRa1, -0.25 * dt * dt * 0.5 * dt);
+    put3(V, 18, 3, 3, I, 0.5 * dt);
+    put3(V, 18, 3, 9, I, 0.5 * dt);
+    put3(V, 18, 6, 0, dR, 0.5 * dt);
+    put3(V, 18, 6, 3, rRa1, -0.5 * dt * 0.5 * dt);
+    put3(V, 18, 6, 6, rR, 0.5 * dt);
+    put3(V, 18, 6, 9, rRa1, -0.5 * dt * 0.5 * dt);
+    put3(V, 18, 9, 12, I, dt);
+    put3(V, 18, 12, 15, I, dt);
+    // jacobian = F * jacobian
+    for (int r = 0; r < 15; r++) for (int c = 0; c < 15; c++) { double a = 0; for (int k = 0; k < 15; k++) a += Fm[r * 15 + k] * Jm[k * 15 + c]; T[r * 15 + c] = a; }
+    for (int i = 0; i < 225; i++) Jm[i] = T[i];
+    // covariance = F * cov * F^T + V * noise * V^T
+    for (int r = 0; r < 15; r++) for (int c = 0; c < 15; c++) { double a = 0; for (int k = 0; k < 15; k++) a += Fm[r * 15 + k] * C[k * 15 + c]; T[r * 15 + c] = a; }
+    for (int r = 0; r < 15; r++) for (int c = 0; c < 15; c++) {
+      double a = 0; for (int k = 0; k < 15; k++) a += T[r * 15 + k] * Fm[c * 15 + k];
+      double b = 0; for (int k = 0; k < 18; k++) b += V[r * 18 + k] * nz[k] * V[c * 18 + k];
+      C[r * 15 + c] = a + b;
+    }
+    dp = rp; dv = rv; dq = qnormalized(rq);
+    sum_dt += dt; acc_0 = acc_1; gyr_0 = gyr_1;
+  }
+  gf2_imu_preint& o = out[idx];
+  o.sum_dt = sum_dt;
+  o.delta_p[0] = dp.x; o.delta_p[1] = dp.y; o.delta_p[2] = dp.z;
+  o.delta_q[0] = dq.x; o.delta_q[1] = dq.y; o.delta_q[2] = dq.z; o.delta_q[3] = dq.w;
+  o.delta_v[0] = dv.x; o.delta_v[1] = dv.y; o.delta_v[2] = dv.z;
+  o.lin_ba[0] = ba.x; o.lin_ba[1] = ba.y; o.lin_ba[2] = ba.z; o.lin_bg[0] = bg.x; o.lin_bg[1] = bg.y; o.lin_bg[2] = bg.z;
+  for (int i = 0; i < 225; i++) { o.jacobian[i] = Jm[i]; o.covariance[i] = C[i]; }
+  o.valid = 1; o.pad_ = 0;
+}
+
+}  // namespace gf2
+
+// ------------------------------------------------------------------------------------------------ handle
+struct gf2_solver {
+  gf2_solver_cfg cfg;
+  int D;
+  cudaStream_t stream, own_stream;
+  double *snap_pose = nullptr, *snap_sb = nullptr, *snap_invdep = nullptr;
+  KP kp;  // device pointers for window 0
+  std::vector<void*> allocs;
+  // raw-sample staging for preintegration
+  gf2_imu_sample* d_imu_samples = nullptr; int32_t* d_imu_n = nullptr; double *d_imu_first = nullptr, *d_imu_bias = nullptr;
+  gf2_imu_preint* d_imu = nullptr;
+  gf2_wheel_preint* d_wheel = nullptr;
+  bool has_imu = false, has_wheel = false, has_prior = false, has_planes = false, dump_full = false;
+  std::vector<int32_t> h_obeg;
+  cudaEvent_t ev[4 * 64 + 3];
+  double timing[8];
+  WinState* h_state = nullptr;
+};
+
+template <typename T>
+static int dalloc(gf2_solver* h, T** p, size_t count) {
+  void* q = nullptr;
+  if (count == 0) count = 1;
+  if (cudaMalloc(&q, count * sizeof(T)) != cudaSuccess) return gf2::fail(GF2_ERR_CUDA, "cudaMalloc of %zu bytes failed: %s", count * sizeof(T), cudaGetErrorString(cudaGetLastError()));
+  cudaMemset(q, 0, count * sizeof(T));
+  h->allocs.push_back(q);
+  *p = (T*)q;
+  return GF2_OK;
+}
+
+#define GF2_TRY(x) do { int rc_ = (x); if (rc_ != GF2_OK) return rc_; } while (0)
+#define GF2_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return gf2::fail(GF2_ERR_CUDA, "%s: %s", #x, cudaGetErrorString(e_)); } while (0)
+
+extern "C" {
+
+const char* gf2_last_error(void) { return gf2::last_error(); }
+int gf2_abi_version(void) { return GF2_ABI_VERSION; }
+int gf2_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; } return n; }
+
+void* gf2_host_alloc(size_t bytes) { void* p = nullptr; if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; } return p; }
+void gf2_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int gf2_solver_create(const gf2_solver_cfg* cfg, gf2_solver** out) {
+  if (!cfg || !out) return gf2::fail(GF2_ERR_INVALID, "null argument");
+  if (cfg->n_frames < 2 || cfg->n_frames > GF2_MAX_FRAMES) return gf2::fail(GF2_ERR_INVALID, "n_frames %d out of range [2, %d]", cfg->n_frames, GF2_MAX_FRAMES);
+  if (cfg->max_landmarks < 1 || cfg->max_landmarks > GF2_MAX_LANDMARKS) return gf2::fail(GF2_ERR_INVALID, "max_landmarks %d out of range", cfg->max_landmarks);
+  if (cfg->max_windows < 1 || cfg->max_obs < 1) return gf2::fail(GF2_ERR_INVALID, "max_windows / max_obs must be positive");
+  if (gf2_device_count() <= cfg->device) return gf2::fail(GF2_ERR_CUDA, "CUDA device %d not available (no CPU fallback exists)", cfg->device);
+  GF2_CUDA(cudaSetDevice(cfg->device));
+  gf2_solver* h = new gf2_solver();
+  h->cfg = *cfg;
+  const int B = cfg->max_windows, F = cfg->n_frames, Lm = cfg->max_landmarks, Om = cfg->max_obs, Pm = cfg->max_planes;
+  h->D = 15 * F;
+  memset(&h->kp, 0, sizeof(KP));
+  KP& k = h->kp;
+  k.nW = B; k.F = F; k.Lm = Lm; k.Om = Om; k.Pm = Pm; k.D = h->D; k.use_wheel = cfg->use_wheel;
+  if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return gf2::fail(GF2_ERR_CUDA, "stream creation failed"); }
+  h->stream = h->own_stream;
+  int rc = GF2_OK;
+#define A(ptr, type, count) if (rc == GF2_OK) rc = dalloc<type>(h, (type**)&(ptr), (size_t)(count))
+  A(k.pose, double, (size_t)B * F * 7); A(k.sb, double, (size_t)B * F * 9); A(k.ex, double, (size_t)B * 7); A(k.td, double, B);
+  A(k.exw, double, (size_t)B * 7); A(k.sxw, double, (size_t)B * 3); A(k.tdw, double, B);
+  A(k.invdep, double, (size_t)B * Lm); A(k.pose_c, double, (size_t)B * F * 7); A(k.sb_c, double, (size_t)B * F * 9); A(k.invdep_c, double, (size_t)B * Lm);
+  A(k.nlm, int32_t, B); A(k.start, int32_t, (size_t)B * Lm); A(k.tlen, int32_t, (size_t)B * Lm); A(k.obeg, int32_t, (size_t)B * Lm);
+  A(k.fixed, uint8_t, (size_t)B * Lm); A(k.obs, float4, (size_t)B * Om); A(k.frame_td, double, (size_t)B * F);
+  A(h->d_imu, gf2_imu_preint, (size_t)B * (F - 1)); A(k.imu_sqrt, double, (size_t)B * (F - 1) * 225);
+  if (cfg->use_wheel) { A(h->d_wheel, gf2_wheel_preint, (size_t)B * (F - 1)); A(k.wheel_sqrt, double, (size_t)B * (F - 1) * 36); }
+  A(k.prior_rows, int32_t, B); A(k.prior_nblocks, int32_t, B); A(k.prior_J0, double, (size_t)B * kP * kP); A(k.prior_r0, double, (size_t)B * kP);
+  A(k.prior_blocks, gf2_prior_block, (size_t)B * (2 * F + 8)); A(k.prior_H, double, (size_t)B * kP * kP); A(k.prior_map, int32_t, (size_t)B * kP);
+  if (Pm > 0) { A(k.n_planes, int32_t, B); A(k.planes, gf2_plane, (size_t)B * Pm); }
+  A(k.Svis, double, (size_t)B * kNVMax * kNVMax); A(k.gvis, double, (size_t)B * kNVP); A(k.Udiag, double, (size_t)B * kNVMax);
+  A(k.lm_v, double, (size_t)B * Lm); A(k.lm_g, double, (size_t)B * Lm); A(k.lm_s, double, (size_t)B * Lm); A(k.lm_z, double, (size_t)B * Lm);
+  A(k.sx, double, (size_t)B * h->D); A(k.zx, double, (size_t)B * h->D); A(k.ux, double, (size_t)B * h->D); A(k.ex_diag, double, (size_t)B * h->D);
+  A(k.st, WinState, B);
+  if (cfg->max_imu_samples > 0) {
+    A(h->d_imu_samples, gf2_imu_sample, (size_t)B * (F - 1) * cfg->max_imu_samples); A(h->d_imu_n, int32_t, (size_t)B * (F - 1));
+    A(h->d_imu_first, double, (size_t)B * (F - 1) * 6); A(h->d_imu_bias, double, (size_t)B * (F - 1) * 6);
+  }
+#undef A
+  if (rc != GF2_OK) { gf2_solver_destroy(h); return rc; }
+  for (auto& e : h->ev) cudaEventCreate(&e);
+  cudaHostAlloc((void**)&h->h_state, sizeof(WinState) * B, cudaHostAllocDefault);
+  // opt in to large dynamic shared memory
+  cudaFuncSetAttribute(k_linearize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LinShared));
+  cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(SolveShared) + sizeof(double) * (h->D * (h->D + 1) / 2)));
+  cudaFuncSetAttribute(k_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * 450 * GF2_MAX_FRAMES));
+  if (cudaGetLastError() != cudaSuccess) { gf2_solver_destroy(h); return gf2::fail(GF2_ERR_CUDA, "cudaFuncSetAttribute failed (is this an sm_100a device?)"); }
+  *out = h;
+  return GF2_OK;
+}
+
+void gf2_solver_destroy(gf2_solver* h) {
+  if (!h) return;
+  cudaSetDevice(h->cfg.device);
+  cudaStreamSynchronize(h->stream);
+  for (void* p : h->allocs) cudaFree(p);
+  for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+  if (h->h_state) cudaFreeHost(h->h_state);
+  cudaStreamDestroy(h->own_stream);
+  delete h;
+}
+
+static int check_range(gf2_solver* h, int first, int n) {
+  if (!h) return gf2::fail(GF2_ERR_INVALID, "null handle");
+  if (first < 0 || n < 0 || first + n > h->cfg.max_windows) return gf2::fail(GF2_ERR_INVALID, "window range [%d, %d) outside capacity %d", first, first + n, h->cfg.max_windows);
+  cudaSetDevice(h->cfg.device);
+  return GF2_OK;
+}
+#define H2D(dst, src, bytes) do { if ((src) && (bytes) > 0) GF2_CUDA(cudaMemcpyAsync((void*)(dst), (src), (bytes), cudaMemcpyHostToDevice, h->stream)); } while (0)
+#define D2H(dst, src, bytes) do { if ((dst) && (bytes) > 0) GF2_CUDA(cudaMemcpyAsync((dst), (const void*)(src), (bytes), cudaMemcpyDeviceToHost, h->stream)); } while (0)
+
+int gf2_set_states(gf2_solver* h, int first, int n, const double* para_pose, const double* para_speedbias, const double* ex_pose,
+                   const double* td, const double* ex_pose_wheel, const double* sxsysw, const double* td_wheel) {
+  GF2_TRY(check_range(h, first, n));
+  const KP& k = h->kp; const int F = k.F;
+  H2D(k.pose + (size_t)first * F * 7, para_pose, sizeof(double) * n * F * 7);
+  H2D(k.sb + (size_t)first * F * 9, para_speedbias, sizeof(double) * n * F * 9);
+  H2D(k.ex + (size_t)first * 7, ex_pose, sizeof(double) * n * 7);
+  H2D(k.td + first, td, sizeof(double) * n);
+  if (h->cfg.use_wheel) {
+    H2D(k.exw + (size_t)first * 7, ex_pose_wheel, sizeof(double) * n * 7);
+    H2D(k.sxw + (size_t)first * 3, sxsysw, sizeof(double) * n * 3);
+    H2D(k.tdw + first, td_wheel, sizeof(double) * n);
+  }
+  return GF2_OK;
+}
+
+int gf2_set_landmarks(gf2_solver* h, int first, int n, const int32_t* n_landmarks, const double* inv_depth, const int32_t* start_frame,
+                      const int32_t* track_len, const uint8_t* fixed, const gf2_obs* obs, const double* frame_td) {
+  GF2_TRY(check_range(h, first, n));
+  const KP& k = h->kp; const int F = k.F, Lm = k.Lm, Om = k.Om;
+  if (!n_landmarks || !inv_depth || !start_frame || !track_len || !obs || !frame_td) return gf2::fail(GF2_ERR_INVALID, "null landmark array");
+  // validate + exclusive prefix sum of track_len on the host (index bookkeeping, bit-exact by construction)
+  h->h_obeg.assign((size_t)n * Lm, 0);
+  for (int w = 0; w < n; w++) {
+    const int nl = n_landmarks[w];
+    if (nl < 0 || nl > Lm) return gf2::fail(GF2_ERR_INVALID, "window %d: n_landmarks %d exceeds capacity %d", first + w, nl, Lm);
+    int acc = 0;
+    for (int l = 0; l < nl; l++) {
+      const int s = start_frame[(size_t)w * Lm + l], L = track_len[(size_t)w * Lm + l];
+      if (s < 0 || L < 1 || s + L > F) return gf2::fail(GF2_ERR_INVALID, "window %d landmark %d: track [%d, %d) outside the %d frames", first + w, l, s, s + L, F);
+      h->h_obeg[(size_t)w * Lm + l] = acc; acc += L;
+    }
+    if (acc > Om) return gf2::fail(GF2_ERR_INVALID, "window %d: %d observations exceed capacity %d", first + w, acc, Om);
+  }
+  H2D(k.nlm + first, n_landmarks, sizeof(int32_t) * n);
+  H2D(k.invdep + (size_t)first * Lm, inv_depth, sizeof(double) * n * Lm);
+  H2D(k.start + (size_t)first * Lm, start_frame, sizeof(int32_t) * n * Lm);
+  H2D(k.tlen + (size_t)first * Lm, track_len, sizeof(int32_t) * n * Lm);
+  H2D(k.obeg + (size_t)first * Lm, h->h_obeg.data(), sizeof(int32_t) * n * Lm);
+  if (fixed) H2D(k.fixed + (size_t)first * Lm, fixed, sizeof(uint8_t) * n * Lm);
+  else GF2_CUDA(cudaMemsetAsync((void*)(k.fixed + (size_t)first * Lm), 0, (size_t)n * Lm, h->stream));
+  H2D(k.obs + (size_t)first * Om, obs, sizeof(gf2_obs) * n * Om);
+  H2D(k.frame_td + (size_t)first * F, frame_td, sizeof(double) * n * F);
+  GF2_CUDA(cudaStreamSynchronize(h->stream));  // h_obeg is reused by the next call
+  return GF2_OK;
+}
+
+int gf2_set_imu(gf2_solver* h, int first, int n, const gf2_imu_preint* preint) {
+  GF2_TRY(check_range(h, first, n));
+  H2D(h->d_imu + (size_t)first * (h->kp.F - 1), preint, sizeof(gf2_imu_preint) * n * (h->kp.F - 1));
+  h->has_imu = preint != nullptr;
+  return GF2_OK;
+}
+
+int gf2_imu_preintegrate(gf2_solver* h, int first, int n, const gf2_imu_sample* samples, const int32_t* n_samples, const double* first_sample,
+                         const double* lin_bias, const double noise[4]) {
+  GF2_TRY(check_range(h, first, n));
+  const int ms = h->cfg.max_imu_samples, Fm1 = h->kp.F - 1;
+  if (ms <= 0) return gf2::fail(GF2_ERR_INVALID, "solver created with max_imu_samples = 0");
+  if (!samples || !n_samples || !first_sample || !lin_bias || !noise) return gf2::fail(GF2_ERR_INVALID, "null argument");
+  for (size_t i = 0; i < (size_t)n * Fm1; i++) if (n_samples[i] < 0 || n_samples[i] > ms) return gf2::fail(GF2_ERR_INVALID, "n_samples[%zu] = %d exceeds max_imu_samples %d", i, n_samples[i], ms);
+  const size_t off = (size_t)first * Fm1;
+  H2D(h->d_imu_samples + off * ms, samples, sizeof(gf2_imu_sample) * n * Fm1 * ms);
+  H2D(h->d_imu_n + off, n_samples, sizeof(int32_t) * n * Fm1);
+  H2D(h->d_imu_first + off * 6, first_sample, sizeof(double) * n * Fm1 * 6);
+  H2D(h->d_imu_bias + off * 6, lin_bias, sizeof(double) * n * Fm1 * 6);
+  const int total = n * Fm1;
+  k_imu_preintegrate<<<(total + 63) / 64, 64, 0, h->stream>>>(total, ms, h->d_imu_samples + off * ms, h->d_imu_n + off, h->d_imu_first + off * 6,
+                                                               h->d_imu_bias + off * 6, noise[0], noise[1], noise[2], noise[3], h->d_imu + off);
+  GF2_CUDA(cudaGetLastError());
+  h->has_imu = true;
+  return GF2_OK;
+}
+
+int gf2_imu_preintegrate_resident(gf2_solver* h, int first, int n, const double noise[4]) {
+  GF2_TRY(check_range(h, first, n));
+  const int ms = h->cfg.max_imu_samples, Fm1 = h->kp.F - 1;
+  if (ms <= 0) return gf2::fail(GF2_ERR_INVALID, "solver created with max_imu_samples = 0");
+  const size_t off = (size_t)first * Fm1; const int total = n * Fm1;
+  k_imu_preintegrate<<<(total + 63) / 64, 64, 0, h->stream>>>(total, ms, h->d_imu_samples + off * ms, h->d_imu_n + off, h->d_imu_first + off * 6,
+                                                               h->d_imu_bias + off * 6, noise[0], noise[1], noise[2], noise[3], h->d_imu + off);
+  GF2_CUDA(cudaGetLastError());
+  h->has_imu = true;
+  return GF2_OK;
+}
+
+int gf2_solver_set_stream(gf2_solver* h, void* cuda_stream) {
+  if (!h) return gf2::fail(GF2_ERR_INVALID, "null handle");
+  cudaStreamSynchronize(h->stream);
+  h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+  return GF2_OK;
+}
+
+int gf2_snapshot_states(gf2_solver* h, int first, int n) {
+  GF2_TRY(check_range(h, first, n));
+  const KP& k = h->kp; const int B = h->cfg.max_windows;
+  if (!h->snap_pose) { GF2_TRY(dalloc<double>(h, &h->snap_pose, (size_t)B * k.F * 7)); GF2_TRY(dalloc<double>(h, &h->snap_sb, (size_t)B * k.F * 9)); GF2_TRY(dalloc<double>(h, &h->snap_invdep, (size_t)B * k.Lm)); }
+  GF2_CUDA(cudaMemcpyAsync(h->snap_pose + (size_t)first * k.F * 7, k.pose + (size_t)first * k.F * 7, sizeof(double) * n * k.F * 7, cudaMemcpyDeviceToDevice, h->stream));
+  GF2_CUDA(cudaMemcpyAsync(h->snap_sb + (size_t)first * k.F * 9, k.sb + (size_t)first * k.F * 9, sizeof(double) * n * k.F * 9, cudaMemcpyDeviceToDevice, h->stream));
+  GF2_CUDA(cudaMemcpyAsync(h->snap_invdep + (size_t)first * k.Lm, k.invdep + (size_t)first * k.Lm, sizeof(double) * n * k.Lm, cudaMemcpyDeviceToDevice, h->stream));
+  return GF2_OK;
+}
+int gf2_restore_states(gf2_solver* h, int first, int n) {
+  GF2_TRY(check_range(h, first, n));
+  const KP& k = h->kp;
+  if (!h->snap_pose) return gf2::fail(GF2_ERR_INVALID, "no snapshot taken");
+  GF2_CUDA(cudaMemcpyAsync(k.pose + (size_t)first * k.F * 7, h->snap_pose + (size_t)first * k.F * 7, sizeof(double) * n * k.F * 7, cudaMemcpyDeviceToDevice, h->stream));
+  GF2_CUDA(cudaMemcpyAsync(k.sb + (size_t)first * k.F * 9, h->snap_sb + (size_t)first * k.F * 9, sizeof(double) * n * k.F * 9, cudaMemcpyDeviceToDevice, h->stream));
+  GF2_CUDA(cudaMemcpyAsync(k.invdep + (size_t)first * k.Lm, h->snap_invdep + (size_t)first * k.Lm, sizeof(double) * n * k.Lm, cudaMemcpyDeviceToDevice, h->stream));
+  return GF2_OK;
+}
+
+int gf2_get_imu(gf2_solver* h, int first, int n, gf2_imu_preint* preint) {
+  GF2_TRY(check_range(h, first, n));
+  D2H(preint, h->d_imu + (size_t)first * (h->kp.F - 1), sizeof(gf2_imu_preint) * n * (h->kp.F - 1));
+  GF2_CUDA(cudaStreamSynchronize(h->stream));
+  return GF2_OK;
+}
+
+int gf2_set_wheel(gf2_solver* h, int first, int n, const gf2_wheel_preint* preint) {
+  GF2_TRY(check_range(h, first, n));
+  if (!h->cfg.use_wheel) return gf2::fail(GF2_ERR_INVALID, "solver created with use_wheel = 0");
+  H2D(h->d_wheel + (size_t)first * (h->kp.F - 1), preint, sizeof(gf2_wheel_preint) * n * (h->kp.F - 1));
+  h->has_wheel = preint != nullptr;
+  return GF2_OK;
+}
+
+int gf2_set_prior(gf2_solver* h, int first, int n, const int32_t* n_rows, const double* J0, const double* r0, const int32_t* n_blocks,
+                  const gf2_prior_block* blocks) {
+  GF2_TRY(check_range(h, first, n));
+  const KP& k = h->kp;
+  if (!n_rows) { h->has_prior = false; return GF2_OK; }
+  for (int w = 0; w < n; w++) {
+    if (n_rows[w] < 0 || n_rows[w] > kP) return gf2::fail(GF2_ERR_INVALID, "prior of window %d has %d rows (max %d)", first + w, n_rows[w], kP);
+    if (n_rows[w] > 0 && (n_blocks[w] < 1 || n_blocks[w] > 2 * k.F + 8)) return gf2::fail(GF2_ERR_INVALID, "prior of window %d has %d blocks", first + w, n_blocks[w]);
+  }
+  H2D(k.prior_rows + first, n_rows, sizeof(int32_t) * n);
+  H2D(k.prior_nblocks + first, n_blocks, sizeof(int32_t) * n);
+  H2D(k.prior_J0 + (size_t)first * kP * kP, J0, sizeof(double) * n * kP * kP);
+  H2D(k.prior_r0 + (size_t)first * kP, r0, sizeof(double) * n * kP);
+  H2D(k.prior_blocks + (size_t)first * (2 * k.F + 8), blocks, sizeof(gf2_prior_block) * n * (2 * k.F + 8));
+  h->has_prior = true;
+  return GF2_OK;
+}
+
+int gf2_set_planes(gf2_solver* h, int first, int n, const int32_t* n_planes, const gf2_plane* planes) {
+  GF2_TRY(check_range(h, first, n));
+  const KP& k = h->kp;
+  if (k.Pm <= 0) return gf2::fail(GF2_ERR_INVALID, "solver created with max_planes = 0");
+  for (int w = 0; w < n; w++) if (n_planes[w] < 0 || n_planes[w] > k.Pm) return gf2::fail(GF2_ERR_INVALID, "n_planes[%d] = %d exceeds capacity %d", w, n_planes[w], k.Pm);
+  H2D(k.n_planes + first, n_planes, sizeof(int32_t) * n);
+  H2D(k.planes + (size_t)first * k.Pm, planes, sizeof(gf2_plane) * n * k.Pm);
+  h->has_planes = true;
+  return gf2::fail(GF2_ERR_UNSUPPORTED, "LiDAR plane factors are not wired into the sweep yet");
+}
+
+static int fill_kp(gf2_solver* h, const gf2_solve_opts* o, KP& k) {
+  if (!o) return gf2::fail(GF2_ERR_INVALID, "null options");
+  if (o->max_time_s != 0.0) return gf2::fail(GF2_ERR_INVALID, "max_time_s must be 0: the wall-clock cap is not reproduced");
+  if (o->max_iterations < 0 || o->max_iterations > 64) return gf2::fail(GF2_ERR_INVALID, "max_iterations %d out of range [0, 64]", o->max_iterations);
+  const uint32_t need = GF2_CONST_EX_POSE | GF2_CONST_TD;
+  if ((o->const_mask & need) != need) return gf2::fail(GF2_ERR_UNSUPPORTED, "free camera extrinsic / td blocks are not built yet (const_mask must hold EX_POSE|TD)");
+  if (h->cfg.use_wheel) {
+    const uint32_t needw = GF2_CONST_EX_WHEEL | GF2_CONST_WHEEL_INTRINSIC | GF2_CONST_TD_WHEEL;
+    if ((o->const_mask & needw) != needw) return gf2::fail(GF2_ERR_UNSUPPORTED, "free wheel calibration blocks are not built yet");
+  }
+  k = h->kp;
+  k.const_mask = o->const_mask; k.huber = o->huber_delta; k.sqrt_info_px = o->sqrt_info_px; k.g_norm = o->g_norm; k.lidar_sqrt_info = o->lidar_sqrt_info;
+  k.ftol = o->function_tolerance > 0 ? o->function_tolerance : 1e-6;
+  k.gtol = o->gradient_tolerance > 0 ? o->gradient_tolerance : 1e-10;
+  k.ptol = o->parameter_tolerance > 0 ? o->parameter_tolerance : 1e-8;
+  k.max_iterations = o->max_iterations;
+  k.imu = h->has_imu ? h->d_imu : nullptr;
+  k.wheel = (h->cfg.use_wheel && h->has_wheel) ? h->d_wheel : nullptr;
+  if (!h->has_prior) { k.prior_rows = nullptr; }
+  return GF2_OK;
+}
+
+static int run(gf2_solver* h, int first, int n, const gf2_solve_opts* opts, gf2_solve_summary* summaries, int iterations, bool only_linearize) {
+  GF2_TRY(check_range(h, first, n));
+  if (n == 0) return GF2_OK;
+  KP k;
+  GF2_TRY(fill_kp(h, opts, k));
+  const int D = h->D;
+  const size_t sh_lin = sizeof(LinShared);
+  const size_t sh_solve = sizeof(SolveShared) + sizeof(double) * (D * (D + 1) / 2);
+  double initial_radius = opts->initial_radius > 0 ? opts->initial_radius : 1e4;
+  int ne = 0;
+  cudaEventRecord(h->ev[ne++], h->stream);
+  k_prepare<<<n, 128, sizeof(double) * 450 * GF2_MAX_FRAMES, h->stream>>>(k, first);
+  cudaEventRecord(h->ev[ne++], h->stream);
+  if (initial_radius != 1e4) return gf2::fail(GF2_ERR_UNSUPPORTED, "initial_radius other than the Ceres default 1e4");
+  const int iters = only_linearize ? 1 : iterations;
+  for (int it = 0; it < iters; it++) {
+    k_linearize<<<n, kLinThreads, sh_lin, h->stream>>>(k, first);
+    cudaEventRecord(h->ev[ne++], h->stream);
+    k_solve<<<n, kSolveThreads, sh_solve, h->stream>>>(k, first);
+    cudaEventRecord(h->ev[ne++], h->stream);
+    if (!only_linearize) {
+      k_backsub<<<n, 256, 0, h->stream>>>(k, first);
+      cudaEventRecord(h->ev[ne++], h->stream);
+      k_candidate<<<n, 256, 0, h->stream>>>(k, first);
+      cudaEventRecord(h->ev[ne++], h->stream);
+    }
+  }
+  GF2_CUDA(cudaGetLastError());
+  GF2_CUDA(cudaMemcpyAsync(h->h_state, k.st + first, sizeof(WinState) * n, cudaMemcpyDeviceToHost, h->stream));
+  GF2_CUDA(cudaStreamSynchronize(h->stream));
+  // timing
+  memset(h->timing, 0, sizeof(h->timing));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, h->ev[0], h->ev[ne - 1]); h->timing[0] = ms;
+  const int per = only_linearize ? 2 : 4;
+  for (int it = 0; it < iters; it++) {
+    const int b = 2 + it * per;
+    cudaEventElapsedTime(&ms, h->ev[b - 1], h->ev[b]); h->timing[1] += ms;       // linearise (iteration 0 includes k_prepare)
+    cudaEventElapsedTime(&ms, h->ev[b], h->ev[b + 1]); h->timing[2] += ms;       // solve
+    if (!only_linearize) { cudaEventElapsedTime(&ms, h->ev[b + 1], h->ev[b + 3]); h->timing[3] += ms; }
+  }
+  h->timing[4] = 1 + iters * per; h->timing[5] = iters;
+  cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]); h->timing[6] = ms;  // k_prepare
+  if (summaries) for (int w = 0; w < n; w++) {
+    const WinState& s = h->h_state[w];
+    summaries[w].initial_cost = s.initial_cost; summaries[w].final_cost = s.x_cost; summaries[w].iterations = s.iteration;
+    summaries[w].successful_steps = s.successful + 1; summaries[w].termination = s.termination; summaries[w].pad_ = 0;
+  }
+  return GF2_OK;
+}
+
+int gf2_solve(gf2_solver* h, int first, int n, const gf2_solve_opts* opts, gf2_solve_summary* summaries) {
+  if (!opts) return gf2::fail(GF2_ERR_INVALID, "null options");
+  return run(h, first, n, opts, summaries, opts->max_iterations, false);
+}
+
+int gf2_linearize(gf2_solver* h, int first, int n, const gf2_solve_opts* opts) {
+  if (!h) return gf2::fail(GF2_ERR_INVALID, "null handle");
+  if (!h->kp.Sfull) {
+    int rc = dalloc<double>(h, &h->kp.Sfull, (size_t)h->cfg.max_windows * h->D * h->D); if (rc) return rc;
+    rc = dalloc<double>(h, &h->kp.gfull, (size_t)h->cfg.max_windows * h->D); if (rc) return rc;
+  }
+  return run(h, first, n, opts, nullptr, 1, true);
+}
+
+int gf2_reduced_dim(gf2_solver* h, const gf2_solve_opts* opts) { (void)opts; return h ? h->D : gf2::fail(GF2_ERR_INVALID, "null handle"); }
+
+int gf2_get_reduced_system(gf2_solver* h, int first, int n, double* S, double* g, double* cost) {
+  GF2_TRY(check_range(h, first, n));
+  if (!h->kp.Sfull) return gf2::fail(GF2_ERR_INVALID, "gf2_linearize has not been called");
+  const int D = h->D;
+  D2H(S, h->kp.Sfull + (size_t)first * D * D, sizeof(double) * n * D * D);
+  D2H(g, h->kp.gfull + (size_t)first * D, sizeof(double) * n * D);
+  GF2_CUDA(cudaMemcpyAsync(h->h_state, h->kp.st + first, sizeof(WinState) * n, cudaMemcpyDeviceToHost, h->stream));
+  GF2_CUDA(cudaStreamSynchronize(h->stream));
+  if (cost) for (int w = 0; w < n; w++) cost[w] = h->h_state[w].x_cost;
+  return GF2_OK;
+}
+
+int gf2_get_states(gf2_solver* h, int first, int n, double* para_pose, double* para_speedbias, double* ex_pose, double* td,
+                   double* ex_pose_wheel, double* sxsysw, double* td_wheel) {
+  GF2_TRY(check_range(h, first, n));
+  const KP& k = h->kp; const int F = k.F;
+  D2H(para_pose, k.pose + (size_t)first * F * 7, sizeof(double) * n * F * 7);
+  D2H(para_speedbias, k.sb + (size_t)first * F * 9, sizeof(double) * n * F * 9);
+  D2H(ex_pose, k.ex + (size_t)first * 7, sizeof(double) * n * 7);
+  D2H(td, k.td + first, sizeof(double) * n);
+  if (h->cfg.use_wheel) {
+    D2H(ex_pose_wheel, k.exw + (size_t)first * 7, sizeof(double) * n * 7);
+    D2H(sxsysw, k.sxw + (size_t)first * 3, sizeof(double) * n * 3);
+    D2H(td_wheel, k.tdw + first, sizeof(double) * n);
+  }
+  GF2_CUDA(cudaStreamSynchronize(h->stream));
+  return GF2_OK;
+}
+
+int gf2_get_landmarks(gf2_solver* h, int first, int n, double* inv_depth) {
+  GF2_TRY(check_range(h, first, n));
+  D2H(inv_depth, h->kp.invdep + (size_t)first * h->kp.Lm, sizeof(double) * n * h->kp.Lm);
+  GF2_CUDA(cudaStreamSynchronize(h->stream));
+  return GF2_OK;
+}
+
+int gf2_comm_init(gf2_solver* h, int rank, int nranks, const void* nccl_unique_id) {
+  (void)h; (void)rank; (void)nranks; (void)nccl_unique_id;
+  return gf2::fail(GF2_ERR_UNSUPPORTED, "factor-sharded mode is not built yet");
+}
+int gf2_comm_unique_id(void* out) { (void)out; return gf2::fail(GF2_ERR_UNSUPPORTED, "factor-sharded mode is not built yet"); }
+
+int gf2_last_timing(gf2_solver* h, double out[8]) {
+  if (!h || !out) return gf2::fail(GF2_ERR_INVALID, "null argument");
+  memcpy(out, h->timing, sizeof(h->timing));
+  return GF2_OK;
+}
+
+}  // extern "C"

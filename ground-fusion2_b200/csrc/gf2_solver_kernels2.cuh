@@ -1,0 +1,538 @@
+// gf2_solver_kernels2.cuh — k_solve (assembly + Cholesky + Gauss-Newton step), k_backsub, k_candidate.
+#pragma once
+#include "gf2_solver_kernels.cuh"
+
+namespace gf2 {
+
+// ------------------------------------------------------------------------------------------------ IMU factor
+struct ImuStates { V3 Pi, Vi, Bai, Bgi, Pj, Vj, Baj, Bgj; Q4 Qi, Qj; };
+
+__device__ __forceinline__ ImuStates load_imu_states(const double* pose, const double* sb, int i) {
+  ImuStates s;
+  const double* pi = pose + 7 * i; const double* pj = pose + 7 * (i + 1);
+  const double* si = sb + 9 * i; const double* sj = sb + 9 * (i + 1);
+  s.Pi = ld3(pi); s.Qi = ldq(pi + 3); s.Pj = ld3(pj); s.Qj = ldq(pj + 3);
+  s.Vi = ld3(si); s.Bai = ld3(si + 3); s.Bgi = ld3(si + 6); s.Vj = ld3(sj); s.Baj = ld3(sj + 3); s.Bgj = ld3(sj + 6);
+  return s;
+}
+__device__ __forceinline__ M3 blk3(const double* J15, int r0, int c0) {
+  M3 m;
+#pragma unroll
+  for (int r = 0; r < 3; r++)
+#pragma unroll
+    for (int c = 0; c < 3; c++) m.m[r * 3 + c] = J15[(r0 + r) * 15 + c0 + c];
+  return m;
+}
+__device__ __forceinline__ void put3(double* J, int ld, int r0, int c0, const M3& m, double sgn) {
+#pragma unroll
+  for (int r = 0; r < 3; r++)
+#pragma unroll
+    for (int c = 0; c < 3; c++) J[(r0 + r) * ld + c0 + c] = sgn * m.m[r * 3 + c];
+}
+
+// IntegrationBase::evaluate (VE/factor/integration_base.h:169-195): raw 15-residual; optionally the raw 15x30 Jacobian of
+// IMUFactor::Evaluate (VE/factor/imu_factor.h:98-187) in tangent columns [pose_i 6 | sb_i 9 | pose_j 6 | sb_j 9].
+__device__ void imu_raw(const gf2_imu_preint& pre, const ImuStates& s, double g_norm, double* r /*15*/, double* J /*15x30 or null*/) {
+  const V3 G = mk3(0, 0, g_norm);
+  const double dt = pre.sum_dt;
+  const M3 dp_dba = blk3(pre.jacobian, 0, 9), dp_dbg = blk3(pre.jacobian, 0, 12), dq_dbg = blk3(pre.jacobian, 3, 12);
+  const M3 dv_dba = blk3(pre.jacobian, 6, 9), dv_dbg = blk3(pre.jacobian, 6, 12);
+  const V3 dba = s.Bai - ld3(pre.lin_ba), dbg = s.Bgi - ld3(pre.lin_bg);
+  const Q4 dq = ldq(pre.delta_q);
+  const Q4 cdq = qmul(dq, deltaQ(mul(dq_dbg, dbg)));
+  const V3 cdv = ld3(pre.delta_v) + mul(dv_dba, dba) + mul(dv_dbg, dbg);
+  const V3 cdp = ld3(pre.delta_p) + mul(dp_dba, dba) + mul(dp_dbg, dbg);
+  const Q4 QiInv = qinv(s.Qi);
+  const V3 tp = 0.5 * dt * dt * G + s.Pj - s.Pi - dt * s.Vi;
+  const V3 tv = dt * G + s.Vj - s.Vi;
+  const V3 a_p = qrot(QiInv, tp), a_v = qrot(QiInv, tv);
+  const V3 rp = a_p - cdp;
+  const V3 rq = 2.0 * qvec(qmul(qinv(cdq), qmul(QiInv, s.Qj)));
+  const V3 rv = a_v - cdv;
+  const V3 rba = s.Baj - s.Bai, rbg = s.Bgj - s.Bgi;
+  r[0] = rp.x; r[1] = rp.y; r[2] = rp.z; r[3] = rq.x; r[4] = rq.y; r[5] = rq.z; r[6] = rv.x; r[7] = rv.y; r[8] = rv.z;
+  r[9] = rba.x; r[10] = rba.y; r[11] = rba.z; r[12] = rbg.x; r[13] = rbg.y; r[14] = rbg.z;
+  if (!J) return;
+  for (int i = 0; i < 450; i++) J[i] = 0.0;
+  const M3 RiT = toR(QiInv);
+  const Q4 QjInv = qinv(s.Qj);
+  // pose_i (cols 0..5)
+  put3(J, 30, 0, 0, RiT, -1.0);
+  put3(J, 30, 0, 3, skew(a_p), 1.0);
+  put3(J, 30, 3, 3, QleftQrightBR(qmul(QjInv, s.Qi), cdq), -1.0);
+  put3(J, 30, 6, 3, skew(a_v), 1.0);
+  // speed-bias_i (cols 6..14): V 6..8, BA 9..11, BG 12..14
+  put3(J, 30, 0, 6, RiT, -dt);
+  put3(J, 30, 0, 9, dp_dba, -1.0);
+  put3(J, 30, 0, 12, dp_dbg, -1.0);
+  put3(J, 30, 3, 12, mul(QleftBR(qmul(qmul(QjInv, s.Qi), dq)), dq_dbg), -1.0);  // uncorrected delta_q, imu_factor.h:137
+  put3(J, 30, 6, 6, RiT, -1.0);
+  put3(J, 30, 6, 9, dv_dba, -1.0);
+  put3(J, 30, 6, 12, dv_dbg, -1.0);
+  put3(J, 30, 9, 9, eye3(), -1.0);
+  put3(J, 30, 12, 12, eye3(), -1.0);
+  // pose_j (cols 15..20)
+  put3(J, 30, 0, 15, RiT, 1.0);
+  put3(J, 30, 3, 18, QleftBR(qmul(qinv(cdq), qmul(QiInv, s.Qj))), 1.0);
+  // speed-bias_j (cols 21..29)
+  put3(J, 30, 6, 21, RiT, 1.0);
+  put3(J, 30, 9, 24, eye3(), 1.0);
+  put3(J, 30, 12, 27, eye3(), 1.0);
+}
+
+// 0.5 * |sqrt_info * r|^2 by one thread
+__device__ __forceinline__ double imu_cost(const double* sq /*15x15 upper*/, const double* r) {
+  double c = 0;
+  for (int a = 0; a < 15; a++) { double s = 0; for (int k = a; k < 15; k++) s += sq[a * 15 + k] * r[k]; c += s * s; }
+  return 0.5 * c;
+}
+
+// MarginalizationFactor::Evaluate's dx (VE/factor/marginalization_factor.cpp:356-374) for one kept block
+__device__ __forceinline__ void prior_block_dx(const gf2_prior_block& b, const double* pose, const double* sb, double* dx /* at offset */) {
+  if (b.kind == GF2_BLK_POSE) {
+    const double* x = pose + 7 * b.index;
+    for (int k = 0; k < 3; k++) dx[b.offset + k] = x[k] - b.x0[k];
+    Q4 q0 = ldq(b.x0 + 3), q = ldq(x + 3);
+    Q4 dq = qmul(qinv(q0), q);
+    V3 v = 2.0 * qvec(dq);
+    if (!(dq.w >= 0)) v = -v;
+    dx[b.offset + 3] = v.x; dx[b.offset + 4] = v.y; dx[b.offset + 5] = v.z;
+  } else if (b.kind == GF2_BLK_SPEEDBIAS) {
+    const double* x = sb + 9 * b.index;
+    for (int k = 0; k < 9; k++) dx[b.offset + k] = x[k] - b.x0[k];
+  } else {
+    // calibration blocks are constant in this build: x == x0 is not guaranteed, but they do not move during the solve,
+    // so their dx contribution is folded in by the caller through r0 (see gf2_set_prior) -> 0 here
+    const int ls = (b.kind == GF2_BLK_EX_POSE || b.kind == GF2_BLK_EX_WHEEL) ? 6 : 1;
+    for (int k = 0; k < ls; k++) dx[b.offset + k] = 0.0;
+  }
+}
+
+__device__ __forceinline__ int pidx(int i, int j) { return i * (i + 1) / 2 + j; }  // packed lower, j <= i
+
+// ------------------------------------------------------------------------------------------------ k_solve
+struct SolveShared {
+  double g[kMaxF * 15], Hd[kMaxF * 15], s[kMaxF * 15], e[kMaxF * 15], u[kMaxF * 15], z[kMaxF * 15], tmp[kMaxF * 15];
+  double dx[kP], pr[kP];
+  double red[8 * 32];
+  double imu_scratch[8][480];
+  int flag;
+  double Lp[1];  // packed lower D(D+1)/2, dynamic tail
+};
+
+__global__ void __launch_bounds__(kSolveThreads, 1) k_solve(KP p, int w0) {
+  const int w = w0 + blockIdx.x;
+  WinState& st = p.st[w];
+  if (!st.active || st.reuse) return;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SolveShared& S = *reinterpret_cast<SolveShared*>(smem_raw);
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5, nt = blockDim.x;
+  const int F = p.F, D = p.D, NV = 6 * F;
+  const int NP = D * (D + 1) / 2;
+  const double* pose = p.pose + (size_t)w * F * 7;
+  const double* sb = p.sb + (size_t)w * F * 9;
+  double* Lp = S.Lp;
+  for (int i = t; i < NP; i += nt) Lp[i] = 0.0;
+  for (int i = t; i < D; i += nt) { S.g[i] = 0.0; S.Hd[i] = 0.0; }
+  __syncthreads();
+  // visual part
+  const double* Svis = p.Svis + (size_t)w * kNVMax * kNVMax;
+  for (int idx = t; idx < NV * NV; idx += nt) {
+    const int a = idx / NV, b = idx % NV;
+    if (b > a) continue;
+    const int da = 15 * (a / 6) + a % 6, db = 15 * (b / 6) + b % 6;
+    Lp[pidx(da, db)] = Svis[a * kNVMax + b];
+  }
+  if (t < NV) { const int da = 15 * (t / 6) + t % 6; S.g[da] = p.gvis[(size_t)w * kNVP + t]; S.Hd[da] = p.Udiag[(size_t)w * kNVMax + t]; }
+  double cost = 0.0;  // thread-local partial of the non-visual cost
+  __syncthreads();
+  // prior
+  const int n = p.prior_rows ? p.prior_rows[w] : 0;
+  if (n > 0) {
+    const gf2_prior_block* blk = p.prior_blocks + (size_t)w * (2 * F + 8);
+    const int nb = p.prior_nblocks[w];
+    if (t < nb) prior_block_dx(blk[t], pose, sb, S.dx);
+    __syncthreads();
+    const double* J0 = p.prior_J0 + (size_t)w * kP * kP;
+    const double* r0 = p.prior_r0 + (size_t)w * kP;
+    if (t < n) { double s2 = r0[t]; for (int c = 0; c < n; c++) s2 += J0[t * kP + c] * S.dx[c]; S.pr[t] = s2; cost += 0.5 * s2 * s2; }
+    __syncthreads();
+    const int32_t* map = p.prior_map + (size_t)w * kP;
+    const double* H = p.prior_H + (size_t)w * kP * kP;
+    if (t < n && map[t] >= 0) { double s2 = 0; for (int r = 0; r < n; r++) s2 += J0[r * kP + t] * S.pr[r]; S.g[map[t]] += s2; S.Hd[map[t]] += H[t * kP + t]; }
+    for (int idx = t; idx < n * n; idx += nt) {
+      const int a = idx / n, b = idx % n;
+      const int ma = map[a], mb = map[b];
+      if (ma < 0 || mb < 0 || mb > ma) continue;
+      Lp[pidx(ma, mb)] += H[a * kP + b];
+    }
+    __syncthreads();
+  }
+  // IMU factors: even then odd (neighbouring factors share frame i+1's block)
+  if (p.imu) {
+    for (int phase = 0; phase < 2; phase++) {
+      for (int k = 2 * wid + phase; k < F - 1; k += 2 * (nt >> 5)) {
+        const gf2_imu_preint& pre = p.imu[(size_t)w * (F - 1) + k];
+        if (!pre.valid || pre.sum_dt > 10.0) continue;
+        double* J = S.imu_scratch[wid];
+        double* r = J + 450;
+        if (lane == 0) { ImuStates s2 = load_imu_states(pose, sb, k); imu_raw(pre, s2, p.g_norm, r, J); }
+        __syncwarp();
+        const double* sq = p.imu_sqrt + ((size_t)w * (F - 1) + k) * 225;
+        // J <- sqrt_info * J (upper triangular, in place row by row), r likewise
+        if (lane < 30) {
+          for (int a = 0; a < 15; a++) { double acc = 0; for (int kk = a; kk < 15; kk++) acc += sq[a * 15 + kk] * J[kk * 30 + lane]; J[a * 30 + lane] = acc; }
+        } else if (lane == 30) {
+          for (int a = 0; a < 15; a++) { double acc = 0; for (int kk = a; kk < 15; kk++) acc += sq[a * 15 + kk] * r[kk]; r[a] = acc; }
+        }
+        __syncwarp();
+        if (lane == 0) { double c = 0; for (int a = 0; a < 15; a++) c += r[a] * r[a]; cost += 0.5 * c; }
+        const int base = 15 * k;
+        for (int idx = lane; idx < 30 * 31 / 2; idx += 32) {
+          // idx -> (a >= b)
+          int a = (int)((sqrt(8.0 * idx + 1.0) - 1.0) * 0.5); while (a * (a + 1) / 2 > idx) a--; while ((a + 1) * (a + 2) / 2 <= idx) a++;
+          const int b = idx - a * (a + 1) / 2;
+          double acc = 0; for (int rr = 0; rr < 15; rr++) acc += J[rr * 30 + a] * J[rr * 30 + b];
+          Lp[pidx(base + a, base + b)] += acc;
+          if (a == b) S.Hd[base + a] += acc;
+        }
+        if (lane < 30) { double acc = 0; for (int rr = 0; rr < 15; rr++) acc += J[rr * 30 + lane] * r[rr]; S.g[base + lane] += acc; }
+        __syncwarp();
+      }
+      __syncthreads();
+    }
+  }
+  // total cost of the linearisation point
+  {
+    double v1[1] = {cost};
+    block_sum<1>(v1, S.red);
+    if (t == 0) { st.x_cost = v1[0] + st.cost_vis; if (st.iteration == 0) st.initial_cost = st.x_cost; }
+  }
+  // optional dump of the assembled (unregularised) reduced system
+  if (p.Sfull) {
+    double* Sf = p.Sfull + (size_t)w * D * D;
+    for (int idx = t; idx < D * D; idx += nt) { const int a = idx / D, b = idx % D; Sf[idx] = a >= b ? Lp[pidx(a, b)] : Lp[pidx(b, a)]; }
+    for (int i = t; i < D; i += nt) p.gfull[(size_t)w * D + i] = S.g[i];
+  }
+  // Jacobi scaling (iteration 0), dogleg diagonal, gradient quantities
+  const double mu = st.mu;
+  double sums[6] = {0, 0, 0, 0, 0, 0};  // dlg2, uEu, gmax(as max), -, -, -
+  double gmax = 0.0;
+  for (int i = t; i < D; i += nt) {
+    double sc;
+    if (st.iteration == 0) { sc = 1.0 / (1.0 + sqrt(S.Hd[i])); p.sx[(size_t)w * D + i] = sc; } else sc = p.sx[(size_t)w * D + i];
+    const double d2 = fmin(fmax(sc * sc * S.Hd[i], 1e-6), 1e32);
+    const double e = d2 / (sc * sc);
+    const double u = sc * sc * S.g[i] / d2;
+    S.s[i] = sc; S.e[i] = e; S.u[i] = u;
+    sums[0] += sc * sc * S.g[i] * S.g[i] / d2;
+    sums[1] += e * u * u;
+  }
+  // gradient_max_norm = |x - Plus(x, -g)|_inf  (TrustRegionMinimizer::EvaluateGradientAndJacobian)
+  if (t < F) {
+    const double* x = pose + 7 * t; const double* gg = &S.g[15 * t];
+    for (int k = 0; k < 3; k++) gmax = fmax(gmax, fabs(gg[k]));
+    Q4 q = ldq(x + 3); Q4 qn = qnormalized(qmul(q, deltaQ(mk3(-gg[3], -gg[4], -gg[5]))));
+    gmax = fmax(gmax, fmax(fmax(fabs(q.x - qn.x), fabs(q.y - qn.y)), fmax(fabs(q.z - qn.z), fabs(q.w - qn.w))));
+    for (int k = 6; k < 15; k++) gmax = fmax(gmax, fabs(gg[k]));
+  }
+  __syncthreads();
+  // S' = S + mu * E ; t = u^T S' u
+  for (int i = t; i < D; i += nt) Lp[pidx(i, i)] += mu * S.e[i];
+  __syncthreads();
+  double uSu = 0.0;
+  for (int i = t; i < D; i += nt) {
+    double acc = 0;
+    for (int j = 0; j <= i; j++) acc += Lp[pidx(i, j)] * S.u[j];
+    for (int j = i + 1; j < D; j++) acc += Lp[pidx(j, i)] * S.u[j];
+    uSu += acc * S.u[i];
+  }
+  sums[2] = uSu;
+  block_sum<6>(sums, S.red);
+  gmax = warp_max(gmax);
+  if (lane == 0) S.red[wid] = gmax;
+  __syncthreads();
+  if (t == 0) {
+    double gm = 0; for (int i = 0; i < (nt >> 5); i++) gm = fmax(gm, S.red[i]);
+    st.dlg2_x = sums[0]; st.uEu_x = sums[1]; st.uSu = sums[2]; st.gmax_x = gm;
+    S.flag = 0;
+    // FinalizeIterationAndCheckIfMinimizerCanContinue: gradient tolerance (checked after a successful step / iteration 0)
+    if (fmax(gm, st.gmax_l) <= p.gtol) { st.active = 0; st.termination = GF2_TERM_GRADIENT_TOL; S.flag = 2; }
+  }
+  __syncthreads();
+  if (S.flag == 2) return;
+  // Cholesky (right-looking, packed lower)
+  for (int j = 0; j < D; j++) {
+    if (t == 0) { const double d = Lp[pidx(j, j)]; if (!(d > 0.0)) S.flag = 1; else Lp[pidx(j, j)] = sqrt(d); }
+    __syncthreads();
+    if (S.flag) break;
+    const double dj = Lp[pidx(j, j)];
+    for (int i = j + 1 + t; i < D; i += nt) Lp[pidx(i, j)] /= dj;
+    __syncthreads();
+    for (int i = j + 1 + t; i < D; i += nt) {
+      const double lij = Lp[pidx(i, j)];
+      double* row = &Lp[pidx(i, 0)];
+      for (int k = j + 1; k <= i; k++) row[k] -= lij * Lp[pidx(k, j)];
+    }
+    __syncthreads();
+  }
+  if (S.flag == 1) {  // LINEAR_SOLVER_FAILURE: treated as an invalid step (mu *= 10, re-linearise); see DESIGN.md deviations
+    if (t == 0) {
+      st.mu *= 10.0; st.reuse = 0; st.iteration++; st.invalid_count++;
+      if (st.invalid_count >= 5 || st.mu >= 1.0) { st.active = 0; st.termination = GF2_TERM_FAILURE; }
+      else if (st.iteration >= p.max_iterations) { st.active = 0; st.termination = GF2_TERM_NO_CONVERGENCE; }
+      st.lin_valid = 0;
+    }
+    return;
+  }
+  // z = S'^-1 g  (forward, backward)
+  for (int i = t; i < D; i += nt) S.z[i] = S.g[i];
+  __syncthreads();
+  for (int j = 0; j < D; j++) {
+    if (t == 0) S.z[j] /= Lp[pidx(j, j)];
+    __syncthreads();
+    const double zj = S.z[j];
+    for (int i = j + 1 + t; i < D; i += nt) S.z[i] -= Lp[pidx(i, j)] * zj;
+    __syncthreads();
+  }
+  for (int j = D - 1; j >= 0; j--) {
+    if (t == 0) S.z[j] /= Lp[pidx(j, j)];
+    __syncthreads();
+    const double zj = S.z[j];
+    for (int i = t; i < j; i += nt) S.z[i] -= Lp[pidx(j, i)] * zj;
+    __syncthreads();
+  }
+  double s2[4] = {0, 0, 0, 0};  // gn2, gz, zEz, uEz
+  for (int i = t; i < D; i += nt) {
+    const double z = S.z[i], sc = S.s[i], e = S.e[i];
+    const double d2 = e * sc * sc;
+    s2[0] += d2 * z * z / (sc * sc);
+    s2[1] += S.g[i] * z;
+    s2[2] += e * z * z;
+    s2[3] += e * S.u[i] * z;
+    p.zx[(size_t)w * D + i] = z; p.ux[(size_t)w * D + i] = S.u[i]; p.ex_diag[(size_t)w * D + i] = e;
+  }
+  block_sum<4>(s2, S.red);
+  if (t == 0) { st.gn2_x = s2[0]; st.gz_x = s2[1]; st.zEz_x = s2[2]; st.uEz_x = s2[3]; st.lin_valid = 1; }
+}
+
+// ------------------------------------------------------------------------------------------------ k_backsub
+// sweep 2: z_l = (g_l - w_l^T z_x) / v'_l and the landmark parts of the dogleg dot products.
+struct StepShared {
+  FrameCtx fr[kMaxF];
+  CamCtx cam;
+  double zx[kNVMax], ux[kNVMax];
+  double red[8 * 32];
+  double dx[kP];
+  int decision;
+};
+
+__global__ void __launch_bounds__(256, 2) k_backsub(KP p, int w0) {
+  const int w = w0 + blockIdx.x;
+  WinState& st = p.st[w];
+  if (!st.active || st.reuse || !st.lin_valid) return;
+  __shared__ StepShared S;
+  const int t = threadIdx.x, F = p.F, D = p.D, NV = 6 * F;
+  build_frames(p.pose + (size_t)w * F * 7, p.ex + (size_t)w * 7, p.td[w], F, S.fr, &S.cam);
+  if (t < NV) { const int d = 15 * (t / 6) + t % 6; S.zx[t] = p.zx[(size_t)w * D + d]; S.ux[t] = p.ux[(size_t)w * D + d]; }
+  __syncthreads();
+  const int nlm = p.nlm[w];
+  const int32_t* start = p.start + (size_t)w * p.Lm; const int32_t* tlen = p.tlen + (size_t)w * p.Lm; const int32_t* obeg = p.obeg + (size_t)w * p.Lm;
+  const float4* obs = p.obs + (size_t)w * p.Om;
+  const double* ftd = p.frame_td + (size_t)w * F;
+  const double mu = st.mu;
+  double sums[6] = {0, 0, 0, 0, 0, 0};  // dlg2, gn2, gz, zEz, uEz, uHu
+  for (int l = t; l < nlm; l += blockDim.x) {
+    const double v = p.lm_v[(size_t)w * p.Lm + l];
+    if (!(v > 0.0)) { p.lm_z[(size_t)w * p.Lm + l] = 0.0; continue; }  // fixed or unobserved landmark
+    const double gl = p.lm_g[(size_t)w * p.Lm + l], s_l = p.lm_s[(size_t)w * p.Lm + l];
+    const int i = start[l], L = tlen[l], ob = obeg[l];
+    LmCtx lc; landmark_ctx(S.fr[i], S.cam, obs[ob], ftd[i], p.invdep[(size_t)w * p.Lm + l], lc);
+    double az = 0.0, cu = 0.0;  // w_l^T z_x, w_l^T u_x
+    for (int k = 1; k < L; k++) {
+      const int j = i + k;
+      double r0, r1, Jx[6], Jj[12]; V3 pcj;
+      obs_residual(S.fr[j], S.cam, lc, obs[ob + k], ftd[j], p.sqrt_info_px, r0, r1, pcj);
+      obs_jacobians(S.fr[j], S.cam, lc, pcj, p.sqrt_info_px, Jx, Jj);
+      double hr, sc; huber(p.huber, r0 * r0 + r1 * r1, hr, sc);
+      const double jl0 = sc * (Jx[0] * lc.dXdl.x + Jx[1] * lc.dXdl.y + Jx[2] * lc.dXdl.z);
+      const double jl1 = sc * (Jx[3] * lc.dXdl.x + Jx[4] * lc.dXdl.y + Jx[5] * lc.dXdl.z);
+#pragma unroll
+      for (int r = 0; r < 2; r++) {
+        const double jl = r == 0 ? jl0 : jl1;
+        double tz = 0, tu = 0;
+        // J_i * [z_i] with Ji = [Jx | Jx Gi]
+        double zi[6], ui[6];
+#pragma unroll
+        for (int c = 0; c < 6; c++) { zi[c] = S.zx[6 * i + c]; ui[c] = S.ux[6 * i + c]; }
+        const V3 gz3 = mul(lc.Gi, mk3(zi[3], zi[4], zi[5])), gu3 = mul(lc.Gi, mk3(ui[3], ui[4], ui[5]));
+        tz += Jx[r * 3] * (zi[0] + gz3.x) + Jx[r * 3 + 1] * (zi[1] + gz3.y) + Jx[r * 3 + 2] * (zi[2] + gz3.z);
+        tu += Jx[r * 3] * (ui[0] + gu3.x) + Jx[r * 3 + 1] * (ui[1] + gu3.y) + Jx[r * 3 + 2] * (ui[2] + gu3.z);
+#pragma unroll
+        for (int c = 0; c < 6; c++) { tz += Jj[r * 6 + c] * S.zx[6 * j + c]; tu += Jj[r * 6 + c] * S.ux[6 * j + c]; }
+        az += sc * jl * tz; cu += sc * jl * tu;
+      }
+    }
+    const double d2 = fmin(fmax(s_l * s_l * v, 1e-6), 1e32);
+    const double e = d2 / (s_l * s_l);
+    const double vp = v + mu * e;
+    const double u = s_l * s_l * gl / d2;
+    const double z = (gl - az) / vp;
+    p.lm_z[(size_t)w * p.Lm + l] = z;
+    sums[0] += s_l * s_l * gl * gl / d2;
+    sums[1] += d2 * z * z / (s_l * s_l);
+    sums[2] += gl * z;
+    sums[3] += e * z * z;
+    sums[4] += e * u * z;
+    sums[5] += cu * cu / vp + 2.0 * u * cu + v * u * u;
+  }
+  block_sum<6>(sums, S.red);
+  if (t == 0) { st.dlg2_l = sums[0]; st.gn2_l = sums[1]; st.gz_l = sums[2]; st.zEz_l = sums[3]; st.uEz_l = sums[4]; st.uHu_l = sums[5]; }
+}
+
+// ------------------------------------------------------------------------------------------------ k_candidate
+// DoglegStrategy::ComputeTraditionalDoglegStep + candidate evaluation + step acceptance.
+__device__ void dogleg_coefficients(WinState& st) {
+  const double dlg2 = st.dlg2_x + st.dlg2_l, gn2 = st.gn2_x + st.gn2_l, gz = st.gz_x + st.gz_l;
+  const double uHu = st.uSu - st.mu * st.uEu_x + st.uHu_l;
+  const double alpha = dlg2 / uHu;
+  const double gradient_norm = sqrt(dlg2), gn_norm = sqrt(gn2), radius = st.radius;
+  double a, b, nrm;
+  if (gn_norm <= radius) { a = 0.0; b = 1.0; nrm = gn_norm; }
+  else if (gradient_norm * alpha >= radius) { a = radius / gradient_norm; b = 0.0; nrm = radius; }
+  else {
+    const double b_dot_a = alpha * gz;  // -alpha * dot(gradient_, gauss_newton_step_), dot = -g^T z
+    const double a_sq = (alpha * gradient_norm) * (alpha * gradient_norm);
+    const double bma = a_sq - 2 * b_dot_a + gn2;
+    const double c = b_dot_a - a_sq;
+    const double d = sqrt(c * c + bma * (radius * radius - a_sq));
+    const double beta = (c <= 0) ? (d - c) / bma : (radius * radius - a_sq) / (d + c);
+    a = alpha * (1.0 - beta); b = beta;
+    nrm = sqrt(a * a * dlg2 + 2 * a * b * gz + b * b * gn2);
+  }
+  st.coef_a = a; st.coef_b = b; st.dogleg_step_norm = nrm;
+  // model_cost_change = -(J delta)^T (r + J delta / 2), delta = -(a u + b z)
+  const double uEz = st.uEz_x + st.uEz_l, zEz = st.zEz_x + st.zEz_l;
+  const double uHz = dlg2 - st.mu * uEz, zHz = gz - st.mu * zEz;
+  st.model_cost_change = a * dlg2 + b * gz - 0.5 * (a * a * uHu + 2 * a * b * uHz + b * b * zHz);
+}
+
+__global__ void __launch_bounds__(256, 2) k_candidate(KP p, int w0) {
+  const int w = w0 + blockIdx.x;
+  WinState& st = p.st[w];
+  if (!st.active) return;
+  if (!st.lin_valid) return;  // invalid linear solve already handled in k_solve
+  __shared__ StepShared S;
+  const int t = threadIdx.x, F = p.F, D = p.D;
+  if (t == 0) dogleg_coefficients(st);
+  __syncthreads();
+  const double a = st.coef_a, b = st.coef_b;
+  const double* pose = p.pose + (size_t)w * F * 7; const double* sb = p.sb + (size_t)w * F * 9;
+  double* pose_c = p.pose_c + (size_t)w * F * 7; double* sb_c = p.sb_c + (size_t)w * F * 9;
+  double acc[3] = {0, 0, 0};  // candidate cost, |x - cand|^2, |x|^2
+  // retraction of frame states: PoseLocalParameterization::Plus (VE/factor/pose_local_parameterization.cpp:12-28)
+  if (t < F) {
+    const double* zx = p.zx + (size_t)w * D + 15 * t; const double* ux = p.ux + (size_t)w * D + 15 * t;
+    double dl[15];
+    for (int k = 0; k < 15; k++) dl[k] = -(a * ux[k] + b * zx[k]);
+    const double* x = pose + 7 * t; double* xc = pose_c + 7 * t;
+    for (int k = 0; k < 3; k++) { xc[k] = x[k] + dl[k]; acc[1] += dl[k] * dl[k]; acc[2] += x[k] * x[k]; }
+    Q4 q = ldq(x + 3); Q4 qn = qnormalized(qmul(q, deltaQ(mk3(dl[3], dl[4], dl[5]))));
+    xc[3] = qn.x; xc[4] = qn.y; xc[5] = qn.z; xc[6] = qn.w;
+    acc[1] += (q.x - qn.x) * (q.x - qn.x) + (q.y - qn.y) * (q.y - qn.y) + (q.z - qn.z) * (q.z - qn.z) + (q.w - qn.w) * (q.w - qn.w);
+    acc[2] += q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w;
+    const double* v = sb + 9 * t; double* vc = sb_c + 9 * t;
+    for (int k = 0; k < 9; k++) { vc[k] = v[k] + dl[6 + k]; acc[1] += dl[6 + k] * dl[6 + k]; acc[2] += v[k] * v[k]; }
+  }
+  __syncthreads();
+  build_frames(pose_c, p.ex + (size_t)w * 7, p.td[w], F, S.fr, &S.cam);
+  __syncthreads();
+  const int nlm = p.nlm[w];
+  const int32_t* start = p.start + (size_t)w * p.Lm; const int32_t* tlen = p.tlen + (size_t)w * p.Lm; const int32_t* obeg = p.obeg + (size_t)w * p.Lm;
+  const float4* obs = p.obs + (size_t)w * p.Om;
+  const double* ftd = p.frame_td + (size_t)w * F;
+  for (int l = t; l < nlm; l += blockDim.x) {
+    const double v = p.lm_v[(size_t)w * p.Lm + l];
+    const double lam = p.invdep[(size_t)w * p.Lm + l];
+    double lam_c = lam;
+    if (v > 0.0) {
+      const double gl = p.lm_g[(size_t)w * p.Lm + l], s_l = p.lm_s[(size_t)w * p.Lm + l];
+      const double d2 = fmin(fmax(s_l * s_l * v, 1e-6), 1e32);
+      const double u = s_l * s_l * gl / d2;
+      const double dl = -(a * u + b * p.lm_z[(size_t)w * p.Lm + l]);
+      lam_c = lam + dl;
+      acc[1] += dl * dl; acc[2] += lam * lam;
+    }
+    p.invdep_c[(size_t)w * p.Lm + l] = lam_c;
+    const int i = start[l], L = tlen[l], ob = obeg[l];
+    LmCtx lc; landmark_ctx(S.fr[i], S.cam, obs[ob], ftd[i], lam_c, lc);
+    for (int k = 1; k < L; k++) {
+      double r0, r1; V3 pcj;
+      obs_residual(S.fr[i + k], S.cam, lc, obs[ob + k], ftd[i + k], p.sqrt_info_px, r0, r1, pcj);
+      double hr, sc; huber(p.huber, r0 * r0 + r1 * r1, hr, sc);
+      acc[0] += hr;
+    }
+  }
+  // IMU factors at the candidate
+  if (p.imu && t < F - 1) {
+    const gf2_imu_preint& pre = p.imu[(size_t)w * (F - 1) + t];
+    if (pre.valid && pre.sum_dt <= 10.0) {
+      double r[15]; ImuStates s2 = load_imu_states(pose_c, sb_c, t);
+      imu_raw(pre, s2, p.g_norm, r, nullptr);
+      acc[0] += imu_cost(p.imu_sqrt + ((size_t)w * (F - 1) + t) * 225, r);
+    }
+  }
+  // prior at the candidate
+  const int n = p.prior_rows ? p.prior_rows[w] : 0;
+  if (n > 0) {
+    const gf2_prior_block* blk = p.prior_blocks + (size_t)w * (2 * F + 8);
+    if (t < p.prior_nblocks[w]) prior_block_dx(blk[t], pose_c, sb_c, S.dx);
+    __syncthreads();
+    const double* J0 = p.prior_J0 + (size_t)w * kP * kP; const double* r0p = p.prior_r0 + (size_t)w * kP;
+    if (t < n) { double s2 = r0p[t]; for (int c = 0; c < n; c++) s2 += J0[t * kP + c] * S.dx[c]; acc[0] += 0.5 * s2 * s2; }
+  }
+  block_sum<3>(acc, S.red);
+  // TrustRegionMinimizer: tolerance checks, step acceptance, radius update
+  if (t == 0) {
+    int decision = 0;  // 0 reject, 1 accept, 2 terminated (no accept)
+    st.cand_cost = acc[0];
+    st.x_norm2 = acc[2];
+    st.iteration++;
+    if (!(st.model_cost_change > 0.0)) {  // HandleInvalidStep
+      st.invalid_count++;
+      st.mu *= 10.0; st.reuse = 0;
+      if (st.invalid_count >= 5) { st.active = 0; st.termination = GF2_TERM_FAILURE; }
+      decision = 2;
+    } else {
+      st.invalid_count = 0;
+      const double step_norm = sqrt(acc[1]), x_norm = sqrt(acc[2]);
+      const double cost_change = st.x_cost - st.cand_cost;
+      if (step_norm <= p.ptol * (x_norm + p.ptol)) { st.active = 0; st.termination = GF2_TERM_PARAMETER_TOL; decision = 2; }
+      else if (fabs(cost_change) <= p.ftol * st.x_cost) { st.active = 0; st.termination = GF2_TERM_FUNCTION_TOL; decision = 2; }
+      else {
+        const double rho = cost_change / st.model_cost_change;
+        if (rho > 1e-3) {
+          decision = 1; st.successful++;
+          if (rho < 0.25) st.radius *= 0.5;
+          if (rho > 0.75) st.radius = fmax(st.radius, 3.0 * st.dogleg_step_norm);
+          st.mu = fmax(1e-8, 2.0 * st.mu / 10.0);
+          st.reuse = 0; st.x_cost = st.cand_cost;
+        } else { st.radius *= 0.5; st.reuse = 1; }
+      }
+    }
+    if (st.active) {
+      if (st.iteration >= p.max_iterations) { st.active = 0; st.termination = GF2_TERM_NO_CONVERGENCE; }
+      else if (st.radius <= 1e-32) { st.active = 0; st.termination = GF2_TERM_MIN_RADIUS; }
+    }
+    S.decision = decision;
+  }
+  __syncthreads();
+  if (S.decision == 1) {  // x = candidate
+    double* poseW = p.pose + (size_t)w * F * 7; double* sbW = p.sb + (size_t)w * F * 9;
+    for (int i = t; i < F * 7; i += blockDim.x) poseW[i] = pose_c[i];
+    for (int i = t; i < F * 9; i += blockDim.x) sbW[i] = sb_c[i];
+    for (int l = t; l < nlm; l += blockDim.x) p.invdep[(size_t)w * p.Lm + l] = p.invdep_c[(size_t)w * p.Lm + l];
+  }
+}
+
+}  // namespace gf2

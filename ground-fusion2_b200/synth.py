@@ -77,7 +77,7 @@ def _heading_R(psi):
 
 def make_windows(n_windows, config_id=2, n_landmarks=1000, n_frames=11, wheel=False, n_planes=0, first_window=0,
                  sorted_landmarks=True, prior="anchor", speed=1.0, yaw_rate=0.2, frame_dt=0.1, imu_hz=200, wheel_hz=50,
-                 pixel_noise=0.5, max_landmarks=None, max_obs=None):
+                 pixel_noise=0.5, max_landmarks=None, max_obs=None, prior_weight=1.0):
     """Return a dict of window-major arrays for `n_windows` windows (W10-F1000 when n_landmarks = 1000).
 
     Landmark l starts in frame s_l = l mod 8 (track length n_frames - s_l, observed in every later frame). With
@@ -234,7 +234,7 @@ def make_windows(n_windows, config_id=2, n_landmarks=1000, n_frames=11, wheel=Fa
         # --- prior
         if prior == "anchor":  # identity-information anchor on frame 0's pose (6 rows), SURVEY 8(d) config 2
             out["prior_rows"][wi] = 6; out["prior_nblocks"][wi] = 1
-            out["prior_J0"][wi, :6, :6] = np.eye(6)
+            out["prior_J0"][wi, :6, :6] = np.eye(6) * prior_weight
             blk = out["prior_blocks"][wi, 0]
             blk["kind"] = abi.BLK_POSE; blk["index"] = 0; blk["offset"] = 0; blk["x0"][:7] = out["para_pose"][wi, 0]
         elif prior == "dense":  # marginalization-shaped prior over poses 0..F-2 and speed-bias 0 (n = 6(F-1)+9)

@@ -216,6 +216,15 @@ int gf2_device_count(void);
 
 int gf2_solver_create(const gf2_solver_cfg* cfg, gf2_solver** out);
 void gf2_solver_destroy(gf2_solver* h);
+/* Run all work of this handle on the caller's cudaStream_t (NULL restores the handle's own stream). */
+int gf2_solver_set_stream(gf2_solver* h, void* cuda_stream);
+/* Device-side copy of the mutable state (frame states + inverse depths) of windows [first, first+n) and its
+ * restore: lets a caller re-solve the same batch without re-uploading (benchmarks, what-if solves). */
+int gf2_snapshot_states(gf2_solver* h, int first, int n);
+int gf2_restore_states(gf2_solver* h, int first, int n);
+/* Pinned host memory for full-speed transfers through this ABI (cudaHostAlloc / cudaFreeHost). */
+void* gf2_host_alloc(size_t bytes);
+void gf2_host_free(void* p);
 
 /* Packed states of windows [first, first+n): para_Pose [n][F][7], para_SpeedBias [n][F][9],
  * para_Ex_Pose[0] [n][7], para_Td [n], and (wheel) para_Ex_Pose_wheel [n][7], sx/sy/sw [n][3],
@@ -245,6 +254,8 @@ int gf2_set_imu(gf2_solver* h, int first, int n, const gf2_imu_preint* preint);
 int gf2_imu_preintegrate(gf2_solver* h, int first, int n, const gf2_imu_sample* samples,
                          const int32_t* n_samples, const double* first_sample, const double* lin_bias,
                          const double noise[4]);
+/* Re-run the preintegration kernel on the samples already resident on the device (no H2D). */
+int gf2_imu_preintegrate_resident(gf2_solver* h, int first, int n, const double noise[4]);
 /* Read back the device-side preintegration records ([n][F-1]). */
 int gf2_get_imu(gf2_solver* h, int first, int n, gf2_imu_preint* preint);
 

@@ -1,0 +1,156 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path, called through the C ABI, against the CPU oracle
+on the same seeded inputs. Tolerances: fp64 path, so linearisation quantities agree to rounding (1e-10 relative to the
+largest entry); solved states to <= 1e-4 relative as BASELINE.json states (observed ~1e-6: the window is conditioned
+~1e9 by the weak identity anchor)."""
+import importlib
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def synth(gf2):
+    if gf2.device_count() < 1:
+        pytest.fail("no CUDA device: the hot path has no CPU fallback")
+    return importlib.import_module("gf2_b200.synth")
+
+
+def _copy(w):
+    return {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in w.items()}
+
+
+def _solver(gf2, w, n):
+    return gf2.Solver(n, w["n_frames"], w["max_landmarks"], w["max_obs"], max_imu_samples=w["n_imu_samples"])
+
+
+def test_device_preintegration_matches_oracle(gf2, oracle, synth):
+    w = synth.make_windows(4, n_landmarks=40)
+    s = _solver(gf2, w, 4)
+    s.set_states(w); s.set_landmarks(w); s.imu_preintegrate(w)
+    d = s.get_imu(4)
+    o = oracle.imu_preintegrate(w)
+    for f in ("sum_dt", "delta_p", "delta_q", "delta_v", "lin_ba", "lin_bg", "jacobian", "covariance"):
+        assert np.abs(d[f] - o[f]).max() <= 1e-12 * max(np.abs(o[f]).max(), 1e-300), f
+    assert (d["valid"] == 1).all()
+    # ragged: fewer samples in some intervals, zero samples in one
+    w["imu_n"][0, 3] = 7; w["imu_n"][1, 0] = 0
+    s.imu_preintegrate(w); d = s.get_imu(4); o = oracle.imu_preintegrate(w)
+    for f in ("sum_dt", "delta_p", "delta_q", "jacobian", "covariance"):
+        assert np.abs(d[f] - o[f]).max() <= 1e-12 * max(np.abs(o[f]).max(), 1e-300), f
+    assert d["sum_dt"][1, 0] == 0.0
+    s.close()
+
+
+@pytest.mark.parametrize("nl,prior,sorted_lm", [(200, "anchor", True), (1000, "anchor", True), (300, "dense", True), (257, "anchor", False)])
+def test_linearize_matches_oracle(gf2, oracle, synth, nl, prior, sorted_lm):
+    w = synth.make_windows(2, n_landmarks=nl, prior=prior, sorted_landmarks=sorted_lm)
+    oracle.imu_preintegrate(w)
+    s = _solver(gf2, w, 2)
+    s.upload(w, preintegrate="records")
+    opts = gf2.abi.default_opts()
+    S, g, cost = s.linearize(opts, 2)
+    for i in range(2):
+        So, go, co, _, _ = oracle.linearize_window(w, i, opts)
+        assert So.shape == S[i].shape == (165, 165)
+        assert abs(cost[i] - co) <= 1e-12 * co
+        assert np.abs(S[i] - So).max() <= 1e-10 * np.abs(So).max()
+        assert np.abs(g[i] - go).max() <= 1e-10 * np.abs(go).max()
+        assert np.abs(S[i] - S[i].T).max() == 0.0
+    s.close()
+
+
+@pytest.mark.parametrize("nl,prior", [(200, "anchor"), (1000, "anchor"), (300, "dense")])
+def test_solve_matches_oracle(gf2, oracle, synth, nl, prior):
+    n = 3
+    w = synth.make_windows(n, n_landmarks=nl, prior=prior)
+    oracle.imu_preintegrate(w)
+    s = _solver(gf2, w, n)
+    s.upload(w, preintegrate="records")
+    opts = gf2.abi.default_opts()
+    summ = s.solve(opts, n)
+    got = s.get_states(n); lam = s.get_landmarks(n)
+    wo = _copy(w)
+    so = oracle.solve_batch(wo, opts, n_threads=3)
+    assert (summ["iterations"] == so["iterations"]).all()
+    assert (summ["termination"] == so["termination"]).all()
+    assert (summ["successful_steps"] == so["successful_steps"]).all()
+    assert np.abs(summ["initial_cost"] - so["initial_cost"]).max() <= 1e-12 * so["initial_cost"].max()
+    assert (np.abs(summ["final_cost"] - so["final_cost"]) <= 1e-6 * so["final_cost"]).all()
+    # BASELINE.json: <= 1e-4 relative on pose states
+    scale = np.abs(wo["para_pose"][..., :3]).max()
+    assert np.abs(got["para_pose"][..., :3] - wo["para_pose"][..., :3]).max() <= 1e-4 * scale
+    assert np.abs(got["para_pose"][..., 3:] - wo["para_pose"][..., 3:]).max() <= 1e-4
+    assert np.abs(got["para_speedbias"] - wo["para_speedbias"]).max() <= 1e-4 * max(1.0, np.abs(wo["para_speedbias"]).max())
+    assert np.abs(lam - wo["inv_depth"]).max() <= 1e-4 * np.abs(wo["inv_depth"]).max()
+    # constant blocks untouched, quaternions unit
+    assert np.array_equal(got["ex_pose"], w["ex_pose"]) and np.array_equal(got["td"], w["td"])
+    assert np.abs(np.linalg.norm(got["para_pose"][..., 3:], axis=-1) - 1).max() < 1e-14
+    s.close()
+
+
+def test_solve_properties_full_size_batch(gf2, synth):
+    """BASELINE-size windows (W10-F1000) in a batch: size-independent properties — cost decreases by orders of magnitude,
+    identical windows give bitwise identical results wherever they sit in the batch, re-solving from the optimum is
+    (nearly) idempotent, and a snapshot/restore round trip reproduces the solve bit for bit."""
+    base = synth.make_windows(2, n_landmarks=1000)
+    n = 8
+    w = {k: (np.concatenate([v[:1]] * 5 + [v[1:2]] * 3) if isinstance(v, np.ndarray) and v.shape[:1] == (2,) else v) for k, v in base.items()}
+    s = _solver(gf2, w, n)
+    s.upload(w, preintegrate="device")
+    s.snapshot(n)
+    opts = gf2.abi.default_opts()
+    summ = s.solve(opts, n)
+    assert (summ["final_cost"] < 1e-5 * summ["initial_cost"]).all()
+    a = s.get_states(n); la = s.get_landmarks(n)
+    for i in (1, 2, 3, 4):
+        assert np.array_equal(a["para_pose"][i], a["para_pose"][0]) and np.array_equal(la[i], la[0])
+    assert np.array_equal(a["para_pose"][6], a["para_pose"][5])
+    summ2 = s.solve(opts, n)  # from the optimum
+    b = s.get_states(n)
+    assert np.abs(b["para_pose"] - a["para_pose"]).max() < 5e-3
+    assert (summ2["final_cost"] <= summ["final_cost"] * (1 + 1e-12)).all()
+    s.restore(n)
+    summ3 = s.solve(opts, n)
+    c = s.get_states(n)
+    assert np.array_equal(c["para_pose"], a["para_pose"]) and np.array_equal(summ3["final_cost"], summ["final_cost"])
+    s.close()
+
+
+def test_edge_cases(gf2, oracle, synth):
+    """Empty window (no landmarks), a window with fixed landmarks, and zero iterations."""
+    w = synth.make_windows(3, n_landmarks=120)
+    oracle.imu_preintegrate(w)
+    w["n_landmarks"][0] = 0
+    w["fixed"][1, :60] = 1
+    s = _solver(gf2, w, 3)
+    s.upload(w, preintegrate="records")
+    opts = gf2.abi.default_opts()
+    summ = s.solve(opts, 3)
+    got = s.get_states(3); lam = s.get_landmarks(3)
+    wo = _copy(w)
+    so = oracle.solve_batch(wo, opts, n_threads=3)
+    assert (summ["iterations"] == so["iterations"]).all() and (summ["termination"] == so["termination"]).all()
+    assert np.abs(got["para_pose"] - wo["para_pose"]).max() < 1e-4 * np.abs(wo["para_pose"]).max()
+    assert np.array_equal(lam[1, :60], w["inv_depth"][1, :60])
+    s.upload(w, preintegrate="records")
+    summ0 = s.solve(gf2.abi.default_opts(max_iterations=0), 3)
+    assert (summ0["iterations"] == 0).all()
+    assert np.array_equal(s.get_states(3)["para_pose"], w["para_pose"])
+    s.close()
+
+
+def test_bad_arguments_are_rejected(gf2, synth):
+    w = synth.make_windows(1, n_landmarks=20)
+    s = _solver(gf2, w, 1)
+    bad = _copy(w); bad["start_frame"][0, 0] = 9; bad["track_len"][0, 0] = 5
+    with pytest.raises(gf2.Gf2Error, match="outside"):
+        s.set_landmarks(bad)
+    o = gf2.abi.default_opts(); o.max_time_s = 0.04
+    s.upload(w, preintegrate="device")
+    with pytest.raises(gf2.Gf2Error, match="max_time_s"):
+        s.solve(o, 1)
+    with pytest.raises(gf2.Gf2Error, match="capacity"):
+        s.solve(gf2.abi.default_opts(), 2)
+    s.close()
