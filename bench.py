@@ -1,0 +1,299 @@
+#!/usr/bin/env python
+"""bench.py — sliding-window solves/sec on the W10-F1000 window (BASELINE.json config 2).
+
+One "step" = one pass of the hot path over one batch of B synthetic windows per GPU: device IMU preintegration
+(200 Hz, 20 samples/interval) + a full 8-iteration trust-region solve (Jacobian sweep, Schur, reduced solve,
+back-substitution, candidate evaluation) of every window. `value` is measured with the inputs resident in HBM; `e2e`
+goes through the public C ABI with pinned HOST buffers (H2D of every input, D2H of states + inverse depths) each step.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--windows B] [--impl gf2|reference]
+
+Under torchrun (N > 1) every rank solves its own B windows (window-level data parallelism, no collective: weak scaling).
+`--impl reference` times the restated-reference CPU path (oracle/, Ceres is not installable here) on the host cores.
+"""
+import argparse
+import ctypes
+import importlib
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "oracle")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+# algorithmic bytes of one Jacobian sweep of one W10-F1000 window
+N_OBS, N_LM, N_FRAMES, N_IMU, D_RED = 6500, 1000, 11, 10, 165
+BYTES_SWEEP = N_OBS * 20 + N_LM * 32 + N_FRAMES * 136 + 64 + N_IMU * 1456 + (D_RED * (D_RED + 1) // 2 + D_RED) * 8  # = 289,000
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(gpu_index)],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush(); self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().strip().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1])); mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        return out
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def make_batch(gf2, synth, B, distinct, first_window=0, pinned=True):
+    """B windows tiled from `distinct` generated ones, in pinned host arrays."""
+    base = synth.make_windows(distinct, n_landmarks=N_LM, first_window=first_window)
+    reps = (B + distinct - 1) // distinct
+    w = {}
+    for k, v in base.items():
+        if isinstance(v, np.ndarray) and v.ndim >= 1 and v.shape[0] == distinct and k != "imu_noise":
+            t = np.concatenate([v] * reps)[:B]
+            if pinned:
+                a = gf2.pinned_empty(t.shape, t.dtype); a[...] = t; t = a
+            w[k] = t
+        else:
+            w[k] = v
+    return w
+
+
+def run_reference(args, rank, world):
+    """Restated-reference CPU baseline: oracle solve (same algorithm as ceres::Solve with the reference's options) on
+    all host threads, each step a bounded sample of the same workload."""
+    if rank != 0:
+        return
+    from gf2_loader import load
+    gf2 = load()
+    synth = importlib.import_module("gf2_b200.synth")
+    import gf2_oracle as orc
+    T = host_threads()
+    n = max(T, 8)  # windows per step: one per thread, ~0.1 s each
+    w = synth.make_windows(n, n_landmarks=N_LM)
+    orc.imu_preintegrate(w)
+    opts = gf2.abi.default_opts()
+    init = {k: w[k].copy() for k in ("para_pose", "para_speedbias", "inv_depth")}
+
+    def step():
+        for k, v in init.items():
+            w[k][...] = v
+        orc.imu_preintegrate(w)  # the reference preintegrates on the host too (processIMU)
+        orc.solve_batch(w, opts, n_threads=T)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    val = n * args.steps / dt
+    line = {"impl": "reference", "metric": "sliding-window solves/sec (10-frame, 1k-feat)", "value": val, "unit": "solves/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "W10-F1000 (11 frames, 1000 landmarks, 6500 projection + 10 IMU factors + anchor prior), 8 iterations, time cap off",
+                       "windows_per_step": n},
+            "cpu_baseline": {"value": val, "unit": "solves/s", "cores": T, "kind": "port",
+                             "sample": f"{n} windows/step x {args.steps} steps, restated-reference CPU baseline (Ceres unavailable), {T} threads over independent windows"},
+            "e2e": {"value": val, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--windows", type=int, default=4096, help="windows per GPU per step (batch B)")
+    ap.add_argument("--distinct", type=int, default=64, help="distinct generated windows tiled to B")
+    ap.add_argument("--impl", default="gf2", choices=["gf2", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "gf2" else args.warmup
+    rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import torch
+    import torch.distributed as dist
+    from gf2_loader import load
+    gf2 = load()
+    synth = importlib.import_module("gf2_b200.synth")
+    abi = gf2.abi
+    if gf2.device_count() < 1:
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    B = args.windows
+    w = make_batch(gf2, synth, B, min(args.distinct, B), first_window=rank * 100000)
+    s = gf2.Solver(B, N_FRAMES, w["max_landmarks"], w["max_obs"], max_imu_samples=w["n_imu_samples"], device=local)
+    stream = torch.cuda.Stream()  # a real (non-default) stream: the library launches on it and the timing events sit on it
+    torch.cuda.set_stream(stream)
+    s.set_stream(stream.cuda_stream)
+    opts = abi.default_opts()
+    noise = w["imu_noise"]
+    summ = gf2.pinned_empty((B,), abi.SUMMARY)
+    out_states = {"para_pose": gf2.pinned_empty((B, N_FRAMES, 7), "f8"), "para_speedbias": gf2.pinned_empty((B, N_FRAMES, 9), "f8"),
+                  "ex_pose": gf2.pinned_empty((B, 7), "f8"), "td": gf2.pinned_empty((B,), "f8")}
+    out_lam = gf2.pinned_empty((B, w["max_landmarks"]), "f8")
+
+    # ------------------------------------------------------------ resident run (value)
+    s.upload(w, preintegrate="device")
+    s.snapshot(B)
+    torch.cuda.synchronize()
+
+    def step_resident():
+        s.restore(B)
+        s.imu_preintegrate_resident(noise, B)
+        s.solve(opts, B, summaries=summ)
+    lin_ms = solve_ms = step_ms = total_ms = 0.0
+    launches = 0
+    for _ in range(args.warmup):
+        step_resident()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local) if rank == 0 else None
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_resident()
+        t = s.last_timing()
+        lin_ms += t["linearize_ms"]; solve_ms += t["solve_ms"]; step_ms += t["step_ms"]; total_ms += t["total_ms"]
+        launches += t["launches"] + 1
+        lin_launches = t["linearize_launches"]
+    e1.record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if sampler else None
+    ms = e0.elapsed_time(e1)
+    tt = torch.tensor([ms], device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms_max = float(tt.item())
+    value = world * B * args.steps / (ms_max / 1e3)
+    ok_frac = float((summ["final_cost"] < 1e-3 * summ["initial_cost"]).mean())
+
+    # ------------------------------------------------------------ end-to-end run through the ABI with host buffers
+    h2d = sum(w[k].nbytes for k in ("para_pose", "para_speedbias", "ex_pose", "td", "n_landmarks", "inv_depth", "start_frame", "track_len",
+                                    "fixed", "obs", "frame_td", "imu_samples", "imu_n", "imu_first", "imu_lin_bias", "prior_rows",
+                                    "prior_J0", "prior_r0", "prior_nblocks", "prior_blocks"))
+    d2h = sum(v.nbytes for v in out_states.values()) + out_lam.nbytes + summ.nbytes
+
+    def step_e2e():
+        s.upload(w, preintegrate="device")
+        s.solve(opts, B, summaries=summ)
+        s.get_states(B, out=out_states)
+        s.get_landmarks(B, out=out_lam)
+    for _ in range(2):
+        step_e2e()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    f0 = torch.cuda.Event(enable_timing=True); f1 = torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    f0.record(stream)
+    for _ in range(args.steps):
+        step_e2e()
+    f1.record(stream)
+    torch.cuda.synchronize()
+    wall_e2e = time.perf_counter() - t0
+    te = torch.tensor([max(f0.elapsed_time(f1) / 1e3, wall_e2e)], device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / float(te.item())
+
+    if rank == 0:
+        peaks, which = measured_peaks()
+        n_lin = lin_launches * args.steps
+        lin_avg_ms = lin_ms / n_lin
+        achieved = BYTES_SWEEP * B / (lin_avg_ms / 1e3) / 1e9
+        line = {
+            "metric": "sliding-window solves/sec (10-frame, 1k-feat)", "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "W10-F1000 (11 frames, 1000 landmarks, 6500 projection + 10 IMU factors + anchor prior), 200 Hz IMU preintegration on device, 8 trust-region iterations, time cap off",
+                       "windows_per_gpu_per_step": B, "distinct_windows": min(args.distinct, B), "parallelism": f"window-dp{world} (no collective)",
+                       "l2": "inputs larger than L2 (%.0f MB of window data per GPU)" % (h2d / 1e6), "converged_fraction": ok_frac},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "k_linearize", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": which,
+                         "algorithmic_bytes_per_launch": BYTES_SWEEP * B, "avg_launch_ms": lin_avg_ms},
+            "phase_ms_per_step": {"linearize": lin_ms / args.steps, "reduced_solve": solve_ms / args.steps, "backsub_candidate": step_ms / args.steps,
+                                  "solve_total": total_ms / args.steps},
+        }
+        if not args.no_cpu_baseline:
+            import gf2_oracle as orc
+            T = host_threads()
+            n = max(T, 8) * 2
+            wc = synth.make_windows(n, n_landmarks=N_LM)
+            t0 = time.perf_counter()
+            orc.imu_preintegrate(wc)
+            orc.solve_batch(wc, opts, n_threads=T)
+            dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": n / dt, "unit": "solves/s", "cores": T, "kind": "port",
+                                    "sample": f"{n} W10-F1000 windows, restated-reference CPU baseline (Ceres unavailable), {T} threads over independent windows, {dt:.1f} s"}
+        print(json.dumps(line))
+    s.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -36,7 +36,7 @@ def lib():
 ABI_SYMBOLS = [
     "gf2_last_error", "gf2_abi_version", "gf2_device_count", "gf2_solver_create", "gf2_solver_destroy", "gf2_set_states",
     "gf2_solver_set_stream", "gf2_snapshot_states", "gf2_restore_states", "gf2_host_alloc", "gf2_host_free",
-    "gf2_imu_preintegrate_resident",
+    "gf2_imu_preintegrate_resident", "gf2_get_trace",
     "gf2_set_landmarks", "gf2_set_imu", "gf2_imu_preintegrate", "gf2_get_imu", "gf2_set_wheel", "gf2_set_prior",
     "gf2_set_planes", "gf2_solve", "gf2_linearize", "gf2_reduced_dim", "gf2_get_reduced_system", "gf2_get_states",
     "gf2_get_landmarks", "gf2_comm_init", "gf2_comm_unique_id", "gf2_last_timing", "gf2_tracker_create",
@@ -191,6 +191,12 @@ class Solver:
         d = out if out is not None else np.zeros((n, self.Lm))
         _check(lib().gf2_get_landmarks(self.h, first, n, _p(d)))
         return d
+
+    def get_trace(self, n=None, first=0):
+        n = n if n is not None else self.B
+        tr = np.zeros((n, 64, 6))
+        _check(lib().gf2_get_trace(self.h, first, n, _p(tr)))
+        return tr
 
     def last_timing(self):
         t = np.zeros(8)

@@ -6,7 +6,8 @@
 #include <string.h>
 #include <string>
 #include <vector>
-#include "gf2_solver_kernels2.cuh"
+#include "gf2_solver_solve.cuh"
+#include "gf2_solver_lin.cuh"
 #include "gf2_common.h"
 
 using namespace gf2;
@@ -172,9 +173,14 @@ int gf2_solver_create(const gf2_solver_cfg* cfg, gf2_solver** out) {
   A(k.prior_rows, int32_t, B); A(k.prior_nblocks, int32_t, B); A(k.prior_J0, double, (size_t)B * kP * kP); A(k.prior_r0, double, (size_t)B * kP);
   A(k.prior_blocks, gf2_prior_block, (size_t)B * (2 * F + 8)); A(k.prior_H, double, (size_t)B * kP * kP); A(k.prior_map, int32_t, (size_t)B * kP);
   if (Pm > 0) { A(k.n_planes, int32_t, B); A(k.planes, gf2_plane, (size_t)B * Pm); }
-  A(k.Svis, double, (size_t)B * kNVMax * kNVMax); A(k.gvis, double, (size_t)B * kNVP); A(k.Udiag, double, (size_t)B * kNVMax);
+  A(k.Svis, double, (size_t)B * kNVMax * kNVMax); A(k.gvis, double, (size_t)B * kNVP); A(k.gschur, double, (size_t)B * kNVP); A(k.Udiag, double, (size_t)B * kNVMax);
   A(k.lm_v, double, (size_t)B * Lm); A(k.lm_g, double, (size_t)B * Lm); A(k.lm_s, double, (size_t)B * Lm); A(k.lm_z, double, (size_t)B * Lm);
   A(k.sx, double, (size_t)B * h->D); A(k.zx, double, (size_t)B * h->D); A(k.ux, double, (size_t)B * h->D); A(k.ex_diag, double, (size_t)B * h->D);
+  A(k.imu_H, double, (size_t)B * (F - 1) * 465); A(k.imu_g, double, (size_t)B * (F - 1) * 30);
+  A(k.prior_g, double, (size_t)B * kP); A(k.cost_nv, double, B);
+  A(k.trace, double, (size_t)B * 64 * 6);
+  A(k.perm, int32_t, (size_t)B * Lm); A(k.task_first, int32_t, (size_t)B * kMaxTasks); A(k.task_cnt, int32_t, (size_t)B * kMaxTasks);
+  A(k.task_start, int32_t, (size_t)B * kMaxTasks); A(k.ntasks, int32_t, B);
   A(k.st, WinState, B);
   if (cfg->max_imu_samples > 0) {
     A(h->d_imu_samples, gf2_imu_sample, (size_t)B * (F - 1) * cfg->max_imu_samples); A(h->d_imu_n, int32_t, (size_t)B * (F - 1));
@@ -186,7 +192,7 @@ int gf2_solver_create(const gf2_solver_cfg* cfg, gf2_solver** out) {
   cudaHostAlloc((void**)&h->h_state, sizeof(WinState) * B, cudaHostAllocDefault);
   // opt in to large dynamic shared memory
   cudaFuncSetAttribute(k_linearize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LinShared));
-  cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(SolveShared) + sizeof(double) * (h->D * (h->D + 1) / 2)));
+  cudaFuncSetAttribute(k_solve2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(Solve2Shared) + sizeof(double) * (F * (F + 1) / 2) * kBlk));
   cudaFuncSetAttribute(k_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * 450 * GF2_MAX_FRAMES));
   if (cudaGetLastError() != cudaSuccess) { gf2_solver_destroy(h); return gf2::fail(GF2_ERR_CUDA, "cudaFuncSetAttribute failed (is this an sm_100a device?)"); }
   *out = h;
@@ -398,23 +404,25 @@ static int run(gf2_solver* h, int first, int n, const gf2_solve_opts* opts, gf2_
   GF2_TRY(fill_kp(h, opts, k));
   const int D = h->D;
   const size_t sh_lin = sizeof(LinShared);
-  const size_t sh_solve = sizeof(SolveShared) + sizeof(double) * (D * (D + 1) / 2);
+  const size_t sh_solve = sizeof(Solve2Shared) + sizeof(double) * (k.F * (k.F + 1) / 2) * kBlk;
   double initial_radius = opts->initial_radius > 0 ? opts->initial_radius : 1e4;
   int ne = 0;
   cudaEventRecord(h->ev[ne++], h->stream);
   k_prepare<<<n, 128, sizeof(double) * 450 * GF2_MAX_FRAMES, h->stream>>>(k, first);
+  k_tasks<<<n, 32, 0, h->stream>>>(k, first);
   cudaEventRecord(h->ev[ne++], h->stream);
   if (initial_radius != 1e4) return gf2::fail(GF2_ERR_UNSUPPORTED, "initial_radius other than the Ceres default 1e4");
   const int iters = only_linearize ? 1 : iterations;
   for (int it = 0; it < iters; it++) {
     k_linearize<<<n, kLinThreads, sh_lin, h->stream>>>(k, first);
     cudaEventRecord(h->ev[ne++], h->stream);
-    k_solve<<<n, kSolveThreads, sh_solve, h->stream>>>(k, first);
+    k_nonvis<<<n, kNonvisThreads, 0, h->stream>>>(k, first);
+    k_solve2<<<n, kSolveThreads, sh_solve, h->stream>>>(k, first);
     cudaEventRecord(h->ev[ne++], h->stream);
     if (!only_linearize) {
       k_backsub<<<n, 256, 0, h->stream>>>(k, first);
       cudaEventRecord(h->ev[ne++], h->stream);
-      k_candidate<<<n, 256, 0, h->stream>>>(k, first);
+      k_candidate<<<n, 288, 0, h->stream>>>(k, first);
       cudaEventRecord(h->ev[ne++], h->stream);
     }
   }
@@ -432,7 +440,7 @@ static int run(gf2_solver* h, int first, int n, const gf2_solve_opts* opts, gf2_
     cudaEventElapsedTime(&ms, h->ev[b], h->ev[b + 1]); h->timing[2] += ms;       // solve
     if (!only_linearize) { cudaEventElapsedTime(&ms, h->ev[b + 1], h->ev[b + 3]); h->timing[3] += ms; }
   }
-  h->timing[4] = 1 + iters * per; h->timing[5] = iters;
+  h->timing[4] = 1 + iters * (per + 1); h->timing[5] = iters;
   cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]); h->timing[6] = ms;  // k_prepare
   if (summaries) for (int w = 0; w < n; w++) {
     const WinState& s = h->h_state[w];
@@ -490,6 +498,13 @@ int gf2_get_states(gf2_solver* h, int first, int n, double* para_pose, double* p
 int gf2_get_landmarks(gf2_solver* h, int first, int n, double* inv_depth) {
   GF2_TRY(check_range(h, first, n));
   D2H(inv_depth, h->kp.invdep + (size_t)first * h->kp.Lm, sizeof(double) * n * h->kp.Lm);
+  GF2_CUDA(cudaStreamSynchronize(h->stream));
+  return GF2_OK;
+}
+
+int gf2_get_trace(gf2_solver* h, int first, int n, double* out) {
+  GF2_TRY(check_range(h, first, n));
+  D2H(out, h->kp.trace + (size_t)first * 64 * 6, sizeof(double) * n * 64 * 6);
   GF2_CUDA(cudaStreamSynchronize(h->stream));
   return GF2_OK;
 }

@@ -31,10 +31,11 @@ constexpr int kP = GF2_MAX_PRIOR_DIM;
 struct WinState {  // per-window trust-region state (DoglegStrategy + TrustRegionMinimizer members)
   double radius, mu, x_cost, cand_cost, model_cost_change, dogleg_step_norm, x_norm2;
   double coef_a, coef_b;            // delta = -(a*u + b*z)
-  double initial_cost;
+  double initial_cost, x_cost_prev;
   // x-part sums from k_solve, landmark-part sums from k_backsub
   double dlg2_x, gn2_x, gz_x, zEz_x, uEz_x, uSu, uEu_x, gmax_x;
-  double dlg2_l, gn2_l, gz_l, zEz_l, uEz_l, uHu_l, gmax_l;
+  double dlg2_l, gn2_l, gz_l, zHz_l, uHz_l, uHu_l, gmax_l;
+  double uSz, zSz;                  // u^T S' z and z^T S' z through the Cholesky factor (k_solve2)
   double cost_vis;                  // from k_linearize
   int32_t iteration, successful, termination, active, reuse, invalid_count, lin_valid, pad_;
 };
@@ -63,16 +64,20 @@ struct KP {  // kernel parameters (device pointers are window-major with the str
   const int32_t *prior_rows, *prior_nblocks;
   const double *prior_J0, *prior_r0;
   const gf2_prior_block* prior_blocks;
+  double *imu_H, *imu_g;   // [nW][F-1][465] packed lower J^T J of each IMU factor, [nW][F-1][30] J^T r  (k_nonvis)
+  double *prior_g, *cost_nv; // [nW][P] J0^T r, [nW] cost of the non-visual factors                  (k_nonvis)
   double* prior_H;    // [nW][P][P] = J0^T J0
   int32_t* prior_map; // [nW][P] column -> tangent index (or -1)
   // planes
   const int32_t* n_planes;
   const gf2_plane* planes;
   // work
-  double *Svis, *gvis, *Udiag;     // [nW][66*66], [nW][72], [nW][66]
+  double *Svis, *gvis, *gschur, *Udiag;  // [nW][66*66], [nW][72], [nW][72], [nW][66]
   double *lm_v, *lm_g, *lm_s, *lm_z; // [nW][Lm]
   double *sx, *zx, *ux, *ex_diag;  // [nW][D] jacobi scale, GN step, u, e
   double *Sfull, *gfull;           // optional dump of the assembled reduced system [nW][D*D], [nW][D]
+  int32_t *perm, *task_first, *task_cnt, *task_start, *ntasks;  // k_tasks: landmark permutation by start frame, warp tasks
+  double* trace;                   // [nW][64][6]: candidate cost, model change, rho, radius, step norm, decision
   WinState* st;
 };
 
@@ -267,273 +272,6 @@ __global__ void k_prepare(KP p, int w0) {
     s.radius = 1e4; s.mu = 1e-8; s.x_cost = 0; s.cand_cost = 0; s.model_cost_change = 0; s.dogleg_step_norm = 0;
     s.iteration = 0; s.successful = 0; s.termination = GF2_TERM_NO_CONVERGENCE; s.active = 1; s.reuse = 0; s.invalid_count = 0; s.lin_valid = 0;
     s.initial_cost = 0; s.coef_a = 0; s.coef_b = 0; s.x_norm2 = 0;
-  }
-}
-
-// ------------------------------------------------------------------------------------------------ k_linearize
-struct LinShared {
-  FrameCtx fr[kMaxF];
-  CamCtx cam;
-  double U[kNVMax * kNVMax];  // pose-block Hessian of the visual factors, upper block triangle filled
-  double g[kNVP];
-  double invv[kLinThreads];
-  double red[8 * 32];
-  double WT[kNVP * kWTStride];
-};
-
-// Add the 63 products of one observation (blocks (i,j), (j,j) upper, g_j) for all lanes of a group sharing (i, j).
-__device__ __forceinline__ void accumulate_pair(double* U, double* g, bool mine, int lane, int leader, int i, int j,
-                                                const double (&Ji)[12], const double (&Jj)[12], double r0, double r1) {
-  const int NV = kNVMax;
-#pragma unroll
-  for (int a = 0; a < 6; a++) {
-#pragma unroll
-    for (int b = 0; b < 6; b++) {
-      double v = mine ? (Ji[a] * Jj[b] + Ji[6 + a] * Jj[6 + b]) : 0.0;
-      v = warp_sum(v);
-      if (lane == leader) atomicAdd(&U[(6 * i + a) * NV + 6 * j + b], v);
-    }
-  }
-#pragma unroll
-  for (int a = 0; a < 6; a++) {
-#pragma unroll
-    for (int b = a; b < 6; b++) {
-      double v = mine ? (Jj[a] * Jj[b] + Jj[6 + a] * Jj[6 + b]) : 0.0;
-      v = warp_sum(v);
-      if (lane == leader) atomicAdd(&U[(6 * j + a) * NV + 6 * j + b], v);
-    }
-    double v = mine ? (Jj[a] * r0 + Jj[6 + a] * r1) : 0.0;
-    v = warp_sum(v);
-    if (lane == leader) atomicAdd(&g[6 * j + a], v);
-  }
-}
-
-__global__ void __launch_bounds__(kLinThreads, 1) k_linearize(KP p, int w0) {
-  const int w = w0 + blockIdx.x;
-  WinState& st = p.st[w];
-  if (!st.active || st.reuse) return;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  LinShared& S = *reinterpret_cast<LinShared*>(smem_raw);
-  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
-  const int F = p.F, NV = 6 * F;
-  const double* pose = p.pose + (size_t)w * F * 7;
-  build_frames(pose, p.ex + (size_t)w * 7, p.td[w], F, S.fr, &S.cam);
-  for (int i = t; i < kNVMax * kNVMax; i += kLinThreads) S.U[i] = 0.0;
-  if (t < kNVP) S.g[t] = 0.0;
-  __syncthreads();
-
-  const int nlm = p.nlm[w];
-  const int32_t* start = p.start + (size_t)w * p.Lm; const int32_t* tlen = p.tlen + (size_t)w * p.Lm; const int32_t* obeg = p.obeg + (size_t)w * p.Lm;
-  const float4* obs = p.obs + (size_t)w * p.Om;
-  const double* ftd = p.frame_td + (size_t)w * F;
-  const double mu = st.mu;
-  const bool it0 = (st.iteration == 0);
-  double cost_acc = 0.0, gmax = 0.0;
-  // Schur accumulators: sym tiles (a <= b) of the 9x9 tile grid, tile index q -> warp q % 8
-  double C[6][2];
-#pragma unroll
-  for (int q = 0; q < 6; q++) { C[q][0] = 0.0; C[q][1] = 0.0; }
-
-  for (int base = 0; base < nlm; base += kLinThreads) {
-    const int l = base + t;
-    const bool have = l < nlm;
-    // zero my column of WT
-    for (int c = 0; c < kNVP; c++) S.WT[c * kWTStride + t] = 0.0;
-    int i = 0, L = 0, ob = 0; bool fx = false; double lam = 1.0;
-    LmCtx lc; float4 oi = make_float4(0, 0, 0, 0);
-    if (have) {
-      i = start[l]; L = tlen[l]; ob = obeg[l]; fx = p.fixed[(size_t)w * p.Lm + l] != 0; lam = p.invdep[(size_t)w * p.Lm + l];
-      oi = obs[ob];
-      landmark_ctx(S.fr[i], S.cam, oi, ftd[i], lam, lc);
-    }
-    double M[6] = {0, 0, 0, 0, 0, 0};  // sum Jx^T Jx (xx xy xz yy yz zz)
-    double m3[3] = {0, 0, 0};          // sum Jx^T jl
-    double n3[3] = {0, 0, 0};          // sum Jx^T r
-    double v = 0.0, gl = 0.0;
-    const int Lmax = __reduce_max_sync(0xffffffffu, L);
-    for (int k = 1; k < Lmax; k++) {
-      const bool valid = have && k < L;
-      const int j = i + k;
-      double Jx[6], Jj[12], Ji[12], r0 = 0, r1 = 0, jl0 = 0, jl1 = 0;
-      if (valid) {
-        V3 pcj; const float4 oj = obs[ob + k];
-        obs_residual(S.fr[j], S.cam, lc, oj, ftd[j], p.sqrt_info_px, r0, r1, pcj);
-        obs_jacobians(S.fr[j], S.cam, lc, pcj, p.sqrt_info_px, Jx, Jj);
-        double hr, sc; huber(p.huber, r0 * r0 + r1 * r1, hr, sc);
-        cost_acc += hr;
-        r0 *= sc; r1 *= sc;
-#pragma unroll
-        for (int c = 0; c < 6; c++) Jx[c] *= sc;
-#pragma unroll
-        for (int c = 0; c < 12; c++) Jj[c] *= sc;
-        // Ji = [Jx | Jx * Gi]
-#pragma unroll
-        for (int r = 0; r < 2; r++) {
-          Ji[r * 6 + 0] = Jx[r * 3]; Ji[r * 6 + 1] = Jx[r * 3 + 1]; Ji[r * 6 + 2] = Jx[r * 3 + 2];
-#pragma unroll
-          for (int c = 0; c < 3; c++) Ji[r * 6 + 3 + c] = Jx[r * 3] * lc.Gi.m[c] + Jx[r * 3 + 1] * lc.Gi.m[3 + c] + Jx[r * 3 + 2] * lc.Gi.m[6 + c];
-        }
-        if (!fx) {
-          jl0 = Jx[0] * lc.dXdl.x + Jx[1] * lc.dXdl.y + Jx[2] * lc.dXdl.z;
-          jl1 = Jx[3] * lc.dXdl.x + Jx[4] * lc.dXdl.y + Jx[5] * lc.dXdl.z;
-        }
-        M[0] += Jx[0] * Jx[0] + Jx[3] * Jx[3]; M[1] += Jx[0] * Jx[1] + Jx[3] * Jx[4]; M[2] += Jx[0] * Jx[2] + Jx[3] * Jx[5];
-        M[3] += Jx[1] * Jx[1] + Jx[4] * Jx[4]; M[4] += Jx[1] * Jx[2] + Jx[4] * Jx[5]; M[5] += Jx[2] * Jx[2] + Jx[5] * Jx[5];
-#pragma unroll
-        for (int c = 0; c < 3; c++) { m3[c] += Jx[c] * jl0 + Jx[3 + c] * jl1; n3[c] += Jx[c] * r0 + Jx[3 + c] * r1; }
-        v += jl0 * jl0 + jl1 * jl1; gl += jl0 * r0 + jl1 * r1;
-        // w_j = Jj^T jl  -> WT rows 6j..6j+5
-#pragma unroll
-        for (int c = 0; c < 6; c++) S.WT[(6 * j + c) * kWTStride + t] = Jj[c] * jl0 + Jj[6 + c] * jl1;
-      } else {
-#pragma unroll
-        for (int c = 0; c < 12; c++) { Ji[c] = 0; Jj[c] = 0; }
-      }
-      // pose-block accumulation, grouped by (i, j) inside the warp
-      const int key = valid ? (i * 16 + j) : -1;
-      unsigned todo = __ballot_sync(0xffffffffu, valid);
-      while (todo) {
-        const int leader = __ffs(todo) - 1;
-        const int k0 = __shfl_sync(0xffffffffu, key, leader);
-        const bool mine = valid && key == k0;
-        const unsigned grp = __ballot_sync(0xffffffffu, mine);
-        accumulate_pair(S.U, S.g, mine, lane, leader, k0 >> 4, k0 & 15, Ji, Jj, r0, r1);
-        todo &= ~grp;
-      }
-    }
-    // host-frame block: U_ii += [M, M Gi; Gi^T M, Gi^T M Gi], g_i += [n3; Gi^T n3], w_i = [m3; Gi^T m3]
-    {
-      double Hii[21], gi[6], wi[6];
-      if (have) {
-        const double Mf[9] = {M[0], M[1], M[2], M[1], M[3], M[4], M[2], M[4], M[5]};
-        double MG[9];
-#pragma unroll
-        for (int r = 0; r < 3; r++)
-#pragma unroll
-          for (int c = 0; c < 3; c++) MG[r * 3 + c] = Mf[r * 3] * lc.Gi.m[c] + Mf[r * 3 + 1] * lc.Gi.m[3 + c] + Mf[r * 3 + 2] * lc.Gi.m[6 + c];
-        int q = 0;
-#pragma unroll
-        for (int a = 0; a < 6; a++)
-#pragma unroll
-          for (int b = a; b < 6; b++) {
-            double val;
-            if (a < 3 && b < 3) val = Mf[a * 3 + b];
-            else if (a < 3) val = MG[a * 3 + (b - 3)];
-            else val = lc.Gi.m[(a - 3)] * MG[(b - 3)] + lc.Gi.m[3 + (a - 3)] * MG[3 + (b - 3)] + lc.Gi.m[6 + (a - 3)] * MG[6 + (b - 3)];
-            Hii[q++] = val;
-          }
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-          gi[c] = n3[c]; wi[c] = m3[c];
-          gi[3 + c] = lc.Gi.m[c] * n3[0] + lc.Gi.m[3 + c] * n3[1] + lc.Gi.m[6 + c] * n3[2];
-          wi[3 + c] = lc.Gi.m[c] * m3[0] + lc.Gi.m[3 + c] * m3[1] + lc.Gi.m[6 + c] * m3[2];
-        }
-#pragma unroll
-        for (int c = 0; c < 6; c++) S.WT[(6 * i + c) * kWTStride + t] = wi[c];
-      } else {
-#pragma unroll
-        for (int q = 0; q < 21; q++) Hii[q] = 0;
-#pragma unroll
-        for (int c = 0; c < 6; c++) gi[c] = 0;
-      }
-      const int key = have ? i : -1;
-      unsigned todo = __ballot_sync(0xffffffffu, have);
-      while (todo) {
-        const int leader = __ffs(todo) - 1;
-        const int k0 = __shfl_sync(0xffffffffu, key, leader);
-        const bool mine = have && key == k0;
-        const unsigned grp = __ballot_sync(0xffffffffu, mine);
-        int q = 0;
-#pragma unroll
-        for (int a = 0; a < 6; a++) {
-#pragma unroll
-          for (int b = a; b < 6; b++) { double s = warp_sum(mine ? Hii[q] : 0.0); q++; if (lane == leader) atomicAdd(&S.U[(6 * k0 + a) * kNVMax + 6 * k0 + b], s); }
-          double s = warp_sum(mine ? gi[a] : 0.0);
-          if (lane == leader) atomicAdd(&S.g[6 * k0 + a], s);
-        }
-        todo &= ~grp;
-      }
-    }
-    // landmark scalars: jacobi scale (iteration 0), regularised v' = v + mu * e, 1/v'
-    double inv = 0.0;
-    if (have) {
-      double s_l;
-      if (it0) { s_l = 1.0 / (1.0 + sqrt(v)); p.lm_s[(size_t)w * p.Lm + l] = s_l; } else s_l = p.lm_s[(size_t)w * p.Lm + l];
-      const double d2 = fmin(fmax(s_l * s_l * v, 1e-6), 1e32);
-      const double e = d2 / (s_l * s_l);
-      const double vp = v + mu * e;
-      inv = (!fx && v > 0.0) ? 1.0 / vp : 0.0;
-      p.lm_v[(size_t)w * p.Lm + l] = fx ? 0.0 : v;
-      p.lm_g[(size_t)w * p.Lm + l] = fx ? 0.0 : gl;
-      S.WT[66 * kWTStride + t] = fx ? 0.0 : gl;
-      if (!fx) gmax = fmax(gmax, fabs(gl));
-    }
-    S.invv[t] = inv;
-    __syncthreads();
-    // Schur SYRK on the fp64 tensor cores: C[a-tile][b-tile] += sum_l (W[l][a] / v'_l) * W[l][b]
-    {
-      const int kr = lane & 3, mc = lane >> 2;
-      int q = 0;
-      for (int ta = 0; ta < 9; ta++)
-        for (int tb = ta; tb < 9; tb++, q++) {
-          if ((q & 7) != wid) continue;
-          const int slot = q >> 3;
-          double c0 = 0, c1 = 0;
-          const double* wa = &S.WT[(8 * ta + mc) * kWTStride + kr];
-          const double* wb = &S.WT[(8 * tb + mc) * kWTStride + kr];
-#pragma unroll 4
-          for (int k0 = 0; k0 < kLinThreads; k0 += 4) {
-            const double a = wa[k0] * S.invv[k0 + kr];
-            const double b = wb[k0];
-            mma_f64(c0, c1, a, b);
-          }
-          // static indexing of the register array
-#pragma unroll
-          for (int s2 = 0; s2 < 6; s2++) if (s2 == slot) { C[s2][0] += c0; C[s2][1] += c1; }
-        }
-    }
-    __syncthreads();
-  }
-
-  // S_vis = U - C (upper block triangle + tiles), g_vis = g - C[:,66]; mirror and write out
-  {
-    const int mc = lane >> 2, kr = lane & 3;
-    int q = 0;
-    for (int ta = 0; ta < 9; ta++)
-      for (int tb = ta; tb < 9; tb++, q++) {
-        if ((q & 7) != wid) continue;
-        const int slot = q >> 3;
-        double c0 = 0, c1 = 0;
-#pragma unroll
-        for (int s2 = 0; s2 < 6; s2++) if (s2 == slot) { c0 = C[s2][0]; c1 = C[s2][1]; }
-        const int row = 8 * ta + mc, col = 8 * tb + 2 * kr;
-        // stash the Schur tile into WT (free now) as a dense 72x72 matrix: reuse WT[row*72 + col]
-        S.WT[row * kNVP + col] = c0; S.WT[row * kNVP + col + 1] = c1;
-      }
-  }
-  __syncthreads();
-  double* Svis = p.Svis + (size_t)w * kNVMax * kNVMax;
-  for (int idx = t; idx < NV * NV; idx += kLinThreads) {
-    const int r = idx / NV, c = idx % NV;
-    const int a = r <= c ? r : c, b = r <= c ? c : r;  // upper element (a <= b)
-    // U upper: blocks with frame(a) <= frame(b); inside diagonal blocks only a<=b stored -> (a,b) with a<=b always stored
-    const double u = S.U[a * kNVMax + b];
-    const int ta = a >> 3, tb = b >> 3;
-    const double cs = (ta <= tb) ? S.WT[a * kNVP + b] : S.WT[b * kNVP + a];
-    Svis[r * kNVMax + c] = u - cs;
-  }
-  if (t < NV) {
-    p.gvis[(size_t)w * kNVP + t] = S.g[t] - S.WT[t * kNVP + 66];
-    p.Udiag[(size_t)w * kNVMax + t] = S.U[t * kNVMax + t];
-  }
-  double red2[2] = {cost_acc, 0.0};
-  block_sum<2>(red2, S.red);
-  gmax = warp_max(gmax);
-  if (lane == 0) S.red[wid] = gmax;
-  __syncthreads();
-  if (t == 0) {
-    double gm = 0; for (int i2 = 0; i2 < kLinThreads / 32; i2++) gm = fmax(gm, S.red[i2]);
-    st.cost_vis = red2[0]; st.gmax_l = gm;
   }
 }
 

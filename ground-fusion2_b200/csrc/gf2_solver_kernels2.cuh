@@ -382,12 +382,12 @@ __global__ void __launch_bounds__(256, 2) k_backsub(KP p, int w0) {
     sums[0] += s_l * s_l * gl * gl / d2;
     sums[1] += d2 * z * z / (s_l * s_l);
     sums[2] += gl * z;
-    sums[3] += e * z * z;
-    sums[4] += e * u * z;
-    sums[5] += cu * cu / vp + 2.0 * u * cu + v * u * u;
+    sums[3] += az * az / vp + 2.0 * az * z + v * z * z;             // landmark part of z^T H z
+    sums[4] += cu * az / vp + cu * z + u * az + v * u * z;          // landmark part of u^T H z
+    sums[5] += cu * cu / vp + 2.0 * u * cu + v * u * u;             // landmark part of u^T H u
   }
   block_sum<6>(sums, S.red);
-  if (t == 0) { st.dlg2_l = sums[0]; st.gn2_l = sums[1]; st.gz_l = sums[2]; st.zEz_l = sums[3]; st.uEz_l = sums[4]; st.uHu_l = sums[5]; }
+  if (t == 0) { st.dlg2_l = sums[0]; st.gn2_l = sums[1]; st.gz_l = sums[2]; st.zHz_l = sums[3]; st.uHz_l = sums[4]; st.uHu_l = sums[5]; }
 }
 
 // ------------------------------------------------------------------------------------------------ k_candidate
@@ -412,12 +412,13 @@ __device__ void dogleg_coefficients(WinState& st) {
   }
   st.coef_a = a; st.coef_b = b; st.dogleg_step_norm = nrm;
   // model_cost_change = -(J delta)^T (r + J delta / 2), delta = -(a u + b z)
-  const double uEz = st.uEz_x + st.uEz_l, zEz = st.zEz_x + st.zEz_l;
-  const double uHz = dlg2 - st.mu * uEz, zHz = gz - st.mu * zEz;
+  // quadratic forms of the UNregularised H evaluated explicitly (x-part through the Cholesky factor, landmark part in
+  // k_backsub): the identity H z = g - mu E z is not used because it amplifies the linear-solve error
+  const double uHz = st.uSz - st.mu * st.uEz_x + st.uHz_l, zHz = st.zSz - st.mu * st.zEz_x + st.zHz_l;
   st.model_cost_change = a * dlg2 + b * gz - 0.5 * (a * a * uHu + 2 * a * b * uHz + b * b * zHz);
 }
 
-__global__ void __launch_bounds__(256, 2) k_candidate(KP p, int w0) {
+__global__ void __launch_bounds__(288, 2) k_candidate(KP p, int w0) {
   const int w = w0 + blockIdx.x;
   WinState& st = p.st[w];
   if (!st.active) return;
@@ -451,7 +452,7 @@ __global__ void __launch_bounds__(256, 2) k_candidate(KP p, int w0) {
   const int32_t* start = p.start + (size_t)w * p.Lm; const int32_t* tlen = p.tlen + (size_t)w * p.Lm; const int32_t* obeg = p.obeg + (size_t)w * p.Lm;
   const float4* obs = p.obs + (size_t)w * p.Om;
   const double* ftd = p.frame_td + (size_t)w * F;
-  for (int l = t; l < nlm; l += blockDim.x) {
+  for (int l = t; l < nlm && t < 256; l += 256) {
     const double v = p.lm_v[(size_t)w * p.Lm + l];
     const double lam = p.invdep[(size_t)w * p.Lm + l];
     double lam_c = lam;
@@ -473,23 +474,25 @@ __global__ void __launch_bounds__(256, 2) k_candidate(KP p, int w0) {
       acc[0] += hr;
     }
   }
-  // IMU factors at the candidate
-  if (p.imu && t < F - 1) {
-    const gf2_imu_preint& pre = p.imu[(size_t)w * (F - 1) + t];
-    if (pre.valid && pre.sum_dt <= 10.0) {
-      double r[15]; ImuStates s2 = load_imu_states(pose_c, sb_c, t);
-      imu_raw(pre, s2, p.g_norm, r, nullptr);
-      acc[0] += imu_cost(p.imu_sqrt + ((size_t)w * (F - 1) + t) * 225, r);
+  // IMU factors and the prior at the candidate: warp 8 alone, concurrently with the landmark warps
+  if (t >= 256) {
+    const int ln = t - 256;
+    if (p.imu && ln < F - 1) {
+      const gf2_imu_preint& pre = p.imu[(size_t)w * (F - 1) + ln];
+      if (pre.valid && pre.sum_dt <= 10.0) {
+        double r[15]; ImuStates s2 = load_imu_states(pose_c, sb_c, ln);
+        imu_raw(pre, s2, p.g_norm, r, nullptr);
+        acc[0] += imu_cost(p.imu_sqrt + ((size_t)w * (F - 1) + ln) * 225, r);
+      }
     }
-  }
-  // prior at the candidate
-  const int n = p.prior_rows ? p.prior_rows[w] : 0;
-  if (n > 0) {
-    const gf2_prior_block* blk = p.prior_blocks + (size_t)w * (2 * F + 8);
-    if (t < p.prior_nblocks[w]) prior_block_dx(blk[t], pose_c, sb_c, S.dx);
-    __syncthreads();
-    const double* J0 = p.prior_J0 + (size_t)w * kP * kP; const double* r0p = p.prior_r0 + (size_t)w * kP;
-    if (t < n) { double s2 = r0p[t]; for (int c = 0; c < n; c++) s2 += J0[t * kP + c] * S.dx[c]; acc[0] += 0.5 * s2 * s2; }
+    const int n = p.prior_rows ? p.prior_rows[w] : 0;
+    if (n > 0) {
+      const gf2_prior_block* blk = p.prior_blocks + (size_t)w * (2 * F + 8);
+      if (ln < p.prior_nblocks[w]) prior_block_dx(blk[ln], pose_c, sb_c, S.dx);
+      __syncwarp();
+      const double* J0 = p.prior_J0 + (size_t)w * kP * kP; const double* r0p = p.prior_r0 + (size_t)w * kP;
+      for (int row = ln; row < n; row += 32) { double s2 = r0p[row]; for (int c = 0; c < n; c++) s2 += J0[row * kP + c] * S.dx[c]; acc[0] += 0.5 * s2 * s2; }
+    }
   }
   block_sum<3>(acc, S.red);
   // TrustRegionMinimizer: tolerance checks, step acceptance, radius update
@@ -497,6 +500,7 @@ __global__ void __launch_bounds__(256, 2) k_candidate(KP p, int w0) {
     int decision = 0;  // 0 reject, 1 accept, 2 terminated (no accept)
     st.cand_cost = acc[0];
     st.x_norm2 = acc[2];
+    st.x_cost_prev = st.x_cost;
     st.iteration++;
     if (!(st.model_cost_change > 0.0)) {  // HandleInvalidStep
       st.invalid_count++;
@@ -525,6 +529,10 @@ __global__ void __launch_bounds__(256, 2) k_candidate(KP p, int w0) {
       else if (st.radius <= 1e-32) { st.active = 0; st.termination = GF2_TERM_MIN_RADIUS; }
     }
     S.decision = decision;
+    if (p.trace && st.iteration <= 64) {
+      double* tr = p.trace + ((size_t)w * 64 + (st.iteration - 1)) * 6;
+      tr[0] = st.cand_cost; tr[1] = st.model_cost_change; tr[2] = (st.x_cost_prev - st.cand_cost) / st.model_cost_change; tr[3] = st.radius; tr[4] = sqrt(acc[1]); tr[5] = decision;
+    }
   }
   __syncthreads();
   if (S.decision == 1) {  // x = candidate

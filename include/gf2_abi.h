@@ -299,6 +299,9 @@ int gf2_comm_unique_id(void* out_128_bytes);
  * [2] reduced solve kernels, [3] back-substitution + candidate evaluation kernels, [4] number of
  * kernel launches, [5] number of linearise launches. */
 int gf2_last_timing(gf2_solver* h, double out[8]);
+/* Per-iteration record of the last solve: out [n][64][6] = {candidate cost, model cost change, relative decrease,
+ * trust-region radius after the step, ambient step norm, decision (0 reject, 1 accept, 2 terminate/invalid)}. */
+int gf2_get_trace(gf2_solver* h, int first, int n, double* out);
 
 /* ---------------------------------------------------------------- tracker */
 
