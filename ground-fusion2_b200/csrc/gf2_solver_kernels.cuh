@@ -161,8 +161,9 @@ __device__ __forceinline__ void obs_residual(const FrameCtx& fj, const CamCtx& c
   pcj = mk3(fj.A[0] * d.x + fj.A[1] * d.y + fj.A[2] * d.z - cam.rtt[0], fj.A[3] * d.x + fj.A[4] * d.y + fj.A[5] * d.z - cam.rtt[1],
             fj.A[6] * d.x + fj.A[7] * d.y + fj.A[8] * d.z - cam.rtt[2]);
   const double ptx = (double)oj.x - dt * (double)oj.z, pty = (double)oj.y - dt * (double)oj.w;
-  r0 = sqrt_info * (pcj.x / pcj.z - ptx);
-  r1 = sqrt_info * (pcj.y / pcj.z - pty);
+  const double iz = 1.0 / pcj.z;  // one reciprocal per observation (fp64 division is a long software sequence)
+  r0 = sqrt_info * (pcj.x * iz - ptx);
+  r1 = sqrt_info * (pcj.y * iz - pty);
 }
 
 // ceres::HuberLoss + Corrector (rho'' <= 0 -> both r and J scaled by sqrt(rho')), restated in-tree at

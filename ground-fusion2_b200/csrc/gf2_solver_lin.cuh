@@ -41,30 +41,30 @@ __global__ void k_tasks(KP p, int w0) {
 }
 
 // ------------------------------------------------------------------------------------------------ k_linearize
+constexpr int kWTRows = 68;        // 66 tangent rows + the landmark-gradient row 66 + one always-zero row 67 (tile padding)
+constexpr int kStageStride = 13;   // per residual row: Ji (6) | Jj (6) | r
+constexpr int kNBlkPairs = kMaxF * (kMaxF + 1) / 2;
+
 struct LinShared {
   FrameCtx fr[kMaxF];
   CamCtx cam;
-  double U[kNVMax * kNVMax];  // pose-block Hessian of the visual factors, upper block triangle filled
+  double U[kNBlkPairs * 36];  // pose-block Hessian of the visual factors: 6x6 blocks (bi <= bj), row-major inside
   double g[kNVP];
-  double invv[kLinThreads];
   double red[8 * 32];
   int task_first[kMaxTasks], task_cnt[kMaxTasks], task_start[kMaxTasks];
-  double WT[kNVP * kWTStride];
+  double stage[8][64 * kStageStride];  // per warp: the 64 residual rows of the current step
+  double WT[kWTRows * kWTStride];      // transposed, pre-scaled landmark columns  w_l / sqrt(v'_l)
 };
 
-// transposed butterfly over 32 values: on return lane L holds sum over all lanes of v[L] (in v[0])
-__device__ __forceinline__ double butterfly32(double (&v)[32], int lane) {
-#pragma unroll
-  for (int bit = 16, h = 16; bit > 0; bit >>= 1, h >>= 1) {
-    const bool up = (lane & bit) != 0;
-#pragma unroll
-    for (int t = 0; t < h; t++) {
-      const double send = up ? v[t] : v[t + h];
-      const double keep = up ? v[t + h] : v[t];
-      v[t] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
-    }
+__device__ __forceinline__ int ublk(int bi, int bj, int F) { return (bi * F - bi * (bi - 1) / 2 + (bj - bi)) * 36; }  // bi <= bj
+
+// flush one 8x8 accumulator tile (m = lane/4, n = 2*(lane%4)+{0,1}) into a 6x6 block (+ optional gradient column n = 6)
+__device__ __forceinline__ void flush_tile(double* blk, double* gvec, double c0, double c1, int lane) {
+  const int m = lane >> 2, n = (lane & 3) * 2;
+  if (m < 6) {
+    if (n < 6) { atomicAdd(&blk[m * 6 + n], c0); atomicAdd(&blk[m * 6 + n + 1], c1); }
+    else if (gvec) atomicAdd(&gvec[m], c0);  // n == 6
   }
-  return v[0];
 }
 
 __global__ void __launch_bounds__(kLinThreads, 1) k_linearize(KP p, int w0) {
@@ -77,10 +77,11 @@ __global__ void __launch_bounds__(kLinThreads, 1) k_linearize(KP p, int w0) {
   const int F = p.F, NV = 6 * F;
   const double* pose = p.pose + (size_t)w * F * 7;
   build_frames(pose, p.ex + (size_t)w * 7, p.td[w], F, S.fr, &S.cam);
-  for (int i = t; i < kNVMax * kNVMax; i += kLinThreads) S.U[i] = 0.0;
+  for (int i = t; i < kNBlkPairs * 36; i += kLinThreads) S.U[i] = 0.0;
   if (t < kNVP) S.g[t] = 0.0;
   const int ntasks = p.ntasks[w];
   if (t < kMaxTasks) { S.task_first[t] = p.task_first[(size_t)w * kMaxTasks + t]; S.task_cnt[t] = p.task_cnt[(size_t)w * kMaxTasks + t]; S.task_start[t] = p.task_start[(size_t)w * kMaxTasks + t]; }
+  for (int i = t; i < kWTRows * kWTStride; i += kLinThreads) S.WT[i] = 0.0;
   __syncthreads();
 
   const int32_t* tlen = p.tlen + (size_t)w * p.Lm; const int32_t* obeg = p.obeg + (size_t)w * p.Lm; const int32_t* perm = p.perm + (size_t)w * p.Lm;
@@ -92,21 +93,33 @@ __global__ void __launch_bounds__(kLinThreads, 1) k_linearize(KP p, int w0) {
   double C[6][2];  // Schur accumulators: sym tiles (a <= b) of the 9x9 tile grid, tile q -> warp q % 8, slot q / 8
 #pragma unroll
   for (int q = 0; q < 6; q++) { C[q][0] = 0.0; C[q][1] = 0.0; }
+  int tile_a[6], tile_b[6];  // tiles owned by this warp: q = wid + 8 * slot in row-major order of the upper 9x9 tile triangle
+#pragma unroll
+  for (int s2 = 0; s2 < 6; s2++) {
+    int q = wid + 8 * s2, a = 0;
+    if (q >= 45) { tile_a[s2] = -1; tile_b[s2] = 0; continue; }
+    while (q >= 9 - a) { q -= 9 - a; a++; }
+    tile_a[s2] = a; tile_b[s2] = a + q;
+  }
+  double* stg = S.stage[wid];
+  const int fq = lane >> 2, fk = lane & 3;  // fragment coordinates: row/col index 0..7, k index 0..3
 
   for (int tbase = 0; tbase < ntasks; tbase += 8) {
     const int task = tbase + wid;
     const bool have_task = task < ntasks;
     const int i = have_task ? S.task_start[task] : 0;
     const bool have = have_task && lane < S.task_cnt[task];
-    for (int c = 8 * ((6 * S.task_start[tbase]) >> 3); c < kNVP; c++) S.WT[c * kWTStride + t] = 0.0;  // tiles left of the round first host frame are skipped below
+    const int row0 = 8 * ((6 * S.task_start[tbase]) >> 3);  // tiles left of the round's first host frame are skipped by the SYRK
+    for (int c = row0; c < kWTRows - 1; c++) S.WT[c * kWTStride + t] = 0.0;
     int l = 0, L = 0, ob = 0; bool fx = false; double lam = 1.0;
     LmCtx lc;
     if (have) {
       l = perm[S.task_first[task] + lane]; L = tlen[l]; ob = obeg[l]; fx = p.fixed[(size_t)w * p.Lm + l] != 0; lam = p.invdep[(size_t)w * p.Lm + l];
       landmark_ctx(S.fr[i], S.cam, obs[ob], ftd[i], lam, lc);
     }
-    double M[6] = {0, 0, 0, 0, 0, 0}, m3[3] = {0, 0, 0}, n3[3] = {0, 0, 0};
+    double wi[6] = {0, 0, 0, 0, 0, 0};  // w_i = sum_k Ji^T jl
     double v = 0.0, gl = 0.0;
+    double cii0 = 0.0, cii1 = 0.0;      // Ji^T [Ji | r] accumulated over the steps of the task (host-frame block + g_i)
     const int Lmax = __reduce_max_sync(0xffffffffu, L);
     for (int k = 1; k < Lmax; k++) {
       const bool valid = have && k < L;
@@ -136,146 +149,100 @@ __global__ void __launch_bounds__(kLinThreads, 1) k_linearize(KP p, int w0) {
           jl0 = Jx[0] * lc.dXdl.x + Jx[1] * lc.dXdl.y + Jx[2] * lc.dXdl.z;
           jl1 = Jx[3] * lc.dXdl.x + Jx[4] * lc.dXdl.y + Jx[5] * lc.dXdl.z;
         }
-        M[0] += Jx[0] * Jx[0] + Jx[3] * Jx[3]; M[1] += Jx[0] * Jx[1] + Jx[3] * Jx[4]; M[2] += Jx[0] * Jx[2] + Jx[3] * Jx[5];
-        M[3] += Jx[1] * Jx[1] + Jx[4] * Jx[4]; M[4] += Jx[1] * Jx[2] + Jx[4] * Jx[5]; M[5] += Jx[2] * Jx[2] + Jx[5] * Jx[5];
-#pragma unroll
-        for (int c = 0; c < 3; c++) { m3[c] += Jx[c] * jl0 + Jx[3 + c] * jl1; n3[c] += Jx[c] * r0 + Jx[3 + c] * r1; }
         v += jl0 * jl0 + jl1 * jl1; gl += jl0 * r0 + jl1 * r1;
 #pragma unroll
-        for (int c = 0; c < 6; c++) S.WT[(6 * j + c) * kWTStride + t] = Jj[c] * jl0 + Jj[6 + c] * jl1;  // w_j = Jj^T jl
-      }
-      if (have_task && j < F) {
-        // batch A: entries 0..31 of the (i, j) block
-        double b[32];
-#pragma unroll
-        for (int e = 0; e < 32; e++) b[e] = Ji[e / 6] * Jj[e % 6] + Ji[6 + e / 6] * Jj[6 + e % 6];
-        double s = butterfly32(b, lane);
-        atomicAdd(&S.U[(6 * i + lane / 6) * kNVMax + 6 * j + lane % 6], s);
-        // batch B: entries 32..35 of (i, j), the 21 upper entries of (j, j), g_j (6), one spare
-#pragma unroll
-        for (int e = 0; e < 4; e++) b[e] = Ji[5] * Jj[2 + e] + Ji[11] * Jj[8 + e];
-        {
-          int q = 4;
-#pragma unroll
-          for (int a = 0; a < 6; a++)
-#pragma unroll
-            for (int c = a; c < 6; c++) b[q++] = Jj[a] * Jj[c] + Jj[6 + a] * Jj[6 + c];
-#pragma unroll
-          for (int a = 0; a < 6; a++) b[q++] = Jj[a] * r0 + Jj[6 + a] * r1;
-          b[31] = 0.0;
-        }
-        s = butterfly32(b, lane);
-        if (lane < 4) atomicAdd(&S.U[(6 * i + 5) * kNVMax + 6 * j + 2 + lane], s);
-        else if (lane < 25) {
-          // unrank the upper-triangular index lane - 4 -> (a, c), a <= c < 6
-          int q = lane - 4, a = 0;
-          while (q >= 6 - a) { q -= 6 - a; a++; }
-          atomicAdd(&S.U[(6 * j + a) * kNVMax + 6 * j + a + q], s);
-        } else if (lane < 31) atomicAdd(&S.g[6 * j + lane - 25], s);
-      }
-    }
-    // host-frame block: U_ii += [M, M Gi; Gi^T M, Gi^T M Gi], g_i += [n3; Gi^T n3], w_i = [m3; Gi^T m3]
-    if (have_task) {
-      double b[32];
-#pragma unroll
-      for (int e = 0; e < 32; e++) b[e] = 0.0;
-      if (have) {
-        const double Mf[9] = {M[0], M[1], M[2], M[1], M[3], M[4], M[2], M[4], M[5]};
-        double MG[9];
-#pragma unroll
-        for (int r = 0; r < 3; r++)
-#pragma unroll
-          for (int c = 0; c < 3; c++) MG[r * 3 + c] = Mf[r * 3] * lc.Gi.m[c] + Mf[r * 3 + 1] * lc.Gi.m[3 + c] + Mf[r * 3 + 2] * lc.Gi.m[6 + c];
-        int q = 0;
-#pragma unroll
-        for (int a = 0; a < 6; a++)
-#pragma unroll
-          for (int c = a; c < 6; c++) {
-            double val;
-            if (a < 3 && c < 3) val = Mf[a * 3 + c];
-            else if (a < 3) val = MG[a * 3 + (c - 3)];
-            else val = lc.Gi.m[(a - 3)] * MG[(c - 3)] + lc.Gi.m[3 + (a - 3)] * MG[3 + (c - 3)] + lc.Gi.m[6 + (a - 3)] * MG[6 + (c - 3)];
-            b[q++] = val;
-          }
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-          b[21 + c] = n3[c];
-          b[24 + c] = lc.Gi.m[c] * n3[0] + lc.Gi.m[3 + c] * n3[1] + lc.Gi.m[6 + c] * n3[2];
-          S.WT[(6 * i + c) * kWTStride + t] = m3[c];
-          S.WT[(6 * i + 3 + c) * kWTStride + t] = lc.Gi.m[c] * m3[0] + lc.Gi.m[3 + c] * m3[1] + lc.Gi.m[6 + c] * m3[2];
+        for (int c = 0; c < 6; c++) {
+          wi[c] += Ji[c] * jl0 + Ji[6 + c] * jl1;
+          S.WT[(6 * j + c) * kWTStride + t] = Jj[c] * jl0 + Jj[6 + c] * jl1;  // w_j = Jj^T jl
         }
       }
-      const double s = butterfly32(b, lane);
-      if (lane < 21) {
-        int q = lane, a = 0;
-        while (q >= 6 - a) { q -= 6 - a; a++; }
-        atomicAdd(&S.U[(6 * i + a) * kNVMax + 6 * i + a + q], s);
-      } else if (lane < 27) atomicAdd(&S.g[6 * i + lane - 21], s);
+      if (have_task) {
+        // stage the 64 residual rows of this step, then reduce across the warp on the tensor cores:
+        //   C1 = Ji^T Jj -> block (i, j);  C2 = Jj^T [Jj | r] -> block (j, j), g_j;  Cii += Ji^T [Ji | r]
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+          double* row = stg + (2 * lane + r) * kStageStride;
+#pragma unroll
+          for (int c = 0; c < 6; c++) { row[c] = Ji[r * 6 + c]; row[6 + c] = Jj[r * 6 + c]; }
+          row[12] = r ? r1 : r0;
+        }
+        __syncwarp();
+        double c10 = 0, c11 = 0, c20 = 0, c21 = 0, d10 = 0, d11 = 0, d20 = 0, d21 = 0, dii0 = 0, dii1 = 0;
+        const int colx = fq < 6 ? fq : 12;  // Ji column, or the residual for fragment index 6 (index 7 reads it too, masked below)
+#pragma unroll 4
+        for (int s = 0; s < 16; s++) {
+          const double* row = stg + (4 * s + fk) * kStageStride;
+          const double x = row[colx];
+          const double y = row[6 + (fq < 6 ? fq : 0)];
+          const double a_i = fq < 6 ? x : 0.0;              // Ji^T as A, also Ji as B (n < 6)
+          const double a_j = fq < 6 ? y : 0.0;              // Jj^T as A, also Jj as B (n < 6)
+          const double b_ir = fq < 7 ? x : 0.0;             // [Ji | r]
+          const double b_jr = fq < 6 ? y : (fq == 6 ? x : 0.0);  // [Jj | r]
+          if (s & 1) { mma_f64(d10, d11, a_i, a_j); mma_f64(d20, d21, a_j, b_jr); mma_f64(dii0, dii1, a_i, b_ir); }
+          else { mma_f64(c10, c11, a_i, a_j); mma_f64(c20, c21, a_j, b_jr); mma_f64(cii0, cii1, a_i, b_ir); }
+        }
+        c10 += d10; c11 += d11; c20 += d20; c21 += d21; cii0 += dii0; cii1 += dii1;
+        flush_tile(&S.U[ublk(i, j, F)], nullptr, c10, c11, lane);
+        flush_tile(&S.U[ublk(j, j, F)], &S.g[6 * j], c20, c21, lane);
+      }
     }
-    // landmark scalars: jacobi scale (iteration 0), regularised v' = v + mu * e, 1/v'
-    double inv = 0.0;
+    if (have_task) flush_tile(&S.U[ublk(i, i, F)], &S.g[6 * i], cii0, cii1, lane);
+    // landmark scalars: jacobi scale (iteration 0), regularised v' = v + mu * e; the landmark's column of W is scaled by
+    // 1/sqrt(v') so that the SYRK below needs no per-element multiply
     if (have) {
       double s_l;
       if (it0) { s_l = 1.0 / (1.0 + sqrt(v)); p.lm_s[(size_t)w * p.Lm + l] = s_l; } else s_l = p.lm_s[(size_t)w * p.Lm + l];
       const double d2 = fmin(fmax(s_l * s_l * v, 1e-6), 1e32);
       const double e = d2 / (s_l * s_l);
       const double vp = v + mu * e;
-      inv = (!fx && v > 0.0) ? 1.0 / vp : 0.0;
+      const double rs = (!fx && v > 0.0) ? rsqrt(vp) : 0.0;
       p.lm_v[(size_t)w * p.Lm + l] = fx ? 0.0 : v;
       p.lm_g[(size_t)w * p.Lm + l] = fx ? 0.0 : gl;
-      S.WT[66 * kWTStride + t] = fx ? 0.0 : gl;
       if (!fx) gmax = fmax(gmax, fabs(gl));
-    }
-    S.invv[t] = inv;
-    __syncthreads();
-    // Schur SYRK on the fp64 tensor cores: C[a-tile][b-tile] += sum_l (W[l][a] / v'_l) * W[l][b]; tiles whose rows are all
-    // left of the round's first host frame are identically zero and skipped
-    {
-      const int kr = lane & 3, mc = lane >> 2;
-      const int ta_min = (6 * S.task_start[tbase]) >> 3;
-      int q = 0;
-      for (int ta = 0; ta < 9; ta++)
-        for (int tb = ta; tb < 9; tb++, q++) {
-          if ((q & 7) != wid || ta < ta_min) continue;
-          const int slot = q >> 3;
-          double c0 = 0, c1 = 0;
-          const double* wa = &S.WT[(8 * ta + mc) * kWTStride + kr];
-          const double* wb = &S.WT[(8 * tb + mc) * kWTStride + kr];
-#pragma unroll 4
-          for (int k0 = 0; k0 < kLinThreads; k0 += 4) mma_f64(c0, c1, wa[k0] * S.invv[k0 + kr], wb[k0]);
 #pragma unroll
-          for (int s2 = 0; s2 < 6; s2++) if (s2 == slot) { C[s2][0] += c0; C[s2][1] += c1; }
-        }
+      for (int c = 0; c < 6; c++) S.WT[(6 * i + c) * kWTStride + t] = wi[c] * rs;
+      for (int c = 6 * (i + 1); c < 6 * (i + L); c++) S.WT[c * kWTStride + t] *= rs;
+      S.WT[66 * kWTStride + t] = fx ? 0.0 : gl * rs;
+    }
+    __syncthreads();
+    // Schur SYRK on the fp64 tensor cores: C[a-tile][b-tile] += sum_l Ws[l][a] * Ws[l][b]
+    {
+      const int ta_min = row0 >> 3;
+      const double* wa[6]; const double* wb[6]; bool on[6];
+#pragma unroll
+      for (int s2 = 0; s2 < 6; s2++) {
+        on[s2] = tile_a[s2] >= ta_min;  // (also false for unowned slots: tile_a = -1)
+        wa[s2] = &S.WT[min(8 * max(tile_a[s2], 0) + fq, kWTRows - 1) * kWTStride + fk];
+        wb[s2] = &S.WT[min(8 * tile_b[s2] + fq, kWTRows - 1) * kWTStride + fk];
+      }
+      // all owned tiles advance together: six independent accumulator chains hide the mma latency
+#pragma unroll 2
+      for (int k0 = 0; k0 < kLinThreads; k0 += 4) {
+#pragma unroll
+        for (int s2 = 0; s2 < 6; s2++) if (on[s2]) mma_f64(C[s2][0], C[s2][1], wa[s2][k0], wb[s2][k0]);
+      }
     }
     __syncthreads();
   }
 
-  // S_vis = U - C, g_vis = g - C[:,66]; the Schur tiles are staged in WT (free now) as a dense 72x72 matrix
-  {
-    const int mc = lane >> 2, kr = lane & 3;
-    int q = 0;
-    for (int ta = 0; ta < 9; ta++)
-      for (int tb = ta; tb < 9; tb++, q++) {
-        if ((q & 7) != wid) continue;
-        const int slot = q >> 3;
-        double c0 = 0, c1 = 0;
+  // S_vis = U - C, g_schur = C[:,66]; the Schur tiles are staged in WT (free now) as a dense 72x72 matrix
 #pragma unroll
-        for (int s2 = 0; s2 < 6; s2++) if (s2 == slot) { c0 = C[s2][0]; c1 = C[s2][1]; }
-        const int row = 8 * ta + mc, col = 8 * tb + 2 * kr;
-        S.WT[row * kNVP + col] = c0; S.WT[row * kNVP + col + 1] = c1;
-      }
+  for (int s2 = 0; s2 < 6; s2++) if (tile_a[s2] >= 0) {
+    const int row = 8 * tile_a[s2] + fq, col = 8 * tile_b[s2] + 2 * fk;
+    S.WT[row * kNVP + col] = C[s2][0]; S.WT[row * kNVP + col + 1] = C[s2][1];
   }
   __syncthreads();
   double* Svis = p.Svis + (size_t)w * kNVMax * kNVMax;
   for (int idx = t; idx < NV * NV; idx += kLinThreads) {
     const int r = idx / NV, c = idx % NV;
-    const int a = r <= c ? r : c, b = r <= c ? c : r;  // stored element (a <= b)
-    Svis[r * kNVMax + c] = S.U[a * kNVMax + b] - S.WT[a * kNVP + b];
+    const int a = r <= c ? r : c, b = r <= c ? c : r;  // upper element (a <= b) of U and of the Schur tiles
+    Svis[r * kNVMax + c] = S.U[ublk(a / 6, b / 6, F) + (a % 6) * 6 + (b % 6)] - S.WT[a * kNVP + b];
   }
   if (t < NV) {
     p.gvis[(size_t)w * kNVP + t] = S.g[t];                       // full visual gradient J^T r (pose part)
     p.gschur[(size_t)w * kNVP + t] = S.WT[t * kNVP + 66];         // sum_l w_l g_l / v'_l, subtracted to form the reduced rhs
-    p.Udiag[(size_t)w * kNVMax + t] = S.U[t * kNVMax + t];
+    p.Udiag[(size_t)w * kNVMax + t] = S.U[ublk(t / 6, t / 6, F) + (t % 6) * 7];
   }
   double red2[2] = {cost_acc, 0.0};
   block_sum<2>(red2, S.red);
