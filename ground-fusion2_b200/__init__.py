@@ -202,3 +202,70 @@ class Solver:
         t = np.zeros(8)
         _check(lib().gf2_last_timing(self.h, _p(t)))
         return {"total_ms": t[0], "linearize_ms": t[1], "solve_ms": t[2], "step_ms": t[3], "launches": int(t[4]), "linearize_launches": int(t[5]), "prepare_ms": t[6]}
+
+
+class Tracker:
+    """Batched pyramidal LK: cv::calcOpticalFlowPyrLK as FeatureTracker::trackImage calls it (feature_tracker.cpp:122-142)."""
+
+    def __init__(self, width=640, height=480, max_pts=300, max_streams=1, max_level=3, win=21, max_iters=30, eps=0.01,
+                 min_eig=1e-4, device=0):
+        cfg = abi.TrackerCfg()
+        cfg.device = device; cfg.width = width; cfg.height = height; cfg.max_pts = max_pts; cfg.win = win
+        cfg.max_level = max_level; cfg.max_iters = max_iters; cfg.max_streams = max_streams; cfg.eps = eps; cfg.min_eig = min_eig
+        self.cfg = cfg
+        self.h = C.c_void_p()
+        _check(lib().gf2_tracker_create(C.byref(cfg), C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            lib().gf2_tracker_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _prep(self, prev, cur, prev_pts, n_pts):
+        cur = np.ascontiguousarray(cur, np.uint8)
+        S = cur.shape[0] if cur.ndim == 3 else 1
+        if prev is not None:
+            prev = np.ascontiguousarray(prev, np.uint8)
+        pts = np.zeros((S, self.cfg.max_pts, 2), np.float32)
+        prev_pts = np.asarray(prev_pts, np.float32)
+        if prev_pts.ndim == 2:
+            prev_pts = prev_pts[None]
+        npts = np.zeros(S, np.int32)
+        for s in range(S):
+            k = prev_pts[s].shape[0] if n_pts is None else int(n_pts[s])
+            pts[s, :k] = prev_pts[s][:k]; npts[s] = k
+        return S, prev, cur, pts, npts
+
+    def track(self, prev, cur, prev_pts, n_pts=None, init_pts=None, max_level=None, flags=0):
+        """prev/cur: [H, W] or [S, H, W] uint8 (prev None = reuse the cached pyramid); prev_pts [n, 2] or [S, n, 2].
+        Returns (cur_pts [S, max_pts, 2], status [S, max_pts], err [S, max_pts])."""
+        S, prev, cur, pts, npts = self._prep(prev, cur, prev_pts, n_pts)
+        out = np.zeros_like(pts)
+        if init_pts is not None:
+            ip = np.asarray(init_pts, np.float32)
+            ip = ip[None] if ip.ndim == 2 else ip
+            for s in range(S):
+                out[s, :ip[s].shape[0]] = ip[s]
+        status = np.zeros((S, self.cfg.max_pts), np.uint8); err = np.zeros((S, self.cfg.max_pts), np.float32)
+        ml = self.cfg.max_level if max_level is None else max_level
+        _check(lib().gf2_tracker_track(self.h, S, _p(prev), _p(cur), C.c_size_t(self.cfg.width), _p(npts), _p(pts), _p(out), _p(status), _p(err), int(flags), int(ml)))
+        return out, status, err
+
+    def track_fb(self, prev, cur, prev_pts, n_pts=None, max_level=None):
+        """forward + reverse check fused (trackImage without prediction). Returns (cur_pts, status)."""
+        S, prev, cur, pts, npts = self._prep(prev, cur, prev_pts, n_pts)
+        out = np.zeros_like(pts); status = np.zeros((S, self.cfg.max_pts), np.uint8)
+        ml = self.cfg.max_level if max_level is None else max_level
+        _check(lib().gf2_tracker_track_fb(self.h, S, _p(prev), _p(cur), C.c_size_t(self.cfg.width), _p(npts), _p(pts), _p(out), _p(status), int(ml)))
+        return out, status
+
+    def last_timing(self):
+        t = np.zeros(8)
+        _check(lib().gf2_tracker_last_timing(self.h, _p(t)))
+        return {"total_ms": t[0], "pyramid_ms": t[1], "lk_ms": t[2], "launches": int(t[3])}

@@ -176,7 +176,7 @@ int gf2_solver_create(const gf2_solver_cfg* cfg, gf2_solver** out) {
   A(k.Svis, double, (size_t)B * kNVMax * kNVMax); A(k.gvis, double, (size_t)B * kNVP); A(k.gschur, double, (size_t)B * kNVP); A(k.Udiag, double, (size_t)B * kNVMax);
   A(k.lm_v, double, (size_t)B * Lm); A(k.lm_g, double, (size_t)B * Lm); A(k.lm_s, double, (size_t)B * Lm); A(k.lm_z, double, (size_t)B * Lm);
   A(k.sx, double, (size_t)B * h->D); A(k.zx, double, (size_t)B * h->D); A(k.ux, double, (size_t)B * h->D); A(k.ex_diag, double, (size_t)B * h->D);
-  A(k.imu_H, double, (size_t)B * (F - 1) * 465); A(k.imu_g, double, (size_t)B * (F - 1) * 30);
+  A(k.imu_H, double, (size_t)B * (F - 1) * 675); A(k.imu_g, double, (size_t)B * (F - 1) * 30);
   A(k.prior_g, double, (size_t)B * kP); A(k.cost_nv, double, B);
   A(k.trace, double, (size_t)B * 64 * 6);
   A(k.perm, int32_t, (size_t)B * Lm); A(k.task_first, int32_t, (size_t)B * kMaxTasks); A(k.task_cnt, int32_t, (size_t)B * kMaxTasks);

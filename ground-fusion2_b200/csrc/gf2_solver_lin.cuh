@@ -234,11 +234,17 @@ __global__ void __launch_bounds__(kLinThreads, 1) k_linearize(KP p, int w0) {
   }
   __syncthreads();
   double* Svis = p.Svis + (size_t)w * kNVMax * kNVMax;
-  for (int idx = t; idx < NV * NV; idx += kLinThreads) {
-    const int r = idx / NV, c = idx % NV;
+  // blocked output: lower block pairs (bi >= bj) in the order bi (bi + 1) / 2 + bj, each a row-major 6x6 block (the layout
+  // k_solve2 assembles from); diagonal blocks are written symmetric from their upper triangle
+  for (int idx = t; idx < (F * (F + 1) / 2) * 36; idx += kLinThreads) {
+    const int blk = idx / 36, e = idx % 36;
+    int bi = 0; while ((bi + 1) * (bi + 2) / 2 <= blk) bi++;
+    const int bj = blk - bi * (bi + 1) / 2;
+    const int r = 6 * bi + e / 6, c = 6 * bj + e % 6;
     const int a = r <= c ? r : c, b = r <= c ? c : r;  // upper element (a <= b) of U and of the Schur tiles
-    Svis[r * kNVMax + c] = S.U[ublk(a / 6, b / 6, F) + (a % 6) * 6 + (b % 6)] - S.WT[a * kNVP + b];
+    Svis[idx] = S.U[ublk(a / 6, b / 6, F) + (a % 6) * 6 + (b % 6)] - S.WT[a * kNVP + b];
   }
+  (void)NV;
   if (t < NV) {
     p.gvis[(size_t)w * kNVP + t] = S.g[t];                       // full visual gradient J^T r (pose part)
     p.gschur[(size_t)w * kNVP + t] = S.WT[t * kNVP + 66];         // sum_l w_l g_l / v'_l, subtracted to form the reduced rhs

@@ -33,10 +33,10 @@ __global__ void __launch_bounds__(kNonvisThreads) k_nonvis(KP p, int w0) {
   if (p.imu) {
     for (int k = wid; k < F - 1; k += nw) {
       const gf2_imu_preint& pre = p.imu[(size_t)w * (F - 1) + k];
-      double* Hout = p.imu_H + ((size_t)w * (F - 1) + k) * 465;
+      double* Hout = p.imu_H + ((size_t)w * (F - 1) + k) * 675;
       double* gout = p.imu_g + ((size_t)w * (F - 1) + k) * 30;
       if (!pre.valid || pre.sum_dt > 10.0) {
-        for (int i = lane; i < 465; i += 32) Hout[i] = 0.0;
+        for (int i = lane; i < 675; i += 32) Hout[i] = 0.0;
         if (lane < 30) gout[lane] = 0.0;
         continue;
       }
@@ -52,8 +52,11 @@ __global__ void __launch_bounds__(kNonvisThreads) k_nonvis(KP p, int w0) {
       }
       __syncwarp();
       if (lane == 0) { double c = 0; for (int a = 0; a < 15; a++) c += r[a] * r[a]; cost += 0.5 * c; }
-      for (int a = 0; a < 30; a++) {  // row a of the packed lower triangle: lanes over columns b <= a
-        if (lane <= a) { double acc = 0; for (int rr = 0; rr < 15; rr++) acc += J[rr * 30 + a] * J[rr * 30 + lane]; Hout[a * (a + 1) / 2 + lane] = acc; }
+      for (int idx = lane; idx < 675; idx += 32) {  // three 15x15 blocks of J^T J: (i,i), (j,i), (j,j)
+        const int blk = idx / 225, e = idx % 225;
+        const int a = e / 15 + (blk >= 1 ? 15 : 0), b = e % 15 + (blk == 2 ? 15 : 0);
+        double acc = 0; for (int rr = 0; rr < 15; rr++) acc += J[rr * 30 + a] * J[rr * 30 + b];
+        Hout[idx] = acc;
       }
       if (lane < 30) { double acc = 0; for (int rr = 0; rr < 15; rr++) acc += J[rr * 30 + lane] * r[rr]; gout[lane] = acc; }
       __syncwarp();
@@ -136,12 +139,11 @@ __global__ void __launch_bounds__(kSolveThreads, 1) k_solve2(KP p, int w0) {
   for (int i = t; i < NB * kBlk; i += nt) A[i] = 0.0;
   for (int i = t; i < F * 16; i += nt) { S.g[i] = 0.0; S.gs[i] = 0.0; S.Hd[i] = 0.0; S.z[i] = 0.0; S.u[i] = 0.0; }
   __syncthreads();
-  // ---- assembly: visual Schur complement
+  // ---- assembly: visual Schur complement (blocked 6x6 layout written by k_linearize: coalesced read, pose part of each block)
   const double* Svis = p.Svis + (size_t)w * kNVMax * kNVMax;
-  for (int idx = t; idx < NV * NV; idx += nt) {
-    const int a = idx / NV, b = idx % NV;
-    if (b > a) continue;
-    Ael(A, 15 * (a / 6) + a % 6, 15 * (b / 6) + b % 6) = Svis[a * kNVMax + b];
+  for (int idx = t; idx < NB * 36; idx += nt) {
+    const int blk = idx / 36, e = idx % 36;
+    A[blk * kBlk + (e / 6) * kBS + e % 6] = Svis[idx];
   }
   if (t < NV) { const int da = 15 * (t / 6) + t % 6; S.g[da] = p.gvis[(size_t)w * kNVP + t]; S.gs[da] = p.gschur[(size_t)w * kNVP + t]; S.Hd[da] = p.Udiag[(size_t)w * kNVMax + t]; }
   __syncthreads();
@@ -159,24 +161,32 @@ __global__ void __launch_bounds__(kSolveThreads, 1) k_solve2(KP p, int w0) {
     }
     __syncthreads();
   }
-  // ---- IMU blocks: factor k covers tangent rows 15k .. 15k+29; even then odd factors (frame k+1 is shared)
+  // ---- IMU blocks, by destination: A_KK += H_{K-1}[(j,j)] + H_K[(i,i)],  A_{K+1,K} += H_K[(j,i)]
   if (p.imu) {
-    for (int phase = 0; phase < 2; phase++) {
-      for (int k = 2 * wid + phase; k < F - 1; k += 2 * nwarp) {
-        const double* Hk = p.imu_H + ((size_t)w * (F - 1) + k) * 465;
-        const double* gk = p.imu_g + ((size_t)w * (F - 1) + k) * 30;
-        const int base = 15 * k;
-        for (int idx = lane; idx < 465; idx += 32) {
-          int a = (int)((sqrt(8.0 * idx + 1.0) - 1.0) * 0.5); while (a * (a + 1) / 2 > idx) a--; while ((a + 1) * (a + 2) / 2 <= idx) a++;
-          const int b = idx - a * (a + 1) / 2;
-          const double v = Hk[idx];
-          Ael(A, base + a, base + b) += v;
-          if (a == b) S.Hd[base + a] += v;
-        }
-        if (lane < 30) S.g[base + lane] += gk[lane];
+    const double* Hw = p.imu_H + (size_t)w * (F - 1) * 675;
+    const double* gw = p.imu_g + (size_t)w * (F - 1) * 30;
+    for (int idx = t; idx < (2 * F - 1) * 225; idx += nt) {
+      const int e = idx % 225, r = e / 15, c = e % 15;
+      if (idx < F * 225) {
+        const int K = idx / 225;
+        double v = 0.0;
+        if (K > 0) v += Hw[(K - 1) * 675 + 450 + e];
+        if (K < F - 1) v += Hw[K * 675 + e];
+        if (c <= r) A[bidx(K, K) + r * kBS + c] += v;
+        if (r == c) S.Hd[15 * K + r] += v;
+      } else {
+        const int K = idx / 225 - F;
+        A[bidx(K + 1, K) + r * kBS + c] += Hw[K * 675 + 225 + e];
       }
-      __syncthreads();
     }
+    for (int i = t; i < D; i += nt) {
+      const int K = i / 15, r = i % 15;
+      double v = 0.0;
+      if (K > 0) v += gw[(K - 1) * 30 + 15 + r];
+      if (K < F - 1) v += gw[K * 30 + r];
+      S.g[i] += v;
+    }
+    __syncthreads();
   }
   if (t == 0) { st.x_cost = st.cost_vis + p.cost_nv[w]; if (st.iteration == 0) st.initial_cost = st.x_cost; }
   if (p.Sfull) {
@@ -221,34 +231,35 @@ __global__ void __launch_bounds__(kSolveThreads, 1) k_solve2(KP p, int w0) {
   __syncthreads();
   if (S.flag == 2) return;
 
-  // ---- blocked Cholesky (right-looking over 15x15 frame blocks)
-  for (int K = 0; K < F; K++) {
+  // ---- blocked Cholesky (right-looking over 15x15 frame blocks) with one-step look-ahead: warp 0 factors diagonal block
+  // K+1 as soon as its own trailing pair (K+1, K+1) is done, while warps 1..7 finish the rest of trailing update K
+  auto factor_diag = [&](int K) {  // executed by warp 0; lane = row, the row lives in registers
     double* Akk = A + bidx(K, K);
-    if (wid == 0) {
-      // diagonal block: lane = row, the row lives in registers, pivots/columns broadcast by shuffles
-      double a[15];
+    double a[15];
 #pragma unroll
-      for (int c = 0; c < 15; c++) a[c] = (lane < 15 && c <= lane) ? Akk[lane * kBS + c] : 0.0;
-      bool bad = false;
+    for (int c = 0; c < 15; c++) a[c] = (lane < 15 && c <= lane) ? Akk[lane * kBS + c] : 0.0;
+    bool bad = false;
 #pragma unroll
-      for (int j = 0; j < 15; j++) {
-        const double d = __shfl_sync(0xffffffffu, a[j], j);
-        if (!(d > 0.0)) bad = true;
-        const double rs = rsqrt(fmax(d, 1e-300));  // fp64 sqrt/div are long dependent software sequences: one rsqrt + multiplies
-        const double lj = (lane == j) ? d * rs : a[j] * rs;
-        if (lane == j) S.dinv[16 * K + j] = rs;
-        if (lane >= j) a[j] = lj;
+    for (int j = 0; j < 15; j++) {
+      const double d = __shfl_sync(0xffffffffu, a[j], j);
+      if (!(d > 0.0)) bad = true;
+      const double rs = rsqrt(fmax(d, 1e-300));  // fp64 sqrt/div are long dependent software sequences: one rsqrt + multiplies
+      const double lj = (lane == j) ? d * rs : a[j] * rs;
+      if (lane == j) S.dinv[16 * K + j] = rs;
+      if (lane >= j) a[j] = lj;
 #pragma unroll
-        for (int k = j + 1; k < 15; k++) { const double lkj = __shfl_sync(0xffffffffu, lj, k); if (lane >= k) a[k] -= lj * lkj; }
-      }
-      if (lane < 15) {
-#pragma unroll
-        for (int c = 0; c < 15; c++) Akk[lane * kBS + c] = (c <= lane) ? a[c] : 0.0;
-      }
-      if (bad && lane == 0) S.flag = 1;
+      for (int k = j + 1; k < 15; k++) { const double lkj = __shfl_sync(0xffffffffu, lj, k); if (lane >= k) a[k] -= lj * lkj; }
     }
-    __syncthreads();
-    if (S.flag) break;
+    if (lane < 15) {
+#pragma unroll
+      for (int c = 0; c < 15; c++) Akk[lane * kBS + c] = (c <= lane) ? a[c] : 0.0;
+    }
+    if (bad && lane == 0) S.flag = 1;
+  };
+  if (wid == 0) factor_diag(0);
+  __syncthreads();
+  for (int K = 0; K < F && !S.flag; K++) {
+    const double* Akk = A + bidx(K, K);
     // panel: X L_KK^T = A_IK, one thread per row of the block column (substitution over the 15 columns)
     if (t < 15 * (F - 1 - K)) {
       double* row = A + bidx(K + 1 + t / 15, K) + (t % 15) * kBS;
@@ -270,10 +281,14 @@ __global__ void __launch_bounds__(kSolveThreads, 1) k_solve2(KP p, int w0) {
     {
       const int m = F - 1 - K;
       const int npairs = m * (m + 1) / 2;
-      for (int q = wid; q < npairs; q += nwarp) {
-        int a = (int)((sqrtf(8.0f * q + 1.0f) - 1.0f) * 0.5f); while (a * (a + 1) / 2 > q) a--; while ((a + 1) * (a + 2) / 2 <= q) a++;
-        const int b = q - a * (a + 1) / 2;
-        block_mma(A + bidx(K + 1 + a, K + 1 + b), A + bidx(K + 1 + a, K), A + bidx(K + 1 + b, K), true, -1.0, lane);
+      if (wid == 0) {
+        if (npairs > 0) { block_mma(A + bidx(K + 1, K + 1), A + bidx(K + 1, K), A + bidx(K + 1, K), true, -1.0, lane); __syncwarp(); factor_diag(K + 1); }
+      } else {
+        for (int q = wid; q < npairs; q += nwarp - 1) {  // pairs 1 .. npairs-1 over warps 1..7 (pair 0 = (K+1, K+1) is warp 0's)
+          int a = 0; while ((a + 1) * (a + 2) / 2 <= q) a++;
+          const int b = q - a * (a + 1) / 2;
+          block_mma(A + bidx(K + 1 + a, K + 1 + b), A + bidx(K + 1 + a, K), A + bidx(K + 1 + b, K), true, -1.0, lane);
+        }
       }
     }
     __syncthreads();
@@ -307,43 +322,47 @@ __global__ void __launch_bounds__(kSolveThreads, 1) k_solve2(KP p, int w0) {
     }
   }
   __syncthreads();
-  // ---- z = S'^-1 g: forward then backward block substitution (z kept per block with stride 16)
-  for (int i = t; i < D; i += nt) S.z[16 * (i / 15) + i % 15] = S.g[i] - S.gs[i];  // reduced rhs
+  // ---- z = S'^-1 (g - g_schur): forward then backward block substitution by warp 0 alone (block-wide barriers cost more
+  // than the 2 x 11 small steps); z kept per block with stride 16
+  for (int i = t; i < D; i += nt) S.z[16 * (i / 15) + i % 15] = S.g[i] - S.gs[i];
   __syncthreads();
-  for (int K = 0; K < F; K++) {
-    const double* Li = S.Linv + K * kBlk;
-    double v = 0;
-    if (t < 15) { for (int c = 0; c <= t; c++) v += Li[t * kBS + c] * S.z[16 * K + c]; }
-    __syncthreads();
-    if (t < 15) S.z[16 * K + t] = v;
-    __syncthreads();
-    for (int row = t; row < 15 * (F - 1 - K); row += nt) {
-      const int I = K + 1 + row / 15, r = row % 15;
-      const double* L = A + bidx(I, K) + r * kBS;
-      double acc = 0;
+  if (wid == 0) {
+    for (int K = 0; K < F; K++) {
+      const double* Li = S.Linv + K * kBlk;
+      double v = 0;
+      if (lane < 15) { for (int c = 0; c <= lane; c++) v += Li[lane * kBS + c] * S.z[16 * K + c]; }
+      __syncwarp();
+      if (lane < 15) S.z[16 * K + lane] = v;
+      __syncwarp();
+      for (int row = lane; row < 15 * (F - 1 - K); row += 32) {
+        const int I = K + 1 + row / 15, r = row % 15;
+        const double* Lr = A + bidx(I, K) + r * kBS;
+        double acc = 0;
 #pragma unroll
-      for (int c = 0; c < 15; c++) acc += L[c] * S.z[16 * K + c];
-      S.z[16 * I + r] -= acc;
+        for (int c = 0; c < 15; c++) acc += Lr[c] * S.z[16 * K + c];
+        S.z[16 * I + r] -= acc;
+      }
+      __syncwarp();
     }
-    __syncthreads();
-  }
-  for (int K = F - 1; K >= 0; K--) {
-    const double* Li = S.Linv + K * kBlk;
-    double v = 0;
-    if (t < 15) { for (int r = t; r < 15; r++) v += Li[r * kBS + t] * S.z[16 * K + r]; }
-    __syncthreads();
-    if (t < 15) S.z[16 * K + t] = v;
-    __syncthreads();
-    for (int col = t; col < 15 * K; col += nt) {
-      const int J = col / 15, c = col % 15;
-      const double* L = A + bidx(K, J) + c;
-      double acc = 0;
+    for (int K = F - 1; K >= 0; K--) {
+      const double* Li = S.Linv + K * kBlk;
+      double v = 0;
+      if (lane < 15) { for (int r = lane; r < 15; r++) v += Li[r * kBS + lane] * S.z[16 * K + r]; }
+      __syncwarp();
+      if (lane < 15) S.z[16 * K + lane] = v;
+      __syncwarp();
+      for (int col = lane; col < 15 * K; col += 32) {
+        const int J = col / 15, c = col % 15;
+        const double* Lc = A + bidx(K, J) + c;
+        double acc = 0;
 #pragma unroll
-      for (int r = 0; r < 15; r++) acc += L[r * kBS] * S.z[16 * K + r];
-      S.z[16 * J + c] -= acc;
+        for (int r = 0; r < 15; r++) acc += Lc[r * kBS] * S.z[16 * K + r];
+        S.z[16 * J + c] -= acc;
+      }
+      __syncwarp();
     }
-    __syncthreads();
   }
+  __syncthreads();
   // y = L^T z and L^T u: z^T S' z = |L^T z|^2 etc. (explicit quadratic forms for the model cost change)
   double s3[3] = {0, 0, 0};  // uSu, uSz, zSz
   for (int col = t; col < D; col += nt) {

@@ -1,18 +1,362 @@
-// gf2_tracker.cu — pyramidal Lucas-Kanade tracker (cv::calcOpticalFlowPyrLK replacement). Placeholder until the
-// kernels land: every entry point reports GF2_ERR_UNSUPPORTED.
+// gf2_tracker.cu — pyramidal Lucas-Kanade on sm_100a: the cv::calcOpticalFlowPyrLK calls of FeatureTracker::trackImage
+// (VE/featureTracker/feature_tracker.cpp:122,132,135,141) for a batch of independent image streams.
+//
+//   k_pyrdown   cv::pyrDown for 8-bit images (5x5 [1 4 6 4 1], BORDER_REFLECT_101, (sum + 128) >> 8)
+//   k_scharr    un-normalised 3x3 Scharr derivatives of the template pyramid, int16 (dx, dy) interleaved
+//   k_lk        one warp per point: all pyramid levels coarse -> fine in one launch; the 21x21 template (I, Ix, Iy) lives in
+//               registers (14 pixels per lane), window sums are exact int64 warp reductions, the 2x2 solve is float32 with
+//               the operation order of OpenCV's lkpyramid.cpp (no FMA contraction)
+// The integer patch extraction (14-bit fixed-point bilinear weights, CV_DESCALE) is bit-exact with OpenCV; only the window
+// sums differ (OpenCV accumulates them in float32 in SIMD-path order), i.e. by float32 rounding of A and b.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+#include <vector>
 #include "gf2_common.h"
+
+namespace gf2 {
+
+constexpr int kMaxLevels = 4;  // levels 0..3
+constexpr int kWBits = 14;
+
+struct Pyr {  // one image pyramid on the device
+  uint8_t* img[kMaxLevels];
+  short2* der[kMaxLevels];
+  int w[kMaxLevels], h[kMaxLevels];
+};
+
+__device__ __forceinline__ int reflect101(int i, int n) {
+  if (n == 1) return 0;
+  const int p = 2 * (n - 1);
+  i %= p; if (i < 0) i += p;
+  return i >= n ? p - i : i;
+}
+
+__global__ void k_pyrdown(const uint8_t* __restrict__ src, int sw, int sh, size_t sstride, uint8_t* __restrict__ dst, int dw, int dh, size_t dstride_img,
+                          size_t src_img_stride) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y, s = blockIdx.z;
+  if (x >= dw || y >= dh) return;
+  const uint8_t* S = src + (size_t)s * src_img_stride;
+  const int k[5] = {1, 4, 6, 4, 1};
+  int acc = 0;
+#pragma unroll
+  for (int dy = -2; dy <= 2; dy++) {
+    const uint8_t* row = S + (size_t)reflect101(2 * y + dy, sh) * sstride;
+    int r = 0;
+#pragma unroll
+    for (int dx = -2; dx <= 2; dx++) r += k[dx + 2] * row[reflect101(2 * x + dx, sw)];
+    acc += k[dy + 2] * r;
+  }
+  dst[(size_t)s * dstride_img + (size_t)y * dw + x] = (uint8_t)((acc + 128) >> 8);
+}
+
+__global__ void k_scharr(const uint8_t* __restrict__ src, int w, int h, size_t stride, size_t img_stride, short2* __restrict__ dst, size_t dst_img_stride) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y, s = blockIdx.z;
+  if (x >= w || y >= h) return;
+  const uint8_t* S = src + (size_t)s * img_stride;
+  const int xm = reflect101(x - 1, w), xp = reflect101(x + 1, w), ym = reflect101(y - 1, h), yp = reflect101(y + 1, h);
+  const uint8_t *r0 = S + (size_t)ym * stride, *r1 = S + (size_t)y * stride, *r2 = S + (size_t)yp * stride;
+  const int t0m = (r0[xm] + r2[xm]) * 3 + r1[xm] * 10, t0p = (r0[xp] + r2[xp]) * 3 + r1[xp] * 10;
+  const int t1m = r2[xm] - r0[xm], t1c = r2[x] - r0[x], t1p = r2[xp] - r0[xp];
+  dst[(size_t)s * dst_img_stride + (size_t)y * w + x] = make_short2((short)(t0p - t0m), (short)((t1m + t1p) * 3 + t1c * 10));
+}
+
+__device__ __forceinline__ long long warp_sum_ll(long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ void lk_weights(float px, float py, int ipx, int ipy, int& w00, int& w01, int& w10, int& w11) {
+  const float a = __fsub_rn(px, (float)ipx), b = __fsub_rn(py, (float)ipy);
+  const float s = (float)(1 << kWBits);
+  w00 = __float2int_rn(__fmul_rn(__fmul_rn(__fsub_rn(1.f, a), __fsub_rn(1.f, b)), s));
+  w01 = __float2int_rn(__fmul_rn(__fmul_rn(a, __fsub_rn(1.f, b)), s));
+  w10 = __float2int_rn(__fmul_rn(__fmul_rn(__fsub_rn(1.f, a), b), s));
+  w11 = (1 << kWBits) - w00 - w01 - w10;
+}
+
+struct LkArgs {
+  int n_streams, max_pts, win, max_level, max_iters, flags;
+  float min_eig; double eps2;
+  const int32_t* n_pts;       // [n_streams]
+  const float* prev_pts;      // [n_streams][max_pts][2]
+  float* next_pts;            // in (initial flow) / out
+  uint8_t* status; float* err;
+  size_t img_stride[kMaxLevels], der_stride[kMaxLevels];
+  Pyr I, J;                   // template (prev) and search (next) pyramids, stream 0 base pointers
+};
+
+constexpr int kPix = 14;  // ceil(441 / 32)
+
+__global__ void __launch_bounds__(128) k_lk(LkArgs a) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int s = warp / a.max_pts, i = warp % a.max_pts;
+  if (s >= a.n_streams || i >= a.n_pts[s]) return;
+  const int win = a.win, npx = win * win;
+  const float half = (win - 1) * 0.5f;
+  const float2 pp = reinterpret_cast<const float2*>(a.prev_pts)[(size_t)s * a.max_pts + i];
+  float2 np = reinterpret_cast<float2*>(a.next_pts)[(size_t)s * a.max_pts + i];
+  bool ok = true; float errv = 0.f;
+  for (int level = a.max_level; level >= 0; level--) {
+    const int cols = a.I.w[level], rows = a.I.h[level];
+    const uint8_t* I = a.I.img[level] + (size_t)s * a.img_stride[level];
+    const uint8_t* J = a.J.img[level] + (size_t)s * a.img_stride[level];
+    const short2* dI = a.I.der[level] + (size_t)s * a.der_stride[level];
+    const float scale = 1.f / (float)(1 << level);
+    const float ppx = __fmul_rn(pp.x, scale), ppy = __fmul_rn(pp.y, scale);
+    float nx, ny;
+    if (level == a.max_level) {
+      if (a.flags & GF2_LK_USE_INITIAL_FLOW) { nx = __fmul_rn(np.x, scale); ny = __fmul_rn(np.y, scale); } else { nx = ppx; ny = ppy; }
+    } else { nx = __fmul_rn(np.x, 2.f); ny = __fmul_rn(np.y, 2.f); }
+    np = make_float2(nx, ny);
+    const float px = __fsub_rn(ppx, half), py = __fsub_rn(ppy, half);
+    const int ipx = (int)floorf(px), ipy = (int)floorf(py);
+    if (ipx < -win || ipx >= cols || ipy < -win || ipy >= rows) { if (level == 0) { ok = false; errv = 0.f; } continue; }
+    int w00, w01, w10, w11; lk_weights(px, py, ipx, ipy, w00, w01, w10, w11);
+    // template patch: intensity (x32), Ix, Iy as int16-range ints, kPix pixels per lane
+    int Iv[kPix], Ix[kPix], Iy[kPix];
+    long long s11 = 0, s12 = 0, s22 = 0;
+#pragma unroll
+    for (int m = 0; m < kPix; m++) {
+      const int idx = lane + 32 * m;
+      Iv[m] = 0; Ix[m] = 0; Iy[m] = 0;
+      if (idx < npx) {
+        const int y = ipy + idx / win, x = ipx + idx % win;
+        const int y0 = reflect101(y, rows), y1 = reflect101(y + 1, rows), x0 = reflect101(x, cols), x1 = reflect101(x + 1, cols);
+        Iv[m] = ((int)I[(size_t)y0 * cols + x0] * w00 + (int)I[(size_t)y0 * cols + x1] * w01 + (int)I[(size_t)y1 * cols + x0] * w10 + (int)I[(size_t)y1 * cols + x1] * w11 + (1 << (kWBits - 5 - 1))) >> (kWBits - 5);
+        // derivative buffers are zero outside the image (BORDER_CONSTANT)
+        const bool yi0 = y >= 0 && y < rows, yi1 = y + 1 >= 0 && y + 1 < rows, xi0 = x >= 0 && x < cols, xi1 = x + 1 >= 0 && x + 1 < cols;
+        const short2 z = make_short2(0, 0);
+        const short2 d00 = (yi0 && xi0) ? dI[(size_t)y * cols + x] : z, d01 = (yi0 && xi1) ? dI[(size_t)y * cols + x + 1] : z;
+        const short2 d10 = (yi1 && xi0) ? dI[(size_t)(y + 1) * cols + x] : z, d11 = (yi1 && xi1) ? dI[(size_t)(y + 1) * cols + x + 1] : z;
+        Ix[m] = (d00.x * w00 + d01.x * w01 + d10.x * w10 + d11.x * w11 + (1 << (kWBits - 1))) >> kWBits;
+        Iy[m] = (d00.y * w00 + d01.y * w01 + d10.y * w10 + d11.y * w11 + (1 << (kWBits - 1))) >> kWBits;
+        s11 += (long long)Ix[m] * Ix[m]; s12 += (long long)Ix[m] * Iy[m]; s22 += (long long)Iy[m] * Iy[m];
+      }
+    }
+    s11 = warp_sum_ll(s11); s12 = warp_sum_ll(s12); s22 = warp_sum_ll(s22);
+    const float FS = 1.f / (float)(1 << 20);
+    const float A11 = __fmul_rn((float)s11, FS), A12 = __fmul_rn((float)s12, FS), A22 = __fmul_rn((float)s22, FS);
+    float D = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
+    const float dA = __fsub_rn(A11, A22);
+    const float me = __fdiv_rn(__fsub_rn(__fadd_rn(A22, A11), __fsqrt_rn(__fadd_rn(__fmul_rn(dA, dA), __fmul_rn(__fmul_rn(4.f, A12), A12)))), (float)(2 * win * win));
+    if (me < a.min_eig || D < 1.1920929e-07f) { if (level == 0) ok = false; continue; }
+    D = __fdiv_rn(1.f, D);
+    nx = __fsub_rn(nx, half); ny = __fsub_rn(ny, half);
+    float pdx = 0.f, pdy = 0.f;
+    for (int j = 0; j < a.max_iters; j++) {
+      const int inx = (int)floorf(nx), iny = (int)floorf(ny);
+      if (inx < -win || inx >= cols || iny < -win || iny >= rows) { if (level == 0) ok = false; break; }
+      int v00, v01, v10, v11; lk_weights(nx, ny, inx, iny, v00, v01, v10, v11);
+      long long sb1 = 0, sb2 = 0;
+#pragma unroll
+      for (int m = 0; m < kPix; m++) {
+        const int idx = lane + 32 * m;
+        if (idx < npx) {
+          const int y = iny + idx / win, x = inx + idx % win;
+          const int y0 = reflect101(y, rows), y1 = reflect101(y + 1, rows), x0 = reflect101(x, cols), x1 = reflect101(x + 1, cols);
+          const int jv = ((int)J[(size_t)y0 * cols + x0] * v00 + (int)J[(size_t)y0 * cols + x1] * v01 + (int)J[(size_t)y1 * cols + x0] * v10 + (int)J[(size_t)y1 * cols + x1] * v11 + (1 << (kWBits - 5 - 1))) >> (kWBits - 5);
+          const int diff = jv - Iv[m];
+          sb1 += (long long)diff * Ix[m]; sb2 += (long long)diff * Iy[m];
+        }
+      }
+      sb1 = warp_sum_ll(sb1); sb2 = warp_sum_ll(sb2);
+      const float b1 = __fmul_rn((float)sb1, FS), b2 = __fmul_rn((float)sb2, FS);
+      const float ddx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), D);
+      const float ddy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), D);
+      nx = __fadd_rn(nx, ddx); ny = __fadd_rn(ny, ddy);
+      np = make_float2(__fadd_rn(nx, half), __fadd_rn(ny, half));
+      if ((double)ddx * (double)ddx + (double)ddy * (double)ddy <= a.eps2) break;
+      if (j > 0 && fabs((double)__fadd_rn(ddx, pdx)) < 0.01 && fabs((double)__fadd_rn(ddy, pdy)) < 0.01) {
+        np.x = __fsub_rn(np.x, __fmul_rn(ddx, 0.5f)); np.y = __fsub_rn(np.y, __fmul_rn(ddy, 0.5f));
+        break;
+      }
+      pdx = ddx; pdy = ddy;
+    }
+    if (ok && level == 0) {  // err = mean |J - I| / 32 over the window at the final position
+      const float fx = __fsub_rn(np.x, half), fy = __fsub_rn(np.y, half);
+      const int inx = (int)floorf(fx), iny = (int)floorf(fy);
+      if (inx < -win || inx >= cols || iny < -win || iny >= rows) { ok = false; errv = 0.f; continue; }
+      int v00, v01, v10, v11; lk_weights(fx, fy, inx, iny, v00, v01, v10, v11);
+      long long se = 0;
+#pragma unroll
+      for (int m = 0; m < kPix; m++) {
+        const int idx = lane + 32 * m;
+        if (idx < npx) {
+          const int y = iny + idx / win, x = inx + idx % win;
+          const int y0 = reflect101(y, rows), y1 = reflect101(y + 1, rows), x0 = reflect101(x, cols), x1 = reflect101(x + 1, cols);
+          const int jv = ((int)J[(size_t)y0 * cols + x0] * v00 + (int)J[(size_t)y0 * cols + x1] * v01 + (int)J[(size_t)y1 * cols + x0] * v10 + (int)J[(size_t)y1 * cols + x1] * v11 + (1 << (kWBits - 5 - 1))) >> (kWBits - 5);
+          se += llabs((long long)(jv - Iv[m]));
+        }
+      }
+      se = warp_sum_ll(se);
+      errv = __fdiv_rn((float)se, (float)(32 * win * win));
+    }
+  }
+  if (lane == 0) {
+    reinterpret_cast<float2*>(a.next_pts)[(size_t)s * a.max_pts + i] = np;
+    a.status[(size_t)s * a.max_pts + i] = ok ? 1 : 0;
+    if (a.err) a.err[(size_t)s * a.max_pts + i] = ok ? errv : 0.f;
+  }
+}
+
+// status &= reverse ok && |prev - reverse| <= 0.5 (FeatureTracker::distance in double, feature_tracker.cpp:22-28,146)
+__global__ void k_fb_check(int total, const float* prev_pts, const float* rev_pts, const uint8_t* rstatus, uint8_t* status) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const double dx = (double)prev_pts[2 * i] - (double)rev_pts[2 * i], dy = (double)prev_pts[2 * i + 1] - (double)rev_pts[2 * i + 1];
+  const double d = sqrt(dx * dx + dy * dy);
+  status[i] = (status[i] && rstatus[i] && d <= 0.5) ? 1 : 0;
+}
+
+}  // namespace gf2
+
+using namespace gf2;
+
+struct gf2_tracker {
+  gf2_tracker_cfg cfg;
+  cudaStream_t stream;
+  Pyr pyr[2];            // ping-pong: [cur_slot] holds the pyramid of the last `cur`
+  size_t img_stride[kMaxLevels], der_stride[kMaxLevels];
+  int cur_slot = 0; bool have_prev = false;
+  int32_t* d_npts; float *d_prev_pts, *d_next_pts, *d_rev_pts, *d_err; uint8_t *d_status, *d_rstatus;
+  std::vector<void*> allocs;
+  cudaEvent_t ev[4];
+  double timing[8];
+};
+
+#define GF2T_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return gf2::fail(GF2_ERR_CUDA, "%s: %s", #x, cudaGetErrorString(e_)); } while (0)
+
+static int build_pyramid(gf2_tracker* h, int slot, int n_streams, const uint8_t* host_img, size_t stride, bool derivs_upto_all, int deriv_levels) {
+  Pyr& P = h->pyr[slot];
+  const int W = h->cfg.width, H = h->cfg.height;
+  GF2T_CUDA(cudaMemcpy2DAsync(P.img[0], W, host_img, stride, W, (size_t)H * n_streams, cudaMemcpyHostToDevice, h->stream));
+  for (int l = 1; l <= h->cfg.max_level; l++) {
+    dim3 b(32, 8), g((P.w[l] + 31) / 32, (P.h[l] + 7) / 8, n_streams);
+    k_pyrdown<<<g, b, 0, h->stream>>>(P.img[l - 1], P.w[l - 1], P.h[l - 1], P.w[l - 1], P.img[l], P.w[l], P.h[l], h->img_stride[l], h->img_stride[l - 1]);
+  }
+  (void)derivs_upto_all;
+  for (int l = 0; l <= deriv_levels; l++) {
+    dim3 b(32, 8), g((P.w[l] + 31) / 32, (P.h[l] + 7) / 8, n_streams);
+    k_scharr<<<g, b, 0, h->stream>>>(P.img[l], P.w[l], P.h[l], P.w[l], h->img_stride[l], P.der[l], h->der_stride[l]);
+  }
+  GF2T_CUDA(cudaGetLastError());
+  return GF2_OK;
+}
+
 extern "C" {
-int gf2_tracker_create(const gf2_tracker_cfg* cfg, gf2_tracker** out) { (void)cfg; (void)out; return gf2::fail(GF2_ERR_UNSUPPORTED, "tracker not built yet"); }
-void gf2_tracker_destroy(gf2_tracker* h) { (void)h; }
+
+int gf2_tracker_create(const gf2_tracker_cfg* cfg, gf2_tracker** out) {
+  if (!cfg || !out) return gf2::fail(GF2_ERR_INVALID, "null argument");
+  if (cfg->max_level < 0 || cfg->max_level >= kMaxLevels) return gf2::fail(GF2_ERR_INVALID, "max_level %d out of range [0, %d]", cfg->max_level, kMaxLevels - 1);
+  if (cfg->win != 21) return gf2::fail(GF2_ERR_UNSUPPORTED, "window %d: the kernel is specialised for the reference's 21x21 window", cfg->win);
+  if (cfg->width < 32 || cfg->height < 32 || cfg->max_pts < 1 || cfg->max_streams < 1) return gf2::fail(GF2_ERR_INVALID, "bad tracker dimensions");
+  int ndev = 0; if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= cfg->device) { cudaGetLastError(); return gf2::fail(GF2_ERR_CUDA, "CUDA device %d not available (no CPU fallback exists)", cfg->device); }
+  // OpenCV lowers maxLevel when a level gets smaller than the window; refuse such configurations instead of guessing
+  { int w = cfg->width, hh = cfg->height; for (int l = 0; l < cfg->max_level; l++) { w = (w + 1) / 2; hh = (hh + 1) / 2; } if (w <= cfg->win || hh <= cfg->win) return gf2::fail(GF2_ERR_INVALID, "coarsest level smaller than the window"); }
+  GF2T_CUDA(cudaSetDevice(cfg->device));
+  gf2_tracker* h = new gf2_tracker();
+  h->cfg = *cfg;
+  cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  const int S = cfg->max_streams;
+  auto alloc = [&](void** p, size_t bytes) { if (cudaMalloc(p, bytes) != cudaSuccess) return false; h->allocs.push_back(*p); return true; };
+  bool ok = true;
+  for (int slot = 0; slot < 2; slot++) {
+    int w = cfg->width, hh = cfg->height;
+    for (int l = 0; l <= cfg->max_level; l++) {
+      h->pyr[slot].w[l] = w; h->pyr[slot].h[l] = hh;
+      h->img_stride[l] = (size_t)w * hh; h->der_stride[l] = (size_t)w * hh;
+      ok = ok && alloc((void**)&h->pyr[slot].img[l], (size_t)w * hh * S) && alloc((void**)&h->pyr[slot].der[l], (size_t)w * hh * S * sizeof(short2));
+      w = (w + 1) / 2; hh = (hh + 1) / 2;
+    }
+  }
+  const size_t np = (size_t)S * cfg->max_pts;
+  ok = ok && alloc((void**)&h->d_npts, sizeof(int32_t) * S) && alloc((void**)&h->d_prev_pts, sizeof(float) * 2 * np) && alloc((void**)&h->d_next_pts, sizeof(float) * 2 * np) &&
+       alloc((void**)&h->d_rev_pts, sizeof(float) * 2 * np) && alloc((void**)&h->d_err, sizeof(float) * np) && alloc((void**)&h->d_status, np) && alloc((void**)&h->d_rstatus, np);
+  if (!ok) { gf2_tracker_destroy(h); return gf2::fail(GF2_ERR_CUDA, "tracker allocation failed"); }
+  for (auto& e : h->ev) cudaEventCreate(&e);
+  *out = h;
+  return GF2_OK;
+}
+
+void gf2_tracker_destroy(gf2_tracker* h) {
+  if (!h) return;
+  cudaSetDevice(h->cfg.device);
+  cudaStreamSynchronize(h->stream);
+  for (void* p : h->allocs) cudaFree(p);
+  for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+  cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+static int lk_launch(gf2_tracker* h, int n_streams, int slotI, int slotJ, const float* d_prev, float* d_next, uint8_t* d_status, float* d_err, int flags, int max_level) {
+  LkArgs a;
+  memset(&a, 0, sizeof(a));
+  a.n_streams = n_streams; a.max_pts = h->cfg.max_pts; a.win = h->cfg.win; a.max_level = max_level; a.max_iters = h->cfg.max_iters; a.flags = flags;
+  a.min_eig = (float)h->cfg.min_eig; a.eps2 = h->cfg.eps * h->cfg.eps;
+  a.n_pts = h->d_npts; a.prev_pts = d_prev; a.next_pts = d_next; a.status = d_status; a.err = d_err;
+  for (int l = 0; l < kMaxLevels; l++) { a.img_stride[l] = h->img_stride[l]; a.der_stride[l] = h->der_stride[l]; }
+  a.I = h->pyr[slotI]; a.J = h->pyr[slotJ];
+  const int warps = n_streams * h->cfg.max_pts;
+  k_lk<<<(warps + 3) / 4, 128, 0, h->stream>>>(a);
+  GF2T_CUDA(cudaGetLastError());
+  return GF2_OK;
+}
+
+static int track_common(gf2_tracker* h, int n_streams, const uint8_t* prev, const uint8_t* cur, size_t stride, const int32_t* n_pts, const float* prev_pts,
+                        float* cur_pts, uint8_t* status, float* err, int flags, int max_level, bool fb) {
+  if (!h || !cur || !n_pts || !prev_pts || !cur_pts || !status) return gf2::fail(GF2_ERR_INVALID, "null argument");
+  if (n_streams < 1 || n_streams > h->cfg.max_streams) return gf2::fail(GF2_ERR_INVALID, "n_streams %d outside [1, %d]", n_streams, h->cfg.max_streams);
+  if (max_level < 0 || max_level > h->cfg.max_level) return gf2::fail(GF2_ERR_INVALID, "max_level %d exceeds the tracker capacity %d", max_level, h->cfg.max_level);
+  if (stride < (size_t)h->cfg.width) return gf2::fail(GF2_ERR_INVALID, "stride smaller than the image width");
+  for (int s = 0; s < n_streams; s++) if (n_pts[s] < 0 || n_pts[s] > h->cfg.max_pts) return gf2::fail(GF2_ERR_INVALID, "n_pts[%d] = %d exceeds max_pts %d", s, n_pts[s], h->cfg.max_pts);
+  if (!prev && !h->have_prev) return gf2::fail(GF2_ERR_INVALID, "prev == NULL but no pyramid is cached from an earlier call");
+  cudaSetDevice(h->cfg.device);
+  const size_t np = (size_t)n_streams * h->cfg.max_pts;
+  cudaEventRecord(h->ev[0], h->stream);
+  int slotI = h->cur_slot, slotJ = 1 - h->cur_slot;
+  if (prev) { int rc = build_pyramid(h, slotI, n_streams, prev, stride, true, h->cfg.max_level); if (rc) return rc; }
+  { int rc = build_pyramid(h, slotJ, n_streams, cur, stride, true, h->cfg.max_level); if (rc) return rc; }  // derivatives of cur: reverse pass now, template of the next call
+  GF2T_CUDA(cudaMemcpyAsync(h->d_npts, n_pts, sizeof(int32_t) * n_streams, cudaMemcpyHostToDevice, h->stream));
+  GF2T_CUDA(cudaMemcpyAsync(h->d_prev_pts, prev_pts, sizeof(float) * 2 * np, cudaMemcpyHostToDevice, h->stream));
+  if (flags & GF2_LK_USE_INITIAL_FLOW) GF2T_CUDA(cudaMemcpyAsync(h->d_next_pts, cur_pts, sizeof(float) * 2 * np, cudaMemcpyHostToDevice, h->stream));
+  cudaEventRecord(h->ev[1], h->stream);
+  { int rc = lk_launch(h, n_streams, slotI, slotJ, h->d_prev_pts, h->d_next_pts, h->d_status, h->d_err, flags, max_level); if (rc) return rc; }
+  if (fb) {
+    // reverse: cur -> prev at maxLevel 1 with the initial flow = prev_pts (feature_tracker.cpp:139-142)
+    GF2T_CUDA(cudaMemcpyAsync(h->d_rev_pts, h->d_prev_pts, sizeof(float) * 2 * np, cudaMemcpyDeviceToDevice, h->stream));
+    int rc = lk_launch(h, n_streams, slotJ, slotI, h->d_next_pts, h->d_rev_pts, h->d_rstatus, nullptr, GF2_LK_USE_INITIAL_FLOW, 1 < h->cfg.max_level ? 1 : h->cfg.max_level);
+    if (rc) return rc;
+    k_fb_check<<<((int)np + 255) / 256, 256, 0, h->stream>>>((int)np, h->d_prev_pts, h->d_rev_pts, h->d_rstatus, h->d_status);
+  }
+  cudaEventRecord(h->ev[2], h->stream);
+  GF2T_CUDA(cudaMemcpyAsync(cur_pts, h->d_next_pts, sizeof(float) * 2 * np, cudaMemcpyDeviceToHost, h->stream));
+  GF2T_CUDA(cudaMemcpyAsync(status, h->d_status, np, cudaMemcpyDeviceToHost, h->stream));
+  if (err) GF2T_CUDA(cudaMemcpyAsync(err, h->d_err, sizeof(float) * np, cudaMemcpyDeviceToHost, h->stream));
+  cudaEventRecord(h->ev[3], h->stream);
+  GF2T_CUDA(cudaStreamSynchronize(h->stream));
+  h->cur_slot = slotJ; h->have_prev = true;  // prev_img = cur_img (feature_tracker.cpp:307)
+  float ms; memset(h->timing, 0, sizeof(h->timing));
+  cudaEventElapsedTime(&ms, h->ev[0], h->ev[3]); h->timing[0] = ms;
+  cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]); h->timing[1] = ms;  // upload + pyramids + derivatives
+  cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]); h->timing[2] = ms;  // LK kernels
+  h->timing[3] = (prev ? 2.0 : 1.0) * (h->cfg.max_level + (h->cfg.max_level + 1)) + (fb ? 3.0 : 1.0);  // launches
+  return GF2_OK;
+}
+
 int gf2_tracker_track(gf2_tracker* h, int n_streams, const uint8_t* prev, const uint8_t* cur, size_t stride, const int32_t* n_pts,
                       const float* prev_pts, float* cur_pts, uint8_t* status, float* err, int flags, int max_level) {
-  (void)h; (void)n_streams; (void)prev; (void)cur; (void)stride; (void)n_pts; (void)prev_pts; (void)cur_pts; (void)status; (void)err; (void)flags; (void)max_level;
-  return gf2::fail(GF2_ERR_UNSUPPORTED, "tracker not built yet");
+  return track_common(h, n_streams, prev, cur, stride, n_pts, prev_pts, cur_pts, status, err, flags, max_level, false);
 }
 int gf2_tracker_track_fb(gf2_tracker* h, int n_streams, const uint8_t* prev, const uint8_t* cur, size_t stride, const int32_t* n_pts,
                          const float* prev_pts, float* cur_pts, uint8_t* status, int max_level) {
-  (void)h; (void)n_streams; (void)prev; (void)cur; (void)stride; (void)n_pts; (void)prev_pts; (void)cur_pts; (void)status; (void)max_level;
-  return gf2::fail(GF2_ERR_UNSUPPORTED, "tracker not built yet");
+  return track_common(h, n_streams, prev, cur, stride, n_pts, prev_pts, cur_pts, status, nullptr, 0, max_level, true);
 }
-int gf2_tracker_last_timing(gf2_tracker* h, double out[8]) { (void)h; (void)out; return gf2::fail(GF2_ERR_UNSUPPORTED, "tracker not built yet"); }
+int gf2_tracker_last_timing(gf2_tracker* h, double out[8]) {
+  if (!h || !out) return gf2::fail(GF2_ERR_INVALID, "null argument");
+  memcpy(out, h->timing, sizeof(h->timing));
+  return GF2_OK;
 }
+
+}  // extern "C"
