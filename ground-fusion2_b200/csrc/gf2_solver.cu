@@ -15,29 +15,46 @@ using namespace gf2;
 namespace gf2 {
 
 // ------------------------------------------------------------------------------------------------ preintegration
-// IntegrationBase::push_back chain (VE/factor/integration_base.h:39-167): mid-point integration with 15x15 jacobian and
-// covariance propagation. One thread per interval; F and V are built explicitly and the sparse products are dense loops.
-__global__ void k_imu_preintegrate(int n_intervals, int max_samples, const gf2_imu_sample* samples, const int32_t* n_samples,
-                                   const double* first, const double* lin_bias, double acc_n, double gyr_n, double acc_w, double gyr_w,
-                                   gf2_imu_preint* out) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+// IntegrationBase::push_back chain (VE/factor/integration_base.h:39-167): mid-point integration with the 15x15 jacobian
+// and covariance propagation  jacobian = F jacobian,  covariance = F covariance F^T + V noise V^T.
+// One warp per interval. Lane c (< 15) keeps column c of the jacobian and of the covariance in registers; F is block
+// sparse (identity + seven 3x3 blocks), so F x is eight 3x3 mat-vecs per column; F C F^T = F (F C)^T uses one transpose
+// through shared memory; V noise V^T comes from the 15x18 V staged in shared memory.
+struct FBlocks { M3 f01, f03, f04, f11, f21, f23, f24; double dt; };
+
+__device__ __forceinline__ void apply_F(const FBlocks& F, double (&x)[15]) {
+  const V3 x0 = mk3(x[0], x[1], x[2]), x1 = mk3(x[3], x[4], x[5]), x2 = mk3(x[6], x[7], x[8]), x3 = mk3(x[9], x[10], x[11]), x4 = mk3(x[12], x[13], x[14]);
+  const V3 n0 = x0 + mul(F.f01, x1) + F.dt * x2 + mul(F.f03, x3) + mul(F.f04, x4);
+  const V3 n1 = mul(F.f11, x1) - F.dt * x4;
+  const V3 n2 = mul(F.f21, x1) + x2 + mul(F.f23, x3) + mul(F.f24, x4);
+  x[0] = n0.x; x[1] = n0.y; x[2] = n0.z; x[3] = n1.x; x[4] = n1.y; x[5] = n1.z; x[6] = n2.x; x[7] = n2.y; x[8] = n2.z;
+}
+
+constexpr int kPreWarps = 4;
+
+__global__ void __launch_bounds__(32 * kPreWarps) k_imu_preintegrate(int n_intervals, int max_samples, const gf2_imu_sample* samples, const int32_t* n_samples,
+                                                                      const double* first, const double* lin_bias, double acc_n, double gyr_n, double acc_w, double gyr_w,
+                                                                      gf2_imu_preint* out) {
+  __shared__ double T[kPreWarps][15 * 16];
+  __shared__ double Vs[kPreWarps][15 * 18];
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int idx = blockIdx.x * kPreWarps + wid;
   if (idx >= n_intervals) return;
   const gf2_imu_sample* smp = samples + (size_t)idx * max_samples;
   V3 acc_0 = ld3(first + 6 * idx), gyr_0 = ld3(first + 6 * idx + 3);
   const V3 ba = ld3(lin_bias + 6 * idx), bg = ld3(lin_bias + 6 * idx + 3);
   V3 dp = mk3(0, 0, 0), dv = mk3(0, 0, 0); Q4 dq; dq.x = dq.y = dq.z = 0; dq.w = 1;
-  double Jm[225], C[225], Fm[225], T[225], V[270];
-  for (int i = 0; i < 225; i++) { Jm[i] = 0; C[i] = 0; }
-  for (int i = 0; i < 15; i++) Jm[i * 16] = 1.0;
+  double jc[15], cc[15];  // column `lane` of jacobian and covariance
+#pragma unroll
+  for (int r = 0; r < 15; r++) { jc[r] = (r == lane) ? 1.0 : 0.0; cc[r] = 0.0; }
   double sum_dt = 0;
-  const double nz[18] = {acc_n * acc_n, acc_n * acc_n, acc_n * acc_n, gyr_n * gyr_n, gyr_n * gyr_n, gyr_n * gyr_n,
-                         acc_n * acc_n, acc_n * acc_n, acc_n * acc_n, gyr_n * gyr_n, gyr_n * gyr_n, gyr_n * gyr_n,
-                         acc_w * acc_w, acc_w * acc_w, acc_w * acc_w, gyr_w * gyr_w, gyr_w * gyr_w, gyr_w * gyr_w};
+  const double nz[6] = {acc_n * acc_n, gyr_n * gyr_n, acc_n * acc_n, gyr_n * gyr_n, acc_w * acc_w, gyr_w * gyr_w};
+  double* Tw = T[wid]; double* Vw = Vs[wid];
   const int ns = n_samples[idx];
   for (int s = 0; s < ns; s++) {
     const double dt = smp[s].dt;
     const V3 acc_1 = ld3(smp[s].acc), gyr_1 = ld3(smp[s].gyr);
-    // midPointIntegration, integration_base.h:72-81
+    // midPointIntegration, integration_base.h:72-81 (every lane, uniform)
     const V3 un_acc_0 = qrot(dq, acc_0 - ba);
     const V3 un_gyr = 0.5 * (gyr_0 + gyr_1) - bg;
     Q4 hq; hq.w = 1; hq.x = un_gyr.x * dt / 2; hq.y = un_gyr.y * dt / 2; hq.z = un_gyr.z * dt / 2;
@@ -46,59 +63,74 @@ __global__ void k_imu_preintegrate(int n_intervals, int max_samples, const gf2_i
     const V3 un_acc = 0.5 * (un_acc_0 + un_acc_1);
     const V3 rp = dp + dt * dv + (0.5 * dt * dt) * un_acc;
     const V3 rv = dv + dt * un_acc;
-    // jacobian / covariance, integration_base.h:83-135
+    // F and V blocks, integration_base.h:83-131 (result_delta_q not normalised here, as in the reference)
     const M3 R_w_x = skew(un_gyr), R_a_0_x = skew(acc_0 - ba), R_a_1_x = skew(acc_1 - ba);
     const M3 dR = toR(dq), rR = toR(rq), I = eye3();
     const M3 IwR = sub(I, scale(R_w_x, dt));
-    for (int i = 0; i < 225; i++) Fm[i] = 0;
-    for (int i = 0; i < 270; i++) V[i] = 0;
     const M3 rRa1 = mul(rR, R_a_1_x);
-    put3(Fm, 15, 0, 0, I, 1.0);
-    put3(Fm, 15, 0, 3, add(scale(mul(dR, R_a_0_x), -0.25 * dt * dt), scale(mul(rRa1, IwR), -0.25 * dt * dt)), 1.0);
-    put3(Fm, 15, 0, 6, I, dt);
-    put3(Fm, 15, 0, 9, add(dR, rR), -0.25 * dt * dt);
-    put3(Fm, 15, 0, 12, rRa1, -0.25 * dt * dt * -dt);
-    put3(Fm, 15, 3, 3, IwR, 1.0);
-    put3(Fm, 15, 3, 12, I, -dt);
-    put3(Fm, 15, 6, 3, add(scale(mul(dR, R_a_0_x), -0.5 * dt), scale(mul(rRa1, IwR), -0.5 * dt)), 1.0);
-    put3(Fm, 15, 6, 6, I, 1.0);
-    put3(Fm, 15, 6, 9, add(dR, rR), -0.5 * dt);
-    put3(Fm, 15, 6, 12, rRa1, -0.5 * dt * -dt);
-    put3(Fm, 15, 9, 9, I, 1.0);
-    put3(Fm, 15, 12, 12, I, 1.0);
-    put3(V, 18, 0, 0, dR, 0.25 * dt * dt);
-    put3(V, 18, 0, 3, rRa1, -0.25 * dt * dt * 0.5 * dt);
-    put3(V, 18, 0, 6, rR, 0.25 * dt * dt);
-    put3(V, 18, 0, 9, rRa1, -0.25 * dt * dt * 0.5 * dt);
-    put3(V, 18, 3, 3, I, 0.5 * dt);
-    put3(V, 18, 3, 9, I, 0.5 * dt);
-    put3(V, 18, 6, 0, dR, 0.5 * dt);
-    put3(V, 18, 6, 3, rRa1, -0.5 * dt * 0.5 * dt);
-    put3(V, 18, 6, 6, rR, 0.5 * dt);
-    put3(V, 18, 6, 9, rRa1, -0.5 * dt * 0.5 * dt);
-    put3(V, 18, 9, 12, I, dt);
-    put3(V, 18, 12, 15, I, dt);
-    // jacobian = F * jacobian
-    for (int r = 0; r < 15; r++) for (int c = 0; c < 15; c++) { double a = 0; for (int k = 0; k < 15; k++) a += Fm[r * 15 + k] * Jm[k * 15 + c]; T[r * 15 + c] = a; }
-    for (int i = 0; i < 225; i++) Jm[i] = T[i];
-    // covariance = F * cov * F^T + V * noise * V^T
-    for (int r = 0; r < 15; r++) for (int c = 0; c < 15; c++) { double a = 0; for (int k = 0; k < 15; k++) a += Fm[r * 15 + k] * C[k * 15 + c]; T[r * 15 + c] = a; }
-    for (int r = 0; r < 15; r++) for (int c = 0; c < 15; c++) {
-      double a = 0; for (int k = 0; k < 15; k++) a += T[r * 15 + k] * Fm[c * 15 + k];
-      double b = 0; for (int k = 0; k < 18; k++) b += V[r * 18 + k] * nz[k] * V[c * 18 + k];
-      C[r * 15 + c] = a + b;
+    FBlocks F;
+    F.dt = dt;
+    F.f01 = add(scale(mul(dR, R_a_0_x), -0.25 * dt * dt), scale(mul(rRa1, IwR), -0.25 * dt * dt));
+    F.f03 = scale(add(dR, rR), -0.25 * dt * dt);
+    F.f04 = scale(rRa1, -0.25 * dt * dt * -dt);
+    F.f11 = IwR;
+    F.f21 = add(scale(mul(dR, R_a_0_x), -0.5 * dt), scale(mul(rRa1, IwR), -0.5 * dt));
+    F.f23 = scale(add(dR, rR), -0.5 * dt);
+    F.f24 = scale(rRa1, -0.5 * dt * -dt);
+    // V staged in shared memory (lanes 0..8 write the nine distinct 3x3 blocks' rows): [15][18]
+    __syncwarp();
+    for (int i = lane; i < 270; i += 32) Vw[i] = 0.0;
+    __syncwarp();
+    if (lane == 0) {
+      put3(Vw, 18, 0, 0, dR, 0.25 * dt * dt);
+      put3(Vw, 18, 0, 3, rRa1, -0.25 * dt * dt * 0.5 * dt);
+      put3(Vw, 18, 0, 6, rR, 0.25 * dt * dt);
+      put3(Vw, 18, 0, 9, rRa1, -0.25 * dt * dt * 0.5 * dt);
+      put3(Vw, 18, 3, 3, I, 0.5 * dt);
+      put3(Vw, 18, 3, 9, I, 0.5 * dt);
+    } else if (lane == 1) {
+      put3(Vw, 18, 6, 0, dR, 0.5 * dt);
+      put3(Vw, 18, 6, 3, rRa1, -0.5 * dt * 0.5 * dt);
+      put3(Vw, 18, 6, 6, rR, 0.5 * dt);
+      put3(Vw, 18, 6, 9, rRa1, -0.5 * dt * 0.5 * dt);
+      put3(Vw, 18, 9, 12, I, dt);
+      put3(Vw, 18, 12, 15, I, dt);
+    }
+    if (lane < 15) {
+      apply_F(F, jc);               // jacobian = F * jacobian
+      apply_F(F, cc);               // column of F * covariance
+#pragma unroll
+      for (int r = 0; r < 15; r++) Tw[r * 16 + lane] = cc[r];
+    }
+    __syncwarp();
+    if (lane < 15) {
+#pragma unroll
+      for (int k = 0; k < 15; k++) cc[k] = Tw[lane * 16 + k];   // column `lane` of (F C)^T
+      apply_F(F, cc);                                          // column of F (F C)^T = F C F^T
+#pragma unroll
+      for (int r = 0; r < 15; r++) {                           // + V noise V^T
+        double q = 0;
+#pragma unroll
+        for (int k = 0; k < 18; k++) q += nz[k / 3] * Vw[r * 18 + k] * Vw[lane * 18 + k];
+        cc[r] += q;
+      }
     }
     dp = rp; dv = rv; dq = qnormalized(rq);
     sum_dt += dt; acc_0 = acc_1; gyr_0 = gyr_1;
   }
   gf2_imu_preint& o = out[idx];
-  o.sum_dt = sum_dt;
-  o.delta_p[0] = dp.x; o.delta_p[1] = dp.y; o.delta_p[2] = dp.z;
-  o.delta_q[0] = dq.x; o.delta_q[1] = dq.y; o.delta_q[2] = dq.z; o.delta_q[3] = dq.w;
-  o.delta_v[0] = dv.x; o.delta_v[1] = dv.y; o.delta_v[2] = dv.z;
-  o.lin_ba[0] = ba.x; o.lin_ba[1] = ba.y; o.lin_ba[2] = ba.z; o.lin_bg[0] = bg.x; o.lin_bg[1] = bg.y; o.lin_bg[2] = bg.z;
-  for (int i = 0; i < 225; i++) { o.jacobian[i] = Jm[i]; o.covariance[i] = C[i]; }
-  o.valid = 1; o.pad_ = 0;
+  if (lane == 0) {
+    o.sum_dt = sum_dt;
+    o.delta_p[0] = dp.x; o.delta_p[1] = dp.y; o.delta_p[2] = dp.z;
+    o.delta_q[0] = dq.x; o.delta_q[1] = dq.y; o.delta_q[2] = dq.z; o.delta_q[3] = dq.w;
+    o.delta_v[0] = dv.x; o.delta_v[1] = dv.y; o.delta_v[2] = dv.z;
+    o.lin_ba[0] = ba.x; o.lin_ba[1] = ba.y; o.lin_ba[2] = ba.z; o.lin_bg[0] = bg.x; o.lin_bg[1] = bg.y; o.lin_bg[2] = bg.z;
+    o.valid = 1; o.pad_ = 0;
+  }
+  if (lane < 15) {
+#pragma unroll
+    for (int r = 0; r < 15; r++) { o.jacobian[r * 15 + lane] = jc[r]; o.covariance[r * 15 + lane] = cc[r]; }
+  }
 }
 
 }  // namespace gf2
@@ -286,7 +318,7 @@ int gf2_imu_preintegrate(gf2_solver* h, int first, int n, const gf2_imu_sample* 
   H2D(h->d_imu_first + off * 6, first_sample, sizeof(double) * n * Fm1 * 6);
   H2D(h->d_imu_bias + off * 6, lin_bias, sizeof(double) * n * Fm1 * 6);
   const int total = n * Fm1;
-  k_imu_preintegrate<<<(total + 63) / 64, 64, 0, h->stream>>>(total, ms, h->d_imu_samples + off * ms, h->d_imu_n + off, h->d_imu_first + off * 6,
+  k_imu_preintegrate<<<(total + kPreWarps - 1) / kPreWarps, 32 * kPreWarps, 0, h->stream>>>(total, ms, h->d_imu_samples + off * ms, h->d_imu_n + off, h->d_imu_first + off * 6,
                                                                h->d_imu_bias + off * 6, noise[0], noise[1], noise[2], noise[3], h->d_imu + off);
   GF2_CUDA(cudaGetLastError());
   h->has_imu = true;
@@ -298,7 +330,7 @@ int gf2_imu_preintegrate_resident(gf2_solver* h, int first, int n, const double 
   const int ms = h->cfg.max_imu_samples, Fm1 = h->kp.F - 1;
   if (ms <= 0) return gf2::fail(GF2_ERR_INVALID, "solver created with max_imu_samples = 0");
   const size_t off = (size_t)first * Fm1; const int total = n * Fm1;
-  k_imu_preintegrate<<<(total + 63) / 64, 64, 0, h->stream>>>(total, ms, h->d_imu_samples + off * ms, h->d_imu_n + off, h->d_imu_first + off * 6,
+  k_imu_preintegrate<<<(total + kPreWarps - 1) / kPreWarps, 32 * kPreWarps, 0, h->stream>>>(total, ms, h->d_imu_samples + off * ms, h->d_imu_n + off, h->d_imu_first + off * 6,
                                                                h->d_imu_bias + off * 6, noise[0], noise[1], noise[2], noise[3], h->d_imu + off);
   GF2_CUDA(cudaGetLastError());
   h->has_imu = true;
