@@ -211,6 +211,8 @@ int gf2_solver_create(const gf2_solver_cfg* cfg, gf2_solver** out) {
   A(k.imu_H, double, (size_t)B * (F - 1) * 675); A(k.imu_g, double, (size_t)B * (F - 1) * 30);
   A(k.prior_g, double, (size_t)B * kP); A(k.cost_nv, double, B);
   A(k.trace, double, (size_t)B * 64 * 6);
+  if (Pm > 0) { A(k.pperm, int32_t, (size_t)B * Pm); A(k.ptask_first, int32_t, (size_t)B * kMaxPlaneTasks); A(k.ptask_cnt, int32_t, (size_t)B * kMaxPlaneTasks); A(k.ptask_frame, int32_t, (size_t)B * kMaxPlaneTasks); A(k.nptasks, int32_t, B); }
+  if (cfg->use_wheel) { A(k.wheel_H, double, (size_t)B * (F - 1) * 108); A(k.wheel_g, double, (size_t)B * (F - 1) * 12); }
   A(k.perm, int32_t, (size_t)B * Lm); A(k.task_first, int32_t, (size_t)B * kMaxTasks); A(k.task_cnt, int32_t, (size_t)B * kMaxTasks);
   A(k.task_start, int32_t, (size_t)B * kMaxTasks); A(k.ntasks, int32_t, B);
   A(k.st, WinState, B);
@@ -403,8 +405,13 @@ int gf2_set_planes(gf2_solver* h, int first, int n, const int32_t* n_planes, con
   for (int w = 0; w < n; w++) if (n_planes[w] < 0 || n_planes[w] > k.Pm) return gf2::fail(GF2_ERR_INVALID, "n_planes[%d] = %d exceeds capacity %d", w, n_planes[w], k.Pm);
   H2D(k.n_planes + first, n_planes, sizeof(int32_t) * n);
   H2D(k.planes + (size_t)first * k.Pm, planes, sizeof(gf2_plane) * n * k.Pm);
+  for (int w = 0; w < n; w++) for (int q = 0; q < n_planes[w]; q++) {
+    const int f = planes[(size_t)w * k.Pm + q].frame;
+    if (f < 0 || f >= k.F) return gf2::fail(GF2_ERR_INVALID, "window %d plane %d: frame %d outside [0, %d)", first + w, q, f, k.F);
+  }
+  if ((k.Pm + 31) / 32 + k.F > kMaxPlaneTasks) return gf2::fail(GF2_ERR_INVALID, "max_planes %d exceeds the task capacity", k.Pm);
   h->has_planes = true;
-  return gf2::fail(GF2_ERR_UNSUPPORTED, "LiDAR plane factors are not wired into the sweep yet");
+  return GF2_OK;
 }
 
 static int fill_kp(gf2_solver* h, const gf2_solve_opts* o, KP& k) {
@@ -426,6 +433,7 @@ static int fill_kp(gf2_solver* h, const gf2_solve_opts* o, KP& k) {
   k.imu = h->has_imu ? h->d_imu : nullptr;
   k.wheel = (h->cfg.use_wheel && h->has_wheel) ? h->d_wheel : nullptr;
   if (!h->has_prior) { k.prior_rows = nullptr; }
+  if (!h->has_planes) { k.planes = nullptr; }
   return GF2_OK;
 }
 

@@ -76,6 +76,8 @@ struct KP {  // kernel parameters (device pointers are window-major with the str
   double *lm_v, *lm_g, *lm_s, *lm_z; // [nW][Lm]
   double *sx, *zx, *ux, *ex_diag;  // [nW][D] jacobi scale, GN step, u, e
   double *Sfull, *gfull;           // optional dump of the assembled reduced system [nW][D*D], [nW][D]
+  int32_t *pperm, *ptask_first, *ptask_cnt, *ptask_frame, *nptasks;  // k_tasks: plane permutation by frame, warp tasks
+  double *wheel_H, *wheel_g;       // [nW][F-1][3*36] pose blocks (i,i),(j,i),(j,j) of each wheel factor, [nW][F-1][12]  (k_nonvis)
   int32_t *perm, *task_first, *task_cnt, *task_start, *ntasks;  // k_tasks: landmark permutation by start frame, warp tasks
   double* trace;                   // [nW][64][6]: candidate cost, model change, rho, radius, step norm, decision
   WinState* st;

@@ -80,6 +80,65 @@ __device__ void imu_raw(const gf2_imu_preint& pre, const ImuStates& s, double g_
   put3(J, 30, 12, 27, eye3(), 1.0);
 }
 
+// ------------------------------------------------------------------------------------------------ wheel factor
+// WheelIntegrationBase::evaluate (VE/factor/wheel_integration_base.h:180-219) and the pose Jacobians of WheelFactor::Evaluate
+// (VE/factor/wheel_factor.h:117-156). Calibration blocks (extrinsic, sx sy sw, td) are constant in this build, so only
+// jacobians[0] (pose_i) and jacobians[1] (pose_j) are formed: J is 6 x 12 in tangent columns [pose_i 6 | pose_j 6].
+__device__ void wheel_raw(const gf2_wheel_preint& pre, const double* pose_i, const double* pose_j, const double* exw, const double* sxw, double tdw,
+                          double* r /*6*/, double* J /*6x12 or null*/) {
+  const V3 Pi = ld3(pose_i), Pj = ld3(pose_j), tio = ld3(exw);
+  const Q4 Qi = ldq(pose_i + 3), Qj = ldq(pose_j + 3), qio = ldq(exw + 3);
+  const double sx = sxw[0], sy = sxw[1], sw = sxw[2];
+  const V3 dp_dsx = mk3(pre.jacobian[0], pre.jacobian[3], pre.jacobian[6]), dp_dsy = mk3(pre.jacobian[1], pre.jacobian[4], pre.jacobian[7]);
+  const V3 dp_dsw = mk3(pre.jacobian[2], pre.jacobian[5], pre.jacobian[8]), dq_dsw = mk3(pre.jacobian[11], pre.jacobian[14], pre.jacobian[17]);
+  const double dsx = sx - pre.lin_sx, dsy = sy - pre.lin_sy, dsw = sw - pre.lin_sw;
+  const M3 Ri = toR(Qi), Rj = toR(Qj), rio = toR(qio);
+  const V3 cdp = ld3(pre.delta_p) + dsx * dp_dsx + dsy * dp_dsy + dsw * dp_dsw;
+  const Q4 cdq = qnormalized(qmul(qnormalized(ldq(pre.delta_q)), so3Exp(dsw * dq_dsw)));
+  const double dtd = tdw - pre.lin_td;
+  const V3 lg = ld3(pre.lin_gyr), lv = ld3(pre.lin_vel), g1 = ld3(pre.gyr_1), v1 = ld3(pre.vel_1);
+  const Q4 ef = so3Exp((sw * dtd) * lg);
+  const Q4 dqt = qnormalized(qmul(qmul(ef, cdq), so3Exp((-sw * dtd) * g1)));
+  const V3 svlv = mk3(sx * lv.x, sy * lv.y, lv.z), svv1 = mk3(sx * v1.x, sy * v1.y, v1.z);
+  const V3 dpt = mul(toR(ef), dtd * svlv + cdp - qrot(cdq, dtd * svv1));
+  const V3 dpw = mul(Rj, tio) + Pj - mul(Ri, tio) - Pi;
+  const M3 Rio = mul(Ri, rio);
+  const V3 rp = mulT(Rio, dpw) - dpt;
+  const Q4 Qio = qmul(Qi, qio);
+  const V3 rr = so3Log(qmul(qmul(qmul(qinv(dqt), qinv(Qio)), Qj), qio));
+  r[0] = rp.x; r[1] = rp.y; r[2] = rp.z; r[3] = rr.x; r[4] = rr.y; r[5] = rr.z;
+  if (!J) return;
+  for (int i = 0; i < 72; i++) J[i] = 0.0;
+  const M3 Jrinv = rightJacobianInvSO3(rr);
+  const M3 RioInv = toR(qinv(Qio));
+  put3(J, 12, 0, 0, RioInv, -1.0);
+  put3(J, 12, 0, 3, add(mulT(Rio, mul(Ri, skew(tio))), mulT(rio, skew(mulT(Ri, dpw)))), 1.0);
+  put3(J, 12, 3, 3, mul(Jrinv, toR(qmul(qinv(qmul(Qj, qio)), Qi))), -1.0);
+  put3(J, 12, 0, 6, RioInv, 1.0);
+  put3(J, 12, 0, 9, mul(toR(qmul(qinv(Qio), Qj)), skew(tio)), -1.0);
+  put3(J, 12, 3, 9, mul(Jrinv, toR(qinv(qio))), 1.0);
+}
+__device__ __forceinline__ double wheel_cost(const double* sq /*6x6 upper*/, const double* r) {
+  double c = 0;
+  for (int a = 0; a < 6; a++) { double s = 0; for (int k = a; k < 6; k++) s += sq[a * 6 + k] * r[k]; c += s * s; }
+  return 0.5 * c;
+}
+
+// LidarPlaneNormFactor (LIO/liw/lidarFactor.cpp:18-50) attached to the window pose of its frame: residual and the 1x6 tangent
+// Jacobian [sqrt_info w n^T | -sqrt_info w n^T R [p]x]
+__device__ __forceinline__ double plane_residual(const gf2_plane& pl, const FrameCtx& f, double sqrt_info, double* J /*6 or null*/) {
+  const V3 p = ld3(pl.p_body), n = ld3(pl.normal);
+  M3 R; for (int i = 0; i < 9; i++) R.m[i] = f.R[i];
+  const V3 pw = mul(R, p) + mk3(f.P[0], f.P[1], f.P[2]);
+  const double sw = sqrt_info * pl.weight;
+  if (J) {
+    const V3 a = mulT(R, n);        // R^T n;  (a^T [p]x) = (a x p)^T
+    const V3 c = cross(a, p);
+    J[0] = sw * n.x; J[1] = sw * n.y; J[2] = sw * n.z; J[3] = -sw * c.x; J[4] = -sw * c.y; J[5] = -sw * c.z;
+  }
+  return sw * (dot(n, pw) + pl.offset);
+}
+
 // 0.5 * |sqrt_info * r|^2 by one thread
 __device__ __forceinline__ double imu_cost(const double* sq /*15x15 upper*/, const double* r) {
   double c = 0;
@@ -474,7 +533,12 @@ __global__ void __launch_bounds__(288, 2) k_candidate(KP p, int w0) {
       acc[0] += hr;
     }
   }
-  // IMU factors and the prior at the candidate: warp 8 alone, concurrently with the landmark warps
+  if (p.planes && t < 256) {  // LiDAR plane residuals at the candidate
+    const int np = p.n_planes[w];
+    const gf2_plane* pls = p.planes + (size_t)w * p.Pm;
+    for (int q = t; q < np; q += 256) { const double r = plane_residual(pls[q], S.fr[pls[q].frame], p.lidar_sqrt_info, nullptr); acc[0] += 0.5 * r * r; }
+  }
+  // IMU / wheel factors and the prior at the candidate: warp 8 alone, concurrently with the landmark warps
   if (t >= 256) {
     const int ln = t - 256;
     if (p.imu && ln < F - 1) {
@@ -483,6 +547,15 @@ __global__ void __launch_bounds__(288, 2) k_candidate(KP p, int w0) {
         double r[15]; ImuStates s2 = load_imu_states(pose_c, sb_c, ln);
         imu_raw(pre, s2, p.g_norm, r, nullptr);
         acc[0] += imu_cost(p.imu_sqrt + ((size_t)w * (F - 1) + ln) * 225, r);
+      }
+    }
+    if (p.wheel && ln >= 16 && ln - 16 < F - 1) {
+      const int k = ln - 16;
+      const gf2_wheel_preint& pre = p.wheel[(size_t)w * (F - 1) + k];
+      if (pre.valid && pre.sum_dt <= 10.0) {
+        double r[6];
+        wheel_raw(pre, pose_c + 7 * k, pose_c + 7 * (k + 1), p.exw + (size_t)w * 7, p.sxw + (size_t)w * 3, p.tdw[w], r, nullptr);
+        acc[0] += wheel_cost(p.wheel_sqrt + ((size_t)w * (F - 1) + k) * 36, r);
       }
     }
     const int n = p.prior_rows ? p.prior_rows[w] : 0;

@@ -12,6 +12,7 @@
 namespace gf2 {
 
 constexpr int kMaxTasks = 48;  // ceil(1000 / 32) + 11 partial tasks + slack
+constexpr int kMaxPlaneTasks = 192;  // planes: up to ~5.8k per window in tasks of 32 of the same frame
 
 // ------------------------------------------------------------------------------------------------ k_tasks
 // Deterministic counting sort of the landmark table by start frame -> perm, and the warp-task list. One thread per start
@@ -38,6 +39,25 @@ __global__ void k_tasks(KP p, int w0) {
   }
   __syncthreads();
   if (t < F) { int32_t* perm = p.perm + (size_t)w * p.Lm; int o = ofs[t]; for (int l = 0; l < nlm; l++) if (start[l] == t) perm[o++] = l; }
+  if (!p.planes) return;
+  // LiDAR plane factors grouped by frame, tasks of <= 32 planes
+  __syncthreads();
+  const int np = p.n_planes[w];
+  const gf2_plane* pls = p.planes + (size_t)w * p.Pm;
+  if (t < F) { int c = 0; for (int q = 0; q < np; q++) c += (pls[q].frame == t); cnt[t] = c; }
+  __syncthreads();
+  if (t == 0) {
+    int o = 0, nt = 0;
+    int32_t* tf = p.ptask_first + (size_t)w * kMaxPlaneTasks; int32_t* tc = p.ptask_cnt + (size_t)w * kMaxPlaneTasks; int32_t* ts = p.ptask_frame + (size_t)w * kMaxPlaneTasks;
+    for (int s = 0; s < F; s++) {
+      ofs[s] = o;
+      for (int c = 0; c < cnt[s] && nt < kMaxPlaneTasks; c += 32) { tf[nt] = o + c; tc[nt] = min(32, cnt[s] - c); ts[nt] = s; nt++; }
+      o += cnt[s];
+    }
+    p.nptasks[w] = nt;
+  }
+  __syncthreads();
+  if (t < F) { int32_t* perm = p.pperm + (size_t)w * p.Pm; int o = ofs[t]; for (int q = 0; q < np; q++) if (pls[q].frame == t) perm[o++] = q; }
 }
 
 // ------------------------------------------------------------------------------------------------ k_linearize
@@ -226,6 +246,31 @@ __global__ void __launch_bounds__(kLinThreads, 1) k_linearize(KP p, int w0) {
     __syncthreads();
   }
 
+  // LiDAR plane factors: tasks of <= 32 planes of one frame; [J | r]^T [J | r] reduced on the tensor cores into block (f, f), g_f
+  if (p.planes) {
+    const int npt = p.nptasks[w];
+    const gf2_plane* pls = p.planes + (size_t)w * p.Pm;
+    const int32_t* pperm = p.pperm + (size_t)w * p.Pm;
+    for (int q = wid; q < npt; q += 8) {
+      const int f = p.ptask_frame[(size_t)w * kMaxPlaneTasks + q], cnt = p.ptask_cnt[(size_t)w * kMaxPlaneTasks + q], first = p.ptask_first[(size_t)w * kMaxPlaneTasks + q];
+      double Jp[6] = {0, 0, 0, 0, 0, 0}, r = 0.0;
+      if (lane < cnt) { r = plane_residual(pls[pperm[first + lane]], S.fr[f], p.lidar_sqrt_info, Jp); cost_acc += 0.5 * r * r; }
+      __syncwarp();
+      double* row = stg + lane * kStageStride;
+#pragma unroll
+      for (int c = 0; c < 6; c++) row[c] = Jp[c];
+      row[6] = r;
+      __syncwarp();
+      double c0 = 0, c1 = 0;
+#pragma unroll
+      for (int s = 0; s < 8; s++) {
+        const double x = stg[(4 * s + fk) * kStageStride + (fq < 7 ? fq : 0)];
+        mma_f64(c0, c1, fq < 6 ? x : 0.0, fq < 7 ? x : 0.0);
+      }
+      flush_tile(&S.U[ublk(f, f, F)], &S.g[6 * f], c0, c1, lane);
+    }
+    __syncthreads();
+  }
   // S_vis = U - C, g_schur = C[:,66]; the Schur tiles are staged in WT (free now) as a dense 72x72 matrix
 #pragma unroll
   for (int s2 = 0; s2 < 6; s2++) if (tile_a[s2] >= 0) {

@@ -62,6 +62,32 @@ __global__ void __launch_bounds__(kNonvisThreads) k_nonvis(KP p, int w0) {
       __syncwarp();
     }
   }
+  if (p.wheel) {  // WheelFactor: 6 residuals, pose_i / pose_j blocks (calibration constant)
+    for (int k = wid; k < F - 1; k += nw) {
+      const gf2_wheel_preint& pre = p.wheel[(size_t)w * (F - 1) + k];
+      double* Hout = p.wheel_H + ((size_t)w * (F - 1) + k) * 108;
+      double* gout = p.wheel_g + ((size_t)w * (F - 1) + k) * 12;
+      if (!pre.valid || pre.sum_dt > 10.0) { for (int i = lane; i < 108; i += 32) Hout[i] = 0.0; if (lane < 12) gout[lane] = 0.0; continue; }
+      double* J = scratch[wid];
+      double* r = J + 72;
+      __syncwarp();
+      if (lane == 0) wheel_raw(pre, pose + 7 * k, pose + 7 * (k + 1), p.exw + (size_t)w * 7, p.sxw + (size_t)w * 3, p.tdw[w], r, J);
+      __syncwarp();
+      const double* sq = p.wheel_sqrt + ((size_t)w * (F - 1) + k) * 36;
+      if (lane < 12) { for (int a = 0; a < 6; a++) { double acc = 0; for (int kk = a; kk < 6; kk++) acc += sq[a * 6 + kk] * J[kk * 12 + lane]; J[a * 12 + lane] = acc; } }
+      else if (lane == 12) { for (int a = 0; a < 6; a++) { double acc = 0; for (int kk = a; kk < 6; kk++) acc += sq[a * 6 + kk] * r[kk]; r[a] = acc; } }
+      __syncwarp();
+      if (lane == 0) { double c = 0; for (int a = 0; a < 6; a++) c += r[a] * r[a]; cost += 0.5 * c; }
+      for (int idx = lane; idx < 108; idx += 32) {  // 6x6 blocks (i,i), (j,i), (j,j)
+        const int blk = idx / 36, e = idx % 36;
+        const int a = e / 6 + (blk >= 1 ? 6 : 0), b = e % 6 + (blk == 2 ? 6 : 0);
+        double acc = 0; for (int rr = 0; rr < 6; rr++) acc += J[rr * 12 + a] * J[rr * 12 + b];
+        Hout[idx] = acc;
+      }
+      if (lane < 12) { double acc = 0; for (int rr = 0; rr < 6; rr++) acc += J[rr * 12 + lane] * r[rr]; gout[lane] = acc; }
+      __syncwarp();
+    }
+  }
   const int n = p.prior_rows ? p.prior_rows[w] : 0;
   if (n > 0) {
     const gf2_prior_block* blk = p.prior_blocks + (size_t)w * (2 * F + 8);
@@ -185,6 +211,32 @@ __global__ void __launch_bounds__(kSolveThreads, 1) k_solve2(KP p, int w0) {
       if (K > 0) v += gw[(K - 1) * 30 + 15 + r];
       if (K < F - 1) v += gw[K * 30 + r];
       S.g[i] += v;
+    }
+    __syncthreads();
+  }
+  if (p.wheel) {  // wheel pose blocks, by destination like the IMU blocks (pose part = rows/cols 0..5 of a frame block)
+    const double* Hw = p.wheel_H + (size_t)w * (F - 1) * 108;
+    const double* gw = p.wheel_g + (size_t)w * (F - 1) * 12;
+    for (int idx = t; idx < (2 * F - 1) * 36; idx += nt) {
+      const int e = idx % 36, r = e / 6, c = e % 6;
+      if (idx < F * 36) {
+        const int K = idx / 36;
+        double v = 0.0;
+        if (K > 0) v += Hw[(K - 1) * 108 + 72 + e];
+        if (K < F - 1) v += Hw[K * 108 + e];
+        if (c <= r) A[bidx(K, K) + r * kBS + c] += v;
+        if (r == c) S.Hd[15 * K + r] += v;
+      } else {
+        const int K = idx / 36 - F;
+        A[bidx(K + 1, K) + r * kBS + c] += Hw[K * 108 + 36 + e];
+      }
+    }
+    for (int i = t; i < 6 * F; i += nt) {
+      const int K = i / 6, r = i % 6;
+      double v = 0.0;
+      if (K > 0) v += gw[(K - 1) * 12 + 6 + r];
+      if (K < F - 1) v += gw[K * 12 + r];
+      S.g[15 * K + r] += v;
     }
     __syncthreads();
   }

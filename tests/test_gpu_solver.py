@@ -91,6 +91,45 @@ def test_solve_matches_oracle(gf2, oracle, synth, nl, prior):
     s.close()
 
 
+def _solver4(gf2, w, n):
+    return gf2.Solver(n, w["n_frames"], w["max_landmarks"], w["max_obs"], max_planes=w["max_planes"], max_imu_samples=w["n_imu_samples"],
+                      use_wheel=bool(w.get("use_wheel")))
+
+
+@pytest.mark.parametrize("nl,planes,wheel", [(300, 1000, True), (1000, 5000, True), (200, 0, True), (200, 777, False)])
+def test_config4_wheel_and_lidar_planes_match_oracle(gf2, oracle, synth, nl, planes, wheel):
+    """BASELINE.json config 4 composition: visual + IMU + WheelFactor + LidarPlaneNormFactor on the window poses."""
+    n = 2
+    w = synth.make_windows(n, config_id=4, n_landmarks=nl, wheel=wheel, n_planes=planes)
+    oracle.imu_preintegrate(w)
+    if wheel:
+        oracle.wheel_preintegrate(w)
+    s = _solver4(gf2, w, n)
+    s.upload(w, preintegrate="records")
+    opts = gf2.abi.default_opts()
+    S, g, cost = s.linearize(opts, n)
+    for i in range(n):
+        So, go, co, _, _ = oracle.linearize_window(w, i, opts)
+        assert abs(cost[i] - co) <= 1e-12 * co
+        assert np.abs(S[i] - So).max() <= 1e-10 * np.abs(So).max()
+        assert np.abs(g[i] - go).max() <= 1e-10 * np.abs(go).max()
+    s.upload(w, preintegrate="records")
+    summ = s.solve(opts, n)
+    got = s.get_states(n); lam = s.get_landmarks(n)
+    wo = _copy(w)
+    so = oracle.solve_batch(wo, opts, n_threads=2)
+    assert (summ["iterations"] == so["iterations"]).all() and (summ["termination"] == so["termination"]).all()
+    assert (summ["successful_steps"] == so["successful_steps"]).all()
+    assert (np.abs(summ["final_cost"] - so["final_cost"]) <= 1e-6 * so["final_cost"]).all()
+    scale = np.abs(wo["para_pose"][..., :3]).max()
+    assert np.abs(got["para_pose"][..., :3] - wo["para_pose"][..., :3]).max() <= 1e-4 * scale
+    assert np.abs(got["para_pose"][..., 3:] - wo["para_pose"][..., 3:]).max() <= 1e-4
+    assert np.abs(lam - wo["inv_depth"]).max() <= 1e-3 * np.abs(wo["inv_depth"]).max()
+    if wheel:  # calibration blocks are constant
+        assert np.array_equal(got["ex_pose_wheel"], w["ex_pose_wheel"]) and np.array_equal(got["sxsysw"], w["sxsysw"])
+    s.close()
+
+
 def test_solve_properties_full_size_batch(gf2, synth):
     """BASELINE-size windows (W10-F1000) in a batch: size-independent properties — cost decreases by orders of magnitude,
     identical windows give the same result wherever they sit in the batch, re-solving from the optimum is
