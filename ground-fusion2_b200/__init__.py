@@ -192,6 +192,17 @@ class Solver:
         _check(lib().gf2_get_landmarks(self.h, first, n, _p(d)))
         return d
 
+    @staticmethod
+    def comm_unique_id():
+        """128-byte ncclUniqueId (rank 0 creates it, the caller broadcasts it)."""
+        buf = np.zeros(128, np.uint8)
+        _check(lib().gf2_comm_unique_id(_p(buf)))
+        return buf
+
+    def comm_init(self, rank, nranks, unique_id):
+        uid = np.ascontiguousarray(unique_id, np.uint8)
+        _check(lib().gf2_comm_init(self.h, int(rank), int(nranks), _p(uid)))
+
     def get_trace(self, n=None, first=0):
         n = n if n is not None else self.B
         tr = np.zeros((n, 64, 6))

@@ -8,7 +8,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libgf2_b200.so")
 SOURCES = ["gf2_solver.cu", "gf2_tracker.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
-              "--expt-relaxed-constexpr", "-Xptxas", "-v", "-shared", "-lcudart"]
+              "--expt-relaxed-constexpr", "-Xptxas", "-v", "-shared", "-lcudart", "-ldl"]
 
 
 def needs_build():

@@ -2,6 +2,7 @@
 // orchestration: device memory, H2D/D2H of the reference's packed arrays, the trust-region kernel sequence and its
 // CUDA-event timing. No CPU fallback: every compute call launches kernels on the handle's device.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <stdio.h>
 #include <string.h>
 #include <string>
@@ -135,6 +136,38 @@ __global__ void __launch_bounds__(32 * kPreWarps) k_imu_preintegrate(int n_inter
 
 }  // namespace gf2
 
+// ------------------------------------------------------------------------------------------------ NCCL (loaded at run time)
+// libgf2_b200.so has no link-time NCCL dependency: the factor-sharded mode dlopen()s libnccl.so.2 (the copy torch already
+// loaded when the caller is a torch.distributed process), so CPU-only boxes and single-GPU users never need it.
+namespace {
+typedef struct { char internal[128]; } gf2_nccl_uid;
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(gf2_nccl_uid*) = nullptr;
+  int (*CommInitRank)(void**, int, gf2_nccl_uid, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool load() {
+    if (lib) return true;
+    lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) return false;
+    GetUniqueId = (int (*)(gf2_nccl_uid*))dlsym(lib, "ncclGetUniqueId");
+    CommInitRank = (int (*)(void**, int, gf2_nccl_uid, int))dlsym(lib, "ncclCommInitRank");
+    AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(lib, "ncclAllReduce");
+    GroupStart = (int (*)())dlsym(lib, "ncclGroupStart"); GroupEnd = (int (*)())dlsym(lib, "ncclGroupEnd");
+    CommDestroy = (int (*)(void*))dlsym(lib, "ncclCommDestroy");
+    GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
+    return GetUniqueId && CommInitRank && AllReduce && GroupStart && GroupEnd && CommDestroy;
+  }
+};
+NcclApi g_nccl;
+constexpr int kNcclFloat64 = 8, kNcclSum = 0, kNcclMax = 2;  // ncclDataType_t / ncclRedOp_t values of nccl.h
+}  // namespace
+
 // ------------------------------------------------------------------------------------------------ handle
 struct gf2_solver {
   gf2_solver_cfg cfg;
@@ -147,6 +180,7 @@ struct gf2_solver {
   gf2_imu_sample* d_imu_samples = nullptr; int32_t* d_imu_n = nullptr; double *d_imu_first = nullptr, *d_imu_bias = nullptr;
   gf2_imu_preint* d_imu = nullptr;
   gf2_wheel_preint* d_wheel = nullptr;
+  void* nccl_comm = nullptr; int comm_rank = 0, comm_size = 1;
   bool has_imu = false, has_wheel = false, has_prior = false, has_planes = false, dump_full = false;
   std::vector<int32_t> h_obeg;
   cudaEvent_t ev[4 * 64 + 3];
@@ -211,6 +245,7 @@ int gf2_solver_create(const gf2_solver_cfg* cfg, gf2_solver** out) {
   A(k.imu_H, double, (size_t)B * (F - 1) * 675); A(k.imu_g, double, (size_t)B * (F - 1) * 30);
   A(k.prior_g, double, (size_t)B * kP); A(k.cost_nv, double, B);
   A(k.trace, double, (size_t)B * 64 * 6);
+  A(k.c_lin, double, (size_t)B * 4); A(k.c_gmax, double, B); A(k.c_sums, double, (size_t)B * 8); A(k.c_cand, double, (size_t)B * 4);
   if (Pm > 0) { A(k.pperm, int32_t, (size_t)B * Pm); A(k.ptask_first, int32_t, (size_t)B * kMaxPlaneTasks); A(k.ptask_cnt, int32_t, (size_t)B * kMaxPlaneTasks); A(k.ptask_frame, int32_t, (size_t)B * kMaxPlaneTasks); A(k.nptasks, int32_t, B); }
   if (cfg->use_wheel) { A(k.wheel_H, double, (size_t)B * (F - 1) * 108); A(k.wheel_g, double, (size_t)B * (F - 1) * 12); }
   A(k.perm, int32_t, (size_t)B * Lm); A(k.task_first, int32_t, (size_t)B * kMaxTasks); A(k.task_cnt, int32_t, (size_t)B * kMaxTasks);
@@ -240,6 +275,7 @@ void gf2_solver_destroy(gf2_solver* h) {
   for (void* p : h->allocs) cudaFree(p);
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
   if (h->h_state) cudaFreeHost(h->h_state);
+  if (h->nccl_comm && g_nccl.lib) g_nccl.CommDestroy(h->nccl_comm);
   cudaStreamDestroy(h->own_stream);
   delete h;
 }
@@ -455,14 +491,27 @@ static int run(gf2_solver* h, int first, int n, const gf2_solve_opts* opts, gf2_
   const int iters = only_linearize ? 1 : iterations;
   for (int it = 0; it < iters; it++) {
     k_linearize<<<n, kLinThreads, sh_lin, h->stream>>>(k, first);
+    if (h->nccl_comm) {  // one all-reduce of the visual reduced system + gradient per linearisation
+      g_nccl.GroupStart();
+      g_nccl.AllReduce(k.Svis + (size_t)first * kNVMax * kNVMax, k.Svis + (size_t)first * kNVMax * kNVMax, (size_t)n * kNVMax * kNVMax, kNcclFloat64, kNcclSum, h->nccl_comm, h->stream);
+      g_nccl.AllReduce(k.gvis + (size_t)first * kNVP, k.gvis + (size_t)first * kNVP, (size_t)n * kNVP, kNcclFloat64, kNcclSum, h->nccl_comm, h->stream);
+      g_nccl.AllReduce(k.gschur + (size_t)first * kNVP, k.gschur + (size_t)first * kNVP, (size_t)n * kNVP, kNcclFloat64, kNcclSum, h->nccl_comm, h->stream);
+      g_nccl.AllReduce(k.Udiag + (size_t)first * kNVMax, k.Udiag + (size_t)first * kNVMax, (size_t)n * kNVMax, kNcclFloat64, kNcclSum, h->nccl_comm, h->stream);
+      g_nccl.AllReduce(k.c_lin + (size_t)first * 4, k.c_lin + (size_t)first * 4, (size_t)n * 4, kNcclFloat64, kNcclSum, h->nccl_comm, h->stream);
+      g_nccl.AllReduce(k.c_gmax + first, k.c_gmax + first, (size_t)n, kNcclFloat64, kNcclMax, h->nccl_comm, h->stream);
+      g_nccl.GroupEnd();
+    }
     cudaEventRecord(h->ev[ne++], h->stream);
     k_nonvis<<<n, kNonvisThreads, 0, h->stream>>>(k, first);
     k_solve2<<<n, kSolveThreads, sh_solve, h->stream>>>(k, first);
     cudaEventRecord(h->ev[ne++], h->stream);
     if (!only_linearize) {
       k_backsub<<<n, 256, 0, h->stream>>>(k, first);
+      if (h->nccl_comm) g_nccl.AllReduce(k.c_sums + (size_t)first * 8, k.c_sums + (size_t)first * 8, (size_t)n * 8, kNcclFloat64, kNcclSum, h->nccl_comm, h->stream);
       cudaEventRecord(h->ev[ne++], h->stream);
-      k_candidate<<<n, 288, 0, h->stream>>>(k, first);
+      k_cand_eval<<<n, 288, 0, h->stream>>>(k, first);
+      if (h->nccl_comm) g_nccl.AllReduce(k.c_cand + (size_t)first * 4, k.c_cand + (size_t)first * 4, (size_t)n * 4, kNcclFloat64, kNcclSum, h->nccl_comm, h->stream);
+      k_decide<<<n, 256, 0, h->stream>>>(k, first);
       cudaEventRecord(h->ev[ne++], h->stream);
     }
   }
@@ -480,7 +529,7 @@ static int run(gf2_solver* h, int first, int n, const gf2_solve_opts* opts, gf2_
     cudaEventElapsedTime(&ms, h->ev[b], h->ev[b + 1]); h->timing[2] += ms;       // solve
     if (!only_linearize) { cudaEventElapsedTime(&ms, h->ev[b + 1], h->ev[b + 3]); h->timing[3] += ms; }
   }
-  h->timing[4] = 1 + iters * (per + 1); h->timing[5] = iters;
+  h->timing[4] = 2 + iters * (only_linearize ? 3 : 6); h->timing[5] = iters;
   cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]); h->timing[6] = ms;  // k_prepare
   if (summaries) for (int w = 0; w < n; w++) {
     const WinState& s = h->h_state[w];
@@ -550,10 +599,29 @@ int gf2_get_trace(gf2_solver* h, int first, int n, double* out) {
 }
 
 int gf2_comm_init(gf2_solver* h, int rank, int nranks, const void* nccl_unique_id) {
-  (void)h; (void)rank; (void)nranks; (void)nccl_unique_id;
-  return gf2::fail(GF2_ERR_UNSUPPORTED, "factor-sharded mode is not built yet");
+  if (!h || !nccl_unique_id) return gf2::fail(GF2_ERR_INVALID, "null argument");
+  if (nranks < 1 || rank < 0 || rank >= nranks) return gf2::fail(GF2_ERR_INVALID, "bad rank %d of %d", rank, nranks);
+  if (!g_nccl.load()) return gf2::fail(GF2_ERR_NCCL, "libnccl.so.2 could not be loaded: %s", dlerror());
+  cudaSetDevice(h->cfg.device);
+  gf2_nccl_uid uid; memcpy(&uid, nccl_unique_id, sizeof(uid));
+  void* comm = nullptr;
+  const int rc = g_nccl.CommInitRank(&comm, nranks, uid, rank);
+  if (rc != 0) return gf2::fail(GF2_ERR_NCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error");
+  if (h->nccl_comm) g_nccl.CommDestroy(h->nccl_comm);
+  h->nccl_comm = nranks > 1 ? comm : nullptr;
+  if (nranks == 1) g_nccl.CommDestroy(comm);
+  h->comm_rank = rank; h->comm_size = nranks;
+  return GF2_OK;
 }
-int gf2_comm_unique_id(void* out) { (void)out; return gf2::fail(GF2_ERR_UNSUPPORTED, "factor-sharded mode is not built yet"); }
+int gf2_comm_unique_id(void* out) {
+  if (!out) return gf2::fail(GF2_ERR_INVALID, "null argument");
+  if (!g_nccl.load()) return gf2::fail(GF2_ERR_NCCL, "libnccl.so.2 could not be loaded: %s", dlerror());
+  gf2_nccl_uid uid;
+  const int rc = g_nccl.GetUniqueId(&uid);
+  if (rc != 0) return gf2::fail(GF2_ERR_NCCL, "ncclGetUniqueId failed (%d)", rc);
+  memcpy(out, &uid, sizeof(uid));
+  return GF2_OK;
+}
 
 int gf2_last_timing(gf2_solver* h, double out[8]) {
   if (!h || !out) return gf2::fail(GF2_ERR_INVALID, "null argument");

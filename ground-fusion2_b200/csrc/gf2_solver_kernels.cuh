@@ -35,6 +35,7 @@ struct WinState {  // per-window trust-region state (DoglegStrategy + TrustRegio
   // x-part sums from k_solve, landmark-part sums from k_backsub
   double dlg2_x, gn2_x, gz_x, zEz_x, uEz_x, uSu, uEu_x, gmax_x;
   double dlg2_l, gn2_l, gz_l, zHz_l, uHz_l, uHu_l, gmax_l;
+  double cand_nv, step2_x, xnorm2_x; // candidate: non-visual cost, |dx|^2 and |x|^2 of the frame states (identical on all ranks)
   double uSz, zSz;                  // u^T S' z and z^T S' z through the Cholesky factor (k_solve2)
   double cost_vis;                  // from k_linearize
   int32_t iteration, successful, termination, active, reuse, invalid_count, lin_valid, pad_;
@@ -79,6 +80,8 @@ struct KP {  // kernel parameters (device pointers are window-major with the str
   int32_t *pperm, *ptask_first, *ptask_cnt, *ptask_frame, *nptasks;  // k_tasks: plane permutation by frame, warp tasks
   double *wheel_H, *wheel_g;       // [nW][F-1][3*36] pose blocks (i,i),(j,i),(j,j) of each wheel factor, [nW][F-1][12]  (k_nonvis)
   int32_t *perm, *task_first, *task_cnt, *task_start, *ntasks;  // k_tasks: landmark permutation by start frame, warp tasks
+  // cross-rank scalars (factor-sharded mode all-reduces them; single GPU reads them straight back)
+  double *c_lin, *c_gmax, *c_sums, *c_cand;  // [nW][4] {visual cost}, [nW] max|g_l|, [nW][8] k_backsub sums, [nW][4] {cand visual cost, |dl|^2, |l|^2}
   double* trace;                   // [nW][64][6]: candidate cost, model change, rho, radius, step norm, decision
   WinState* st;
 };

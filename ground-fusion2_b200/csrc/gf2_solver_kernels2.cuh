@@ -446,12 +446,13 @@ __global__ void __launch_bounds__(256, 2) k_backsub(KP p, int w0) {
     sums[5] += cu * cu / vp + 2.0 * u * cu + v * u * u;             // landmark part of u^T H u
   }
   block_sum<6>(sums, S.red);
-  if (t == 0) { st.dlg2_l = sums[0]; st.gn2_l = sums[1]; st.gz_l = sums[2]; st.zHz_l = sums[3]; st.uHz_l = sums[4]; st.uHu_l = sums[5]; }
+  if (t == 0) { double* cs = p.c_sums + (size_t)w * 8; for (int i = 0; i < 6; i++) cs[i] = sums[i]; }
 }
 
 // ------------------------------------------------------------------------------------------------ k_candidate
 // DoglegStrategy::ComputeTraditionalDoglegStep + candidate evaluation + step acceptance.
-__device__ void dogleg_coefficients(WinState& st) {
+__device__ void dogleg_coefficients(WinState& st, const double* cs) {
+  st.dlg2_l = cs[0]; st.gn2_l = cs[1]; st.gz_l = cs[2]; st.zHz_l = cs[3]; st.uHz_l = cs[4]; st.uHu_l = cs[5];
   const double dlg2 = st.dlg2_x + st.dlg2_l, gn2 = st.gn2_x + st.gn2_l, gz = st.gz_x + st.gz_l;
   const double uHu = st.uSu - st.mu * st.uEu_x + st.uHu_l;
   const double alpha = dlg2 / uHu;
@@ -477,32 +478,33 @@ __device__ void dogleg_coefficients(WinState& st) {
   st.model_cost_change = a * dlg2 + b * gz - 0.5 * (a * a * uHu + 2 * a * b * uHz + b * b * zHz);
 }
 
-__global__ void __launch_bounds__(288, 2) k_candidate(KP p, int w0) {
+__global__ void __launch_bounds__(288, 2) k_cand_eval(KP p, int w0) {
   const int w = w0 + blockIdx.x;
   WinState& st = p.st[w];
   if (!st.active) return;
   if (!st.lin_valid) return;  // invalid linear solve already handled in k_solve
   __shared__ StepShared S;
   const int t = threadIdx.x, F = p.F, D = p.D;
-  if (t == 0) dogleg_coefficients(st);
+  if (t == 0) dogleg_coefficients(st, p.c_sums + (size_t)w * 8);
   __syncthreads();
   const double a = st.coef_a, b = st.coef_b;
   const double* pose = p.pose + (size_t)w * F * 7; const double* sb = p.sb + (size_t)w * F * 9;
   double* pose_c = p.pose_c + (size_t)w * F * 7; double* sb_c = p.sb_c + (size_t)w * F * 9;
-  double acc[3] = {0, 0, 0};  // candidate cost, |x - cand|^2, |x|^2
+  double acc[3] = {0, 0, 0};   // this rank's landmarks / planes: candidate cost, |dl|^2, |l|^2   (all-reduced in sharded mode)
+  double accx[3] = {0, 0, 0};  // frame states and non-visual factors (every rank computes the same): cost, |dx|^2, |x|^2
   // retraction of frame states: PoseLocalParameterization::Plus (VE/factor/pose_local_parameterization.cpp:12-28)
   if (t < F) {
     const double* zx = p.zx + (size_t)w * D + 15 * t; const double* ux = p.ux + (size_t)w * D + 15 * t;
     double dl[15];
     for (int k = 0; k < 15; k++) dl[k] = -(a * ux[k] + b * zx[k]);
     const double* x = pose + 7 * t; double* xc = pose_c + 7 * t;
-    for (int k = 0; k < 3; k++) { xc[k] = x[k] + dl[k]; acc[1] += dl[k] * dl[k]; acc[2] += x[k] * x[k]; }
+    for (int k = 0; k < 3; k++) { xc[k] = x[k] + dl[k]; accx[1] += dl[k] * dl[k]; accx[2] += x[k] * x[k]; }
     Q4 q = ldq(x + 3); Q4 qn = qnormalized(qmul(q, deltaQ(mk3(dl[3], dl[4], dl[5]))));
     xc[3] = qn.x; xc[4] = qn.y; xc[5] = qn.z; xc[6] = qn.w;
-    acc[1] += (q.x - qn.x) * (q.x - qn.x) + (q.y - qn.y) * (q.y - qn.y) + (q.z - qn.z) * (q.z - qn.z) + (q.w - qn.w) * (q.w - qn.w);
-    acc[2] += q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w;
+    accx[1] += (q.x - qn.x) * (q.x - qn.x) + (q.y - qn.y) * (q.y - qn.y) + (q.z - qn.z) * (q.z - qn.z) + (q.w - qn.w) * (q.w - qn.w);
+    accx[2] += q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w;
     const double* v = sb + 9 * t; double* vc = sb_c + 9 * t;
-    for (int k = 0; k < 9; k++) { vc[k] = v[k] + dl[6 + k]; acc[1] += dl[6 + k] * dl[6 + k]; acc[2] += v[k] * v[k]; }
+    for (int k = 0; k < 9; k++) { vc[k] = v[k] + dl[6 + k]; accx[1] += dl[6 + k] * dl[6 + k]; accx[2] += v[k] * v[k]; }
   }
   __syncthreads();
   build_frames(pose_c, p.ex + (size_t)w * 7, p.td[w], F, S.fr, &S.cam);
@@ -546,7 +548,7 @@ __global__ void __launch_bounds__(288, 2) k_candidate(KP p, int w0) {
       if (pre.valid && pre.sum_dt <= 10.0) {
         double r[15]; ImuStates s2 = load_imu_states(pose_c, sb_c, ln);
         imu_raw(pre, s2, p.g_norm, r, nullptr);
-        acc[0] += imu_cost(p.imu_sqrt + ((size_t)w * (F - 1) + ln) * 225, r);
+        accx[0] += imu_cost(p.imu_sqrt + ((size_t)w * (F - 1) + ln) * 225, r);
       }
     }
     if (p.wheel && ln >= 16 && ln - 16 < F - 1) {
@@ -555,7 +557,7 @@ __global__ void __launch_bounds__(288, 2) k_candidate(KP p, int w0) {
       if (pre.valid && pre.sum_dt <= 10.0) {
         double r[6];
         wheel_raw(pre, pose_c + 7 * k, pose_c + 7 * (k + 1), p.exw + (size_t)w * 7, p.sxw + (size_t)w * 3, p.tdw[w], r, nullptr);
-        acc[0] += wheel_cost(p.wheel_sqrt + ((size_t)w * (F - 1) + k) * 36, r);
+        accx[0] += wheel_cost(p.wheel_sqrt + ((size_t)w * (F - 1) + k) * 36, r);
       }
     }
     const int n = p.prior_rows ? p.prior_rows[w] : 0;
@@ -564,12 +566,30 @@ __global__ void __launch_bounds__(288, 2) k_candidate(KP p, int w0) {
       if (ln < p.prior_nblocks[w]) prior_block_dx(blk[ln], pose_c, sb_c, S.dx);
       __syncwarp();
       const double* J0 = p.prior_J0 + (size_t)w * kP * kP; const double* r0p = p.prior_r0 + (size_t)w * kP;
-      for (int row = ln; row < n; row += 32) { double s2 = r0p[row]; for (int c = 0; c < n; c++) s2 += J0[row * kP + c] * S.dx[c]; acc[0] += 0.5 * s2 * s2; }
+      for (int row = ln; row < n; row += 32) { double s2 = r0p[row]; for (int c = 0; c < n; c++) s2 += J0[row * kP + c] * S.dx[c]; accx[0] += 0.5 * s2 * s2; }
     }
   }
   block_sum<3>(acc, S.red);
-  // TrustRegionMinimizer: tolerance checks, step acceptance, radius update
+  block_sum<3>(accx, S.red);
   if (t == 0) {
+    double* cc = p.c_cand + (size_t)w * 4;
+    cc[0] = acc[0]; cc[1] = acc[1]; cc[2] = acc[2];
+    st.cand_nv = accx[0]; st.step2_x = accx[1]; st.xnorm2_x = accx[2];
+  }
+}
+
+// TrustRegionMinimizer: tolerance checks, step acceptance, radius update (after the candidate sums are complete)
+__global__ void __launch_bounds__(256) k_decide(KP p, int w0) {
+  const int w = w0 + blockIdx.x;
+  WinState& st = p.st[w];
+  if (!st.active) return;
+  if (!st.lin_valid) return;
+  __shared__ int s_decision;
+  const int t = threadIdx.x, F = p.F;
+  const int nlm = p.nlm[w];
+  if (t == 0) {
+    const double* cc = p.c_cand + (size_t)w * 4;
+    const double acc[3] = {cc[0] + st.cand_nv, cc[1] + st.step2_x, cc[2] + st.xnorm2_x};
     int decision = 0;  // 0 reject, 1 accept, 2 terminated (no accept)
     st.cand_cost = acc[0];
     st.x_norm2 = acc[2];
@@ -601,15 +621,16 @@ __global__ void __launch_bounds__(288, 2) k_candidate(KP p, int w0) {
       if (st.iteration >= p.max_iterations) { st.active = 0; st.termination = GF2_TERM_NO_CONVERGENCE; }
       else if (st.radius <= 1e-32) { st.active = 0; st.termination = GF2_TERM_MIN_RADIUS; }
     }
-    S.decision = decision;
+    s_decision = decision;
     if (p.trace && st.iteration <= 64) {
       double* tr = p.trace + ((size_t)w * 64 + (st.iteration - 1)) * 6;
       tr[0] = st.cand_cost; tr[1] = st.model_cost_change; tr[2] = (st.x_cost_prev - st.cand_cost) / st.model_cost_change; tr[3] = st.radius; tr[4] = sqrt(acc[1]); tr[5] = decision;
     }
   }
   __syncthreads();
-  if (S.decision == 1) {  // x = candidate
+  if (s_decision == 1) {  // x = candidate
     double* poseW = p.pose + (size_t)w * F * 7; double* sbW = p.sb + (size_t)w * F * 9;
+    const double* pose_c = p.pose_c + (size_t)w * F * 7; const double* sb_c = p.sb_c + (size_t)w * F * 9;
     for (int i = t; i < F * 7; i += blockDim.x) poseW[i] = pose_c[i];
     for (int i = t; i < F * 9; i += blockDim.x) sbW[i] = sb_c[i];
     for (int l = t; l < nlm; l += blockDim.x) p.invdep[(size_t)w * p.Lm + l] = p.invdep_c[(size_t)w * p.Lm + l];

@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(kLinThreads, 1) k_linearize(KP p, int w0) {
   __syncthreads();
   if (t == 0) {
     double gm = 0; for (int i2 = 0; i2 < kLinThreads / 32; i2++) gm = fmax(gm, S.red[i2]);
-    st.cost_vis = red2[0]; st.gmax_l = gm;
+    p.c_lin[(size_t)w * 4] = red2[0]; p.c_gmax[w] = gm;
   }
 }
 

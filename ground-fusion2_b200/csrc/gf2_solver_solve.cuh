@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) k_solve2(KP p, int w0) {
     }
     __syncthreads();
   }
-  if (t == 0) { st.x_cost = st.cost_vis + p.cost_nv[w]; if (st.iteration == 0) st.initial_cost = st.x_cost; }
+  if (t == 0) { st.cost_vis = p.c_lin[(size_t)w * 4]; st.gmax_l = p.c_gmax[w]; st.x_cost = st.cost_vis + p.cost_nv[w]; if (st.iteration == 0) st.initial_cost = st.x_cost; }
   if (p.Sfull) {
     double* Sf = p.Sfull + (size_t)w * D * D;
     for (int idx = t; idx < D * D; idx += nt) { const int a = idx / D, b = idx % D; Sf[idx] = a >= b ? Ael(A, a, b) : Ael(A, b, a); }
@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) k_solve2(KP p, int w0) {
     double gm = 0; for (int i = 0; i < nwarp; i++) gm = fmax(gm, S.red[i]);
     st.dlg2_x = sums[0]; st.uEu_x = sums[1]; st.gmax_x = gm;
     S.flag = 0;
-    if (fmax(gm, st.gmax_l) <= p.gtol) { st.active = 0; st.termination = GF2_TERM_GRADIENT_TOL; S.flag = 2; }
+    if (fmax(gm, p.c_gmax[w]) <= p.gtol) { st.active = 0; st.termination = GF2_TERM_GRADIENT_TOL; S.flag = 2; }
   }
   __syncthreads();
   if (S.flag == 2) return;

@@ -1,0 +1,71 @@
+"""Factor-sharded multi-GPU solve (BASELINE.json config 4): launch with
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P scripts/run_sharded.py [--windows B]
+Every rank holds all frame states + IMU/wheel/prior and its l mod N landmarks / planes; one NCCL all-reduce of the visual block
+system per linearisation. Rank 0 also solves the unsharded windows on its own GPU and checks parity; prints one JSON line."""
+import argparse, importlib, json, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT]
+import numpy as np
+import torch
+import torch.distributed as dist
+from gf2_loader import load
+
+ap = argparse.ArgumentParser(); ap.add_argument("--windows", type=int, default=64); ap.add_argument("--landmarks", type=int, default=1000)
+ap.add_argument("--planes", type=int, default=5000); ap.add_argument("--steps", type=int, default=3)
+args = ap.parse_args()
+rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+gf2 = load(); synth = importlib.import_module("gf2_b200.synth"); shard = importlib.import_module("gf2_b200.shard")
+B = args.windows
+distinct = min(B, 8)
+base = synth.make_windows(distinct, config_id=4, n_landmarks=args.landmarks, wheel=True, n_planes=args.planes)
+w = {k: (np.concatenate([v] * ((B + distinct - 1) // distinct))[:B] if isinstance(v, np.ndarray) and v.ndim >= 1 and v.shape[0] == distinct and k not in ("imu_noise", "wheel_noise") else v) for k, v in base.items()}
+
+def solver_for(d):
+    return gf2.Solver(B, d["n_frames"], d["max_landmarks"], d["max_obs"], max_planes=d["max_planes"], max_imu_samples=d["n_imu_samples"], use_wheel=True, device=local)
+
+# wheel preintegration records: device kernel not built yet -> records come from the caller; here a zero-motion-consistent
+# record is not available without the oracle, so the wheel factor is exercised in tests/ (oracle records) and left out here
+w["use_wheel"] = False
+def mk(d):
+    s = gf2.Solver(B, d["n_frames"], d["max_landmarks"], d["max_obs"], max_planes=d["max_planes"], max_imu_samples=d["n_imu_samples"], device=local)
+    return s
+mine = shard.shard_windows(w, rank, world)
+s = mk(mine)
+uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+if rank == 0:
+    uid.copy_(torch.from_numpy(gf2.Solver.comm_unique_id()).cuda())
+dist.broadcast(uid, 0)
+s.comm_init(rank, world, uid.cpu().numpy())
+opts = gf2.abi.default_opts()
+s.upload(mine, preintegrate="device"); s.snapshot(B)
+summ = s.solve(opts, B)   # warm-up
+times = []
+for _ in range(args.steps):
+    s.restore(B); torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter()
+    summ = s.solve(opts, B)
+    torch.cuda.synchronize(); times.append(time.perf_counter() - t0)
+tt = torch.tensor([min(times)], device="cuda"); dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+st = s.get_states(B); lam = s.get_landmarks(B)
+lam_t = torch.from_numpy(lam).cuda(); gathered = [torch.zeros_like(lam_t) for _ in range(world)]
+dist.all_gather(gathered, lam_t)
+if rank == 0:
+    ref = mk(w); ref.upload(w, preintegrate="device"); ref.snapshot(B)
+    rs = ref.solve(opts, B)
+    t1 = []
+    for _ in range(args.steps):
+        ref.restore(B); torch.cuda.synchronize(); t0 = time.perf_counter(); rs = ref.solve(opts, B); torch.cuda.synchronize(); t1.append(time.perf_counter() - t0)
+    rst = ref.get_states(B); rlam = ref.get_landmarks(B)
+    lam_full = shard.gather_landmarks(w["n_landmarks"], [g.cpu().numpy() for g in gathered], world)
+    out = {"n_gpus": world, "windows": B, "landmarks": args.landmarks, "planes": args.planes,
+           "sharded_ms": 1e3 * float(tt.item()), "single_gpu_ms": 1e3 * min(t1),
+           "sharded_solves_per_s": B / float(tt.item()), "single_solves_per_s": B / min(t1),
+           "pose_diff": float(np.abs(st["para_pose"] - rst["para_pose"]).max()), "speedbias_diff": float(np.abs(st["para_speedbias"] - rst["para_speedbias"]).max()),
+           "inv_depth_diff": float(np.abs(lam_full - rlam).max()),
+           "iterations_equal": bool((summ["iterations"] == rs["iterations"]).all()), "termination_equal": bool((summ["termination"] == rs["termination"]).all()),
+           "final_cost_rel_diff": float((np.abs(summ["final_cost"] - rs["final_cost"]) / rs["final_cost"]).max())}
+    print(json.dumps(out))
+    assert out["iterations_equal"] and out["termination_equal"] and out["pose_diff"] < 1e-6 and out["inv_depth_diff"] < 1e-6, out
+s.close()
+dist.destroy_process_group()

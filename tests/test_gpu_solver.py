@@ -196,3 +196,22 @@ def test_bad_arguments_are_rejected(gf2, synth):
     with pytest.raises(gf2.Gf2Error, match="capacity"):
         s.solve(gf2.abi.default_opts(), 2)
     s.close()
+
+
+def test_factor_sharded_two_gpus_match_single_gpu(gf2):
+    """landmarks/planes sharded over 2 GPUs with one NCCL all-reduce per linearisation == single-GPU solve.
+    Needs 2 visible GPUs (skipped on the 1-GPU box; run with `gpurun --gpus 2 -- python -m pytest tests -m gpu -k sharded`)."""
+    import json as _json
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29531",
+                          os.path.join(root, "scripts", "run_sharded.py"), "--windows", "8", "--landmarks", "400", "--planes", "800", "--steps", "1"],
+                         capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    out = _json.loads([ln for ln in res.stdout.splitlines() if ln.startswith("{")][-1])
+    assert out["iterations_equal"] and out["pose_diff"] < 1e-6
