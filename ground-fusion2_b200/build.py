@@ -15,7 +15,7 @@ def needs_build():
     if not os.path.exists(OUT):
         return True
     t = os.path.getmtime(OUT)
-    for root in (CSRC, os.path.join(HERE, "..", "include")):
+    for root in (CSRC, os.path.join(HERE, "host"), os.path.join(HERE, "..", "include")):
         for f in os.listdir(root):
             if os.path.getmtime(os.path.join(root, f)) > t:
                 return True
@@ -35,6 +35,17 @@ def build(force=False, verbose=False):
         print(log)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed building libgf2_b200.so")
+    # host-side C++ mirror of the reference classes (Estimator / FeatureManager / FeatureTracker glue) over the C ABI
+    host_out = os.path.join(HERE, "libgf2_host.so")
+    cmd = [os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-o", host_out, os.path.join(HERE, "host", "gf2_host.cpp"),
+           "-L" + HERE, "-lgf2_b200", "-Wl,-rpath,$ORIGIN", "-Wl,--exclude-libs,ALL"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    with open(os.path.join(HERE, "build.log"), "a") as f:
+        f.write(" ".join(cmd) + "\n" + res.stdout + res.stderr)
+    if verbose or res.returncode != 0:
+        print(res.stdout + res.stderr)
+    if res.returncode != 0:
+        raise RuntimeError("g++ failed building libgf2_host.so")
     return OUT
 
 

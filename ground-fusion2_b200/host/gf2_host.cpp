@@ -1,0 +1,529 @@
+// gf2_host.cpp — see gf2_host.h. Host-side mirror of Estimator / FeatureManager / FeatureTracker glue over the C ABI.
+#include "gf2_host.h"
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <cstdlib>
+
+namespace gf2host {
+
+// ------------------------------------------------------------------------------------------------ small math
+Matrix3d mul(const Matrix3d& a, const Matrix3d& b) {
+  Matrix3d r;
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) r.m[i * 3 + j] = a.m[i * 3] * b.m[j] + a.m[i * 3 + 1] * b.m[3 + j] + a.m[i * 3 + 2] * b.m[6 + j];
+  return r;
+}
+Vector3d mul(const Matrix3d& a, const Vector3d& v) {
+  return {a.m[0] * v.x + a.m[1] * v.y + a.m[2] * v.z, a.m[3] * v.x + a.m[4] * v.y + a.m[5] * v.z, a.m[6] * v.x + a.m[7] * v.y + a.m[8] * v.z};
+}
+Matrix3d transpose(const Matrix3d& a) { Matrix3d r; for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) r.m[i * 3 + j] = a.m[j * 3 + i]; return r; }
+Quaterniond quatFromMatrix(const Matrix3d& R) {  // Eigen::Quaterniond(Matrix3d)
+  Quaterniond q; const double* m = R.m;
+  double t = m[0] + m[4] + m[8];
+  if (t > 0) { t = std::sqrt(t + 1.0); q.w = 0.5 * t; t = 0.5 / t; q.x = (m[7] - m[5]) * t; q.y = (m[2] - m[6]) * t; q.z = (m[3] - m[1]) * t; }
+  else {
+    int i = 0; if (m[4] > m[0]) i = 1; if (m[8] > m[i * 4]) i = 2;
+    int j = (i + 1) % 3, k = (j + 1) % 3;
+    t = std::sqrt(m[i * 4] - m[j * 4] - m[k * 4] + 1.0);
+    double v[3]; v[i] = 0.5 * t; t = 0.5 / t;
+    q.w = (m[k * 3 + j] - m[j * 3 + k]) * t; v[j] = (m[j * 3 + i] + m[i * 3 + j]) * t; v[k] = (m[k * 3 + i] + m[i * 3 + k]) * t;
+    q.x = v[0]; q.y = v[1]; q.z = v[2];
+  }
+  return q;
+}
+Matrix3d toRotationMatrix(const Quaterniond& q) {
+  Matrix3d r; const double tx = 2 * q.x, ty = 2 * q.y, tz = 2 * q.z;
+  const double twx = tx * q.w, twy = ty * q.w, twz = tz * q.w, txx = tx * q.x, txy = ty * q.x, txz = tz * q.x, tyy = ty * q.y, tyz = tz * q.y, tzz = tz * q.z;
+  r.m[0] = 1 - (tyy + tzz); r.m[1] = txy - twz; r.m[2] = txz + twy; r.m[3] = txy + twz; r.m[4] = 1 - (txx + tzz); r.m[5] = tyz - twx;
+  r.m[6] = txz - twy; r.m[7] = tyz + twx; r.m[8] = 1 - (txx + tyy);
+  return r;
+}
+static Quaterniond normalized(Quaterniond q) { double n = std::sqrt(q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z); return {q.w / n, q.x / n, q.y / n, q.z / n}; }
+Vector3d R2ypr(const Matrix3d& R) {  // VE/utility/utility.h:78-93
+  const double n0 = R.m[0], n1 = R.m[3], n2 = R.m[6], o0 = R.m[1], o1 = R.m[4], a0 = R.m[2], a1 = R.m[5];
+  const double y = std::atan2(n1, n0);
+  const double p = std::atan2(-n2, n0 * std::cos(y) + n1 * std::sin(y));
+  const double r = std::atan2(a0 * std::sin(y) - a1 * std::cos(y), -o0 * std::sin(y) + o1 * std::cos(y));
+  return {y / M_PI * 180.0, p / M_PI * 180.0, r / M_PI * 180.0};
+}
+Matrix3d ypr2R(const Vector3d& ypr) {  // VE/utility/utility.h:95-121
+  const double y = ypr.x / 180.0 * M_PI, p = ypr.y / 180.0 * M_PI, r = ypr.z / 180.0 * M_PI;
+  Matrix3d Rz, Ry, Rx;
+  Rz.m[0] = std::cos(y); Rz.m[1] = -std::sin(y); Rz.m[3] = std::sin(y); Rz.m[4] = std::cos(y);
+  Ry.m[0] = std::cos(p); Ry.m[2] = std::sin(p); Ry.m[6] = -std::sin(p); Ry.m[8] = std::cos(p);
+  Rx.m[4] = std::cos(r); Rx.m[5] = -std::sin(r); Rx.m[7] = std::sin(r); Rx.m[8] = std::cos(r);
+  return mul(mul(Rz, Ry), Rx);
+}
+
+// ------------------------------------------------------------------------------------------------ YAML (OpenCV FileStorage dialect)
+namespace {
+struct Yaml {
+  std::map<std::string, std::string> scalars;
+  std::map<std::string, std::vector<double>> matrices;
+  // C stdio + strtod only: this library is loaded into Python processes next to other C++ runtimes, iostream/locale
+  // state must not be touched
+  bool load(const std::string& path) {
+    FILE* f = fopen(path.c_str(), "r");
+    if (!f) return false;
+    std::string cur_key; bool in_data = false; std::string data;
+    auto trim = [](std::string s) { size_t a = s.find_first_not_of(" \t\r\n\""); size_t b = s.find_last_not_of(" \t\r\n\""); return a == std::string::npos ? std::string() : s.substr(a, b - a + 1); };
+    auto flush = [&]() {
+      if (cur_key.empty() || data.empty()) return;
+      std::vector<double> v;
+      const char* c = data.c_str();
+      while (*c) {
+        while (*c && (*c == ',' || *c == '[' || *c == ']' || *c == ' ' || *c == '\t' || *c == '\r' || *c == '\n')) c++;
+        if (!*c) break;
+        char* end = nullptr; const double x = strtod(c, &end);
+        if (end == c) break;
+        v.push_back(x); c = end;
+      }
+      matrices[cur_key] = v; data.clear();
+    };
+    char buf[4096];
+    while (fgets(buf, sizeof(buf), f)) {
+      std::string line(buf);
+      while (!line.empty() && (line.back() == '\n' || line.back() == '\r')) line.pop_back();
+      size_t hash = line.find('#'); if (hash != std::string::npos) line = line.substr(0, hash);
+      if (line.empty() || line[0] == '%' || line.compare(0, 3, "---") == 0) continue;
+      if (in_data) { data += " " + line; if (line.find(']') != std::string::npos) { in_data = false; flush(); } continue; }
+      size_t colon = line.find(':');
+      if (colon == std::string::npos) continue;
+      std::string key = trim(line.substr(0, colon)), val = trim(line.substr(colon + 1));
+      const bool nested = line[0] == ' ' || line[0] == '\t';
+      if (!nested) {
+        if (val.find("!!opencv-matrix") != std::string::npos) { cur_key = key; continue; }
+        if (val.empty()) { cur_key = key; continue; }  // mapping node (distortion_parameters: ...)
+        scalars[key] = val; cur_key.clear();
+      } else {
+        if (key == "data") { data = val; if (val.find(']') == std::string::npos) in_data = true; else flush(); }
+        else if (key != "rows" && key != "cols" && key != "dt") scalars[cur_key.empty() ? key : cur_key + "." + key] = val;
+      }
+    }
+    fclose(f);
+    return true;
+  }
+  double num(const std::string& k) const { auto it = scalars.find(k); return it == scalars.end() ? 0.0 : std::atof(it->second.c_str()); }  // absent -> 0 (cv::FileNode)
+  std::string str(const std::string& k) const { auto it = scalars.find(k); return it == scalars.end() ? std::string() : it->second; }
+};
+}  // namespace
+
+bool readParameters(const std::string& config_file, Parameters& P) {  // keys and derived values of parameters.cpp:160-556
+  Yaml y;
+  if (!y.load(config_file)) return false;
+  P.USE_IMU = (int)y.num("imu"); P.USE_WHEEL = (int)y.num("wheel");
+  P.MAX_CNT = (int)y.num("max_cnt"); P.MIN_DIST = (int)y.num("min_dist"); P.F_THRESHOLD = y.num("F_threshold"); P.FLOW_BACK = (int)y.num("flow_back");
+  P.ACC_N = y.num("acc_n"); P.ACC_W = y.num("acc_w"); P.GYR_N = y.num("gyr_n"); P.GYR_W = y.num("gyr_w"); P.G_NORM = y.num("g_norm");
+  P.SOLVER_TIME = y.num("max_solver_time"); P.NUM_ITERATIONS = (int)y.num("max_num_iterations");
+  P.MIN_PARALLAX = y.num("keyframe_parallax") / FOCAL_LENGTH;  // :351-352
+  P.ESTIMATE_EXTRINSIC = (int)y.num("estimate_extrinsic"); P.ESTIMATE_TD = (int)y.num("estimate_td"); P.TD = y.num("td");
+  P.ROW = (int)y.num("image_height"); P.COL = (int)y.num("image_width");
+  auto it = y.matrices.find("body_T_cam0");
+  if (it != y.matrices.end() && it->second.size() == 16) {
+    const std::vector<double>& T = it->second;
+    Matrix3d R; for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) R.m[r * 3 + c] = T[r * 4 + c];
+    P.RIC = toRotationMatrix(normalized(quatFromMatrix(R)));  // re-orthonormalised through a quaternion (:387-395)
+    P.TIC = {T[3], T[7], T[11]};
+  }
+  const std::string cam = y.str("cam0_calib");
+  if (!cam.empty()) {
+    const size_t slash = config_file.find_last_of('/');
+    Yaml c;
+    if (c.load((slash == std::string::npos ? std::string() : config_file.substr(0, slash + 1)) + cam)) {
+      P.fx = c.num("projection_parameters.fx"); P.fy = c.num("projection_parameters.fy"); P.cx = c.num("projection_parameters.cx"); P.cy = c.num("projection_parameters.cy");
+      P.k1 = c.num("distortion_parameters.k1"); P.k2 = c.num("distortion_parameters.k2"); P.p1 = c.num("distortion_parameters.p1"); P.p2 = c.num("distortion_parameters.p2");
+    }
+  }
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------------ FeatureManager
+int FeatureManager::getFeatureCount() {
+  int cnt = 0;
+  for (auto& it : feature) { it.used_num = (int)it.feature_per_frame.size(); if (it.used_num >= 4) cnt++; }
+  return cnt;
+}
+std::vector<double> FeatureManager::getDepthVector() {
+  std::vector<double> dep_vec(getFeatureCount());
+  int feature_index = -1;
+  for (auto& it_per_id : feature) {
+    it_per_id.used_num = (int)it_per_id.feature_per_frame.size();
+    if (it_per_id.used_num < 4) continue;
+    dep_vec[++feature_index] = 1. / it_per_id.estimated_depth;
+  }
+  return dep_vec;
+}
+void FeatureManager::setDepth(const std::vector<double>& x) {
+  int feature_index = -1;
+  for (auto& it_per_id : feature) {
+    it_per_id.used_num = (int)it_per_id.feature_per_frame.size();
+    if (it_per_id.used_num < 4) continue;
+    it_per_id.estimated_depth = 1.0 / x[++feature_index];
+    it_per_id.solve_flag = it_per_id.estimated_depth < 0 ? 2 : 1;
+  }
+}
+void FeatureManager::removeFailures() {
+  for (auto it = feature.begin(), it_next = feature.begin(); it != feature.end(); it = it_next) { it_next++; if (it->solve_flag == 2) feature.erase(it); }
+}
+void FeatureManager::clearDepth() { for (auto& it : feature) it.estimated_depth = -1; }
+void FeatureManager::addFeatures(int frame_count, const std::map<int, std::vector<std::pair<int, std::vector<double>>>>& image, double td) {
+  for (auto& id_pts : image) {  // std::map iteration = ascending feature id, new features appended at the list tail
+    FeaturePerFrame f_per_fra(id_pts.second[0].second.data(), td);
+    const int feature_id = id_pts.first;
+    auto it = std::find_if(feature.begin(), feature.end(), [feature_id](const FeaturePerId& f) { return f.feature_id == feature_id; });
+    if (it == feature.end()) { feature.push_back(FeaturePerId(feature_id, frame_count)); feature.back().feature_per_frame.push_back(f_per_fra); }
+    else it->feature_per_frame.push_back(f_per_fra);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ Estimator
+Estimator::Estimator() { clearState(); memset(&last_summary, 0, sizeof(last_summary)); }
+Estimator::~Estimator() {
+  if (gf2) gf2_solver_destroy(gf2);
+  for (auto& p : pre_integrations) { delete p; p = nullptr; }
+}
+void Estimator::setParameter(const Parameters& p) { P = p; tic[0] = p.TIC; ric[0] = p.RIC; td = p.TD; }
+void Estimator::clearState() {
+  for (int i = 0; i <= WINDOW_SIZE; i++) { Rs[i] = Matrix3d(); Ps[i] = Vector3d(); Vs[i] = Vector3d(); Bas[i] = Vector3d(); Bgs[i] = Vector3d(); delete pre_integrations[i]; pre_integrations[i] = nullptr; }
+  f_manager.feature.clear(); last_marginalization_info = MarginalizationPrior(); failure_occur = false; openExEstimation = false;
+}
+
+void Estimator::vector2double() {
+  for (int i = 0; i <= WINDOW_SIZE; i++) {
+    para_Pose[i][0] = Ps[i].x; para_Pose[i][1] = Ps[i].y; para_Pose[i][2] = Ps[i].z;
+    const Quaterniond q = quatFromMatrix(Rs[i]);
+    para_Pose[i][3] = q.x; para_Pose[i][4] = q.y; para_Pose[i][5] = q.z; para_Pose[i][6] = q.w;
+    if (P.USE_IMU) {
+      para_SpeedBias[i][0] = Vs[i].x; para_SpeedBias[i][1] = Vs[i].y; para_SpeedBias[i][2] = Vs[i].z;
+      para_SpeedBias[i][3] = Bas[i].x; para_SpeedBias[i][4] = Bas[i].y; para_SpeedBias[i][5] = Bas[i].z;
+      para_SpeedBias[i][6] = Bgs[i].x; para_SpeedBias[i][7] = Bgs[i].y; para_SpeedBias[i][8] = Bgs[i].z;
+    }
+  }
+  para_Ex_Pose[0][0] = tic[0].x; para_Ex_Pose[0][1] = tic[0].y; para_Ex_Pose[0][2] = tic[0].z;
+  const Quaterniond q = quatFromMatrix(ric[0]);
+  para_Ex_Pose[0][3] = q.x; para_Ex_Pose[0][4] = q.y; para_Ex_Pose[0][5] = q.z; para_Ex_Pose[0][6] = q.w;
+  const std::vector<double> dep = f_manager.getDepthVector();
+  for (int i = 0; i < f_manager.getFeatureCount(); i++) para_Feature[i][0] = dep[i];
+  para_Td[0][0] = td;
+}
+
+void Estimator::double2vector() {
+  Vector3d origin_R0 = R2ypr(Rs[0]);
+  Vector3d origin_P0 = Ps[0];
+  if (failure_occur) { origin_R0 = R2ypr(last_R0); origin_P0 = last_P0; failure_occur = false; }
+  if (P.USE_IMU) {
+    const Matrix3d R00 = toRotationMatrix({para_Pose[0][6], para_Pose[0][3], para_Pose[0][4], para_Pose[0][5]});
+    const Vector3d origin_R00 = R2ypr(R00);
+    const double y_diff = origin_R0.x - origin_R00.x;
+    Matrix3d rot_diff = ypr2R({y_diff, 0, 0});
+    if (std::fabs(std::fabs(origin_R0.y) - 90) < 1.0 || std::fabs(std::fabs(origin_R00.y) - 90) < 1.0) rot_diff = mul(Rs[0], transpose(R00));  // euler singular point
+    for (int i = 0; i <= WINDOW_SIZE; i++) {
+      Rs[i] = mul(rot_diff, toRotationMatrix(normalized({para_Pose[i][6], para_Pose[i][3], para_Pose[i][4], para_Pose[i][5]})));
+      const Vector3d d = mul(rot_diff, Vector3d{para_Pose[i][0] - para_Pose[0][0], para_Pose[i][1] - para_Pose[0][1], para_Pose[i][2] - para_Pose[0][2]});
+      Ps[i] = {d.x + origin_P0.x, d.y + origin_P0.y, d.z + origin_P0.z};
+      Vs[i] = mul(rot_diff, Vector3d{para_SpeedBias[i][0], para_SpeedBias[i][1], para_SpeedBias[i][2]});
+      Bas[i] = {para_SpeedBias[i][3], para_SpeedBias[i][4], para_SpeedBias[i][5]};
+      Bgs[i] = {para_SpeedBias[i][6], para_SpeedBias[i][7], para_SpeedBias[i][8]};
+    }
+    tic[0] = {para_Ex_Pose[0][0], para_Ex_Pose[0][1], para_Ex_Pose[0][2]};
+    ric[0] = toRotationMatrix({para_Ex_Pose[0][6], para_Ex_Pose[0][3], para_Ex_Pose[0][4], para_Ex_Pose[0][5]});
+  } else {
+    for (int i = 0; i <= WINDOW_SIZE; i++) {
+      Rs[i] = toRotationMatrix(normalized({para_Pose[i][6], para_Pose[i][3], para_Pose[i][4], para_Pose[i][5]}));
+      Ps[i] = {para_Pose[i][0], para_Pose[i][1], para_Pose[i][2]};
+    }
+  }
+  std::vector<double> dep = f_manager.getDepthVector();
+  for (int i = 0; i < f_manager.getFeatureCount(); i++) dep[i] = para_Feature[i][0];
+  f_manager.setDepth(dep);
+  if (P.USE_IMU) td = para_Td[0][0];
+}
+
+void Estimator::optimization() {
+  last_error.clear();
+  vector2double();
+  const int F = frame_count + 1;
+  if (!gf2) {
+    gf2_solver_cfg cfg; memset(&cfg, 0, sizeof(cfg));
+    cfg.device = 0; cfg.max_windows = 1; cfg.n_frames = WINDOW_SIZE + 1; cfg.max_landmarks = NUM_OF_F; cfg.max_obs = NUM_OF_F * (WINDOW_SIZE + 1);
+    cfg.max_imu_samples = 64;
+    if (gf2_solver_create(&cfg, &gf2) != GF2_OK) { last_error = gf2_last_error(); gf2 = nullptr; return; }
+  }
+  if (F != WINDOW_SIZE + 1) { last_error = "gf2host::Estimator::optimization handles the steady state frame_count == WINDOW_SIZE"; return; }
+  // landmark table in getDepthVector order (used_num >= 4, estimator.cpp:3330-3358)
+  std::vector<int32_t> start, len; std::vector<uint8_t> fixed; std::vector<gf2_obs> obs; std::vector<double> frame_td(F, td);
+  for (auto& it_per_id : f_manager.feature) {
+    it_per_id.used_num = (int)it_per_id.feature_per_frame.size();
+    if (it_per_id.used_num < 4) continue;
+    start.push_back(it_per_id.start_frame); len.push_back(it_per_id.used_num); fixed.push_back(it_per_id.estimate_flag == 1);
+    int f = it_per_id.start_frame;
+    for (auto& pf : it_per_id.feature_per_frame) {
+      obs.push_back({(float)pf.point.x, (float)pf.point.y, (float)pf.velocity[0], (float)pf.velocity[1]});
+      if (f < F) frame_td[f] = pf.cur_td;
+      f++;
+    }
+  }
+  int32_t n_lm = (int32_t)start.size();
+  std::vector<double> invdep(NUM_OF_F, 1.0); for (int i = 0; i < n_lm; i++) invdep[i] = para_Feature[i][0];
+  start.resize(NUM_OF_F, 0); len.resize(NUM_OF_F, 0); fixed.resize(NUM_OF_F, 0); obs.resize((size_t)NUM_OF_F * (WINDOW_SIZE + 1));
+  int rc = gf2_set_states(gf2, 0, 1, &para_Pose[0][0], &para_SpeedBias[0][0], para_Ex_Pose[0], para_Td[0], nullptr, nullptr, nullptr);
+  if (rc == GF2_OK) rc = gf2_set_landmarks(gf2, 0, 1, &n_lm, invdep.data(), start.data(), len.data(), fixed.data(), obs.data(), frame_td.data());
+  // raw IMU samples of every interval -> device preintegration (IntegrationBase::push_back chain)
+  if (rc == GF2_OK && P.USE_IMU) {
+    std::vector<gf2_imu_sample> smp((size_t)(F - 1) * 64); std::vector<int32_t> ns(F - 1, 0); std::vector<double> first((F - 1) * 6, 0.0), bias((F - 1) * 6, 0.0);
+    for (int j = 1; j < F; j++) {
+      const IntegrationBase* pi = pre_integrations[j];
+      if (!pi) { last_error = "pre_integrations[j] missing"; return; }
+      const int n = (int)std::min<size_t>(pi->dt_buf.size(), 64);
+      ns[j - 1] = n;
+      for (int s = 0; s < n; s++) { gf2_imu_sample& o = smp[(size_t)(j - 1) * 64 + s]; o.dt = pi->dt_buf[s]; o.acc[0] = pi->acc_buf[s].x; o.acc[1] = pi->acc_buf[s].y; o.acc[2] = pi->acc_buf[s].z; o.gyr[0] = pi->gyr_buf[s].x; o.gyr[1] = pi->gyr_buf[s].y; o.gyr[2] = pi->gyr_buf[s].z; }
+      double* f6 = &first[(j - 1) * 6]; f6[0] = pi->linearized_acc.x; f6[1] = pi->linearized_acc.y; f6[2] = pi->linearized_acc.z; f6[3] = pi->linearized_gyr.x; f6[4] = pi->linearized_gyr.y; f6[5] = pi->linearized_gyr.z;
+      double* b6 = &bias[(j - 1) * 6]; b6[0] = pi->linearized_ba.x; b6[1] = pi->linearized_ba.y; b6[2] = pi->linearized_ba.z; b6[3] = pi->linearized_bg.x; b6[4] = pi->linearized_bg.y; b6[5] = pi->linearized_bg.z;
+    }
+    const double noise[4] = {P.ACC_N, P.GYR_N, P.ACC_W, P.GYR_W};
+    rc = gf2_imu_preintegrate(gf2, 0, 1, smp.data(), ns.data(), first.data(), bias.data(), noise);
+  }
+  if (rc == GF2_OK) {
+    const MarginalizationPrior& mp = last_marginalization_info;
+    int32_t rows = (mp.valid ? mp.n : 0), nb = (int32_t)mp.blocks.size();
+    std::vector<double> J0((size_t)GF2_MAX_PRIOR_DIM * GF2_MAX_PRIOR_DIM, 0.0), r0(GF2_MAX_PRIOR_DIM, 0.0);
+    std::vector<gf2_prior_block> blocks(2 * F + 8); memset(blocks.data(), 0, sizeof(gf2_prior_block) * blocks.size());
+    for (int r = 0; r < rows; r++) { r0[r] = mp.linearized_residuals[r]; for (int c = 0; c < rows; c++) J0[(size_t)r * GF2_MAX_PRIOR_DIM + c] = mp.linearized_jacobians[(size_t)r * rows + c]; }
+    for (int b = 0; b < nb && b < (int)blocks.size(); b++) blocks[b] = mp.blocks[b];
+    rc = gf2_set_prior(gf2, 0, 1, &rows, J0.data(), r0.data(), &nb, blocks.data());
+  }
+  if (rc == GF2_OK) {
+    gf2_solve_opts o; memset(&o, 0, sizeof(o));
+    o.max_iterations = P.NUM_ITERATIONS; o.huber_delta = 1.0; o.sqrt_info_px = FOCAL_LENGTH / 1.5; o.g_norm = P.G_NORM; o.lidar_sqrt_info = 1.0;
+    // blocks held constant exactly when the reference calls SetParameterBlockConstant (estimator.cpp:3051-3060, 3158-3161)
+    const double v0 = std::sqrt(Vs[0].x * Vs[0].x + Vs[0].y * Vs[0].y + Vs[0].z * Vs[0].z);
+    if ((P.ESTIMATE_EXTRINSIC && frame_count == WINDOW_SIZE && v0 > 0.2) || openExEstimation) openExEstimation = true; else o.const_mask |= GF2_CONST_EX_POSE;
+    if (!P.ESTIMATE_TD || v0 < 0.2) o.const_mask |= GF2_CONST_TD;
+    o.const_mask |= GF2_CONST_EX_WHEEL | GF2_CONST_WHEEL_INTRINSIC | GF2_CONST_TD_WHEEL;
+    o.max_time_s = 0;  // SOLVER_TIME is a wall-clock cap: machine dependent, not reproduced
+    rc = gf2_solve(gf2, 0, 1, &o, &last_summary);
+  }
+  if (rc == GF2_OK) rc = gf2_get_states(gf2, 0, 1, &para_Pose[0][0], &para_SpeedBias[0][0], para_Ex_Pose[0], para_Td[0], nullptr, nullptr, nullptr);
+  if (rc == GF2_OK) { rc = gf2_get_landmarks(gf2, 0, 1, invdep.data()); for (int i = 0; i < n_lm; i++) para_Feature[i][0] = invdep[i]; }
+  if (rc != GF2_OK) { last_error = gf2_last_error(); return; }  // the reference logs and carries on (no exceptions)
+  double2vector();
+}
+
+// ------------------------------------------------------------------------------------------------ FeatureTracker
+FeatureTracker::FeatureTracker() {}
+FeatureTracker::~FeatureTracker() { if (trk) gf2_tracker_destroy(trk); }
+void FeatureTracker::readIntrinsicParameter(const Parameters& p) {
+  row = p.ROW; col = p.COL; MAX_CNT = p.MAX_CNT; MIN_DIST = p.MIN_DIST; FLOW_BACK = p.FLOW_BACK;
+  fx = p.fx; fy = p.fy; cx = p.cx; cy = p.cy; k1 = p.k1; k2 = p.k2; p1 = p.p1; p2 = p.p2;
+}
+static inline int cvRound(double v) { return (int)std::nearbyint(v); }
+bool FeatureTracker::inBorder(const Point2f& pt) const {
+  const int BORDER_SIZE = 1;
+  const int img_x = cvRound(pt.x), img_y = cvRound(pt.y);
+  return BORDER_SIZE <= img_x && img_x < col - BORDER_SIZE && BORDER_SIZE <= img_y && img_y < row - BORDER_SIZE;
+}
+// cv::circle(mask, center, radius, 0, -1) with LINE_8 / shift 0: OpenCV's Bresenham Circle() in fill mode
+static void fillCircle(std::vector<uint8_t>& img, int rows, int cols, int cxi, int cyi, int radius) {
+  int err = 0, dx = radius, dy = 0, plus = 1, minus = (radius << 1) - 1;
+  auto hline = [&](int y, int x0, int x1) { if (y < 0 || y >= rows) return; x0 = std::max(x0, 0); x1 = std::min(x1, cols - 1); for (int x = x0; x <= x1; x++) img[(size_t)y * cols + x] = 0; };
+  while (dx >= dy) {
+    hline(cyi - dy, cxi - dx, cxi + dx); hline(cyi + dy, cxi - dx, cxi + dx);
+    hline(cyi - dx, cxi - dy, cxi + dy); hline(cyi + dx, cxi - dy, cxi + dy);
+    dy++; err += plus; plus += 2;
+    const int mask = (err <= 0) - 1;
+    err -= minus & mask; dx += mask; minus -= mask & 2;
+  }
+}
+void FeatureTracker::setMask() {
+  mask.assign((size_t)row * col, 255);
+  std::vector<std::pair<int, std::pair<Point2f, int>>> cnt_pts_id;
+  for (unsigned int i = 0; i < cur_pts.size(); i++) cnt_pts_id.push_back(std::make_pair(track_cnt[i], std::make_pair(cur_pts[i], ids[i])));
+  std::sort(cnt_pts_id.begin(), cnt_pts_id.end(), [](const std::pair<int, std::pair<Point2f, int>>& a, const std::pair<int, std::pair<Point2f, int>>& b) { return a.first > b.first; });
+  cur_pts.clear(); ids.clear(); track_cnt.clear();
+  for (auto& it : cnt_pts_id) {
+    const int px = cvRound(it.second.first.x), py = cvRound(it.second.first.y);  // mask.at<uchar>(Point2f) -> Point via saturate_cast
+    if (px >= 0 && px < col && py >= 0 && py < row && mask[(size_t)py * col + px] == 255) {
+      cur_pts.push_back(it.second.first); ids.push_back(it.second.second); track_cnt.push_back(it.first);
+      fillCircle(mask, row, col, px, py, MIN_DIST);
+    }
+  }
+}
+void FeatureTracker::addPoints() {
+  for (auto& p : n_pts) { cur_pts.push_back(p); ids.push_back(n_id++); track_cnt.push_back(1); }
+}
+std::vector<Point2f> FeatureTracker::undistortedPts(const std::vector<Point2f>& pts) const {
+  std::vector<Point2f> un_pts;
+  const bool noDistortion = (k1 == 0.0 && k2 == 0.0 && p1 == 0.0 && p2 == 0.0);
+  auto distortion = [&](double x, double y, double& dxo, double& dyo) {  // PinholeCamera::distortion
+    const double mx2 = x * x, my2 = y * y, mxy = x * y, rho2 = mx2 + my2, rad = k1 * rho2 + k2 * rho2 * rho2;
+    dxo = x * rad + 2.0 * p1 * mxy + p2 * (rho2 + 2.0 * mx2); dyo = y * rad + 2.0 * p2 * mxy + p1 * (rho2 + 2.0 * my2);
+  };
+  for (auto& p : pts) {  // PinholeCamera::liftProjective (PinholeCamera.cc:450-510), recursive distortion model, n = 8
+    const double mx_d = (1.0 / fx) * p.x + (-cx / fx), my_d = (1.0 / fy) * p.y + (-cy / fy);
+    double mx_u = mx_d, my_u = my_d;
+    if (!noDistortion) {
+      double dx, dy; distortion(mx_d, my_d, dx, dy); mx_u = mx_d - dx; my_u = my_d - dy;
+      for (int i = 1; i < 8; ++i) { distortion(mx_u, my_u, dx, dy); mx_u = mx_d - dx; my_u = my_d - dy; }
+    }
+    un_pts.push_back({(float)(mx_u / 1.0), (float)(my_u / 1.0)});
+  }
+  return un_pts;
+}
+std::vector<Point2f> FeatureTracker::ptsVelocity(const std::vector<int>& ids_, const std::vector<Point2f>& pts, std::map<int, Point2f>& cur_id_pts, std::map<int, Point2f>& prev_id_pts) {
+  std::vector<Point2f> v;
+  cur_id_pts.clear();
+  for (unsigned int i = 0; i < ids_.size(); i++) cur_id_pts.insert(std::make_pair(ids_[i], pts[i]));
+  if (!prev_id_pts.empty()) {
+    const double dt = cur_time - prev_time;
+    for (unsigned int i = 0; i < pts.size(); i++) {
+      auto it = prev_id_pts.find(ids_[i]);
+      if (it != prev_id_pts.end()) v.push_back({(float)((pts[i].x - it->second.x) / dt), (float)((pts[i].y - it->second.y) / dt)});
+      else v.push_back({0, 0});
+    }
+  } else for (unsigned int i = 0; i < cur_pts.size(); i++) v.push_back({0, 0});
+  return v;
+}
+
+std::map<int, std::vector<std::pair<int, std::vector<double>>>> FeatureTracker::trackImage(double _cur_time, const uint8_t* _img, const uint16_t* depth) {
+  std::map<int, std::vector<std::pair<int, std::vector<double>>>> featureFrame;
+  last_error.clear();
+  cur_time = _cur_time;
+  cur_img.assign(_img, _img + (size_t)row * col);
+  cur_pts.clear();
+  if (!trk) {
+    gf2_tracker_cfg c; memset(&c, 0, sizeof(c));
+    c.device = 0; c.width = col; c.height = row; c.max_pts = std::max(MAX_CNT, 8); c.win = 21; c.max_level = 3; c.max_iters = 30; c.max_streams = 1; c.eps = 0.01; c.min_eig = 1e-4;
+    if (gf2_tracker_create(&c, &trk) != GF2_OK) { last_error = gf2_last_error(); trk = nullptr; return featureFrame; }
+  }
+  if (prev_pts.size() > 0) {
+    int32_t n = (int32_t)prev_pts.size();
+    cur_pts.resize(n);
+    std::vector<uint8_t> status(std::max(MAX_CNT, 8), 0);
+    std::vector<float> pin((size_t)std::max(MAX_CNT, 8) * 2, 0.f), pout((size_t)std::max(MAX_CNT, 8) * 2, 0.f);
+    for (int i = 0; i < n; i++) { pin[2 * i] = prev_pts[i].x; pin[2 * i + 1] = prev_pts[i].y; }
+    // forward LK (maxLevel 3) + reverse check (maxLevel 1, initial flow, <= 0.5 px): feature_tracker.cpp:135-153. The pyramid of the
+    // previous image is still on the device (prev_img = cur_img, :307), so only the new image is uploaded.
+    int rc = FLOW_BACK ? gf2_tracker_track_fb(trk, 1, nullptr, cur_img.data(), (size_t)col, &n, pin.data(), pout.data(), status.data(), 3)
+                       : gf2_tracker_track(trk, 1, nullptr, cur_img.data(), (size_t)col, &n, pin.data(), pout.data(), status.data(), nullptr, 0, 3);
+    if (rc != GF2_OK) { last_error = gf2_last_error(); return featureFrame; }
+    for (int i = 0; i < n; i++) cur_pts[i] = {pout[2 * i], pout[2 * i + 1]};
+    for (int i = 0; i < n; i++) {
+      if (status[i] && !inBorder(cur_pts[i])) status[i] = 0;
+      const int p_u = (int)cur_pts[i].x, p_v = (int)cur_pts[i].y;  // truncation, not rounding (:160-163)
+      if (status[i] && p_u >= 0 && p_u < col && p_v >= 0 && p_v < row && cur_img[(size_t)p_v * col + p_u] > 250) status[i] = 0;
+    }
+    auto reduce_pts = [&](std::vector<Point2f>& v) { int j = 0; for (int i = 0; i < (int)v.size(); i++) if (status[i]) v[j++] = v[i]; v.resize(j); };
+    auto reduce_int = [&](std::vector<int>& v) { int j = 0; for (int i = 0; i < (int)v.size(); i++) if (status[i]) v[j++] = v[i]; v.resize(j); };
+    reduce_pts(prev_pts); reduce_pts(cur_pts); reduce_int(ids); reduce_int(track_cnt);
+  } else {
+    // first image: upload it so that its pyramid is the cached "prev" of the next call
+    int32_t n0 = 0; float dummy[2] = {0, 0}; uint8_t st = 0;
+    gf2_tracker_track(trk, 1, cur_img.data(), cur_img.data(), (size_t)col, &n0, dummy, dummy, &st, nullptr, 0, 3);
+  }
+  for (auto& n : track_cnt) n++;
+  setMask();
+  const int n_max_cnt = MAX_CNT - (int)cur_pts.size();
+  n_pts.clear();
+  if (n_max_cnt > 0 && detector) {
+    std::vector<float> xy((size_t)n_max_cnt * 2);
+    const int got = detector(cur_img.data(), row, col, mask.data(), n_max_cnt, MIN_DIST, xy.data(), detector_user);
+    for (int i = 0; i < got && i < n_max_cnt; i++) n_pts.push_back({xy[2 * i], xy[2 * i + 1]});
+  }
+  addPoints();
+  cur_un_pts = undistortedPts(cur_pts);
+  pts_velocity = ptsVelocity(ids, cur_un_pts, cur_un_pts_map, prev_un_pts_map);
+  prev_pts = cur_pts; prev_un_pts = cur_un_pts; prev_un_pts_map = cur_un_pts_map; prev_time = cur_time; have_prev = true;
+  for (size_t i = 0; i < ids.size(); i++) {
+    double depth_value = -2.4;  // "depthmono" of the mono branch (:331)
+    if (depth) depth_value = (double)(int)depth[(size_t)std::lround(cur_pts[i].y) * col + std::lround(cur_pts[i].x)] / 1000;  // :360-361
+    featureFrame[ids[i]].emplace_back(0, std::vector<double>{cur_un_pts[i].x, cur_un_pts[i].y, 1.0, cur_pts[i].x, cur_pts[i].y, pts_velocity[i].x, pts_velocity[i].y, depth_value});
+  }
+  return featureFrame;
+}
+
+}  // namespace gf2host
+
+// ------------------------------------------------------------------------------------------------ flat C test API (ctypes)
+using namespace gf2host;
+extern "C" {
+void* gf2h_estimator_create() { return new Estimator(); }
+void gf2h_estimator_destroy(void* e) { delete (Estimator*)e; }
+int gf2h_read_parameters(void* e, const char* path) { Parameters p; if (!readParameters(path, p)) return -1; ((Estimator*)e)->setParameter(p); return 0; }
+void gf2h_get_parameters(void* e, double* out /*24*/) {
+  const Parameters& p = ((Estimator*)e)->P;
+  const double v[24] = {p.ACC_N, p.ACC_W, p.GYR_N, p.GYR_W, p.G_NORM, p.SOLVER_TIME, (double)p.NUM_ITERATIONS, (double)p.MAX_CNT, (double)p.MIN_DIST, (double)p.ROW, (double)p.COL,
+                        p.fx, p.fy, p.cx, p.cy, p.TIC.x, p.TIC.y, p.TIC.z, p.RIC.m[0], p.RIC.m[4], p.RIC.m[8], p.MIN_PARALLAX, (double)p.ESTIMATE_EXTRINSIC, (double)p.FLOW_BACK};
+  memcpy(out, v, sizeof(v));
+}
+// states as rows of [P(3) R(9 row-major) V(3) Ba(3) Bg(3)] = 21 doubles per frame
+void gf2h_set_frame_states(void* e, const double* s) {
+  Estimator* E = (Estimator*)e;
+  for (int i = 0; i <= WINDOW_SIZE; i++) { const double* r = s + 21 * i; E->Ps[i] = {r[0], r[1], r[2]}; memcpy(E->Rs[i].m, r + 3, 72); E->Vs[i] = {r[12], r[13], r[14]}; E->Bas[i] = {r[15], r[16], r[17]}; E->Bgs[i] = {r[18], r[19], r[20]}; }
+}
+void gf2h_get_frame_states(void* e, double* s) {
+  Estimator* E = (Estimator*)e;
+  for (int i = 0; i <= WINDOW_SIZE; i++) { double* r = s + 21 * i; r[0] = E->Ps[i].x; r[1] = E->Ps[i].y; r[2] = E->Ps[i].z; memcpy(r + 3, E->Rs[i].m, 72); r[12] = E->Vs[i].x; r[13] = E->Vs[i].y; r[14] = E->Vs[i].z;
+    r[15] = E->Bas[i].x; r[16] = E->Bas[i].y; r[17] = E->Bas[i].z; r[18] = E->Bgs[i].x; r[19] = E->Bgs[i].y; r[20] = E->Bgs[i].z; }
+}
+void gf2h_set_extrinsic(void* e, const double* tic3, const double* ric9, double td, double g_norm, const double noise[4]) {
+  Estimator* E = (Estimator*)e; E->tic[0] = {tic3[0], tic3[1], tic3[2]}; memcpy(E->ric[0].m, ric9, 72); E->td = td; E->P.G_NORM = g_norm;
+  E->P.ACC_N = noise[0]; E->P.GYR_N = noise[1]; E->P.ACC_W = noise[2]; E->P.GYR_W = noise[3];
+}
+// one image worth of features: ids[n], 8-vectors[n][8]; appended in std::map (ascending id) order like processImage does
+void gf2h_add_image(void* e, int frame_count, int n, const int* ids, const double* pts8, double td) {
+  std::map<int, std::vector<std::pair<int, std::vector<double>>>> image;
+  for (int i = 0; i < n; i++) image[ids[i]].emplace_back(0, std::vector<double>(pts8 + 8 * i, pts8 + 8 * i + 8));
+  ((Estimator*)e)->f_manager.addFeatures(frame_count, image, td);
+}
+void gf2h_set_depths(void* e, int n, const int* ids, const double* depth, const int* estimate_flag) {
+  Estimator* E = (Estimator*)e;
+  for (int i = 0; i < n; i++) for (auto& f : E->f_manager.feature) if (f.feature_id == ids[i]) { f.estimated_depth = depth[i]; if (estimate_flag) f.estimate_flag = estimate_flag[i]; }
+}
+int gf2h_feature_table(void* e, int max_n, int* ids, int* start, int* len, double* depth, int* solve_flag) {
+  Estimator* E = (Estimator*)e; int k = 0;
+  for (auto& f : E->f_manager.feature) { if (k >= max_n) break; ids[k] = f.feature_id; start[k] = f.start_frame; len[k] = (int)f.feature_per_frame.size(); depth[k] = f.estimated_depth; solve_flag[k] = f.solve_flag; k++; }
+  return k;
+}
+int gf2h_depth_vector(void* e, double* out) { auto v = ((Estimator*)e)->f_manager.getDepthVector(); for (size_t i = 0; i < v.size(); i++) out[i] = v[i]; return (int)v.size(); }
+void gf2h_new_interval(void* e, int j, const double* acc0, const double* gyr0, const double* ba, const double* bg) {
+  Estimator* E = (Estimator*)e; delete E->pre_integrations[j];
+  E->pre_integrations[j] = new IntegrationBase({acc0[0], acc0[1], acc0[2]}, {gyr0[0], gyr0[1], gyr0[2]}, {ba[0], ba[1], ba[2]}, {bg[0], bg[1], bg[2]});
+}
+void gf2h_push_imu(void* e, int j, double dt, const double* acc, const double* gyr) { ((Estimator*)e)->pre_integrations[j]->push_back(dt, {acc[0], acc[1], acc[2]}, {gyr[0], gyr[1], gyr[2]}); }
+void gf2h_set_prior(void* e, int n, const double* J0, const double* r0, int nblocks, const gf2_prior_block* blocks) {
+  MarginalizationPrior& mp = ((Estimator*)e)->last_marginalization_info;
+  mp.valid = n > 0; mp.n = n; mp.linearized_jacobians.assign(J0, J0 + (size_t)n * n); mp.linearized_residuals.assign(r0, r0 + n); mp.blocks.assign(blocks, blocks + nblocks);
+}
+void gf2h_vector2double(void* e, double* pose /*11x7*/, double* sb /*11x9*/, double* ex /*7*/) {
+  Estimator* E = (Estimator*)e; E->vector2double(); memcpy(pose, E->para_Pose, sizeof(E->para_Pose)); memcpy(sb, E->para_SpeedBias, sizeof(E->para_SpeedBias)); memcpy(ex, E->para_Ex_Pose[0], 56);
+}
+void gf2h_double2vector(void* e, const double* pose, const double* sb, int n_feat, const double* feat) {
+  Estimator* E = (Estimator*)e; memcpy(E->para_Pose, pose, sizeof(E->para_Pose)); memcpy(E->para_SpeedBias, sb, sizeof(E->para_SpeedBias));
+  for (int i = 0; i < n_feat; i++) E->para_Feature[i][0] = feat[i];
+  E->double2vector();
+}
+int gf2h_optimization(void* e, gf2_solve_summary* s) { Estimator* E = (Estimator*)e; E->optimization(); if (s) *s = E->last_summary; return E->lastError()[0] ? -1 : 0; }
+const char* gf2h_last_error(void* e) { return ((Estimator*)e)->lastError(); }
+
+void* gf2h_tracker_create(int rows, int cols, int max_cnt, int min_dist, const double* intr8) {
+  FeatureTracker* t = new FeatureTracker(); Parameters p; p.ROW = rows; p.COL = cols; p.MAX_CNT = max_cnt; p.MIN_DIST = min_dist; p.FLOW_BACK = 1;
+  p.fx = intr8[0]; p.fy = intr8[1]; p.cx = intr8[2]; p.cy = intr8[3]; p.k1 = intr8[4]; p.k2 = intr8[5]; p.p1 = intr8[6]; p.p2 = intr8[7];
+  t->readIntrinsicParameter(p); return t;
+}
+void gf2h_tracker_destroy(void* t) { delete (FeatureTracker*)t; }
+void gf2h_tracker_set_detector(void* t, FeatureTracker::Detector d, void* user) { ((FeatureTracker*)t)->setDetector(d, user); }
+// returns n; out rows = [id, x, y, 1, u, v, vx, vy, depth, track_cnt]
+int gf2h_tracker_track(void* t, double time, const uint8_t* img, const uint16_t* depth, int max_n, double* out10) {
+  FeatureTracker* T = (FeatureTracker*)t;
+  auto ff = T->trackImage(time, img, depth);
+  if (T->lastError()[0]) return -1;
+  int k = 0;
+  for (size_t i = 0; i < T->ids.size() && k < max_n; i++, k++) {
+    const auto& v = ff[T->ids[i]][0].second; double* o = out10 + 10 * k;
+    o[0] = T->ids[i]; for (int c = 0; c < 8; c++) o[1 + c] = v[c]; o[9] = T->track_cnt[i];
+  }
+  return k;
+}
+int gf2h_tracker_mask(void* t, uint8_t* out) { FeatureTracker* T = (FeatureTracker*)t; memcpy(out, T->mask.data(), T->mask.size()); return (int)T->mask.size(); }
+const char* gf2h_tracker_last_error(void* t) { return ((FeatureTracker*)t)->lastError(); }
+}

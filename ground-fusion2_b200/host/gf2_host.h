@@ -1,0 +1,180 @@
+// gf2_host.h — host-side C++ mirror of the reference classes on the hot path, on top of the C ABI (include/gf2_abi.h).
+//
+// Same class / member / method names as the reference so that the calling code (rosNodeTest.cpp, processImage) reads the
+// same; Eigen / OpenCV / Ceres / ROS do not exist in this build environment, so vectors are plain structs and images are raw
+// uint8 pointers. What stays on the host is exactly what the reference keeps there: buffering of raw IMU samples per
+// interval (IntegrationBase::push_back, VE/factor/integration_base.h:39-46), the landmark table and its index order
+// (FeatureManager, VE/estimator/feature_manager.cpp:43-55,249-302), state packing (Estimator::vector2double / double2vector,
+// VE/estimator/estimator.cpp:2337-2414 / 2501-2630) and the tracker glue (FeatureTracker::inBorder / setMask / addPoints /
+// undistortedPts / ptsVelocity, VE/featureTracker/feature_tracker.cpp:14-93,797-847). All arithmetic of the hot path runs
+// in the CUDA kernels behind gf2_solve / gf2_imu_preintegrate / gf2_tracker_track_fb; nothing here is a CPU fallback.
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <list>
+#include <map>
+#include <string>
+#include <utility>
+#include <vector>
+#include "../../include/gf2_abi.h"
+
+namespace gf2host {
+
+const double FOCAL_LENGTH = 600.0;  // VE/estimator/parameters.h:23-25
+const int WINDOW_SIZE = 10;
+const int NUM_OF_F = 1000;
+
+struct Vector3d { double x = 0, y = 0, z = 0; };
+struct Matrix3d { double m[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}; };  // row-major
+struct Quaterniond { double w = 1, x = 0, y = 0, z = 0; };
+Quaterniond quatFromMatrix(const Matrix3d& R);   // Eigen Quaterniond(Matrix3d)
+Matrix3d toRotationMatrix(const Quaterniond& q);  // Eigen toRotationMatrix (after normalisation where the reference normalises)
+Vector3d R2ypr(const Matrix3d& R);               // Utility::R2ypr, VE/utility/utility.h:78-93 (degrees)
+Matrix3d ypr2R(const Vector3d& ypr);             // Utility::ypr2R, :95-121
+Matrix3d mul(const Matrix3d& a, const Matrix3d& b);
+Vector3d mul(const Matrix3d& a, const Vector3d& v);
+Matrix3d transpose(const Matrix3d& a);
+
+// Parameters the path reads (subset of readParameters, VE/estimator/parameters.cpp:142-560)
+struct Parameters {
+  double ACC_N = 0.1, ACC_W = 0.001, GYR_N = 0.01, GYR_W = 0.0001, G_NORM = 9.81007;
+  double SOLVER_TIME = 0.04; int NUM_ITERATIONS = 8;
+  int ESTIMATE_EXTRINSIC = 0, ESTIMATE_TD = 0, USE_IMU = 1, USE_WHEEL = 0, MAX_CNT = 150, MIN_DIST = 30, FLOW_BACK = 1, ROW = 480, COL = 640;
+  double TD = 0.0, F_THRESHOLD = 1.0, MIN_PARALLAX = 10.0 / FOCAL_LENGTH;
+  Matrix3d RIC; Vector3d TIC;
+  double fx = 0, fy = 0, cx = 0, cy = 0, k1 = 0, k2 = 0, p1 = 0, p2 = 0;  // camodocal PINHOLE (GF/config/realsense/color.yaml)
+};
+// Reads the OpenCV-FileStorage YAML dialect of GF/config/realsense/m3dgr.yaml (+ the camera file named by cam0_calib);
+// absent keys read as 0 like cv::FileNode. Returns false if the file cannot be opened.
+bool readParameters(const std::string& config_file, Parameters& P);
+
+// Raw-sample buffer of one preintegration interval; the integration itself is gf2_imu_preintegrate on the device.
+class IntegrationBase {
+ public:
+  IntegrationBase(const Vector3d& _acc_0, const Vector3d& _gyr_0, const Vector3d& _linearized_ba, const Vector3d& _linearized_bg)
+      : acc_0(_acc_0), gyr_0(_gyr_0), linearized_acc(_acc_0), linearized_gyr(_gyr_0), linearized_ba(_linearized_ba), linearized_bg(_linearized_bg) {}
+  void push_back(double dt, const Vector3d& acc, const Vector3d& gyr) { dt_buf.push_back(dt); acc_buf.push_back(acc); gyr_buf.push_back(gyr); sum_dt += dt; acc_0 = acc; gyr_0 = gyr; }
+  Vector3d acc_0, gyr_0;
+  const Vector3d linearized_acc, linearized_gyr;
+  Vector3d linearized_ba, linearized_bg;
+  double sum_dt = 0.0;
+  std::vector<double> dt_buf;
+  std::vector<Vector3d> acc_buf, gyr_buf;
+};
+
+class FeaturePerFrame {  // VE/estimator/feature_manager.h:28-62
+ public:
+  FeaturePerFrame(const double _point[8], double td) : cur_td(td) {
+    point = {_point[0], _point[1], _point[2]}; uv[0] = _point[3]; uv[1] = _point[4]; velocity[0] = _point[5]; velocity[1] = _point[6]; depth = _point[7];
+  }
+  double cur_td;
+  Vector3d point;
+  double uv[2], velocity[2], depth;
+};
+
+class FeaturePerId {  // VE/estimator/feature_manager.h:64-90
+ public:
+  FeaturePerId(int _feature_id, int _start_frame) : feature_id(_feature_id), start_frame(_start_frame) {}
+  const int feature_id;
+  int start_frame;
+  std::vector<FeaturePerFrame> feature_per_frame;
+  int used_num = 0;
+  double estimated_depth = -1.0;
+  int estimate_flag = 0;  // 1: depth verified by the depth camera -> held constant (estimator.cpp:3352)
+  int solve_flag = 0;     // 0 not solved, 1 ok, 2 failed
+  int endFrame() const { return start_frame + (int)feature_per_frame.size() - 1; }
+};
+
+class FeatureManager {
+ public:
+  std::list<FeaturePerId> feature;
+  int getFeatureCount();                         // feature_manager.cpp:43-55
+  std::vector<double> getDepthVector();          // :286-302 (inverse depths, list order, used_num >= 4)
+  void setDepth(const std::vector<double>& x);   // :249-267
+  void removeFailures();                         // :269-278
+  void clearDepth();                             // :280-284
+  // append the observations of one image in the reference's container: map<id, vector<pair<cam, 8-vector>>> (cam 0 only)
+  void addFeatures(int frame_count, const std::map<int, std::vector<std::pair<int, std::vector<double>>>>& image, double td);  // :67-88 (list insertion part)
+};
+
+// The kept part of a MarginalizationInfo (VE/factor/marginalization_factor.h:74-79)
+struct MarginalizationPrior {
+  bool valid = false;
+  int n = 0;
+  std::vector<double> linearized_jacobians;  // n x n row-major
+  std::vector<double> linearized_residuals;
+  std::vector<gf2_prior_block> blocks;       // keep_block_size / idx / data with the block each one maps to
+};
+
+class Estimator {
+ public:
+  Estimator();
+  ~Estimator();
+  void setParameter(const Parameters& p);
+  void clearState();
+  void vector2double();   // estimator.cpp:2337-2414
+  void double2vector();   // estimator.cpp:2501-2630 (yaw / position re-anchoring to frame 0, setDepth)
+  void optimization();    // estimator.cpp:2951-3392: the ceres::Problem build + ceres::Solve, through gf2_solve
+  const char* lastError() const { return last_error.c_str(); }
+
+  Parameters P;
+  Vector3d Ps[WINDOW_SIZE + 1], Vs[WINDOW_SIZE + 1], Bas[WINDOW_SIZE + 1], Bgs[WINDOW_SIZE + 1];
+  Matrix3d Rs[WINDOW_SIZE + 1];
+  Vector3d tic[2]; Matrix3d ric[2];
+  double td = 0.0;
+  int frame_count = WINDOW_SIZE;
+  bool openExEstimation = false, failure_occur = false;
+  Matrix3d last_R0; Vector3d last_P0;
+  FeatureManager f_manager;
+  IntegrationBase* pre_integrations[WINDOW_SIZE + 1] = {nullptr};
+  MarginalizationPrior last_marginalization_info;
+
+  double para_Pose[WINDOW_SIZE + 1][7];
+  double para_SpeedBias[WINDOW_SIZE + 1][9];
+  double para_Feature[NUM_OF_F][1];
+  double para_Ex_Pose[2][7];
+  double para_Td[1][1];
+  gf2_solve_summary last_summary;
+
+ private:
+  gf2_solver* gf2 = nullptr;
+  std::string last_error;
+};
+
+struct Point2f { float x = 0, y = 0; };
+
+class FeatureTracker {
+ public:
+  FeatureTracker();
+  ~FeatureTracker();
+  void readIntrinsicParameter(const Parameters& p);
+  // detector hook: goodFeaturesToTrack(img, maxCorners, 0.01, MIN_DIST, mask) stays outside this build;
+  // the caller supplies it (tests: cv2.goodFeaturesToTrack through ctypes)
+  typedef int (*Detector)(const uint8_t* img, int rows, int cols, const uint8_t* mask, int max_corners, int min_dist, float* out_xy, void* user);
+  void setDetector(Detector d, void* user) { detector = d; detector_user = user; }
+  // trackImage for the mono (+depth lookup) configuration with hasPrediction == false (feature_tracker.cpp:103-372)
+  std::map<int, std::vector<std::pair<int, std::vector<double>>>> trackImage(double _cur_time, const uint8_t* _img, const uint16_t* depth = nullptr);
+  bool inBorder(const Point2f& pt) const;        // :14-20
+  void setMask();                                // :56-83
+  void addPoints();                              // :85-93
+  std::vector<Point2f> undistortedPts(const std::vector<Point2f>& pts) const;  // :797-808 + PinholeCamera::liftProjective
+  std::vector<Point2f> ptsVelocity(const std::vector<int>& ids, const std::vector<Point2f>& pts, std::map<int, Point2f>& cur_id_pts, std::map<int, Point2f>& prev_id_pts);  // :810-847
+  const char* lastError() const { return last_error.c_str(); }
+
+  int row = 480, col = 640, MAX_CNT = 150, MIN_DIST = 30, FLOW_BACK = 1;
+  double fx = 0, fy = 0, cx = 0, cy = 0, k1 = 0, k2 = 0, p1 = 0, p2 = 0;
+  std::vector<uint8_t> mask, cur_img;
+  std::vector<Point2f> n_pts, prev_pts, cur_pts, cur_un_pts, prev_un_pts, pts_velocity;
+  std::vector<int> ids, track_cnt;
+  std::map<int, Point2f> cur_un_pts_map, prev_un_pts_map;
+  double cur_time = 0, prev_time = 0;
+  int n_id = 0;
+  bool have_prev = false;
+
+ private:
+  gf2_tracker* trk = nullptr;
+  Detector detector = nullptr; void* detector_user = nullptr;
+  std::string last_error;
+};
+
+}  // namespace gf2host
