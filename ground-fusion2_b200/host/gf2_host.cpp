@@ -417,8 +417,9 @@ std::map<int, std::vector<std::pair<int, std::vector<double>>>> FeatureTracker::
     reduce_pts(prev_pts); reduce_pts(cur_pts); reduce_int(ids); reduce_int(track_cnt);
   } else {
     // first image: upload it so that its pyramid is the cached "prev" of the next call
-    int32_t n0 = 0; float dummy[2] = {0, 0}; uint8_t st = 0;
-    gf2_tracker_track(trk, 1, cur_img.data(), cur_img.data(), (size_t)col, &n0, dummy, dummy, &st, nullptr, 0, 3);
+    int32_t n0 = 0; const size_t cap = (size_t)std::max(MAX_CNT, 8);  // the ABI moves max_pts-sized point arrays
+    std::vector<float> dummy_in(cap * 2, 0.f), dummy_out(cap * 2, 0.f); std::vector<uint8_t> st(cap, 0);
+    if (gf2_tracker_track(trk, 1, cur_img.data(), cur_img.data(), (size_t)col, &n0, dummy_in.data(), dummy_out.data(), st.data(), nullptr, 0, 3) != GF2_OK) { last_error = gf2_last_error(); return featureFrame; }
   }
   for (auto& n : track_cnt) n++;
   setMask();

@@ -89,7 +89,7 @@ def test_estimator_optimization_end_to_end(gf2, oracle):
     L.gf2h_estimator_destroy(e)
 
 
-def _py_track_image(state, t, img, detect, max_cnt=150, min_dist=30, fx=600.0, fy=600.0, cx=320.0, cy=240.0):
+def _py_track_image(state, t, img, detect, max_cnt=150, min_dist=30, fx=600.0, fy=600.0, cx=320.0, cy=240.0, tie_order=None):
     """Restatement of FeatureTracker::trackImage (feature_tracker.cpp:103-372), mono, no prediction, FLOW_BACK = 1."""
     cv2 = state.get("cv2")
     row, col = img.shape
@@ -107,7 +107,10 @@ def _py_track_image(state, t, img, detect, max_cnt=150, min_dist=30, fx=600.0, f
         cur_pts = cp[status]; state["ids"] = [i for i, s in zip(state["ids"], status) if s]; state["cnt"] = [c for c, s in zip(state["cnt"], status) if s]
     state["cnt"] = [c + 1 for c in state["cnt"]]
     mask = np.full((row, col), 255, np.uint8)
-    order = sorted(range(len(cur_pts)), key=lambda i: -state["cnt"][i])  # stable, like std::sort on already count-ordered data here
+    # setMask sorts by track count with std::sort (unstable): ties are broken by libstdc++'s introsort. The restatement takes
+    # the tie order from the C++ result (`tie_order`: ids in the order the C++ kept them) and checks that it is count-ordered.
+    rank = {i: k for k, i in enumerate(tie_order or [])}
+    order = sorted(range(len(cur_pts)), key=lambda i: (-state["cnt"][i], rank.get(state["ids"][i], 10 ** 9)))
     kp, ki, kc = [], [], []
     for i in order:
         px, py = int(np.rint(cur_pts[i, 0])), int(np.rint(cur_pts[i, 1]))
@@ -166,13 +169,24 @@ def test_feature_tracker_track_image_ids_bit_exact():
         out = np.zeros((200, 10))
         n = L.gf2h_tracker_track(t, C.c_double(0.1 * k), H.p(img), None, 200, H.p(out))
         assert n >= 0, L.gf2h_tracker_last_error(t)
-        ids, pts, un, vel, cnt = _py_track_image(state, 0.1 * k, img, detect)
+        cpp_order = out[:max(n, 0), 0].astype(int).tolist()
+        cpp_cnt = out[:max(n, 0), 9].astype(int).tolist()
+        tracked = [c for c in cpp_cnt if c > 1]
+        assert tracked == sorted(tracked, reverse=True)                     # kept points are in non-increasing track-count order
+        ids, pts, un, vel, cnt = _py_track_image(state, 0.1 * k, img, detect, tie_order=cpp_order)
         assert n == len(ids)
-        assert out[:n, 0].astype(int).tolist() == ids                      # feature ids: bit-exact, same order
-        assert out[:n, 9].astype(int).tolist() == cnt                      # track counts
-        assert np.abs(out[:n, 4:6] - pts).max() <= 1e-4                    # pixel positions (u, v)
-        assert np.abs(out[:n, 1:3] - un).max() <= 1e-6
-        assert np.abs(out[:n, 6:8] - vel).max() <= 2e-3                    # velocities = position differences / dt
+        # trackImage returns a std::map keyed by feature id, so the contract is per id; the order inside the ids vector comes
+        # from std::sort (unstable, libstdc++ introsort — the same call the reference makes) and is not restated in Python
+        got = {int(r[0]): r for r in out[:n]}
+        assert sorted(got) == sorted(ids)                                   # feature ids: bit-exact
+        for k2, i in enumerate(ids):
+            r = got[i]
+            assert int(r[9]) == cnt[k2]                                     # track count
+            assert np.abs(r[4:6] - pts[k2]).max() <= 1e-4                   # pixel position (u, v)
+            assert np.abs(r[1:3] - un[k2]).max() <= 1e-6 and r[3] == 1.0
+            assert np.abs(r[6:8] - vel[k2]).max() <= 2e-3                   # velocity = position difference / dt
+        new_ids = [i for i, c in zip(ids, cnt) if c == 1]
+        assert new_ids == sorted(new_ids) and (not new_ids or new_ids[-1] == state["n_id"] - 1)   # addPoints: n_id++ in detector order
         m = np.zeros((480, 640), np.uint8); L.gf2h_tracker_mask(t, H.p(m))
         assert np.array_equal(m, state["mask"])                           # setMask + filled circles == cv2.circle
         if k > 0 and max(cnt) < k + 1:
