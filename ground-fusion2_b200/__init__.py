@@ -72,11 +72,13 @@ class Solver:
     """Batched sliding-window solver: the ceres::Solve call of Estimator::optimization() for `max_windows` windows."""
 
     def __init__(self, max_windows, n_frames=11, max_landmarks=1000, max_obs=7500, max_planes=0, max_imu_samples=0,
-                 use_wheel=False, device=0):
+                 use_wheel=False, device=0, max_prior_rows=0):
         cfg = abi.SolverCfg()
         cfg.device = device; cfg.max_windows = max_windows; cfg.n_frames = n_frames; cfg.max_landmarks = max_landmarks
         cfg.max_obs = max_obs; cfg.max_planes = max_planes; cfg.max_imu_samples = max_imu_samples
         cfg.use_wheel = 1 if use_wheel else 0
+        cfg.max_prior_rows = max_prior_rows
+        self.Pr = max_prior_rows or abi.MAX_PRIOR_DIM
         self.cfg = cfg
         self.h = C.c_void_p()
         _check(lib().gf2_solver_create(C.byref(cfg), C.byref(self.h)))
@@ -137,6 +139,7 @@ class Solver:
 
     def set_prior(self, w, first=0):
         n = w["prior_rows"].shape[0]
+        assert w["prior_J0"].shape[1] == self.Pr, "prior arrays must use the solver's max_prior_rows as stride"
         _check(lib().gf2_set_prior(self.h, first, n, _p(w["prior_rows"]), _p(w["prior_J0"]), _p(w["prior_r0"]),
                                    _p(w["prior_nblocks"]), _p(w["prior_blocks"])))
 

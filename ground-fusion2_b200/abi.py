@@ -32,7 +32,7 @@ class SolverCfg(C.Structure):
     _fields_ = [("device", C.c_int32), ("max_windows", C.c_int32), ("n_frames", C.c_int32),
                 ("max_landmarks", C.c_int32), ("max_obs", C.c_int32), ("max_planes", C.c_int32),
                 ("max_imu_samples", C.c_int32), ("max_wheel_samples", C.c_int32), ("use_wheel", C.c_int32),
-                ("reserved_", C.c_int32 * 7)]
+                ("max_prior_rows", C.c_int32), ("reserved_", C.c_int32 * 6)]
 
 
 class SolveOpts(C.Structure):

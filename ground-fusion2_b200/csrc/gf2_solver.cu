@@ -225,6 +225,8 @@ int gf2_solver_create(const gf2_solver_cfg* cfg, gf2_solver** out) {
   memset(&h->kp, 0, sizeof(KP));
   KP& k = h->kp;
   k.nW = B; k.F = F; k.Lm = Lm; k.Om = Om; k.Pm = Pm; k.D = h->D; k.use_wheel = cfg->use_wheel;
+  k.Pr = cfg->max_prior_rows > 0 ? cfg->max_prior_rows : GF2_MAX_PRIOR_DIM;
+  if (k.Pr > GF2_MAX_PRIOR_DIM) { delete h; return gf2::fail(GF2_ERR_INVALID, "max_prior_rows %d exceeds %d", k.Pr, GF2_MAX_PRIOR_DIM); }
   if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return gf2::fail(GF2_ERR_CUDA, "stream creation failed"); }
   h->stream = h->own_stream;
   int rc = GF2_OK;
@@ -236,14 +238,14 @@ int gf2_solver_create(const gf2_solver_cfg* cfg, gf2_solver** out) {
   A(k.fixed, uint8_t, (size_t)B * Lm); A(k.obs, float4, (size_t)B * Om); A(k.frame_td, double, (size_t)B * F);
   A(h->d_imu, gf2_imu_preint, (size_t)B * (F - 1)); A(k.imu_sqrt, double, (size_t)B * (F - 1) * 225);
   if (cfg->use_wheel) { A(h->d_wheel, gf2_wheel_preint, (size_t)B * (F - 1)); A(k.wheel_sqrt, double, (size_t)B * (F - 1) * 36); }
-  A(k.prior_rows, int32_t, B); A(k.prior_nblocks, int32_t, B); A(k.prior_J0, double, (size_t)B * kP * kP); A(k.prior_r0, double, (size_t)B * kP);
-  A(k.prior_blocks, gf2_prior_block, (size_t)B * (2 * F + 8)); A(k.prior_H, double, (size_t)B * kP * kP); A(k.prior_map, int32_t, (size_t)B * kP);
+  A(k.prior_rows, int32_t, B); A(k.prior_nblocks, int32_t, B); A(k.prior_J0, double, (size_t)B * k.Pr * k.Pr); A(k.prior_r0, double, (size_t)B * k.Pr);
+  A(k.prior_blocks, gf2_prior_block, (size_t)B * (2 * F + 8)); A(k.prior_H, double, (size_t)B * k.Pr * k.Pr); A(k.prior_map, int32_t, (size_t)B * k.Pr);
   if (Pm > 0) { A(k.n_planes, int32_t, B); A(k.planes, gf2_plane, (size_t)B * Pm); }
   A(k.Svis, double, (size_t)B * kNVMax * kNVMax); A(k.gvis, double, (size_t)B * kNVP); A(k.gschur, double, (size_t)B * kNVP); A(k.Udiag, double, (size_t)B * kNVMax);
   A(k.lm_v, double, (size_t)B * Lm); A(k.lm_g, double, (size_t)B * Lm); A(k.lm_s, double, (size_t)B * Lm); A(k.lm_z, double, (size_t)B * Lm);
   A(k.sx, double, (size_t)B * h->D); A(k.zx, double, (size_t)B * h->D); A(k.ux, double, (size_t)B * h->D); A(k.ex_diag, double, (size_t)B * h->D);
   A(k.imu_H, double, (size_t)B * (F - 1) * 675); A(k.imu_g, double, (size_t)B * (F - 1) * 30);
-  A(k.prior_g, double, (size_t)B * kP); A(k.cost_nv, double, B);
+  A(k.prior_g, double, (size_t)B * k.Pr); A(k.cost_nv, double, B);
   A(k.trace, double, (size_t)B * 64 * 6);
   A(k.c_lin, double, (size_t)B * 4); A(k.c_gmax, double, B); A(k.c_sums, double, (size_t)B * 8); A(k.c_cand, double, (size_t)B * 4);
   if (Pm > 0) { A(k.pperm, int32_t, (size_t)B * Pm); A(k.ptask_first, int32_t, (size_t)B * kMaxPlaneTasks); A(k.ptask_cnt, int32_t, (size_t)B * kMaxPlaneTasks); A(k.ptask_frame, int32_t, (size_t)B * kMaxPlaneTasks); A(k.nptasks, int32_t, B); }
@@ -422,13 +424,13 @@ int gf2_set_prior(gf2_solver* h, int first, int n, const int32_t* n_rows, const 
   const KP& k = h->kp;
   if (!n_rows) { h->has_prior = false; return GF2_OK; }
   for (int w = 0; w < n; w++) {
-    if (n_rows[w] < 0 || n_rows[w] > kP) return gf2::fail(GF2_ERR_INVALID, "prior of window %d has %d rows (max %d)", first + w, n_rows[w], kP);
+    if (n_rows[w] < 0 || n_rows[w] > k.Pr) return gf2::fail(GF2_ERR_INVALID, "prior of window %d has %d rows (max %d)", first + w, n_rows[w], k.Pr);
     if (n_rows[w] > 0 && (n_blocks[w] < 1 || n_blocks[w] > 2 * k.F + 8)) return gf2::fail(GF2_ERR_INVALID, "prior of window %d has %d blocks", first + w, n_blocks[w]);
   }
   H2D(k.prior_rows + first, n_rows, sizeof(int32_t) * n);
   H2D(k.prior_nblocks + first, n_blocks, sizeof(int32_t) * n);
-  H2D(k.prior_J0 + (size_t)first * kP * kP, J0, sizeof(double) * n * kP * kP);
-  H2D(k.prior_r0 + (size_t)first * kP, r0, sizeof(double) * n * kP);
+  H2D(k.prior_J0 + (size_t)first * k.Pr * k.Pr, J0, sizeof(double) * n * k.Pr * k.Pr);
+  H2D(k.prior_r0 + (size_t)first * k.Pr, r0, sizeof(double) * n * k.Pr);
   H2D(k.prior_blocks + (size_t)first * (2 * k.F + 8), blocks, sizeof(gf2_prior_block) * n * (2 * k.F + 8));
   h->has_prior = true;
   return GF2_OK;

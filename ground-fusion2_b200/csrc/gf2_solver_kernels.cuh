@@ -42,7 +42,7 @@ struct WinState {  // per-window trust-region state (DoglegStrategy + TrustRegio
 };
 
 struct KP {  // kernel parameters (device pointers are window-major with the strides below)
-  int nW, F, Lm, Om, Pm, D, use_wheel;
+  int nW, F, Lm, Om, Pm, D, use_wheel, Pr;  // Pr: row stride of the prior arrays (<= GF2_MAX_PRIOR_DIM)
   uint32_t const_mask;
   double huber, sqrt_info_px, g_norm, lidar_sqrt_info;
   double ftol, gtol, ptol;
@@ -253,10 +253,10 @@ __global__ void k_prepare(KP p, int w0) {
   // prior: column map and H = J0^T J0
   const int n = p.prior_rows ? p.prior_rows[w] : 0;
   if (n > 0) {
-    int32_t* map = p.prior_map + (size_t)w * kP;
+    int32_t* map = p.prior_map + (size_t)w * p.Pr;
     const gf2_prior_block* blk = p.prior_blocks + (size_t)w * (2 * F + 8);
     if (t == 0) {
-      for (int c = 0; c < kP; c++) map[c] = -1;
+      for (int c = 0; c < p.Pr; c++) map[c] = -1;
       for (int b = 0; b < p.prior_nblocks[w]; b++) {
         int base = -1, ls = 0;
         if (blk[b].kind == GF2_BLK_POSE) { base = 15 * blk[b].index; ls = 6; }
@@ -265,12 +265,12 @@ __global__ void k_prepare(KP p, int w0) {
         for (int c = 0; c < ls; c++) map[blk[b].offset + c] = base < 0 ? -1 : base + c;
       }
     }
-    const double* J0 = p.prior_J0 + (size_t)w * kP * kP;
-    double* H = p.prior_H + (size_t)w * kP * kP;
+    const double* J0 = p.prior_J0 + (size_t)w * p.Pr * p.Pr;
+    double* H = p.prior_H + (size_t)w * p.Pr * p.Pr;
     for (int idx = t; idx < n * n; idx += blockDim.x) {
       const int a = idx / n, b = idx % n;
-      double s = 0; for (int r = 0; r < n; r++) s += J0[r * kP + a] * J0[r * kP + b];
-      H[a * kP + b] = s;
+      double s = 0; for (int r = 0; r < n; r++) s += J0[r * p.Pr + a] * J0[r * p.Pr + b];
+      H[a * p.Pr + b] = s;
     }
   }
   if (t == 0) {

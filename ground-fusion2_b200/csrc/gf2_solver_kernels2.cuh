@@ -212,18 +212,18 @@ __global__ void __launch_bounds__(kSolveThreads, 1) k_solve(KP p, int w0) {
     const int nb = p.prior_nblocks[w];
     if (t < nb) prior_block_dx(blk[t], pose, sb, S.dx);
     __syncthreads();
-    const double* J0 = p.prior_J0 + (size_t)w * kP * kP;
-    const double* r0 = p.prior_r0 + (size_t)w * kP;
-    if (t < n) { double s2 = r0[t]; for (int c = 0; c < n; c++) s2 += J0[t * kP + c] * S.dx[c]; S.pr[t] = s2; cost += 0.5 * s2 * s2; }
+    const double* J0 = p.prior_J0 + (size_t)w * p.Pr * p.Pr;
+    const double* r0 = p.prior_r0 + (size_t)w * p.Pr;
+    if (t < n) { double s2 = r0[t]; for (int c = 0; c < n; c++) s2 += J0[t * p.Pr + c] * S.dx[c]; S.pr[t] = s2; cost += 0.5 * s2 * s2; }
     __syncthreads();
-    const int32_t* map = p.prior_map + (size_t)w * kP;
-    const double* H = p.prior_H + (size_t)w * kP * kP;
-    if (t < n && map[t] >= 0) { double s2 = 0; for (int r = 0; r < n; r++) s2 += J0[r * kP + t] * S.pr[r]; S.g[map[t]] += s2; S.Hd[map[t]] += H[t * kP + t]; }
+    const int32_t* map = p.prior_map + (size_t)w * p.Pr;
+    const double* H = p.prior_H + (size_t)w * p.Pr * p.Pr;
+    if (t < n && map[t] >= 0) { double s2 = 0; for (int r = 0; r < n; r++) s2 += J0[r * p.Pr + t] * S.pr[r]; S.g[map[t]] += s2; S.Hd[map[t]] += H[t * p.Pr + t]; }
     for (int idx = t; idx < n * n; idx += nt) {
       const int a = idx / n, b = idx % n;
       const int ma = map[a], mb = map[b];
       if (ma < 0 || mb < 0 || mb > ma) continue;
-      Lp[pidx(ma, mb)] += H[a * kP + b];
+      Lp[pidx(ma, mb)] += H[a * p.Pr + b];
     }
     __syncthreads();
   }
@@ -565,8 +565,8 @@ __global__ void __launch_bounds__(288, 2) k_cand_eval(KP p, int w0) {
       const gf2_prior_block* blk = p.prior_blocks + (size_t)w * (2 * F + 8);
       if (ln < p.prior_nblocks[w]) prior_block_dx(blk[ln], pose_c, sb_c, S.dx);
       __syncwarp();
-      const double* J0 = p.prior_J0 + (size_t)w * kP * kP; const double* r0p = p.prior_r0 + (size_t)w * kP;
-      for (int row = ln; row < n; row += 32) { double s2 = r0p[row]; for (int c = 0; c < n; c++) s2 += J0[row * kP + c] * S.dx[c]; accx[0] += 0.5 * s2 * s2; }
+      const double* J0 = p.prior_J0 + (size_t)w * p.Pr * p.Pr; const double* r0p = p.prior_r0 + (size_t)w * p.Pr;
+      for (int row = ln; row < n; row += 32) { double s2 = r0p[row]; for (int c = 0; c < n; c++) s2 += J0[row * p.Pr + c] * S.dx[c]; accx[0] += 0.5 * s2 * s2; }
     }
   }
   block_sum<3>(acc, S.red);

@@ -93,11 +93,11 @@ __global__ void __launch_bounds__(kNonvisThreads) k_nonvis(KP p, int w0) {
     const gf2_prior_block* blk = p.prior_blocks + (size_t)w * (2 * F + 8);
     if (t < p.prior_nblocks[w]) prior_block_dx(blk[t], pose, sb, dx);
     __syncthreads();
-    const double* J0 = p.prior_J0 + (size_t)w * kP * kP;
-    const double* r0 = p.prior_r0 + (size_t)w * kP;
-    if (t < n) { double s2 = r0[t]; for (int c = 0; c < n; c++) s2 += J0[t * kP + c] * dx[c]; pr[t] = s2; cost += 0.5 * s2 * s2; }
+    const double* J0 = p.prior_J0 + (size_t)w * p.Pr * p.Pr;
+    const double* r0 = p.prior_r0 + (size_t)w * p.Pr;
+    if (t < n) { double s2 = r0[t]; for (int c = 0; c < n; c++) s2 += J0[t * p.Pr + c] * dx[c]; pr[t] = s2; cost += 0.5 * s2 * s2; }
     __syncthreads();
-    if (t < n) { double s2 = 0; for (int r = 0; r < n; r++) s2 += J0[r * kP + t] * pr[r]; p.prior_g[(size_t)w * kP + t] = s2; }
+    if (t < n) { double s2 = 0; for (int r = 0; r < n; r++) s2 += J0[r * p.Pr + t] * pr[r]; p.prior_g[(size_t)w * p.Pr + t] = s2; }
   }
   cost = warp_sum(cost);
   if (lane == 0) red[wid] = cost;
@@ -176,14 +176,14 @@ __global__ void __launch_bounds__(kSolveThreads, 1) k_solve2(KP p, int w0) {
   // ---- prior (H = J0^T J0 precomputed by k_prepare, gradient by k_nonvis)
   const int n = p.prior_rows ? p.prior_rows[w] : 0;
   if (n > 0) {
-    const int32_t* map = p.prior_map + (size_t)w * kP;
-    const double* H = p.prior_H + (size_t)w * kP * kP;
-    if (t < n && map[t] >= 0) { S.g[map[t]] += p.prior_g[(size_t)w * kP + t]; S.Hd[map[t]] += H[t * kP + t]; }
+    const int32_t* map = p.prior_map + (size_t)w * p.Pr;
+    const double* H = p.prior_H + (size_t)w * p.Pr * p.Pr;
+    if (t < n && map[t] >= 0) { S.g[map[t]] += p.prior_g[(size_t)w * p.Pr + t]; S.Hd[map[t]] += H[t * p.Pr + t]; }
     for (int idx = t; idx < n * n; idx += nt) {
       const int a = idx / n, b = idx % n;
       const int ma = map[a], mb = map[b];
       if (ma < 0 || mb < 0 || mb > ma) continue;
-      Ael(A, ma, mb) += H[a * kP + b];
+      Ael(A, ma, mb) += H[a * p.Pr + b];
     }
     __syncthreads();
   }

@@ -246,7 +246,7 @@ void Estimator::optimization() {
   if (!gf2) {
     gf2_solver_cfg cfg; memset(&cfg, 0, sizeof(cfg));
     cfg.device = 0; cfg.max_windows = 1; cfg.n_frames = WINDOW_SIZE + 1; cfg.max_landmarks = NUM_OF_F; cfg.max_obs = NUM_OF_F * (WINDOW_SIZE + 1);
-    cfg.max_imu_samples = 64;
+    cfg.max_imu_samples = 64; cfg.max_prior_rows = GF2_MAX_PRIOR_DIM;
     if (gf2_solver_create(&cfg, &gf2) != GF2_OK) { last_error = gf2_last_error(); gf2 = nullptr; return; }
   }
   if (F != WINDOW_SIZE + 1) { last_error = "gf2host::Estimator::optimization handles the steady state frame_count == WINDOW_SIZE"; return; }

@@ -77,7 +77,7 @@ def _heading_R(psi):
 
 def make_windows(n_windows, config_id=2, n_landmarks=1000, n_frames=11, wheel=False, n_planes=0, first_window=0,
                  sorted_landmarks=True, prior="anchor", speed=1.0, yaw_rate=0.2, frame_dt=0.1, imu_hz=200, wheel_hz=50,
-                 pixel_noise=0.5, max_landmarks=None, max_obs=None, prior_weight=1.0):
+                 pixel_noise=0.5, max_landmarks=None, max_obs=None, prior_weight=1.0, prior_stride=None):
     """Return a dict of window-major arrays for `n_windows` windows (W10-F1000 when n_landmarks = 1000).
 
     Landmark l starts in frame s_l = l mod 8 (track length n_frames - s_l, observed in every later frame). With
@@ -128,7 +128,8 @@ def make_windows(n_windows, config_id=2, n_landmarks=1000, n_frames=11, wheel=Fa
     if n_planes:
         out["n_planes"] = np.full(n_windows, n_planes, np.int32)
         out["planes"] = np.zeros((n_windows, n_planes), abi.PLANE)
-    P = abi.MAX_PRIOR_DIM
+    P = prior_stride or abi.MAX_PRIOR_DIM
+    out["prior_stride"] = P
     out["prior_rows"] = np.zeros(n_windows, np.int32); out["prior_nblocks"] = np.zeros(n_windows, np.int32)
     out["prior_J0"] = np.zeros((n_windows, P, P)); out["prior_r0"] = np.zeros((n_windows, P))
     out["prior_blocks"] = np.zeros((n_windows, 2 * F + 8), abi.PRIOR_BLOCK)

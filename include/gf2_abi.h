@@ -168,7 +168,8 @@ typedef struct gf2_solver_cfg {
   int32_t max_imu_samples;   /* per interval, for gf2_imu_preintegrate (0 = records only) */
   int32_t max_wheel_samples; /* per interval */
   int32_t use_wheel;     /* allocate wheel factor storage */
-  int32_t reserved_[7];
+  int32_t max_prior_rows; /* row stride P of the prior arrays of gf2_set_prior; 0 selects GF2_MAX_PRIOR_DIM */
+  int32_t reserved_[6];
 } gf2_solver_cfg;
 
 /* Options of one solve = the ceres::Solver::Options the reference sets (estimator.cpp:3364-3376)
@@ -262,7 +263,7 @@ int gf2_get_imu(gf2_solver* h, int first, int n, gf2_imu_preint* preint);
 int gf2_set_wheel(gf2_solver* h, int first, int n, const gf2_wheel_preint* preint);
 
 /* Marginalization prior per window: n_rows [n] (0 = no prior), J0 [n][P][P] with
- * P = GF2_MAX_PRIOR_DIM (row r, column c at r*P + c; rows/cols >= n_rows ignored),
+ * P = cfg.max_prior_rows (GF2_MAX_PRIOR_DIM when 0; row r, column c at r*P + c; rows/cols >= n_rows ignored),
  * r0 [n][P], n_blocks [n], blocks [n][2*F+8]. */
 int gf2_set_prior(gf2_solver* h, int first, int n, const int32_t* n_rows, const double* J0, const double* r0,
                   const int32_t* n_blocks, const gf2_prior_block* blocks);

@@ -24,14 +24,14 @@ lib = _load()
 
 class Window(C.Structure):
     _fields_ = [("n_frames", C.c_int32), ("n_landmarks", C.c_int32), ("n_planes", C.c_int32), ("prior_rows", C.c_int32),
-                ("prior_nblocks", C.c_int32), ("use_wheel", C.c_int32)] + [(n, C.c_void_p) for n in (
+                ("prior_nblocks", C.c_int32), ("use_wheel", C.c_int32), ("prior_stride", C.c_int32), ("pad_", C.c_int32)] + [(n, C.c_void_p) for n in (
                     "para_pose", "para_speedbias", "ex_pose", "td", "ex_pose_wheel", "sxsysw", "td_wheel", "inv_depth",
                     "start_frame", "track_len", "fixed", "obs", "frame_td", "imu", "wheel", "prior_J0", "prior_r0",
                     "prior_blocks", "planes")]
 
 
 class Batch(C.Structure):
-    _fields_ = [(n, C.c_int32) for n in ("n_windows", "n_frames", "max_landmarks", "max_obs", "max_planes", "use_wheel")] + \
+    _fields_ = [(n, C.c_int32) for n in ("n_windows", "n_frames", "max_landmarks", "max_obs", "max_planes", "use_wheel", "prior_stride", "pad_")] + \
                [(n, C.c_void_p) for n in ("para_pose", "para_speedbias", "ex_pose", "td", "ex_pose_wheel", "sxsysw", "td_wheel",
                                           "inv_depth", "n_landmarks", "start_frame", "track_len", "fixed", "obs", "frame_td",
                                           "imu", "wheel", "prior_rows", "prior_J0", "prior_r0", "prior_nblocks", "prior_blocks",
@@ -51,6 +51,7 @@ def make_batch(w, keep):
     n = w["para_pose"].shape[0]
     b.n_windows = n; b.n_frames = w["n_frames"]; b.max_landmarks = w["max_landmarks"]; b.max_obs = w["max_obs"]
     b.max_planes = w.get("max_planes", 0); b.use_wheel = 1 if w.get("use_wheel") else 0
+    b.prior_stride = int(w["prior_J0"].shape[1]) if w.get("prior_J0") is not None else 96
     for name in ("para_pose", "para_speedbias", "ex_pose", "td", "ex_pose_wheel", "sxsysw", "td_wheel", "inv_depth",
                  "n_landmarks", "start_frame", "track_len", "fixed", "obs", "frame_td", "imu", "wheel", "prior_rows",
                  "prior_J0", "prior_r0", "prior_nblocks", "prior_blocks", "n_planes", "planes"):

@@ -19,6 +19,8 @@ typedef struct gf2o_window {
   int32_t prior_rows;
   int32_t prior_nblocks;
   int32_t use_wheel;
+  int32_t prior_stride;   /* row stride of prior_J0 */
+  int32_t pad_;
   double* para_pose;      /* [F][7] in/out */
   double* para_speedbias; /* [F][9] in/out */
   double* ex_pose;        /* [7] in/out */
@@ -95,7 +97,7 @@ void buildWindow(const gf2o_window& w, const gf2_solve_opts& o, BuiltWindow& bw)
     MarginalizationInfo& mi = bw.prior;
     mi.m = 0; mi.n = w.prior_rows;
     mi.linearized_jacobians.resize((size_t)mi.n * mi.n); mi.linearized_residuals.resize(mi.n);
-    for (int r = 0; r < mi.n; r++) { mi.linearized_residuals[r] = w.prior_r0[r]; for (int c = 0; c < mi.n; c++) mi.linearized_jacobians[(size_t)r * mi.n + c] = w.prior_J0[(size_t)r * GF2_MAX_PRIOR_DIM + c]; }
+    for (int r = 0; r < mi.n; r++) { mi.linearized_residuals[r] = w.prior_r0[r]; for (int c = 0; c < mi.n; c++) mi.linearized_jacobians[(size_t)r * mi.n + c] = w.prior_J0[(size_t)r * w.prior_stride + c]; }
     std::vector<int> ids;
     for (int b = 0; b < w.prior_nblocks; b++) {
       const gf2_prior_block& pb = w.prior_blocks[b];
@@ -193,7 +195,7 @@ int gf2o_linearize_window(const gf2o_window* w, const gf2_solve_opts* opts, int 
 // Batched solve over independent windows with a thread pool: the CPU baseline ("port") of bench.py.
 // Arrays use the same window-major strides as the gf2_set_* calls.
 typedef struct gf2o_batch {
-  int32_t n_windows, n_frames, max_landmarks, max_obs, max_planes, use_wheel;
+  int32_t n_windows, n_frames, max_landmarks, max_obs, max_planes, use_wheel, prior_stride, pad_;
   double *para_pose, *para_speedbias, *ex_pose, *td, *ex_pose_wheel, *sxsysw, *td_wheel, *inv_depth;
   const int32_t *n_landmarks, *start_frame, *track_len;
   const uint8_t* fixed;
@@ -221,7 +223,7 @@ static void windowOf(const gf2o_batch& b, int i, gf2o_window& w) {
   w.wheel = (b.use_wheel && b.wheel) ? b.wheel + (size_t)i * (F - 1) : nullptr;
   if (b.prior_rows) {
     w.prior_rows = b.prior_rows[i]; w.prior_nblocks = b.prior_nblocks[i];
-    w.prior_J0 = b.prior_J0 + (size_t)i * GF2_MAX_PRIOR_DIM * GF2_MAX_PRIOR_DIM; w.prior_r0 = b.prior_r0 + (size_t)i * GF2_MAX_PRIOR_DIM;
+    w.prior_stride = b.prior_stride; w.prior_J0 = b.prior_J0 + (size_t)i * b.prior_stride * b.prior_stride; w.prior_r0 = b.prior_r0 + (size_t)i * b.prior_stride;
     w.prior_blocks = b.prior_blocks + (size_t)i * (2 * F + 8);
   }
   if (b.n_planes && b.max_planes > 0) { w.n_planes = b.n_planes[i]; w.planes = b.planes + (size_t)i * b.max_planes; }
