@@ -262,16 +262,19 @@ def main():
         cs.get_states(n, out=co)
         cs.get_landmarks(n, out=cl)
 
-    def step_e2e():
-        list(pool.map(chunk_step, range(nch)))
-    for _ in range(2):
-        step_e2e()
+    def run_e2e(steps):
+        # every step passes all B windows through upload -> solve -> download; the chunk threads are not re-synchronised
+        # between steps, so chunk c of step k+1 may start while chunk c' of step k is still in flight (a streaming server)
+        def loop(c):
+            for _ in range(steps):
+                chunk_step(c)
+        list(pool.map(loop, range(nch)))
+    run_e2e(2)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_e2e()
+    run_e2e(args.steps)
     torch.cuda.synchronize()
     wall_e2e = time.perf_counter() - t0   # host wall clock around blocking calls + device synchronize: bounds the device time from above
     te = torch.tensor([wall_e2e], device="cuda")
