@@ -37,7 +37,7 @@ ABI_SYMBOLS = [
     "gf2_last_error", "gf2_abi_version", "gf2_device_count", "gf2_solver_create", "gf2_solver_destroy", "gf2_set_states",
     "gf2_solver_set_stream", "gf2_snapshot_states", "gf2_restore_states", "gf2_host_alloc", "gf2_host_free",
     "gf2_imu_preintegrate_resident", "gf2_get_trace",
-    "gf2_set_landmarks", "gf2_set_imu", "gf2_imu_preintegrate", "gf2_get_imu", "gf2_set_wheel", "gf2_set_prior",
+    "gf2_set_landmarks", "gf2_set_imu", "gf2_imu_preintegrate", "gf2_get_imu", "gf2_set_wheel", "gf2_wheel_preintegrate", "gf2_get_wheel", "gf2_set_prior",
     "gf2_set_planes", "gf2_solve", "gf2_linearize", "gf2_reduced_dim", "gf2_get_reduced_system", "gf2_get_states",
     "gf2_get_landmarks", "gf2_comm_init", "gf2_comm_unique_id", "gf2_last_timing", "gf2_tracker_create",
     "gf2_tracker_destroy", "gf2_tracker_track", "gf2_tracker_track_fb", "gf2_tracker_last_timing",
@@ -72,10 +72,10 @@ class Solver:
     """Batched sliding-window solver: the ceres::Solve call of Estimator::optimization() for `max_windows` windows."""
 
     def __init__(self, max_windows, n_frames=11, max_landmarks=1000, max_obs=7500, max_planes=0, max_imu_samples=0,
-                 use_wheel=False, device=0, max_prior_rows=0):
+                 use_wheel=False, device=0, max_prior_rows=0, max_wheel_samples=0):
         cfg = abi.SolverCfg()
         cfg.device = device; cfg.max_windows = max_windows; cfg.n_frames = n_frames; cfg.max_landmarks = max_landmarks
-        cfg.max_obs = max_obs; cfg.max_planes = max_planes; cfg.max_imu_samples = max_imu_samples
+        cfg.max_obs = max_obs; cfg.max_planes = max_planes; cfg.max_imu_samples = max_imu_samples; cfg.max_wheel_samples = max_wheel_samples
         cfg.use_wheel = 1 if use_wheel else 0
         cfg.max_prior_rows = max_prior_rows
         self.Pr = max_prior_rows or abi.MAX_PRIOR_DIM
@@ -137,6 +137,17 @@ class Solver:
     def set_wheel(self, rec, first=0):
         _check(lib().gf2_set_wheel(self.h, first, rec.shape[0], _p(rec)))
 
+    def wheel_preintegrate(self, w, first=0):
+        n = w["wheel_n"].shape[0]
+        noise = np.ascontiguousarray(w["wheel_noise"], dtype=np.float64)
+        _check(lib().gf2_wheel_preintegrate(self.h, first, n, _p(w["wheel_samples"]), _p(w["wheel_n"]), _p(w["wheel_first"]),
+                                            _p(w["wheel_lin"]), _p(noise)))
+
+    def get_wheel(self, n, first=0):
+        rec = np.zeros((n, self.F - 1), abi.WHEEL_PREINT)
+        _check(lib().gf2_get_wheel(self.h, first, n, _p(rec)))
+        return rec
+
     def set_prior(self, w, first=0):
         n = w["prior_rows"].shape[0]
         assert w["prior_J0"].shape[1] == self.Pr, "prior arrays must use the solver's max_prior_rows as stride"
@@ -158,6 +169,8 @@ class Solver:
             self.set_imu(w["imu"], first)
         if w.get("use_wheel") and "wheel" in w:
             self.set_wheel(w["wheel"], first)
+        elif w.get("use_wheel") and self.cfg.max_wheel_samples > 0:
+            self.wheel_preintegrate(w, first)
         self.set_prior(w, first)
         if w.get("max_planes", 0) > 0:
             self.set_planes(w, first)

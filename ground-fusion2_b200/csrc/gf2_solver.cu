@@ -141,6 +141,81 @@ __global__ void __launch_bounds__(32 * kPreWarps) k_imu_preintegrate(int n_inter
 // loaded when the caller is a torch.distributed process), so CPU-only boxes and single-GPU users never need it.
 namespace {
 typedef struct { char internal[128]; } gf2_nccl_uid;
+// ---------------------------------------------------------------------------------------------------------------------
+// Wheel-odometry preintegration (WheelIntegrationBase::push_back -> propagate -> midPointIntegration,
+// VE/factor/wheel_integration_base.h:41-178). The chain is 6x6 and 5 samples long at 50 Hz / 10 Hz frames, so one thread
+// per interval is enough (B * (F-1) threads); F = [[I, A], [0, ddR^T]] and the 6x12 V are used in their block form.
+__global__ void __launch_bounds__(128) k_wheel_preintegrate(int total, int max_samples, const gf2_wheel_sample* __restrict__ samples, const int32_t* __restrict__ n_samples,
+                                                             const double* __restrict__ first_sample, const double* __restrict__ lin, double vel_n, double gyr_n,
+                                                             gf2_wheel_preint* __restrict__ out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const gf2_wheel_sample* sm = samples + (size_t)t * max_samples;
+  const int ns = n_samples[t];
+  V3 vel_0 = ld3(first_sample + 6 * t), gyr_0 = ld3(first_sample + 6 * t + 3);
+  const V3 lin_vel = vel_0, lin_gyr = gyr_0;
+  const double sx = lin[4 * t], sy = lin[4 * t + 1], sw = lin[4 * t + 2], ltd = lin[4 * t + 3];
+  V3 delta_p = mk3(0, 0, 0); Q4 delta_q; delta_q.x = delta_q.y = delta_q.z = 0; delta_q.w = 1;
+  double jac[18], cov[36];
+  for (int i = 0; i < 18; i++) jac[i] = 0;
+  for (int i = 0; i < 36; i++) cov[i] = 0;
+  double sum_dt = 0;
+  const double nv = vel_n * vel_n, ng = gyr_n * gyr_n;
+  for (int k = 0; k < ns; k++) {
+    const double dt = sm[k].dt; const V3 vel_1 = ld3(sm[k].vel), gyr_1 = ld3(sm[k].gyr);
+    const V3 sv0 = mk3(sx * vel_0.x, sy * vel_0.y, vel_0.z), sv1 = mk3(sx * vel_1.x, sy * vel_1.y, vel_1.z);
+    const V3 un_vel_0 = qrot(delta_q, sv0);
+    const V3 gsum = gyr_0 + gyr_1;
+    const V3 un_gyr = (0.5 * sw) * gsum;
+    Q4 ddq; ddq.w = 1; ddq.x = un_gyr.x * dt / 2; ddq.y = un_gyr.y * dt / 2; ddq.z = un_gyr.z * dt / 2;
+    const Q4 rq = qmul(delta_q, ddq);
+    const V3 un_vel_1 = qrot(rq, sv1);
+    const V3 un_vel = 0.5 * (un_vel_0 + un_vel_1);
+    const V3 result_delta_p = delta_p + un_vel * dt;
+    const M3 dR = toR(delta_q), rR = toR(rq), ddR = toR(ddq);
+    const M3 Rv0 = skew(sv0), Rv1 = skew(sv1);
+    const M3 rRv1 = mul(rR, Rv1);
+    const M3 A = scale(add(mul(dR, Rv0), mulBT(rRv1, ddR)), -0.5 * dt);   // F(0:3, 3:6)
+    const M3 Bt = transpose(ddR);                                          // F(3:6, 3:6)
+    const M3 Jr = rightJacobianSO3(un_gyr * dt);
+    M3 Ssv = zero3(); Ssv.m[0] = sx; Ssv.m[4] = sy; Ssv.m[8] = 1;
+    const M3 V00 = scale(mul(dR, Ssv), 0.5 * dt), V03 = scale(mul(rRv1, Jr), -0.25 * dt * dt), V06 = scale(mul(rR, Ssv), 0.5 * dt);
+    const M3 V33 = scale(Jr, 0.5 * sw * dt);
+    // jacobian wrt (sx, sy, sw)
+    const V3 c0 = (0.5 * dt) * (mul(dR, mk3(vel_0.x, 0, 0)) + mul(rR, mk3(vel_1.x, 0, 0)));
+    const V3 c1 = (0.5 * dt) * (mul(dR, mk3(0, vel_0.y, 0)) + mul(rR, mk3(0, vel_1.y, 0)));
+    const V3 dr_last = mk3(jac[3 * 3 + 2], jac[4 * 3 + 2], jac[5 * 3 + 2]);
+    const V3 dr_new = dr_last + mul(Jr, 0.5 * gsum) * dt;
+    const V3 c2 = (0.5 * dt) * (mul(dR, cross(dr_last, sv0)) + mul(rR, cross(dr_new, sv1)));
+    for (int i = 0; i < 3; i++) { jac[i * 3 + 0] += get(c0, i); jac[i * 3 + 1] += get(c1, i); jac[(3 + i) * 3 + 2] = get(dr_new, i); jac[i * 3 + 2] += get(c2, i); }
+    // covariance = F cov F^T + V noise V^T with cov = [[P, Q], [Q^T, R]]
+    M3 P, Q, QT, R;
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { P.m[i * 3 + j] = cov[i * 6 + j]; Q.m[i * 3 + j] = cov[i * 6 + 3 + j]; QT.m[i * 3 + j] = cov[(3 + i) * 6 + j]; R.m[i * 3 + j] = cov[(3 + i) * 6 + 3 + j]; }
+    // F cov = [[P + A Q^T, Q + A R], [B Q^T, B R]];  (F cov) F^T = [[(P + A QT) + (Q + A R) A^T, (Q + A R) B^T], [B QT + B R A^T, B R B^T]]
+    const M3 X0 = add(P, mul(A, QT)), X1 = add(Q, mul(A, R)), Y0 = mul(Bt, QT), Y1 = mul(Bt, R);
+    M3 N00 = add(X0, mulBT(X1, A)), N01 = mulBT(X1, Bt), N10 = add(Y0, mulBT(Y1, A)), N11 = mulBT(Y1, Bt);
+    // V noise V^T: noise = diag(nv I, ng I, nv I, ng I); V = [[V00, V03, V06, V03], [0, V33, 0, V33]]
+    N00 = add(N00, add(scale(add(mulBT(V00, V00), mulBT(V06, V06)), nv), scale(mulBT(V03, V03), 2.0 * ng)));
+    const M3 c03 = scale(mulBT(V03, V33), 2.0 * ng);
+    N01 = add(N01, c03); N10 = add(N10, transpose(c03));
+    N11 = add(N11, scale(mulBT(V33, V33), 2.0 * ng));
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { cov[i * 6 + j] = N00.m[i * 3 + j]; cov[i * 6 + 3 + j] = N01.m[i * 3 + j]; cov[(3 + i) * 6 + j] = N10.m[i * 3 + j]; cov[(3 + i) * 6 + 3 + j] = N11.m[i * 3 + j]; }
+    delta_p = result_delta_p; delta_q = qnormalized(rq);
+    sum_dt += dt;
+    vel_0 = vel_1; gyr_0 = gyr_1;
+  }
+  gf2_wheel_preint& r = out[t];
+  r.sum_dt = sum_dt;
+  r.delta_p[0] = delta_p.x; r.delta_p[1] = delta_p.y; r.delta_p[2] = delta_p.z;
+  r.delta_q[0] = delta_q.x; r.delta_q[1] = delta_q.y; r.delta_q[2] = delta_q.z; r.delta_q[3] = delta_q.w;
+  r.lin_sx = sx; r.lin_sy = sy; r.lin_sw = sw; r.lin_td = ltd;
+  r.lin_vel[0] = lin_vel.x; r.lin_vel[1] = lin_vel.y; r.lin_vel[2] = lin_vel.z; r.lin_gyr[0] = lin_gyr.x; r.lin_gyr[1] = lin_gyr.y; r.lin_gyr[2] = lin_gyr.z;
+  r.vel_1[0] = vel_0.x; r.vel_1[1] = vel_0.y; r.vel_1[2] = vel_0.z; r.gyr_1[0] = gyr_0.x; r.gyr_1[1] = gyr_0.y; r.gyr_1[2] = gyr_0.z;
+  for (int i = 0; i < 18; i++) r.jacobian[i] = jac[i];
+  for (int i = 0; i < 36; i++) r.covariance[i] = cov[i];
+  r.valid = 1; r.pad_ = 0;
+}
+
 struct NcclApi {
   void* lib = nullptr;
   int (*GetUniqueId)(gf2_nccl_uid*) = nullptr;
@@ -180,6 +255,7 @@ struct gf2_solver {
   gf2_imu_sample* d_imu_samples = nullptr; int32_t* d_imu_n = nullptr; double *d_imu_first = nullptr, *d_imu_bias = nullptr;
   gf2_imu_preint* d_imu = nullptr;
   gf2_wheel_preint* d_wheel = nullptr;
+  gf2_wheel_sample* d_wheel_samples = nullptr; int32_t* d_wheel_n = nullptr; double *d_wheel_first = nullptr, *d_wheel_lin = nullptr;
   void* nccl_comm = nullptr; int comm_rank = 0, comm_size = 1;
   bool has_imu = false, has_wheel = false, has_prior = false, has_planes = false, dump_full = false;
   std::vector<int32_t> h_obeg;
@@ -238,6 +314,10 @@ int gf2_solver_create(const gf2_solver_cfg* cfg, gf2_solver** out) {
   A(k.fixed, uint8_t, (size_t)B * Lm); A(k.obs, float4, (size_t)B * Om); A(k.frame_td, double, (size_t)B * F);
   A(h->d_imu, gf2_imu_preint, (size_t)B * (F - 1)); A(k.imu_sqrt, double, (size_t)B * (F - 1) * 225);
   if (cfg->use_wheel) { A(h->d_wheel, gf2_wheel_preint, (size_t)B * (F - 1)); A(k.wheel_sqrt, double, (size_t)B * (F - 1) * 36); }
+  if (cfg->use_wheel && cfg->max_wheel_samples > 0) {
+    A(h->d_wheel_samples, gf2_wheel_sample, (size_t)B * (F - 1) * cfg->max_wheel_samples); A(h->d_wheel_n, int32_t, (size_t)B * (F - 1));
+    A(h->d_wheel_first, double, (size_t)B * (F - 1) * 6); A(h->d_wheel_lin, double, (size_t)B * (F - 1) * 4);
+  }
   A(k.prior_rows, int32_t, B); A(k.prior_nblocks, int32_t, B); A(k.prior_J0, double, (size_t)B * k.Pr * k.Pr); A(k.prior_r0, double, (size_t)B * k.Pr);
   A(k.prior_blocks, gf2_prior_block, (size_t)B * (2 * F + 8)); A(k.prior_H, double, (size_t)B * k.Pr * k.Pr); A(k.prior_map, int32_t, (size_t)B * k.Pr);
   if (Pm > 0) { A(k.n_planes, int32_t, B); A(k.planes, gf2_plane, (size_t)B * Pm); }
@@ -415,6 +495,34 @@ int gf2_set_wheel(gf2_solver* h, int first, int n, const gf2_wheel_preint* prein
   if (!h->cfg.use_wheel) return gf2::fail(GF2_ERR_INVALID, "solver created with use_wheel = 0");
   H2D(h->d_wheel + (size_t)first * (h->kp.F - 1), preint, sizeof(gf2_wheel_preint) * n * (h->kp.F - 1));
   h->has_wheel = preint != nullptr;
+  return GF2_OK;
+}
+
+int gf2_wheel_preintegrate(gf2_solver* h, int first, int n, const gf2_wheel_sample* samples, const int32_t* n_samples, const double* first_sample,
+                           const double* lin, const double noise[2]) {
+  GF2_TRY(check_range(h, first, n));
+  const int ms = h->cfg.max_wheel_samples, Fm1 = h->kp.F - 1;
+  if (!h->cfg.use_wheel || ms <= 0) return gf2::fail(GF2_ERR_INVALID, "solver created with use_wheel = 0 or max_wheel_samples = 0");
+  if (!samples || !n_samples || !first_sample || !lin || !noise) return gf2::fail(GF2_ERR_INVALID, "null argument");
+  for (size_t i = 0; i < (size_t)n * Fm1; i++) if (n_samples[i] < 0 || n_samples[i] > ms) return gf2::fail(GF2_ERR_INVALID, "n_samples[%zu] = %d exceeds max_wheel_samples %d", i, n_samples[i], ms);
+  const size_t off = (size_t)first * Fm1;
+  H2D(h->d_wheel_samples + off * ms, samples, sizeof(gf2_wheel_sample) * n * Fm1 * ms);
+  H2D(h->d_wheel_n + off, n_samples, sizeof(int32_t) * n * Fm1);
+  H2D(h->d_wheel_first + off * 6, first_sample, sizeof(double) * n * Fm1 * 6);
+  H2D(h->d_wheel_lin + off * 4, lin, sizeof(double) * n * Fm1 * 4);
+  const int total = n * Fm1;
+  k_wheel_preintegrate<<<(total + 127) / 128, 128, 0, h->stream>>>(total, ms, h->d_wheel_samples + off * ms, h->d_wheel_n + off, h->d_wheel_first + off * 6,
+                                                                  h->d_wheel_lin + off * 4, noise[0], noise[1], h->d_wheel + off);
+  GF2_CUDA(cudaGetLastError());
+  h->has_wheel = true;
+  return GF2_OK;
+}
+
+int gf2_get_wheel(gf2_solver* h, int first, int n, gf2_wheel_preint* preint) {
+  GF2_TRY(check_range(h, first, n));
+  if (!h->cfg.use_wheel) return gf2::fail(GF2_ERR_INVALID, "solver created with use_wheel = 0");
+  D2H(preint, h->d_wheel + (size_t)first * (h->kp.F - 1), sizeof(gf2_wheel_preint) * n * (h->kp.F - 1));
+  GF2_CUDA(cudaStreamSynchronize(h->stream));
   return GF2_OK;
 }
 

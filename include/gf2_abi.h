@@ -261,6 +261,13 @@ int gf2_imu_preintegrate_resident(gf2_solver* h, int first, int n, const double 
 int gf2_get_imu(gf2_solver* h, int first, int n, gf2_imu_preint* preint);
 
 int gf2_set_wheel(gf2_solver* h, int first, int n, const gf2_wheel_preint* preint);
+/* Same from raw samples, preintegrated on the device (WheelIntegrationBase::push_back chain,
+ * VE/factor/wheel_integration_base.h:41-178): samples [n][F-1][max_wheel_samples], n_samples [n][F-1],
+ * first sample vel_0/gyr_0 [n][F-1][6], lin [n][F-1][4] = linearized sx, sy, sw, td, noise = {VEL_N_wheel, GYR_N_wheel}. */
+int gf2_wheel_preintegrate(gf2_solver* h, int first, int n, const gf2_wheel_sample* samples,
+                           const int32_t* n_samples, const double* first_sample, const double* lin,
+                           const double noise[2]);
+int gf2_get_wheel(gf2_solver* h, int first, int n, gf2_wheel_preint* preint);
 
 /* Marginalization prior per window: n_rows [n] (0 = no prior), J0 [n][P][P] with
  * P = cfg.max_prior_rows (GF2_MAX_PRIOR_DIM when 0; row r, column c at r*P + c; rows/cols >= n_rows ignored),

@@ -5,7 +5,10 @@
 #include <thread>
 #include <atomic>
 #include <memory>
+#include <map>
+#include <algorithm>
 #include "gf2o_ceres.h"
+#include "gf2o_marg.h"
 
 using namespace gf2o;
 
@@ -296,6 +299,124 @@ int gf2o_wheel_preintegrate(const gf2_wheel_sample* samples, int n, const double
   for (int i = 0; i < n; i++) wb.push_back(samples[i].dt, v3(samples[i].vel[0], samples[i].vel[1], samples[i].vel[2]), v3(samples[i].gyr[0], samples[i].gyr[1], samples[i].gyr[2]));
   wb.pack(out);
   return 0;
+}
+
+// Marginalization after the solve (VE/estimator/estimator.cpp:3394-3690). mode 0 = MARGIN_OLD, 1 = MARGIN_SECOND_NEW.
+// Output = the kept part of the new MarginalizationInfo with the blocks already renamed by addr_shift (:3561-3595 /
+// :3653-3681), i.e. in the indexing of the window AFTER slideWindow: J0 [n][P] row stride P, r0 [n], blocks.
+// Returns n (>= 0), -1 if the new prior is invalid (m == 0), -2 if nothing is marginalized (SECOND_NEW without the
+// second-newest pose in the old prior: the old prior stays), -3 on an unsupported input.
+int gf2o_marginalize_window(const gf2o_window* w, const gf2_solve_opts* o, int mode, int P, double* J0, double* r0, int32_t* n_blocks,
+                            gf2_prior_block* blocks, int32_t* m_out) {
+  const int F = w->n_frames;
+  ProjectionTwoFrameOneCamFactor::sqrt_info = o->sqrt_info_px;
+  IntegrationBase::G = v3(0, 0, o->g_norm);
+  gf2o_marg::Info info;
+  std::vector<std::unique_ptr<CostFunction>> owned;
+  MarginalizationInfo last;  // the kept part of last_marginalization_info
+  std::unique_ptr<IntegrationBase> imu0; std::unique_ptr<WheelIntegrationBase> wheel0;
+  auto addrOf = [&](const gf2_prior_block& b) -> double* {
+    switch (b.kind) {
+      case GF2_BLK_POSE: return w->para_pose + 7 * b.index;
+      case GF2_BLK_SPEEDBIAS: return w->para_speedbias + 9 * b.index;
+      case GF2_BLK_EX_POSE: return w->ex_pose;
+      case GF2_BLK_TD: return w->td;
+      case GF2_BLK_EX_WHEEL: return w->ex_pose_wheel;
+      case GF2_BLK_SX: return w->sxsysw + 0;
+      case GF2_BLK_SY: return w->sxsysw + 1;
+      case GF2_BLK_SW: return w->sxsysw + 2;
+      case GF2_BLK_TD_WHEEL: return w->td_wheel;
+    }
+    return nullptr;
+  };
+  std::vector<double*> last_blocks;
+  if (w->prior_rows > 0) {
+    last.m = 0; last.n = w->prior_rows;
+    last.linearized_jacobians.resize((size_t)last.n * last.n); last.linearized_residuals.resize(last.n);
+    for (int r = 0; r < last.n; r++) { last.linearized_residuals[r] = w->prior_r0[r]; for (int c = 0; c < last.n; c++) last.linearized_jacobians[(size_t)r * last.n + c] = w->prior_J0[(size_t)r * w->prior_stride + c]; }
+    for (int b = 0; b < w->prior_nblocks; b++) {
+      const gf2_prior_block& pb = w->prior_blocks[b];
+      int size = (pb.kind == GF2_BLK_POSE || pb.kind == GF2_BLK_EX_POSE || pb.kind == GF2_BLK_EX_WHEEL) ? 7 : (pb.kind == GF2_BLK_SPEEDBIAS ? 9 : 1);
+      last.keep_block_size.push_back(size); last.keep_block_idx.push_back(pb.offset); last.keep_block_data.emplace_back(pb.x0, pb.x0 + size);
+      last_blocks.push_back(addrOf(pb));
+    }
+  }
+  auto add = [&](CostFunction* f, bool loss, std::vector<double*> blocks_, std::vector<int> drop) {
+    owned.emplace_back(f);
+    auto* r = new gf2o_marg::ResidualBlockInfo(); r->cost_function = f; r->loss = loss; r->parameter_blocks = blocks_; r->drop_set = drop;
+    info.addResidualBlockInfo(r);
+  };
+  std::map<double*, std::pair<int, int>> shift;  // address -> (kind, index) after slideWindow
+  if (mode == 0) {
+    if (w->prior_rows > 0) {  // :3401-3415
+      std::vector<int> drop;
+      for (size_t i = 0; i < last_blocks.size(); i++) if (last_blocks[i] == w->para_pose || last_blocks[i] == w->para_speedbias) drop.push_back((int)i);
+      add(new MarginalizationFactor(&last), false, last_blocks, drop);
+    }
+    if (w->imu && w->imu[0].valid && w->imu[0].sum_dt < 10.0) {  // :3416-3427
+      imu0.reset(new IntegrationBase(w->imu[0]));
+      add(new IMUFactor(imu0.get()), false, {w->para_pose, w->para_speedbias, w->para_pose + 7, w->para_speedbias + 9}, {0, 1});
+    }
+    if (w->use_wheel && w->wheel && w->wheel[0].valid && w->wheel[0].sum_dt < 10.0) {  // :3428-3439
+      wheel0.reset(new WheelIntegrationBase(w->wheel[0]));
+      add(new WheelFactor(wheel0.get()), false, {w->para_pose, w->para_pose + 7, w->ex_pose_wheel, w->sxsysw, w->sxsysw + 1, w->sxsysw + 2, w->td_wheel}, {0});
+    }
+    int ob = 0;  // :3495-3528
+    for (int l = 0; l < w->n_landmarks; l++) {
+      const int imu_i = w->start_frame[l];
+      if (imu_i == 0) {
+        const gf2_obs& oi = w->obs[ob];
+        V3 pts_i = v3(oi.x, oi.y, 1.0); double vi[2] = {oi.vx, oi.vy};
+        for (int k = 1; k < w->track_len[l]; k++) {
+          const gf2_obs& oj = w->obs[ob + k];
+          V3 pts_j = v3(oj.x, oj.y, 1.0); double vj[2] = {oj.vx, oj.vy};
+          add(new ProjectionTwoFrameOneCamFactor(pts_i, pts_j, vi, vj, w->frame_td[0], w->frame_td[k]), true,
+              {w->para_pose, w->para_pose + 7 * k, w->ex_pose, w->inv_depth + l, w->td}, {0, 3});
+        }
+      }
+      ob += w->track_len[l];
+    }
+    for (int i = 1; i < F; i++) { shift[w->para_pose + 7 * i] = {GF2_BLK_POSE, i - 1}; shift[w->para_speedbias + 9 * i] = {GF2_BLK_SPEEDBIAS, i - 1}; }  // :3561-3570
+  } else {
+    const int sn = F - 2;  // WINDOW_SIZE - 1
+    if (!(w->prior_rows > 0) || !std::count(last_blocks.begin(), last_blocks.end(), w->para_pose + 7 * sn)) return -2;  // :3599-3600
+    std::vector<int> drop;
+    for (size_t i = 0; i < last_blocks.size(); i++) {
+      if (last_blocks[i] == w->para_speedbias + 9 * sn) return -3;  // ROS_ASSERT, :3612
+      if (last_blocks[i] == w->para_pose + 7 * sn) drop.push_back((int)i);
+    }
+    add(new MarginalizationFactor(&last), false, last_blocks, drop);
+    for (int i = 0; i < F; i++) {  // :3653-3676
+      if (i == sn) continue;
+      const int to = (i == F - 1) ? i - 1 : i;
+      shift[w->para_pose + 7 * i] = {GF2_BLK_POSE, to}; shift[w->para_speedbias + 9 * i] = {GF2_BLK_SPEEDBIAS, to};
+    }
+  }
+  shift[w->ex_pose] = {GF2_BLK_EX_POSE, 0}; shift[w->td] = {GF2_BLK_TD, 0};
+  if (w->use_wheel) {
+    shift[w->ex_pose_wheel] = {GF2_BLK_EX_WHEEL, 0}; shift[w->sxsysw] = {GF2_BLK_SX, 0}; shift[w->sxsysw + 1] = {GF2_BLK_SY, 0};
+    shift[w->sxsysw + 2] = {GF2_BLK_SW, 0}; shift[w->td_wheel] = {GF2_BLK_TD_WHEEL, 0};
+  }
+  info.preMarginalize(o->huber_delta);
+  info.marginalize(1e-8);  // eps, marginalization_factor.h:83
+  if (m_out) *m_out = info.m;
+  if (!info.valid) return -1;
+  if (info.n > P) return -3;
+  // getParameterBlocks, :310-330
+  int nb = 0;
+  for (double* a : info.order) {
+    if (info.idx[a] < info.m) continue;
+    auto it = shift.find(a);
+    if (it == shift.end()) return -3;
+    gf2_prior_block& pb = blocks[nb++];
+    std::memset(&pb, 0, sizeof(pb));
+    pb.kind = it->second.first; pb.index = it->second.second; pb.offset = info.idx[a] - info.m;
+    const std::vector<double>& d = info.data[a];
+    for (size_t k = 0; k < d.size(); k++) pb.x0[k] = d[k];
+  }
+  *n_blocks = nb;
+  for (int r = 0; r < info.n; r++) { r0[r] = info.linearized_residuals[r]; for (int c = 0; c < info.n; c++) J0[(size_t)r * P + c] = info.linearized_jacobians[(size_t)r * info.n + c]; }
+  return info.n;
 }
 
 int gf2o_sym_eigen(int n, const double* A, double* evals, double* evecs) { symEigen(n, A, evals, evecs); return 0; }
