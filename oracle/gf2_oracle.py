@@ -147,3 +147,44 @@ def wheel_preintegrate(w):
             rec[i, k] = one[0]
     w["wheel"] = rec
     return rec
+
+
+def marginalize_window(w, i, opts, mode=0, P=96):
+    """Restated marginalization (estimator.cpp:3394-3690) of window i at its current states. Returns a dict
+    {status, n, m, J0 [n][n], r0 [n], blocks [nb] PRIOR_BLOCK} in the indexing of the window after slideWindow."""
+    from gf2_loader import load
+    abi = load().abi
+    keep = []
+    b = make_batch(w, keep)
+    win = Window()
+    lib.gf2o_batch_window(C.byref(b), int(i), C.byref(win))
+    J0 = np.zeros((P, P)); r0 = np.zeros(P); nb = C.c_int32(0); m = C.c_int32(0)
+    blocks = np.zeros(2 * w["n_frames"] + 8, abi.PRIOR_BLOCK)
+    n = lib.gf2o_marginalize_window(C.byref(win), C.byref(opts), int(mode), int(P), _p(J0), _p(r0), C.byref(nb), _p(blocks), C.byref(m))
+    if n < 0:
+        return {"status": n, "n": 0, "m": m.value}
+    return {"status": 0, "n": n, "m": m.value, "J0": J0[:n, :n].copy(), "r0": r0[:n].copy(), "blocks": blocks[:nb.value].copy()}
+
+
+BLOCK_LOCAL = {0: 6, 1: 9, 2: 6, 3: 1, 4: 6, 5: 1, 6: 1, 7: 1, 8: 1}
+
+
+def prior_information(prior, n_frames=11):
+    """Order-independent form of a prior: (H, g, x0) with H = J0^T J0 and g = J0^T r0 scattered into the canonical tangent
+    layout [pose f (6) | speed-bias f (9)] per frame, then ex-pose 6, td 1, ex-wheel 6, sx sy sw, td-wheel; x0 maps
+    (kind, index) -> linearisation point."""
+    F = n_frames
+    base = {2: 15 * F, 3: 15 * F + 6, 4: 15 * F + 7, 5: 15 * F + 13, 6: 15 * F + 14, 7: 15 * F + 15, 8: 15 * F + 16}
+    T = 15 * F + 17
+    cols = np.full(prior["n"], -1)
+    x0 = {}
+    for b in prior["blocks"]:
+        kind, index, off = int(b["kind"]), int(b["index"]), int(b["offset"])
+        start = 15 * index + (0 if kind == 0 else 6) if kind in (0, 1) else base[kind]
+        cols[off:off + BLOCK_LOCAL[kind]] = start + np.arange(BLOCK_LOCAL[kind])
+        x0[(kind, index)] = np.array(b["x0"])
+    assert (cols >= 0).all()
+    H = np.zeros((T, T)); g = np.zeros(T)
+    Hs = prior["J0"].T @ prior["J0"]; gs = prior["J0"].T @ prior["r0"]
+    H[np.ix_(cols, cols)] = Hs; g[cols] = gs
+    return H, g, x0
