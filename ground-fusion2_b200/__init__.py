@@ -28,6 +28,8 @@ def lib():
         _lib = C.CDLL(LIB_PATH)
         _lib.gf2_last_error.restype = C.c_char_p
         _lib.gf2_host_alloc.restype = C.c_void_p
+        _lib.gf2_last_marginalize_ms.restype = C.c_double
+        _lib.gf2_last_marginalize_ms.argtypes = [C.c_void_p]
         _lib.gf2_host_alloc.argtypes = [C.c_size_t]
         _lib.gf2_host_free.argtypes = [C.c_void_p]
     return _lib
@@ -38,7 +40,7 @@ ABI_SYMBOLS = [
     "gf2_solver_set_stream", "gf2_snapshot_states", "gf2_restore_states", "gf2_host_alloc", "gf2_host_free",
     "gf2_imu_preintegrate_resident", "gf2_get_trace",
     "gf2_set_landmarks", "gf2_set_imu", "gf2_imu_preintegrate", "gf2_get_imu", "gf2_set_wheel", "gf2_wheel_preintegrate", "gf2_get_wheel", "gf2_set_prior",
-    "gf2_set_planes", "gf2_solve", "gf2_linearize", "gf2_reduced_dim", "gf2_get_reduced_system", "gf2_get_states",
+    "gf2_set_planes", "gf2_marginalize", "gf2_get_prior", "gf2_last_marginalize_ms", "gf2_solve", "gf2_linearize", "gf2_reduced_dim", "gf2_get_reduced_system", "gf2_get_states",
     "gf2_get_landmarks", "gf2_comm_init", "gf2_comm_unique_id", "gf2_last_timing", "gf2_tracker_create",
     "gf2_tracker_destroy", "gf2_tracker_track", "gf2_tracker_track_fb", "gf2_tracker_last_timing",
 ]
@@ -153,6 +155,24 @@ class Solver:
         assert w["prior_J0"].shape[1] == self.Pr, "prior arrays must use the solver's max_prior_rows as stride"
         _check(lib().gf2_set_prior(self.h, first, n, _p(w["prior_rows"]), _p(w["prior_J0"]), _p(w["prior_r0"]),
                                    _p(w["prior_nblocks"]), _p(w["prior_blocks"])))
+
+    def marginalize(self, opts, mode=0, n=None, first=0):
+        """gf2_marginalize: returns (status [n], m [n]); the new prior stays resident (get_prior downloads it)."""
+        n = n if n is not None else self.B
+        status = np.zeros(n, np.int32); m = np.zeros(n, np.int32)
+        _check(lib().gf2_marginalize(self.h, first, n, int(mode), C.byref(opts), _p(status), _p(m)))
+        return status, m
+
+    def get_prior(self, n=None, first=0):
+        n = n if n is not None else self.B
+        out = {"prior_rows": np.zeros(n, np.int32), "prior_J0": np.zeros((n, self.Pr, self.Pr)), "prior_r0": np.zeros((n, self.Pr)),
+               "prior_nblocks": np.zeros(n, np.int32), "prior_blocks": np.zeros((n, 2 * self.F + 8), abi.PRIOR_BLOCK)}
+        _check(lib().gf2_get_prior(self.h, first, n, _p(out["prior_rows"]), _p(out["prior_J0"]), _p(out["prior_r0"]),
+                                   _p(out["prior_nblocks"]), _p(out["prior_blocks"])))
+        return out
+
+    def last_marginalize_ms(self):
+        return float(lib().gf2_last_marginalize_ms(self.h))
 
     def set_planes(self, w, first=0):
         _check(lib().gf2_set_planes(self.h, first, w["n_planes"].shape[0], _p(w["n_planes"]), _p(w["planes"])))

@@ -71,3 +71,6 @@ def ptr(a, ctype=C.c_void_p):
         return None
     assert a.flags["C_CONTIGUOUS"], "array must be C-contiguous"
     return a.ctypes.data_as(ctype)
+
+MARGIN_OLD, MARGIN_SECOND_NEW = 0, 1
+MARG_INVALID, MARG_UNCHANGED, MARG_UNSUPPORTED, MARG_DEGENERATE, MARG_TOO_LARGE = -1, -2, -3, -4, -5

@@ -9,6 +9,7 @@
 #include <vector>
 #include "gf2_solver_solve.cuh"
 #include "gf2_solver_lin.cuh"
+#include "gf2_solver_marg.cuh"
 #include "gf2_common.h"
 
 using namespace gf2;
@@ -256,6 +257,7 @@ struct gf2_solver {
   gf2_imu_preint* d_imu = nullptr;
   gf2_wheel_preint* d_wheel = nullptr;
   gf2_wheel_sample* d_wheel_samples = nullptr; int32_t* d_wheel_n = nullptr; double *d_wheel_first = nullptr, *d_wheel_lin = nullptr;
+  MargP marg = {}; int32_t* h_marg = nullptr; double marg_ms = 0;  // marginalization work buffers (allocated on first gf2_marginalize)
   void* nccl_comm = nullptr; int comm_rank = 0, comm_size = 1;
   bool has_imu = false, has_wheel = false, has_prior = false, has_planes = false, dump_full = false;
   std::vector<int32_t> h_obeg;
@@ -339,6 +341,7 @@ int gf2_solver_create(const gf2_solver_cfg* cfg, gf2_solver** out) {
   }
 #undef A
   if (rc != GF2_OK) { gf2_solver_destroy(h); return rc; }
+  cudaMemset((void*)k.prior_rows, 0, sizeof(int32_t) * B); cudaMemset((void*)k.prior_nblocks, 0, sizeof(int32_t) * B);
   for (auto& e : h->ev) cudaEventCreate(&e);
   cudaHostAlloc((void**)&h->h_state, sizeof(WinState) * B, cudaHostAllocDefault);
   // opt in to large dynamic shared memory
@@ -357,6 +360,7 @@ void gf2_solver_destroy(gf2_solver* h) {
   for (void* p : h->allocs) cudaFree(p);
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
   if (h->h_state) cudaFreeHost(h->h_state);
+  if (h->h_marg) cudaFreeHost(h->h_marg);
   if (h->nccl_comm && g_nccl.lib) g_nccl.CommDestroy(h->nccl_comm);
   cudaStreamDestroy(h->own_stream);
   delete h;
@@ -700,6 +704,65 @@ int gf2_get_landmarks(gf2_solver* h, int first, int n, double* inv_depth) {
   GF2_CUDA(cudaStreamSynchronize(h->stream));
   return GF2_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+int gf2_marginalize(gf2_solver* h, int first, int n, int32_t mode, const gf2_solve_opts* opts, int32_t* status, int32_t* m_dims) {
+  GF2_TRY(check_range(h, first, n));
+  if (!opts) return gf2::fail(GF2_ERR_INVALID, "null options");
+  if (mode != GF2_MARGIN_OLD && mode != GF2_MARGIN_SECOND_NEW) return gf2::fail(GF2_ERR_INVALID, "mode %d", mode);
+  if (h->nccl_comm) return gf2::fail(GF2_ERR_UNSUPPORTED, "marginalization in factor-sharded mode is not built (the frame-0 landmarks live on different ranks)");
+  if (h->cfg.use_wheel && h->has_wheel) return gf2::fail(GF2_ERR_UNSUPPORTED, "marginalization with wheel factors is not built yet (calibration-block Jacobians of WheelFactor)");
+  if (n == 0) return GF2_OK;
+  KP k;
+  GF2_TRY(fill_kp(h, opts, k));
+  const int B = h->cfg.max_windows;
+  if (!h->marg.A) {
+    GF2_TRY(dalloc<double>(h, &h->marg.A, (size_t)B * kMargKMax * kMargKMax)); GF2_TRY(dalloc<double>(h, &h->marg.b, (size_t)B * kMargKMax));
+    GF2_TRY(dalloc<int32_t>(h, &h->marg.touched, (size_t)B * kMargBlocksMax)); GF2_TRY(dalloc<int32_t>(h, &h->marg.status, B)); GF2_TRY(dalloc<int32_t>(h, &h->marg.mdim, B));
+    GF2_CUDA(cudaMallocHost((void**)&h->h_marg, sizeof(int32_t) * 2 * B));
+  }
+  MargP mp = h->marg;
+  mp.mode = mode;
+  mp.out_rows = const_cast<int32_t*>(h->kp.prior_rows); mp.out_nblocks = const_cast<int32_t*>(h->kp.prior_nblocks);
+  mp.out_J0 = const_cast<double*>(h->kp.prior_J0); mp.out_r0 = const_cast<double*>(h->kp.prior_r0);
+  mp.out_blocks = const_cast<gf2_prior_block*>(h->kp.prior_blocks);
+  const size_t sh_build = ((sizeof(MargShared) + 15) & ~size_t(15)) + sizeof(double) * kMargTMax * kMargLD;
+  const size_t sh_eig = ((sizeof(EigShared) + 15) & ~size_t(15)) + sizeof(double) * 2 * kMargKMax * (kMargKMax | 1);
+  static bool attr_done = false;
+  if (!attr_done) {
+    GF2_CUDA(cudaFuncSetAttribute(k_marg_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh_build));
+    GF2_CUDA(cudaFuncSetAttribute(k_marg_eig, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh_eig));
+    attr_done = true;
+  }
+  cudaEventRecord(h->ev[0], h->stream);
+  k_prepare<<<n, 128, sizeof(double) * 450 * GF2_MAX_FRAMES, h->stream>>>(k, first);   // IMU sqrt_info, J0^T J0 of the old prior
+  k_marg_build<<<n, kMargThreads, sh_build, h->stream>>>(k, first, mp);
+  k_marg_eig<<<n, kMargThreads, sh_eig, h->stream>>>(k, first, mp);
+  cudaEventRecord(h->ev[1], h->stream);
+  GF2_CUDA(cudaGetLastError());
+  GF2_CUDA(cudaMemcpyAsync(h->h_marg, mp.status + first, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, h->stream));
+  GF2_CUDA(cudaMemcpyAsync(h->h_marg + B, mp.mdim + first, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, h->stream));
+  GF2_CUDA(cudaStreamSynchronize(h->stream));
+  float ms = 0; cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
+  h->marg_ms = ms;
+  for (int i = 0; i < n; i++) { if (status) status[i] = h->h_marg[i]; if (m_dims) m_dims[i] = h->h_marg[B + i]; }
+  h->has_prior = true;   // windows outside [first, first + n) keep prior_rows = 0 from creation unless gf2_set_prior filled them
+  return GF2_OK;
+}
+
+int gf2_get_prior(gf2_solver* h, int first, int n, int32_t* n_rows, double* J0, double* r0, int32_t* n_blocks, gf2_prior_block* blocks) {
+  GF2_TRY(check_range(h, first, n));
+  const KP& k = h->kp;
+  D2H(n_rows, k.prior_rows + first, sizeof(int32_t) * n);
+  D2H(J0, k.prior_J0 + (size_t)first * k.Pr * k.Pr, sizeof(double) * n * k.Pr * k.Pr);
+  D2H(r0, k.prior_r0 + (size_t)first * k.Pr, sizeof(double) * n * k.Pr);
+  D2H(n_blocks, k.prior_nblocks + first, sizeof(int32_t) * n);
+  D2H(blocks, k.prior_blocks + (size_t)first * (2 * k.F + 8), sizeof(gf2_prior_block) * n * (2 * k.F + 8));
+  GF2_CUDA(cudaStreamSynchronize(h->stream));
+  return GF2_OK;
+}
+
+double gf2_last_marginalize_ms(gf2_solver* h) { return h ? h->marg_ms : 0.0; }
 
 int gf2_get_trace(gf2_solver* h, int first, int n, double* out) {
   GF2_TRY(check_range(h, first, n));

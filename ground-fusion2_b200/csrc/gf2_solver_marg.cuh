@@ -1,0 +1,539 @@
+// gf2_solver_marg.cuh — marginalization after the solve (the prior of the next window).
+//
+// Replaces MarginalizationInfo::addResidualBlockInfo / preMarginalize / marginalize / getParameterBlocks
+// (VE/factor/marginalization_factor.cpp:98-330) as driven by Estimator::optimization() (VE/estimator/estimator.cpp:3394-3595
+// MARGIN_OLD, :3597-3690 MARGIN_SECOND_NEW). One CTA per window.
+//
+//   k_marg_build   evaluates the factors that touch the dropped blocks at the current states (old prior, IMU factor 0, the
+//                  projection factors of the landmarks hosted in frame 0 with the Huber corrector of :46-77), assembles
+//                  A = sum J^T J, b = sum J^T r in shared memory and eliminates the dropped blocks: the landmarks one at a time
+//                  (each is a 1x1 diagonal block of Amm coupled to pose 0 only), then the frame-0 block by Cholesky.
+//                  This equals Arr - Arm pinv(Amm) Amr of :285-291 whenever no eigenvalue of Amm is below eps = 1e-8, which is
+//                  tested exactly (Amm - eps I positive definite <=> every v_l > eps and the eps-shifted 15x15 Schur
+//                  complement has a Cholesky factor). Windows that fail the test are reported (GF2_MARG_DEGENERATE) and
+//                  keep their old prior — see DESIGN.md.
+//   k_marg_eig     compacts the kept system to the blocks the factors touched, runs a cyclic Jacobi eigensolver in shared
+//                  memory (round-robin parallel ordering, n/2 disjoint rotations per step) and writes
+//                  linearized_jacobians = sqrt(S) V^T, linearized_residuals = sqrt(1/S) V^T b (:293-303, eps truncation)
+//                  plus the kept blocks renamed by addr_shift (:3561-3595 / :3653-3681) straight into the solver's prior
+//                  storage, so the next gf2_solve uses it without a host round trip.
+//
+// Block order: the reference iterates an unordered_map keyed by address, so its order is unspecified; here kept blocks are
+// ordered pose 0..F-2, speed-bias 0, ex-pose, td (new-window indices). The prior as a function of the states is the same.
+#pragma once
+#include "gf2_solver_kernels2.cuh"
+
+namespace gf2 {
+
+constexpr int kMargM = 15;                              // frame-0 part of the dropped set: pose 6 + speed-bias 9
+constexpr int kMargKMax = 6 * (kMaxF - 1) + 9 + 6 + 1;  // kept tangent dims, canonical: poses, sb0, ex-pose, td   (76)
+constexpr int kMargTMax = kMargM + kMargKMax;           // 91
+constexpr int kMargLD = kMargTMax | 1;                  // odd leading dimension: conflict-free column walks
+constexpr int kMargThreads = 256;
+constexpr int kMargBlocksMax = kMaxF + 3;               // kept blocks: F-1 poses, sb0, ex, td
+constexpr double kMargEps = 1e-8;                       // MarginalizationInfo::eps, VE/factor/marginalization_factor.h:83
+
+enum { GF2_MARG_OK_ = 0, GF2_MARG_INVALID_ = -1, GF2_MARG_UNCHANGED_ = -2, GF2_MARG_UNSUPPORTED_ = -3, GF2_MARG_DEGENERATE_ = -4, GF2_MARG_TOO_LARGE_ = -5 };
+
+struct MargP {
+  int mode;            // 0 MARGIN_OLD, 1 MARGIN_SECOND_NEW
+  double* A;           // [nW][kMargKMax][kMargKMax] kept system after elimination
+  double* b;           // [nW][kMargKMax]
+  int32_t* touched;    // [nW][kMargBlocksMax] kept block touched by a factor
+  int32_t* status;     // [nW]
+  int32_t* mdim;       // [nW] m (dropped tangent dims) for reporting
+  // outputs of k_marg_eig (may alias the solver's prior storage)
+  int32_t *out_rows, *out_nblocks;
+  double *out_J0, *out_r0;
+  gf2_prior_block* out_blocks;
+};
+
+struct MargShared {
+  FrameCtx fr[kMaxF];
+  CamCtx cam;
+  double b[kMargTMax];
+  double ww[kMargThreads / 32][kMargTMax];
+  double Z[kMargM][kMargKMax + 1];
+  double Y[kMargM][kMargM + 1];
+  double C6[6][6];
+  double dx[kP], pr[kP];
+  int cmap[kP];
+  int touched[kMargBlocksMax];
+  int mtouched[2];   // pose0 / sb0 (MARGIN_OLD) present in the problem
+  int n_lm0, bad, maxlen;
+};
+
+// kept-layout column of (kind, new index); -1 if the block cannot be kept in this build
+__device__ __forceinline__ int marg_kept_col(int F, int kind, int index) {
+  const int NP = 6 * (F - 1);
+  switch (kind) {
+    case GF2_BLK_POSE: return (index >= 0 && index < F - 1) ? 6 * index : -1;
+    case GF2_BLK_SPEEDBIAS: return index == 0 ? NP : -1;
+    case GF2_BLK_EX_POSE: return NP + 9;
+    case GF2_BLK_TD: return NP + 15;
+  }
+  return -1;
+}
+__device__ __forceinline__ int marg_kept_block(int F, int kind, int index) {  // slot in touched[]
+  switch (kind) {
+    case GF2_BLK_POSE: return index;
+    case GF2_BLK_SPEEDBIAS: return F - 1;
+    case GF2_BLK_EX_POSE: return F;
+    case GF2_BLK_TD: return F + 1;
+  }
+  return -1;
+}
+
+// Jacobians of one projection factor wrt the camera extrinsic (2x6) and td (2x1),
+// VE/factor/projectionTwoFrameOneCamFactor.cpp:125-146, expressed with the quantities obs_jacobians already has:
+//   reduce * ric^T (Rj^T Ri - I)                 = Jx Ri - B
+//   reduce * (-tmp_r [pc_i]x + [pc_j]x)          with reduce * tmp_r = Jx Ri ric =: Jc
+//   td: -Jc velocity_i / inv_dep + sqrt_info * velocity_j
+__device__ __forceinline__ void obs_jacobians_calib(const FrameCtx& fi, const CamCtx& cam, V3 pci, V3 pcj, double sqrt_info, const double (&Jx)[6],
+                                                    float4 oi, float4 oj, double inv_dep, double (&Jex)[12], double (&Jtd)[2]) {
+  const double iz = 1.0 / pcj.z;
+  const double a = sqrt_info * iz, bx = -sqrt_info * pcj.x * iz * iz, by = -sqrt_info * pcj.y * iz * iz;
+  double B[6];
+#pragma unroll
+  for (int c = 0; c < 3; c++) { B[c] = a * cam.ric[c * 3 + 0] + bx * cam.ric[c * 3 + 2]; B[3 + c] = a * cam.ric[c * 3 + 1] + by * cam.ric[c * 3 + 2]; }
+  double JR[6], Jc[6];
+#pragma unroll
+  for (int r = 0; r < 2; r++)
+#pragma unroll
+    for (int c = 0; c < 3; c++) JR[r * 3 + c] = Jx[r * 3] * fi.R[c] + Jx[r * 3 + 1] * fi.R[3 + c] + Jx[r * 3 + 2] * fi.R[6 + c];
+#pragma unroll
+  for (int r = 0; r < 2; r++)
+#pragma unroll
+    for (int c = 0; c < 3; c++) Jc[r * 3 + c] = JR[r * 3] * cam.ric[c] + JR[r * 3 + 1] * cam.ric[3 + c] + JR[r * 3 + 2] * cam.ric[6 + c];
+  const double red[6] = {a, 0.0, bx, 0.0, a, by};
+#pragma unroll
+  for (int r = 0; r < 2; r++) {
+    Jex[r * 6 + 0] = JR[r * 3 + 0] - B[r * 3 + 0]; Jex[r * 6 + 1] = JR[r * 3 + 1] - B[r * 3 + 1]; Jex[r * 6 + 2] = JR[r * 3 + 2] - B[r * 3 + 2];
+    // row * [p]x = (row_1 p_z - row_2 p_y, row_2 p_x - row_0 p_z, row_0 p_y - row_1 p_x)
+    const double c0 = Jc[r * 3], c1 = Jc[r * 3 + 1], c2 = Jc[r * 3 + 2];
+    const double d0 = red[r * 3], d1 = red[r * 3 + 1], d2 = red[r * 3 + 2];
+    Jex[r * 6 + 3] = -(c1 * pci.z - c2 * pci.y) + (d1 * pcj.z - d2 * pcj.y);
+    Jex[r * 6 + 4] = -(c2 * pci.x - c0 * pci.z) + (d2 * pcj.x - d0 * pcj.z);
+    Jex[r * 6 + 5] = -(c0 * pci.y - c1 * pci.x) + (d0 * pcj.y - d1 * pcj.x);
+  }
+  Jtd[0] = -(Jc[0] * (double)oi.z + Jc[1] * (double)oi.w) / inv_dep + sqrt_info * (double)oj.z;
+  Jtd[1] = -(Jc[3] * (double)oi.z + Jc[4] * (double)oi.w) / inv_dep + sqrt_info * (double)oj.w;
+}
+
+__global__ void __launch_bounds__(kMargThreads) k_marg_build(KP p, int w0, MargP mp) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  MargShared& s = *reinterpret_cast<MargShared*>(smem_raw);
+  double* A = reinterpret_cast<double*>(smem_raw + ((sizeof(MargShared) + 15) & ~size_t(15)));  // [kMargTMax][kMargLD], upper triangle accumulated
+  const int w = w0 + blockIdx.x;
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5, nw = blockDim.x >> 5;
+  const int F = p.F, NP = 6 * (F - 1), K = NP + 16, T = kMargM + K;
+  const double* pose = p.pose + (size_t)w * F * 7;
+  const double* sb = p.sb + (size_t)w * F * 9;
+  const int sn = F - 2;  // second-newest frame (WINDOW_SIZE - 1)
+
+  for (int i = t; i < kMargTMax * kMargLD; i += blockDim.x) A[i] = 0.0;
+  for (int i = t; i < kMargTMax; i += blockDim.x) s.b[i] = 0.0;
+  if (t < kMargBlocksMax) s.touched[t] = 0;
+  if (t < 36) (&s.C6[0][0])[t] = 0.0;
+  if (t == 0) { s.mtouched[0] = s.mtouched[1] = 0; s.n_lm0 = 0; s.bad = 0; s.maxlen = 0; }
+  build_frames(pose, p.ex + (size_t)w * 7, p.td[w], F, s.fr, &s.cam);
+  __syncthreads();
+
+  // ---- old prior: r = r0 + J0 dx at the current states; A += J0^T J0, b += J0^T r in the marginalization layout
+  const int n0 = p.prior_rows ? p.prior_rows[w] : 0;
+  if (n0 > 0) {
+    const gf2_prior_block* blk = p.prior_blocks + (size_t)w * (2 * F + 8);
+    const int nb = p.prior_nblocks[w];
+    if (t < nb) {
+      const gf2_prior_block& b = blk[t];
+      prior_block_dx(b, pose, sb, s.dx);
+      int col = -1, ls = (b.kind == GF2_BLK_POSE || b.kind == GF2_BLK_EX_POSE || b.kind == GF2_BLK_EX_WHEEL) ? 6 : (b.kind == GF2_BLK_SPEEDBIAS ? 9 : 1);
+      if (mp.mode == 0) {
+        if (b.kind == GF2_BLK_POSE && b.index == 0) { col = 0; s.mtouched[0] = 1; }
+        else if (b.kind == GF2_BLK_SPEEDBIAS && b.index == 0) { col = 6; s.mtouched[1] = 1; }
+        else {
+          const int ni = (b.kind == GF2_BLK_POSE || b.kind == GF2_BLK_SPEEDBIAS) ? b.index - 1 : b.index;
+          const int kc = marg_kept_col(F, b.kind, ni);
+          if (kc >= 0) { col = kMargM + kc; s.touched[marg_kept_block(F, b.kind, ni)] = 1; }
+        }
+      } else {
+        if (b.kind == GF2_BLK_POSE && b.index == sn) { col = 0; s.mtouched[0] = 1; }
+        else {
+          const int ni = (b.kind == GF2_BLK_POSE || b.kind == GF2_BLK_SPEEDBIAS) ? (b.index == F - 1 ? F - 2 : b.index) : b.index;
+          const int kc = (b.kind == GF2_BLK_SPEEDBIAS && b.index == sn) ? -1 : marg_kept_col(F, b.kind, ni);
+          if (kc >= 0) { col = kMargM + kc; s.touched[marg_kept_block(F, b.kind, ni)] = 1; }
+        }
+      }
+      if (col < 0) s.bad = 1;
+      for (int k = 0; k < ls; k++) s.cmap[b.offset + k] = col < 0 ? 0 : col + k;
+    }
+    __syncthreads();
+    const double* J0 = p.prior_J0 + (size_t)w * p.Pr * p.Pr;
+    const double* r0 = p.prior_r0 + (size_t)w * p.Pr;
+    if (t < n0) { double v = r0[t]; for (int c = 0; c < n0; c++) v += J0[t * p.Pr + c] * s.dx[c]; s.pr[t] = v; }
+    __syncthreads();
+    const double* H = p.prior_H + (size_t)w * p.Pr * p.Pr;  // J0^T J0 (k_prepare)
+    for (int e = t; e < n0 * n0; e += blockDim.x) {
+      const int a = e / n0, c = e % n0;
+      const int ia = s.cmap[a], ic = s.cmap[c];
+      if (ia <= ic) A[ia * kMargLD + ic] += H[a * p.Pr + c];   // cmap is injective: no two (a, c) share a target
+    }
+    if (t < n0) { double v = 0; for (int r = 0; r < n0; r++) v += J0[r * p.Pr + t] * s.pr[r]; s.b[s.cmap[t]] += v; }
+  }
+  __syncthreads();
+  if (mp.mode == 1 && !(n0 > 0 && s.mtouched[0])) {  // estimator.cpp:3599-3600: nothing to do, the old prior stays
+    if (t == 0) { mp.status[w] = GF2_MARG_UNCHANGED_; mp.mdim[w] = 0; }
+    return;
+  }
+
+  if (mp.mode == 0) {
+    // ---- IMU factor 0 (estimator.cpp:3416-3427): blocks pose0, sb0 dropped; pose1, sb1 kept as pose 0 / sb 0 of the next window
+    if (wid == 0 && p.imu) {
+      const gf2_imu_preint& pre = p.imu[(size_t)w * (F - 1)];
+      if (pre.valid && pre.sum_dt < 10.0) {
+        double* J = &s.Z[0][0];   // 15x30 + 15 scratch: Z is free until the elimination
+        double* r = J + 450;
+        static_assert(sizeof(s.Z) >= sizeof(double) * 465, "scratch");
+        if (lane == 0) { ImuStates s2 = load_imu_states(pose, sb, 0); imu_raw(pre, s2, p.g_norm, r, J); }
+        __syncwarp();
+        const double* sq = p.imu_sqrt + ((size_t)w * (F - 1)) * 225;
+        if (lane < 30) { for (int a = 0; a < 15; a++) { double acc = 0; for (int kk = a; kk < 15; kk++) acc += sq[a * 15 + kk] * J[kk * 30 + lane]; J[a * 30 + lane] = acc; } }
+        else if (lane == 30) { for (int a = 0; a < 15; a++) { double acc = 0; for (int kk = a; kk < 15; kk++) acc += sq[a * 15 + kk] * r[kk]; r[a] = acc; } }
+        __syncwarp();
+        // factor columns [pose_i 6 | sb_i 9 | pose_j 6 | sb_j 9] -> layout columns
+        for (int e = lane; e < 900; e += 32) {
+          const int a = e / 30, c = e % 30;
+          const int ia = a < 15 ? a : (a < 21 ? kMargM + (a - 15) : kMargM + NP + (a - 21));
+          const int ic = c < 15 ? c : (c < 21 ? kMargM + (c - 15) : kMargM + NP + (c - 21));
+          if (ia <= ic) { double acc = 0; for (int rr = 0; rr < 15; rr++) acc += J[rr * 30 + a] * J[rr * 30 + c]; A[ia * kMargLD + ic] += acc; }
+        }
+        if (lane < 30) {
+          const int a = lane; const int ia = a < 15 ? a : (a < 21 ? kMargM + (a - 15) : kMargM + NP + (a - 21));
+          double acc = 0; for (int rr = 0; rr < 15; rr++) acc += J[rr * 30 + a] * r[rr];
+          s.b[ia] += acc;
+        }
+        if (lane == 0) { s.mtouched[0] = s.mtouched[1] = 1; s.touched[0] = 1; s.touched[F - 1] = 1; }
+      }
+    }
+    __syncthreads();
+
+    // ---- projection factors of the landmarks hosted in frame 0 (estimator.cpp:3495-3528), one warp per landmark, one lane
+    //      per observation; the landmark (a 1x1 block of Amm) is eliminated as soon as its row is complete
+    const int nl = p.nlm[w];
+    const int32_t* start = p.start + (size_t)w * p.Lm;
+    const int32_t* tlen = p.tlen + (size_t)w * p.Lm;
+    const int32_t* obeg = p.obeg + (size_t)w * p.Lm;
+    const float4* obs = p.obs + (size_t)w * p.Om;
+    const double* ftd = p.frame_td + (size_t)w * F;
+    const int cEX = kMargM + NP + 9, cTD = kMargM + NP + 15;
+    double* wv = s.ww[wid];
+    for (int l = wid; l < nl; l += nw) {
+      if (start[l] != 0) continue;
+      const int len = tlen[l];
+      const float4 oi = obs[obeg[l]];
+      const double lam = p.invdep[(size_t)w * p.Lm + l];
+      LmCtx lc; landmark_ctx(s.fr[0], s.cam, oi, ftd[0], lam, lc);
+      const double dti = s.cam.td - ftd[0];
+      const V3 pci = mk3(((double)oi.x - dti * (double)oi.z) / lam, ((double)oi.y - dti * (double)oi.w) / lam, 1.0 / lam);
+      const int k = lane + 1;           // this lane's observation: frame k
+      const bool on = k < len;
+      double Jc13[2][13];               // common columns [pose0 6 | ex 6 | td 1]
+      double Jj[12], Jl[2], r[2];
+#pragma unroll
+      for (int i = 0; i < 13; i++) Jc13[0][i] = Jc13[1][i] = 0.0;
+#pragma unroll
+      for (int i = 0; i < 12; i++) Jj[i] = 0.0;
+      Jl[0] = Jl[1] = r[0] = r[1] = 0.0;
+      if (on) {
+        const float4 oj = obs[obeg[l] + k];
+        V3 pcj; double r0v, r1v;
+        obs_residual(s.fr[k], s.cam, lc, oj, ftd[k], p.sqrt_info_px, r0v, r1v, pcj);
+        double Jx[6];
+        obs_jacobians(s.fr[k], s.cam, lc, pcj, p.sqrt_info_px, Jx, Jj);
+        double Jex[12], Jtd[2];
+        obs_jacobians_calib(s.fr[0], s.cam, pci, pcj, p.sqrt_info_px, Jx, oi, oj, lam, Jex, Jtd);
+        double half_rho, scl; huber(p.huber, r0v * r0v + r1v * r1v, half_rho, scl);
+#pragma unroll
+        for (int rr = 0; rr < 2; rr++) {
+          const double jx0 = Jx[rr * 3], jx1 = Jx[rr * 3 + 1], jx2 = Jx[rr * 3 + 2];
+          Jc13[rr][0] = scl * jx0; Jc13[rr][1] = scl * jx1; Jc13[rr][2] = scl * jx2;
+#pragma unroll
+          for (int c = 0; c < 3; c++) Jc13[rr][3 + c] = scl * (jx0 * lc.Gi.m[c] + jx1 * lc.Gi.m[3 + c] + jx2 * lc.Gi.m[6 + c]);
+#pragma unroll
+          for (int c = 0; c < 6; c++) { Jc13[rr][6 + c] = scl * Jex[rr * 6 + c]; Jj[rr * 6 + c] *= scl; }
+          Jc13[rr][12] = scl * Jtd[rr];
+          Jl[rr] = scl * (jx0 * lc.dXdl.x + jx1 * lc.dXdl.y + jx2 * lc.dXdl.z);
+        }
+        r[0] = scl * r0v; r[1] = scl * r1v;
+      }
+      // landmark row: v, g_l, w over the touched columns
+      const double v = warp_sum(Jl[0] * Jl[0] + Jl[1] * Jl[1]);
+      const double gl = warp_sum(Jl[0] * r[0] + Jl[1] * r[1]);
+#pragma unroll
+      for (int i = 0; i < 13; i++) {
+        const double wi = warp_sum(Jc13[0][i] * Jl[0] + Jc13[1][i] * Jl[1]);
+        if (lane == 0) wv[i < 6 ? i : (i < 12 ? cEX + (i - 6) : cTD)] = wi;
+      }
+      if (on) {
+#pragma unroll
+        for (int c = 0; c < 6; c++) wv[kMargM + 6 * (k - 1) + c] = Jj[c] * Jl[0] + Jj[6 + c] * Jl[1];
+      }
+      // direct J^T J, J^T r: common x common (reduced over the lanes), common x pose_k and pose_k x pose_k (lane local)
+      {
+        int e = 0;
+#pragma unroll
+        for (int a = 0; a < 13; a++) {
+#pragma unroll
+          for (int c = a; c < 13; c++, e++) {
+            const double val = warp_sum(Jc13[0][a] * Jc13[0][c] + Jc13[1][a] * Jc13[1][c]);
+            if (lane == (e & 31)) {
+              const int ia = a < 6 ? a : (a < 12 ? cEX + (a - 6) : cTD), ic = c < 6 ? c : (c < 12 ? cEX + (c - 6) : cTD);
+              atomicAdd(&A[ia * kMargLD + ic], val);
+            }
+          }
+          const double gb = warp_sum(Jc13[0][a] * r[0] + Jc13[1][a] * r[1]);
+          if (lane == 0) atomicAdd(&s.b[a < 6 ? a : (a < 12 ? cEX + (a - 6) : cTD)], gb);
+        }
+      }
+      if (on) {
+        const int cj = kMargM + 6 * (k - 1);
+#pragma unroll
+        for (int a = 0; a < 13; a++) {
+          const int ia = a < 6 ? a : (a < 12 ? cEX + (a - 6) : cTD);
+#pragma unroll
+          for (int c = 0; c < 6; c++) {
+            const double val = Jc13[0][a] * Jj[c] + Jc13[1][a] * Jj[6 + c];
+            if (ia <= cj) atomicAdd(&A[ia * kMargLD + cj + c], val); else atomicAdd(&A[(cj + c) * kMargLD + ia], val);
+          }
+        }
+#pragma unroll
+        for (int a = 0; a < 6; a++) {
+#pragma unroll
+          for (int c = a; c < 6; c++) atomicAdd(&A[(cj + a) * kMargLD + cj + c], Jj[a] * Jj[c] + Jj[6 + a] * Jj[6 + c]);
+          atomicAdd(&s.b[cj + a], Jj[a] * r[0] + Jj[6 + a] * r[1]);
+        }
+      }
+      __syncwarp();
+      // eliminate the landmark: A -= w w^T / v, b -= w g_l / v over its columns {pose0, poses 1..len-1, ex, td}
+      if (!(v > kMargEps)) { if (lane == 0) s.bad = 2; }
+      else {
+        const double iv = 1.0 / v;
+        const int npose = 6 * (len - 1), nz = 13 + npose;
+        for (int e = lane; e < nz * nz; e += 32) {
+          const int a = e / nz, c = e % nz;
+          if (a > c) continue;
+          const int ia = a < 6 ? a : (a < 6 + npose ? kMargM + (a - 6) : (a < 12 + npose ? cEX + (a - 6 - npose) : cTD));
+          const int ic = c < 6 ? c : (c < 6 + npose ? kMargM + (c - 6) : (c < 12 + npose ? cEX + (c - 6 - npose) : cTD));
+          atomicAdd(&A[ia * kMargLD + ic], -wv[ia] * wv[ic] * iv);
+        }
+        for (int a = lane; a < nz; a += 32) {
+          const int ia = a < 6 ? a : (a < 6 + npose ? kMargM + (a - 6) : (a < 12 + npose ? cEX + (a - 6 - npose) : cTD));
+          atomicAdd(&s.b[ia], -wv[ia] * gl * iv);
+        }
+        // eps-shifted test matrix: Y_eps = Y - eps I - sum q q^T eps / (v (v - eps))
+        if (lane < 21) {
+          int a = 0, c = lane; while (c >= 6 - a) { c -= 6 - a; a++; } c += a;
+          atomicAdd(&s.C6[a][c], wv[a] * wv[c] * (kMargEps / (v * (v - kMargEps))));
+        }
+      }
+      if (lane == 0) { atomicAdd(&s.n_lm0, 1); atomicMax(&s.maxlen, len); }
+      __syncwarp();
+    }
+    __syncthreads();
+    if (t == 0 && s.n_lm0 > 0) { s.mtouched[0] = 1; s.touched[F] = 1; s.touched[F + 1] = 1; }
+    if (t >= 1 && t < s.maxlen) s.touched[t - 1] = 1;   // poses 1..maxlen-1 observed a frame-0 landmark -> new index t-1
+    __syncthreads();
+  }
+
+  // ---- symmetrise, then eliminate the frame-0 block (MARGIN_OLD: pose0 + sb0, MARGIN_SECOND_NEW: pose F-2)
+  for (int e = t; e < T * T; e += blockDim.x) { const int a = e / T, c = e % T; if (a > c) A[a * kMargLD + c] = A[c * kMargLD + a]; }
+  __syncthreads();
+  const int md = (mp.mode == 0 ? (s.mtouched[0] ? 6 : 0) + (s.mtouched[1] ? 9 : 0) : 6);
+  if (t == 0) {
+    int status = GF2_MARG_OK_;
+    if (s.bad == 1) status = GF2_MARG_UNSUPPORTED_;
+    else if (s.bad == 2) status = GF2_MARG_DEGENERATE_;
+    else if (md + s.n_lm0 == 0) status = GF2_MARG_INVALID_;
+    else {
+      // Cholesky of Y (the dropped frame block after the landmarks) and of its eps-shifted twin
+      for (int pass = 0; pass < 2 && status == GF2_MARG_OK_; pass++) {
+        for (int i = 0; i < kMargM; i++) for (int j = 0; j <= i; j++) {
+          const bool pi = mp.mode == 1 ? i < 6 : (i < 6 ? s.mtouched[0] : s.mtouched[1]) != 0;
+          const bool pj = mp.mode == 1 ? j < 6 : (j < 6 ? s.mtouched[0] : s.mtouched[1]) != 0;
+          double a = (pi && pj) ? A[i * kMargLD + j] : (i == j ? 1.0 : 0.0);   // absent dims: identity pivot, zero coupling
+          if (pass == 0 && pi && pj) { if (i == j) a -= kMargEps; if (i < 6) a -= s.C6[j][i]; }
+          s.Y[i][j] = a;
+        }
+        for (int j = 0; j < kMargM && status == GF2_MARG_OK_; j++) {
+          double d = s.Y[j][j]; for (int k = 0; k < j; k++) d -= s.Y[j][k] * s.Y[j][k];
+          if (!(d > 0.0)) { status = GF2_MARG_DEGENERATE_; break; }
+          d = sqrt(d); s.Y[j][j] = d;
+          for (int i = j + 1; i < kMargM; i++) { double v = s.Y[i][j]; for (int k = 0; k < j; k++) v -= s.Y[i][k] * s.Y[j][k]; s.Y[i][j] = v / d; }
+        }
+      }
+    }
+    mp.status[w] = status; mp.mdim[w] = md + s.n_lm0;
+    s.bad = status;
+  }
+  __syncthreads();
+  if (s.bad != GF2_MARG_OK_) return;
+  // Z = L^-1 [X | b_m], X = A[0:15, 15:T]; absent dropped dims have zero rows in X and an identity pivot
+  if (t <= K) {
+    double z[kMargM];
+    for (int i = 0; i < kMargM; i++) {
+      double v = (t < K) ? A[i * kMargLD + kMargM + t] : s.b[i];
+      for (int k = 0; k < i; k++) v -= s.Y[i][k] * z[k];
+      z[i] = v / s.Y[i][i];
+    }
+    for (int i = 0; i < kMargM; i++) s.Z[i][t] = z[i];
+  }
+  __syncthreads();
+  double* Ao = mp.A + (size_t)w * kMargKMax * kMargKMax;
+  for (int e = t; e < K * K; e += blockDim.x) {
+    const int a = e / K, c = e % K;
+    double v = A[(kMargM + a) * kMargLD + kMargM + c];
+    for (int k = 0; k < kMargM; k++) v -= s.Z[k][a] * s.Z[k][c];
+    Ao[a * kMargKMax + c] = v;
+  }
+  if (t < K) { double v = s.b[kMargM + t]; for (int k = 0; k < kMargM; k++) v -= s.Z[k][t] * s.Z[k][K]; mp.b[(size_t)w * kMargKMax + t] = v; }
+  if (t < kMargBlocksMax) mp.touched[(size_t)w * kMargBlocksMax + t] = s.touched[t];
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// Cyclic Jacobi (two-sided, round-robin parallel ordering) on an n x n symmetric matrix in shared memory; V accumulates
+// the rotations. Stand-in for Eigen::SelfAdjointEigenSolver at VE/factor/marginalization_factor.cpp:293.
+struct EigShared {
+  double c[kMargKMax / 2 + 1], s[kMargKMax / 2 + 1];
+  int pp[kMargKMax / 2 + 1], qq[kMargKMax / 2 + 1];
+  double red[2][kMargThreads / 32];
+  double bvec[kMargKMax];
+  int col[kMargKMax];          // compact column -> canonical kept column
+  int boff[kMargBlocksMax];    // compact offset of each kept block (-1 if absent)
+  int n, done;
+};
+
+__global__ void __launch_bounds__(kMargThreads) k_marg_eig(KP p, int w0, MargP mp) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  EigShared& s = *reinterpret_cast<EigShared*>(smem_raw);
+  double* A = reinterpret_cast<double*>(smem_raw + ((sizeof(EigShared) + 15) & ~size_t(15)));
+  constexpr int LD = kMargKMax | 1;
+  double* V = A + kMargKMax * LD;
+  const int w = w0 + blockIdx.x;
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5, nw = blockDim.x >> 5;
+  const int F = p.F, NP = 6 * (F - 1);
+  const int st = mp.status[w];
+  if (st == GF2_MARG_UNCHANGED_ || st == GF2_MARG_UNSUPPORTED_ || st == GF2_MARG_DEGENERATE_) return;   // old prior stays
+  if (st == GF2_MARG_INVALID_) { if (t == 0) { mp.out_rows[w] = 0; mp.out_nblocks[w] = 0; } return; }       // valid = false, :205-210
+  if (t == 0) {
+    int n = 0;
+    for (int b = 0; b < F + 2; b++) {
+      const int ls = b < F - 1 ? 6 : (b == F - 1 ? 9 : (b == F ? 6 : 1));
+      const int c0 = b < F - 1 ? 6 * b : (b == F - 1 ? NP : (b == F ? NP + 9 : NP + 15));
+      if (mp.touched[(size_t)w * kMargBlocksMax + b]) { s.boff[b] = n; for (int k = 0; k < ls; k++) s.col[n + k] = c0 + k; n += ls; }
+      else s.boff[b] = -1;
+    }
+    s.n = n; s.done = 0;
+  }
+  __syncthreads();
+  const int n = s.n;
+  if (n > p.Pr) { if (t == 0) mp.status[w] = GF2_MARG_TOO_LARGE_; return; }
+  const double* Ai = mp.A + (size_t)w * kMargKMax * kMargKMax;
+  for (int e = t; e < n * n; e += blockDim.x) { const int a = e / n, c = e % n; A[a * LD + c] = Ai[s.col[a] * kMargKMax + s.col[c]]; V[a * LD + c] = (a == c) ? 1.0 : 0.0; }
+  if (t < n) s.bvec[t] = mp.b[(size_t)w * kMargKMax + s.col[t]];
+  __syncthreads();
+  const int np = n + (n & 1), half = np / 2;
+  for (int sweep = 0; sweep < 60; sweep++) {
+    // convergence: off^2 <= 1e-32 * diag^2 (same test as the oracle's symEigen)
+    double off = 0, dg = 0;
+    for (int e = t; e < n * n; e += blockDim.x) { const int a = e / n, c = e % n; const double v = A[a * LD + c]; if (a == c) dg += v * v; else if (a < c) off += v * v; }
+    off = warp_sum(off); dg = warp_sum(dg);
+    if (lane == 0) { s.red[0][wid] = off; s.red[1][wid] = dg; }
+    __syncthreads();
+    if (t == 0) { double o = 0, d = 0; for (int i = 0; i < nw; i++) { o += s.red[0][i]; d += s.red[1][i]; } s.done = (o <= 1e-32 * (d + 1e-300)); }
+    __syncthreads();
+    if (s.done) break;
+    for (int step = 0; step < np - 1; step++) {
+      if (t < half) {
+        int a, b;
+        if (t == 0) { a = np - 1; b = step; }
+        else { a = (step + t) % (np - 1); b = (step - t + (np - 1)) % (np - 1); }
+        const int pi = a < b ? a : b, qi = a < b ? b : a;
+        double c = 1.0, sn = 0.0;
+        if (qi < n) {
+          const double apq = A[pi * LD + qi];
+          if (apq != 0.0) {
+            const double app = A[pi * LD + pi], aqq = A[qi * LD + qi];
+            const double tau = (aqq - app) / (2.0 * apq);
+            const double tt = (tau >= 0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+            c = 1.0 / sqrt(1.0 + tt * tt); sn = tt * c;
+          }
+        }
+        s.pp[t] = pi; s.qq[t] = qi < n ? qi : -1; s.c[t] = c; s.s[t] = sn;
+      }
+      __syncthreads();
+      for (int e = t; e < half * n; e += blockDim.x) {   // rows: A <- J^T A
+        const int k = e / n, j = e % n;
+        const int pi = s.pp[k], qi = s.qq[k];
+        if (qi < 0 || s.s[k] == 0.0) continue;
+        const double c = s.c[k], sn = s.s[k];
+        const double x = A[pi * LD + j], y = A[qi * LD + j];
+        A[pi * LD + j] = c * x - sn * y; A[qi * LD + j] = sn * x + c * y;
+      }
+      __syncthreads();
+      for (int e = t; e < half * n; e += blockDim.x) {   // columns: A <- A J, V <- V J
+        const int k = e / n, i = e % n;
+        const int pi = s.pp[k], qi = s.qq[k];
+        if (qi < 0 || s.s[k] == 0.0) continue;
+        const double c = s.c[k], sn = s.s[k];
+        const double x = A[i * LD + pi], y = A[i * LD + qi];
+        A[i * LD + pi] = c * x - sn * y; A[i * LD + qi] = sn * x + c * y;
+        const double vx = V[i * LD + pi], vy = V[i * LD + qi];
+        V[i * LD + pi] = c * vx - sn * vy; V[i * LD + qi] = sn * vx + c * vy;
+      }
+      __syncthreads();
+    }
+  }
+  // linearized_jacobians = sqrt(S) V^T, linearized_residuals = sqrt(1/S) V^T b with the eps truncation of :294-303
+  double* J0 = mp.out_J0 + (size_t)w * p.Pr * p.Pr;
+  double* r0 = mp.out_r0 + (size_t)w * p.Pr;
+  for (int e = t; e < n * n; e += blockDim.x) {
+    const int k = e / n, c = e % n;
+    const double S = A[k * LD + k];
+    J0[k * p.Pr + c] = S > kMargEps ? sqrt(S) * V[c * LD + k] : 0.0;
+  }
+  if (t < n) {
+    const double S = A[t * LD + t];
+    double vb = 0; for (int c = 0; c < n; c++) vb += V[c * LD + t] * s.bvec[c];
+    r0[t] = S > kMargEps ? sqrt(1.0 / S) * vb : 0.0;
+  }
+  // kept blocks renamed by addr_shift; keep_block_data = the states at marginalization time (preMarginalize, :119-138)
+  if (t < F + 2) {
+    const int b = t;
+    if (s.boff[b] >= 0) {
+      int slot = 0; for (int i = 0; i < b; i++) slot += (s.boff[i] >= 0);
+      gf2_prior_block& o = mp.out_blocks[(size_t)w * (2 * F + 8) + slot];
+      o.offset = s.boff[b]; o.pad_ = 0;
+      for (int k = 0; k < 9; k++) o.x0[k] = 0.0;
+      if (b < F - 1) {
+        const int old = mp.mode == 0 ? b + 1 : (b == F - 2 ? F - 1 : b);
+        o.kind = GF2_BLK_POSE; o.index = b;
+        for (int k = 0; k < 7; k++) o.x0[k] = p.pose[(size_t)w * F * 7 + 7 * old + k];
+      } else if (b == F - 1) {
+        const int old = mp.mode == 0 ? 1 : 0;
+        o.kind = GF2_BLK_SPEEDBIAS; o.index = 0;
+        for (int k = 0; k < 9; k++) o.x0[k] = p.sb[(size_t)w * F * 9 + 9 * old + k];
+      } else if (b == F) {
+        o.kind = GF2_BLK_EX_POSE; o.index = 0;
+        for (int k = 0; k < 7; k++) o.x0[k] = p.ex[(size_t)w * 7 + k];
+      } else {
+        o.kind = GF2_BLK_TD; o.index = 0; o.x0[0] = p.td[w];
+      }
+    }
+  }
+  if (t == 0) {
+    int nb = 0; for (int b = 0; b < F + 2; b++) nb += (s.boff[b] >= 0);
+    mp.out_rows[w] = n; mp.out_nblocks[w] = nb;
+  }
+}
+
+}  // namespace gf2

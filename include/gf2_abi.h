@@ -275,6 +275,27 @@ int gf2_get_wheel(gf2_solver* h, int first, int n, gf2_wheel_preint* preint);
 int gf2_set_prior(gf2_solver* h, int first, int n, const int32_t* n_rows, const double* J0, const double* r0,
                   const int32_t* n_blocks, const gf2_prior_block* blocks);
 
+/* Marginalization after the solve (MarginalizationInfo::preMarginalize / marginalize / getParameterBlocks,
+ * VE/factor/marginalization_factor.cpp:119-330, as driven by VE/estimator/estimator.cpp:3394-3690).
+ * Builds the prior of the NEXT window from what is resident on the device (states as gf2_solve left them, landmarks,
+ * IMU records, the current prior) and replaces the resident prior with it; its kept blocks are already renamed by
+ * addr_shift (frame f -> f-1 for GF2_MARGIN_OLD; newest -> second-newest for GF2_MARGIN_SECOND_NEW), so after
+ * slideWindow the caller uploads the new states / landmarks and solves. status [n] (may be NULL):
+ *   0 ok; GF2_MARG_INVALID: m == 0, prior cleared (valid = false, :205-210); GF2_MARG_UNCHANGED: SECOND_NEW without the
+ *   second-newest pose in the old prior (estimator.cpp:3599), old prior kept; GF2_MARG_UNSUPPORTED: the old prior holds a
+ *   block this build cannot keep; GF2_MARG_DEGENERATE: an eigenvalue of Amm is below eps = 1e-8 (the truncated
+ *   pseudo-inverse of :281 would differ from the inverse), old prior kept; GF2_MARG_TOO_LARGE: n > max_prior_rows.
+ * m_dims [n] (may be NULL): the number of marginalized tangent dimensions m. */
+enum { GF2_MARGIN_OLD = 0, GF2_MARGIN_SECOND_NEW = 1 };
+enum { GF2_MARG_INVALID = -1, GF2_MARG_UNCHANGED = -2, GF2_MARG_UNSUPPORTED = -3, GF2_MARG_DEGENERATE = -4, GF2_MARG_TOO_LARGE = -5 };
+int gf2_marginalize(gf2_solver* h, int first, int n, int32_t mode, const gf2_solve_opts* opts, int32_t* status,
+                    int32_t* m_dims);
+/* The resident prior (same layout as gf2_set_prior). */
+int gf2_get_prior(gf2_solver* h, int first, int n, int32_t* n_rows, double* J0, double* r0, int32_t* n_blocks,
+                  gf2_prior_block* blocks);
+/* Device time of the last gf2_marginalize (CUDA events on the handle's stream), ms. */
+double gf2_last_marginalize_ms(gf2_solver* h);
+
 /* LiDAR plane factors: n_planes [n], planes [n][max_planes] sorted or not by frame. */
 int gf2_set_planes(gf2_solver* h, int first, int n, const int32_t* n_planes, const gf2_plane* planes);
 

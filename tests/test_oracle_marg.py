@@ -31,9 +31,9 @@ def _huber_correct(res, jacs, delta=1.0):
     return res * scal, jacs
 
 
-def numpy_marginalize_old(w, i, oracle, abi, opts):
-    """MARGIN_OLD (estimator.cpp:3396-3595) in a canonical tangent layout; returns (H, g) over the layout of
-    gf2_oracle.prior_information of the window AFTER the slide, plus m."""
+def assemble_margin_old(w, i, oracle, opts):
+    """A = sum J^T J, b = sum J^T r of the MARGIN_OLD factors (estimator.cpp:3396-3528) in a canonical tangent layout:
+    returns (A, b, mm, rr, T): dropped columns mm, kept (touched) columns rr, T = size of the non-landmark layout."""
     F = w["n_frames"]
     T = 15 * F + 17
     base = {2: 15 * F, 3: 15 * F + 6, 4: 15 * F + 7, 5: 15 * F + 13, 6: 15 * F + 14, 7: 15 * F + 15, 8: 15 * F + 16}
@@ -91,7 +91,16 @@ def numpy_marginalize_old(w, i, oracle, abi, opts):
             res, jacs = _huber_correct(res, jacs, opts.huber_delta)
             add(res, jacs, [pose(0), pose(t), np.arange(base[2], base[2] + 6), np.array([T + k]), np.array([base[3]])])
     mm = np.concatenate([pose(0), sb(0), T + np.arange(len(lm0))])
+    mm = np.array([c for c in mm if touched[c]], dtype=int)
     rr = np.array([c for c in range(T) if touched[c] and c >= 15])
+    return A, b, mm, rr, T
+
+
+def numpy_marginalize_old(w, i, oracle, abi, opts):
+    """MARGIN_OLD (estimator.cpp:3396-3595): returns (H, g) over the layout of gf2_oracle.prior_information of the window
+    AFTER the slide, plus m."""
+    F = w["n_frames"]
+    A, b, mm, rr, T = assemble_margin_old(w, i, oracle, opts)
     Amm = 0.5 * (A[np.ix_(mm, mm)] + A[np.ix_(mm, mm)].T)
     ev, V = np.linalg.eigh(Amm)
     inv = np.where(ev > EPS, 1.0 / np.where(ev > EPS, ev, 1.0), 0.0)
