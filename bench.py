@@ -97,9 +97,9 @@ def host_threads():
         return os.cpu_count() or 1
 
 
-def make_batch(gf2, synth, B, distinct, first_window=0, pinned=True):
+def make_batch(gf2, synth, B, distinct, first_window=0, pinned=True, prior_stride=PRIOR_STRIDE):
     """B windows tiled from `distinct` generated ones, in pinned host arrays."""
-    base = synth.make_windows(distinct, n_landmarks=N_LM, first_window=first_window, prior_stride=PRIOR_STRIDE)
+    base = synth.make_windows(distinct, n_landmarks=N_LM, first_window=first_window, prior_stride=prior_stride)
     reps = (B + distinct - 1) // distinct
     w = {}
     for k, v in base.items():
@@ -162,6 +162,7 @@ def main():
     ap.add_argument("--e2e-chunks", type=int, default=4, help="chunks (handle + stream + host thread each) the e2e leg pipelines the batch over")
     ap.add_argument("--impl", default="gf2", choices=["gf2", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-marginalize", action="store_true", help="skip the marginalization leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "gf2" else args.warmup
     rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
@@ -282,6 +283,31 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * B * args.steps / float(te.item())
 
+    # ------------------------------------------------------------ marginalization leg, reported beside the metric
+    marg = None
+    if rank == 0 and not args.no_marginalize:
+        nm = min(B, 1024)
+        wm = make_batch(gf2, synth, nm, min(args.distinct, nm), pinned=False, prior_stride=80)
+        sm = gf2.Solver(nm, N_FRAMES, wm["max_landmarks"], wm["max_obs"], max_imu_samples=wm["n_imu_samples"], device=local, max_prior_rows=80)
+        sm.upload(wm, preintegrate="device")
+        sm.solve(opts, nm)
+        ms_m = []
+        for _ in range(4):
+            sm.set_prior(wm)                      # marginalization replaces the resident prior: put the anchor back
+            st_m, m_m = sm.marginalize(opts, abi.MARGIN_OLD, nm)
+            ms_m.append(sm.last_marginalize_ms())
+        marg = {"windows": nm, "ms": float(np.median(ms_m[1:])), "windows_per_s": nm / (float(np.median(ms_m[1:])) / 1e3), "ok_fraction": float((st_m == 0).mean()),
+                "m_dims": int(m_m[0]), "kept_dims": int(sm.get_prior(1)["prior_rows"][0]), "timing": "CUDA events on the handle's stream (k_prepare + k_marg_build + k_marg_eig)"}
+        if not args.no_cpu_baseline:
+            import gf2_oracle as orc
+            wc = synth.make_windows(4, n_landmarks=N_LM)
+            orc.imu_preintegrate(wc)
+            t0 = time.perf_counter()
+            for i in range(4):
+                orc.marginalize_window(wc, i, opts, mode=0)
+            marg["cpu_port_ms_per_window_1thread"] = 1e3 * (time.perf_counter() - t0) / 4
+        sm.close()
+
     if rank == 0:
         peaks, which = measured_peaks()
         n_lin = lin_launches * args.steps
@@ -301,6 +327,7 @@ def main():
             "roofline": {"bound": "hbm", "kernel": "k_linearize", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved / peaks["hbm_gbs"], "traffic": TRAFFIC_PER_WINDOW * B, "traffic_source": "ncu --set full capture of k_linearize, profiles/ (per window x windows per launch)", "peak_source": which,
                          "algorithmic_bytes_per_launch": BYTES_SWEEP * B, "avg_launch_ms": lin_avg_ms},
+            "marginalize": marg,
             "phase_ms_per_step": {"linearize": lin_ms / args.steps, "reduced_solve": solve_ms / args.steps, "backsub_candidate": step_ms / args.steps,
                                   "solve_total": total_ms / args.steps},
         }

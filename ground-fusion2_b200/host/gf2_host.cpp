@@ -307,6 +307,32 @@ void Estimator::optimization() {
   if (rc == GF2_OK) { rc = gf2_get_landmarks(gf2, 0, 1, invdep.data()); for (int i = 0; i < n_lm; i++) para_Feature[i][0] = invdep[i]; }
   if (rc != GF2_OK) { last_error = gf2_last_error(); return; }  // the reference logs and carries on (no exceptions)
   double2vector();
+
+  // ---- marginalization (estimator.cpp:3394-3690): runs at the states double2vector() left (yaw / position re-anchored),
+  // re-packed by vector2double() exactly as the reference does at :3399 / :3603
+  vector2double();
+  for (int i = 0; i < n_lm; i++) invdep[i] = para_Feature[i][0];
+  rc = gf2_set_states(gf2, 0, 1, &para_Pose[0][0], &para_SpeedBias[0][0], para_Ex_Pose[0], para_Td[0], nullptr, nullptr, nullptr);
+  if (rc == GF2_OK) rc = gf2_set_landmarks(gf2, 0, 1, &n_lm, invdep.data(), start.data(), len.data(), fixed.data(), obs.data(), frame_td.data());
+  int32_t st = 0, m = 0;
+  gf2_solve_opts o; memset(&o, 0, sizeof(o));
+  o.max_iterations = P.NUM_ITERATIONS; o.huber_delta = 1.0; o.sqrt_info_px = FOCAL_LENGTH / 1.5; o.g_norm = P.G_NORM; o.lidar_sqrt_info = 1.0;
+  o.const_mask = GF2_CONST_EX_POSE | GF2_CONST_TD | GF2_CONST_EX_WHEEL | GF2_CONST_WHEEL_INTRINSIC | GF2_CONST_TD_WHEEL;
+  if (rc == GF2_OK) rc = gf2_marginalize(gf2, 0, 1, marginalization_flag == MARGIN_OLD ? GF2_MARGIN_OLD : GF2_MARGIN_SECOND_NEW, &o, &st, &m);
+  if (rc != GF2_OK) { last_error = gf2_last_error(); return; }
+  last_marginalization_status = st;
+  if (st == GF2_MARG_INVALID) { last_marginalization_info = MarginalizationPrior(); }   // valid = false
+  else if (st == 0) {
+    int32_t rows = 0, nb = 0;
+    std::vector<double> J0((size_t)GF2_MAX_PRIOR_DIM * GF2_MAX_PRIOR_DIM), r0(GF2_MAX_PRIOR_DIM);
+    std::vector<gf2_prior_block> blocks(2 * F + 8);
+    rc = gf2_get_prior(gf2, 0, 1, &rows, J0.data(), r0.data(), &nb, blocks.data());
+    if (rc != GF2_OK) { last_error = gf2_last_error(); return; }
+    MarginalizationPrior& mp = last_marginalization_info;
+    mp.valid = true; mp.n = rows; mp.linearized_jacobians.resize((size_t)rows * rows); mp.linearized_residuals.assign(r0.begin(), r0.begin() + rows);
+    for (int r = 0; r < rows; r++) for (int c = 0; c < rows; c++) mp.linearized_jacobians[(size_t)r * rows + c] = J0[(size_t)r * GF2_MAX_PRIOR_DIM + c];
+    mp.blocks.assign(blocks.begin(), blocks.begin() + nb);
+  }  // GF2_MARG_UNCHANGED / DEGENERATE / UNSUPPORTED: the previous prior stays (block indices untouched, as at :3599)
 }
 
 // ------------------------------------------------------------------------------------------------ FeatureTracker
@@ -502,6 +528,19 @@ void gf2h_double2vector(void* e, const double* pose, const double* sb, int n_fea
   Estimator* E = (Estimator*)e; memcpy(E->para_Pose, pose, sizeof(E->para_Pose)); memcpy(E->para_SpeedBias, sb, sizeof(E->para_SpeedBias));
   for (int i = 0; i < n_feat; i++) E->para_Feature[i][0] = feat[i];
   E->double2vector();
+}
+void gf2h_set_marginalization_flag(void* e, int flag) { ((Estimator*)e)->marginalization_flag = flag ? Estimator::MARGIN_SECOND_NEW : Estimator::MARGIN_OLD; }
+int gf2h_get_prior(void* e, int* n, double* J0 /* n*n */, double* r0, int* nblocks, gf2_prior_block* blocks, int* status) {
+  Estimator* E = (Estimator*)e; const MarginalizationPrior& mp = E->last_marginalization_info;
+  *n = mp.valid ? mp.n : 0; *nblocks = (int)mp.blocks.size(); *status = E->last_marginalization_status;
+  for (size_t i = 0; i < mp.linearized_jacobians.size(); i++) J0[i] = mp.linearized_jacobians[i];
+  for (size_t i = 0; i < mp.linearized_residuals.size(); i++) r0[i] = mp.linearized_residuals[i];
+  for (size_t i = 0; i < mp.blocks.size(); i++) blocks[i] = mp.blocks[i];
+  return mp.valid ? 1 : 0;
+}
+void gf2h_get_para(void* e, double* pose /*11x7*/, double* sb /*11x9*/, double* feat /*NUM_OF_F*/) {
+  Estimator* E = (Estimator*)e; memcpy(pose, E->para_Pose, sizeof(E->para_Pose)); memcpy(sb, E->para_SpeedBias, sizeof(E->para_SpeedBias));
+  for (int i = 0; i < NUM_OF_F; i++) feat[i] = E->para_Feature[i][0];
 }
 int gf2h_optimization(void* e, gf2_solve_summary* s) { Estimator* E = (Estimator*)e; E->optimization(); if (s) *s = E->last_summary; return E->lastError()[0] ? -1 : 0; }
 const char* gf2h_last_error(void* e) { return ((Estimator*)e)->lastError(); }

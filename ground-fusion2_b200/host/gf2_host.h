@@ -114,7 +114,11 @@ class Estimator {
   void clearState();
   void vector2double();   // estimator.cpp:2337-2414
   void double2vector();   // estimator.cpp:2501-2630 (yaw / position re-anchoring to frame 0, setDepth)
-  void optimization();    // estimator.cpp:2951-3392: the ceres::Problem build + ceres::Solve, through gf2_solve
+  void optimization();    // estimator.cpp:2951-3693: the ceres::Problem build + ceres::Solve (gf2_solve), then the
+                          // marginalization of the oldest / second-newest frame (gf2_marginalize) into last_marginalization_info
+  enum MarginalizationFlag { MARGIN_OLD = 0, MARGIN_SECOND_NEW = 1 };  // estimator.h:60-64
+  MarginalizationFlag marginalization_flag = MARGIN_OLD;
+  int last_marginalization_status = 0;   // gf2_marginalize status of the last optimization()
   const char* lastError() const { return last_error.c_str(); }
 
   Parameters P;

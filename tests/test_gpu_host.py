@@ -86,6 +86,24 @@ def test_estimator_optimization_end_to_end(gf2, oracle):
     assert ids.tolist() == list(range(nl))
     assert np.abs(1.0 / dep - wo["inv_depth"][0, :nl]).max() < 1e-3 * np.abs(wo["inv_depth"]).max()
     assert ((flg == 1) | (flg == 2)).all()
+    # marginalization ran inside optimization() (MARGIN_OLD) at the re-anchored states: compare with the oracle at the
+    # para_* arrays the estimator holds (vector2double after double2vector, estimator.cpp:3399)
+    pose = np.zeros((11, 7)); sbv = np.zeros((11, 9)); feat = np.zeros(1000)
+    L.gf2h_get_para(e, H.p(pose), H.p(sbv), H.p(feat))
+    nn = C.c_int(0); nb = C.c_int(0); stt = C.c_int(0)
+    J0 = np.zeros(96 * 96); r0 = np.zeros(96); blocks = np.zeros(30, gf2.abi.PRIOR_BLOCK)
+    assert L.gf2h_get_prior(e, C.byref(nn), H.p(J0), H.p(r0), C.byref(nb), H.p(blocks), C.byref(stt)) == 1 and stt.value == 0
+    got = {"n": nn.value, "J0": J0[:nn.value ** 2].reshape(nn.value, nn.value), "r0": r0[:nn.value], "blocks": blocks[:nb.value]}
+    wm = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in w.items()}
+    wm["para_pose"][0] = pose; wm["para_speedbias"][0] = sbv; wm["inv_depth"][0, :nl] = feat[:nl]
+    ref = oracle.marginalize_window(wm, 0, gf2.abi.default_opts(), mode=0)
+    assert ref["status"] == 0 and ref["n"] == got["n"]
+    Hg, gg, xg = oracle.prior_information(got, 11); Hr, gr, xr = oracle.prior_information(ref, 11)
+    assert np.abs(Hg - Hr).max() <= 1e-8 * np.abs(Hr).max()
+    d = np.sqrt(np.diag(Hr)); nz = d > 0
+    assert (np.abs(gg - gr)[nz] / d[nz]).max() <= 5e-6
+    for key in xr:
+        assert np.array_equal(xg[key], xr[key])
     L.gf2h_estimator_destroy(e)
 
 
