@@ -95,7 +95,8 @@ def test_estimator_optimization_end_to_end(gf2, oracle):
     assert L.gf2h_get_prior(e, C.byref(nn), H.p(J0), H.p(r0), C.byref(nb), H.p(blocks), C.byref(stt)) == 1 and stt.value == 0
     got = {"n": nn.value, "J0": J0[:nn.value ** 2].reshape(nn.value, nn.value), "r0": r0[:nn.value], "blocks": blocks[:nb.value]}
     wm = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in w.items()}
-    wm["para_pose"][0] = pose; wm["para_speedbias"][0] = sbv; wm["inv_depth"][0, :nl] = feat[:nl]
+    exv = np.zeros(7); L.gf2h_vector2double(e, H.p(pose), H.p(sbv), H.p(exv))   # para_Ex_Pose as the estimator packs it (ric -> quaternion)
+    wm["para_pose"][0] = pose; wm["para_speedbias"][0] = sbv; wm["inv_depth"][0, :nl] = feat[:nl]; wm["ex_pose"][0] = exv
     ref = oracle.marginalize_window(wm, 0, gf2.abi.default_opts(), mode=0)
     assert ref["status"] == 0 and ref["n"] == got["n"]
     Hg, gg, xg = oracle.prior_information(got, 11); Hr, gr, xr = oracle.prior_information(ref, 11)
