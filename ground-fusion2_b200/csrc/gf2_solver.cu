@@ -737,7 +737,7 @@ int gf2_marginalize(gf2_solver* h, int first, int n, int32_t mode, const gf2_sol
   cudaEventRecord(h->ev[0], h->stream);
   k_prepare<<<n, 128, sizeof(double) * 450 * GF2_MAX_FRAMES, h->stream>>>(k, first);   // IMU sqrt_info, J0^T J0 of the old prior
   k_marg_build<<<n, kMargThreads, sh_build, h->stream>>>(k, first, mp);
-  k_marg_eig<<<n, kMargThreads, sh_eig, h->stream>>>(k, first, mp);
+  k_marg_eig<<<n, kEigThreads, sh_eig, h->stream>>>(k, first, mp);
   cudaEventRecord(h->ev[1], h->stream);
   GF2_CUDA(cudaGetLastError());
   GF2_CUDA(cudaMemcpyAsync(h->h_marg, mp.status + first, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, h->stream));
