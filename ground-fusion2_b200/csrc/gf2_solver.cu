@@ -346,7 +346,7 @@ int gf2_solver_create(const gf2_solver_cfg* cfg, gf2_solver** out) {
   cudaHostAlloc((void**)&h->h_state, sizeof(WinState) * B, cudaHostAllocDefault);
   // opt in to large dynamic shared memory
   cudaFuncSetAttribute(k_linearize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LinShared));
-  cudaFuncSetAttribute(k_solve2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(Solve2Shared) + sizeof(double) * (F * (F + 1) / 2) * kBlk));
+  cudaFuncSetAttribute(k_solve2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(Solve2Shared) + sizeof(double) * solve2_matrix_doubles(F)));
   cudaFuncSetAttribute(k_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * 450 * GF2_MAX_FRAMES));
   if (cudaGetLastError() != cudaSuccess) { gf2_solver_destroy(h); return gf2::fail(GF2_ERR_CUDA, "cudaFuncSetAttribute failed (is this an sm_100a device?)"); }
   *out = h;
@@ -537,6 +537,12 @@ int gf2_set_prior(gf2_solver* h, int first, int n, const int32_t* n_rows, const 
   if (!n_rows) { h->has_prior = false; return GF2_OK; }
   for (int w = 0; w < n; w++) {
     if (n_rows[w] < 0 || n_rows[w] > k.Pr) return gf2::fail(GF2_ERR_INVALID, "prior of window %d has %d rows (max %d)", first + w, n_rows[w], k.Pr);
+    // k_solve2 stores the speed-bias rows of frame I only against frames I-1 and I (structural zeros of S and of its Cholesky
+    // factor): a prior that couples speed-bias k >= 2 to far frames would break that; the reference's priors keep speed-bias 0 only
+    if (blocks && n_blocks) for (int b = 0; b < n_blocks[w]; b++) {
+      const gf2_prior_block& pb = blocks[(size_t)w * (2 * k.F + 8) + b];
+      if (pb.kind == GF2_BLK_SPEEDBIAS && pb.index >= 2) return gf2::fail(GF2_ERR_UNSUPPORTED, "prior of window %d keeps speed-bias %d (only 0 and 1 are supported)", first + w, pb.index);
+    }
     if (n_rows[w] > 0 && (n_blocks[w] < 1 || n_blocks[w] > 2 * k.F + 8)) return gf2::fail(GF2_ERR_INVALID, "prior of window %d has %d blocks", first + w, n_blocks[w]);
   }
   H2D(k.prior_rows + first, n_rows, sizeof(int32_t) * n);
@@ -594,7 +600,7 @@ static int run(gf2_solver* h, int first, int n, const gf2_solve_opts* opts, gf2_
   GF2_TRY(fill_kp(h, opts, k));
   const int D = h->D;
   const size_t sh_lin = sizeof(LinShared);
-  const size_t sh_solve = sizeof(Solve2Shared) + sizeof(double) * (k.F * (k.F + 1) / 2) * kBlk;
+  const size_t sh_solve = sizeof(Solve2Shared) + sizeof(double) * solve2_matrix_doubles(k.F);
   double initial_radius = opts->initial_radius > 0 ? opts->initial_radius : 1e4;
   int ne = 0;
   cudaEventRecord(h->ev[ne++], h->stream);

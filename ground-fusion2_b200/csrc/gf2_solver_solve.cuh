@@ -106,53 +106,66 @@ __global__ void __launch_bounds__(kNonvisThreads) k_nonvis(KP p, int w0) {
 }
 
 // ------------------------------------------------------------------------------------------------ k_solve2
+// Storage of the reduced camera matrix / its Cholesky factor in shared memory. In frame-major order [pose 6 | speed-bias 9]
+// the speed-bias rows of frame I are structurally zero against every frame J <= I - 2 — in S (an IMU factor links
+// adjacent frames only) and in L (eliminating frame J connects its later neighbours: every later pose and the speed-bias of
+// frame J + 1, nothing further). So blocks (I, J) with I - J >= 2 ("far") keep only their 6 pose rows. 15 x 20 doubles for a
+// near block, 6 x 20 for a far one: 21 * 300 + 45 * 120 = 11,700 doubles instead of 66 * 320 = 21,120, which lets two
+// windows share one SM (the kernel is a chain of short dependent phases; a second resident CTA fills the bubbles).
+constexpr int kNearBlk = 15 * kBS, kFarBlk = 6 * kBS;
+
 struct Solve2Shared {
   double g[kMaxF * 16], gs[kMaxF * 16], Hd[kMaxF * 16], s[kMaxF * 16], e[kMaxF * 16], u[kMaxF * 16], z[kMaxF * 16];
+  double yu[kMaxF * 16], fw[kMaxF * 16];  // L^T u and the forward-substitution result (= L^T z)
   double red[8 * 32];
+  double dinv[kMaxF * 16];  // reciprocal diagonal of every factored diagonal block
+  int boff[kMaxF * kMaxF];  // offset of block (I, J), J <= I
+  int blin[kMaxF * (kMaxF + 1) / 2];  // offset of block number I (I + 1) / 2 + J (the order k_linearize writes Svis in)
   int flag;
   int pad_;
-  double dinv[kMaxF * 16];  // reciprocal diagonal of every factored diagonal block
-  double Linv[kMaxF * kBlk];
-  double A[1];  // F(F+1)/2 blocks of kBlk doubles (dynamic tail)
+  double A[1];  // dynamic tail
 };
 
-__device__ __forceinline__ double& Ael(double* A, int i, int j) {  // element (i, j), j <= i, global tangent indices
-  const int I = i / 15, J = j / 15;
-  return A[bidx(I, J) + (i - 15 * I) * kBS + (j - 15 * J)];
-}
+__host__ __device__ __forceinline__ int solve2_matrix_doubles(int F) { return (2 * F - 1) * kNearBlk + ((F - 1) * (F - 2) / 2) * kFarBlk; }
+__device__ __forceinline__ int brows(int I, int J) { return (I - J >= 2) ? 6 : 15; }
 
-// C(16x16 block at c) += sign * X(16x16 at x) * Y(16x16 at y)^T over k = 0..15, one warp, results kept in registers and
-// written back after all reads (c may alias x).
-__device__ __forceinline__ void block_mma(double* c, const double* x, const double* y, bool accumulate_c, double sign, int lane) {
+// C (rc rows) -= X (rx rows) * Y (ry rows)^T over k = 0..15 on the fp64 tensor cores, one warp; rows beyond a block's own
+// are never read (predicated to zero) or written. c may alias x.
+__device__ __forceinline__ void block_mma(double* c, const double* x, const double* y, int rc, int rx, int ry, int lane) {
   const int r = lane >> 2, q = lane & 3;
+  const int rmin = rc < rx ? rc : rx;
+  const bool m1 = rmin > 8, n1 = ry > 8;
   double acc[2][2][2];
 #pragma unroll
   for (int mt = 0; mt < 2; mt++)
 #pragma unroll
     for (int nt = 0; nt < 2; nt++) {
-      if (accumulate_c) { acc[mt][nt][0] = c[(8 * mt + r) * kBS + 8 * nt + 2 * q]; acc[mt][nt][1] = c[(8 * mt + r) * kBS + 8 * nt + 2 * q + 1]; }
-      else { acc[mt][nt][0] = 0.0; acc[mt][nt][1] = 0.0; }
+      const bool ok = (8 * mt + r) < rc && (mt == 0 || m1) && (nt == 0 || n1);
+      acc[mt][nt][0] = ok ? c[(8 * mt + r) * kBS + 8 * nt + 2 * q] : 0.0;
+      acc[mt][nt][1] = ok ? c[(8 * mt + r) * kBS + 8 * nt + 2 * q + 1] : 0.0;
     }
 #pragma unroll
   for (int ks = 0; ks < 4; ks++) {
     double a[2], b[2];
-#pragma unroll
-    for (int mt = 0; mt < 2; mt++) a[mt] = sign * x[(8 * mt + r) * kBS + 4 * ks + q];
-#pragma unroll
-    for (int nt = 0; nt < 2; nt++) b[nt] = y[(8 * nt + r) * kBS + 4 * ks + q];
-#pragma unroll
-    for (int mt = 0; mt < 2; mt++)
-#pragma unroll
-      for (int nt = 0; nt < 2; nt++) mma_f64(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+    a[0] = (r < rx) ? -x[r * kBS + 4 * ks + q] : 0.0;
+    a[1] = (m1 && 8 + r < rx) ? -x[(8 + r) * kBS + 4 * ks + q] : 0.0;
+    b[0] = (r < ry) ? y[r * kBS + 4 * ks + q] : 0.0;
+    b[1] = (n1 && 8 + r < ry) ? y[(8 + r) * kBS + 4 * ks + q] : 0.0;
+    mma_f64(acc[0][0][0], acc[0][0][1], a[0], b[0]);
+    if (n1) mma_f64(acc[0][1][0], acc[0][1][1], a[0], b[1]);
+    if (m1) { mma_f64(acc[1][0][0], acc[1][0][1], a[1], b[0]); if (n1) mma_f64(acc[1][1][0], acc[1][1][1], a[1], b[1]); }
   }
   __syncwarp();
 #pragma unroll
   for (int mt = 0; mt < 2; mt++)
 #pragma unroll
-    for (int nt = 0; nt < 2; nt++) { c[(8 * mt + r) * kBS + 8 * nt + 2 * q] = acc[mt][nt][0]; c[(8 * mt + r) * kBS + 8 * nt + 2 * q + 1] = acc[mt][nt][1]; }
+    for (int nt = 0; nt < 2; nt++) {
+      const bool ok = (8 * mt + r) < rc && (mt == 0 || m1) && (nt == 0 || n1);
+      if (ok) { c[(8 * mt + r) * kBS + 8 * nt + 2 * q] = acc[mt][nt][0]; c[(8 * mt + r) * kBS + 8 * nt + 2 * q + 1] = acc[mt][nt][1]; }
+    }
 }
 
-__global__ void __launch_bounds__(kSolveThreads, 1) k_solve2(KP p, int w0) {
+__global__ void __launch_bounds__(kSolveThreads, 2) k_solve2(KP p, int w0) {
   const int w = w0 + blockIdx.x;
   WinState& st = p.st[w];
   if (!st.active || st.reuse) return;
@@ -161,15 +174,28 @@ __global__ void __launch_bounds__(kSolveThreads, 1) k_solve2(KP p, int w0) {
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5, nt = blockDim.x, nwarp = nt >> 5;
   const int F = p.F, D = p.D, NV = 6 * F;
   const int NB = F * (F + 1) / 2;
+  const int NA = solve2_matrix_doubles(F);
   double* A = S.A;
-  for (int i = t; i < NB * kBlk; i += nt) A[i] = 0.0;
+  if (t < NB) {  // block offsets, row-major over the lower triangle
+    int I = 0; while ((I + 1) * (I + 2) / 2 <= t) I++;
+    const int J = t - I * (I + 1) / 2;
+    int off = 0;
+    for (int i = 0; i < I; i++) off += (i >= 2 ? (i - 1) * kFarBlk : 0) + (i >= 1 ? 2 : 1) * kNearBlk;
+    off += (J <= I - 2) ? J * kFarBlk : ((I >= 2 ? (I - 1) * kFarBlk : 0) + (J - (I >= 1 ? I - 1 : 0)) * kNearBlk);
+    S.boff[I * kMaxF + J] = off; S.blin[t] = off;
+  }
+  for (int i = t; i < NA; i += nt) A[i] = 0.0;
   for (int i = t; i < F * 16; i += nt) { S.g[i] = 0.0; S.gs[i] = 0.0; S.Hd[i] = 0.0; S.z[i] = 0.0; S.u[i] = 0.0; }
   __syncthreads();
+  auto bidx2 = [&](int I, int J) -> int { return S.boff[I * kMaxF + J]; };
+  // element (i, j), j <= i, global tangent indices; rows a far block does not store read as zero / are never written
+  auto stored = [&](int i, int j) -> bool { const int I = i / 15, J = j / 15; return (I - J < 2) || (i - 15 * I) < 6; };
+  auto Ael2 = [&](int i, int j) -> double& { const int I = i / 15, J = j / 15; return A[bidx2(I, J) + (i - 15 * I) * kBS + (j - 15 * J)]; };
   // ---- assembly: visual Schur complement (blocked 6x6 layout written by k_linearize: coalesced read, pose part of each block)
   const double* Svis = p.Svis + (size_t)w * kNVMax * kNVMax;
   for (int idx = t; idx < NB * 36; idx += nt) {
     const int blk = idx / 36, e = idx % 36;
-    A[blk * kBlk + (e / 6) * kBS + e % 6] = Svis[idx];
+    A[S.blin[blk] + (e / 6) * kBS + e % 6] = Svis[idx];
   }
   if (t < NV) { const int da = 15 * (t / 6) + t % 6; S.g[da] = p.gvis[(size_t)w * kNVP + t]; S.gs[da] = p.gschur[(size_t)w * kNVP + t]; S.Hd[da] = p.Udiag[(size_t)w * kNVMax + t]; }
   __syncthreads();
@@ -183,7 +209,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) k_solve2(KP p, int w0) {
       const int a = idx / n, b = idx % n;
       const int ma = map[a], mb = map[b];
       if (ma < 0 || mb < 0 || mb > ma) continue;
-      Ael(A, ma, mb) += H[a * p.Pr + b];
+      if (stored(ma, mb)) Ael2(ma, mb) += H[a * p.Pr + b];   // gf2_set_prior rejects priors that would put mass elsewhere
     }
     __syncthreads();
   }
@@ -198,11 +224,11 @@ __global__ void __launch_bounds__(kSolveThreads, 1) k_solve2(KP p, int w0) {
         double v = 0.0;
         if (K > 0) v += Hw[(K - 1) * 675 + 450 + e];
         if (K < F - 1) v += Hw[K * 675 + e];
-        if (c <= r) A[bidx(K, K) + r * kBS + c] += v;
+        if (c <= r) A[bidx2(K, K) + r * kBS + c] += v;
         if (r == c) S.Hd[15 * K + r] += v;
       } else {
         const int K = idx / 225 - F;
-        A[bidx(K + 1, K) + r * kBS + c] += Hw[K * 675 + 225 + e];
+        A[bidx2(K + 1, K) + r * kBS + c] += Hw[K * 675 + 225 + e];
       }
     }
     for (int i = t; i < D; i += nt) {
@@ -224,11 +250,11 @@ __global__ void __launch_bounds__(kSolveThreads, 1) k_solve2(KP p, int w0) {
         double v = 0.0;
         if (K > 0) v += Hw[(K - 1) * 108 + 72 + e];
         if (K < F - 1) v += Hw[K * 108 + e];
-        if (c <= r) A[bidx(K, K) + r * kBS + c] += v;
+        if (c <= r) A[bidx2(K, K) + r * kBS + c] += v;
         if (r == c) S.Hd[15 * K + r] += v;
       } else {
         const int K = idx / 36 - F;
-        A[bidx(K + 1, K) + r * kBS + c] += Hw[K * 108 + 36 + e];
+        A[bidx2(K + 1, K) + r * kBS + c] += Hw[K * 108 + 36 + e];
       }
     }
     for (int i = t; i < 6 * F; i += nt) {
@@ -243,12 +269,15 @@ __global__ void __launch_bounds__(kSolveThreads, 1) k_solve2(KP p, int w0) {
   if (t == 0) { st.cost_vis = p.c_lin[(size_t)w * 4]; st.gmax_l = p.c_gmax[w]; st.x_cost = st.cost_vis + p.cost_nv[w]; if (st.iteration == 0) st.initial_cost = st.x_cost; }
   if (p.Sfull) {
     double* Sf = p.Sfull + (size_t)w * D * D;
-    for (int idx = t; idx < D * D; idx += nt) { const int a = idx / D, b = idx % D; Sf[idx] = a >= b ? Ael(A, a, b) : Ael(A, b, a); }
+    for (int idx = t; idx < D * D; idx += nt) {
+      const int a = idx / D, b = idx % D; const int hi = a >= b ? a : b, lo = a >= b ? b : a;
+      Sf[idx] = stored(hi, lo) ? Ael2(hi, lo) : 0.0;
+    }
     for (int i = t; i < D; i += nt) p.gfull[(size_t)w * D + i] = S.g[i] - S.gs[i];  // reduced gradient (rhs)
   }
   // ---- Jacobi scaling (iteration 0), dogleg diagonal, gradient quantities
   const double mu = st.mu;
-  double sums[3] = {0, 0, 0};  // dlg2, uEu, uSu
+  double sums[3] = {0, 0, 0};  // dlg2, uEu, -
   double gmax = 0.0;
   for (int i = t; i < D; i += nt) {
     double sc;
@@ -268,7 +297,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) k_solve2(KP p, int w0) {
     for (int k = 6; k < 15; k++) gmax = fmax(gmax, fabs(gg[k]));
   }
   __syncthreads();
-  for (int i = t; i < D; i += nt) Ael(A, i, i) += mu * S.e[i];
+  for (int i = t; i < D; i += nt) Ael2(i, i) += mu * S.e[i];
   __syncthreads();
   block_sum<3>(sums, S.red);
   gmax = warp_max(gmax);
@@ -283,10 +312,10 @@ __global__ void __launch_bounds__(kSolveThreads, 1) k_solve2(KP p, int w0) {
   __syncthreads();
   if (S.flag == 2) return;
 
-  // ---- blocked Cholesky (right-looking over 15x15 frame blocks) with one-step look-ahead: warp 0 factors diagonal block
+  // ---- blocked Cholesky (right-looking over the frame blocks) with one-step look-ahead: warp 0 factors diagonal block
   // K+1 as soon as its own trailing pair (K+1, K+1) is done, while warps 1..7 finish the rest of trailing update K
   auto factor_diag = [&](int K) {  // executed by warp 0; lane = row, the row lives in registers
-    double* Akk = A + bidx(K, K);
+    double* Akk = A + bidx2(K, K);
     double a[15];
 #pragma unroll
     for (int c = 0; c < 15; c++) a[c] = (lane < 15 && c <= lane) ? Akk[lane * kBS + c] : 0.0;
@@ -311,10 +340,12 @@ __global__ void __launch_bounds__(kSolveThreads, 1) k_solve2(KP p, int w0) {
   if (wid == 0) factor_diag(0);
   __syncthreads();
   for (int K = 0; K < F && !S.flag; K++) {
-    const double* Akk = A + bidx(K, K);
-    // panel: X L_KK^T = A_IK, one thread per row of the block column (substitution over the 15 columns)
-    if (t < 15 * (F - 1 - K)) {
-      double* row = A + bidx(K + 1 + t / 15, K) + (t % 15) * kBS;
+    const double* Akk = A + bidx2(K, K);
+    // panel: X L_KK^T = A_IK, one thread per stored row of the block column (15 rows of the near block, 6 of each far one)
+    const int prow = (K + 1 < F ? 15 : 0) + 6 * (F - 2 - K > 0 ? F - 2 - K : 0);
+    if (t < prow) {
+      const int I = t < 15 ? K + 1 : K + 2 + (t - 15) / 6, rr = t < 15 ? t : (t - 15) % 6;
+      double* row = A + bidx2(I, K) + rr * kBS;
       double x[15];
 #pragma unroll
       for (int c = 0; c < 15; c++) x[c] = row[c];
@@ -334,12 +365,13 @@ __global__ void __launch_bounds__(kSolveThreads, 1) k_solve2(KP p, int w0) {
       const int m = F - 1 - K;
       const int npairs = m * (m + 1) / 2;
       if (wid == 0) {
-        if (npairs > 0) { block_mma(A + bidx(K + 1, K + 1), A + bidx(K + 1, K), A + bidx(K + 1, K), true, -1.0, lane); __syncwarp(); factor_diag(K + 1); }
+        if (npairs > 0) { block_mma(A + bidx2(K + 1, K + 1), A + bidx2(K + 1, K), A + bidx2(K + 1, K), 15, 15, 15, lane); __syncwarp(); factor_diag(K + 1); }
       } else {
         for (int q = wid; q < npairs; q += nwarp - 1) {  // pairs 1 .. npairs-1 over warps 1..7 (pair 0 = (K+1, K+1) is warp 0's)
           int a = 0; while ((a + 1) * (a + 2) / 2 <= q) a++;
           const int b = q - a * (a + 1) / 2;
-          block_mma(A + bidx(K + 1 + a, K + 1 + b), A + bidx(K + 1 + a, K), A + bidx(K + 1 + b, K), true, -1.0, lane);
+          const int I = K + 1 + a, J = K + 1 + b;
+          block_mma(A + bidx2(I, J), A + bidx2(I, K), A + bidx2(J, K), brows(I, J), brows(I, K), brows(J, K), lane);
         }
       }
     }
@@ -354,14 +386,23 @@ __global__ void __launch_bounds__(kSolveThreads, 1) k_solve2(KP p, int w0) {
     }
     return;
   }
-  // ---- inverses of the diagonal blocks, all K in parallel (lane = column of L^-1, forward substitution down the rows)
+  // ---- yu = L^T u (needs the diagonal blocks as factored, before they are overwritten by their inverses)
+  for (int col = t; col < D; col += nt) {
+    const int J = col / 15, c = col % 15;
+    double yu = 0;
+    for (int I = J; I < F; I++) {
+      const double* L = A + bidx2(I, J) + c;
+      const int nr = brows(I, J);
+      for (int r = 0; r < nr; r++) yu += L[r * kBS] * S.u[15 * I + r];
+    }
+    S.yu[col] = yu;
+  }
+  __syncthreads();
+  // ---- inverses of the diagonal blocks IN PLACE, all K in parallel (lane = column of L^-1, forward substitution down the rows)
   for (int K = wid; K < F; K += nwarp) {
-    const double* Akk = A + bidx(K, K);
-    double* Li = S.Linv + K * kBlk;
-    for (int i = lane; i < kBlk; i += 32) Li[i] = 0.0;
-    __syncwarp();
+    double* Akk = A + bidx2(K, K);
+    double x[15];
     if (lane < 15) {
-      double x[15];
 #pragma unroll
       for (int r = 0; r < 15; r++) {
         double acc = (r == lane) ? 1.0 : 0.0;
@@ -369,26 +410,29 @@ __global__ void __launch_bounds__(kSolveThreads, 1) k_solve2(KP p, int w0) {
         for (int k = 0; k < r; k++) acc -= Akk[r * kBS + k] * x[k];
         x[r] = (r >= lane) ? acc * S.dinv[16 * K + r] : 0.0;
       }
+    }
+    __syncwarp();
+    if (lane < 15) {
 #pragma unroll
-      for (int r = 0; r < 15; r++) if (r >= lane) Li[r * kBS + lane] = x[r];
+      for (int r = 0; r < 15; r++) Akk[r * kBS + lane] = (r >= lane) ? x[r] : 0.0;
     }
   }
-  __syncthreads();
   // ---- z = S'^-1 (g - g_schur): forward then backward block substitution by warp 0 alone (block-wide barriers cost more
   // than the 2 x 11 small steps); z kept per block with stride 16
   for (int i = t; i < D; i += nt) S.z[16 * (i / 15) + i % 15] = S.g[i] - S.gs[i];
   __syncthreads();
   if (wid == 0) {
     for (int K = 0; K < F; K++) {
-      const double* Li = S.Linv + K * kBlk;
+      const double* Li = A + bidx2(K, K);
       double v = 0;
       if (lane < 15) { for (int c = 0; c <= lane; c++) v += Li[lane * kBS + c] * S.z[16 * K + c]; }
       __syncwarp();
-      if (lane < 15) S.z[16 * K + lane] = v;
+      if (lane < 15) { S.z[16 * K + lane] = v; S.fw[15 * K + lane] = v; }
       __syncwarp();
-      for (int row = lane; row < 15 * (F - 1 - K); row += 32) {
-        const int I = K + 1 + row / 15, r = row % 15;
-        const double* Lr = A + bidx(I, K) + r * kBS;
+      const int prow = (K + 1 < F ? 15 : 0) + 6 * (F - 2 - K > 0 ? F - 2 - K : 0);
+      for (int row = lane; row < prow; row += 32) {
+        const int I = row < 15 ? K + 1 : K + 2 + (row - 15) / 6, r = row < 15 ? row : (row - 15) % 6;
+        const double* Lr = A + bidx2(I, K) + r * kBS;
         double acc = 0;
 #pragma unroll
         for (int c = 0; c < 15; c++) acc += Lr[c] * S.z[16 * K + c];
@@ -397,7 +441,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) k_solve2(KP p, int w0) {
       __syncwarp();
     }
     for (int K = F - 1; K >= 0; K--) {
-      const double* Li = S.Linv + K * kBlk;
+      const double* Li = A + bidx2(K, K);
       double v = 0;
       if (lane < 15) { for (int r = lane; r < 15; r++) v += Li[r * kBS + lane] * S.z[16 * K + r]; }
       __syncwarp();
@@ -405,28 +449,20 @@ __global__ void __launch_bounds__(kSolveThreads, 1) k_solve2(KP p, int w0) {
       __syncwarp();
       for (int col = lane; col < 15 * K; col += 32) {
         const int J = col / 15, c = col % 15;
-        const double* Lc = A + bidx(K, J) + c;
+        const double* Lc = A + bidx2(K, J) + c;
+        const int nr = brows(K, J);
         double acc = 0;
-#pragma unroll
-        for (int r = 0; r < 15; r++) acc += Lc[r * kBS] * S.z[16 * K + r];
+        for (int r = 0; r < nr; r++) acc += Lc[r * kBS] * S.z[16 * K + r];
         S.z[16 * J + c] -= acc;
       }
       __syncwarp();
     }
   }
   __syncthreads();
-  // y = L^T z and L^T u: z^T S' z = |L^T z|^2 etc. (explicit quadratic forms for the model cost change)
+  // quadratic forms of the model cost change through the factor: u^T S' u = |L^T u|^2, u^T S' z = (L^T u) . (L^T z),
+  // z^T S' z = |L^T z|^2 with L^T z = the forward-substitution result
   double s3[3] = {0, 0, 0};  // uSu, uSz, zSz
-  for (int col = t; col < D; col += nt) {
-    const int J = col / 15, c = col % 15;
-    double yz = 0, yu = 0;
-    for (int I = J; I < F; I++) {
-      const double* L = A + bidx(I, J) + c;
-#pragma unroll
-      for (int r = 0; r < 15; r++) { const double lv = L[r * kBS]; yz += lv * S.z[16 * I + r]; yu += lv * S.u[15 * I + r]; }
-    }
-    s3[0] += yu * yu; s3[1] += yu * yz; s3[2] += yz * yz;
-  }
+  for (int col = t; col < D; col += nt) { const double yu = S.yu[col], yz = S.fw[col]; s3[0] += yu * yu; s3[1] += yu * yz; s3[2] += yz * yz; }
   block_sum<3>(s3, S.red);
   if (t == 0) { st.uSu = s3[0]; st.uSz = s3[1]; st.zSz = s3[2]; }
   double s2[4] = {0, 0, 0, 0};  // gn2, gz, zEz, uEz
