@@ -80,6 +80,58 @@ __device__ void imu_raw(const gf2_imu_preint& pre, const ImuStates& s, double g_
   put3(J, 30, 12, 27, eye3(), 1.0);
 }
 
+// Warp-cooperative form of imu_raw for k_nonvis: every lane derives the (cheap) shared quantities itself, then lane b < 19
+// forms the b-th non-zero 3x3 block of the Jacobian and lane 19 the residual — the serial version above costs one thread a
+// few thousand dependent fp64 operations per factor. J (15x30) must have been zeroed by the caller.
+__device__ void imu_raw_warp(const gf2_imu_preint& pre, const ImuStates& s, double g_norm, double* r /*15*/, double* J /*15x30*/, int lane) {
+  const V3 G = mk3(0, 0, g_norm);
+  const double dt = pre.sum_dt;
+  const M3 dq_dbg = blk3(pre.jacobian, 3, 12);
+  const V3 dba = s.Bai - ld3(pre.lin_ba), dbg = s.Bgi - ld3(pre.lin_bg);
+  const Q4 dq = ldq(pre.delta_q);
+  const Q4 cdq = qmul(dq, deltaQ(mul(dq_dbg, dbg)));
+  const Q4 QiInv = qinv(s.Qi);
+  const V3 tp = 0.5 * dt * dt * G + s.Pj - s.Pi - dt * s.Vi;
+  const V3 tv = dt * G + s.Vj - s.Vi;
+  const V3 a_p = qrot(QiInv, tp), a_v = qrot(QiInv, tv);
+  if (lane == 19) {
+    const M3 dp_dba = blk3(pre.jacobian, 0, 9), dp_dbg = blk3(pre.jacobian, 0, 12), dv_dba = blk3(pre.jacobian, 6, 9), dv_dbg = blk3(pre.jacobian, 6, 12);
+    const V3 cdv = ld3(pre.delta_v) + mul(dv_dba, dba) + mul(dv_dbg, dbg);
+    const V3 cdp = ld3(pre.delta_p) + mul(dp_dba, dba) + mul(dp_dbg, dbg);
+    const V3 rp = a_p - cdp;
+    const V3 rq = 2.0 * qvec(qmul(qinv(cdq), qmul(QiInv, s.Qj)));
+    const V3 rv = a_v - cdv;
+    const V3 rba = s.Baj - s.Bai, rbg = s.Bgj - s.Bgi;
+    r[0] = rp.x; r[1] = rp.y; r[2] = rp.z; r[3] = rq.x; r[4] = rq.y; r[5] = rq.z; r[6] = rv.x; r[7] = rv.y; r[8] = rv.z;
+    r[9] = rba.x; r[10] = rba.y; r[11] = rba.z; r[12] = rbg.x; r[13] = rbg.y; r[14] = rbg.z;
+    return;
+  }
+  if (lane > 19) return;
+  int r0 = 0, c0 = 0; double sgn = 1.0; M3 m;
+  switch (lane) {
+    case 0: r0 = 0; c0 = 0; m = toR(QiInv); sgn = -1.0; break;
+    case 1: r0 = 0; c0 = 3; m = skew(a_p); break;
+    case 2: r0 = 3; c0 = 3; m = QleftQrightBR(qmul(qinv(s.Qj), s.Qi), cdq); sgn = -1.0; break;
+    case 3: r0 = 6; c0 = 3; m = skew(a_v); break;
+    case 4: r0 = 0; c0 = 6; m = toR(QiInv); sgn = -dt; break;
+    case 5: r0 = 0; c0 = 9; m = blk3(pre.jacobian, 0, 9); sgn = -1.0; break;
+    case 6: r0 = 0; c0 = 12; m = blk3(pre.jacobian, 0, 12); sgn = -1.0; break;
+    case 7: r0 = 3; c0 = 12; m = mul(QleftBR(qmul(qmul(qinv(s.Qj), s.Qi), dq)), dq_dbg); sgn = -1.0; break;  // uncorrected delta_q, imu_factor.h:137
+    case 8: r0 = 6; c0 = 6; m = toR(QiInv); sgn = -1.0; break;
+    case 9: r0 = 6; c0 = 9; m = blk3(pre.jacobian, 6, 9); sgn = -1.0; break;
+    case 10: r0 = 6; c0 = 12; m = blk3(pre.jacobian, 6, 12); sgn = -1.0; break;
+    case 11: r0 = 9; c0 = 9; m = eye3(); sgn = -1.0; break;
+    case 12: r0 = 12; c0 = 12; m = eye3(); sgn = -1.0; break;
+    case 13: r0 = 0; c0 = 15; m = toR(QiInv); break;
+    case 14: r0 = 3; c0 = 18; m = QleftBR(qmul(qinv(cdq), qmul(QiInv, s.Qj))); break;
+    case 15: r0 = 6; c0 = 21; m = toR(QiInv); break;
+    case 16: r0 = 9; c0 = 24; m = eye3(); break;
+    case 17: r0 = 12; c0 = 27; m = eye3(); break;
+    default: return;
+  }
+  put3(J, 30, r0, c0, m, sgn);
+}
+
 // ------------------------------------------------------------------------------------------------ wheel factor
 // WheelIntegrationBase::evaluate (VE/factor/wheel_integration_base.h:180-219) and the pose Jacobians of WheelFactor::Evaluate
 // (VE/factor/wheel_factor.h:117-156). Calibration blocks (extrinsic, sx sy sw, td) are constant in this build, so only

@@ -42,21 +42,68 @@ __global__ void __launch_bounds__(kNonvisThreads) k_nonvis(KP p, int w0) {
       }
       double* J = scratch[wid];
       double* r = J + 450;
-      if (lane == 0) { ImuStates s2 = load_imu_states(pose, sb, k); imu_raw(pre, s2, p.g_norm, r, J); }
+      for (int i = lane; i < 450; i += 32) J[i] = 0.0;
+      __syncwarp();
+      { ImuStates s2 = load_imu_states(pose, sb, k); imu_raw_warp(pre, s2, p.g_norm, r, J, lane); }
       __syncwarp();
       const double* sq = p.imu_sqrt + ((size_t)w * (F - 1) + k) * 225;
-      if (lane < 30) {
-        for (int a = 0; a < 15; a++) { double acc = 0; for (int kk = a; kk < 15; kk++) acc += sq[a * 15 + kk] * J[kk * 30 + lane]; J[a * 30 + lane] = acc; }
-      } else if (lane == 30) {
-        for (int a = 0; a < 15; a++) { double acc = 0; for (int kk = a; kk < 15; kk++) acc += sq[a * 15 + kk] * r[kk]; r[a] = acc; }
+      const int mr = lane >> 2, mq = lane & 3;
+      {  // J <- sqrt_info * J (15x15 upper triangular times 15x30) on the fp64 tensor cores; residual by lane 30 alongside
+        double jv[4][4];
+#pragma unroll
+        for (int nt = 0; nt < 4; nt++)
+#pragma unroll
+          for (int ks = 0; ks < 4; ks++) { const int kk = 4 * ks + mq, c = 8 * nt + mr; jv[nt][ks] = (kk < 15 && c < 30) ? J[kk * 30 + c] : 0.0; }
+        double rs = 0.0;
+        if (lane < 15) { for (int kk = lane; kk < 15; kk++) rs += sq[lane * 15 + kk] * r[kk]; }
+        double acc[2][4][2];
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++) {
+          double av[4];
+#pragma unroll
+          for (int ks = 0; ks < 4; ks++) { const int a = 8 * mt + mr, kk = 4 * ks + mq; av[ks] = (a < 15 && kk < 15 && kk >= a) ? sq[a * 15 + kk] : 0.0; }
+#pragma unroll
+          for (int nt = 0; nt < 4; nt++) {
+            acc[mt][nt][0] = 0.0; acc[mt][nt][1] = 0.0;
+#pragma unroll
+            for (int ks = 0; ks < 4; ks++) mma_f64(acc[mt][nt][0], acc[mt][nt][1], av[ks], jv[nt][ks]);
+          }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+          for (int nt = 0; nt < 4; nt++) {
+            const int a = 8 * mt + mr, c = 8 * nt + 2 * mq;
+            if (a < 15 && c < 30) { J[a * 30 + c] = acc[mt][nt][0]; J[a * 30 + c + 1] = acc[mt][nt][1]; }
+          }
+        if (lane < 15) r[lane] = rs;
       }
       __syncwarp();
       if (lane == 0) { double c = 0; for (int a = 0; a < 15; a++) c += r[a] * r[a]; cost += 0.5 * c; }
-      for (int idx = lane; idx < 675; idx += 32) {  // three 15x15 blocks of J^T J: (i,i), (j,i), (j,j)
-        const int blk = idx / 225, e = idx % 225;
-        const int a = e / 15 + (blk >= 1 ? 15 : 0), b = e % 15 + (blk == 2 ? 15 : 0);
-        double acc = 0; for (int rr = 0; rr < 15; rr++) acc += J[rr * 30 + a] * J[rr * 30 + b];
-        Hout[idx] = acc;
+      {  // J^T J (30x30, K = 15): lower tiles only; blocks (i,i), (j,i), (j,j) in the layout k_solve2 reads (diagonal blocks: lower part)
+        double jv[4][4];
+#pragma unroll
+        for (int nt = 0; nt < 4; nt++)
+#pragma unroll
+          for (int ks = 0; ks < 4; ks++) { const int kk = 4 * ks + mq, c = 8 * nt + mr; jv[nt][ks] = (kk < 15 && c < 30) ? J[kk * 30 + c] : 0.0; }
+#pragma unroll
+        for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+          for (int nt = 0; nt <= mt; nt++) {
+            double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+            for (int ks = 0; ks < 4; ks++) mma_f64(d0, d1, jv[mt][ks], jv[nt][ks]);
+            const int a = 8 * mt + mr;
+#pragma unroll
+            for (int h2 = 0; h2 < 2; h2++) {
+              const int b = 8 * nt + 2 * mq + h2; const double v = h2 ? d1 : d0;
+              if (a >= 30 || b >= 30) continue;
+              if (a < 15) { if (b < 15) Hout[a * 15 + b] = v; }
+              else if (b < 15) Hout[225 + (a - 15) * 15 + b] = v;
+              else Hout[450 + (a - 15) * 15 + (b - 15)] = v;
+            }
+          }
       }
       if (lane < 30) { double acc = 0; for (int rr = 0; rr < 15; rr++) acc += J[rr * 30 + lane] * r[rr]; gout[lane] = acc; }
       __syncwarp();
