@@ -149,13 +149,14 @@ struct LmCtx {  // per-landmark quantities (host frame side of ProjectionTwoFram
 __device__ __forceinline__ void landmark_ctx(const FrameCtx& fi, const CamCtx& cam, float4 oi, double td_i, double inv_dep, LmCtx& lc) {
   const double dt = cam.td - td_i;
   V3 pts_i_td = mk3((double)oi.x - dt * (double)oi.z, (double)oi.y - dt * (double)oi.w, 1.0);
-  V3 pc = mk3(pts_i_td.x / inv_dep, pts_i_td.y / inv_dep, pts_i_td.z / inv_dep);
+  const double il = 1.0 / inv_dep;  // one reciprocal (fp64 division is a long software sequence); pts / inv_dep -> pts * il
+  V3 pc = mk3(pts_i_td.x * il, pts_i_td.y * il, il);
   M3 ric; for (int i = 0; i < 9; i++) ric.m[i] = cam.ric[i];
   M3 Ri; for (int i = 0; i < 9; i++) Ri.m[i] = fi.R[i];
   V3 p_imu = mul(ric, pc) + mk3(cam.tic[0], cam.tic[1], cam.tic[2]);
   lc.Xw = mul(Ri, p_imu) + mk3(fi.P[0], fi.P[1], fi.P[2]);
   lc.Gi = scale(mul(Ri, skew(p_imu)), -1.0);
-  lc.dXdl = mul(Ri, mul(ric, pts_i_td)) * (-1.0 / (inv_dep * inv_dep));
+  lc.dXdl = mul(Ri, mul(ric, pts_i_td)) * (-(il * il));
 }
 
 // residual of one observation in frame j (projectionTwoFrameOneCamFactor.cpp:59-76), Huber weight applied by caller

@@ -430,6 +430,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) k_solve(KP p, int w0) {
 // ------------------------------------------------------------------------------------------------ k_backsub
 // sweep 2: z_l = (g_l - w_l^T z_x) / v'_l and the landmark parts of the dogleg dot products.
 struct StepShared {
+  double rimu[kMaxF][15];   // raw IMU residuals of the candidate (k_cand_eval)
   FrameCtx fr[kMaxF];
   CamCtx cam;
   double zx[kNVMax], ux[kNVMax];
@@ -595,12 +596,23 @@ __global__ void __launch_bounds__(288, 2) k_cand_eval(KP p, int w0) {
   // IMU / wheel factors and the prior at the candidate: warp 8 alone, concurrently with the landmark warps
   if (t >= 256) {
     const int ln = t - 256;
-    if (p.imu && ln < F - 1) {
-      const gf2_imu_preint& pre = p.imu[(size_t)w * (F - 1) + ln];
-      if (pre.valid && pre.sum_dt <= 10.0) {
-        double r[15]; ImuStates s2 = load_imu_states(pose_c, sb_c, ln);
-        imu_raw(pre, s2, p.g_norm, r, nullptr);
-        accx[0] += imu_cost(p.imu_sqrt + ((size_t)w * (F - 1) + ln) * 225, r);
+    if (p.imu) {
+      // lane k < F-1 evaluates the raw residual of interval k; the weighted cost 0.5 |sqrt_info r|^2 of all intervals is then
+      // spread over the warp as (interval, row) items so that no lane walks a whole 15x15 matrix out of global memory alone
+      bool ok = false;
+      if (ln < F - 1) {
+        const gf2_imu_preint& pre = p.imu[(size_t)w * (F - 1) + ln];
+        ok = pre.valid && pre.sum_dt <= 10.0;
+        if (ok) { double r[15]; ImuStates s2 = load_imu_states(pose_c, sb_c, ln); imu_raw(pre, s2, p.g_norm, r, nullptr); for (int k = 0; k < 15; k++) S.rimu[ln][k] = r[k]; }
+      }
+      const unsigned okmask = __ballot_sync(0xffffffffu, ok);
+      __syncwarp();
+      for (int it = ln; it < 15 * (F - 1); it += 32) {
+        const int k = it / 15, a = it % 15;
+        if (!((okmask >> k) & 1u)) continue;
+        const double* sq = p.imu_sqrt + ((size_t)w * (F - 1) + k) * 225 + a * 15;
+        double s2 = 0; for (int c = a; c < 15; c++) s2 += sq[c] * S.rimu[k][c];
+        accx[0] += 0.5 * s2 * s2;
       }
     }
     if (p.wheel && ln >= 16 && ln - 16 < F - 1) {
