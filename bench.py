@@ -113,6 +113,53 @@ def make_batch(gf2, synth, B, distinct, first_window=0, pinned=True, prior_strid
     return w
 
 
+def run_lk(gf2, synth, streams=64, steps=10, cv2_seconds=2.0):
+    """FeatureTracker::trackImage's LK stage (forward 4 levels + backward 2 levels + consistency check) on `streams`
+    independent 640x480 frame pairs per launch; images cross PCIe every call (the tracker API takes host images)."""
+    base = [synth.image_pair(s % 8, shift=(2.0 + 0.3 * (s % 8), -1.0)) for s in range(min(streams, 8))]
+    prev = np.stack([base[s % len(base)][0] for s in range(streams)]); cur = np.stack([base[s % len(base)][1] for s in range(streams)])
+    npts = min(len(b[2]) for b in base)
+    pts = np.stack([base[s % len(base)][2][:npts] for s in range(streams)])
+    t = gf2.Tracker(640, 480, max_pts=npts, max_streams=streams)
+    for _ in range(3):
+        t.track_fb(prev, cur, pts)
+    lk_ms = tot_ms = 0.0
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        out, ok = t.track_fb(prev, cur, pts)
+        tm = t.last_timing(); lk_ms += tm["lk_ms"]; tot_ms += tm["total_ms"]
+    wall = time.perf_counter() - t0
+    t1 = gf2.Tracker(640, 480, max_pts=npts, max_streams=1)
+    for _ in range(3):
+        t1.track_fb(prev[:1], cur[:1], pts[:1])
+    one = []
+    for _ in range(20):
+        t1.track_fb(prev[:1], cur[:1], pts[:1]); one.append(t1.last_timing()["total_ms"])
+    # SURVEY 8(d): algorithmic bytes of one frame pair (image + its pyramid once, patch + search window per level pass)
+    bytes_lk = 640 * 480 * (1 + 2 * (0.25 + 0.0625 + 0.015625)) + npts * 6 * ((21 + 2) ** 2 + (21 + 8) ** 2)
+    peaks, _ = measured_peaks()
+    ach = bytes_lk * streams / (lk_ms / steps / 1e3) / 1e9
+    line = {"metric": "LK frame pairs/sec (640x480, 4 levels, fwd+bwd)", "value": streams * steps / wall, "unit": "frame pairs/s", "streams": streams, "points": int(npts),
+            "device_ms_per_batch": tot_ms / steps, "lk_kernel_ms_per_batch": lk_ms / steps, "single_stream_ms_per_pair": float(np.median(one)), "tracked_fraction": float(ok.mean()),
+            "roofline": {"bound": "hbm", "kernel": "k_lk", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "algorithmic_bytes_per_pair": bytes_lk}}
+    if cv2_seconds > 0:
+        try:
+            import cv2
+            crit = (cv2.TERM_CRITERIA_COUNT + cv2.TERM_CRITERIA_EPS, 30, 0.01)
+            cv2.setNumThreads(0)
+            t0 = time.perf_counter(); n = 0
+            while time.perf_counter() - t0 < cv2_seconds:
+                s = n % len(base)
+                c, st, _ = cv2.calcOpticalFlowPyrLK(base[s][0], base[s][1], base[s][2][:npts].reshape(-1, 1, 2), None, winSize=(21, 21), maxLevel=3, criteria=crit)
+                cv2.calcOpticalFlowPyrLK(base[s][1], base[s][0], c, base[s][2][:npts].reshape(-1, 1, 2).copy(), winSize=(21, 21), maxLevel=1, criteria=crit, flags=cv2.OPTFLOW_USE_INITIAL_FLOW)
+                n += 1
+            line["cpu_baseline"] = {"value": n / (time.perf_counter() - t0), "unit": "frame pairs/s", "kind": "reference", "sample": f"cv2 {cv2.__version__} calcOpticalFlowPyrLK x2, all threads, one stream, {cv2_seconds:.0f} s"}
+        except ImportError:
+            pass
+    t.close(); t1.close()
+    return line
+
+
 def run_reference(args, rank, world):
     """Restated-reference CPU baseline: oracle solve (same algorithm as ceres::Solve with the reference's options) on
     all host threads, each step a bounded sample of the same workload."""
@@ -163,6 +210,7 @@ def main():
     ap.add_argument("--impl", default="gf2", choices=["gf2", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-marginalize", action="store_true", help="skip the marginalization leg")
+    ap.add_argument("--no-lk", action="store_true", help="skip the front-end (LK) leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "gf2" else args.warmup
     rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
@@ -308,6 +356,11 @@ def main():
             marg["cpu_port_ms_per_window_1thread"] = 1e3 * (time.perf_counter() - t0) / 4
         sm.close()
 
+    # ------------------------------------------------------------ front-end leg (BASELINE.json config 3), reported beside the metric
+    lk_line = None
+    if rank == 0 and not args.no_lk:
+        lk_line = run_lk(gf2, synth, streams=64, steps=10, cv2_seconds=0.0 if args.no_cpu_baseline else 2.0)
+
     if rank == 0:
         peaks, which = measured_peaks()
         n_lin = lin_launches * args.steps
@@ -327,7 +380,7 @@ def main():
             "roofline": {"bound": "hbm", "kernel": "k_linearize", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved / peaks["hbm_gbs"], "traffic": TRAFFIC_PER_WINDOW * B, "traffic_source": "ncu --set full capture of k_linearize, profiles/ (per window x windows per launch)", "peak_source": which,
                          "algorithmic_bytes_per_launch": BYTES_SWEEP * B, "avg_launch_ms": lin_avg_ms},
-            "marginalize": marg,
+            "marginalize": marg, "lk": lk_line,
             "phase_ms_per_step": {"linearize": lin_ms / args.steps, "reduced_solve": solve_ms / args.steps, "backsub_candidate": step_ms / args.steps,
                                   "solve_total": total_ms / args.steps},
         }

@@ -254,3 +254,40 @@ def make_windows(n_windows, config_id=2, n_landmarks=1000, n_frames=11, wheel=Fa
                     blk["kind"] = abi.BLK_SPEEDBIAS; blk["index"] = 0; blk["offset"] = 6 * (F - 1); blk["x0"][:9] = out["para_speedbias"][wi, 0]
             # keep block list ordered: poses first then speed-bias (any order is valid)
     return out
+
+
+# ---------------------------------------------------------------------------------------------------- front-end images
+def image_pair(seed=0, w=640, h=480, shift=(3.3, -2.1), n_pts=300):
+    """Band-limited random texture (blurred white noise, contrast normalised) and a smoothly warped second frame + noise;
+    corners from a coarse grid of local texture maxima (no cv2 needed)."""
+    rng = np.random.default_rng(seed)
+    big = rng.normal(size=(h + 64, w + 64))
+    k = np.exp(-0.5 * (np.arange(-6, 7) / 2.0) ** 2); k /= k.sum()
+    big = np.apply_along_axis(lambda r: np.convolve(r, k, mode="same"), 1, big)
+    big = np.apply_along_axis(lambda c: np.convolve(c, k, mode="same"), 0, big)
+    big = (big - big.mean()) / big.std()
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float64)
+
+    def sample(dx, dy, rot):
+        cx, cy = w / 2, h / 2
+        xs = cx + (xx - cx) * np.cos(rot) - (yy - cy) * np.sin(rot) + dx + 32
+        ys = cy + (xx - cx) * np.sin(rot) + (yy - cy) * np.cos(rot) + dy + 32
+        x0 = np.floor(xs).astype(int); y0 = np.floor(ys).astype(int); ax = xs - x0; ay = ys - y0
+        x0 = np.clip(x0, 0, w + 62); y0 = np.clip(y0, 0, h + 62)
+        v = big[y0, x0] * (1 - ax) * (1 - ay) + big[y0, x0 + 1] * ax * (1 - ay) + big[y0 + 1, x0] * (1 - ax) * ay + big[y0 + 1, x0 + 1] * ax * ay
+        return v
+    a = sample(0, 0, 0.0); b = sample(-shift[0], -shift[1], 0.004)
+    to8 = lambda v: np.clip(128 + 45 * v + rng.normal(0, 2, v.shape), 0, 255).astype(np.uint8)
+    prev, cur = to8(a), to8(b)
+    # corners: strongest gradient-energy pixel of each cell of a coarse grid, away from the border
+    gy, gx = np.gradient(prev.astype(np.float64))
+    e = gx * gx + gy * gy
+    pts = []
+    step = int(np.sqrt(w * h / n_pts))
+    for y in range(12, h - 12 - step, step):
+        for x in range(12, w - 12 - step, step):
+            c = e[y:y + step, x:x + step]
+            iy, ix = np.unravel_index(np.argmax(c), c.shape)
+            pts.append((x + ix + 0.25 * ((x + y) % 3), y + iy + 0.125 * ((x * 7 + y) % 5)))
+    pts = np.array(pts[:n_pts], np.float32)
+    return prev, cur, pts
