@@ -89,6 +89,18 @@ struct LkArgs {
 
 constexpr int kPix = 14;  // ceil(441 / 32)
 
+// Bilinear sample of a u8 image in the 5-extra-bit fixed point of cv::calcOpticalFlowPyrLK (CV_DESCALE(.., W_BITS1 - 5)).
+// `inside` is uniform over the warp: the window and its +1 neighbours lie in the image, so no BORDER_REFLECT_101 folding.
+__device__ __forceinline__ int lk_sample_u8(const uint8_t* __restrict__ im, int cols, int rows, int y, int x, bool inside, int w00, int w01, int w10, int w11) {
+  int a, b, c, d;
+  if (inside) { const uint8_t* q = im + y * cols + x; a = q[0]; b = q[1]; c = q[cols]; d = q[cols + 1]; }
+  else {
+    const int y0 = reflect101(y, rows), y1 = reflect101(y + 1, rows), x0 = reflect101(x, cols), x1 = reflect101(x + 1, cols);
+    a = im[(size_t)y0 * cols + x0]; b = im[(size_t)y0 * cols + x1]; c = im[(size_t)y1 * cols + x0]; d = im[(size_t)y1 * cols + x1];
+  }
+  return (a * w00 + b * w01 + c * w10 + d * w11 + (1 << (kWBits - 5 - 1))) >> (kWBits - 5);
+}
+
 __global__ void __launch_bounds__(128) k_lk(LkArgs a) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int s = warp / a.max_pts, i = warp % a.max_pts;
@@ -98,6 +110,9 @@ __global__ void __launch_bounds__(128) k_lk(LkArgs a) {
   const float2 pp = reinterpret_cast<const float2*>(a.prev_pts)[(size_t)s * a.max_pts + i];
   float2 np = reinterpret_cast<float2*>(a.next_pts)[(size_t)s * a.max_pts + i];
   bool ok = true; float errv = 0.f;
+  int oy[kPix], ox[kPix];   // window pixel of (lane, m): the divisions by the runtime window size are done once
+#pragma unroll
+  for (int m = 0; m < kPix; m++) { const int idx = lane + 32 * m; oy[m] = idx / win; ox[m] = idx - oy[m] * win; }
   for (int level = a.max_level; level >= 0; level--) {
     const int cols = a.I.w[level], rows = a.I.h[level];
     const uint8_t* I = a.I.img[level] + (size_t)s * a.img_stride[level];
@@ -116,25 +131,30 @@ __global__ void __launch_bounds__(128) k_lk(LkArgs a) {
     int w00, w01, w10, w11; lk_weights(px, py, ipx, ipy, w00, w01, w10, w11);
     // template patch: intensity (x32), Ix, Iy as int16-range ints, kPix pixels per lane
     int Iv[kPix], Ix[kPix], Iy[kPix];
-    long long s11 = 0, s12 = 0, s22 = 0;
+    // per-lane partial sums fit 32 bits: |Ix|, |Iy| <= 16 * 255 (Scharr), |J - I| <= 255 * 32, 14 pixels per lane
+    int p11 = 0, p12 = 0, p22 = 0;
+    const bool in_t = ipx >= 0 && ipy >= 0 && ipx + win < cols && ipy + win < rows;
 #pragma unroll
     for (int m = 0; m < kPix; m++) {
       const int idx = lane + 32 * m;
       Iv[m] = 0; Ix[m] = 0; Iy[m] = 0;
       if (idx < npx) {
-        const int y = ipy + idx / win, x = ipx + idx % win;
-        const int y0 = reflect101(y, rows), y1 = reflect101(y + 1, rows), x0 = reflect101(x, cols), x1 = reflect101(x + 1, cols);
-        Iv[m] = ((int)I[(size_t)y0 * cols + x0] * w00 + (int)I[(size_t)y0 * cols + x1] * w01 + (int)I[(size_t)y1 * cols + x0] * w10 + (int)I[(size_t)y1 * cols + x1] * w11 + (1 << (kWBits - 5 - 1))) >> (kWBits - 5);
-        // derivative buffers are zero outside the image (BORDER_CONSTANT)
-        const bool yi0 = y >= 0 && y < rows, yi1 = y + 1 >= 0 && y + 1 < rows, xi0 = x >= 0 && x < cols, xi1 = x + 1 >= 0 && x + 1 < cols;
-        const short2 z = make_short2(0, 0);
-        const short2 d00 = (yi0 && xi0) ? dI[(size_t)y * cols + x] : z, d01 = (yi0 && xi1) ? dI[(size_t)y * cols + x + 1] : z;
-        const short2 d10 = (yi1 && xi0) ? dI[(size_t)(y + 1) * cols + x] : z, d11 = (yi1 && xi1) ? dI[(size_t)(y + 1) * cols + x + 1] : z;
+        const int y = ipy + oy[m], x = ipx + ox[m];
+        Iv[m] = lk_sample_u8(I, cols, rows, y, x, in_t, w00, w01, w10, w11);
+        short2 d00, d01, d10, d11;
+        if (in_t) { const short2* q = dI + y * cols + x; d00 = q[0]; d01 = q[1]; d10 = q[cols]; d11 = q[cols + 1]; }
+        else {  // derivative buffers are zero outside the image (BORDER_CONSTANT)
+          const bool yi0 = y >= 0 && y < rows, yi1 = y + 1 >= 0 && y + 1 < rows, xi0 = x >= 0 && x < cols, xi1 = x + 1 >= 0 && x + 1 < cols;
+          const short2 z = make_short2(0, 0);
+          d00 = (yi0 && xi0) ? dI[(size_t)y * cols + x] : z; d01 = (yi0 && xi1) ? dI[(size_t)y * cols + x + 1] : z;
+          d10 = (yi1 && xi0) ? dI[(size_t)(y + 1) * cols + x] : z; d11 = (yi1 && xi1) ? dI[(size_t)(y + 1) * cols + x + 1] : z;
+        }
         Ix[m] = (d00.x * w00 + d01.x * w01 + d10.x * w10 + d11.x * w11 + (1 << (kWBits - 1))) >> kWBits;
         Iy[m] = (d00.y * w00 + d01.y * w01 + d10.y * w10 + d11.y * w11 + (1 << (kWBits - 1))) >> kWBits;
-        s11 += (long long)Ix[m] * Ix[m]; s12 += (long long)Ix[m] * Iy[m]; s22 += (long long)Iy[m] * Iy[m];
+        p11 += Ix[m] * Ix[m]; p12 += Ix[m] * Iy[m]; p22 += Iy[m] * Iy[m];
       }
     }
+    long long s11 = p11, s12 = p12, s22 = p22;
     s11 = warp_sum_ll(s11); s12 = warp_sum_ll(s12); s22 = warp_sum_ll(s22);
     const float FS = 1.f / (float)(1 << 20);
     const float A11 = __fmul_rn((float)s11, FS), A12 = __fmul_rn((float)s12, FS), A22 = __fmul_rn((float)s22, FS);
@@ -149,18 +169,17 @@ __global__ void __launch_bounds__(128) k_lk(LkArgs a) {
       const int inx = (int)floorf(nx), iny = (int)floorf(ny);
       if (inx < -win || inx >= cols || iny < -win || iny >= rows) { if (level == 0) ok = false; break; }
       int v00, v01, v10, v11; lk_weights(nx, ny, inx, iny, v00, v01, v10, v11);
-      long long sb1 = 0, sb2 = 0;
+      int q1 = 0, q2 = 0;
+      const bool in_j = inx >= 0 && iny >= 0 && inx + win < cols && iny + win < rows;
 #pragma unroll
       for (int m = 0; m < kPix; m++) {
         const int idx = lane + 32 * m;
         if (idx < npx) {
-          const int y = iny + idx / win, x = inx + idx % win;
-          const int y0 = reflect101(y, rows), y1 = reflect101(y + 1, rows), x0 = reflect101(x, cols), x1 = reflect101(x + 1, cols);
-          const int jv = ((int)J[(size_t)y0 * cols + x0] * v00 + (int)J[(size_t)y0 * cols + x1] * v01 + (int)J[(size_t)y1 * cols + x0] * v10 + (int)J[(size_t)y1 * cols + x1] * v11 + (1 << (kWBits - 5 - 1))) >> (kWBits - 5);
-          const int diff = jv - Iv[m];
-          sb1 += (long long)diff * Ix[m]; sb2 += (long long)diff * Iy[m];
+          const int diff = lk_sample_u8(J, cols, rows, iny + oy[m], inx + ox[m], in_j, v00, v01, v10, v11) - Iv[m];
+          q1 += diff * Ix[m]; q2 += diff * Iy[m];
         }
       }
+      long long sb1 = q1, sb2 = q2;
       sb1 = warp_sum_ll(sb1); sb2 = warp_sum_ll(sb2);
       const float b1 = __fmul_rn((float)sb1, FS), b2 = __fmul_rn((float)sb2, FS);
       const float ddx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), D);
@@ -179,17 +198,14 @@ __global__ void __launch_bounds__(128) k_lk(LkArgs a) {
       const int inx = (int)floorf(fx), iny = (int)floorf(fy);
       if (inx < -win || inx >= cols || iny < -win || iny >= rows) { ok = false; errv = 0.f; continue; }
       int v00, v01, v10, v11; lk_weights(fx, fy, inx, iny, v00, v01, v10, v11);
-      long long se = 0;
+      int pe = 0;
+      const bool in_e = inx >= 0 && iny >= 0 && inx + win < cols && iny + win < rows;
 #pragma unroll
       for (int m = 0; m < kPix; m++) {
         const int idx = lane + 32 * m;
-        if (idx < npx) {
-          const int y = iny + idx / win, x = inx + idx % win;
-          const int y0 = reflect101(y, rows), y1 = reflect101(y + 1, rows), x0 = reflect101(x, cols), x1 = reflect101(x + 1, cols);
-          const int jv = ((int)J[(size_t)y0 * cols + x0] * v00 + (int)J[(size_t)y0 * cols + x1] * v01 + (int)J[(size_t)y1 * cols + x0] * v10 + (int)J[(size_t)y1 * cols + x1] * v11 + (1 << (kWBits - 5 - 1))) >> (kWBits - 5);
-          se += llabs((long long)(jv - Iv[m]));
-        }
+        if (idx < npx) pe += abs(lk_sample_u8(J, cols, rows, iny + oy[m], inx + ox[m], in_e, v00, v01, v10, v11) - Iv[m]);
       }
+      long long se = pe;
       se = warp_sum_ll(se);
       errv = __fdiv_rn((float)se, (float)(32 * win * win));
     }
