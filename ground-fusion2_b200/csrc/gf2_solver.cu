@@ -717,7 +717,6 @@ int gf2_marginalize(gf2_solver* h, int first, int n, int32_t mode, const gf2_sol
   if (!opts) return gf2::fail(GF2_ERR_INVALID, "null options");
   if (mode != GF2_MARGIN_OLD && mode != GF2_MARGIN_SECOND_NEW) return gf2::fail(GF2_ERR_INVALID, "mode %d", mode);
   if (h->nccl_comm) return gf2::fail(GF2_ERR_UNSUPPORTED, "marginalization in factor-sharded mode is not built (the frame-0 landmarks live on different ranks)");
-  if (h->cfg.use_wheel && h->has_wheel) return gf2::fail(GF2_ERR_UNSUPPORTED, "marginalization with wheel factors is not built yet (calibration-block Jacobians of WheelFactor)");
   if (n == 0) return GF2_OK;
   KP k;
   GF2_TRY(fill_kp(h, opts, k));
@@ -733,11 +732,12 @@ int gf2_marginalize(gf2_solver* h, int first, int n, int32_t mode, const gf2_sol
   mp.out_J0 = const_cast<double*>(h->kp.prior_J0); mp.out_r0 = const_cast<double*>(h->kp.prior_r0);
   mp.out_blocks = const_cast<gf2_prior_block*>(h->kp.prior_blocks);
   const size_t sh_build = ((sizeof(MargShared) + 15) & ~size_t(15)) + sizeof(double) * kMargTMax * kMargLD;
-  const size_t sh_eig = ((sizeof(EigShared) + 15) & ~size_t(15)) + sizeof(double) * 2 * kMargKMax * (kMargKMax | 1);
+  const int Kc = 6 * (k.F - 1) + 16 + (k.use_wheel ? 10 : 0);
+  const size_t sh_eig = ((sizeof(EigShared) + 15) & ~size_t(15)) + sizeof(double) * 2 * Kc * (Kc | 1);
   static bool attr_done = false;
   if (!attr_done) {
     GF2_CUDA(cudaFuncSetAttribute(k_marg_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh_build));
-    GF2_CUDA(cudaFuncSetAttribute(k_marg_eig, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh_eig));
+    GF2_CUDA(cudaFuncSetAttribute(k_marg_eig, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(((sizeof(EigShared) + 15) & ~size_t(15)) + sizeof(double) * 2 * kMargKMax * (kMargKMax | 1))));
     attr_done = true;
   }
   cudaEventRecord(h->ev[0], h->stream);

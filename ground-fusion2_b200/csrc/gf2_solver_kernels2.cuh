@@ -170,6 +170,57 @@ __device__ void wheel_raw(const gf2_wheel_preint& pre, const double* pose_i, con
   put3(J, 12, 0, 9, mul(toR(qmul(qinv(Qio), Qj)), skew(tio)), -1.0);
   put3(J, 12, 3, 9, mul(Jrinv, toR(qinv(qio))), 1.0);
 }
+// Calibration-block Jacobians of WheelFactor::Evaluate (VE/factor/wheel_factor.h:157-247): extrinsic body_T_wheel (6),
+// sx, sy, sw, td — constant in the solve of this build, but kept variables of the marginalization prior. Jc is 6 x 10 in
+// tangent columns [ex_wheel 6 | sx | sy | sw | td]. Quirks of the reference are kept (e.g. Exp(forward_compensate_v) as a
+// rotation in the sx / sy columns).
+__device__ void wheel_calib_jacobians(const gf2_wheel_preint& pre, const double* pose_i, const double* pose_j, const double* exw, const double* sxw, double tdw,
+                                      double* Jc /*6x10*/) {
+  const V3 Pi = ld3(pose_i), Pj = ld3(pose_j), tio = ld3(exw);
+  const Q4 Qi = ldq(pose_i + 3), Qj = ldq(pose_j + 3), qio = ldq(exw + 3);
+  const double sx = sxw[0], sy = sxw[1], sw = sxw[2];
+  const V3 dp_dsx = mk3(pre.jacobian[0], pre.jacobian[3], pre.jacobian[6]), dp_dsy = mk3(pre.jacobian[1], pre.jacobian[4], pre.jacobian[7]);
+  const V3 dp_dsw = mk3(pre.jacobian[2], pre.jacobian[5], pre.jacobian[8]), dq_dsw = mk3(pre.jacobian[11], pre.jacobian[14], pre.jacobian[17]);
+  const double dsx = sx - pre.lin_sx, dsy = sy - pre.lin_sy, dsw = sw - pre.lin_sw;
+  const M3 Ri = toR(Qi), Rj = toR(Qj);
+  const V3 cdp = ld3(pre.delta_p) + dsx * dp_dsx + dsy * dp_dsy + dsw * dp_dsw;
+  const Q4 cdq = qnormalized(qmul(qnormalized(ldq(pre.delta_q)), so3Exp(dsw * dq_dsw)));
+  const double dtd = tdw - pre.lin_td;
+  const V3 lg = ld3(pre.lin_gyr), lv = ld3(pre.lin_vel), g1 = ld3(pre.gyr_1), v1 = ld3(pre.vel_1);
+  const Q4 ef = so3Exp((sw * dtd) * lg);
+  const Q4 dqt = qnormalized(qmul(qmul(ef, cdq), so3Exp((-sw * dtd) * g1)));
+  const Q4 Qio = qmul(Qi, qio);
+  const V3 rr = so3Log(qmul(qmul(qmul(qinv(dqt), qinv(Qio)), Qj), qio));   // raw rotation residual
+  const M3 Jrinv = rightJacobianInvSO3(rr);
+  const M3 Jr_drdsw = rightJacobianSO3(dsw * dq_dsw);
+  const V3 fcw = (sw * dtd) * lg, bcw = (sw * dtd) * g1;
+  const V3 fcv = dtd * mk3(sx * lv.x, sy * lv.y, lv.z), bcv = dtd * mk3(sx * v1.x, sy * v1.y, v1.z);
+  const M3 Jrtd = rightJacobianSO3(fcw), Jr_minus_td = rightJacobianSO3(-fcw);
+  const M3 cdqR = toR(cdq), RioInv = toR(qinv(Qio));
+  for (int i = 0; i < 60; i++) Jc[i] = 0.0;
+  // extrinsic, wheel_factor.h:157-171
+  put3(Jc, 10, 0, 0, mul(RioInv, sub(Rj, Ri)), 1.0);
+  put3(Jc, 10, 0, 3, skew(qrot(qinv(Qio), qrot(Qj, tio) + Pj - qrot(Qi, tio) - Pi)), 1.0);
+  put3(Jc, 10, 3, 3, mul(Jrinv, sub(eye3(), toR(qmul(qmul(qinv(qmul(Qj, qio)), Qi), qio)))), 1.0);
+  // sx, sy
+  const M3 Efv = toR(so3Exp(fcv));
+  const V3 tsx = -mul(Efv, mk3(lv.x * dtd, 0, 0) + dp_dsx - mul(cdqR, mk3(v1.x, 0, 0)) * dtd);
+  const V3 tsy = -mul(Efv, mk3(0, lv.y * dtd, 0) + dp_dsy - mul(cdqR, mk3(0, v1.y, 0)) * dtd);
+  Jc[0 * 10 + 6] = tsx.x; Jc[1 * 10 + 6] = tsx.y; Jc[2 * 10 + 6] = tsx.z;
+  Jc[0 * 10 + 7] = tsy.x; Jc[1 * 10 + 7] = tsy.y; Jc[2 * 10 + 7] = tsy.z;
+  // sw
+  const M3 Efw = toR(so3Exp(fcw));
+  const V3 inner = fcv + cdp - qrot(cdq, bcv);
+  const V3 tpw = -mul(Efw, dp_dsw - mul(cdqR, cross(mul(Jr_drdsw, dq_dsw), mk3(sx * v1.x, sy * v1.y, v1.z) * dtd)) + cross(mul(Jrtd, lg * dtd), inner));
+  const M3 Emr = toR(so3Exp(-rr)), Ebw = toR(so3Exp(bcw)), cdqInvR = toR(qinv(cdq));
+  const V3 trw = -mul(Jrinv, mul(Emr, mul(Ebw, mul(cdqInvR, mul(Jrtd, lg * dtd)) + mul(Jr_drdsw, dq_dsw))));
+  Jc[0 * 10 + 8] = tpw.x; Jc[1 * 10 + 8] = tpw.y; Jc[2 * 10 + 8] = tpw.z; Jc[3 * 10 + 8] = trw.x; Jc[4 * 10 + 8] = trw.y; Jc[5 * 10 + 8] = trw.z;
+  // td
+  const V3 svlv = mk3(sx * lv.x, sy * lv.y, lv.z), svv1 = mk3(sx * v1.x, sy * v1.y, v1.z);
+  const V3 tpt = -mul(Efw, svlv - mul(cdqR, svv1) + cross(mul(Jrtd, sw * lg), fcv + cdp - mul(cdqR, bcv)));
+  const V3 trt = -mul(Jrinv, mul(Emr, mul(Ebw, mul(cdqInvR, mul(Jrtd, sw * lg))) - mul(Jr_minus_td, sw * g1)));
+  Jc[0 * 10 + 9] = tpt.x; Jc[1 * 10 + 9] = tpt.y; Jc[2 * 10 + 9] = tpt.z; Jc[3 * 10 + 9] = trt.x; Jc[4 * 10 + 9] = trt.y; Jc[5 * 10 + 9] = trt.z;
+}
 __device__ __forceinline__ double wheel_cost(const double* sq /*6x6 upper*/, const double* r) {
   double c = 0;
   for (int a = 0; a < 6; a++) { double s = 0; for (int k = a; k < 6; k++) s += sq[a * 6 + k] * r[k]; c += s * s; }

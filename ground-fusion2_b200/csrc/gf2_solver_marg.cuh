@@ -26,12 +26,12 @@
 namespace gf2 {
 
 constexpr int kMargM = 15;                              // frame-0 part of the dropped set: pose 6 + speed-bias 9
-constexpr int kMargKMax = 6 * (kMaxF - 1) + 9 + 6 + 1;  // kept tangent dims, canonical: poses, sb0, ex-pose, td   (76)
-constexpr int kMargTMax = kMargM + kMargKMax;           // 91
+constexpr int kMargKMax = 6 * (kMaxF - 1) + 9 + 6 + 1 + 10;  // kept tangent dims, canonical: poses, sb0, ex-pose, td, wheel calibration (86)
+constexpr int kMargTMax = kMargM + kMargKMax;           // 101
 constexpr int kMargLD = kMargTMax | 1;                  // odd leading dimension: conflict-free column walks
 constexpr int kMargThreads = 256;
 constexpr int kEigThreads = 512;
-constexpr int kMargBlocksMax = kMaxF + 3;               // kept blocks: F-1 poses, sb0, ex, td
+constexpr int kMargBlocksMax = kMaxF + 8;               // kept blocks: F-1 poses, sb0, ex, td, ex-wheel, sx, sy, sw, td-wheel
 constexpr int kMargChunk = 32;                          // landmarks eliminated per rank-k update
 constexpr int kMargNCMax = 13 + 6 * (kMaxF - 1);        // columns a frame-0 landmark can touch: pose0, poses 1..F-1, ex, td  (73)
 constexpr int kMargOwn = (kMargNCMax * (kMargNCMax + 1) / 2 + kMargNCMax + kMargThreads - 1) / kMargThreads;  // matrix entries per thread (11)
@@ -76,6 +76,11 @@ __device__ __forceinline__ int marg_kept_col(int F, int kind, int index) {
     case GF2_BLK_SPEEDBIAS: return index == 0 ? NP : -1;
     case GF2_BLK_EX_POSE: return NP + 9;
     case GF2_BLK_TD: return NP + 15;
+    case GF2_BLK_EX_WHEEL: return NP + 16;
+    case GF2_BLK_SX: return NP + 22;
+    case GF2_BLK_SY: return NP + 23;
+    case GF2_BLK_SW: return NP + 24;
+    case GF2_BLK_TD_WHEEL: return NP + 25;
   }
   return -1;
 }
@@ -85,8 +90,23 @@ __device__ __forceinline__ int marg_kept_block(int F, int kind, int index) {  //
     case GF2_BLK_SPEEDBIAS: return F - 1;
     case GF2_BLK_EX_POSE: return F;
     case GF2_BLK_TD: return F + 1;
+    case GF2_BLK_EX_WHEEL: return F + 2;
+    case GF2_BLK_SX: return F + 3;
+    case GF2_BLK_SY: return F + 4;
+    case GF2_BLK_SW: return F + 5;
+    case GF2_BLK_TD_WHEEL: return F + 6;
   }
   return -1;
+}
+// kept block b (slot of touched[]) -> kind, local size, canonical column
+__device__ __forceinline__ void marg_block_info(int F, int b, int& kind, int& ls, int& c0) {
+  const int NP = 6 * (F - 1);
+  if (b < F - 1) { kind = GF2_BLK_POSE; ls = 6; c0 = 6 * b; }
+  else if (b == F - 1) { kind = GF2_BLK_SPEEDBIAS; ls = 9; c0 = NP; }
+  else if (b == F) { kind = GF2_BLK_EX_POSE; ls = 6; c0 = NP + 9; }
+  else if (b == F + 1) { kind = GF2_BLK_TD; ls = 1; c0 = NP + 15; }
+  else if (b == F + 2) { kind = GF2_BLK_EX_WHEEL; ls = 6; c0 = NP + 16; }
+  else { kind = GF2_BLK_SX + (b - (F + 3)); ls = 1; c0 = NP + 22 + (b - (F + 3)); }
 }
 
 // Jacobians of one projection factor wrt the camera extrinsic (2x6) and td (2x1),
@@ -131,7 +151,7 @@ __global__ void __launch_bounds__(kMargThreads) k_marg_build(KP p, int w0, MargP
   double* A = reinterpret_cast<double*>(smem_raw + ((sizeof(MargShared) + 15) & ~size_t(15)));  // [kMargTMax][kMargLD], upper triangle accumulated
   const int w = w0 + blockIdx.x;
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5, nw = blockDim.x >> 5;
-  const int F = p.F, NP = 6 * (F - 1), K = NP + 16, T = kMargM + K;
+  const int F = p.F, NP = 6 * (F - 1), K = NP + 16 + (p.use_wheel ? 10 : 0), T = kMargM + K;
   const double* pose = p.pose + (size_t)w * F * 7;
   const double* sb = p.sb + (size_t)w * F * 9;
   const int sn = F - 2;  // second-newest frame (WINDOW_SIZE - 1)
@@ -218,6 +238,39 @@ __global__ void __launch_bounds__(kMargThreads) k_marg_build(KP p, int w0, MargP
           s.b[ia] += acc;
         }
         if (lane == 0) { s.mtouched[0] = s.mtouched[1] = 1; s.touched[0] = 1; s.touched[F - 1] = 1; }
+      }
+    }
+    __syncthreads();
+
+    // ---- wheel factor 0 (estimator.cpp:3428-3439): pose0 dropped; pose1, body_T_wheel, sx, sy, sw, td_wheel kept
+    if (wid == 0 && p.wheel) {
+      const gf2_wheel_preint& pre = p.wheel[(size_t)w * (F - 1)];
+      if (pre.valid && pre.sum_dt < 10.0) {
+        double* J = &s.Z[0][0];   // 6 x 22 [pose_i 6 | pose_j 6 | ex_wheel 6 | sx sy sw td] + 6 residuals
+        double* r = J + 132;
+        if (lane == 0) {
+          double Jp[72], Jc[60];
+          wheel_raw(pre, pose, pose + 7, p.exw + (size_t)w * 7, p.sxw + (size_t)w * 3, p.tdw[w], r, Jp);
+          wheel_calib_jacobians(pre, pose, pose + 7, p.exw + (size_t)w * 7, p.sxw + (size_t)w * 3, p.tdw[w], Jc);
+          for (int a = 0; a < 6; a++) { for (int c = 0; c < 12; c++) J[a * 22 + c] = Jp[a * 12 + c]; for (int c = 0; c < 10; c++) J[a * 22 + 12 + c] = Jc[a * 10 + c]; }
+        }
+        __syncwarp();
+        const double* sq = p.wheel_sqrt + ((size_t)w * (F - 1)) * 36;
+        if (lane < 22) { for (int a = 0; a < 6; a++) { double acc = 0; for (int kk = a; kk < 6; kk++) acc += sq[a * 6 + kk] * J[kk * 22 + lane]; J[a * 22 + lane] = acc; } }
+        else if (lane == 22) { for (int a = 0; a < 6; a++) { double acc = 0; for (int kk = a; kk < 6; kk++) acc += sq[a * 6 + kk] * r[kk]; r[a] = acc; } }
+        __syncwarp();
+        for (int e = lane; e < 484; e += 32) {
+          const int a = e / 22, c = e % 22;
+          const int ia = a < 6 ? a : (a < 12 ? kMargM + (a - 6) : kMargM + NP + 16 + (a - 12));
+          const int ic = c < 6 ? c : (c < 12 ? kMargM + (c - 6) : kMargM + NP + 16 + (c - 12));
+          if (ia <= ic) { double acc = 0; for (int rr = 0; rr < 6; rr++) acc += J[rr * 22 + a] * J[rr * 22 + c]; A[ia * kMargLD + ic] += acc; }
+        }
+        if (lane < 22) {
+          const int a = lane; const int ia = a < 6 ? a : (a < 12 ? kMargM + (a - 6) : kMargM + NP + 16 + (a - 12));
+          double acc = 0; for (int rr = 0; rr < 6; rr++) acc += J[rr * 22 + a] * r[rr];
+          s.b[ia] += acc;
+        }
+        if (lane == 0) { s.mtouched[0] = 1; s.touched[0] = 1; for (int b2 = F + 2; b2 <= F + 6; b2++) s.touched[b2] = 1; }
       }
     }
     __syncthreads();
@@ -481,8 +534,9 @@ __global__ void __launch_bounds__(kEigThreads, 2) k_marg_eig(KP p, int w0, MargP
   extern __shared__ __align__(16) unsigned char smem_raw[];
   EigShared& s = *reinterpret_cast<EigShared*>(smem_raw);
   double* A = reinterpret_cast<double*>(smem_raw + ((sizeof(EigShared) + 15) & ~size_t(15)));
-  constexpr int LD = kMargKMax | 1;
-  double* V = A + kMargKMax * LD;
+  const int Kc = 6 * (p.F - 1) + 16 + (p.use_wheel ? 10 : 0);   // capacity of this handle's kept system
+  const int LD = Kc | 1;
+  double* V = A + Kc * LD;
   const int w = w0 + blockIdx.x;
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5, nw = blockDim.x >> 5;
   const int F = p.F, NP = 6 * (F - 1);
@@ -491,10 +545,10 @@ __global__ void __launch_bounds__(kEigThreads, 2) k_marg_eig(KP p, int w0, MargP
   if (st == GF2_MARG_INVALID_) { if (t == 0) { mp.out_rows[w] = 0; mp.out_nblocks[w] = 0; } return; }       // valid = false, :205-210
   if (t == 0) {
     int n = 0;
-    for (int b = 0; b < F + 2; b++) {
-      const int ls = b < F - 1 ? 6 : (b == F - 1 ? 9 : (b == F ? 6 : 1));
-      const int c0 = b < F - 1 ? 6 * b : (b == F - 1 ? NP : (b == F ? NP + 9 : NP + 15));
-      if (mp.touched[(size_t)w * kMargBlocksMax + b]) { s.boff[b] = n; for (int k = 0; k < ls; k++) s.col[n + k] = c0 + k; n += ls; }
+    const int nblk = F + 2 + (p.use_wheel ? 5 : 0);
+    for (int b = 0; b < kMargBlocksMax; b++) {
+      int kind, ls, c0; marg_block_info(F, b, kind, ls, c0);
+      if (b < nblk && mp.touched[(size_t)w * kMargBlocksMax + b]) { s.boff[b] = n; for (int k = 0; k < ls; k++) s.col[n + k] = c0 + k; n += ls; }
       else s.boff[b] = -1;
     }
     s.n = n; s.done = 0;
@@ -580,31 +634,30 @@ __global__ void __launch_bounds__(kEigThreads, 2) k_marg_eig(KP p, int w0, MargP
     r0[t] = S > kMargEps ? sqrt(1.0 / S) * vb : 0.0;
   }
   // kept blocks renamed by addr_shift; keep_block_data = the states at marginalization time (preMarginalize, :119-138)
-  if (t < F + 2) {
+  if (t < kMargBlocksMax) {
     const int b = t;
     if (s.boff[b] >= 0) {
       int slot = 0; for (int i = 0; i < b; i++) slot += (s.boff[i] >= 0);
       gf2_prior_block& o = mp.out_blocks[(size_t)w * (2 * F + 8) + slot];
-      o.offset = s.boff[b]; o.pad_ = 0;
+      int kind, ls, c0; marg_block_info(F, b, kind, ls, c0);
+      o.kind = kind; o.index = 0; o.offset = s.boff[b]; o.pad_ = 0;
       for (int k = 0; k < 9; k++) o.x0[k] = 0.0;
-      if (b < F - 1) {
+      if (kind == GF2_BLK_POSE) {
         const int old = mp.mode == 0 ? b + 1 : (b == F - 2 ? F - 1 : b);
-        o.kind = GF2_BLK_POSE; o.index = b;
+        o.index = b;
         for (int k = 0; k < 7; k++) o.x0[k] = p.pose[(size_t)w * F * 7 + 7 * old + k];
-      } else if (b == F - 1) {
+      } else if (kind == GF2_BLK_SPEEDBIAS) {
         const int old = mp.mode == 0 ? 1 : 0;
-        o.kind = GF2_BLK_SPEEDBIAS; o.index = 0;
         for (int k = 0; k < 9; k++) o.x0[k] = p.sb[(size_t)w * F * 9 + 9 * old + k];
-      } else if (b == F) {
-        o.kind = GF2_BLK_EX_POSE; o.index = 0;
-        for (int k = 0; k < 7; k++) o.x0[k] = p.ex[(size_t)w * 7 + k];
-      } else {
-        o.kind = GF2_BLK_TD; o.index = 0; o.x0[0] = p.td[w];
-      }
+      } else if (kind == GF2_BLK_EX_POSE) { for (int k = 0; k < 7; k++) o.x0[k] = p.ex[(size_t)w * 7 + k]; }
+      else if (kind == GF2_BLK_TD) o.x0[0] = p.td[w];
+      else if (kind == GF2_BLK_EX_WHEEL) { for (int k = 0; k < 7; k++) o.x0[k] = p.exw[(size_t)w * 7 + k]; }
+      else if (kind == GF2_BLK_TD_WHEEL) o.x0[0] = p.tdw[w];
+      else o.x0[0] = p.sxw[(size_t)w * 3 + (kind - GF2_BLK_SX)];
     }
   }
   if (t == 0) {
-    int nb = 0; for (int b = 0; b < F + 2; b++) nb += (s.boff[b] >= 0);
+    int nb = 0; for (int b = 0; b < kMargBlocksMax; b++) nb += (s.boff[b] >= 0);
     mp.out_rows[w] = n; mp.out_nblocks[w] = nb;
   }
 }

@@ -62,6 +62,30 @@ def test_margin_old_matches_oracle(gf2, oracle, synth, prior, nl):
     s.close()
 
 
+def test_margin_old_with_wheel_matches_oracle(gf2, oracle, synth):
+    """config 4 composition: IMU + wheel + projection (+ planes, which never touch frame 0's dropped blocks... they do touch
+    pose 0 but the reference does not marginalize LiDAR factors in the VINS window) -> the wheel factor's calibration blocks
+    (body_T_wheel, sx, sy, sw, td_wheel) become kept blocks of the prior."""
+    n = 4
+    w = synth.make_windows(n, config_id=4, n_landmarks=300, wheel=True, prior="dense")
+    oracle.imu_preintegrate(w); oracle.wheel_preintegrate(w)
+    w["sxsysw"][1] = [1.01, 0.99, 1.02]; w["td_wheel"][2] = 0.004
+    opts = gf2.abi.default_opts()
+    s = gf2.Solver(n, w["n_frames"], w["max_landmarks"], w["max_obs"], use_wheel=True)
+    s.upload(w, preintegrate="records")
+    s.solve(opts, n)
+    st = s.get_states(n); lam = s.get_landmarks(n)
+    status, m = s.marginalize(opts, mode=0)
+    assert (status == 0).all(), status
+    got = s.get_prior(n)
+    w["para_pose"][...] = st["para_pose"]; w["para_speedbias"][...] = st["para_speedbias"]; w["inv_depth"][...] = lam
+    for i in range(n):
+        ref = oracle.marginalize_window(w, i, opts, mode=0)
+        assert ref["status"] == 0 and ref["m"] == m[i] and ref["n"] == 86
+        _check_prior(oracle, _prior_of(got, i), ref, w["n_frames"])
+    s.close()
+
+
 def test_prior_chain_stays_resident(gf2, oracle, synth):
     """solve -> marginalize -> (slide) -> solve again with the device-resident prior == oracle doing the same on the host."""
     n = 3

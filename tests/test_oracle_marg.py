@@ -79,6 +79,12 @@ def assemble_margin_old(w, i, oracle, opts):
     params = np.concatenate([w["para_pose"][i, 0], w["para_speedbias"][i, 0], w["para_pose"][i, 1], w["para_speedbias"][i, 1]])
     res, jacs = oracle.factor_eval(1, np.frombuffer(rec.tobytes(), np.uint8), params, extra=[opts.g_norm])
     add(res, jacs, [pose(0), sb(0), pose(1), sb(1)])
+    # wheel factor 0 (estimator.cpp:3428-3439)
+    if w.get("use_wheel") and "wheel" in w:
+        recw = w["wheel"][i, 0]
+        params = np.concatenate([w["para_pose"][i, 0], w["para_pose"][i, 1], w["ex_pose_wheel"][i], w["sxsysw"][i], [w["td_wheel"][i]]])
+        res, jacs = oracle.factor_eval(2, np.frombuffer(recw.tobytes(), np.uint8), params)
+        add(res, jacs, [pose(0), pose(1), np.arange(base[4], base[4] + 6), np.array([base[5]]), np.array([base[6]]), np.array([base[7]]), np.array([base[8]])])
     # projection factors of landmarks hosted in frame 0
     obeg = np.concatenate([[0], np.cumsum(w["track_len"][i])])
     for k, l in enumerate(lm0):
@@ -140,6 +146,24 @@ def test_margin_old_matches_numpy(gf2, oracle, synth, prior):
         assert got["n"] == 6 * (w["n_frames"] - 1) + 9 + 6 + 1
         assert np.array_equal(x0[(0, 3)][:7], w["para_pose"][i, 4]) and np.array_equal(x0[(1, 0)], w["para_speedbias"][i, 1])
         assert np.array_equal(x0[(2, 0)][:7], w["ex_pose"][i])
+
+
+def test_margin_old_with_wheel_matches_numpy(gf2, oracle, synth):
+    abi = gf2.abi
+    w = synth.make_windows(2, config_id=4, n_landmarks=160, wheel=True, prior="dense")
+    oracle.imu_preintegrate(w); oracle.wheel_preintegrate(w)
+    w["sxsysw"][1] = [1.01, 0.99, 1.02]; w["td_wheel"][1] = 0.004    # off the linearisation point of the wheel preintegration
+    opts = abi.default_opts()
+    for i in range(2):
+        got = oracle.marginalize_window(w, i, opts, mode=0)
+        assert got["status"] == 0
+        H, g, m = numpy_marginalize_old(w, i, oracle, abi, opts)
+        Ho, go, x0 = oracle.prior_information(got, w["n_frames"])
+        assert np.abs(Ho - H).max() <= 1e-7 * np.abs(H).max()
+        assert np.abs(go - g).max() <= 1e-7 * max(1.0, np.abs(g).max())
+        kinds = sorted((int(b["kind"]), int(b["index"])) for b in got["blocks"])
+        assert kinds == sorted([(0, f) for f in range(w["n_frames"] - 1)] + [(1, 0), (2, 0), (3, 0), (4, 0), (5, 0), (6, 0), (7, 0), (8, 0)])
+        assert got["n"] == 6 * (w["n_frames"] - 1) + 9 + 6 + 1 + 10
 
 
 def test_margin_second_new(gf2, oracle, synth):
