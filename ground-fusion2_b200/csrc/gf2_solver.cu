@@ -599,7 +599,6 @@ static int run(gf2_solver* h, int first, int n, const gf2_solve_opts* opts, gf2_
   KP k;
   GF2_TRY(fill_kp(h, opts, k));
   const int D = h->D;
-  const size_t sh_lin = sizeof(LinShared);
   const size_t sh_solve = sizeof(Solve2Shared) + sizeof(double) * solve2_matrix_doubles(k.F);
   double initial_radius = opts->initial_radius > 0 ? opts->initial_radius : 1e4;
   int ne = 0;
@@ -610,7 +609,7 @@ static int run(gf2_solver* h, int first, int n, const gf2_solve_opts* opts, gf2_
   if (initial_radius != 1e4) return gf2::fail(GF2_ERR_UNSUPPORTED, "initial_radius other than the Ceres default 1e4");
   const int iters = only_linearize ? 1 : iterations;
   for (int it = 0; it < iters; it++) {
-    k_linearize<<<n, kLinThreads, sh_lin, h->stream>>>(k, first);
+    k_linearize<<<n, kLinThreads, sizeof(LinShared), h->stream>>>(k, first);
     if (h->nccl_comm) {  // one all-reduce of the visual reduced system + gradient per linearisation
       g_nccl.GroupStart();
       g_nccl.AllReduce(k.Svis + (size_t)first * kNVMax * kNVMax, k.Svis + (size_t)first * kNVMax * kNVMax, (size_t)n * kNVMax * kNVMax, kNcclFloat64, kNcclSum, h->nccl_comm, h->stream);

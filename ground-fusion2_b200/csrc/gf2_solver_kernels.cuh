@@ -23,8 +23,6 @@ namespace gf2 {
 constexpr int kMaxF = GF2_MAX_FRAMES;
 constexpr int kNVMax = 6 * kMaxF;          // 66 visual tangent dims
 constexpr int kNVP = 72;                   // padded to 9 mma tiles of 8; column 66 carries the landmark gradient
-constexpr int kLinThreads = 256;
-constexpr int kWTStride = kLinThreads + 4; // transposed W tile: [kNVP][kWTStride] doubles
 constexpr int kSolveThreads = 256;
 constexpr int kP = GF2_MAX_PRIOR_DIM;
 

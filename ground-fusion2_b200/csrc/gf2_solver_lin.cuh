@@ -2,10 +2,19 @@
 //
 // Work decomposition of the Jacobian sweep: landmarks are grouped by host frame (start_frame); every group is cut into
 // warp tasks of <= 32 landmarks, so all lanes of a warp evaluate, at step k, observations of the SAME frame pair
-// (i, i + k). Their 63 Hessian/gradient products (block (i,j) 36, block (j,j) upper 21, g_j 6) are then reduced across
-// the warp with a transposed butterfly (31 shuffle-adds per 32 values instead of 5 per value) and each lane flushes
-// one reduced value per batch into the CTA's shared pose-block matrix. Landmark columns w_l go, transposed, into a
-// shared tile consumed by the fp64 tensor-core SYRK (mma.sync m8n8k4) that forms the Schur complement.
+// (i, i + k).
+//
+// Moment form of the pose-block Hessian. Every Jacobian of ProjectionTwoFrameOneCamFactor
+// (VE/factor/projectionTwoFrameOneCamFactor.cpp:102-140) factors through Jx = d r / d pts_w (2x3):
+//     J_pose_i = Jx [ I | -[Xw - Pi]x Ri ],   J_pose_j = Jx [ -I | [d]x Rj ],   j_lambda = Jx dXw/dlambda,   d = Xw - Pj,
+// and [Xw - Pi]x = [d]x + [Pj - Pi]x. With N = Jx^T Jx, h = Jx^T r and D = [d]x, the three 6x6 blocks (i,i), (i,j), (j,j)
+// and both gradients of ALL factors of one frame pair follow from five sums over those factors,
+//     M0 = sum N (6),  M1 = sum N D (9),  M2 = sum D^T N D (6),  h0 = sum h (3),  h1 = sum D^T h (3)      -- 27 doubles,
+// and frame-only quantities (Ri, Rj, Pj - Pi). A lane therefore forms 27 numbers per observation (no 2x6 Jacobians, no
+// 6x6 products); the warp reduces them with a transposed butterfly (31 shuffle-adds for 32 values, lane q ends up with
+// total q) and adds them to the pair's moment record in shared memory; the blocks are expanded once per pair at the end
+// of the kernel. Landmark columns w_l = J_pose^T j_lambda = [ -n ; Rj^T (n x d) ], n = Jx^T j_lambda, go, transposed, into
+// a shared tile consumed by the fp64 tensor-core SYRK (mma.sync m8n8k4) that forms the Schur complement.
 #pragma once
 #include "gf2_solver_kernels.cuh"
 
@@ -61,33 +70,179 @@ __global__ void k_tasks(KP p, int w0) {
 }
 
 // ------------------------------------------------------------------------------------------------ k_linearize
+constexpr int kLinThreads = 128;   // 4 warps; 110 KB of shared memory -> two windows resident per SM
+constexpr int kLinWarps = kLinThreads / 32;
 constexpr int kWTRows = 68;        // 66 tangent rows + the landmark-gradient row 66 + one always-zero row 67 (tile padding)
-constexpr int kStageStride = 13;   // per residual row: Ji (6) | Jj (6) | r
+constexpr int kWTStride = kLinThreads + 4;  // transposed W tile: [kWTRows][kWTStride] doubles
 constexpr int kNBlkPairs = kMaxF * (kMaxF + 1) / 2;
+constexpr int kNPairs = kMaxF * (kMaxF - 1) / 2;  // frame pairs i < j
+constexpr int kMomStride = 28;     // upper part (m <= n, m < 6, n < 7) of the 7x7 Gram matrix of Y = [Jx | Jx [d]x | r]
+constexpr int kYStride = 68;       // staging of Y^T per warp: [8][kYStride], rows 0..63 = the warp's residual rows, column 7 stays zero
+constexpr int kSchurSlots = 12;    // Schur tiles owned by a warp (11, 11, 11, 12)
 
 struct LinShared {
   FrameCtx fr[kMaxF];
   CamCtx cam;
-  double U[kNBlkPairs * 36];  // pose-block Hessian of the visual factors: 6x6 blocks (bi <= bj), row-major inside
   double g[kNVP];
-  double red[8 * 32];
+  double Mom[kNPairs * kMomStride];  // per frame pair (i < j): the 27 moment sums
+  double red[2 * 32];
   int task_first[kMaxTasks], task_cnt[kMaxTasks], task_start[kMaxTasks];
-  double stage[8][64 * kStageStride];  // per warp: the 64 residual rows of the current step
-  double WT[kWTRows * kWTStride];      // transposed, pre-scaled landmark columns  w_l / sqrt(v'_l)
+  union {
+    double Y[kLinWarps][8 * kYStride];  // during the sweep
+    double U[kNBlkPairs * 36];          // afterwards: pose-block Hessian of the visual factors, 6x6 blocks (bi <= bj), row-major inside
+  };
+  double WT[kWTRows * kWTStride];      // transposed, pre-scaled landmark columns  w_l / sqrt(v'_l); afterwards scratch
 };
+constexpr int kSumStride = 32;
+constexpr int kSumsOfs = kNVP * kNVP;  // scratch in WT after the sweep: dense 72x72 Schur tiles, then the per-frame un-rotated sums
+static_assert(kWTRows * kWTStride >= kSumsOfs + kMaxF * kSumStride, "scratch fits in WT");
 
 __device__ __forceinline__ int ublk(int bi, int bj, int F) { return (bi * F - bi * (bi - 1) / 2 + (bj - bi)) * 36; }  // bi <= bj
+__device__ __forceinline__ int pidx(int i, int j, int F) { return i * (2 * F - i - 1) / 2 + (j - i - 1); }             // i < j
+__device__ __forceinline__ int momidx(int m, int n) { return 7 * m - m * (m - 1) / 2 + (n - m); }                      // m <= n
 
-// flush one 8x8 accumulator tile (m = lane/4, n = 2*(lane%4)+{0,1}) into a 6x6 block (+ optional gradient column n = 6)
-__device__ __forceinline__ void flush_tile(double* blk, double* gvec, double c0, double c1, int lane) {
-  const int m = lane >> 2, n = (lane & 3) * 2;
-  if (m < 6) {
-    if (n < 6) { atomicAdd(&blk[m * 6 + n], c0); atomicAdd(&blk[m * 6 + n + 1], c1); }
-    else if (gvec) atomicAdd(&gvec[m], c0);  // n == 6
+// Transposed butterfly: every lane brings 32 values; afterwards lane q holds the warp-wide sum of value q.
+__device__ __forceinline__ double butterfly32(double (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int q = 0; q < off; q++) {
+      const double send = up ? v[q] : v[q + off];
+      const double keep = up ? v[q + off] : v[q];
+      v[q] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+// ---- Schur SYRK tile ownership. The 45 tiles (a <= b) of the 9x9 grid are owned by diagonals d = b - a:
+// warp 0: d = 0, 7; warp 1: d = 1, 6; warp 2: d = 2, 5; warp 3: d = 3, 4, 8  (11 / 11 / 11 / 12 tiles). Every warp then
+// owns about a quarter of EVERY tile row a, so the suffix a >= a_min that a round touches stays balanced, and per k-step
+// a warp loads each row fragment once (the A and B fragments of m8n8k4 have the same lane layout) for all its tiles.
+struct TileAB { int a, b; };
+__host__ __device__ constexpr TileAB tile_of(int W, int slot) {
+  const int dg[4][3] = {{0, 7, -1}, {1, 6, -1}, {2, 5, -1}, {3, 4, 8}};
+  int s = 0;
+  for (int q = 0; q < 3; q++) {
+    const int d = dg[W][q];
+    if (d < 0) break;
+    for (int a = 0; a + d < 9; a++) { if (s == slot) return TileAB{a, a + d}; s++; }
+  }
+  return TileAB{-1, -1};
+}
+template <int W, int M, int S>
+__device__ __forceinline__ void syrk_tile(const double (&f)[9], double (&C)[kSchurSlots][2]) {
+  constexpr TileAB tl = tile_of(W, S);
+  if constexpr (tl.a >= 0 && tl.a >= M) mma_f64(C[S][0], C[S][1], f[tl.a], f[tl.b]);
+}
+template <int M, int I>
+__device__ __forceinline__ void syrk_frag(double (&f)[9], const double* wb, const double* w8) {
+  if constexpr (I >= M) f[I] = (I == 8) ? *w8 : wb[I * 8 * kWTStride];
+}
+// one round: C[tile] += sum over the 128 landmark columns, tiles with a >= M only
+template <int W, int M>
+__device__ __forceinline__ void syrk_round(const double* wb /* &WT[fq][fk] */, const double* w8 /* row min(64 + fq, 67) */, double (&C)[kSchurSlots][2]) {
+#pragma unroll 4
+  for (int k0 = 0; k0 < kLinThreads; k0 += 4) {
+    double f[9];
+    syrk_frag<M, 0>(f, wb + k0, w8 + k0); syrk_frag<M, 1>(f, wb + k0, w8 + k0); syrk_frag<M, 2>(f, wb + k0, w8 + k0);
+    syrk_frag<M, 3>(f, wb + k0, w8 + k0); syrk_frag<M, 4>(f, wb + k0, w8 + k0); syrk_frag<M, 5>(f, wb + k0, w8 + k0);
+    syrk_frag<M, 6>(f, wb + k0, w8 + k0); syrk_frag<M, 7>(f, wb + k0, w8 + k0); syrk_frag<M, 8>(f, wb + k0, w8 + k0);
+    syrk_tile<W, M, 0>(f, C); syrk_tile<W, M, 1>(f, C); syrk_tile<W, M, 2>(f, C); syrk_tile<W, M, 3>(f, C);
+    syrk_tile<W, M, 4>(f, C); syrk_tile<W, M, 5>(f, C); syrk_tile<W, M, 6>(f, C); syrk_tile<W, M, 7>(f, C);
+    syrk_tile<W, M, 8>(f, C); syrk_tile<W, M, 9>(f, C); syrk_tile<W, M, 10>(f, C); syrk_tile<W, M, 11>(f, C);
+  }
+}
+template <int W>
+__device__ __forceinline__ void syrk_warp(int a_min, const double* wb, const double* w8, double (&C)[kSchurSlots][2]) {
+  switch (a_min) {
+    case 0: syrk_round<W, 0>(wb, w8, C); break;
+    case 1: syrk_round<W, 1>(wb, w8, C); break;
+    case 2: syrk_round<W, 2>(wb, w8, C); break;
+    case 3: syrk_round<W, 3>(wb, w8, C); break;
+    case 4: syrk_round<W, 4>(wb, w8, C); break;
+    case 5: syrk_round<W, 5>(wb, w8, C); break;
+    case 6: syrk_round<W, 6>(wb, w8, C); break;
+    case 7: syrk_round<W, 7>(wb, w8, C); break;
+    default: syrk_round<W, 8>(wb, w8, C); break;
+  }
+}
+// accumulator tiles -> dense 72x72 (upper tiles) in shared memory
+template <int W, int S>
+__device__ __forceinline__ void syrk_store_tile(double* dense, const double (&C)[kSchurSlots][2], int fq, int fk) {
+  constexpr TileAB tl = tile_of(W, S);
+  if constexpr (tl.a >= 0) { double* d = dense + (8 * tl.a + fq) * kNVP + 8 * tl.b + 2 * fk; d[0] = C[S][0]; d[1] = C[S][1]; }
+}
+template <int W>
+__device__ __forceinline__ void syrk_store(double* dense, const double (&C)[kSchurSlots][2], int fq, int fk) {
+  syrk_store_tile<W, 0>(dense, C, fq, fk); syrk_store_tile<W, 1>(dense, C, fq, fk); syrk_store_tile<W, 2>(dense, C, fq, fk);
+  syrk_store_tile<W, 3>(dense, C, fq, fk); syrk_store_tile<W, 4>(dense, C, fq, fk); syrk_store_tile<W, 5>(dense, C, fq, fk);
+  syrk_store_tile<W, 6>(dense, C, fq, fk); syrk_store_tile<W, 7>(dense, C, fq, fk); syrk_store_tile<W, 8>(dense, C, fq, fk);
+  syrk_store_tile<W, 9>(dense, C, fq, fk); syrk_store_tile<W, 10>(dense, C, fq, fk); syrk_store_tile<W, 11>(dense, C, fq, fk);
+}
+
+// ---- expansion of the frame-pair moments (header comment)
+struct PairMom { M3 M0, M1, M2; V3 h0, h1; };
+__device__ __forceinline__ PairMom load_mom(const double* m) {
+  PairMom q;
+  q.M0.m[0] = m[momidx(0, 0)]; q.M0.m[1] = q.M0.m[3] = m[momidx(0, 1)]; q.M0.m[2] = q.M0.m[6] = m[momidx(0, 2)];
+  q.M0.m[4] = m[momidx(1, 1)]; q.M0.m[5] = q.M0.m[7] = m[momidx(1, 2)]; q.M0.m[8] = m[momidx(2, 2)];
+#pragma unroll
+  for (int a = 0; a < 3; a++)
+#pragma unroll
+    for (int b = 0; b < 3; b++) q.M1.m[a * 3 + b] = m[momidx(a, 3 + b)];
+  q.M2.m[0] = m[momidx(3, 3)]; q.M2.m[1] = q.M2.m[3] = m[momidx(3, 4)]; q.M2.m[2] = q.M2.m[6] = m[momidx(3, 5)];
+  q.M2.m[4] = m[momidx(4, 4)]; q.M2.m[5] = q.M2.m[7] = m[momidx(4, 5)]; q.M2.m[8] = m[momidx(5, 5)];
+  q.h0 = mk3(m[momidx(0, 6)], m[momidx(1, 6)], m[momidx(2, 6)]);
+  q.h1 = mk3(m[momidx(3, 6)], m[momidx(4, 6)], m[momidx(5, 6)]);
+  return q;
+}
+__device__ __forceinline__ M3 ldm3(const double* p) { M3 m; for (int i = 0; i < 9; i++) m.m[i] = p[i]; return m; }
+__device__ __forceinline__ void put3s(double* blk, int r0, int c0, const M3& m, double sgn) {
+#pragma unroll
+  for (int r = 0; r < 3; r++)
+#pragma unroll
+    for (int c = 0; c < 3; c++) blk[(r0 + r) * 6 + c0 + c] = sgn * m.m[r * 3 + c];
+}
+// off-diagonal block (i, j), i < j, sub-block sub = 0: pp, 1: p-theta, 2: theta-p, 3: theta-theta
+__device__ __forceinline__ void expand_offdiag(const double* mom, const FrameCtx& fi, const FrameCtx& fj, int sub, double* B) {
+  const PairMom q = load_mom(mom);
+  const M3 Ri = ldm3(fi.R), Rj = ldm3(fj.R);
+  if (sub == 0) { put3s(B, 0, 0, q.M0, -1.0); return; }
+  if (sub == 1) { put3s(B, 0, 3, mul(q.M1, Rj), 1.0); return; }
+  const M3 C = skew(mk3(fj.P[0] - fi.P[0], fj.P[1] - fi.P[1], fj.P[2] - fi.P[2]));
+  if (sub == 2) { put3s(B, 3, 0, mulT(Ri, add(transpose(q.M1), mulT(C, q.M0))), 1.0); return; }
+  put3s(B, 3, 3, mulT(Ri, mul(add(q.M2, mulT(C, q.M1)), Rj)), -1.0);
+}
+// un-rotated sums of frame f over all pairs it takes part in; grp 0: PP (sym 6) | GP (3) | GT (3), grp 1: PT (9), grp 2: TT (9)
+// so that block (f,f) = [[PP, -PT Rf], [., Rf^T TT Rf]] and g_f = [GP ; Rf^T GT]; out: PP 0..5 | GP 6..8 | GT 9..11 | PT 12..20 | TT 21..29
+__device__ __forceinline__ void expand_diag_sums(const double* Mom, const FrameCtx* fr, int f, int F, int grp, double* out /* kSumStride */) {
+  M3 acc = zero3(); V3 gp = mk3(0, 0, 0), gt = mk3(0, 0, 0);
+  for (int o = 0; o < F; o++) {
+    if (o == f) continue;
+    const bool irole = f < o;  // f is the host frame of the pair
+    const PairMom q = load_mom(Mom + (irole ? pidx(f, o, F) : pidx(o, f, F)) * kMomStride);
+    if (!irole) {
+      if (grp == 0) { acc = add(acc, q.M0); gp = gp - q.h0; gt = gt + q.h1; }
+      else if (grp == 1) acc = add(acc, q.M1);
+      else acc = add(acc, q.M2);
+    } else {
+      const M3 C = skew(mk3(fr[o].P[0] - fr[f].P[0], fr[o].P[1] - fr[f].P[1], fr[o].P[2] - fr[f].P[2]));
+      if (grp == 0) { acc = add(acc, q.M0); gp = gp + q.h0; gt = gt - (q.h1 + mulT(C, q.h0)); }
+      else if (grp == 1) acc = add(acc, add(q.M1, mul(q.M0, C)));
+      else { const M3 CtM1 = mulT(C, q.M1); acc = add(acc, add(add(q.M2, CtM1), add(transpose(CtM1), mulT(C, mul(q.M0, C))))); }
+    }
+  }
+  if (grp == 0) {
+    out[0] = acc.m[0]; out[1] = acc.m[1]; out[2] = acc.m[2]; out[3] = acc.m[4]; out[4] = acc.m[5]; out[5] = acc.m[8];
+    out[6] = gp.x; out[7] = gp.y; out[8] = gp.z; out[9] = gt.x; out[10] = gt.y; out[11] = gt.z;
+  } else {
+    for (int c = 0; c < 9; c++) out[(grp == 1 ? 12 : 21) + c] = acc.m[c];
   }
 }
 
-__global__ void __launch_bounds__(kLinThreads, 1) k_linearize(KP p, int w0) {
+__global__ void __launch_bounds__(kLinThreads, 2) k_linearize(KP p, int w0) {
   const int w = w0 + blockIdx.x;
   WinState& st = p.st[w];
   if (!st.active || st.reuse) return;
@@ -97,7 +252,8 @@ __global__ void __launch_bounds__(kLinThreads, 1) k_linearize(KP p, int w0) {
   const int F = p.F, NV = 6 * F;
   const double* pose = p.pose + (size_t)w * F * 7;
   build_frames(pose, p.ex + (size_t)w * 7, p.td[w], F, S.fr, &S.cam);
-  for (int i = t; i < kNBlkPairs * 36; i += kLinThreads) S.U[i] = 0.0;
+  for (int i = t; i < kNPairs * kMomStride; i += kLinThreads) S.Mom[i] = 0.0;
+  for (int i = t; i < kLinWarps * 8 * kYStride; i += kLinThreads) (&S.Y[0][0])[i] = 0.0;
   if (t < kNVP) S.g[t] = 0.0;
   const int ntasks = p.ntasks[w];
   if (t < kMaxTasks) { S.task_first[t] = p.task_first[(size_t)w * kMaxTasks + t]; S.task_cnt[t] = p.task_cnt[(size_t)w * kMaxTasks + t]; S.task_start[t] = p.task_start[(size_t)w * kMaxTasks + t]; }
@@ -109,105 +265,101 @@ __global__ void __launch_bounds__(kLinThreads, 1) k_linearize(KP p, int w0) {
   const double* ftd = p.frame_td + (size_t)w * F;
   const double mu = st.mu;
   const bool it0 = (st.iteration == 0);
+  const double sqi = p.sqrt_info_px;
   double cost_acc = 0.0, gmax = 0.0;
-  double C[6][2];  // Schur accumulators: sym tiles (a <= b) of the 9x9 tile grid, tile q -> warp q % 8, slot q / 8
+  double C[kSchurSlots][2];  // Schur accumulators of the tiles this warp owns (tile_of)
 #pragma unroll
-  for (int q = 0; q < 6; q++) { C[q][0] = 0.0; C[q][1] = 0.0; }
-  int tile_a[6], tile_b[6];  // tiles owned by this warp: q = wid + 8 * slot in row-major order of the upper 9x9 tile triangle
-#pragma unroll
-  for (int s2 = 0; s2 < 6; s2++) {
-    int q = wid + 8 * s2, a = 0;
-    if (q >= 45) { tile_a[s2] = -1; tile_b[s2] = 0; continue; }
-    while (q >= 9 - a) { q -= 9 - a; a++; }
-    tile_a[s2] = a; tile_b[s2] = a + q;
-  }
-  double* stg = S.stage[wid];
+  for (int q = 0; q < kSchurSlots; q++) { C[q][0] = 0.0; C[q][1] = 0.0; }
   const int fq = lane >> 2, fk = lane & 3;  // fragment coordinates: row/col index 0..7, k index 0..3
+  double* Yw = S.Y[wid];
+  const double* wb = &S.WT[fq * kWTStride + fk];
+  const double* w8 = &S.WT[min(64 + fq, kWTRows - 1) * kWTStride + fk];
 
-  for (int tbase = 0; tbase < ntasks; tbase += 8) {
+  for (int tbase = 0; tbase < ntasks; tbase += kLinWarps) {
     const int task = tbase + wid;
     const bool have_task = task < ntasks;
     const int i = have_task ? S.task_start[task] : 0;
     const bool have = have_task && lane < S.task_cnt[task];
     const int row0 = 8 * ((6 * S.task_start[tbase]) >> 3);  // tiles left of the round's first host frame are skipped by the SYRK
-    for (int c = row0; c < kWTRows - 1; c++) S.WT[c * kWTStride + t] = 0.0;
     int l = 0, L = 0, ob = 0; bool fx = false; double lam = 1.0;
     LmCtx lc;
     if (have) {
       l = perm[S.task_first[task] + lane]; L = tlen[l]; ob = obeg[l]; fx = p.fixed[(size_t)w * p.Lm + l] != 0; lam = p.invdep[(size_t)w * p.Lm + l];
       landmark_ctx(S.fr[i], S.cam, obs[ob], ftd[i], lam, lc);
     }
-    double wi[6] = {0, 0, 0, 0, 0, 0};  // w_i = sum_k Ji^T jl
+    // rows of this thread's column that the step loop below will not write: everything for an idle lane, else the rows
+    // left of the host frame and right of the track's last frame
+    {
+      const int z0 = have ? 6 * i : kWTRows - 1, z1 = have ? 6 * (i + L) : kWTRows - 1;
+      for (int c = row0; c < z0; c++) S.WT[c * kWTStride + t] = 0.0;
+      for (int c = z1; c < kWTRows - 1; c++) S.WT[c * kWTStride + t] = 0.0;
+    }
+    V3 ns = mk3(0, 0, 0);  // sum_k n_k  ->  w_i = [ ns ; Ri^T ((Xw - Pi) x ns) ]
     double v = 0.0, gl = 0.0;
-    double cii0 = 0.0, cii1 = 0.0;      // Ji^T [Ji | r] accumulated over the steps of the task (host-frame block + g_i)
     const int Lmax = __reduce_max_sync(0xffffffffu, L);
-    for (int k = 1; k < Lmax; k++) {
-      const bool valid = have && k < L;
+    if (have_task) for (int k = 1; k < Lmax; k++) {
       const int j = i + k;  // uniform across the warp
-      double Jx[6], Jj[12], Ji[12], r0 = 0, r1 = 0;
-#pragma unroll
-      for (int c = 0; c < 12; c++) { Ji[c] = 0; Jj[c] = 0; }
-      if (valid) {
-        V3 pcj; const float4 oj = obs[ob + k];
-        obs_residual(S.fr[j], S.cam, lc, oj, ftd[j], p.sqrt_info_px, r0, r1, pcj);
-        obs_jacobians(S.fr[j], S.cam, lc, pcj, p.sqrt_info_px, Jx, Jj);
+      // this lane's two rows of Y = [Jx | Jx [d]x | r]
+      double y0[7] = {0, 0, 0, 0, 0, 0, 0}, y1[7] = {0, 0, 0, 0, 0, 0, 0};
+      if (have && k < L) {
+        const FrameCtx& fj = S.fr[j];
+        const float4 oj = obs[ob + k];
+        const double dx = lc.Xw.x - fj.P[0], dy = lc.Xw.y - fj.P[1], dz = lc.Xw.z - fj.P[2];
+        const double px = fj.A[0] * dx + fj.A[1] * dy + fj.A[2] * dz - S.cam.rtt[0];
+        const double py = fj.A[3] * dx + fj.A[4] * dy + fj.A[5] * dz - S.cam.rtt[1];
+        const double pz = fj.A[6] * dx + fj.A[7] * dy + fj.A[8] * dz - S.cam.rtt[2];
+        const double dt = S.cam.td - ftd[j];
+        const double iz = 1.0 / pz;  // one reciprocal per observation (fp64 division is a long software sequence)
+        double r0 = sqi * (px * iz - ((double)oj.x - dt * (double)oj.z));
+        double r1 = sqi * (py * iz - ((double)oj.y - dt * (double)oj.w));
         double hr, sc; huber(p.huber, r0 * r0 + r1 * r1, hr, sc);
         cost_acc += hr;
         r0 *= sc; r1 *= sc;
-#pragma unroll
-        for (int c = 0; c < 6; c++) Jx[c] *= sc;
-#pragma unroll
-        for (int c = 0; c < 12; c++) Jj[c] *= sc;
-#pragma unroll
-        for (int r = 0; r < 2; r++) {  // Ji = [Jx | Jx * Gi]
-          Ji[r * 6 + 0] = Jx[r * 3]; Ji[r * 6 + 1] = Jx[r * 3 + 1]; Ji[r * 6 + 2] = Jx[r * 3 + 2];
-#pragma unroll
-          for (int c = 0; c < 3; c++) Ji[r * 6 + 3 + c] = Jx[r * 3] * lc.Gi.m[c] + Jx[r * 3 + 1] * lc.Gi.m[3 + c] + Jx[r * 3 + 2] * lc.Gi.m[6 + c];
-        }
+        // Jx = sc * sqrt_info * [[1/z, 0, -x/z^2], [0, 1/z, -y/z^2]] * A_j
+        const double a = sc * sqi * iz, bx = -a * px * iz, by = -a * py * iz;
+        const double j00 = a * fj.A[0] + bx * fj.A[6], j01 = a * fj.A[1] + bx * fj.A[7], j02 = a * fj.A[2] + bx * fj.A[8];
+        const double j10 = a * fj.A[3] + by * fj.A[6], j11 = a * fj.A[4] + by * fj.A[7], j12 = a * fj.A[5] + by * fj.A[8];
+        y0[0] = j00; y0[1] = j01; y0[2] = j02; y1[0] = j10; y1[1] = j11; y1[2] = j12;
+        // (row [d]x)_c: (b1 dz - b2 dy, b2 dx - b0 dz, b0 dy - b1 dx)
+        y0[3] = j01 * dz - j02 * dy; y0[4] = j02 * dx - j00 * dz; y0[5] = j00 * dy - j01 * dx;
+        y1[3] = j11 * dz - j12 * dy; y1[4] = j12 * dx - j10 * dz; y1[5] = j10 * dy - j11 * dx;
+        y0[6] = r0; y1[6] = r1;
+        // landmark column: j_lambda = Jx dXw/dlambda, n = Jx^T j_lambda, w_j = [ -n ; Rj^T (n x d) ]
         double jl0 = 0, jl1 = 0;
         if (!fx) {
-          jl0 = Jx[0] * lc.dXdl.x + Jx[1] * lc.dXdl.y + Jx[2] * lc.dXdl.z;
-          jl1 = Jx[3] * lc.dXdl.x + Jx[4] * lc.dXdl.y + Jx[5] * lc.dXdl.z;
+          jl0 = j00 * lc.dXdl.x + j01 * lc.dXdl.y + j02 * lc.dXdl.z;
+          jl1 = j10 * lc.dXdl.x + j11 * lc.dXdl.y + j12 * lc.dXdl.z;
         }
         v += jl0 * jl0 + jl1 * jl1; gl += jl0 * r0 + jl1 * r1;
-#pragma unroll
-        for (int c = 0; c < 6; c++) {
-          wi[c] += Ji[c] * jl0 + Ji[6 + c] * jl1;
-          S.WT[(6 * j + c) * kWTStride + t] = Jj[c] * jl0 + Jj[6 + c] * jl1;  // w_j = Jj^T jl
-        }
+        const double nx = j00 * jl0 + j10 * jl1, ny = j01 * jl0 + j11 * jl1, nz = j02 * jl0 + j12 * jl1;
+        ns.x += nx; ns.y += ny; ns.z += nz;
+        const double qx = ny * dz - nz * dy, qy = nz * dx - nx * dz, qz = nx * dy - ny * dx;
+        double* wt = &S.WT[(6 * j) * kWTStride + t];
+        wt[0] = -nx; wt[kWTStride] = -ny; wt[2 * kWTStride] = -nz;
+        wt[3 * kWTStride] = fj.R[0] * qx + fj.R[3] * qy + fj.R[6] * qz;
+        wt[4 * kWTStride] = fj.R[1] * qx + fj.R[4] * qy + fj.R[7] * qz;
+        wt[5 * kWTStride] = fj.R[2] * qx + fj.R[5] * qy + fj.R[8] * qz;
       }
-      if (have_task) {
-        // stage the 64 residual rows of this step, then reduce across the warp on the tensor cores:
-        //   C1 = Ji^T Jj -> block (i, j);  C2 = Jj^T [Jj | r] -> block (j, j), g_j;  Cii += Ji^T [Ji | r]
-        __syncwarp();
+      // Gram matrix Y^T Y of the warp's 64 rows on the tensor cores: one 8x8 tile, K = 64; the A and B fragments are the
+      // same element of the staged Y^T (column 7 of Y is never written and stays zero)
+      __syncwarp();
 #pragma unroll
-        for (int r = 0; r < 2; r++) {
-          double* row = stg + (2 * lane + r) * kStageStride;
+      for (int c = 0; c < 7; c++) { Yw[c * kYStride + lane] = y0[c]; Yw[c * kYStride + 32 + lane] = y1[c]; }
+      __syncwarp();
+      double c0 = 0, c1 = 0, e0 = 0, e1 = 0;
+      const double* yf = Yw + fq * kYStride + fk;
 #pragma unroll
-          for (int c = 0; c < 6; c++) { row[c] = Ji[r * 6 + c]; row[6 + c] = Jj[r * 6 + c]; }
-          row[12] = r ? r1 : r0;
-        }
-        __syncwarp();
-        double c10 = 0, c11 = 0, c20 = 0, c21 = 0, d10 = 0, d11 = 0, d20 = 0, d21 = 0, dii0 = 0, dii1 = 0;
-        const int colx = fq < 6 ? fq : 12;  // Ji column, or the residual for fragment index 6 (index 7 reads it too, masked below)
-#pragma unroll 4
-        for (int s = 0; s < 16; s++) {
-          const double* row = stg + (4 * s + fk) * kStageStride;
-          const double x = row[colx];
-          const double y = row[6 + (fq < 6 ? fq : 0)];
-          const double a_i = fq < 6 ? x : 0.0;              // Ji^T as A, also Ji as B (n < 6)
-          const double a_j = fq < 6 ? y : 0.0;              // Jj^T as A, also Jj as B (n < 6)
-          const double b_ir = fq < 7 ? x : 0.0;             // [Ji | r]
-          const double b_jr = fq < 6 ? y : (fq == 6 ? x : 0.0);  // [Jj | r]
-          if (s & 1) { mma_f64(d10, d11, a_i, a_j); mma_f64(d20, d21, a_j, b_jr); mma_f64(dii0, dii1, a_i, b_ir); }
-          else { mma_f64(c10, c11, a_i, a_j); mma_f64(c20, c21, a_j, b_jr); mma_f64(cii0, cii1, a_i, b_ir); }
-        }
-        c10 += d10; c11 += d11; c20 += d20; c21 += d21; cii0 += dii0; cii1 += dii1;
-        flush_tile(&S.U[ublk(i, j, F)], nullptr, c10, c11, lane);
-        flush_tile(&S.U[ublk(j, j, F)], &S.g[6 * j], c20, c21, lane);
+      for (int s = 0; s < 16; s += 2) {
+        const double ya = yf[4 * s], yb = yf[4 * s + 4];
+        mma_f64(c0, c1, ya, ya); mma_f64(e0, e1, yb, yb);
+      }
+      c0 += e0; c1 += e1;
+      if (fq < 6) {
+        double* mom = &S.Mom[pidx(i, j, F) * kMomStride + momidx(fq, fq)] - fq;  // entry (fq, n) at mom[n]
+        if (2 * fk >= fq) atomicAdd(&mom[2 * fk], c0);
+        if (2 * fk + 1 >= fq && fk < 3) atomicAdd(&mom[2 * fk + 1], c1);
       }
     }
-    if (have_task) flush_tile(&S.U[ublk(i, i, F)], &S.g[6 * i], cii0, cii1, lane);
     // landmark scalars: jacobi scale (iteration 0), regularised v' = v + mu * e; the landmark's column of W is scaled by
     // 1/sqrt(v') so that the SYRK below needs no per-element multiply
     if (have) {
@@ -220,64 +372,117 @@ __global__ void __launch_bounds__(kLinThreads, 1) k_linearize(KP p, int w0) {
       p.lm_v[(size_t)w * p.Lm + l] = fx ? 0.0 : v;
       p.lm_g[(size_t)w * p.Lm + l] = fx ? 0.0 : gl;
       if (!fx) gmax = fmax(gmax, fabs(gl));
-#pragma unroll
-      for (int c = 0; c < 6; c++) S.WT[(6 * i + c) * kWTStride + t] = wi[c] * rs;
+      const FrameCtx& fi = S.fr[i];
+      const V3 e_i = mk3(lc.Xw.x - fi.P[0], lc.Xw.y - fi.P[1], lc.Xw.z - fi.P[2]);
+      const V3 q = cross(e_i, ns);  // Gi^T ns = Ri^T ((Xw - Pi) x ns)
+      double* wt = &S.WT[(6 * i) * kWTStride + t];
+      wt[0] = ns.x * rs; wt[kWTStride] = ns.y * rs; wt[2 * kWTStride] = ns.z * rs;
+      wt[3 * kWTStride] = (fi.R[0] * q.x + fi.R[3] * q.y + fi.R[6] * q.z) * rs;
+      wt[4 * kWTStride] = (fi.R[1] * q.x + fi.R[4] * q.y + fi.R[7] * q.z) * rs;
+      wt[5 * kWTStride] = (fi.R[2] * q.x + fi.R[5] * q.y + fi.R[8] * q.z) * rs;
       for (int c = 6 * (i + 1); c < 6 * (i + L); c++) S.WT[c * kWTStride + t] *= rs;
       S.WT[66 * kWTStride + t] = fx ? 0.0 : gl * rs;
+    } else {
+      S.WT[66 * kWTStride + t] = 0.0;
     }
     __syncthreads();
     // Schur SYRK on the fp64 tensor cores: C[a-tile][b-tile] += sum_l Ws[l][a] * Ws[l][b]
     {
-      const int ta_min = row0 >> 3;
-      const double* wa[6]; const double* wb[6]; bool on[6];
-#pragma unroll
-      for (int s2 = 0; s2 < 6; s2++) {
-        on[s2] = tile_a[s2] >= ta_min;  // (also false for unowned slots: tile_a = -1)
-        wa[s2] = &S.WT[min(8 * max(tile_a[s2], 0) + fq, kWTRows - 1) * kWTStride + fk];
-        wb[s2] = &S.WT[min(8 * tile_b[s2] + fq, kWTRows - 1) * kWTStride + fk];
-      }
-      // all owned tiles advance together: six independent accumulator chains hide the mma latency
-#pragma unroll 2
-      for (int k0 = 0; k0 < kLinThreads; k0 += 4) {
-#pragma unroll
-        for (int s2 = 0; s2 < 6; s2++) if (on[s2]) mma_f64(C[s2][0], C[s2][1], wa[s2][k0], wb[s2][k0]);
+      const int a_min = row0 >> 3;
+      switch (wid) {
+        case 0: syrk_warp<0>(a_min, wb, w8, C); break;
+        case 1: syrk_warp<1>(a_min, wb, w8, C); break;
+        case 2: syrk_warp<2>(a_min, wb, w8, C); break;
+        default: syrk_warp<3>(a_min, wb, w8, C); break;
       }
     }
     __syncthreads();
   }
 
-  // LiDAR plane factors: tasks of <= 32 planes of one frame; [J | r]^T [J | r] reduced on the tensor cores into block (f, f), g_f
+  // Schur tiles -> dense 72x72 (upper tiles) in WT, which is free now
+  switch (wid) {
+    case 0: syrk_store<0>(S.WT, C, fq, fk); break;
+    case 1: syrk_store<1>(S.WT, C, fq, fk); break;
+    case 2: syrk_store<2>(S.WT, C, fq, fk); break;
+    default: syrk_store<3>(S.WT, C, fq, fk); break;
+  }
+  // frame-pair moments -> off-diagonal blocks (i, j) and the un-rotated per-frame sums
+  {
+    const int npairs = F * (F - 1) / 2;
+    double* sums = S.WT + kSumsOfs;
+    for (int q = t; q < 3 * F + 4 * npairs; q += kLinThreads) {
+      if (q < 3 * F) { const int grp = q / F, f = q - grp * F; expand_diag_sums(S.Mom, S.fr, f, F, grp, sums + f * kSumStride); continue; }
+      const int q2 = q - 3 * F, pr = q2 >> 2, sub = q2 & 3;
+      int i = 0, rem = pr;
+      while (rem >= F - 1 - i) { rem -= F - 1 - i; i++; }
+      const int j = i + 1 + rem;
+      expand_offdiag(&S.Mom[pr * kMomStride], S.fr[i], S.fr[j], sub, &S.U[ublk(i, j, F)]);
+    }
+  }
+  __syncthreads();
+  // diagonal blocks (f, f) = [[PP, -PT Rf], [., Rf^T TT Rf]] and the gradient g_f = [GP ; Rf^T GT]
+  {
+    const double* sums = S.WT + kSumsOfs;
+    for (int q = t; q < 42 * F; q += kLinThreads) {
+      const int f = q / 42, e = q - 42 * f;
+      const double* sf = sums + f * kSumStride;
+      const double* R = S.fr[f].R;
+      if (e >= 36) {
+        const int c = e - 36;
+        S.g[6 * f + c] = c < 3 ? sf[6 + c] : R[c - 3] * sf[9] + R[3 + c - 3] * sf[10] + R[6 + c - 3] * sf[11];
+        continue;
+      }
+      int r = e / 6, c = e - 6 * r;
+      if (r > c) { const int x = r; r = c; c = x; }  // symmetric: evaluate the upper element
+      double val;
+      if (c < 3) { const int lo = r, hi = c; val = sf[lo == 0 ? hi : (lo == 1 ? 2 + hi : 5)]; }  // PP sym: (00 01 02 11 12 22)
+      else if (r < 3) { const double* pt = sf + 12 + 3 * r; const int cc = c - 3; val = -(pt[0] * R[cc] + pt[1] * R[3 + cc] + pt[2] * R[6 + cc]); }
+      else {
+        const double* tt = sf + 21; const int rr = r - 3, cc = c - 3;
+        double acc = 0;
+#pragma unroll
+        for (int a = 0; a < 3; a++) acc += R[3 * a + rr] * (tt[3 * a] * R[cc] + tt[3 * a + 1] * R[3 + cc] + tt[3 * a + 2] * R[6 + cc]);
+        val = acc;
+      }
+      S.U[ublk(f, f, F) + e] = val;
+    }
+  }
+  __syncthreads();
+
+  // LiDAR plane factors: tasks of <= 32 planes of one frame; [J | r]^T [J | r] (upper 21 + J^T r 6 = 27 sums) by a warp butterfly
   if (p.planes) {
     const int npt = p.nptasks[w];
     const gf2_plane* pls = p.planes + (size_t)w * p.Pm;
     const int32_t* pperm = p.pperm + (size_t)w * p.Pm;
-    for (int q = wid; q < npt; q += 8) {
+    for (int q = wid; q < npt; q += kLinWarps) {
       const int f = p.ptask_frame[(size_t)w * kMaxPlaneTasks + q], cnt = p.ptask_cnt[(size_t)w * kMaxPlaneTasks + q], first = p.ptask_first[(size_t)w * kMaxPlaneTasks + q];
       double Jp[6] = {0, 0, 0, 0, 0, 0}, r = 0.0;
       if (lane < cnt) { r = plane_residual(pls[pperm[first + lane]], S.fr[f], p.lidar_sqrt_info, Jp); cost_acc += 0.5 * r * r; }
-      __syncwarp();
-      double* row = stg + lane * kStageStride;
+      double m[32];
+      {
+        int c = 0;
 #pragma unroll
-      for (int c = 0; c < 6; c++) row[c] = Jp[c];
-      row[6] = r;
-      __syncwarp();
-      double c0 = 0, c1 = 0;
+        for (int a = 0; a < 6; a++)
 #pragma unroll
-      for (int s = 0; s < 8; s++) {
-        const double x = stg[(4 * s + fk) * kStageStride + (fq < 7 ? fq : 0)];
-        mma_f64(c0, c1, fq < 6 ? x : 0.0, fq < 7 ? x : 0.0);
+          for (int b = a; b < 6; b++) m[c++] = Jp[a] * Jp[b];
+#pragma unroll
+        for (int a = 0; a < 6; a++) m[21 + a] = Jp[a] * r;
+#pragma unroll
+        for (int a = 27; a < 32; a++) m[a] = 0.0;
       }
-      flush_tile(&S.U[ublk(f, f, F)], &S.g[6 * f], c0, c1, lane);
+      const double tot = butterfly32(m, lane);
+      double* B = &S.U[ublk(f, f, F)];
+      if (lane < 21) {
+        int a = 0, rem = lane;
+        while (rem >= 6 - a) { rem -= 6 - a; a++; }
+        const int b = a + rem;
+        atomicAdd(&B[a * 6 + b], tot);
+        if (a != b) atomicAdd(&B[b * 6 + a], tot);
+      } else if (lane < 27) atomicAdd(&S.g[6 * f + lane - 21], tot);
     }
     __syncthreads();
   }
-  // S_vis = U - C, g_schur = C[:,66]; the Schur tiles are staged in WT (free now) as a dense 72x72 matrix
-#pragma unroll
-  for (int s2 = 0; s2 < 6; s2++) if (tile_a[s2] >= 0) {
-    const int row = 8 * tile_a[s2] + fq, col = 8 * tile_b[s2] + 2 * fk;
-    S.WT[row * kNVP + col] = C[s2][0]; S.WT[row * kNVP + col + 1] = C[s2][1];
-  }
-  __syncthreads();
+  // S_vis = U - Schur, g_schur = Schur[:,66]
   double* Svis = p.Svis + (size_t)w * kNVMax * kNVMax;
   // blocked output: lower block pairs (bi >= bj) in the order bi (bi + 1) / 2 + bj, each a row-major 6x6 block (the layout
   // k_solve2 assembles from); diagonal blocks are written symmetric from their upper triangle
@@ -289,11 +494,10 @@ __global__ void __launch_bounds__(kLinThreads, 1) k_linearize(KP p, int w0) {
     const int a = r <= c ? r : c, b = r <= c ? c : r;  // upper element (a <= b) of U and of the Schur tiles
     Svis[idx] = S.U[ublk(a / 6, b / 6, F) + (a % 6) * 6 + (b % 6)] - S.WT[a * kNVP + b];
   }
-  (void)NV;
-  if (t < NV) {
-    p.gvis[(size_t)w * kNVP + t] = S.g[t];                       // full visual gradient J^T r (pose part)
-    p.gschur[(size_t)w * kNVP + t] = S.WT[t * kNVP + 66];         // sum_l w_l g_l / v'_l, subtracted to form the reduced rhs
-    p.Udiag[(size_t)w * kNVMax + t] = S.U[ublk(t / 6, t / 6, F) + (t % 6) * 7];
+  for (int q = t; q < NV; q += kLinThreads) {
+    p.gvis[(size_t)w * kNVP + q] = S.g[q];                       // full visual gradient J^T r (pose part)
+    p.gschur[(size_t)w * kNVP + q] = S.WT[q * kNVP + 66];         // sum_l w_l g_l / v'_l, subtracted to form the reduced rhs
+    p.Udiag[(size_t)w * kNVMax + q] = S.U[ublk(q / 6, q / 6, F) + (q % 6) * 7];
   }
   double red2[2] = {cost_acc, 0.0};
   block_sum<2>(red2, S.red);
@@ -301,7 +505,7 @@ __global__ void __launch_bounds__(kLinThreads, 1) k_linearize(KP p, int w0) {
   if (lane == 0) S.red[wid] = gmax;
   __syncthreads();
   if (t == 0) {
-    double gm = 0; for (int i2 = 0; i2 < kLinThreads / 32; i2++) gm = fmax(gm, S.red[i2]);
+    double gm = 0; for (int i2 = 0; i2 < kLinWarps; i2++) gm = fmax(gm, S.red[i2]);
     p.c_lin[(size_t)w * 4] = red2[0]; p.c_gmax[w] = gm;
   }
 }

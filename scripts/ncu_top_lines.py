@@ -17,10 +17,12 @@ col = {n: i for i, n in enumerate(hdr)}
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", so], cwd=tmp, capture_output=True)
 lines = None
+dis_name = sys.argv[5] if len(sys.argv) > 5 else kernel  # (part of) the mangled name when the kernel is a template instance
+lines = None
 for cubin in glob.glob(os.path.join(tmp, "*.cubin")):
     dis = subprocess.run(["nvdisasm", "--print-line-info", "-c", cubin], capture_output=True, text=True).stdout
     # split by function
-    m = re.search(r"\.text\.[^\n]*" + kernel + r"[^\n]*:\n(.*?)(?=\n\.section|\Z)", dis, re.S)
+    m = re.search(r"\n\.text\.[^\n]*" + re.escape(dis_name) + r"[^\n]*:\n(.*?)(?=\n\s*\.section|\Z)", dis, re.S)
     if not m: continue
     cur = ("?", 0); lines = []
     for ln in m.group(1).splitlines():
