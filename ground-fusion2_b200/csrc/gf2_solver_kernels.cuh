@@ -174,8 +174,12 @@ __device__ __forceinline__ void obs_residual(const FrameCtx& fj, const CamCtx& c
 // VE/factor/marginalization_factor.cpp:46-77. Returns rho(s)/... : cost contribution 0.5*rho0 and the scale.
 __device__ __forceinline__ void huber(double delta, double sq, double& half_rho, double& scl) {
   const double b = delta * delta;
-  if (sq > b) { const double r = sqrt(sq); half_rho = 0.5 * (2.0 * delta * r - b); scl = sqrt(fmax(2.2250738585072014e-308, delta / r)); }
-  else { half_rho = 0.5 * sq; scl = 1.0; }
+  if (sq > b) {
+    // r = sqrt(sq) and scl = sqrt(delta / r) through two reciprocal square roots (fp64 sqrt and division are long software
+    // sequences): r = sq * rsqrt(sq), delta / r = delta * rsqrt(sq), sqrt(y) = y * rsqrt(y)
+    const double ir = rsqrt(sq), r = sq * ir, y = fmax(2.2250738585072014e-308, delta * ir);
+    half_rho = 0.5 * (2.0 * delta * r - b); scl = y * rsqrt(y);
+  } else { half_rho = 0.5 * sq; scl = 1.0; }
 }
 
 // Jacobians of one observation wrt d pts_w (Jx, 2x3) and pose_j (Jj, 2x6), projectionTwoFrameOneCamFactor.cpp:83-124

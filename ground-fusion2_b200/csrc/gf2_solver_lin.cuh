@@ -275,18 +275,32 @@ __global__ void __launch_bounds__(kLinThreads, 2) k_linearize(KP p, int w0) {
   const double* wb = &S.WT[fq * kWTStride + fk];
   const double* w8 = &S.WT[min(64 + fq, kWTRows - 1) * kWTStride + fk];
 
+  // landmark record of a lane for one round; fetched one round ahead so that the dependent global loads
+  // (perm -> table -> first observations) are in flight during the SYRK of the previous round
+  struct LaneLm { int l, L, ob; bool have, fx; double lam, s_l; float4 oi, o1; };
+  auto fetch_lm = [&](int tb) {
+    LaneLm q; q.l = 0; q.L = 0; q.ob = 0; q.fx = false; q.lam = 1.0; q.s_l = 1.0; q.oi = make_float4(0, 0, 0, 0); q.o1 = q.oi;
+    const int task = tb + wid;
+    q.have = task < ntasks && lane < S.task_cnt[task];
+    if (q.have) {
+      q.l = perm[S.task_first[task] + lane]; q.L = tlen[q.l]; q.ob = obeg[q.l]; q.fx = p.fixed[(size_t)w * p.Lm + q.l] != 0; q.lam = p.invdep[(size_t)w * p.Lm + q.l];
+      if (!it0) q.s_l = p.lm_s[(size_t)w * p.Lm + q.l];
+      q.oi = obs[q.ob];
+      if (q.L > 1) q.o1 = obs[q.ob + 1];
+    }
+    return q;
+  };
+  LaneLm nxt = fetch_lm(0);
   for (int tbase = 0; tbase < ntasks; tbase += kLinWarps) {
     const int task = tbase + wid;
     const bool have_task = task < ntasks;
     const int i = have_task ? S.task_start[task] : 0;
-    const bool have = have_task && lane < S.task_cnt[task];
+    const LaneLm cur = nxt;
+    const bool have = cur.have;
     const int row0 = 8 * ((6 * S.task_start[tbase]) >> 3);  // tiles left of the round's first host frame are skipped by the SYRK
-    int l = 0, L = 0, ob = 0; bool fx = false; double lam = 1.0;
+    const int l = cur.l, L = cur.L, ob = cur.ob; const bool fx = cur.fx;
     LmCtx lc;
-    if (have) {
-      l = perm[S.task_first[task] + lane]; L = tlen[l]; ob = obeg[l]; fx = p.fixed[(size_t)w * p.Lm + l] != 0; lam = p.invdep[(size_t)w * p.Lm + l];
-      landmark_ctx(S.fr[i], S.cam, obs[ob], ftd[i], lam, lc);
-    }
+    if (have) landmark_ctx(S.fr[i], S.cam, cur.oi, ftd[i], cur.lam, lc);
     // rows of this thread's column that the step loop below will not write: everything for an idle lane, else the rows
     // left of the host frame and right of the track's last frame
     {
@@ -297,13 +311,15 @@ __global__ void __launch_bounds__(kLinThreads, 2) k_linearize(KP p, int w0) {
     V3 ns = mk3(0, 0, 0);  // sum_k n_k  ->  w_i = [ ns ; Ri^T ((Xw - Pi) x ns) ]
     double v = 0.0, gl = 0.0;
     const int Lmax = __reduce_max_sync(0xffffffffu, L);
+    float4 oj_n = cur.o1;
     if (have_task) for (int k = 1; k < Lmax; k++) {
       const int j = i + k;  // uniform across the warp
+      const float4 oj = oj_n;
+      if (have && k + 1 < L) oj_n = obs[ob + k + 1];  // next step's observation: in flight during this step
       // this lane's two rows of Y = [Jx | Jx [d]x | r]
       double y0[7] = {0, 0, 0, 0, 0, 0, 0}, y1[7] = {0, 0, 0, 0, 0, 0, 0};
       if (have && k < L) {
         const FrameCtx& fj = S.fr[j];
-        const float4 oj = obs[ob + k];
         const double dx = lc.Xw.x - fj.P[0], dy = lc.Xw.y - fj.P[1], dz = lc.Xw.z - fj.P[2];
         const double px = fj.A[0] * dx + fj.A[1] * dy + fj.A[2] * dz - S.cam.rtt[0];
         const double py = fj.A[3] * dx + fj.A[4] * dy + fj.A[5] * dz - S.cam.rtt[1];
@@ -346,14 +362,14 @@ __global__ void __launch_bounds__(kLinThreads, 2) k_linearize(KP p, int w0) {
 #pragma unroll
       for (int c = 0; c < 7; c++) { Yw[c * kYStride + lane] = y0[c]; Yw[c * kYStride + 32 + lane] = y1[c]; }
       __syncwarp();
-      double c0 = 0, c1 = 0, e0 = 0, e1 = 0;
+      double c0 = 0, c1 = 0, e0 = 0, e1 = 0, c2 = 0, c3 = 0, e2 = 0, e3 = 0;  // four independent accumulator chains
       const double* yf = Yw + fq * kYStride + fk;
 #pragma unroll
-      for (int s = 0; s < 16; s += 2) {
-        const double ya = yf[4 * s], yb = yf[4 * s + 4];
-        mma_f64(c0, c1, ya, ya); mma_f64(e0, e1, yb, yb);
+      for (int s = 0; s < 16; s += 4) {
+        const double ya = yf[4 * s], yb = yf[4 * s + 4], yc = yf[4 * s + 8], yd = yf[4 * s + 12];
+        mma_f64(c0, c1, ya, ya); mma_f64(e0, e1, yb, yb); mma_f64(c2, c3, yc, yc); mma_f64(e2, e3, yd, yd);
       }
-      c0 += e0; c1 += e1;
+      c0 = (c0 + e0) + (c2 + e2); c1 = (c1 + e1) + (c3 + e3);
       if (fq < 6) {
         double* mom = &S.Mom[pidx(i, j, F) * kMomStride + momidx(fq, fq)] - fq;  // entry (fq, n) at mom[n]
         if (2 * fk >= fq) atomicAdd(&mom[2 * fk], c0);
@@ -364,7 +380,7 @@ __global__ void __launch_bounds__(kLinThreads, 2) k_linearize(KP p, int w0) {
     // 1/sqrt(v') so that the SYRK below needs no per-element multiply
     if (have) {
       double s_l;
-      if (it0) { s_l = 1.0 / (1.0 + sqrt(v)); p.lm_s[(size_t)w * p.Lm + l] = s_l; } else s_l = p.lm_s[(size_t)w * p.Lm + l];
+      if (it0) { s_l = 1.0 / (1.0 + sqrt(v)); p.lm_s[(size_t)w * p.Lm + l] = s_l; } else s_l = cur.s_l;
       const double d2 = fmin(fmax(s_l * s_l * v, 1e-6), 1e32);
       const double e = d2 / (s_l * s_l);
       const double vp = v + mu * e;
@@ -385,6 +401,7 @@ __global__ void __launch_bounds__(kLinThreads, 2) k_linearize(KP p, int w0) {
     } else {
       S.WT[66 * kWTStride + t] = 0.0;
     }
+    nxt = fetch_lm(tbase + kLinWarps);
     __syncthreads();
     // Schur SYRK on the fp64 tensor cores: C[a-tile][b-tile] += sum_l Ws[l][a] * Ws[l][b]
     {
@@ -488,7 +505,8 @@ __global__ void __launch_bounds__(kLinThreads, 2) k_linearize(KP p, int w0) {
   // k_solve2 assembles from); diagonal blocks are written symmetric from their upper triangle
   for (int idx = t; idx < (F * (F + 1) / 2) * 36; idx += kLinThreads) {
     const int blk = idx / 36, e = idx % 36;
-    int bi = 0; while ((bi + 1) * (bi + 2) / 2 <= blk) bi++;
+    int bi = (int)((sqrtf(8.0f * (float)blk + 1.0f) - 1.0f) * 0.5f);  // row of the lower block triangle
+    if ((bi + 1) * (bi + 2) / 2 <= blk) bi++; else if (bi * (bi + 1) / 2 > blk) bi--;
     const int bj = blk - bi * (bi + 1) / 2;
     const int r = 6 * bi + e / 6, c = 6 * bj + e % 6;
     const int a = r <= c ? r : c, b = r <= c ? c : r;  // upper element (a <= b) of U and of the Schur tiles
