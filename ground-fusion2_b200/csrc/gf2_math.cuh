@@ -104,6 +104,24 @@ GF2_HD M3 QleftQrightBR(Q4 a, Q4 b) {
   return r;
 }
 
+#ifdef __CUDACC__
+// Branch-free reciprocal / reciprocal square root for normal, positive arguments (depths, squared norms): the 2^-23
+// hardware approximation refined by three Newton steps (about 1 ulp; the library versions carry special-case branches that
+// split the basic block the kernel wants to software-pipeline).
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r; asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+#pragma unroll
+  for (int it = 0; it < 3; it++) { const double e = fma(-x, r, 1.0); r = fma(r, e, r); }
+  return r;
+}
+__device__ __forceinline__ double fast_rsqrt(double x) {
+  double r; asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+#pragma unroll
+  for (int it = 0; it < 3; it++) { const double e = fma(-x * r, r, 1.0); r = fma(0.5 * r, e, r); }
+  return r;
+}
+#endif
+
 // Sophus SO3::exp / log and the SO(3) right Jacobians (VE/utility/sophus_utils.hpp:155-236), used by the wheel factor.
 GF2_HD Q4 so3Exp(V3 om) {
   const double eps = 1e-10;

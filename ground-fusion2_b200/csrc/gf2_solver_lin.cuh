@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(kLinThreads, 2) k_linearize(KP p, int w0) {
     const bool have = cur.have;
     const int row0 = 8 * ((6 * S.task_start[tbase]) >> 3);  // tiles left of the round's first host frame are skipped by the SYRK
     const int l = cur.l, L = cur.L, ob = cur.ob; const bool fx = cur.fx;
-    LmCtx lc;
+    LmCtx lc; lc.Xw = mk3(0, 0, 0); lc.dXdl = mk3(0, 0, 0);
     if (have) landmark_ctx(S.fr[i], S.cam, cur.oi, ftd[i], cur.lam, lc);
     // rows of this thread's column that the step loop below will not write: everything for an idle lane, else the rows
     // left of the host frame and right of the track's last frame
@@ -312,69 +312,93 @@ __global__ void __launch_bounds__(kLinThreads, 2) k_linearize(KP p, int w0) {
     double v = 0.0, gl = 0.0;
     const int Lmax = __reduce_max_sync(0xffffffffu, L);
     float4 oj_n = cur.o1;
-    if (have_task) for (int k = 1; k < Lmax; k++) {
+    const double* yf = Yw + fq * kYStride + fk;
+    // One observation per lane, branch-free (idle lanes compute on dummy data and contribute zeros) so that it shares a basic
+    // block with the tensor-core Gram of the PREVIOUS step and the scheduler can interleave the two: this lane's two rows of
+    // Y = [Jx | Jx [d]x | r], the landmark sums and the column w_j.
+    auto obs_math = [&](int k, double (&y0)[7], double (&y1)[7]) {
       const int j = i + k;  // uniform across the warp
+      const bool valid = have && k < L;
       const float4 oj = oj_n;
-      if (have && k + 1 < L) oj_n = obs[ob + k + 1];  // next step's observation: in flight during this step
-      // this lane's two rows of Y = [Jx | Jx [d]x | r]
-      double y0[7] = {0, 0, 0, 0, 0, 0, 0}, y1[7] = {0, 0, 0, 0, 0, 0, 0};
-      if (have && k < L) {
-        const FrameCtx& fj = S.fr[j];
-        const double dx = lc.Xw.x - fj.P[0], dy = lc.Xw.y - fj.P[1], dz = lc.Xw.z - fj.P[2];
-        const double px = fj.A[0] * dx + fj.A[1] * dy + fj.A[2] * dz - S.cam.rtt[0];
-        const double py = fj.A[3] * dx + fj.A[4] * dy + fj.A[5] * dz - S.cam.rtt[1];
-        const double pz = fj.A[6] * dx + fj.A[7] * dy + fj.A[8] * dz - S.cam.rtt[2];
-        const double dt = S.cam.td - ftd[j];
-        const double iz = 1.0 / pz;  // one reciprocal per observation (fp64 division is a long software sequence)
-        double r0 = sqi * (px * iz - ((double)oj.x - dt * (double)oj.z));
-        double r1 = sqi * (py * iz - ((double)oj.y - dt * (double)oj.w));
-        double hr, sc; huber(p.huber, r0 * r0 + r1 * r1, hr, sc);
-        cost_acc += hr;
-        r0 *= sc; r1 *= sc;
-        // Jx = sc * sqrt_info * [[1/z, 0, -x/z^2], [0, 1/z, -y/z^2]] * A_j
-        const double a = sc * sqi * iz, bx = -a * px * iz, by = -a * py * iz;
-        const double j00 = a * fj.A[0] + bx * fj.A[6], j01 = a * fj.A[1] + bx * fj.A[7], j02 = a * fj.A[2] + bx * fj.A[8];
-        const double j10 = a * fj.A[3] + by * fj.A[6], j11 = a * fj.A[4] + by * fj.A[7], j12 = a * fj.A[5] + by * fj.A[8];
-        y0[0] = j00; y0[1] = j01; y0[2] = j02; y1[0] = j10; y1[1] = j11; y1[2] = j12;
-        // (row [d]x)_c: (b1 dz - b2 dy, b2 dx - b0 dz, b0 dy - b1 dx)
-        y0[3] = j01 * dz - j02 * dy; y0[4] = j02 * dx - j00 * dz; y0[5] = j00 * dy - j01 * dx;
-        y1[3] = j11 * dz - j12 * dy; y1[4] = j12 * dx - j10 * dz; y1[5] = j10 * dy - j11 * dx;
-        y0[6] = r0; y1[6] = r1;
-        // landmark column: j_lambda = Jx dXw/dlambda, n = Jx^T j_lambda, w_j = [ -n ; Rj^T (n x d) ]
-        double jl0 = 0, jl1 = 0;
-        if (!fx) {
-          jl0 = j00 * lc.dXdl.x + j01 * lc.dXdl.y + j02 * lc.dXdl.z;
-          jl1 = j10 * lc.dXdl.x + j11 * lc.dXdl.y + j12 * lc.dXdl.z;
-        }
-        v += jl0 * jl0 + jl1 * jl1; gl += jl0 * r0 + jl1 * r1;
-        const double nx = j00 * jl0 + j10 * jl1, ny = j01 * jl0 + j11 * jl1, nz = j02 * jl0 + j12 * jl1;
-        ns.x += nx; ns.y += ny; ns.z += nz;
-        const double qx = ny * dz - nz * dy, qy = nz * dx - nx * dz, qz = nx * dy - ny * dx;
-        double* wt = &S.WT[(6 * j) * kWTStride + t];
-        wt[0] = -nx; wt[kWTStride] = -ny; wt[2 * kWTStride] = -nz;
-        wt[3 * kWTStride] = fj.R[0] * qx + fj.R[3] * qy + fj.R[6] * qz;
-        wt[4 * kWTStride] = fj.R[1] * qx + fj.R[4] * qy + fj.R[7] * qz;
-        wt[5 * kWTStride] = fj.R[2] * qx + fj.R[5] * qy + fj.R[8] * qz;
-      }
-      // Gram matrix Y^T Y of the warp's 64 rows on the tensor cores: one 8x8 tile, K = 64; the A and B fragments are the
-      // same element of the staged Y^T (column 7 of Y is never written and stays zero)
+      oj_n = obs[ob + (have ? min(k + 1, L - 1) : 0)];  // next step's observation: in flight during this step (index clamped, no branch)
+      const FrameCtx& fj = S.fr[j];
+      const double dx = lc.Xw.x - fj.P[0], dy = lc.Xw.y - fj.P[1], dz = lc.Xw.z - fj.P[2];
+      const double px = fj.A[0] * dx + fj.A[1] * dy + fj.A[2] * dz - S.cam.rtt[0];
+      const double py = fj.A[3] * dx + fj.A[4] * dy + fj.A[5] * dz - S.cam.rtt[1];
+      const double pzr = fj.A[6] * dx + fj.A[7] * dy + fj.A[8] * dz - S.cam.rtt[2];
+      const double dt = S.cam.td - ftd[j];
+      const double iz = fast_rcp(valid ? pzr : 1.0);
+      double r0 = sqi * (px * iz - ((double)oj.x - dt * (double)oj.z));
+      double r1 = sqi * (py * iz - ((double)oj.y - dt * (double)oj.w));
+      // ceres::HuberLoss + Corrector as in huber(), branch-free: outside the inlier region r = sqrt(sq), scale = sqrt(delta / r)
+      const double sq = r0 * r0 + r1 * r1, hb = p.huber * p.huber;
+      const bool outl = sq > hb;
+      const double ir = fast_rsqrt(fmax(sq, hb)), yy = fmax(2.2250738585072014e-308, p.huber * ir);
+      const double sc = outl ? yy * fast_rsqrt(yy) : 1.0;
+      const double hr = outl ? 0.5 * (2.0 * p.huber * (sq * ir) - hb) : 0.5 * sq;
+      const double msk = valid ? 1.0 : 0.0;
+      cost_acc += msk * hr;
+      r0 *= sc * msk; r1 *= sc * msk;
+      // Jx = sc * sqrt_info * [[1/z, 0, -x/z^2], [0, 1/z, -y/z^2]] * A_j
+      const double a = msk * sc * sqi * iz, bx = -a * px * iz, by = -a * py * iz;
+      const double j00 = a * fj.A[0] + bx * fj.A[6], j01 = a * fj.A[1] + bx * fj.A[7], j02 = a * fj.A[2] + bx * fj.A[8];
+      const double j10 = a * fj.A[3] + by * fj.A[6], j11 = a * fj.A[4] + by * fj.A[7], j12 = a * fj.A[5] + by * fj.A[8];
+      y0[0] = j00; y0[1] = j01; y0[2] = j02; y1[0] = j10; y1[1] = j11; y1[2] = j12;
+      // (row [d]x)_c: (b1 dz - b2 dy, b2 dx - b0 dz, b0 dy - b1 dx)
+      y0[3] = j01 * dz - j02 * dy; y0[4] = j02 * dx - j00 * dz; y0[5] = j00 * dy - j01 * dx;
+      y1[3] = j11 * dz - j12 * dy; y1[4] = j12 * dx - j10 * dz; y1[5] = j10 * dy - j11 * dx;
+      y0[6] = r0; y1[6] = r1;
+      // landmark column: j_lambda = Jx dXw/dlambda (zero for a fixed landmark), n = Jx^T j_lambda, w_j = [ -n ; Rj^T (n x d) ]
+      const double fm = fx ? 0.0 : 1.0;
+      const double jl0 = fm * (j00 * lc.dXdl.x + j01 * lc.dXdl.y + j02 * lc.dXdl.z);
+      const double jl1 = fm * (j10 * lc.dXdl.x + j11 * lc.dXdl.y + j12 * lc.dXdl.z);
+      v += jl0 * jl0 + jl1 * jl1; gl += jl0 * r0 + jl1 * r1;
+      const double nx = j00 * jl0 + j10 * jl1, ny = j01 * jl0 + j11 * jl1, nz = j02 * jl0 + j12 * jl1;
+      ns.x += nx; ns.y += ny; ns.z += nz;
+      const double qx = ny * dz - nz * dy, qy = nz * dx - nx * dz, qz = nx * dy - ny * dx;
+      // unconditional: an idle lane stores the zeros these rows of its column hold anyway
+      double* wt = &S.WT[(6 * j) * kWTStride + t];
+      wt[0] = -nx; wt[kWTStride] = -ny; wt[2 * kWTStride] = -nz;
+      wt[3 * kWTStride] = fj.R[0] * qx + fj.R[3] * qy + fj.R[6] * qz;
+      wt[4 * kWTStride] = fj.R[1] * qx + fj.R[4] * qy + fj.R[7] * qz;
+      wt[5 * kWTStride] = fj.R[2] * qx + fj.R[5] * qy + fj.R[8] * qz;
+    };
+    // staging of the warp's 64 rows (transposed) and the fragments of the Gram product: the A and B fragment of a k-step are
+    // the same element of Y^T (column 7 of Y is never written and stays zero)
+    auto stage = [&](const double (&y0)[7], const double (&y1)[7], double (&fa)[16]) {
       __syncwarp();
 #pragma unroll
       for (int c = 0; c < 7; c++) { Yw[c * kYStride + lane] = y0[c]; Yw[c * kYStride + 32 + lane] = y1[c]; }
       __syncwarp();
-      double c0 = 0, c1 = 0, e0 = 0, e1 = 0, c2 = 0, c3 = 0, e2 = 0, e3 = 0;  // four independent accumulator chains
-      const double* yf = Yw + fq * kYStride + fk;
 #pragma unroll
-      for (int s = 0; s < 16; s += 4) {
-        const double ya = yf[4 * s], yb = yf[4 * s + 4], yc = yf[4 * s + 8], yd = yf[4 * s + 12];
-        mma_f64(c0, c1, ya, ya); mma_f64(e0, e1, yb, yb); mma_f64(c2, c3, yc, yc); mma_f64(e2, e3, yd, yd);
-      }
-      c0 = (c0 + e0) + (c2 + e2); c1 = (c1 + e1) + (c3 + e3);
+      for (int s = 0; s < 16; s++) fa[s] = yf[4 * s];
+    };
+    // Gram matrix Y^T Y on the tensor cores: one 8x8 tile, K = 64, four independent accumulator chains
+    auto gram = [&](const double (&fa)[16], double& g0, double& g1) {
+      double c0 = 0, c1 = 0, e0 = 0, e1 = 0, c2 = 0, c3 = 0, e2 = 0, e3 = 0;
+#pragma unroll
+      for (int s = 0; s < 16; s += 4) { mma_f64(c0, c1, fa[s], fa[s]); mma_f64(e0, e1, fa[s + 1], fa[s + 1]); mma_f64(c2, c3, fa[s + 2], fa[s + 2]); mma_f64(e2, e3, fa[s + 3], fa[s + 3]); }
+      g0 = (c0 + e0) + (c2 + e2); g1 = (c1 + e1) + (c3 + e3);
+    };
+    auto flush = [&](int j, double g0, double g1) {
       if (fq < 6) {
         double* mom = &S.Mom[pidx(i, j, F) * kMomStride + momidx(fq, fq)] - fq;  // entry (fq, n) at mom[n]
-        if (2 * fk >= fq) atomicAdd(&mom[2 * fk], c0);
-        if (2 * fk + 1 >= fq && fk < 3) atomicAdd(&mom[2 * fk + 1], c1);
+        if (2 * fk >= fq) atomicAdd(&mom[2 * fk], g0);
+        if (2 * fk + 1 >= fq && fk < 3) atomicAdd(&mom[2 * fk + 1], g1);
       }
+    };
+    if (have_task && Lmax > 1) {
+      double y0[7], y1[7], fa[16], g0, g1;
+      obs_math(1, y0, y1);
+      stage(y0, y1, fa);
+      for (int k = 2; k < Lmax; k++) {
+        gram(fa, g0, g1);      // the tensor cores reduce step k - 1 ...
+        obs_math(k, y0, y1);   // ... while step k runs on the fp64 FMA pipe
+        flush(i + k - 1, g0, g1);
+        stage(y0, y1, fa);
+      }
+      gram(fa, g0, g1);
+      flush(i + Lmax - 1, g0, g1);
     }
     // landmark scalars: jacobi scale (iteration 0), regularised v' = v + mu * e; the landmark's column of W is scaled by
     // 1/sqrt(v') so that the SYRK below needs no per-element multiply
