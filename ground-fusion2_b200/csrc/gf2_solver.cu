@@ -332,7 +332,7 @@ int gf2_solver_create(const gf2_solver_cfg* cfg, gf2_solver** out) {
   A(k.c_lin, double, (size_t)B * 4); A(k.c_gmax, double, B); A(k.c_sums, double, (size_t)B * 8); A(k.c_cand, double, (size_t)B * 4);
   if (Pm > 0) { A(k.pperm, int32_t, (size_t)B * Pm); A(k.ptask_first, int32_t, (size_t)B * kMaxPlaneTasks); A(k.ptask_cnt, int32_t, (size_t)B * kMaxPlaneTasks); A(k.ptask_frame, int32_t, (size_t)B * kMaxPlaneTasks); A(k.nptasks, int32_t, B); }
   if (cfg->use_wheel) { A(k.wheel_H, double, (size_t)B * (F - 1) * 108); A(k.wheel_g, double, (size_t)B * (F - 1) * 12); }
-  A(k.perm, int32_t, (size_t)B * Lm); A(k.task_first, int32_t, (size_t)B * kMaxTasks); A(k.task_cnt, int32_t, (size_t)B * kMaxTasks);
+  A(k.lminfo, int4, (size_t)B * Lm); A(k.task_first, int32_t, (size_t)B * kMaxTasks); A(k.task_cnt, int32_t, (size_t)B * kMaxTasks);
   A(k.task_start, int32_t, (size_t)B * kMaxTasks); A(k.ntasks, int32_t, B);
   A(k.st, WinState, B);
   if (cfg->max_imu_samples > 0) {

@@ -77,7 +77,8 @@ struct KP {  // kernel parameters (device pointers are window-major with the str
   double *Sfull, *gfull;           // optional dump of the assembled reduced system [nW][D*D], [nW][D]
   int32_t *pperm, *ptask_first, *ptask_cnt, *ptask_frame, *nptasks;  // k_tasks: plane permutation by frame, warp tasks
   double *wheel_H, *wheel_g;       // [nW][F-1][3*36] pose blocks (i,i),(j,i),(j,j) of each wheel factor, [nW][F-1][12]  (k_nonvis)
-  int32_t *perm, *task_first, *task_cnt, *task_start, *ntasks;  // k_tasks: landmark permutation by start frame, warp tasks
+  int4* lminfo;                    // k_tasks: landmarks sorted by start frame, packed (index, track length, first observation, fixed)
+  int32_t *task_first, *task_cnt, *task_start, *ntasks;  // k_tasks: warp tasks over that order
   // cross-rank scalars (factor-sharded mode all-reduces them; single GPU reads them straight back)
   double *c_lin, *c_gmax, *c_sums, *c_cand;  // [nW][4] {visual cost}, [nW] max|g_l|, [nW][8] k_backsub sums, [nW][4] {cand visual cost, |dl|^2, |l|^2}
   double* trace;                   // [nW][64][6]: candidate cost, model change, rho, radius, step norm, decision

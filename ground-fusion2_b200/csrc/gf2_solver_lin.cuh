@@ -47,7 +47,14 @@ __global__ void k_tasks(KP p, int w0) {
     p.ntasks[w] = nt;
   }
   __syncthreads();
-  if (t < F) { int32_t* perm = p.perm + (size_t)w * p.Lm; int o = ofs[t]; for (int l = 0; l < nlm; l++) if (start[l] == t) perm[o++] = l; }
+  // packed record (landmark, track length, first observation, fixed) in sorted order: one load gives k_linearize everything
+  // it needs to issue the dependent loads of a landmark
+  if (t < F) {
+    int4* info = p.lminfo + (size_t)w * p.Lm; const int32_t* tlen = p.tlen + (size_t)w * p.Lm; const int32_t* obeg = p.obeg + (size_t)w * p.Lm;
+    const uint8_t* fixed = p.fixed + (size_t)w * p.Lm;
+    int o = ofs[t];
+    for (int l = 0; l < nlm; l++) if (start[l] == t) info[o++] = make_int4(l, tlen[l], obeg[l], fixed[l] != 0);
+  }
   if (!p.planes) return;
   // LiDAR plane factors grouped by frame, tasks of <= 32 planes
   __syncthreads();
@@ -260,7 +267,7 @@ __global__ void __launch_bounds__(kLinThreads, 2) k_linearize(KP p, int w0) {
   for (int i = t; i < kWTRows * kWTStride; i += kLinThreads) S.WT[i] = 0.0;
   __syncthreads();
 
-  const int32_t* tlen = p.tlen + (size_t)w * p.Lm; const int32_t* obeg = p.obeg + (size_t)w * p.Lm; const int32_t* perm = p.perm + (size_t)w * p.Lm;
+  const int4* lminfo = p.lminfo + (size_t)w * p.Lm;
   const float4* obs = p.obs + (size_t)w * p.Om;
   const double* ftd = p.frame_td + (size_t)w * F;
   const double mu = st.mu;
@@ -275,22 +282,28 @@ __global__ void __launch_bounds__(kLinThreads, 2) k_linearize(KP p, int w0) {
   const double* wb = &S.WT[fq * kWTStride + fk];
   const double* w8 = &S.WT[min(64 + fq, kWTRows - 1) * kWTStride + fk];
 
-  // landmark record of a lane for one round; fetched one round ahead so that the dependent global loads
-  // (perm -> table -> first observations) are in flight during the SYRK of the previous round
+  // landmark record of a lane for one round, fetched ahead in two levels so that the dependent global loads are in flight
+  // during the SYRK of earlier rounds: the packed table entry two rounds ahead, the landmark's state and first observations
+  // one round ahead
   struct LaneLm { int l, L, ob; bool have, fx; double lam, s_l; float4 oi, o1; };
-  auto fetch_lm = [&](int tb) {
-    LaneLm q; q.l = 0; q.L = 0; q.ob = 0; q.fx = false; q.lam = 1.0; q.s_l = 1.0; q.oi = make_float4(0, 0, 0, 0); q.o1 = q.oi;
+  auto fetch_info = [&](int tb) {
     const int task = tb + wid;
-    q.have = task < ntasks && lane < S.task_cnt[task];
+    return (task < ntasks && lane < S.task_cnt[task]) ? lminfo[S.task_first[task] + lane] : make_int4(0, 0, 0, -1);  // w = -1: idle lane
+  };
+  auto fetch_lm = [&](int4 info) {
+    LaneLm q; q.l = info.x; q.L = info.y; q.ob = info.z; q.fx = info.w > 0; q.have = info.w >= 0; q.lam = 1.0; q.s_l = 1.0; q.oi = make_float4(0, 0, 0, 0); q.o1 = q.oi;
     if (q.have) {
-      q.l = perm[S.task_first[task] + lane]; q.L = tlen[q.l]; q.ob = obeg[q.l]; q.fx = p.fixed[(size_t)w * p.Lm + q.l] != 0; q.lam = p.invdep[(size_t)w * p.Lm + q.l];
+      q.lam = p.invdep[(size_t)w * p.Lm + q.l];
       if (!it0) q.s_l = p.lm_s[(size_t)w * p.Lm + q.l];
       q.oi = obs[q.ob];
-      if (q.L > 1) q.o1 = obs[q.ob + 1];
     }
+    // observation of the first step this warp will take (the step order is rotated per warp, see below)
+    const int nk = __reduce_max_sync(0xffffffffu, q.L) - 1;
+    if (q.have && q.L > 1) q.o1 = obs[q.ob + min(1 + (wid * nk) / kLinWarps, q.L - 1)];
     return q;
   };
-  LaneLm nxt = fetch_lm(0);
+  LaneLm nxt = fetch_lm(fetch_info(0));
+  int4 info_n = fetch_info(kLinWarps);
   for (int tbase = 0; tbase < ntasks; tbase += kLinWarps) {
     const int task = tbase + wid;
     const bool have_task = task < ntasks;
@@ -320,7 +333,7 @@ __global__ void __launch_bounds__(kLinThreads, 2) k_linearize(KP p, int w0) {
       const int j = i + k;  // uniform across the warp
       const bool valid = have && k < L;
       const float4 oj = oj_n;
-      oj_n = obs[ob + (have ? min(k + 1, L - 1) : 0)];  // next step's observation: in flight during this step (index clamped, no branch)
+      oj_n = obs[ob + (have ? min(k == Lmax - 1 ? 1 : k + 1, L - 1) : 0)];  // next step's observation: in flight during this step (index clamped, no branch)
       const FrameCtx& fj = S.fr[j];
       const double dx = lc.Xw.x - fj.P[0], dy = lc.Xw.y - fj.P[1], dz = lc.Xw.z - fj.P[2];
       const double px = fj.A[0] * dx + fj.A[1] * dy + fj.A[2] * dz - S.cam.rtt[0];
@@ -389,16 +402,21 @@ __global__ void __launch_bounds__(kLinThreads, 2) k_linearize(KP p, int w0) {
     };
     if (have_task && Lmax > 1) {
       double y0[7], y1[7], fa[16], g0, g1;
-      obs_math(1, y0, y1);
+      // the warps of a round usually share the host frame: each starts at a different step so that their atomic flushes
+      // hit different frame pairs
+      const int nk = Lmax - 1;
+      int k = 1 + (wid * nk) / kLinWarps, kp;
+      obs_math(k, y0, y1);
       stage(y0, y1, fa);
-      for (int k = 2; k < Lmax; k++) {
-        gram(fa, g0, g1);      // the tensor cores reduce step k - 1 ...
-        obs_math(k, y0, y1);   // ... while step k runs on the fp64 FMA pipe
-        flush(i + k - 1, g0, g1);
+      for (int q = 1; q < nk; q++) {
+        kp = k; k = k == nk ? 1 : k + 1;
+        gram(fa, g0, g1);      // the tensor cores reduce the previous step ...
+        obs_math(k, y0, y1);   // ... while this step runs on the fp64 FMA pipe
+        flush(i + kp, g0, g1);
         stage(y0, y1, fa);
       }
       gram(fa, g0, g1);
-      flush(i + Lmax - 1, g0, g1);
+      flush(i + k, g0, g1);
     }
     // landmark scalars: jacobi scale (iteration 0), regularised v' = v + mu * e; the landmark's column of W is scaled by
     // 1/sqrt(v') so that the SYRK below needs no per-element multiply
@@ -425,7 +443,8 @@ __global__ void __launch_bounds__(kLinThreads, 2) k_linearize(KP p, int w0) {
     } else {
       S.WT[66 * kWTStride + t] = 0.0;
     }
-    nxt = fetch_lm(tbase + kLinWarps);
+    nxt = fetch_lm(info_n);
+    info_n = fetch_info(tbase + 2 * kLinWarps);
     __syncthreads();
     // Schur SYRK on the fp64 tensor cores: C[a-tile][b-tile] += sum_l Ws[l][a] * Ws[l][b]
     {
