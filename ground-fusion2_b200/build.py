@@ -26,7 +26,8 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return OUT
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", OUT] + [os.path.join(CSRC, s) for s in SOURCES]
+    extra = os.environ.get("GF2_EXTRA_NVCC_FLAGS", "").split()  # debug builds only (e.g. -DGF2_PHASE_CLOCKS)
+    cmd = [nvcc] + NVCC_FLAGS + extra + ["-o", OUT] + [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)
     log = res.stdout + res.stderr
     with open(os.path.join(HERE, "build.log"), "w") as f:

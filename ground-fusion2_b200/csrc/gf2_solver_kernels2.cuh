@@ -480,11 +480,17 @@ __global__ void __launch_bounds__(kSolveThreads, 1) k_solve(KP p, int w0) {
 
 // ------------------------------------------------------------------------------------------------ k_backsub
 // sweep 2: z_l = (g_l - w_l^T z_x) / v'_l and the landmark parts of the dogleg dot products.
+//
+// w_l^T x for a pose-space vector x never needs the 2x6 Jacobians: with Jx = d r / d pts_w (gf2_solver_lin.cuh, header)
+//     J_pose_i x_i + J_pose_j x_j = Jx ( x_i^p - [Xw - Pi]x (Ri x_i^th)  -  x_j^p + [Xw - Pj]x (Rj x_j^th) ),
+// so per frame the two rotated vectors Rf x_f^th are formed once and every observation costs one cross product and one
+// 2x3 product per vector.
 struct StepShared {
   double rimu[kMaxF][15];   // raw IMU residuals of the candidate (k_cand_eval)
   FrameCtx fr[kMaxF];
   CamCtx cam;
   double zx[kNVMax], ux[kNVMax];
+  double rz[kMaxF][3], ru[kMaxF][3];  // Rf z_f^theta, Rf u_f^theta
   double red[8 * 32];
   double dx[kP];
   int decision;
@@ -496,45 +502,80 @@ __global__ void __launch_bounds__(256, 2) k_backsub(KP p, int w0) {
   if (!st.active || st.reuse || !st.lin_valid) return;
   __shared__ StepShared S;
   const int t = threadIdx.x, F = p.F, D = p.D, NV = 6 * F;
-  build_frames(p.pose + (size_t)w * F * 7, p.ex + (size_t)w * 7, p.td[w], F, S.fr, &S.cam);
-  if (t < NV) { const int d = 15 * (t / 6) + t % 6; S.zx[t] = p.zx[(size_t)w * D + d]; S.ux[t] = p.ux[(size_t)w * D + d]; }
-  __syncthreads();
+  // landmark records of this thread (4 per pass), loaded before the frame prologue so that the global-memory latency of the
+  // table -> first-observation chain is hidden behind it
+  constexpr int LPT = 4;
   const int nlm = p.nlm[w];
   const int32_t* start = p.start + (size_t)w * p.Lm; const int32_t* tlen = p.tlen + (size_t)w * p.Lm; const int32_t* obeg = p.obeg + (size_t)w * p.Lm;
   const float4* obs = p.obs + (size_t)w * p.Om;
+  double lv[LPT], llam[LPT], lgl[LPT], ls[LPT]; int li[LPT], lL[LPT], lob[LPT]; float4 loi[LPT], lo1[LPT];
+  auto load_chunk = [&](int base) {
+#pragma unroll
+    for (int q = 0; q < LPT; q++) {
+      const int l = base + t + 256 * q;
+      lL[q] = -1;
+      if (l < nlm) {
+        const size_t o = (size_t)w * p.Lm + l;
+        lv[q] = p.lm_v[o]; llam[q] = p.invdep[o]; lgl[q] = p.lm_g[o]; ls[q] = p.lm_s[o];
+        li[q] = start[l]; lL[q] = tlen[l]; lob[q] = obeg[l];
+        loi[q] = obs[lob[q]]; lo1[q] = obs[lob[q] + (lL[q] > 1 ? 1 : 0)];
+      }
+    }
+  };
+  load_chunk(0);
+  build_frames(p.pose + (size_t)w * F * 7, p.ex + (size_t)w * 7, p.td[w], F, S.fr, &S.cam);
+  if (t < NV) { const int d = 15 * (t / 6) + t % 6; S.zx[t] = p.zx[(size_t)w * D + d]; S.ux[t] = p.ux[(size_t)w * D + d]; }
+  __syncthreads();
+  if (t < 2 * F) {
+    const int f = t >> 1; const double* x = (t & 1) ? &S.ux[6 * f + 3] : &S.zx[6 * f + 3]; const double* R = S.fr[f].R;
+    double* o = (t & 1) ? S.ru[f] : S.rz[f];
+    o[0] = R[0] * x[0] + R[1] * x[1] + R[2] * x[2]; o[1] = R[3] * x[0] + R[4] * x[1] + R[5] * x[2]; o[2] = R[6] * x[0] + R[7] * x[1] + R[8] * x[2];
+  }
+  __syncthreads();
   const double* ftd = p.frame_td + (size_t)w * F;
-  const double mu = st.mu;
+  const double mu = st.mu, sqi = p.sqrt_info_px;
   double sums[6] = {0, 0, 0, 0, 0, 0};  // dlg2, gn2, gz, zEz, uEz, uHu
-  for (int l = t; l < nlm; l += blockDim.x) {
-    const double v = p.lm_v[(size_t)w * p.Lm + l];
+  for (int base = 0; base < nlm; base += 256 * LPT) {
+   if (base > 0) load_chunk(base);
+#pragma unroll
+   for (int q = 0; q < LPT; q++) {
+    if (lL[q] < 0) continue;
+    const int l = base + t + 256 * q;
+    const double v = lv[q];
     if (!(v > 0.0)) { p.lm_z[(size_t)w * p.Lm + l] = 0.0; continue; }  // fixed or unobserved landmark
-    const double gl = p.lm_g[(size_t)w * p.Lm + l], s_l = p.lm_s[(size_t)w * p.Lm + l];
-    const int i = start[l], L = tlen[l], ob = obeg[l];
-    LmCtx lc; landmark_ctx(S.fr[i], S.cam, obs[ob], ftd[i], p.invdep[(size_t)w * p.Lm + l], lc);
+    const double gl = lgl[q], s_l = ls[q];
+    const int i = li[q], L = lL[q], ob = lob[q];
+    LmCtx lc; landmark_ctx(S.fr[i], S.cam, loi[q], ftd[i], llam[q], lc);
+    // host-frame part: x_i^p - (Xw - Pi) x (Ri x_i^th)
+    const V3 ei = mk3(lc.Xw.x - S.fr[i].P[0], lc.Xw.y - S.fr[i].P[1], lc.Xw.z - S.fr[i].P[2]);
+    const V3 hz = mk3(S.zx[6 * i], S.zx[6 * i + 1], S.zx[6 * i + 2]) - cross(ei, ld3(S.rz[i]));
+    const V3 hu = mk3(S.ux[6 * i], S.ux[6 * i + 1], S.ux[6 * i + 2]) - cross(ei, ld3(S.ru[i]));
     double az = 0.0, cu = 0.0;  // w_l^T z_x, w_l^T u_x
+    float4 oj = lo1[q];
     for (int k = 1; k < L; k++) {
       const int j = i + k;
-      double r0, r1, Jx[6], Jj[12]; V3 pcj;
-      obs_residual(S.fr[j], S.cam, lc, obs[ob + k], ftd[j], p.sqrt_info_px, r0, r1, pcj);
-      obs_jacobians(S.fr[j], S.cam, lc, pcj, p.sqrt_info_px, Jx, Jj);
-      double hr, sc; huber(p.huber, r0 * r0 + r1 * r1, hr, sc);
-      const double jl0 = sc * (Jx[0] * lc.dXdl.x + Jx[1] * lc.dXdl.y + Jx[2] * lc.dXdl.z);
-      const double jl1 = sc * (Jx[3] * lc.dXdl.x + Jx[4] * lc.dXdl.y + Jx[5] * lc.dXdl.z);
-#pragma unroll
-      for (int r = 0; r < 2; r++) {
-        const double jl = r == 0 ? jl0 : jl1;
-        double tz = 0, tu = 0;
-        // J_i * [z_i] with Ji = [Jx | Jx Gi]
-        double zi[6], ui[6];
-#pragma unroll
-        for (int c = 0; c < 6; c++) { zi[c] = S.zx[6 * i + c]; ui[c] = S.ux[6 * i + c]; }
-        const V3 gz3 = mul(lc.Gi, mk3(zi[3], zi[4], zi[5])), gu3 = mul(lc.Gi, mk3(ui[3], ui[4], ui[5]));
-        tz += Jx[r * 3] * (zi[0] + gz3.x) + Jx[r * 3 + 1] * (zi[1] + gz3.y) + Jx[r * 3 + 2] * (zi[2] + gz3.z);
-        tu += Jx[r * 3] * (ui[0] + gu3.x) + Jx[r * 3 + 1] * (ui[1] + gu3.y) + Jx[r * 3 + 2] * (ui[2] + gu3.z);
-#pragma unroll
-        for (int c = 0; c < 6; c++) { tz += Jj[r * 6 + c] * S.zx[6 * j + c]; tu += Jj[r * 6 + c] * S.ux[6 * j + c]; }
-        az += sc * jl * tz; cu += sc * jl * tu;
-      }
+      const FrameCtx& fj = S.fr[j];
+      const float4 o = oj;
+      if (k + 1 < L) oj = obs[ob + k + 1];
+      const V3 d = mk3(lc.Xw.x - fj.P[0], lc.Xw.y - fj.P[1], lc.Xw.z - fj.P[2]);
+      const double px = fj.A[0] * d.x + fj.A[1] * d.y + fj.A[2] * d.z - S.cam.rtt[0];
+      const double py = fj.A[3] * d.x + fj.A[4] * d.y + fj.A[5] * d.z - S.cam.rtt[1];
+      const double pz = fj.A[6] * d.x + fj.A[7] * d.y + fj.A[8] * d.z - S.cam.rtt[2];
+      const double dt = S.cam.td - ftd[j];
+      const double iz = fast_rcp(pz);
+      const double r0 = sqi * (px * iz - ((double)o.x - dt * (double)o.z)), r1 = sqi * (py * iz - ((double)o.y - dt * (double)o.w));
+      // Jx enters twice (through j_lambda and through the pose Jacobians): the Huber scale appears squared, rho' = delta / |r|
+      const double sq = r0 * r0 + r1 * r1, hb = p.huber * p.huber;
+      const double sc2 = sq > hb ? p.huber * fast_rsqrt(sq) : 1.0;
+      const double a = sc2 * sqi * sqi * iz * iz;
+      const double qx = -px * iz, qy = -py * iz;   // unscaled rows of Jx / (sqrt_info / z): (A0 + qx A2), (A1 + qy A2)
+      const double j00 = fj.A[0] + qx * fj.A[6], j01 = fj.A[1] + qx * fj.A[7], j02 = fj.A[2] + qx * fj.A[8];
+      const double j10 = fj.A[3] + qy * fj.A[6], j11 = fj.A[4] + qy * fj.A[7], j12 = fj.A[5] + qy * fj.A[8];
+      const double jl0 = j00 * lc.dXdl.x + j01 * lc.dXdl.y + j02 * lc.dXdl.z, jl1 = j10 * lc.dXdl.x + j11 * lc.dXdl.y + j12 * lc.dXdl.z;
+      const V3 tz = hz - mk3(S.zx[6 * j], S.zx[6 * j + 1], S.zx[6 * j + 2]) + cross(d, ld3(S.rz[j]));
+      const V3 tu = hu - mk3(S.ux[6 * j], S.ux[6 * j + 1], S.ux[6 * j + 2]) + cross(d, ld3(S.ru[j]));
+      az += a * (jl0 * (j00 * tz.x + j01 * tz.y + j02 * tz.z) + jl1 * (j10 * tz.x + j11 * tz.y + j12 * tz.z));
+      cu += a * (jl0 * (j00 * tu.x + j01 * tu.y + j02 * tu.z) + jl1 * (j10 * tu.x + j11 * tu.y + j12 * tu.z));
     }
     const double d2 = fmin(fmax(s_l * s_l * v, 1e-6), 1e32);
     const double e = d2 / (s_l * s_l);
@@ -548,6 +589,7 @@ __global__ void __launch_bounds__(256, 2) k_backsub(KP p, int w0) {
     sums[3] += az * az / vp + 2.0 * az * z + v * z * z;             // landmark part of z^T H z
     sums[4] += cu * az / vp + cu * z + u * az + v * u * z;          // landmark part of u^T H z
     sums[5] += cu * cu / vp + 2.0 * u * cu + v * u * u;             // landmark part of u^T H u
+   }
   }
   block_sum<6>(sums, S.red);
   if (t == 0) { double* cs = p.c_sums + (size_t)w * 8; for (int i = 0; i < 6; i++) cs[i] = sums[i]; }
@@ -617,26 +659,38 @@ __global__ void __launch_bounds__(288, 2) k_cand_eval(KP p, int w0) {
   const int32_t* start = p.start + (size_t)w * p.Lm; const int32_t* tlen = p.tlen + (size_t)w * p.Lm; const int32_t* obeg = p.obeg + (size_t)w * p.Lm;
   const float4* obs = p.obs + (size_t)w * p.Om;
   const double* ftd = p.frame_td + (size_t)w * F;
+  const double sqi = p.sqrt_info_px;
   for (int l = t; l < nlm && t < 256; l += 256) {
-    const double v = p.lm_v[(size_t)w * p.Lm + l];
-    const double lam = p.invdep[(size_t)w * p.Lm + l];
+    const size_t o = (size_t)w * p.Lm + l;
+    const int i = start[l], L = tlen[l], ob = obeg[l];
+    const double v = p.lm_v[o], lam = p.invdep[o];
+    const float4 oi = obs[ob];
+    float4 oj = obs[ob + (L > 1 ? 1 : 0)];
     double lam_c = lam;
     if (v > 0.0) {
-      const double gl = p.lm_g[(size_t)w * p.Lm + l], s_l = p.lm_s[(size_t)w * p.Lm + l];
+      const double s_l = p.lm_s[o];
       const double d2 = fmin(fmax(s_l * s_l * v, 1e-6), 1e32);
-      const double u = s_l * s_l * gl / d2;
-      const double dl = -(a * u + b * p.lm_z[(size_t)w * p.Lm + l]);
+      const double u = s_l * s_l * p.lm_g[o] / d2;
+      const double dl = -(a * u + b * p.lm_z[o]);
       lam_c = lam + dl;
       acc[1] += dl * dl; acc[2] += lam * lam;
     }
-    p.invdep_c[(size_t)w * p.Lm + l] = lam_c;
-    const int i = start[l], L = tlen[l], ob = obeg[l];
-    LmCtx lc; landmark_ctx(S.fr[i], S.cam, obs[ob], ftd[i], lam_c, lc);
+    p.invdep_c[o] = lam_c;
+    LmCtx lc; landmark_ctx(S.fr[i], S.cam, oi, ftd[i], lam_c, lc);
     for (int k = 1; k < L; k++) {
-      double r0, r1; V3 pcj;
-      obs_residual(S.fr[i + k], S.cam, lc, obs[ob + k], ftd[i + k], p.sqrt_info_px, r0, r1, pcj);
-      double hr, sc; huber(p.huber, r0 * r0 + r1 * r1, hr, sc);
-      acc[0] += hr;
+      const FrameCtx& fj = S.fr[i + k];
+      const float4 ok = oj;
+      if (k + 1 < L) oj = obs[ob + k + 1];
+      const double dx = lc.Xw.x - fj.P[0], dy = lc.Xw.y - fj.P[1], dz = lc.Xw.z - fj.P[2];
+      const double px = fj.A[0] * dx + fj.A[1] * dy + fj.A[2] * dz - S.cam.rtt[0];
+      const double py = fj.A[3] * dx + fj.A[4] * dy + fj.A[5] * dz - S.cam.rtt[1];
+      const double pz = fj.A[6] * dx + fj.A[7] * dy + fj.A[8] * dz - S.cam.rtt[2];
+      const double dt = S.cam.td - ftd[i + k];
+      const double iz = fast_rcp(pz);
+      const double r0 = sqi * (px * iz - ((double)ok.x - dt * (double)ok.z)), r1 = sqi * (py * iz - ((double)ok.y - dt * (double)ok.w));
+      // 0.5 * rho(s) of ceres::HuberLoss
+      const double sq = r0 * r0 + r1 * r1, hb = p.huber * p.huber;
+      acc[0] += sq > hb ? 0.5 * (2.0 * p.huber * (sq * fast_rsqrt(sq)) - hb) : 0.5 * sq;
     }
   }
   if (p.planes && t < 256) {  // LiDAR plane residuals at the candidate

@@ -302,9 +302,15 @@ __global__ void __launch_bounds__(kLinThreads, 2) k_linearize(KP p, int w0) {
     if (q.have && q.L > 1) q.o1 = obs[q.ob + min(1 + (wid * nk) / kLinWarps, q.L - 1)];
     return q;
   };
+#ifdef GF2_PHASE_CLOCKS
+  long long lc_t0 = clock64(), lc_step = 0, lc_syrk = 0, lc_a, lc_b, lc_c;
+#endif
   LaneLm nxt = fetch_lm(fetch_info(0));
   int4 info_n = fetch_info(kLinWarps);
   for (int tbase = 0; tbase < ntasks; tbase += kLinWarps) {
+#ifdef GF2_PHASE_CLOCKS
+    lc_a = clock64();
+#endif
     const int task = tbase + wid;
     const bool have_task = task < ntasks;
     const int i = have_task ? S.task_start[task] : 0;
@@ -446,6 +452,9 @@ __global__ void __launch_bounds__(kLinThreads, 2) k_linearize(KP p, int w0) {
     nxt = fetch_lm(info_n);
     info_n = fetch_info(tbase + 2 * kLinWarps);
     __syncthreads();
+#ifdef GF2_PHASE_CLOCKS
+    lc_b = clock64();
+#endif
     // Schur SYRK on the fp64 tensor cores: C[a-tile][b-tile] += sum_l Ws[l][a] * Ws[l][b]
     {
       const int a_min = row0 >> 3;
@@ -457,7 +466,13 @@ __global__ void __launch_bounds__(kLinThreads, 2) k_linearize(KP p, int w0) {
       }
     }
     __syncthreads();
+#ifdef GF2_PHASE_CLOCKS
+    lc_c = clock64(); lc_step += lc_b - lc_a; lc_syrk += lc_c - lc_b;
+#endif
   }
+#ifdef GF2_PHASE_CLOCKS
+  const long long lc_t1 = clock64();
+#endif
 
   // Schur tiles -> dense 72x72 (upper tiles) in WT, which is free now
   switch (wid) {
@@ -569,6 +584,9 @@ __global__ void __launch_bounds__(kLinThreads, 2) k_linearize(KP p, int w0) {
     double gm = 0; for (int i2 = 0; i2 < kLinWarps; i2++) gm = fmax(gm, S.red[i2]);
     p.c_lin[(size_t)w * 4] = red2[0]; p.c_gmax[w] = gm;
   }
+#ifdef GF2_PHASE_CLOCKS
+  if (t == 0 && blockIdx.x == 300) printf("k_linearize clocks: init %lld step %lld syrk %lld tail %lld total %lld\n", lc_t1 - lc_t0 - lc_step - lc_syrk, lc_step, lc_syrk, clock64() - lc_t1, clock64() - lc_t0);
+#endif
 }
 
 }  // namespace gf2

@@ -19,7 +19,7 @@ __device__ __forceinline__ int bidx(int I, int J) { return (I * (I + 1) / 2 + J)
 // ------------------------------------------------------------------------------------------------ k_nonvis
 // IMUFactor linearisation (VE/factor/imu_factor.h:28-191): per factor the 30x30 J^T J (packed lower), J^T r and cost.
 // Marginalization prior (VE/factor/marginalization_factor.cpp:344-392): r = r0 + J0 dx, gradient J0^T r, cost.
-__global__ void __launch_bounds__(kNonvisThreads) k_nonvis(KP p, int w0) {
+__global__ void __launch_bounds__(kNonvisThreads, 2) k_nonvis(KP p, int w0) {
   const int w = w0 + blockIdx.x;
   WinState& st = p.st[w];
   if (!st.active || st.reuse) return;
@@ -161,6 +161,9 @@ __global__ void __launch_bounds__(kNonvisThreads) k_nonvis(KP p, int w0) {
 // windows share one SM (the kernel is a chain of short dependent phases; a second resident CTA fills the bubbles).
 constexpr int kNearBlk = 15 * kBS, kFarBlk = 6 * kBS;
 
+constexpr int kNBlkPairsS = kMaxF * (kMaxF + 1) / 2;
+static_assert(kSolveThreads >= 15 * kMaxF, "one thread per tangent dimension in the assembly");
+
 struct Solve2Shared {
   double g[kMaxF * 16], gs[kMaxF * 16], Hd[kMaxF * 16], s[kMaxF * 16], e[kMaxF * 16], u[kMaxF * 16], z[kMaxF * 16];
   double yu[kMaxF * 16], fw[kMaxF * 16];  // L^T u and the forward-substitution result (= L^T z)
@@ -223,6 +226,13 @@ __global__ void __launch_bounds__(kSolveThreads, 2) k_solve2(KP p, int w0) {
   const int NB = F * (F + 1) / 2;
   const int NA = solve2_matrix_doubles(F);
   double* A = S.A;
+#ifdef GF2_PHASE_CLOCKS
+  long long pc[16]; int npc = 0;
+#define GF2_PC() do { __syncthreads(); pc[npc++] = clock64(); } while (0)
+#else
+#define GF2_PC() do {} while (0)
+#endif
+  GF2_PC();
   if (t < NB) {  // block offsets, row-major over the lower triangle
     int I = 0; while ((I + 1) * (I + 2) / 2 <= t) I++;
     const int J = t - I * (I + 1) / 2;
@@ -231,21 +241,48 @@ __global__ void __launch_bounds__(kSolveThreads, 2) k_solve2(KP p, int w0) {
     off += (J <= I - 2) ? J * kFarBlk : ((I >= 2 ? (I - 1) * kFarBlk : 0) + (J - (I >= 1 ? I - 1 : 0)) * kNearBlk);
     S.boff[I * kMaxF + J] = off; S.blin[t] = off;
   }
+  // ---- assembly. Every global load of the visual and IMU parts is issued before anything waits on one (the per-element
+  // load -> shared-memory update loops this replaces cost 40k cycles of exposed DRAM latency per window)
+  // and never summed in flight (an accumulate-as-you-load chain waits one DRAM latency per element). Thread t < 225 owns
+  // element e = t of every 15x15 IMU block; the visual blocks are spread over all threads.
+  constexpr int kVisPT = (kNBlkPairsS * 36 + kSolveThreads - 1) / kSolveThreads;          // 10
+  const double* Svis = p.Svis + (size_t)w * kNVMax * kNVMax;
+  const double* Hw = p.imu ? p.imu_H + (size_t)w * (F - 1) * 675 : nullptr;
+  const bool imu_on = Hw != nullptr && t < 225;
+  double vis[kVisPT], hii[kMaxF - 1], hji[kMaxF - 1], hjj[kMaxF - 1];  // blocks (i,i), (j,i), (j,j) of IMU factor K
+#pragma unroll
+  for (int u = 0; u < kVisPT; u++) { const int idx = t + u * kSolveThreads; vis[u] = idx < NB * 36 ? Svis[idx] : 0.0; }
+#pragma unroll
+  for (int K = 0; K < kMaxF - 1; K++) {
+    const bool on = imu_on && K < F - 1;
+    hii[K] = on ? Hw[K * 675 + t] : 0.0; hji[K] = on ? Hw[K * 675 + 225 + t] : 0.0; hjj[K] = on ? Hw[K * 675 + 450 + t] : 0.0;
+  }
+  double gv = 0.0, gsv = 0.0, udv = 0.0, gimu = 0.0;
+  if (t < NV) { gv = p.gvis[(size_t)w * kNVP + t]; gsv = p.gschur[(size_t)w * kNVP + t]; udv = p.Udiag[(size_t)w * kNVMax + t]; }
+  if (p.imu && t < D) {
+    const double* gw = p.imu_g + (size_t)w * (F - 1) * 30;
+    const int K = t / 15, r = t % 15;
+    if (K > 0) gimu += gw[(K - 1) * 30 + 15 + r];
+    if (K < F - 1) gimu += gw[K * 30 + r];
+  }
+  GF2_PC();
   for (int i = t; i < NA; i += nt) A[i] = 0.0;
   for (int i = t; i < F * 16; i += nt) { S.g[i] = 0.0; S.gs[i] = 0.0; S.Hd[i] = 0.0; S.z[i] = 0.0; S.u[i] = 0.0; }
   __syncthreads();
+  GF2_PC();
   auto bidx2 = [&](int I, int J) -> int { return S.boff[I * kMaxF + J]; };
   // element (i, j), j <= i, global tangent indices; rows a far block does not store read as zero / are never written
   auto stored = [&](int i, int j) -> bool { const int I = i / 15, J = j / 15; return (I - J < 2) || (i - 15 * I) < 6; };
   auto Ael2 = [&](int i, int j) -> double& { const int I = i / 15, J = j / 15; return A[bidx2(I, J) + (i - 15 * I) * kBS + (j - 15 * J)]; };
-  // ---- assembly: visual Schur complement (blocked 6x6 layout written by k_linearize: coalesced read, pose part of each block)
-  const double* Svis = p.Svis + (size_t)w * kNVMax * kNVMax;
-  for (int idx = t; idx < NB * 36; idx += nt) {
-    const int blk = idx / 36, e = idx % 36;
-    A[S.blin[blk] + (e / 6) * kBS + e % 6] = Svis[idx];
+  // visual Schur complement (blocked 6x6 layout written by k_linearize: coalesced read, pose part of each block)
+#pragma unroll
+  for (int u = 0; u < kVisPT; u++) {
+    const int idx = t + u * kSolveThreads;
+    if (idx < NB * 36) { const int blk = idx / 36, e = idx % 36; A[S.blin[blk] + (e / 6) * kBS + e % 6] = vis[u]; }
   }
-  if (t < NV) { const int da = 15 * (t / 6) + t % 6; S.g[da] = p.gvis[(size_t)w * kNVP + t]; S.gs[da] = p.gschur[(size_t)w * kNVP + t]; S.Hd[da] = p.Udiag[(size_t)w * kNVMax + t]; }
+  if (t < NV) { const int da = 15 * (t / 6) + t % 6; S.g[da] = gv; S.gs[da] = gsv; S.Hd[da] = udv; }
   __syncthreads();
+  GF2_PC();
   // ---- prior (H = J0^T J0 precomputed by k_prepare, gradient by k_nonvis)
   const int n = p.prior_rows ? p.prior_rows[w] : 0;
   if (n > 0) {
@@ -260,31 +297,21 @@ __global__ void __launch_bounds__(kSolveThreads, 2) k_solve2(KP p, int w0) {
     }
     __syncthreads();
   }
-  // ---- IMU blocks, by destination: A_KK += H_{K-1}[(j,j)] + H_K[(i,i)],  A_{K+1,K} += H_K[(j,i)]
+  GF2_PC();
+  // ---- IMU blocks, by destination: A_KK += H_{K-1}[(j,j)] + H_K[(i,i)],  A_{K+1,K} += H_K[(j,i)]  (values loaded above)
   if (p.imu) {
-    const double* Hw = p.imu_H + (size_t)w * (F - 1) * 675;
-    const double* gw = p.imu_g + (size_t)w * (F - 1) * 30;
-    for (int idx = t; idx < (2 * F - 1) * 225; idx += nt) {
-      const int e = idx % 225, r = e / 15, c = e % 15;
-      if (idx < F * 225) {
-        const int K = idx / 225;
-        double v = 0.0;
-        if (K > 0) v += Hw[(K - 1) * 675 + 450 + e];
-        if (K < F - 1) v += Hw[K * 675 + e];
+    if (t < 225) {
+      const int r = t / 15, c = t % 15;
+#pragma unroll
+      for (int K = 0; K < kMaxF; K++) {
+        if (K >= F) break;
+        const double v = (K > 0 ? hjj[K > 0 ? K - 1 : 0] : 0.0) + (K < kMaxF - 1 ? hii[K < kMaxF - 1 ? K : 0] : 0.0);
         if (c <= r) A[bidx2(K, K) + r * kBS + c] += v;
         if (r == c) S.Hd[15 * K + r] += v;
-      } else {
-        const int K = idx / 225 - F;
-        A[bidx2(K + 1, K) + r * kBS + c] += Hw[K * 675 + 225 + e];
+        if (K < F - 1) A[bidx2(K + 1, K) + r * kBS + c] += hji[K < kMaxF - 1 ? K : 0];
       }
     }
-    for (int i = t; i < D; i += nt) {
-      const int K = i / 15, r = i % 15;
-      double v = 0.0;
-      if (K > 0) v += gw[(K - 1) * 30 + 15 + r];
-      if (K < F - 1) v += gw[K * 30 + r];
-      S.g[i] += v;
-    }
+    if (t < D) S.g[t] += gimu;
     __syncthreads();
   }
   if (p.wheel) {  // wheel pose blocks, by destination like the IMU blocks (pose part = rows/cols 0..5 of a frame block)
@@ -322,6 +349,7 @@ __global__ void __launch_bounds__(kSolveThreads, 2) k_solve2(KP p, int w0) {
     }
     for (int i = t; i < D; i += nt) p.gfull[(size_t)w * D + i] = S.g[i] - S.gs[i];  // reduced gradient (rhs)
   }
+  GF2_PC();
   // ---- Jacobi scaling (iteration 0), dogleg diagonal, gradient quantities
   const double mu = st.mu;
   double sums[3] = {0, 0, 0};  // dlg2, uEu, -
@@ -371,7 +399,7 @@ __global__ void __launch_bounds__(kSolveThreads, 2) k_solve2(KP p, int w0) {
     for (int j = 0; j < 15; j++) {
       const double d = __shfl_sync(0xffffffffu, a[j], j);
       if (!(d > 0.0)) bad = true;
-      const double rs = rsqrt(fmax(d, 1e-300));  // fp64 sqrt/div are long dependent software sequences: one rsqrt + multiplies
+      const double rs = fast_rsqrt(fmax(d, 1e-300));  // fp64 sqrt/div are long dependent software sequences: one rsqrt + multiplies
       const double lj = (lane == j) ? d * rs : a[j] * rs;
       if (lane == j) S.dinv[16 * K + j] = rs;
       if (lane >= j) a[j] = lj;
@@ -384,16 +412,26 @@ __global__ void __launch_bounds__(kSolveThreads, 2) k_solve2(KP p, int w0) {
     }
     if (bad && lane == 0) S.flag = 1;
   };
+  GF2_PC();
+  // right-hand side g - g_schur, kept per block with stride 16; it rides along the factorisation as one more row of every
+  // panel (forward substitution for free): after block step K, S.fw[15 K ..] = (L^-1 rhs)_K
+  for (int i = t; i < D; i += nt) S.z[16 * (i / 15) + i % 15] = S.g[i] - S.gs[i];
   if (wid == 0) factor_diag(0);
   __syncthreads();
+#ifdef GF2_PHASE_CLOCKS
+  long long cp_panel = 0, cp_w0 = 0, cp_trail = 0, cq0, cq1, cq2, cq3;
+#endif
   for (int K = 0; K < F && !S.flag; K++) {
+#ifdef GF2_PHASE_CLOCKS
+    cq0 = clock64();
+#endif
     const double* Akk = A + bidx2(K, K);
     // panel: X L_KK^T = A_IK, one thread per stored row of the block column (15 rows of the near block, 6 of each far one)
     const int prow = (K + 1 < F ? 15 : 0) + 6 * (F - 2 - K > 0 ? F - 2 - K : 0);
-    if (t < prow) {
-      const int I = t < 15 ? K + 1 : K + 2 + (t - 15) / 6, rr = t < 15 ? t : (t - 15) % 6;
-      double* row = A + bidx2(I, K) + rr * kBS;
+    const int pI = t < 15 ? K + 1 : K + 2 + (t - 15) / 6, prr = t < 15 ? t : (t - 15) % 6;
+    if (t <= prow) {  // t == prow: the right-hand-side row
       double x[15];
+      double* row = t < prow ? A + bidx2(pI, K) + prr * kBS : &S.z[16 * K];
 #pragma unroll
       for (int c = 0; c < 15; c++) x[c] = row[c];
 #pragma unroll
@@ -403,10 +441,22 @@ __global__ void __launch_bounds__(kSolveThreads, 2) k_solve2(KP p, int w0) {
         for (int k = 0; k < c; k++) acc -= x[k] * Akk[c * kBS + k];
         x[c] = acc * S.dinv[16 * K + c];
       }
+      double* out = t < prow ? row : &S.fw[15 * K];
 #pragma unroll
-      for (int c = 0; c < 15; c++) row[c] = x[c];
+      for (int c = 0; c < 15; c++) out[c] = x[c];
     }
     __syncthreads();
+    if (t < prow) {  // right-hand side of the rows below: rhs_I[rr] -= L_IK[rr, :] . fw_K
+      const double* row = A + bidx2(pI, K) + prr * kBS;
+      double acc = 0.0;
+#pragma unroll
+      for (int c = 0; c < 15; c++) acc += row[c] * S.fw[15 * K + c];
+      S.z[16 * pI + prr] -= acc;
+    }
+    __syncthreads();
+#ifdef GF2_PHASE_CLOCKS
+    cq1 = clock64();
+#endif
     // trailing update on the fp64 tensor cores: A_IJ -= L_IK L_JK^T for K < J <= I
     {
       const int m = F - 1 - K;
@@ -415,15 +465,23 @@ __global__ void __launch_bounds__(kSolveThreads, 2) k_solve2(KP p, int w0) {
         if (npairs > 0) { block_mma(A + bidx2(K + 1, K + 1), A + bidx2(K + 1, K), A + bidx2(K + 1, K), 15, 15, 15, lane); __syncwarp(); factor_diag(K + 1); }
       } else {
         for (int q = wid; q < npairs; q += nwarp - 1) {  // pairs 1 .. npairs-1 over warps 1..7 (pair 0 = (K+1, K+1) is warp 0's)
-          int a = 0; while ((a + 1) * (a + 2) / 2 <= q) a++;
+          int a = (int)((sqrtf(8.0f * (float)q + 1.0f) - 1.0f) * 0.5f);  // row of pair q in the lower triangle
+          if ((a + 1) * (a + 2) / 2 <= q) a++; else if (a * (a + 1) / 2 > q) a--;
           const int b = q - a * (a + 1) / 2;
           const int I = K + 1 + a, J = K + 1 + b;
           block_mma(A + bidx2(I, J), A + bidx2(I, K), A + bidx2(J, K), brows(I, J), brows(I, K), brows(J, K), lane);
         }
       }
     }
+#ifdef GF2_PHASE_CLOCKS
+    cq2 = clock64();
+#endif
     __syncthreads();
+#ifdef GF2_PHASE_CLOCKS
+    cq3 = clock64(); cp_panel += cq1 - cq0; cp_w0 += cq2 - cq1; cp_trail += cq3 - cq1;
+#endif
   }
+
   if (S.flag == 1) {  // LINEAR_SOLVER_FAILURE -> invalid step (mu *= 10, re-linearise); DESIGN.md "deviations"
     if (t == 0) {
       st.mu *= 10.0; st.reuse = 0; st.iteration++; st.invalid_count++;
@@ -433,6 +491,7 @@ __global__ void __launch_bounds__(kSolveThreads, 2) k_solve2(KP p, int w0) {
     }
     return;
   }
+  GF2_PC();
   // ---- yu = L^T u (needs the diagonal blocks as factored, before they are overwritten by their inverses)
   for (int col = t; col < D; col += nt) {
     const int J = col / 15, c = col % 15;
@@ -445,6 +504,7 @@ __global__ void __launch_bounds__(kSolveThreads, 2) k_solve2(KP p, int w0) {
     S.yu[col] = yu;
   }
   __syncthreads();
+  GF2_PC();
   // ---- inverses of the diagonal blocks IN PLACE, all K in parallel (lane = column of L^-1, forward substitution down the rows)
   for (int K = wid; K < F; K += nwarp) {
     double* Akk = A + bidx2(K, K);
@@ -464,48 +524,39 @@ __global__ void __launch_bounds__(kSolveThreads, 2) k_solve2(KP p, int w0) {
       for (int r = 0; r < 15; r++) Akk[r * kBS + lane] = (r >= lane) ? x[r] : 0.0;
     }
   }
-  // ---- z = S'^-1 (g - g_schur): forward then backward block substitution by warp 0 alone (block-wide barriers cost more
-  // than the 2 x 11 small steps); z kept per block with stride 16
-  for (int i = t; i < D; i += nt) S.z[16 * (i / 15) + i % 15] = S.g[i] - S.gs[i];
+  GF2_PC();
+  // ---- z = L^-T fw: backward block substitution (the forward half was done inside the factorisation); the block solve by
+  // warp 0, the column updates by one thread per column. z kept per block with stride 16.
+  for (int i = t; i < D; i += nt) S.z[16 * (i / 15) + i % 15] = S.fw[i];
   __syncthreads();
-  if (wid == 0) {
-    for (int K = 0; K < F; K++) {
+  for (int K = F - 1; K >= 0; K--) {
+    if (wid == 0) {  // z_K = L_KK^-T z_K (explicit inverse)
       const double* Li = A + bidx2(K, K);
       double v = 0;
-      if (lane < 15) { for (int c = 0; c <= lane; c++) v += Li[lane * kBS + c] * S.z[16 * K + c]; }
-      __syncwarp();
-      if (lane < 15) { S.z[16 * K + lane] = v; S.fw[15 * K + lane] = v; }
-      __syncwarp();
-      const int prow = (K + 1 < F ? 15 : 0) + 6 * (F - 2 - K > 0 ? F - 2 - K : 0);
-      for (int row = lane; row < prow; row += 32) {
-        const int I = row < 15 ? K + 1 : K + 2 + (row - 15) / 6, r = row < 15 ? row : (row - 15) % 6;
-        const double* Lr = A + bidx2(I, K) + r * kBS;
-        double acc = 0;
+      if (lane < 15) {
 #pragma unroll
-        for (int c = 0; c < 15; c++) acc += Lr[c] * S.z[16 * K + c];
-        S.z[16 * I + r] -= acc;
+        for (int r = 0; r < 15; r++) v += (r >= lane) ? Li[r * kBS + lane] * S.z[16 * K + r] : 0.0;
       }
-      __syncwarp();
-    }
-    for (int K = F - 1; K >= 0; K--) {
-      const double* Li = A + bidx2(K, K);
-      double v = 0;
-      if (lane < 15) { for (int r = lane; r < 15; r++) v += Li[r * kBS + lane] * S.z[16 * K + r]; }
       __syncwarp();
       if (lane < 15) S.z[16 * K + lane] = v;
-      __syncwarp();
-      for (int col = lane; col < 15 * K; col += 32) {
-        const int J = col / 15, c = col % 15;
-        const double* Lc = A + bidx2(K, J) + c;
-        const int nr = brows(K, J);
-        double acc = 0;
-        for (int r = 0; r < nr; r++) acc += Lc[r * kBS] * S.z[16 * K + r];
-        S.z[16 * J + c] -= acc;
-      }
-      __syncwarp();
     }
+    __syncthreads();
+    if (t < 15 * K) {  // z_J -= L_KJ^T z_K for all J < K, one column per thread
+      const int J = t / 15, c = t % 15;
+      const double* Lc = A + bidx2(K, J) + c;
+      double acc = 0.0;
+      if (K - J >= 2) {
+#pragma unroll
+        for (int r = 0; r < 6; r++) acc += Lc[r * kBS] * S.z[16 * K + r];
+      } else {
+#pragma unroll
+        for (int r = 0; r < 15; r++) acc += Lc[r * kBS] * S.z[16 * K + r];
+      }
+      S.z[16 * J + c] -= acc;
+    }
+    __syncthreads();
   }
-  __syncthreads();
+  GF2_PC();
   // quadratic forms of the model cost change through the factor: u^T S' u = |L^T u|^2, u^T S' z = (L^T u) . (L^T z),
   // z^T S' z = |L^T z|^2 with L^T z = the forward-substitution result
   double s3[3] = {0, 0, 0};  // uSu, uSz, zSz
@@ -524,6 +575,10 @@ __global__ void __launch_bounds__(kSolveThreads, 2) k_solve2(KP p, int w0) {
   }
   block_sum<4>(s2, S.red);
   if (t == 0) { st.gn2_x = s2[0]; st.gz_x = s2[1]; st.zEz_x = s2[2]; st.uEz_x = s2[3]; st.lin_valid = 1; }
+  GF2_PC();
+#ifdef GF2_PHASE_CLOCKS
+  if (t == 0 && blockIdx.x == 300) { printf("k_solve2 phases:"); for (int i = 1; i < npc; i++) printf(" %lld", pc[i] - pc[i - 1]); printf(" total %lld\n", pc[npc - 1] - pc[0]); }
+#endif
 }
 
 }  // namespace gf2
