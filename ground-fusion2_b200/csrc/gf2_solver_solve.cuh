@@ -215,6 +215,54 @@ __device__ __forceinline__ void block_mma(double* c, const double* x, const doub
     }
 }
 
+// One row of a panel: x L_KK^T = a (15 entries) by one thread, x -> out (may alias in). Out of line for the same reason as
+// factor_diag_block.
+__device__ __noinline__ void panel_row(const double* in, const double* Akk, const double* dinv, double* out) {
+  double x[15];
+#pragma unroll
+  for (int c = 0; c < 15; c++) x[c] = in[c];
+#pragma unroll
+  for (int c = 0; c < 15; c++) {
+    double acc = x[c];
+#pragma unroll
+    for (int k = 0; k < c; k++) acc -= x[k] * Akk[c * kBS + k];
+    x[c] = acc * dinv[c];
+  }
+#pragma unroll
+  for (int c = 0; c < 15; c++) out[c] = x[c];
+}
+
+// Cholesky factor of one 15x15 diagonal block in place by one warp: lane = row, the row lives in registers, pivots and
+// column entries travel by shuffle; the reciprocal pivots go to dinv. Returns true when a pivot is not positive. Kept out of
+// line so that the fully unrolled pivot chain is register-allocated on its own (inlined twice into k_solve2 it fell back to
+// local memory, on the kernel's critical path).
+template <int J>
+__device__ __forceinline__ void chol_pivot(double (&a)[15], double* dinv, int lane, bool& bad) {
+  if constexpr (J < 15) {
+    const double d = __shfl_sync(0xffffffffu, a[J], J);
+    if (!(d > 0.0)) bad = true;
+    const double rs = fast_rsqrt(fmax(d, 1e-300));  // fp64 sqrt/div are long dependent software sequences: one rsqrt + multiplies
+    const double lj = (lane == J) ? d * rs : a[J] * rs;
+    if (lane == J) dinv[J] = rs;
+    if (lane >= J) a[J] = lj;
+#pragma unroll
+    for (int k = J + 1; k < 15; k++) { const double lkj = __shfl_sync(0xffffffffu, lj, k); if (lane >= k) a[k] -= lj * lkj; }
+    chol_pivot<J + 1>(a, dinv, lane, bad);  // compile-time recursion: the pivot loop must be fully unrolled for a[] to stay in registers
+  }
+}
+__device__ __noinline__ bool factor_diag_block(double* Akk, double* dinv, int lane) {
+  double a[15];
+#pragma unroll
+  for (int c = 0; c < 15; c++) a[c] = (lane < 15 && c <= lane) ? Akk[lane * kBS + c] : 0.0;
+  bool bad = false;
+  chol_pivot<0>(a, dinv, lane, bad);
+  if (lane < 15) {
+#pragma unroll
+    for (int c = 0; c < 15; c++) Akk[lane * kBS + c] = (c <= lane) ? a[c] : 0.0;
+  }
+  return bad;
+}
+
 __global__ void __launch_bounds__(kSolveThreads, 2) k_solve2(KP p, int w0) {
   const int w = w0 + blockIdx.x;
   WinState& st = p.st[w];
@@ -389,30 +437,7 @@ __global__ void __launch_bounds__(kSolveThreads, 2) k_solve2(KP p, int w0) {
 
   // ---- blocked Cholesky (right-looking over the frame blocks) with one-step look-ahead: warp 0 factors diagonal block
   // K+1 as soon as its own trailing pair (K+1, K+1) is done, while warps 1..7 finish the rest of trailing update K
-  auto factor_diag = [&](int K) {  // executed by warp 0; lane = row, the row lives in registers
-    double* Akk = A + bidx2(K, K);
-    double a[15];
-#pragma unroll
-    for (int c = 0; c < 15; c++) a[c] = (lane < 15 && c <= lane) ? Akk[lane * kBS + c] : 0.0;
-    bool bad = false;
-#pragma unroll
-    for (int j = 0; j < 15; j++) {
-      const double d = __shfl_sync(0xffffffffu, a[j], j);
-      if (!(d > 0.0)) bad = true;
-      const double rs = fast_rsqrt(fmax(d, 1e-300));  // fp64 sqrt/div are long dependent software sequences: one rsqrt + multiplies
-      const double lj = (lane == j) ? d * rs : a[j] * rs;
-      if (lane == j) S.dinv[16 * K + j] = rs;
-      if (lane >= j) a[j] = lj;
-#pragma unroll
-      for (int k = j + 1; k < 15; k++) { const double lkj = __shfl_sync(0xffffffffu, lj, k); if (lane >= k) a[k] -= lj * lkj; }
-    }
-    if (lane < 15) {
-#pragma unroll
-      for (int c = 0; c < 15; c++) Akk[lane * kBS + c] = (c <= lane) ? a[c] : 0.0;
-    }
-    if (bad && lane == 0) S.flag = 1;
-  };
-  GF2_PC();
+  auto factor_diag = [&](int K) { if (factor_diag_block(A + bidx2(K, K), &S.dinv[16 * K], lane) && lane == 0) S.flag = 1; };  // by warp 0
   // right-hand side g - g_schur, kept per block with stride 16; it rides along the factorisation as one more row of every
   // panel (forward substitution for free): after block step K, S.fw[15 K ..] = (L^-1 rhs)_K
   for (int i = t; i < D; i += nt) S.z[16 * (i / 15) + i % 15] = S.g[i] - S.gs[i];
@@ -429,22 +454,8 @@ __global__ void __launch_bounds__(kSolveThreads, 2) k_solve2(KP p, int w0) {
     // panel: X L_KK^T = A_IK, one thread per stored row of the block column (15 rows of the near block, 6 of each far one)
     const int prow = (K + 1 < F ? 15 : 0) + 6 * (F - 2 - K > 0 ? F - 2 - K : 0);
     const int pI = t < 15 ? K + 1 : K + 2 + (t - 15) / 6, prr = t < 15 ? t : (t - 15) % 6;
-    if (t <= prow) {  // t == prow: the right-hand-side row
-      double x[15];
-      double* row = t < prow ? A + bidx2(pI, K) + prr * kBS : &S.z[16 * K];
-#pragma unroll
-      for (int c = 0; c < 15; c++) x[c] = row[c];
-#pragma unroll
-      for (int c = 0; c < 15; c++) {
-        double acc = x[c];
-#pragma unroll
-        for (int k = 0; k < c; k++) acc -= x[k] * Akk[c * kBS + k];
-        x[c] = acc * S.dinv[16 * K + c];
-      }
-      double* out = t < prow ? row : &S.fw[15 * K];
-#pragma unroll
-      for (int c = 0; c < 15; c++) out[c] = x[c];
-    }
+    if (t < prow) { double* row = A + bidx2(pI, K) + prr * kBS; panel_row(row, Akk, &S.dinv[16 * K], row); }
+    else if (t == prow) panel_row(&S.z[16 * K], Akk, &S.dinv[16 * K], &S.fw[15 * K]);  // the right-hand-side row
     __syncthreads();
     if (t < prow) {  // right-hand side of the rows below: rhs_I[rr] -= L_IK[rr, :] . fw_K
       const double* row = A + bidx2(pI, K) + prr * kBS;
