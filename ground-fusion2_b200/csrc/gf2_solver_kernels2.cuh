@@ -496,33 +496,15 @@ struct StepShared {
   int decision;
 };
 
-__global__ void __launch_bounds__(256, 2) k_backsub(KP p, int w0) {
+__global__ void __launch_bounds__(256, 3) k_backsub(KP p, int w0) {
   const int w = w0 + blockIdx.x;
   WinState& st = p.st[w];
   if (!st.active || st.reuse || !st.lin_valid) return;
   __shared__ StepShared S;
   const int t = threadIdx.x, F = p.F, D = p.D, NV = 6 * F;
-  // landmark records of this thread (4 per pass), loaded before the frame prologue so that the global-memory latency of the
-  // table -> first-observation chain is hidden behind it
-  constexpr int LPT = 4;
   const int nlm = p.nlm[w];
   const int32_t* start = p.start + (size_t)w * p.Lm; const int32_t* tlen = p.tlen + (size_t)w * p.Lm; const int32_t* obeg = p.obeg + (size_t)w * p.Lm;
   const float4* obs = p.obs + (size_t)w * p.Om;
-  double lv[LPT], llam[LPT], lgl[LPT], ls[LPT]; int li[LPT], lL[LPT], lob[LPT]; float4 loi[LPT], lo1[LPT];
-  auto load_chunk = [&](int base) {
-#pragma unroll
-    for (int q = 0; q < LPT; q++) {
-      const int l = base + t + 256 * q;
-      lL[q] = -1;
-      if (l < nlm) {
-        const size_t o = (size_t)w * p.Lm + l;
-        lv[q] = p.lm_v[o]; llam[q] = p.invdep[o]; lgl[q] = p.lm_g[o]; ls[q] = p.lm_s[o];
-        li[q] = start[l]; lL[q] = tlen[l]; lob[q] = obeg[l];
-        loi[q] = obs[lob[q]]; lo1[q] = obs[lob[q] + (lL[q] > 1 ? 1 : 0)];
-      }
-    }
-  };
-  load_chunk(0);
   build_frames(p.pose + (size_t)w * F * 7, p.ex + (size_t)w * 7, p.td[w], F, S.fr, &S.cam);
   if (t < NV) { const int d = 15 * (t / 6) + t % 6; S.zx[t] = p.zx[(size_t)w * D + d]; S.ux[t] = p.ux[(size_t)w * D + d]; }
   __syncthreads();
@@ -535,23 +517,20 @@ __global__ void __launch_bounds__(256, 2) k_backsub(KP p, int w0) {
   const double* ftd = p.frame_td + (size_t)w * F;
   const double mu = st.mu, sqi = p.sqrt_info_px;
   double sums[6] = {0, 0, 0, 0, 0, 0};  // dlg2, gn2, gz, zEz, uEz, uHu
-  for (int base = 0; base < nlm; base += 256 * LPT) {
-   if (base > 0) load_chunk(base);
-#pragma unroll
-   for (int q = 0; q < LPT; q++) {
-    if (lL[q] < 0) continue;
-    const int l = base + t + 256 * q;
-    const double v = lv[q];
-    if (!(v > 0.0)) { p.lm_z[(size_t)w * p.Lm + l] = 0.0; continue; }  // fixed or unobserved landmark
-    const double gl = lgl[q], s_l = ls[q];
-    const int i = li[q], L = lL[q], ob = lob[q];
-    LmCtx lc; landmark_ctx(S.fr[i], S.cam, loi[q], ftd[i], llam[q], lc);
-    // host-frame part: x_i^p - (Xw - Pi) x (Ri x_i^th)
-    const V3 ei = mk3(lc.Xw.x - S.fr[i].P[0], lc.Xw.y - S.fr[i].P[1], lc.Xw.z - S.fr[i].P[2]);
-    const V3 hz = mk3(S.zx[6 * i], S.zx[6 * i + 1], S.zx[6 * i + 2]) - cross(ei, ld3(S.rz[i]));
-    const V3 hu = mk3(S.ux[6 * i], S.ux[6 * i + 1], S.ux[6 * i + 2]) - cross(ei, ld3(S.ru[i]));
+  for (int l = t; l < nlm; l += blockDim.x) {
+   {
+    const size_t o = (size_t)w * p.Lm + l;
+    const double v = p.lm_v[o];
+    if (!(v > 0.0)) { p.lm_z[o] = 0.0; continue; }  // fixed or unobserved landmark
+    const int i = start[l], L = tlen[l], ob = obeg[l];
+    const double gl = p.lm_g[o], s_l = p.lm_s[o];
+    LmCtx lc; landmark_ctx(S.fr[i], S.cam, obs[ob], ftd[i], p.invdep[o], lc);
+    float4 lo1 = obs[ob + (L > 1 ? 1 : 0)];
+    // per observation only m = Jx^T j_lambda (Huber-weighted) and c = m x d are formed:
+    //   w_l^T x = (sum m) . (x_i^p - e_i x (Ri x_i^th))  +  sum_k ( -m_k . x_j^p + c_k . (Rj x_j^th) )
     double az = 0.0, cu = 0.0;  // w_l^T z_x, w_l^T u_x
-    float4 oj = lo1[q];
+    V3 ms = mk3(0, 0, 0);
+    float4 oj = lo1;
     for (int k = 1; k < L; k++) {
       const int j = i + k;
       const FrameCtx& fj = S.fr[j];
@@ -568,14 +547,21 @@ __global__ void __launch_bounds__(256, 2) k_backsub(KP p, int w0) {
       const double sq = r0 * r0 + r1 * r1, hb = p.huber * p.huber;
       const double sc2 = sq > hb ? p.huber * fast_rsqrt(sq) : 1.0;
       const double a = sc2 * sqi * sqi * iz * iz;
-      const double qx = -px * iz, qy = -py * iz;   // unscaled rows of Jx / (sqrt_info / z): (A0 + qx A2), (A1 + qy A2)
+      const double qx = -px * iz, qy = -py * iz;   // rows of Jx / (sqrt_info / z): (A0 + qx A2), (A1 + qy A2)
       const double j00 = fj.A[0] + qx * fj.A[6], j01 = fj.A[1] + qx * fj.A[7], j02 = fj.A[2] + qx * fj.A[8];
       const double j10 = fj.A[3] + qy * fj.A[6], j11 = fj.A[4] + qy * fj.A[7], j12 = fj.A[5] + qy * fj.A[8];
-      const double jl0 = j00 * lc.dXdl.x + j01 * lc.dXdl.y + j02 * lc.dXdl.z, jl1 = j10 * lc.dXdl.x + j11 * lc.dXdl.y + j12 * lc.dXdl.z;
-      const V3 tz = hz - mk3(S.zx[6 * j], S.zx[6 * j + 1], S.zx[6 * j + 2]) + cross(d, ld3(S.rz[j]));
-      const V3 tu = hu - mk3(S.ux[6 * j], S.ux[6 * j + 1], S.ux[6 * j + 2]) + cross(d, ld3(S.ru[j]));
-      az += a * (jl0 * (j00 * tz.x + j01 * tz.y + j02 * tz.z) + jl1 * (j10 * tz.x + j11 * tz.y + j12 * tz.z));
-      cu += a * (jl0 * (j00 * tu.x + j01 * tu.y + j02 * tu.z) + jl1 * (j10 * tu.x + j11 * tu.y + j12 * tu.z));
+      const double jl0 = a * (j00 * lc.dXdl.x + j01 * lc.dXdl.y + j02 * lc.dXdl.z), jl1 = a * (j10 * lc.dXdl.x + j11 * lc.dXdl.y + j12 * lc.dXdl.z);
+      const V3 m = mk3(jl0 * j00 + jl1 * j10, jl0 * j01 + jl1 * j11, jl0 * j02 + jl1 * j12);
+      const V3 c = cross(m, d);
+      ms = ms + m;
+      az += c.x * S.rz[j][0] + c.y * S.rz[j][1] + c.z * S.rz[j][2] - (m.x * S.zx[6 * j] + m.y * S.zx[6 * j + 1] + m.z * S.zx[6 * j + 2]);
+      cu += c.x * S.ru[j][0] + c.y * S.ru[j][1] + c.z * S.ru[j][2] - (m.x * S.ux[6 * j] + m.y * S.ux[6 * j + 1] + m.z * S.ux[6 * j + 2]);
+    }
+    {  // host-frame part
+      const V3 ei = mk3(lc.Xw.x - S.fr[i].P[0], lc.Xw.y - S.fr[i].P[1], lc.Xw.z - S.fr[i].P[2]);
+      const V3 hz = mk3(S.zx[6 * i], S.zx[6 * i + 1], S.zx[6 * i + 2]) - cross(ei, ld3(S.rz[i]));
+      const V3 hu = mk3(S.ux[6 * i], S.ux[6 * i + 1], S.ux[6 * i + 2]) - cross(ei, ld3(S.ru[i]));
+      az += dot(ms, hz); cu += dot(ms, hu);
     }
     const double d2 = fmin(fmax(s_l * s_l * v, 1e-6), 1e32);
     const double e = d2 / (s_l * s_l);
