@@ -32,8 +32,11 @@ for _p in (ROOT, os.path.join(ROOT, "oracle")):
 N_OBS, N_LM, N_FRAMES, N_IMU, D_RED = 6500, 1000, 11, 10, 165
 PRIOR_STRIDE = 8   # row stride of the prior arrays (the anchor prior of this workload has 6 rows)
 # DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of one k_linearize launch per window, from the ncu --set full capture
-# summarised in profiles/ncu_full_k_linearize_B4096_r1.csv (753.4 MB at 4096 windows)
-TRAFFIC_PER_WINDOW = 753.4e6 / 4096
+# summarised in profiles/ncu_full_solver_kernels_B4096_r1.csv (629.2 MB read + 135.2 MB written at 4096 windows)
+TRAFFIC_PER_WINDOW = 764.4e6 / 4096
+# fp64 tensor sub-pipe activity (sm__inst_executed_pipe_tensor_subpipe_dmma, % of peak) from the same capture: north_star asks for
+# tensor-pipe utilisation of the reduced solve next to the HBM fraction of the Jacobian sweep
+NCU_DMMA_PCT = {"k_linearize": 34.4, "k_solve2": 8.9}
 BYTES_SWEEP = N_OBS * 20 + N_LM * 32 + N_FRAMES * 136 + 64 + N_IMU * 1456 + (D_RED * (D_RED + 1) // 2 + D_RED) * 8  # = 289,000
 
 
@@ -170,8 +173,8 @@ def run_reference(args, rank, world):
     synth = importlib.import_module("gf2_b200.synth")
     import gf2_oracle as orc
     T = host_threads()
-    n = max(T, 8)  # windows per step: one per thread, ~0.1 s each
-    w = synth.make_windows(n, n_landmarks=N_LM)
+    n = max(T, 8) * 24  # windows per step: a bounded sample of the workload, ~0.1 s per window per thread => ~2.5 s per step
+    w = make_batch(gf2, synth, n, min(args.distinct, n), pinned=False)
     orc.imu_preintegrate(w)
     opts = gf2.abi.default_opts()
     init = {k: w[k].copy() for k in ("para_pose", "para_speedbias", "inv_depth")}
@@ -380,6 +383,8 @@ def main():
             "roofline": {"bound": "hbm", "kernel": "k_linearize", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved / peaks["hbm_gbs"], "traffic": TRAFFIC_PER_WINDOW * B, "traffic_source": "ncu --set full capture of k_linearize, profiles/ (per window x windows per launch)", "peak_source": which,
                          "algorithmic_bytes_per_launch": BYTES_SWEEP * B, "avg_launch_ms": lin_avg_ms},
+            "reduced_solve": {"kernels": "k_nonvis + k_solve2", "avg_ms_per_iteration": solve_ms / n_lin, "bound": "serial pivot chain (latency), not the tensor pipe",
+                              "dmma_pipe_pct_ncu": NCU_DMMA_PCT, "source": "profiles/ncu_full_solver_kernels_B4096_r1.csv"},
             "marginalize": marg, "lk": lk_line,
             "phase_ms_per_step": {"linearize": lin_ms / args.steps, "reduced_solve": solve_ms / args.steps, "backsub_candidate": step_ms / args.steps,
                                   "solve_total": total_ms / args.steps},
@@ -387,8 +392,8 @@ def main():
         if not args.no_cpu_baseline:
             import gf2_oracle as orc
             T = host_threads()
-            n = max(T, 8) * 2
-            wc = synth.make_windows(n, n_landmarks=N_LM)
+            n = max(T, 8) * 96  # bounded sample: ~0.1 s per window per thread => ~10 s of CPU work on every host thread
+            wc = make_batch(gf2, synth, n, min(args.distinct, n), pinned=False)
             t0 = time.perf_counter()
             orc.imu_preintegrate(wc)
             orc.solve_batch(wc, opts, n_threads=T)
