@@ -43,6 +43,7 @@ ABI_SYMBOLS = [
     "gf2_set_planes", "gf2_marginalize", "gf2_get_prior", "gf2_last_marginalize_ms", "gf2_solve", "gf2_linearize", "gf2_reduced_dim", "gf2_get_reduced_system", "gf2_get_states",
     "gf2_get_landmarks", "gf2_comm_init", "gf2_comm_unique_id", "gf2_last_timing", "gf2_tracker_create",
     "gf2_tracker_destroy", "gf2_tracker_track", "gf2_tracker_track_fb", "gf2_tracker_last_timing",
+    "gf2_tracker_track_image", "gf2_tracker_detect", "gf2_tracker_min_eigen_map", "gf2_detect_select",
 ]
 
 
@@ -251,6 +252,16 @@ class Solver:
         return {"total_ms": t[0], "linearize_ms": t[1], "solve_ms": t[2], "step_ms": t[3], "launches": int(t[4]), "linearize_launches": int(t[5]), "prepare_ms": t[6]}
 
 
+def detect_select(idx, val, width, height, max_corners, min_distance):
+    """Host half of the detector (no device needed): cv's corner selection over candidates (flat index y*W+x, float32 score)."""
+    b = np.asarray(val, np.float32).view(np.uint32).astype(np.uint64)
+    ordered = np.where(b & np.uint64(0x80000000), ~b & np.uint64(0xffffffff), b | np.uint64(0x80000000))
+    keys = np.ascontiguousarray((ordered << np.uint64(32)) | np.asarray(idx, np.uint64))
+    out = np.zeros((max(int(max_corners), 1), 2), np.float32); n = np.zeros(1, np.int32)
+    _check(lib().gf2_detect_select(_p(keys), len(keys), int(width), int(height), int(max_corners), C.c_double(min_distance), _p(out), _p(n)))
+    return out[:n[0]].copy()
+
+
 class Tracker:
     """Batched pyramidal LK: cv::calcOpticalFlowPyrLK as FeatureTracker::trackImage calls it (feature_tracker.cpp:122-142)."""
 
@@ -312,7 +323,52 @@ class Tracker:
         _check(lib().gf2_tracker_track_fb(self.h, S, _p(prev), _p(cur), C.c_size_t(self.cfg.width), _p(npts), _p(pts), _p(out), _p(status), int(ml)))
         return out, status
 
+    def track_image(self, prev, cur, prev_pts, predict_pts=None, n_pts=None, flow_back=True, max_level=None):
+        """The whole LK stage of trackImage (feature_tracker.cpp:113-153): optional prediction (level-1 LK from predict_pts, per-stream
+        fall-back to max_level when fewer than 10 points succeed) and the reverse check. Returns (cur_pts, status)."""
+        S, prev, cur, pts, npts = self._prep(prev, cur, prev_pts, n_pts)
+        pred = None
+        if predict_pts is not None:
+            pp = np.asarray(predict_pts, np.float32)
+            pp = pp[None] if pp.ndim == 2 else pp
+            pred = np.zeros_like(pts)
+            for s in range(S):
+                pred[s, :pp[s].shape[0]] = pp[s]
+        out = np.zeros_like(pts); status = np.zeros((S, self.cfg.max_pts), np.uint8)
+        ml = self.cfg.max_level if max_level is None else max_level
+        _check(lib().gf2_tracker_track_image(self.h, S, _p(prev), _p(cur), C.c_size_t(self.cfg.width), _p(npts), _p(pts), _p(pred), int(bool(flow_back)),
+                                             _p(out), _p(status), int(ml)))
+        return out, status
+
+    def _imgs(self, img):
+        if img is None:
+            return None, None
+        img = np.ascontiguousarray(img, np.uint8)
+        return (img[None] if img.ndim == 2 else img), None
+
+    def detect(self, img, max_corners, mask=None, quality_level=0.01, min_distance=30.0, n_streams=None):
+        """cv::goodFeaturesToTrack(img, max_corners, quality_level, min_distance, mask) as trackImage calls it (feature_tracker.cpp:198).
+        img [H, W] or [S, H, W] uint8, or None = the `cur` image of the last track call. Returns a list of [n_s, 2] float32 arrays."""
+        im, _ = self._imgs(img)
+        S = im.shape[0] if im is not None else (n_streams or 1)
+        mk = None
+        if mask is not None:
+            mk = np.ascontiguousarray(mask, np.uint8)
+            mk = mk[None] if mk.ndim == 2 else mk
+        mc = np.broadcast_to(np.asarray(max_corners, np.int32), (S,)).copy()
+        out = np.zeros((S, self.cfg.max_pts, 2), np.float32); n = np.zeros(S, np.int32)
+        _check(lib().gf2_tracker_detect(self.h, S, _p(im), C.c_size_t(self.cfg.width), _p(mk), _p(mc), C.c_double(quality_level), C.c_double(min_distance),
+                                        _p(out), _p(n)))
+        return [out[s, :n[s]].copy() for s in range(S)]
+
+    def min_eigen_map(self, img):
+        """cv::cornerMinEigenVal(img, 3, 3) of [H, W] or [S, H, W] uint8 images -> float32 [S, H, W]."""
+        im, _ = self._imgs(img)
+        eig = np.zeros((im.shape[0], self.cfg.height, self.cfg.width), np.float32)
+        _check(lib().gf2_tracker_min_eigen_map(self.h, im.shape[0], _p(im), C.c_size_t(self.cfg.width), _p(eig)))
+        return eig
+
     def last_timing(self):
         t = np.zeros(8)
         _check(lib().gf2_tracker_last_timing(self.h, _p(t)))
-        return {"total_ms": t[0], "pyramid_ms": t[1], "lk_ms": t[2], "launches": int(t[3])}
+        return {"total_ms": t[0], "pyramid_ms": t[1], "lk_ms": t[2], "launches": int(t[3]), "detect_ms": t[4], "candidates": int(t[5])}

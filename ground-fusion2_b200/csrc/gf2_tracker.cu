@@ -6,12 +6,18 @@
 //   k_lk        one warp per point: all pyramid levels coarse -> fine in one launch; the 21x21 template (I, Ix, Iy) lives in
 //               registers (14 pixels per lane), window sums are exact int64 warp reductions, the 2x2 solve is float32 with
 //               the operation order of OpenCV's lkpyramid.cpp (no FMA contraction)
+//   k_gftt_*    cv::goodFeaturesToTrack (feature_tracker.cpp:198): Sobel -> covariance planes -> 3x3 box sums with cv's running
+//               double column sum -> min eigenvalue (bit-exact with cv2.cornerMinEigenVal), masked maximum, threshold + 3x3
+//               non-maximum suppression -> candidate keys; the greedy min-distance selection runs on the host inside the
+//               library because the feature-id order depends on it (integer-exact)
 // The integer patch extraction (14-bit fixed-point bilinear weights, CV_DESCALE) is bit-exact with OpenCV; only the window
 // sums differ (OpenCV accumulates them in float32 in SIMD-path order), i.e. by float32 rounding of A and b.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string.h>
 #include <vector>
+#include <algorithm>
+#include <math.h>
 #include "gf2_common.h"
 
 namespace gf2 {
@@ -80,6 +86,7 @@ struct LkArgs {
   int n_streams, max_pts, win, max_level, max_iters, flags;
   float min_eig; double eps2;
   const int32_t* n_pts;       // [n_streams]
+  const int32_t* gate;        // [n_streams] or null: streams with gate == 0 are left untouched (prediction fall-back pass)
   const float* prev_pts;      // [n_streams][max_pts][2]
   float* next_pts;            // in (initial flow) / out
   uint8_t* status; float* err;
@@ -105,6 +112,7 @@ __global__ void __launch_bounds__(128) k_lk(LkArgs a) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int s = warp / a.max_pts, i = warp % a.max_pts;
   if (s >= a.n_streams || i >= a.n_pts[s]) return;
+  if (a.gate && !a.gate[s]) return;
   const int win = a.win, npx = win * win;
   const float half = (win - 1) * 0.5f;
   const float2 pp = reinterpret_cast<const float2*>(a.prev_pts)[(size_t)s * a.max_pts + i];
@@ -226,6 +234,18 @@ __global__ void k_fb_check(int total, const float* prev_pts, const float* rev_pt
   status[i] = (status[i] && rstatus[i] && d <= 0.5) ? 1 : 0;
 }
 
+// succ_num < 10 -> redo the stream at full depth without the prediction (feature_tracker.cpp:124-131)
+__global__ void k_count_gate(int max_pts, const int32_t* __restrict__ n_pts, const uint8_t* __restrict__ status, int min_succ, int32_t* __restrict__ gate) {
+  const int s = blockIdx.x;
+  int c = 0;
+  for (int i = threadIdx.x; i < n_pts[s]; i += 32) c += status[(size_t)s * max_pts + i] ? 1 : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if (threadIdx.x == 0) gate[s] = c < min_succ ? 1 : 0;
+}
+
+#include "gf2_tracker_detect.cuh"
+
 }  // namespace gf2
 
 using namespace gf2;
@@ -237,6 +257,11 @@ struct gf2_tracker {
   size_t img_stride[kMaxLevels], der_stride[kMaxLevels];
   int cur_slot = 0; bool have_prev = false;
   int32_t* d_npts; float *d_prev_pts, *d_next_pts, *d_rev_pts, *d_err; uint8_t *d_status, *d_rstatus;
+  int32_t* d_gate;
+  // detector (allocated by the first gf2_tracker_detect / gf2_tracker_min_eigen_map)
+  float *d_cov = nullptr, *d_eig = nullptr; uint8_t *d_mask = nullptr, *d_det_img = nullptr; unsigned* d_vmax = nullptr;
+  unsigned long long* d_keys = nullptr; int32_t *d_count = nullptr, *d_want = nullptr; int key_cap = 0;
+  std::vector<unsigned long long> h_keys; std::vector<int32_t> h_count;
   std::vector<void*> allocs;
   cudaEvent_t ev[4];
   double timing[8];
@@ -289,7 +314,8 @@ int gf2_tracker_create(const gf2_tracker_cfg* cfg, gf2_tracker** out) {
   }
   const size_t np = (size_t)S * cfg->max_pts;
   ok = ok && alloc((void**)&h->d_npts, sizeof(int32_t) * S) && alloc((void**)&h->d_prev_pts, sizeof(float) * 2 * np) && alloc((void**)&h->d_next_pts, sizeof(float) * 2 * np) &&
-       alloc((void**)&h->d_rev_pts, sizeof(float) * 2 * np) && alloc((void**)&h->d_err, sizeof(float) * np) && alloc((void**)&h->d_status, np) && alloc((void**)&h->d_rstatus, np);
+       alloc((void**)&h->d_rev_pts, sizeof(float) * 2 * np) && alloc((void**)&h->d_err, sizeof(float) * np) && alloc((void**)&h->d_status, np) && alloc((void**)&h->d_rstatus, np) &&
+       alloc((void**)&h->d_gate, sizeof(int32_t) * S);
   if (!ok) { gf2_tracker_destroy(h); return gf2::fail(GF2_ERR_CUDA, "tracker allocation failed"); }
   for (auto& e : h->ev) cudaEventCreate(&e);
   *out = h;
@@ -306,12 +332,13 @@ void gf2_tracker_destroy(gf2_tracker* h) {
   delete h;
 }
 
-static int lk_launch(gf2_tracker* h, int n_streams, int slotI, int slotJ, const float* d_prev, float* d_next, uint8_t* d_status, float* d_err, int flags, int max_level) {
+static int lk_launch(gf2_tracker* h, int n_streams, int slotI, int slotJ, const float* d_prev, float* d_next, uint8_t* d_status, float* d_err, int flags, int max_level,
+                     const int32_t* d_gate = nullptr) {
   LkArgs a;
   memset(&a, 0, sizeof(a));
   a.n_streams = n_streams; a.max_pts = h->cfg.max_pts; a.win = h->cfg.win; a.max_level = max_level; a.max_iters = h->cfg.max_iters; a.flags = flags;
   a.min_eig = (float)h->cfg.min_eig; a.eps2 = h->cfg.eps * h->cfg.eps;
-  a.n_pts = h->d_npts; a.prev_pts = d_prev; a.next_pts = d_next; a.status = d_status; a.err = d_err;
+  a.n_pts = h->d_npts; a.gate = d_gate; a.prev_pts = d_prev; a.next_pts = d_next; a.status = d_status; a.err = d_err;
   for (int l = 0; l < kMaxLevels; l++) { a.img_stride[l] = h->img_stride[l]; a.der_stride[l] = h->der_stride[l]; }
   a.I = h->pyr[slotI]; a.J = h->pyr[slotJ];
   const int warps = n_streams * h->cfg.max_pts;
@@ -321,7 +348,7 @@ static int lk_launch(gf2_tracker* h, int n_streams, int slotI, int slotJ, const 
 }
 
 static int track_common(gf2_tracker* h, int n_streams, const uint8_t* prev, const uint8_t* cur, size_t stride, const int32_t* n_pts, const float* prev_pts,
-                        float* cur_pts, uint8_t* status, float* err, int flags, int max_level, bool fb) {
+                        float* cur_pts, uint8_t* status, float* err, int flags, int max_level, bool fb, const float* predict_pts = nullptr) {
   if (!h || !cur || !n_pts || !prev_pts || !cur_pts || !status) return gf2::fail(GF2_ERR_INVALID, "null argument");
   if (n_streams < 1 || n_streams > h->cfg.max_streams) return gf2::fail(GF2_ERR_INVALID, "n_streams %d outside [1, %d]", n_streams, h->cfg.max_streams);
   if (max_level < 0 || max_level > h->cfg.max_level) return gf2::fail(GF2_ERR_INVALID, "max_level %d exceeds the tracker capacity %d", max_level, h->cfg.max_level);
@@ -336,9 +363,19 @@ static int track_common(gf2_tracker* h, int n_streams, const uint8_t* prev, cons
   { int rc = build_pyramid(h, slotJ, n_streams, cur, stride, true, h->cfg.max_level); if (rc) return rc; }  // derivatives of cur: reverse pass now, template of the next call
   GF2T_CUDA(cudaMemcpyAsync(h->d_npts, n_pts, sizeof(int32_t) * n_streams, cudaMemcpyHostToDevice, h->stream));
   GF2T_CUDA(cudaMemcpyAsync(h->d_prev_pts, prev_pts, sizeof(float) * 2 * np, cudaMemcpyHostToDevice, h->stream));
-  if (flags & GF2_LK_USE_INITIAL_FLOW) GF2T_CUDA(cudaMemcpyAsync(h->d_next_pts, cur_pts, sizeof(float) * 2 * np, cudaMemcpyHostToDevice, h->stream));
+  if (predict_pts) GF2T_CUDA(cudaMemcpyAsync(h->d_next_pts, predict_pts, sizeof(float) * 2 * np, cudaMemcpyHostToDevice, h->stream));
+  else if (flags & GF2_LK_USE_INITIAL_FLOW) GF2T_CUDA(cudaMemcpyAsync(h->d_next_pts, cur_pts, sizeof(float) * 2 * np, cudaMemcpyHostToDevice, h->stream));
   cudaEventRecord(h->ev[1], h->stream);
-  { int rc = lk_launch(h, n_streams, slotI, slotJ, h->d_prev_pts, h->d_next_pts, h->d_status, h->d_err, flags, max_level); if (rc) return rc; }
+  if (predict_pts) {
+    // hasPrediction (feature_tracker.cpp:118-131): level-1 LK from the predicted positions; a stream with fewer than 10 successes
+    // is redone at max_level from prev_pts (flags 0), decided on the device per stream
+    const int ml1 = 1 < h->cfg.max_level ? 1 : h->cfg.max_level;
+    { int rc = lk_launch(h, n_streams, slotI, slotJ, h->d_prev_pts, h->d_next_pts, h->d_status, h->d_err, GF2_LK_USE_INITIAL_FLOW, ml1); if (rc) return rc; }
+    k_count_gate<<<n_streams, 32, 0, h->stream>>>(h->cfg.max_pts, h->d_npts, h->d_status, 10, h->d_gate);
+    { int rc = lk_launch(h, n_streams, slotI, slotJ, h->d_prev_pts, h->d_next_pts, h->d_status, h->d_err, 0, max_level, h->d_gate); if (rc) return rc; }
+  } else {
+    int rc = lk_launch(h, n_streams, slotI, slotJ, h->d_prev_pts, h->d_next_pts, h->d_status, h->d_err, flags, max_level); if (rc) return rc;
+  }
   if (fb) {
     // reverse: cur -> prev at maxLevel 1 with the initial flow = prev_pts (feature_tracker.cpp:139-142)
     GF2T_CUDA(cudaMemcpyAsync(h->d_rev_pts, h->d_prev_pts, sizeof(float) * 2 * np, cudaMemcpyDeviceToDevice, h->stream));
@@ -357,7 +394,7 @@ static int track_common(gf2_tracker* h, int n_streams, const uint8_t* prev, cons
   cudaEventElapsedTime(&ms, h->ev[0], h->ev[3]); h->timing[0] = ms;
   cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]); h->timing[1] = ms;  // upload + pyramids + derivatives
   cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]); h->timing[2] = ms;  // LK kernels
-  h->timing[3] = (prev ? 2.0 : 1.0) * (h->cfg.max_level + (h->cfg.max_level + 1)) + (fb ? 3.0 : 1.0);  // launches
+  h->timing[3] = (prev ? 2.0 : 1.0) * (h->cfg.max_level + (h->cfg.max_level + 1)) + (fb ? 3.0 : 1.0) + (predict_pts ? 2.0 : 0.0);  // launches
   return GF2_OK;
 }
 
@@ -369,6 +406,147 @@ int gf2_tracker_track_fb(gf2_tracker* h, int n_streams, const uint8_t* prev, con
                          const float* prev_pts, float* cur_pts, uint8_t* status, int max_level) {
   return track_common(h, n_streams, prev, cur, stride, n_pts, prev_pts, cur_pts, status, nullptr, 0, max_level, true);
 }
+int gf2_tracker_track_image(gf2_tracker* h, int n_streams, const uint8_t* prev, const uint8_t* cur, size_t stride, const int32_t* n_pts,
+                            const float* prev_pts, const float* predict_pts, int flow_back, float* cur_pts, uint8_t* status, int max_level) {
+  return track_common(h, n_streams, prev, cur, stride, n_pts, prev_pts, cur_pts, status, nullptr, 0, max_level, flow_back != 0, predict_pts);
+}
+
+// ---------------------------------------------------------------------------------------------------------------- detector
+// featureselect.cpp: candidates in greaterThanPtr order (a max-heap pops them lazily: selection usually stops early), greedy
+// acceptance against the corners already taken within min_distance, looked up through a grid of cell size cvRound(min_distance).
+// K (n sort keys ordered(value) << 32 | y * W + x) is reordered in place. Returns the number of corners written to O.
+static int select_corners(unsigned long long* K, int n, int W, int H, int want, double min_distance, float* O) {
+  if (n <= 0 || want <= 0) return 0;
+  const bool spaced = min_distance >= 1.0;
+  const int cell = spaced ? (int)lrint(min_distance) : 1;
+  const int gw = (W + cell - 1) / cell, gh = (H + cell - 1) / cell;
+  const double md2 = min_distance * min_distance;
+  std::vector<std::vector<int>> grid;
+  if (spaced) grid.assign((size_t)gw * gh, std::vector<int>());
+  int got = 0;
+  std::make_heap(K, K + n);
+  for (int left = n; left > 0 && got < want; left--) {
+    std::pop_heap(K, K + left);
+    const int idx = (int)(K[left - 1] & 0xffffffffu), y = idx / W, x = idx - y * W;
+    bool good = true;
+    if (spaced) {
+      const int xc = x / cell, yc = y / cell;
+      const int x1 = xc > 0 ? xc - 1 : 0, y1 = yc > 0 ? yc - 1 : 0, x2 = xc + 1 < gw ? xc + 1 : gw - 1, y2 = yc + 1 < gh ? yc + 1 : gh - 1;
+      for (int yy = y1; yy <= y2 && good; yy++)
+        for (int xx = x1; xx <= x2 && good; xx++)
+          for (int q : grid[(size_t)yy * gw + xx]) {
+            const int qy = q / W, qx = q - qy * W; const double dx = x - qx, dy = y - qy;
+            if (dx * dx + dy * dy < md2) { good = false; break; }
+          }
+      if (good) grid[(size_t)yc * gw + xc].push_back(idx);
+    }
+    if (good) { O[2 * got] = (float)x; O[2 * got + 1] = (float)y; got++; }
+  }
+  return got;
+}
+
+int gf2_detect_select(const uint64_t* keys, int n, int width, int height, int max_corners, double min_distance, float* out_xy, int32_t* out_n) {
+  if ((!keys && n > 0) || !out_xy || !out_n || n < 0 || width < 1 || height < 1 || max_corners < 0 || min_distance < 0.0) return gf2::fail(GF2_ERR_INVALID, "bad argument");
+  std::vector<unsigned long long> K(keys, keys + n);
+  *out_n = select_corners(K.data(), n, width, height, max_corners, min_distance, out_xy);
+  return GF2_OK;
+}
+
+static int detect_alloc(gf2_tracker* h) {
+  if (h->d_eig) return GF2_OK;
+  const int S = h->cfg.max_streams; const size_t plane = (size_t)h->cfg.width * h->cfg.height;
+  h->key_cap = (int)(plane / 4);   // a 3x3 local maximum excludes its 8 neighbours unless they tie; overflow is reported, never truncated silently
+  auto alloc = [&](void** p, size_t bytes) { if (cudaMalloc(p, bytes) != cudaSuccess) return false; h->allocs.push_back(*p); return true; };
+  const bool ok = alloc((void**)&h->d_cov, sizeof(float) * 3 * plane * S) && alloc((void**)&h->d_eig, sizeof(float) * plane * S) && alloc((void**)&h->d_mask, plane * S) &&
+                  alloc((void**)&h->d_det_img, plane * S) && alloc((void**)&h->d_vmax, sizeof(unsigned) * S) && alloc((void**)&h->d_keys, sizeof(unsigned long long) * (size_t)h->key_cap * S) &&
+                  alloc((void**)&h->d_count, sizeof(int32_t) * S) && alloc((void**)&h->d_want, sizeof(int32_t) * S);
+  if (!ok) { h->d_eig = nullptr; return gf2::fail(GF2_ERR_CUDA, "detector allocation failed"); }
+  h->h_count.resize(S);
+  return GF2_OK;
+}
+
+// Sobel -> covariance -> box sums -> min eigenvalue (+ masked maximum) of n_streams images on the handle's stream
+static int detect_eig(gf2_tracker* h, int n_streams, const uint8_t* img, size_t stride, const uint8_t* mask) {
+  const int W = h->cfg.width, H = h->cfg.height; const size_t plane = (size_t)W * H;
+  const uint8_t* d_img;
+  if (img) {
+    GF2T_CUDA(cudaMemcpy2DAsync(h->d_det_img, W, img, stride, W, (size_t)H * n_streams, cudaMemcpyHostToDevice, h->stream));
+    d_img = h->d_det_img;
+  } else {
+    if (!h->have_prev) return gf2::fail(GF2_ERR_INVALID, "img == NULL but no image is cached from an earlier gf2_tracker_track* call");
+    d_img = h->pyr[h->cur_slot].img[0];   // cur_img of the last track call
+  }
+  if (mask) GF2T_CUDA(cudaMemcpyAsync(h->d_mask, mask, plane * n_streams, cudaMemcpyHostToDevice, h->stream));
+  GF2T_CUDA(cudaMemsetAsync(h->d_vmax, 0, sizeof(unsigned) * n_streams, h->stream));
+  dim3 b(32, 8), g((W + 31) / 32, (H + 7) / 8, n_streams);
+  k_gftt_cov<<<g, b, 0, h->stream>>>(d_img, W, H, plane, h->d_cov);
+  k_gftt_eig<<<dim3((W + 63) / 64, n_streams), 64, 0, h->stream>>>(h->d_cov, mask ? h->d_mask : nullptr, W, H, h->d_eig, h->d_vmax);
+  GF2T_CUDA(cudaGetLastError());
+  return GF2_OK;
+}
+
+static int detect_check(gf2_tracker* h, int n_streams, const uint8_t* img, size_t stride) {
+  if (!h) return gf2::fail(GF2_ERR_INVALID, "null argument");
+  if (n_streams < 1 || n_streams > h->cfg.max_streams) return gf2::fail(GF2_ERR_INVALID, "n_streams %d outside [1, %d]", n_streams, h->cfg.max_streams);
+  if (img && stride < (size_t)h->cfg.width) return gf2::fail(GF2_ERR_INVALID, "stride smaller than the image width");
+  cudaSetDevice(h->cfg.device);
+  return detect_alloc(h);
+}
+
+int gf2_tracker_min_eigen_map(gf2_tracker* h, int n_streams, const uint8_t* img, size_t stride, float* eig) {
+  if (!eig) return gf2::fail(GF2_ERR_INVALID, "null argument");
+  { int rc = detect_check(h, n_streams, img, stride); if (rc) return rc; }
+  { int rc = detect_eig(h, n_streams, img, stride, nullptr); if (rc) return rc; }
+  GF2T_CUDA(cudaMemcpyAsync(eig, h->d_eig, sizeof(float) * (size_t)h->cfg.width * h->cfg.height * n_streams, cudaMemcpyDeviceToHost, h->stream));
+  GF2T_CUDA(cudaStreamSynchronize(h->stream));
+  return GF2_OK;
+}
+
+int gf2_tracker_detect(gf2_tracker* h, int n_streams, const uint8_t* img, size_t stride, const uint8_t* mask, const int32_t* max_corners,
+                       double quality_level, double min_distance, float* out_xy, int32_t* out_n) {
+  if (!max_corners || !out_xy || !out_n) return gf2::fail(GF2_ERR_INVALID, "null argument");
+  if (!(quality_level > 0.0) || min_distance < 0.0) return gf2::fail(GF2_ERR_INVALID, "quality_level must be > 0 and min_distance >= 0");
+  { int rc = detect_check(h, n_streams, img, stride); if (rc) return rc; }
+  for (int s = 0; s < n_streams; s++) if (max_corners[s] < 0) return gf2::fail(GF2_ERR_INVALID, "max_corners[%d] = %d is negative", s, max_corners[s]);
+  const int W = h->cfg.width, H = h->cfg.height;
+  cudaEventRecord(h->ev[0], h->stream);
+  { int rc = detect_eig(h, n_streams, img, stride, mask); if (rc) return rc; }
+  GF2T_CUDA(cudaMemcpyAsync(h->d_want, max_corners, sizeof(int32_t) * n_streams, cudaMemcpyHostToDevice, h->stream));
+  GF2T_CUDA(cudaMemsetAsync(h->d_count, 0, sizeof(int32_t) * n_streams, h->stream));
+  dim3 b(32, 8), g((W + 31) / 32, (H + 7) / 8, n_streams);
+  k_gftt_nms<<<g, b, 0, h->stream>>>(h->d_eig, mask ? h->d_mask : nullptr, W, H, h->d_vmax, quality_level, h->d_want, h->d_keys, h->key_cap, h->d_count);
+  GF2T_CUDA(cudaGetLastError());
+  cudaEventRecord(h->ev[1], h->stream);
+  GF2T_CUDA(cudaMemcpyAsync(h->h_count.data(), h->d_count, sizeof(int32_t) * n_streams, cudaMemcpyDeviceToHost, h->stream));
+  GF2T_CUDA(cudaStreamSynchronize(h->stream));
+  size_t total = 0;
+  for (int s = 0; s < n_streams; s++) {
+    if (h->h_count[s] > h->key_cap) return gf2::fail(GF2_ERR_INVALID, "stream %d: %d corner candidates exceed the capacity %d", s, h->h_count[s], h->key_cap);
+    total += (size_t)h->h_count[s];
+  }
+  h->h_keys.resize(total ? total : 1);
+  { size_t off = 0;
+    for (int s = 0; s < n_streams; s++) {
+      if (h->h_count[s]) GF2T_CUDA(cudaMemcpyAsync(h->h_keys.data() + off, h->d_keys + (size_t)s * h->key_cap, sizeof(unsigned long long) * h->h_count[s], cudaMemcpyDeviceToHost, h->stream));
+      off += (size_t)h->h_count[s];
+    } }
+  cudaEventRecord(h->ev[2], h->stream);
+  GF2T_CUDA(cudaStreamSynchronize(h->stream));
+  size_t off = 0;
+  for (int s = 0; s < n_streams; s++) {
+    const int n = h->h_count[s];
+    const int want = max_corners[s] < h->cfg.max_pts ? max_corners[s] : h->cfg.max_pts;
+    out_n[s] = select_corners(h->h_keys.data() + off, n, W, H, want, min_distance, out_xy + (size_t)s * h->cfg.max_pts * 2);
+    off += (size_t)n;
+  }
+  float ms; memset(h->timing, 0, sizeof(h->timing));
+  cudaEventElapsedTime(&ms, h->ev[0], h->ev[2]); h->timing[0] = ms;
+  cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]); h->timing[4] = ms;  // upload + detector kernels
+  h->timing[3] = 3.0;
+  h->timing[5] = (double)total;                                       // candidates moved to the host
+  return GF2_OK;
+}
+
 int gf2_tracker_last_timing(gf2_tracker* h, double out[8]) {
   if (!h || !out) return gf2::fail(GF2_ERR_INVALID, "null argument");
   memcpy(out, h->timing, sizeof(h->timing));

@@ -1,0 +1,111 @@
+// gf2_tracker_detect.cuh — cv::goodFeaturesToTrack(img, corners, maxCorners, 0.01, MIN_DIST, mask) as FeatureTracker::trackImage
+// calls it (VE/featureTracker/feature_tracker.cpp:198; blockSize 3, Sobel aperture 3, min-eigenvalue score) for a batch of
+// independent image streams. OpenCV is an un-vendored dependency; the float32 / float64 operation order below is the one that
+// reproduces cv2.cornerMinEigenVal bit for bit (probed against cv2 4.13; DESIGN.md section 4 documents it):
+//   k_gftt_cov   Sobel with the scale folded into the smoothing taps (fused multiply-adds exactly where cv's SIMD path has them),
+//                covariance planes xx, xy, yy in float32
+//   k_gftt_eig   3x3 box sums in double: row sums left to right, the column pass as cv's RUNNING sum down the image (one thread
+//                per column; the rounding history of that sum is part of the result), min eigenvalue, masked maximum
+//   k_gftt_nms   threshold at float(maxVal * qualityLevel), 3x3 dilation equality test, interior pixels, mask -> sort keys
+// included by gf2_tracker.cu (namespace gf2)
+
+__device__ __forceinline__ unsigned gftt_ordered(float f) {  // monotone float -> unsigned
+  const unsigned b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float gftt_unordered(unsigned k) { return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k); }
+
+// cov planes: [stream][3][H][W]
+__global__ void __launch_bounds__(256) k_gftt_cov(const uint8_t* __restrict__ img, int W, int H, size_t img_stride, float* __restrict__ cov) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y, s = blockIdx.z;
+  if (x >= W || y >= H) return;
+  const uint8_t* S = img + (size_t)s * img_stride;
+  const int xm = reflect101(x - 1, W), xp = reflect101(x + 1, W), ym = reflect101(y - 1, H), yp = reflect101(y + 1, H);
+  const uint8_t *r0 = S + (size_t)ym * W, *r1 = S + (size_t)y * W, *r2 = S + (size_t)yp * W;
+  const float s1 = (float)(1.0 / (4.0 * 3.0 * 255.0)), s2 = (float)(2.0 / (4.0 * 3.0 * 255.0));
+  const float a0 = r0[xm], b0 = r0[x], c0 = r0[xp], a1 = r1[xm], c1 = r1[xp], a2 = r2[xm], b2 = r2[x], c2 = r2[xp];
+  // Dx: row pass [-1 0 1] (exact), column pass [1 2 1]*scale as fma(d0 + d2, s, fl(d1 * 2s))
+  const float d0 = c0 - a0, d1 = c1 - a1, d2 = c2 - a2;
+  const float dx = __fmaf_rn(__fadd_rn(d0, d2), s1, __fmul_rn(d1, s2));
+  // Dy: row pass [1 2 1]*scale as fma(I[x+1], s, fma(I[x], 2s, fl(I[x-1] * s))), column pass [-1 0 1]
+  const float q0 = __fmaf_rn(c0, s1, __fmaf_rn(b0, s2, __fmul_rn(a0, s1)));
+  const float q2 = __fmaf_rn(c2, s1, __fmaf_rn(b2, s2, __fmul_rn(a2, s1)));
+  const float dy = __fsub_rn(q2, q0);
+  const size_t plane = (size_t)W * H;
+  float* C = cov + (size_t)s * 3 * plane + (size_t)y * W + x;
+  C[0] = __fmul_rn(dx, dx); C[plane] = __fmul_rn(dx, dy); C[2 * plane] = __fmul_rn(dy, dy);
+}
+
+struct GfttRow { double xx, xy, yy; };
+__device__ __forceinline__ GfttRow gftt_row_sum(const float* __restrict__ C, size_t plane, int W, int y, int xm, int x, int xp) {
+  const float* p = C + (size_t)y * W;
+  GfttRow r;
+  r.xx = __dadd_rn(__dadd_rn((double)p[xm], (double)p[x]), (double)p[xp]); p += plane;
+  r.xy = __dadd_rn(__dadd_rn((double)p[xm], (double)p[x]), (double)p[xp]); p += plane;
+  r.yy = __dadd_rn(__dadd_rn((double)p[xm], (double)p[x]), (double)p[xp]);
+  return r;
+}
+
+// one thread per image column; eig [stream][H][W]; vmax [stream] ordered-float maximum over the masked pixels
+constexpr int kGfttUnroll = 4;
+__global__ void __launch_bounds__(64) k_gftt_eig(const float* __restrict__ cov, const uint8_t* __restrict__ mask, int W, int H, float* __restrict__ eig,
+                                                  unsigned* __restrict__ vmax) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, s = blockIdx.y;
+  unsigned best = 0u;  // below every ordered float
+  if (x < W) {
+    const size_t plane = (size_t)W * H;
+    const float* C = cov + (size_t)s * 3 * plane;
+    const uint8_t* M = mask ? mask + (size_t)s * plane : nullptr;
+    float* E = eig + (size_t)s * plane;
+    const int xm = reflect101(x - 1, W), xp = reflect101(x + 1, W);
+    // SUM = r[-1] + r[0] (ColumnSum: zero, then the first ksize-1 rows); r[-1] = r[1] (BORDER_REFLECT_101)
+    GfttRow prev2 = gftt_row_sum(C, plane, W, reflect101(-1, H), xm, x, xp);  // r[y-1] of the running update
+    GfttRow prev1 = gftt_row_sum(C, plane, W, 0, xm, x, xp);                   // r[y]
+    double Sxx = __dadd_rn(__dadd_rn(0.0, prev2.xx), prev1.xx), Sxy = __dadd_rn(__dadd_rn(0.0, prev2.xy), prev1.xy), Syy = __dadd_rn(__dadd_rn(0.0, prev2.yy), prev1.yy);
+    for (int y0 = 0; y0 < H; y0 += kGfttUnroll) {
+      GfttRow nx[kGfttUnroll];
+#pragma unroll
+      for (int k = 0; k < kGfttUnroll; k++) nx[k] = gftt_row_sum(C, plane, W, reflect101(min(y0 + k, H - 1) + 1, H), xm, x, xp);  // r[y+1]
+#pragma unroll
+      for (int k = 0; k < kGfttUnroll; k++) {
+        const int y = y0 + k;
+        if (y < H) {
+          const double sxx = __dadd_rn(Sxx, nx[k].xx), sxy = __dadd_rn(Sxy, nx[k].xy), syy = __dadd_rn(Syy, nx[k].yy);
+          Sxx = __dsub_rn(sxx, prev2.xx); Sxy = __dsub_rn(sxy, prev2.xy); Syy = __dsub_rn(syy, prev2.yy);
+          prev2 = prev1; prev1 = nx[k];
+          const float a = __fmul_rn((float)sxx, 0.5f), b = (float)sxy, c = __fmul_rn((float)syy, 0.5f);
+          const float t = __fsub_rn(a, c);
+          const float e = __fsub_rn(__fadd_rn(a, c), __fsqrt_rn(__fadd_rn(__fmul_rn(t, t), __fmul_rn(b, b))));
+          E[(size_t)y * W + x] = e;
+          if (!M || M[(size_t)y * W + x]) best = max(best, gftt_ordered(e));
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+  if ((threadIdx.x & 31) == 0 && best) atomicMax(&vmax[s], best);
+}
+
+// candidates: key = ordered(value) << 32 | (y * W + x); descending key order == cv's greaterThanPtr (value, then address)
+__global__ void __launch_bounds__(256) k_gftt_nms(const float* __restrict__ eig, const uint8_t* __restrict__ mask, int W, int H, const unsigned* __restrict__ vmax,
+                                                   double quality, const int32_t* __restrict__ want, unsigned long long* __restrict__ keys, int cap, int32_t* __restrict__ count) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y, s = blockIdx.z;
+  if (x < 1 || y < 1 || x >= W - 1 || y >= H - 1 || want[s] <= 0) return;
+  const size_t plane = (size_t)W * H;
+  if (mask && !mask[(size_t)s * plane + (size_t)y * W + x]) return;
+  const unsigned km = vmax[s];
+  const double max_val = km ? (double)gftt_unordered(km) : 0.0;       // minMaxLoc over an empty mask reports 0
+  const float thr = (float)(max_val * quality);                       // cv::threshold casts the double threshold to float
+  const float* E = eig + (size_t)s * plane + (size_t)y * W + x;
+  const float v = E[0] > thr ? E[0] : 0.f;                            // THRESH_TOZERO
+  if (v == 0.f) return;
+  float d = v;
+#pragma unroll
+  for (int dy = -1; dy <= 1; dy++)
+#pragma unroll
+    for (int dx = -1; dx <= 1; dx++) { const float n = E[dy * W + dx]; d = fmaxf(d, n > thr ? n : 0.f); }
+  if (v != d) return;
+  const int slot = atomicAdd(&count[s], 1);
+  if (slot < cap) keys[(size_t)s * cap + slot] = ((unsigned long long)gftt_ordered(v) << 32) | (unsigned)(y * W + x);
+}

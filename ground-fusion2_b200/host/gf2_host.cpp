@@ -410,6 +410,30 @@ std::vector<Point2f> FeatureTracker::ptsVelocity(const std::vector<int>& ids_, c
   return v;
 }
 
+void FeatureTracker::setPrediction(const std::map<int, Vector3d>& predictPts) {
+  hasPrediction = true;
+  predict_pts.clear();
+  const bool noDistortion = (k1 == 0.0 && k2 == 0.0 && p1 == 0.0 && p2 == 0.0);
+  for (size_t i = 0; i < ids.size(); i++) {
+    auto it = predictPts.find(ids[i]);
+    if (it != predictPts.end()) {  // PinholeCamera::spaceToPlane (PinholeCamera.cc:520-542)
+      const double x = it->second.x / it->second.z, y = it->second.y / it->second.z;
+      double xd = x, yd = y;
+      if (!noDistortion) {
+        const double mx2 = x * x, my2 = y * y, mxy = x * y, rho2 = mx2 + my2, rad = k1 * rho2 + k2 * rho2 * rho2;
+        xd = x + (x * rad + 2.0 * p1 * mxy + p2 * (rho2 + 2.0 * mx2)); yd = y + (y * rad + 2.0 * p2 * mxy + p1 * (rho2 + 2.0 * my2));
+      }
+      predict_pts.push_back({(float)(fx * xd + cx), (float)(fy * yd + cy)});
+    } else predict_pts.push_back(prev_pts[i]);
+  }
+}
+void FeatureTracker::removeOutliers(const std::set<int>& removePtsIds) {
+  size_t j = 0;
+  for (size_t i = 0; i < ids.size(); i++)
+    if (removePtsIds.find(ids[i]) == removePtsIds.end()) { prev_pts[j] = prev_pts[i]; ids[j] = ids[i]; track_cnt[j] = track_cnt[i]; j++; }
+  prev_pts.resize(j); ids.resize(j); track_cnt.resize(j);
+}
+
 std::map<int, std::vector<std::pair<int, std::vector<double>>>> FeatureTracker::trackImage(double _cur_time, const uint8_t* _img, const uint16_t* depth) {
   std::map<int, std::vector<std::pair<int, std::vector<double>>>> featureFrame;
   last_error.clear();
@@ -429,8 +453,14 @@ std::map<int, std::vector<std::pair<int, std::vector<double>>>> FeatureTracker::
     for (int i = 0; i < n; i++) { pin[2 * i] = prev_pts[i].x; pin[2 * i + 1] = prev_pts[i].y; }
     // forward LK (maxLevel 3) + reverse check (maxLevel 1, initial flow, <= 0.5 px): feature_tracker.cpp:135-153. The pyramid of the
     // previous image is still on the device (prev_img = cur_img, :307), so only the new image is uploaded.
-    int rc = FLOW_BACK ? gf2_tracker_track_fb(trk, 1, nullptr, cur_img.data(), (size_t)col, &n, pin.data(), pout.data(), status.data(), 3)
-                       : gf2_tracker_track(trk, 1, nullptr, cur_img.data(), (size_t)col, &n, pin.data(), pout.data(), status.data(), nullptr, 0, 3);
+    // With a prediction (:118-131) the forward pass starts from predict_pts at level 1 and falls back to level 3 when fewer than 10
+    // points succeed; the decision is taken on the device inside gf2_tracker_track_image.
+    std::vector<float> ppred;
+    if (hasPrediction && (int)predict_pts.size() == n) {
+      ppred.assign((size_t)std::max(MAX_CNT, 8) * 2, 0.f);
+      for (int i = 0; i < n; i++) { ppred[2 * i] = predict_pts[i].x; ppred[2 * i + 1] = predict_pts[i].y; }
+    }
+    int rc = gf2_tracker_track_image(trk, 1, nullptr, cur_img.data(), (size_t)col, &n, pin.data(), ppred.empty() ? nullptr : ppred.data(), FLOW_BACK, pout.data(), status.data(), 3);
     if (rc != GF2_OK) { last_error = gf2_last_error(); return featureFrame; }
     for (int i = 0; i < n; i++) cur_pts[i] = {pout[2 * i], pout[2 * i + 1]};
     for (int i = 0; i < n; i++) {
@@ -455,11 +485,17 @@ std::map<int, std::vector<std::pair<int, std::vector<double>>>> FeatureTracker::
     std::vector<float> xy((size_t)n_max_cnt * 2);
     const int got = detector(cur_img.data(), row, col, mask.data(), n_max_cnt, MIN_DIST, xy.data(), detector_user);
     for (int i = 0; i < got && i < n_max_cnt; i++) n_pts.push_back({xy[2 * i], xy[2 * i + 1]});
+  } else if (n_max_cnt > 0) {
+    // cv::goodFeaturesToTrack(cur_img, n_pts, MAX_CNT - cur_pts.size(), 0.01, MIN_DIST, mask) (:198) on the image already resident
+    std::vector<float> xy((size_t)std::max(MAX_CNT, 8) * 2); int32_t want = n_max_cnt, got = 0;
+    if (gf2_tracker_detect(trk, 1, nullptr, (size_t)col, mask.data(), &want, 0.01, (double)MIN_DIST, xy.data(), &got) != GF2_OK) { last_error = gf2_last_error(); return featureFrame; }
+    for (int i = 0; i < got; i++) n_pts.push_back({xy[2 * i], xy[2 * i + 1]});
   }
   addPoints();
   cur_un_pts = undistortedPts(cur_pts);
   pts_velocity = ptsVelocity(ids, cur_un_pts, cur_un_pts_map, prev_un_pts_map);
   prev_pts = cur_pts; prev_un_pts = cur_un_pts; prev_un_pts_map = cur_un_pts_map; prev_time = cur_time; have_prev = true;
+  hasPrediction = false;  // :312
   for (size_t i = 0; i < ids.size(); i++) {
     double depth_value = -2.4;  // "depthmono" of the mono branch (:331)
     if (depth) depth_value = (double)(int)depth[(size_t)std::lround(cur_pts[i].y) * col + std::lround(cur_pts[i].x)] / 1000;  // :360-361
@@ -552,6 +588,11 @@ void* gf2h_tracker_create(int rows, int cols, int max_cnt, int min_dist, const d
 }
 void gf2h_tracker_destroy(void* t) { delete (FeatureTracker*)t; }
 void gf2h_tracker_set_detector(void* t, FeatureTracker::Detector d, void* user) { ((FeatureTracker*)t)->setDetector(d, user); }
+void gf2h_tracker_set_prediction(void* t, int n, const int* ids, const double* xyz) {
+  std::map<int, Vector3d> m; for (int i = 0; i < n; i++) m[ids[i]] = {xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]};
+  ((FeatureTracker*)t)->setPrediction(m);
+}
+void gf2h_tracker_remove_outliers(void* t, int n, const int* ids) { ((FeatureTracker*)t)->removeOutliers(std::set<int>(ids, ids + n)); }
 // returns n; out rows = [id, x, y, 1, u, v, vx, vy, depth, track_cnt]
 int gf2h_tracker_track(void* t, double time, const uint8_t* img, const uint16_t* depth, int max_n, double* out10) {
   FeatureTracker* T = (FeatureTracker*)t;

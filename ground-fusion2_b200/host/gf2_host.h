@@ -13,6 +13,7 @@
 #include <cstdint>
 #include <list>
 #include <map>
+#include <set>
 #include <string>
 #include <utility>
 #include <vector>
@@ -152,10 +153,12 @@ class FeatureTracker {
   FeatureTracker();
   ~FeatureTracker();
   void readIntrinsicParameter(const Parameters& p);
-  // detector hook: goodFeaturesToTrack(img, maxCorners, 0.01, MIN_DIST, mask) stays outside this build;
-  // the caller supplies it (tests: cv2.goodFeaturesToTrack through ctypes)
+  // goodFeaturesToTrack(cur_img, n_pts, MAX_CNT - cur_pts.size(), 0.01, MIN_DIST, mask) (:198) runs on the device through
+  // gf2_tracker_detect on the image trackImage has just uploaded. A hook can replace it for A/B checks (tests: cv2 through ctypes).
   typedef int (*Detector)(const uint8_t* img, int rows, int cols, const uint8_t* mask, int max_corners, int min_dist, float* out_xy, void* user);
   void setDetector(Detector d, void* user) { detector = d; detector_user = user; }
+  void setPrediction(const std::map<int, Vector3d>& predictPts);   // :1006-1027 (spaceToPlane of the pinhole model)
+  void removeOutliers(const std::set<int>& removePtsIds);          // :1029-1045
   // trackImage for the mono (+depth lookup) configuration with hasPrediction == false (feature_tracker.cpp:103-372)
   std::map<int, std::vector<std::pair<int, std::vector<double>>>> trackImage(double _cur_time, const uint8_t* _img, const uint16_t* depth = nullptr);
   bool inBorder(const Point2f& pt) const;        // :14-20
@@ -168,7 +171,8 @@ class FeatureTracker {
   int row = 480, col = 640, MAX_CNT = 150, MIN_DIST = 30, FLOW_BACK = 1;
   double fx = 0, fy = 0, cx = 0, cy = 0, k1 = 0, k2 = 0, p1 = 0, p2 = 0;
   std::vector<uint8_t> mask, cur_img;
-  std::vector<Point2f> n_pts, prev_pts, cur_pts, cur_un_pts, prev_un_pts, pts_velocity;
+  std::vector<Point2f> n_pts, prev_pts, cur_pts, cur_un_pts, prev_un_pts, pts_velocity, predict_pts;
+  bool hasPrediction = false;
   std::vector<int> ids, track_cnt;
   std::map<int, Point2f> cur_un_pts_map, prev_un_pts_map;
   double cur_time = 0, prev_time = 0;

@@ -369,6 +369,38 @@ int gf2_tracker_track_fb(gf2_tracker* h, int n_streams, const uint8_t* prev, con
                          const int32_t* n_pts, const float* prev_pts, float* cur_pts, uint8_t* status,
                          int max_level);
 
+/* The whole LK stage of FeatureTracker::trackImage (feature_tracker.cpp:113-153). predict_pts == NULL: forward LK at
+ * max_level (:132-135). predict_pts != NULL (hasPrediction, set by setPrediction :851-871): forward LK at level 1 from the
+ * predicted positions with OPTFLOW_USE_INITIAL_FLOW (:122-123); every stream with fewer than 10 successes is redone at
+ * max_level from prev_pts without the prediction (:124-131; decided per stream on the device). flow_back != 0 adds the
+ * reverse check of :137-153. Outputs cur_pts and the combined status. */
+int gf2_tracker_track_image(gf2_tracker* h, int n_streams, const uint8_t* prev, const uint8_t* cur, size_t stride,
+                            const int32_t* n_pts, const float* prev_pts, const float* predict_pts, int flow_back,
+                            float* cur_pts, uint8_t* status, int max_level);
+
+/* cv::goodFeaturesToTrack(img, corners, max_corners, quality_level, min_distance, mask) with the defaults trackImage uses
+ * (feature_tracker.cpp:198: blockSize 3, Sobel aperture 3, min-eigenvalue score) for n_streams images.
+ * img: [n_streams] images of height*stride bytes, or NULL to detect on the `cur` image of the last gf2_tracker_track* call
+ * (the reference detects on cur_img right after tracking it). mask: [n_streams][height][width] bytes (0 = excluded, the
+ * setMask() image :56-83) or NULL. max_corners[s] = MAX_CNT - tracked; 0 skips the stream (the reference's n_pts.clear()
+ * branch), negative is rejected; at most cfg.max_pts corners are returned per stream.
+ * out_xy: [n_streams][max_pts][2] in cv's order (descending score, ties by descending address, greedy min-distance
+ * acceptance) - the order feature ids are assigned in (addPoints :85-93); out_n [n_streams].
+ * The score map is bit-exact with cv::cornerMinEigenVal for widths that are multiples of 32. */
+int gf2_tracker_detect(gf2_tracker* h, int n_streams, const uint8_t* img, size_t stride, const uint8_t* mask,
+                       const int32_t* max_corners, double quality_level, double min_distance, float* out_xy,
+                       int32_t* out_n);
+
+/* The host half of gf2_tracker_detect on its own (needs no device): cv's corner selection (featureselect.cpp: sort by
+ * descending score then descending address, greedy min-distance acceptance through a cvRound(min_distance) grid) over n
+ * candidate keys = ordered_score << 32 | (y * width + x). Writes at most max_corners corners to out_xy and their number
+ * to out_n. */
+int gf2_detect_select(const uint64_t* keys, int n, int width, int height, int max_corners, double min_distance,
+                      float* out_xy, int32_t* out_n);
+
+/* cv::cornerMinEigenVal(img, eig, 3, 3): the detector's score map, eig [n_streams][height][width] float (parity checks). */
+int gf2_tracker_min_eigen_map(gf2_tracker* h, int n_streams, const uint8_t* img, size_t stride, float* eig);
+
 int gf2_tracker_last_timing(gf2_tracker* h, double out[8]);
 
 #ifdef __cplusplus

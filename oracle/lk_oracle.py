@@ -188,6 +188,28 @@ def track_forward_backward(prev, cur, prev_pts, win=21, max_level=3):
     return cur_pts, ok.astype(np.uint8)
 
 
+def track_image_lk(prev, cur, prev_pts, predict_pts=None, flow_back=True, win=21, max_level=3):
+    """The whole LK stage of trackImage (feature_tracker.cpp:113-153). With a prediction (:118-131): forward at maxLevel 1 from
+    predict_pts with OPTFLOW_USE_INITIAL_FLOW; fewer than 10 successes -> forward again at maxLevel 3 from prev_pts (flags 0).
+    Returns (cur_pts, status, used_fallback)."""
+    prev_pts = np.asarray(prev_pts, np.float32)
+    fallback = False
+    if predict_pts is not None:
+        cur_pts, status, _ = calc_optical_flow_pyr_lk(prev, cur, prev_pts, next_pts=np.asarray(predict_pts, np.float32).copy(), win=win, max_level=1,
+                                                      use_initial_flow=True)
+        if int(status.sum()) < 10:
+            fallback = True
+            cur_pts, status, _ = calc_optical_flow_pyr_lk(prev, cur, prev_pts, win=win, max_level=max_level)
+    else:
+        cur_pts, status, _ = calc_optical_flow_pyr_lk(prev, cur, prev_pts, win=win, max_level=max_level)
+    ok = status == 1
+    if flow_back:
+        rev, rstatus, _ = calc_optical_flow_pyr_lk(cur, prev, cur_pts, next_pts=prev_pts.copy(), win=win, max_level=1, use_initial_flow=True)
+        d = prev_pts.astype(np.float64) - rev.astype(np.float64)
+        ok = ok & (rstatus == 1) & (np.sqrt(d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) <= 0.5)
+    return cur_pts, ok.astype(np.uint8), fallback
+
+
 def synthetic_pair(*a, **kw):
     """Synthetic image pair + corners: the generator lives with the other synthetic inputs (gf2_b200.synth.image_pair)."""
     import importlib

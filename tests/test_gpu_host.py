@@ -108,13 +108,18 @@ def test_estimator_optimization_end_to_end(gf2, oracle):
     L.gf2h_estimator_destroy(e)
 
 
-def _py_track_image(state, t, img, detect, max_cnt=150, min_dist=30, fx=600.0, fy=600.0, cx=320.0, cy=240.0, tie_order=None):
+def _py_track_image(state, t, img, detect, max_cnt=150, min_dist=30, fx=600.0, fy=600.0, cx=320.0, cy=240.0, tie_order=None, predict=None):
     """Restatement of FeatureTracker::trackImage (feature_tracker.cpp:103-372), mono, no prediction, FLOW_BACK = 1."""
     cv2 = state.get("cv2")
     row, col = img.shape
     cur_pts = np.zeros((0, 2), np.float32)
     if len(state["prev_pts"]) > 0:
-        cp, ok = lk.track_forward_backward(state["prev_img"], img, state["prev_pts"])
+        if predict is not None:   # setPrediction (:1006-1027): spaceToPlane of the predicted 3-D point, prev_pts where there is none
+            pp = np.array([[np.float32(fx * (predict[i][0] / predict[i][2]) + cx), np.float32(fy * (predict[i][1] / predict[i][2]) + cy)] if i in predict else state["prev_pts"][k]
+                           for k, i in enumerate(state["ids"])], np.float32)
+            cp, ok, state["fallback"] = lk.track_image_lk(state["prev_img"], img, state["prev_pts"], predict_pts=pp)
+        else:
+            cp, ok = lk.track_forward_backward(state["prev_img"], img, state["prev_pts"])
         status = ok.astype(bool)
         for i in range(len(cp)):
             ix, iy = int(np.rint(cp[i, 0])), int(np.rint(cp[i, 1]))
@@ -155,7 +160,10 @@ def _py_track_image(state, t, img, detect, max_cnt=150, min_dist=30, fx=600.0, f
     return ki, cur_pts, un, vel, kc
 
 
-def test_feature_tracker_track_image_ids_bit_exact():
+@pytest.mark.parametrize("device_detector", [False, True])
+def test_feature_tracker_track_image_ids_bit_exact(device_detector):
+    """device_detector = False: the C++ mirror calls back into cv2.goodFeaturesToTrack (hook); True: it runs gf2_tracker_detect on
+    the device — the feature ids, counts and positions must not change (the restatement keeps using cv2 / the pinned oracle)."""
     try:
         import cv2
         cv2.setNumThreads(1)
@@ -169,6 +177,9 @@ def test_feature_tracker_track_image_ids_bit_exact():
         if cv2 is not None:
             p_ = cv2.goodFeaturesToTrack(img, maxc, 0.01, mind, mask=mask)
             return np.zeros((0, 2), np.float32) if p_ is None else p_.reshape(-1, 2)
+        if device_detector:
+            import gftt_oracle
+            return gftt_oracle.good_features_to_track(img, maxc, 0.01, mind, mask)
         ys, xs = np.mgrid[20:460:40, 20:620:40]
         pts = np.stack([xs.ravel(), ys.ravel()], -1).astype(np.float32)
         return pts[mask[pts[:, 1].astype(int), pts[:, 0].astype(int)] == 255][:maxc]
@@ -181,7 +192,8 @@ def test_feature_tracker_track_image_ids_bit_exact():
         return len(pts)
     cb = H.DETECTOR(det_cb)
     t = C.c_void_p(L.gf2h_tracker_create(480, 640, 150, 30, H.p(np.array([600.0, 600.0, 320.0, 240.0, 0, 0, 0, 0]))))
-    L.gf2h_tracker_set_detector(t, cb, None)
+    if not device_detector:
+        L.gf2h_tracker_set_detector(t, cb, None)
     state = dict(prev_pts=np.zeros((0, 2), np.float32), prev_img=None, ids=[], cnt=[], n_id=0, prev_un={}, prev_time=0.0, cv2=cv2)
     lost_any = False
     for k, img in enumerate(frames):
@@ -211,4 +223,51 @@ def test_feature_tracker_track_image_ids_bit_exact():
         if k > 0 and max(cnt) < k + 1:
             lost_any = True
     assert state["n_id"] > 150 or lost_any or True
+    L.gf2h_tracker_destroy(t)
+
+
+def test_feature_tracker_prediction_and_remove_outliers():
+    """setPrediction (feature_tracker.cpp:1006-1027) -> level-1 LK from the predicted pixels with the < 10 fall-back (:118-131), and
+    removeOutliers (:1029-1045), through the C++ mirror with the device detector."""
+    import gftt_oracle
+    L = H.lib()
+    frames = [lk.synthetic_pair(41, shift=(3.0 * k, 2.0 * k))[1] for k in range(4)]
+    fx = fy = 600.0; cx, cy = 320.0, 240.0
+
+    def detect(img, mask, maxc, mind):
+        return gftt_oracle.good_features_to_track(img, maxc, 0.01, mind, mask)
+    t = C.c_void_p(L.gf2h_tracker_create(480, 640, 120, 30, H.p(np.array([fx, fy, cx, cy, 0, 0, 0, 0]))))
+    state = dict(prev_pts=np.zeros((0, 2), np.float32), prev_img=None, ids=[], cnt=[], n_id=0, prev_un={}, prev_time=0.0, cv2=None)
+    fallbacks = []
+    for k, img in enumerate(frames):
+        predict = None
+        if k == 3:   # removeOutliers first (the estimator's order: removeOutliers, predictPtsInNextFrame -> setPrediction), on both sides
+            drop = np.array(state["ids"][::7], np.int32)
+            L.gf2h_tracker_remove_outliers(t, len(drop), H.p(drop))
+            keep = [j for j, i in enumerate(state["ids"]) if i not in set(drop.tolist())]
+            state["prev_pts"] = state["prev_pts"][keep]; state["ids"] = [state["ids"][j] for j in keep]; state["cnt"] = [state["cnt"][j] for j in keep]
+        if k >= 1:
+            # frames 1, 3: predictions close to the true motion for every second id (the others fall back to prev_pts);
+            # frame 2: predictions far outside the image for every id -> fewer than 10 successes -> level-3 fall-back
+            predict = {}
+            for j, i in enumerate(state["ids"]):
+                u, v = state["prev_pts"][j]
+                if k == 2:
+                    predict[i] = (((u + 5000.0) - cx) / fx, (v - cy) / fy, 1.0)
+                elif j % 2 == 0:
+                    predict[i] = (((u + 3.0) - cx) / fx * 2.0, ((v + 2.0) - cy) / fy * 2.0, 2.0)
+            ids = np.array(list(predict), np.int32); xyz = np.array([predict[i] for i in predict], np.float64)
+            L.gf2h_tracker_set_prediction(t, len(ids), H.p(ids), H.p(xyz))
+        out = np.zeros((200, 10))
+        n = L.gf2h_tracker_track(t, C.c_double(0.1 * k), H.p(img), None, 200, H.p(out))
+        assert n >= 0, L.gf2h_tracker_last_error(t)
+        cpp_order = out[:n, 0].astype(int).tolist()
+        state.pop("fallback", None)
+        ids, pts, un, vel, cnt = _py_track_image(state, 0.1 * k, img, detect, max_cnt=120, tie_order=cpp_order, predict=predict)
+        fallbacks.append(state.get("fallback"))
+        got = {int(r[0]): r for r in out[:n]}
+        assert sorted(got) == sorted(ids)
+        for k2, i in enumerate(ids):
+            assert int(got[i][9]) == cnt[k2] and np.abs(got[i][4:6] - pts[k2]).max() <= 1e-4
+    assert fallbacks == [None, False, True, False]
     L.gf2h_tracker_destroy(t)

@@ -55,3 +55,20 @@ def test_live_cv2(seed, shift):
     assert ok.mean() > 0.9
     flow = (cp - pts)[ok == 1].mean(0)
     assert np.abs(flow - np.array(shift)).max() < 0.3
+
+
+def test_prediction_path_against_live_cv2():
+    """trackImage with hasPrediction (feature_tracker.cpp:118-131): level-1 LK from predicted positions, fall-back to level 3."""
+    cv2 = pytest.importorskip("cv2")
+    cv2.setNumThreads(1)
+    prev, cur, pts = lk.synthetic_pair(9, shift=(6.0, -3.5))
+    crit = (cv2.TERM_CRITERIA_COUNT + cv2.TERM_CRITERIA_EPS, 30, 0.01)
+    for pred, expect_fallback in ((pts + np.float32([5.5, -3.0]), False), (pts + np.float32([2000.0, 0.0]), True)):
+        c, st, fb = lk.track_image_lk(prev, cur, pts, predict_pts=pred, flow_back=False)
+        r, rst, _ = cv2.calcOpticalFlowPyrLK(prev, cur, pts.reshape(-1, 1, 2), pred.reshape(-1, 1, 2).copy(), winSize=(21, 21), maxLevel=1, criteria=crit,
+                                             flags=cv2.OPTFLOW_USE_INITIAL_FLOW)
+        if int(rst.sum()) < 10:
+            r, rst, _ = cv2.calcOpticalFlowPyrLK(prev, cur, pts.reshape(-1, 1, 2), None, winSize=(21, 21), maxLevel=3)
+        assert fb == expect_fallback
+        assert np.array_equal(st, rst.ravel())
+        assert np.abs(c - r.reshape(-1, 2))[st == 1].max() < 1e-3
