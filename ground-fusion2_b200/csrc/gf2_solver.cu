@@ -248,6 +248,7 @@ constexpr int kNcclFloat64 = 8, kNcclSum = 0, kNcclMax = 2;  // ncclDataType_t /
 struct gf2_solver {
   gf2_solver_cfg cfg;
   int D;
+  int last_Dx = 0;   // reduced dimension of the last run (D, or 15 (F + 1) with free wheel calibration blocks)
   cudaStream_t stream, own_stream;
   double *snap_pose = nullptr, *snap_sb = nullptr, *snap_invdep = nullptr;
   KP kp;  // device pointers for window 0
@@ -302,7 +303,7 @@ int gf2_solver_create(const gf2_solver_cfg* cfg, gf2_solver** out) {
   h->D = 15 * F;
   memset(&h->kp, 0, sizeof(KP));
   KP& k = h->kp;
-  k.nW = B; k.F = F; k.Lm = Lm; k.Om = Om; k.Pm = Pm; k.D = h->D; k.use_wheel = cfg->use_wheel;
+  k.nW = B; k.F = F; k.Lm = Lm; k.Om = Om; k.Pm = Pm; k.D = h->D; k.Ds = 15 * (F + 1); k.wcal = 0; k.use_wheel = cfg->use_wheel;
   k.Pr = cfg->max_prior_rows > 0 ? cfg->max_prior_rows : GF2_MAX_PRIOR_DIM;
   if (k.Pr > GF2_MAX_PRIOR_DIM) { delete h; return gf2::fail(GF2_ERR_INVALID, "max_prior_rows %d exceeds %d", k.Pr, GF2_MAX_PRIOR_DIM); }
   if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return gf2::fail(GF2_ERR_CUDA, "stream creation failed"); }
@@ -325,13 +326,17 @@ int gf2_solver_create(const gf2_solver_cfg* cfg, gf2_solver** out) {
   if (Pm > 0) { A(k.n_planes, int32_t, B); A(k.planes, gf2_plane, (size_t)B * Pm); }
   A(k.Svis, double, (size_t)B * kNVMax * kNVMax); A(k.gvis, double, (size_t)B * kNVP); A(k.gschur, double, (size_t)B * kNVP); A(k.Udiag, double, (size_t)B * kNVMax);
   A(k.lm_v, double, (size_t)B * Lm); A(k.lm_g, double, (size_t)B * Lm); A(k.lm_s, double, (size_t)B * Lm); A(k.lm_z, double, (size_t)B * Lm);
-  A(k.sx, double, (size_t)B * h->D); A(k.zx, double, (size_t)B * h->D); A(k.ux, double, (size_t)B * h->D); A(k.ex_diag, double, (size_t)B * h->D);
+  A(k.sx, double, (size_t)B * k.Ds); A(k.zx, double, (size_t)B * k.Ds); A(k.ux, double, (size_t)B * k.Ds); A(k.ex_diag, double, (size_t)B * k.Ds);
   A(k.imu_H, double, (size_t)B * (F - 1) * 675); A(k.imu_g, double, (size_t)B * (F - 1) * 30);
   A(k.prior_g, double, (size_t)B * k.Pr); A(k.cost_nv, double, B);
   A(k.trace, double, (size_t)B * 64 * 6);
   A(k.c_lin, double, (size_t)B * 4); A(k.c_gmax, double, B); A(k.c_sums, double, (size_t)B * 8); A(k.c_cand, double, (size_t)B * 4);
   if (Pm > 0) { A(k.pperm, int32_t, (size_t)B * Pm); A(k.ptask_first, int32_t, (size_t)B * kMaxPlaneTasks); A(k.ptask_cnt, int32_t, (size_t)B * kMaxPlaneTasks); A(k.ptask_frame, int32_t, (size_t)B * kMaxPlaneTasks); A(k.nptasks, int32_t, B); }
-  if (cfg->use_wheel) { A(k.wheel_H, double, (size_t)B * (F - 1) * 108); A(k.wheel_g, double, (size_t)B * (F - 1) * 12); }
+  if (cfg->use_wheel) {
+    A(k.wheel_H, double, (size_t)B * (F - 1) * 108); A(k.wheel_g, double, (size_t)B * (F - 1) * 12);
+    A(k.wheel_Hc, double, (size_t)B * (F - 1) * 220); A(k.wheel_gc, double, (size_t)B * (F - 1) * 10);
+    A(k.exw_c, double, (size_t)B * 7); A(k.sxw_c, double, (size_t)B * 3); A(k.tdw_c, double, B);
+  }
   A(k.lminfo, int4, (size_t)B * Lm); A(k.task_first, int32_t, (size_t)B * kMaxTasks); A(k.task_cnt, int32_t, (size_t)B * kMaxTasks);
   A(k.task_start, int32_t, (size_t)B * kMaxTasks); A(k.ntasks, int32_t, B);
   A(k.st, WinState, B);
@@ -346,7 +351,7 @@ int gf2_solver_create(const gf2_solver_cfg* cfg, gf2_solver** out) {
   cudaHostAlloc((void**)&h->h_state, sizeof(WinState) * B, cudaHostAllocDefault);
   // opt in to large dynamic shared memory
   cudaFuncSetAttribute(k_linearize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LinShared));
-  cudaFuncSetAttribute(k_solve2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(Solve2Shared) + sizeof(double) * solve2_matrix_doubles(F)));
+  cudaFuncSetAttribute(k_solve2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(Solve2Shared) + sizeof(double) * solve2_matrix_doubles(F, 1)));
   cudaFuncSetAttribute(k_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * 450 * GF2_MAX_FRAMES));
   if (cudaGetLastError() != cudaSuccess) { gf2_solver_destroy(h); return gf2::fail(GF2_ERR_CUDA, "cudaFuncSetAttribute failed (is this an sm_100a device?)"); }
   *out = h;
@@ -576,11 +581,11 @@ static int fill_kp(gf2_solver* h, const gf2_solve_opts* o, KP& k) {
   if (o->max_iterations < 0 || o->max_iterations > 64) return gf2::fail(GF2_ERR_INVALID, "max_iterations %d out of range [0, 64]", o->max_iterations);
   const uint32_t need = GF2_CONST_EX_POSE | GF2_CONST_TD;
   if ((o->const_mask & need) != need) return gf2::fail(GF2_ERR_UNSUPPORTED, "free camera extrinsic / td blocks are not built yet (const_mask must hold EX_POSE|TD)");
-  if (h->cfg.use_wheel) {
-    const uint32_t needw = GF2_CONST_EX_WHEEL | GF2_CONST_WHEEL_INTRINSIC | GF2_CONST_TD_WHEEL;
-    if ((o->const_mask & needw) != needw) return gf2::fail(GF2_ERR_UNSUPPORTED, "free wheel calibration blocks are not built yet");
-  }
   k = h->kp;
+  // free wheel calibration blocks (estimate_wheel_extrinsic: 1 in the shipped wheel configs): one more block row of the reduced system
+  k.wcal = 0;
+  if (h->cfg.use_wheel && h->has_wheel) k.wcal = ((o->const_mask & GF2_CONST_EX_WHEEL) ? 0 : 1) | ((o->const_mask & GF2_CONST_WHEEL_INTRINSIC) ? 0 : 2) | ((o->const_mask & GF2_CONST_TD_WHEEL) ? 0 : 4);
+  if (k.wcal && h->nccl_comm) return gf2::fail(GF2_ERR_UNSUPPORTED, "free wheel calibration blocks in factor-sharded mode are not built");
   k.const_mask = o->const_mask; k.huber = o->huber_delta; k.sqrt_info_px = o->sqrt_info_px; k.g_norm = o->g_norm; k.lidar_sqrt_info = o->lidar_sqrt_info;
   k.ftol = o->function_tolerance > 0 ? o->function_tolerance : 1e-6;
   k.gtol = o->gradient_tolerance > 0 ? o->gradient_tolerance : 1e-10;
@@ -599,7 +604,8 @@ static int run(gf2_solver* h, int first, int n, const gf2_solve_opts* opts, gf2_
   KP k;
   GF2_TRY(fill_kp(h, opts, k));
   const int D = h->D;
-  const size_t sh_solve = sizeof(Solve2Shared) + sizeof(double) * solve2_matrix_doubles(k.F);
+  h->last_Dx = k.wcal ? k.Ds : h->D;
+  const size_t sh_solve = sizeof(Solve2Shared) + sizeof(double) * solve2_matrix_doubles(k.F, k.wcal);
   double initial_radius = opts->initial_radius > 0 ? opts->initial_radius : 1e4;
   int ne = 0;
   cudaEventRecord(h->ev[ne++], h->stream);
@@ -666,20 +672,26 @@ int gf2_solve(gf2_solver* h, int first, int n, const gf2_solve_opts* opts, gf2_s
 int gf2_linearize(gf2_solver* h, int first, int n, const gf2_solve_opts* opts) {
   if (!h) return gf2::fail(GF2_ERR_INVALID, "null handle");
   if (!h->kp.Sfull) {
-    int rc = dalloc<double>(h, &h->kp.Sfull, (size_t)h->cfg.max_windows * h->D * h->D); if (rc) return rc;
-    rc = dalloc<double>(h, &h->kp.gfull, (size_t)h->cfg.max_windows * h->D); if (rc) return rc;
+    int rc = dalloc<double>(h, &h->kp.Sfull, (size_t)h->cfg.max_windows * h->kp.Ds * h->kp.Ds); if (rc) return rc;
+    rc = dalloc<double>(h, &h->kp.gfull, (size_t)h->cfg.max_windows * h->kp.Ds); if (rc) return rc;
   }
   return run(h, first, n, opts, nullptr, 1, true);
 }
 
-int gf2_reduced_dim(gf2_solver* h, const gf2_solve_opts* opts) { (void)opts; return h ? h->D : gf2::fail(GF2_ERR_INVALID, "null handle"); }
+// D = 15 F; with free wheel calibration blocks (opts->const_mask) one more block row [ex_wheel 6 | sx sy sw | td_wheel | 5 unused]
+int gf2_reduced_dim(gf2_solver* h, const gf2_solve_opts* opts) {
+  if (!h) return gf2::fail(GF2_ERR_INVALID, "null handle");
+  KP k;
+  if (opts && fill_kp(h, opts, k) == GF2_OK && k.wcal) return h->kp.Ds;
+  return h->D;
+}
 
 int gf2_get_reduced_system(gf2_solver* h, int first, int n, double* S, double* g, double* cost) {
   GF2_TRY(check_range(h, first, n));
   if (!h->kp.Sfull) return gf2::fail(GF2_ERR_INVALID, "gf2_linearize has not been called");
-  const int D = h->D;
-  D2H(S, h->kp.Sfull + (size_t)first * D * D, sizeof(double) * n * D * D);
-  D2H(g, h->kp.gfull + (size_t)first * D, sizeof(double) * n * D);
+  const int D = h->last_Dx, Ds = h->kp.Ds;   // the dimension of the last linearisation (gf2_reduced_dim for the same options)
+  GF2_CUDA(cudaMemcpy2DAsync(S, sizeof(double) * D * D, h->kp.Sfull + (size_t)first * Ds * Ds, sizeof(double) * Ds * Ds, sizeof(double) * D * D, n, cudaMemcpyDeviceToHost, h->stream));
+  GF2_CUDA(cudaMemcpy2DAsync(g, sizeof(double) * D, h->kp.gfull + (size_t)first * Ds, sizeof(double) * Ds, sizeof(double) * D, n, cudaMemcpyDeviceToHost, h->stream));
   GF2_CUDA(cudaMemcpyAsync(h->h_state, h->kp.st + first, sizeof(WinState) * n, cudaMemcpyDeviceToHost, h->stream));
   GF2_CUDA(cudaStreamSynchronize(h->stream));
   if (cost) for (int w = 0; w < n; w++) cost[w] = h->h_state[w].x_cost;

@@ -41,6 +41,10 @@ struct WinState {  // per-window trust-region state (DoglegStrategy + TrustRegio
 
 struct KP {  // kernel parameters (device pointers are window-major with the strides below)
   int nW, F, Lm, Om, Pm, D, use_wheel, Pr;  // Pr: row stride of the prior arrays (<= GF2_MAX_PRIOR_DIM)
+  // Free wheel calibration blocks (estimate_wheel_extrinsic / _intrinsic / td_wheel, VE/estimator/estimator.cpp:3063-3118,3160):
+  // wcal bit 0: body_T_wheel free, bit 1: sx sy sw free, bit 2: td_wheel free. They form one more block row "frame F" of the
+  // reduced system with tangent layout [ex_wheel 6 | sx sy sw | td_wheel | 5 unused]. Ds = 15 (F + 1): row stride of sx/zx/ux/ex_diag.
+  int wcal, Ds;
   uint32_t const_mask;
   double huber, sqrt_info_px, g_norm, lidar_sqrt_info;
   double ftol, gtol, ptol;
@@ -48,6 +52,7 @@ struct KP {  // kernel parameters (device pointers are window-major with the str
   // states (current / candidate)
   double *pose, *sb, *ex, *td, *exw, *sxw, *tdw, *invdep;
   double *pose_c, *sb_c, *invdep_c;
+  double *exw_c, *sxw_c, *tdw_c;   // candidate wheel calibration (wcal != 0)
   // landmarks
   const int32_t *nlm, *start, *tlen, *obeg;
   const uint8_t* fixed;
@@ -77,6 +82,7 @@ struct KP {  // kernel parameters (device pointers are window-major with the str
   double *Sfull, *gfull;           // optional dump of the assembled reduced system [nW][D*D], [nW][D]
   int32_t *pperm, *ptask_first, *ptask_cnt, *ptask_frame, *nptasks;  // k_tasks: plane permutation by frame, warp tasks
   double *wheel_H, *wheel_g;       // [nW][F-1][3*36] pose blocks (i,i),(j,i),(j,j) of each wheel factor, [nW][F-1][12]  (k_nonvis)
+  double *wheel_Hc, *wheel_gc;     // wcal: [nW][F-1][220] blocks (calib,pose_i) 10x6, (calib,pose_j) 10x6, (calib,calib) 10x10; [nW][F-1][10]
   int4* lminfo;                    // k_tasks: landmarks sorted by start frame, packed (index, track length, first observation, fixed)
   int32_t *task_first, *task_cnt, *task_start, *ntasks;  // k_tasks: warp tasks over that order
   // cross-rank scalars (factor-sharded mode all-reduces them; single GPU reads them straight back)
@@ -265,7 +271,13 @@ __global__ void k_prepare(KP p, int w0) {
         int base = -1, ls = 0;
         if (blk[b].kind == GF2_BLK_POSE) { base = 15 * blk[b].index; ls = 6; }
         else if (blk[b].kind == GF2_BLK_SPEEDBIAS) { base = 15 * blk[b].index + 6; ls = 9; }
-        else { ls = (blk[b].kind == GF2_BLK_EX_POSE || blk[b].kind == GF2_BLK_EX_WHEEL) ? 6 : 1; }  // constant calibration blocks: no column
+        else {  // calibration blocks: a column only when the block is free in this solve (wheel calibration, block row F)
+          ls = (blk[b].kind == GF2_BLK_EX_POSE || blk[b].kind == GF2_BLK_EX_WHEEL) ? 6 : 1;
+          const int k = blk[b].kind;
+          if (k == GF2_BLK_EX_WHEEL && (p.wcal & 1)) base = 15 * F;
+          else if (k >= GF2_BLK_SX && k <= GF2_BLK_SW && (p.wcal & 2)) base = 15 * F + 6 + (k - GF2_BLK_SX);
+          else if (k == GF2_BLK_TD_WHEEL && (p.wcal & 4)) base = 15 * F + 9;
+        }
         for (int c = 0; c < ls; c++) map[blk[b].offset + c] = base < 0 ? -1 : base + c;
       }
     }

@@ -221,6 +221,16 @@ __device__ void wheel_calib_jacobians(const gf2_wheel_preint& pre, const double*
   const V3 trt = -mul(Jrinv, mul(Emr, mul(Ebw, mul(cdqInvR, mul(Jrtd, sw * lg))) - mul(Jr_minus_td, sw * g1)));
   Jc[0 * 10 + 9] = tpt.x; Jc[1 * 10 + 9] = tpt.y; Jc[2 * 10 + 9] = tpt.z; Jc[3 * 10 + 9] = trt.x; Jc[4 * 10 + 9] = trt.y; Jc[5 * 10 + 9] = trt.z;
 }
+// out-of-line copy for k_nonvis: inlined there it quadruples the spills of the IMU path, which never calls it
+__device__ __noinline__ void wheel_calib_jacobians_masked(const gf2_wheel_preint& pre, const double* pose_i, const double* pose_j, const double* exw, const double* sxw, double tdw,
+                                                          int wcal, double* Jc /*6x10*/) {
+  wheel_calib_jacobians(pre, pose_i, pose_j, exw, sxw, tdw, Jc);
+  for (int a = 0; a < 6; a++) {  // constant sub-blocks have no column
+    if (!(wcal & 1)) for (int c = 0; c < 6; c++) Jc[a * 10 + c] = 0.0;
+    if (!(wcal & 2)) for (int c = 6; c < 9; c++) Jc[a * 10 + c] = 0.0;
+    if (!(wcal & 4)) Jc[a * 10 + 9] = 0.0;
+  }
+}
 __device__ __forceinline__ double wheel_cost(const double* sq /*6x6 upper*/, const double* r) {
   double c = 0;
   for (int a = 0; a < 6; a++) { double s = 0; for (int k = a; k < 6; k++) s += sq[a * 6 + k] * r[k]; c += s * s; }
@@ -249,234 +259,40 @@ __device__ __forceinline__ double imu_cost(const double* sq /*15x15 upper*/, con
   return 0.5 * c;
 }
 
-// MarginalizationFactor::Evaluate's dx (VE/factor/marginalization_factor.cpp:356-374) for one kept block
-__device__ __forceinline__ void prior_block_dx(const gf2_prior_block& b, const double* pose, const double* sb, double* dx /* at offset */) {
-  if (b.kind == GF2_BLK_POSE) {
-    const double* x = pose + 7 * b.index;
-    for (int k = 0; k < 3; k++) dx[b.offset + k] = x[k] - b.x0[k];
-    Q4 q0 = ldq(b.x0 + 3), q = ldq(x + 3);
-    Q4 dq = qmul(qinv(q0), q);
-    V3 v = 2.0 * qvec(dq);
-    if (!(dq.w >= 0)) v = -v;
-    dx[b.offset + 3] = v.x; dx[b.offset + 4] = v.y; dx[b.offset + 5] = v.z;
-  } else if (b.kind == GF2_BLK_SPEEDBIAS) {
+// MarginalizationFactor::Evaluate's dx (VE/factor/marginalization_factor.cpp:356-374) for one kept block. cal = {ex_wheel[7],
+// sxsysw[3], td_wheel} of the state the prior is evaluated at (null without wheel). The camera extrinsic and td never move in
+// this build (x == x0), so their dx is 0.
+struct CalibPtr { const double *exw, *sxw, *tdw; };
+__device__ __forceinline__ void prior_pose_dx(const double* x, const double* x0, double* dx) {
+  for (int k = 0; k < 3; k++) dx[k] = x[k] - x0[k];
+  Q4 q0 = ldq(x0 + 3), q = ldq(x + 3);
+  Q4 dq = qmul(qinv(q0), q);
+  V3 v = 2.0 * qvec(dq);
+  if (!(dq.w >= 0)) v = -v;
+  dx[3] = v.x; dx[4] = v.y; dx[5] = v.z;
+}
+__device__ __forceinline__ void prior_block_dx(const gf2_prior_block& b, const double* pose, const double* sb, const CalibPtr& cal, double* dx /* at offset */) {
+  if (b.kind == GF2_BLK_POSE) prior_pose_dx(pose + 7 * b.index, b.x0, dx + b.offset);
+  else if (b.kind == GF2_BLK_SPEEDBIAS) {
     const double* x = sb + 9 * b.index;
     for (int k = 0; k < 9; k++) dx[b.offset + k] = x[k] - b.x0[k];
-  } else {
-    // calibration blocks are constant in this build: x == x0 is not guaranteed, but they do not move during the solve,
-    // so their dx contribution is folded in by the caller through r0 (see gf2_set_prior) -> 0 here
+  } else if (b.kind == GF2_BLK_EX_WHEEL && cal.exw) prior_pose_dx(cal.exw, b.x0, dx + b.offset);
+  else if (b.kind >= GF2_BLK_SX && b.kind <= GF2_BLK_SW && cal.sxw) dx[b.offset] = cal.sxw[b.kind - GF2_BLK_SX] - b.x0[0];
+  else if (b.kind == GF2_BLK_TD_WHEEL && cal.tdw) dx[b.offset] = cal.tdw[0] - b.x0[0];
+  else {
     const int ls = (b.kind == GF2_BLK_EX_POSE || b.kind == GF2_BLK_EX_WHEEL) ? 6 : 1;
     for (int k = 0; k < ls; k++) dx[b.offset + k] = 0.0;
   }
 }
+__device__ __forceinline__ CalibPtr calib_of(const KP& p, int w, bool candidate) {
+  CalibPtr c = {nullptr, nullptr, nullptr};
+  if (!p.use_wheel) return c;
+  const bool cc = candidate && p.wcal;
+  c.exw = (cc ? p.exw_c : p.exw) + (size_t)w * 7; c.sxw = (cc ? p.sxw_c : p.sxw) + (size_t)w * 3; c.tdw = (cc ? p.tdw_c : p.tdw) + w;
+  return c;
+}
 
 __device__ __forceinline__ int pidx(int i, int j) { return i * (i + 1) / 2 + j; }  // packed lower, j <= i
-
-// ------------------------------------------------------------------------------------------------ k_solve
-struct SolveShared {
-  double g[kMaxF * 15], Hd[kMaxF * 15], s[kMaxF * 15], e[kMaxF * 15], u[kMaxF * 15], z[kMaxF * 15], tmp[kMaxF * 15];
-  double dx[kP], pr[kP];
-  double red[8 * 32];
-  double imu_scratch[8][480];
-  int flag;
-  double Lp[1];  // packed lower D(D+1)/2, dynamic tail
-};
-
-__global__ void __launch_bounds__(kSolveThreads, 1) k_solve(KP p, int w0) {
-  const int w = w0 + blockIdx.x;
-  WinState& st = p.st[w];
-  if (!st.active || st.reuse) return;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  SolveShared& S = *reinterpret_cast<SolveShared*>(smem_raw);
-  const int t = threadIdx.x, lane = t & 31, wid = t >> 5, nt = blockDim.x;
-  const int F = p.F, D = p.D, NV = 6 * F;
-  const int NP = D * (D + 1) / 2;
-  const double* pose = p.pose + (size_t)w * F * 7;
-  const double* sb = p.sb + (size_t)w * F * 9;
-  double* Lp = S.Lp;
-  for (int i = t; i < NP; i += nt) Lp[i] = 0.0;
-  for (int i = t; i < D; i += nt) { S.g[i] = 0.0; S.Hd[i] = 0.0; }
-  __syncthreads();
-  // visual part
-  const double* Svis = p.Svis + (size_t)w * kNVMax * kNVMax;
-  for (int idx = t; idx < NV * NV; idx += nt) {
-    const int a = idx / NV, b = idx % NV;
-    if (b > a) continue;
-    const int da = 15 * (a / 6) + a % 6, db = 15 * (b / 6) + b % 6;
-    Lp[pidx(da, db)] = Svis[a * kNVMax + b];
-  }
-  if (t < NV) { const int da = 15 * (t / 6) + t % 6; S.g[da] = p.gvis[(size_t)w * kNVP + t]; S.Hd[da] = p.Udiag[(size_t)w * kNVMax + t]; }
-  double cost = 0.0;  // thread-local partial of the non-visual cost
-  __syncthreads();
-  // prior
-  const int n = p.prior_rows ? p.prior_rows[w] : 0;
-  if (n > 0) {
-    const gf2_prior_block* blk = p.prior_blocks + (size_t)w * (2 * F + 8);
-    const int nb = p.prior_nblocks[w];
-    if (t < nb) prior_block_dx(blk[t], pose, sb, S.dx);
-    __syncthreads();
-    const double* J0 = p.prior_J0 + (size_t)w * p.Pr * p.Pr;
-    const double* r0 = p.prior_r0 + (size_t)w * p.Pr;
-    if (t < n) { double s2 = r0[t]; for (int c = 0; c < n; c++) s2 += J0[t * p.Pr + c] * S.dx[c]; S.pr[t] = s2; cost += 0.5 * s2 * s2; }
-    __syncthreads();
-    const int32_t* map = p.prior_map + (size_t)w * p.Pr;
-    const double* H = p.prior_H + (size_t)w * p.Pr * p.Pr;
-    if (t < n && map[t] >= 0) { double s2 = 0; for (int r = 0; r < n; r++) s2 += J0[r * p.Pr + t] * S.pr[r]; S.g[map[t]] += s2; S.Hd[map[t]] += H[t * p.Pr + t]; }
-    for (int idx = t; idx < n * n; idx += nt) {
-      const int a = idx / n, b = idx % n;
-      const int ma = map[a], mb = map[b];
-      if (ma < 0 || mb < 0 || mb > ma) continue;
-      Lp[pidx(ma, mb)] += H[a * p.Pr + b];
-    }
-    __syncthreads();
-  }
-  // IMU factors: even then odd (neighbouring factors share frame i+1's block)
-  if (p.imu) {
-    for (int phase = 0; phase < 2; phase++) {
-      for (int k = 2 * wid + phase; k < F - 1; k += 2 * (nt >> 5)) {
-        const gf2_imu_preint& pre = p.imu[(size_t)w * (F - 1) + k];
-        if (!pre.valid || pre.sum_dt > 10.0) continue;
-        double* J = S.imu_scratch[wid];
-        double* r = J + 450;
-        if (lane == 0) { ImuStates s2 = load_imu_states(pose, sb, k); imu_raw(pre, s2, p.g_norm, r, J); }
-        __syncwarp();
-        const double* sq = p.imu_sqrt + ((size_t)w * (F - 1) + k) * 225;
-        // J <- sqrt_info * J (upper triangular, in place row by row), r likewise
-        if (lane < 30) {
-          for (int a = 0; a < 15; a++) { double acc = 0; for (int kk = a; kk < 15; kk++) acc += sq[a * 15 + kk] * J[kk * 30 + lane]; J[a * 30 + lane] = acc; }
-        } else if (lane == 30) {
-          for (int a = 0; a < 15; a++) { double acc = 0; for (int kk = a; kk < 15; kk++) acc += sq[a * 15 + kk] * r[kk]; r[a] = acc; }
-        }
-        __syncwarp();
-        if (lane == 0) { double c = 0; for (int a = 0; a < 15; a++) c += r[a] * r[a]; cost += 0.5 * c; }
-        const int base = 15 * k;
-        for (int idx = lane; idx < 30 * 31 / 2; idx += 32) {
-          // idx -> (a >= b)
-          int a = (int)((sqrt(8.0 * idx + 1.0) - 1.0) * 0.5); while (a * (a + 1) / 2 > idx) a--; while ((a + 1) * (a + 2) / 2 <= idx) a++;
-          const int b = idx - a * (a + 1) / 2;
-          double acc = 0; for (int rr = 0; rr < 15; rr++) acc += J[rr * 30 + a] * J[rr * 30 + b];
-          Lp[pidx(base + a, base + b)] += acc;
-          if (a == b) S.Hd[base + a] += acc;
-        }
-        if (lane < 30) { double acc = 0; for (int rr = 0; rr < 15; rr++) acc += J[rr * 30 + lane] * r[rr]; S.g[base + lane] += acc; }
-        __syncwarp();
-      }
-      __syncthreads();
-    }
-  }
-  // total cost of the linearisation point
-  {
-    double v1[1] = {cost};
-    block_sum<1>(v1, S.red);
-    if (t == 0) { st.x_cost = v1[0] + st.cost_vis; if (st.iteration == 0) st.initial_cost = st.x_cost; }
-  }
-  // optional dump of the assembled (unregularised) reduced system
-  if (p.Sfull) {
-    double* Sf = p.Sfull + (size_t)w * D * D;
-    for (int idx = t; idx < D * D; idx += nt) { const int a = idx / D, b = idx % D; Sf[idx] = a >= b ? Lp[pidx(a, b)] : Lp[pidx(b, a)]; }
-    for (int i = t; i < D; i += nt) p.gfull[(size_t)w * D + i] = S.g[i];
-  }
-  // Jacobi scaling (iteration 0), dogleg diagonal, gradient quantities
-  const double mu = st.mu;
-  double sums[6] = {0, 0, 0, 0, 0, 0};  // dlg2, uEu, gmax(as max), -, -, -
-  double gmax = 0.0;
-  for (int i = t; i < D; i += nt) {
-    double sc;
-    if (st.iteration == 0) { sc = 1.0 / (1.0 + sqrt(S.Hd[i])); p.sx[(size_t)w * D + i] = sc; } else sc = p.sx[(size_t)w * D + i];
-    const double d2 = fmin(fmax(sc * sc * S.Hd[i], 1e-6), 1e32);
-    const double e = d2 / (sc * sc);
-    const double u = sc * sc * S.g[i] / d2;
-    S.s[i] = sc; S.e[i] = e; S.u[i] = u;
-    sums[0] += sc * sc * S.g[i] * S.g[i] / d2;
-    sums[1] += e * u * u;
-  }
-  // gradient_max_norm = |x - Plus(x, -g)|_inf  (TrustRegionMinimizer::EvaluateGradientAndJacobian)
-  if (t < F) {
-    const double* x = pose + 7 * t; const double* gg = &S.g[15 * t];
-    for (int k = 0; k < 3; k++) gmax = fmax(gmax, fabs(gg[k]));
-    Q4 q = ldq(x + 3); Q4 qn = qnormalized(qmul(q, deltaQ(mk3(-gg[3], -gg[4], -gg[5]))));
-    gmax = fmax(gmax, fmax(fmax(fabs(q.x - qn.x), fabs(q.y - qn.y)), fmax(fabs(q.z - qn.z), fabs(q.w - qn.w))));
-    for (int k = 6; k < 15; k++) gmax = fmax(gmax, fabs(gg[k]));
-  }
-  __syncthreads();
-  // S' = S + mu * E ; t = u^T S' u
-  for (int i = t; i < D; i += nt) Lp[pidx(i, i)] += mu * S.e[i];
-  __syncthreads();
-  double uSu = 0.0;
-  for (int i = t; i < D; i += nt) {
-    double acc = 0;
-    for (int j = 0; j <= i; j++) acc += Lp[pidx(i, j)] * S.u[j];
-    for (int j = i + 1; j < D; j++) acc += Lp[pidx(j, i)] * S.u[j];
-    uSu += acc * S.u[i];
-  }
-  sums[2] = uSu;
-  block_sum<6>(sums, S.red);
-  gmax = warp_max(gmax);
-  if (lane == 0) S.red[wid] = gmax;
-  __syncthreads();
-  if (t == 0) {
-    double gm = 0; for (int i = 0; i < (nt >> 5); i++) gm = fmax(gm, S.red[i]);
-    st.dlg2_x = sums[0]; st.uEu_x = sums[1]; st.uSu = sums[2]; st.gmax_x = gm;
-    S.flag = 0;
-    // FinalizeIterationAndCheckIfMinimizerCanContinue: gradient tolerance (checked after a successful step / iteration 0)
-    if (fmax(gm, st.gmax_l) <= p.gtol) { st.active = 0; st.termination = GF2_TERM_GRADIENT_TOL; S.flag = 2; }
-  }
-  __syncthreads();
-  if (S.flag == 2) return;
-  // Cholesky (right-looking, packed lower)
-  for (int j = 0; j < D; j++) {
-    if (t == 0) { const double d = Lp[pidx(j, j)]; if (!(d > 0.0)) S.flag = 1; else Lp[pidx(j, j)] = sqrt(d); }
-    __syncthreads();
-    if (S.flag) break;
-    const double dj = Lp[pidx(j, j)];
-    for (int i = j + 1 + t; i < D; i += nt) Lp[pidx(i, j)] /= dj;
-    __syncthreads();
-    for (int i = j + 1 + t; i < D; i += nt) {
-      const double lij = Lp[pidx(i, j)];
-      double* row = &Lp[pidx(i, 0)];
-      for (int k = j + 1; k <= i; k++) row[k] -= lij * Lp[pidx(k, j)];
-    }
-    __syncthreads();
-  }
-  if (S.flag == 1) {  // LINEAR_SOLVER_FAILURE: treated as an invalid step (mu *= 10, re-linearise); see DESIGN.md deviations
-    if (t == 0) {
-      st.mu *= 10.0; st.reuse = 0; st.iteration++; st.invalid_count++;
-      if (st.invalid_count >= 5 || st.mu >= 1.0) { st.active = 0; st.termination = GF2_TERM_FAILURE; }
-      else if (st.iteration >= p.max_iterations) { st.active = 0; st.termination = GF2_TERM_NO_CONVERGENCE; }
-      st.lin_valid = 0;
-    }
-    return;
-  }
-  // z = S'^-1 g  (forward, backward)
-  for (int i = t; i < D; i += nt) S.z[i] = S.g[i];
-  __syncthreads();
-  for (int j = 0; j < D; j++) {
-    if (t == 0) S.z[j] /= Lp[pidx(j, j)];
-    __syncthreads();
-    const double zj = S.z[j];
-    for (int i = j + 1 + t; i < D; i += nt) S.z[i] -= Lp[pidx(i, j)] * zj;
-    __syncthreads();
-  }
-  for (int j = D - 1; j >= 0; j--) {
-    if (t == 0) S.z[j] /= Lp[pidx(j, j)];
-    __syncthreads();
-    const double zj = S.z[j];
-    for (int i = t; i < j; i += nt) S.z[i] -= Lp[pidx(j, i)] * zj;
-    __syncthreads();
-  }
-  double s2[4] = {0, 0, 0, 0};  // gn2, gz, zEz, uEz
-  for (int i = t; i < D; i += nt) {
-    const double z = S.z[i], sc = S.s[i], e = S.e[i];
-    const double d2 = e * sc * sc;
-    s2[0] += d2 * z * z / (sc * sc);
-    s2[1] += S.g[i] * z;
-    s2[2] += e * z * z;
-    s2[3] += e * S.u[i] * z;
-    p.zx[(size_t)w * D + i] = z; p.ux[(size_t)w * D + i] = S.u[i]; p.ex_diag[(size_t)w * D + i] = e;
-  }
-  block_sum<4>(s2, S.red);
-  if (t == 0) { st.gn2_x = s2[0]; st.gz_x = s2[1]; st.zEz_x = s2[2]; st.uEz_x = s2[3]; st.lin_valid = 1; }
-}
 
 // ------------------------------------------------------------------------------------------------ k_backsub
 // sweep 2: z_l = (g_l - w_l^T z_x) / v'_l and the landmark parts of the dogleg dot products.
@@ -506,7 +322,7 @@ __global__ void __launch_bounds__(256, 3) k_backsub(KP p, int w0) {
   const int32_t* start = p.start + (size_t)w * p.Lm; const int32_t* tlen = p.tlen + (size_t)w * p.Lm; const int32_t* obeg = p.obeg + (size_t)w * p.Lm;
   const float4* obs = p.obs + (size_t)w * p.Om;
   build_frames(p.pose + (size_t)w * F * 7, p.ex + (size_t)w * 7, p.td[w], F, S.fr, &S.cam);
-  if (t < NV) { const int d = 15 * (t / 6) + t % 6; S.zx[t] = p.zx[(size_t)w * D + d]; S.ux[t] = p.ux[(size_t)w * D + d]; }
+  if (t < NV) { const int d = 15 * (t / 6) + t % 6; S.zx[t] = p.zx[(size_t)w * p.Ds + d]; S.ux[t] = p.ux[(size_t)w * p.Ds + d]; }
   __syncthreads();
   if (t < 2 * F) {
     const int f = t >> 1; const double* x = (t & 1) ? &S.ux[6 * f + 3] : &S.zx[6 * f + 3]; const double* R = S.fr[f].R;
@@ -626,7 +442,7 @@ __global__ void __launch_bounds__(288, 2) k_cand_eval(KP p, int w0) {
   double accx[3] = {0, 0, 0};  // frame states and non-visual factors (every rank computes the same): cost, |dx|^2, |x|^2
   // retraction of frame states: PoseLocalParameterization::Plus (VE/factor/pose_local_parameterization.cpp:12-28)
   if (t < F) {
-    const double* zx = p.zx + (size_t)w * D + 15 * t; const double* ux = p.ux + (size_t)w * D + 15 * t;
+    const double* zx = p.zx + (size_t)w * p.Ds + 15 * t; const double* ux = p.ux + (size_t)w * p.Ds + 15 * t;
     double dl[15];
     for (int k = 0; k < 15; k++) dl[k] = -(a * ux[k] + b * zx[k]);
     const double* x = pose + 7 * t; double* xc = pose_c + 7 * t;
@@ -637,6 +453,23 @@ __global__ void __launch_bounds__(288, 2) k_cand_eval(KP p, int w0) {
     accx[2] += q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w;
     const double* v = sb + 9 * t; double* vc = sb_c + 9 * t;
     for (int k = 0; k < 9; k++) { vc[k] = v[k] + dl[6 + k]; accx[1] += dl[6 + k] * dl[6 + k]; accx[2] += v[k] * v[k]; }
+  } else if (t == F && p.wcal) {
+    // free wheel calibration blocks (block row F of the reduced system): body_T_wheel by PoseLocalParameterization::Plus, the
+    // scalars additively; constant sub-blocks are copied (their step entries are zero) and stay out of the norms, as in Ceres
+    const double* zx = p.zx + (size_t)w * p.Ds + 15 * F; const double* ux = p.ux + (size_t)w * p.Ds + 15 * F;
+    double dl[10];
+    for (int k = 0; k < 10; k++) dl[k] = -(a * ux[k] + b * zx[k]);
+    const double* x = p.exw + (size_t)w * 7; double* xc = p.exw_c + (size_t)w * 7;
+    if (p.wcal & 1) {
+      for (int k = 0; k < 3; k++) { xc[k] = x[k] + dl[k]; accx[1] += dl[k] * dl[k]; accx[2] += x[k] * x[k]; }
+      Q4 q = ldq(x + 3); Q4 qn = qnormalized(qmul(q, deltaQ(mk3(dl[3], dl[4], dl[5]))));
+      xc[3] = qn.x; xc[4] = qn.y; xc[5] = qn.z; xc[6] = qn.w;
+      accx[1] += (q.x - qn.x) * (q.x - qn.x) + (q.y - qn.y) * (q.y - qn.y) + (q.z - qn.z) * (q.z - qn.z) + (q.w - qn.w) * (q.w - qn.w);
+      accx[2] += q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w;
+    } else for (int k = 0; k < 7; k++) xc[k] = x[k];
+    const double* sv = p.sxw + (size_t)w * 3; double* svc = p.sxw_c + (size_t)w * 3;
+    for (int k = 0; k < 3; k++) { const double d = (p.wcal & 2) ? dl[6 + k] : 0.0; svc[k] = sv[k] + d; if (p.wcal & 2) { accx[1] += d * d; accx[2] += sv[k] * sv[k]; } }
+    { const double d = (p.wcal & 4) ? dl[9] : 0.0; p.tdw_c[w] = p.tdw[w] + d; if (p.wcal & 4) { accx[1] += d * d; accx[2] += p.tdw[w] * p.tdw[w]; } }
   }
   __syncthreads();
   build_frames(pose_c, p.ex + (size_t)w * 7, p.td[w], F, S.fr, &S.cam);
@@ -711,14 +544,15 @@ __global__ void __launch_bounds__(288, 2) k_cand_eval(KP p, int w0) {
       const gf2_wheel_preint& pre = p.wheel[(size_t)w * (F - 1) + k];
       if (pre.valid && pre.sum_dt <= 10.0) {
         double r[6];
-        wheel_raw(pre, pose_c + 7 * k, pose_c + 7 * (k + 1), p.exw + (size_t)w * 7, p.sxw + (size_t)w * 3, p.tdw[w], r, nullptr);
+        const CalibPtr cal = calib_of(p, w, true);
+        wheel_raw(pre, pose_c + 7 * k, pose_c + 7 * (k + 1), cal.exw, cal.sxw, cal.tdw[0], r, nullptr);
         accx[0] += wheel_cost(p.wheel_sqrt + ((size_t)w * (F - 1) + k) * 36, r);
       }
     }
     const int n = p.prior_rows ? p.prior_rows[w] : 0;
     if (n > 0) {
       const gf2_prior_block* blk = p.prior_blocks + (size_t)w * (2 * F + 8);
-      if (ln < p.prior_nblocks[w]) prior_block_dx(blk[ln], pose_c, sb_c, S.dx);
+      if (ln < p.prior_nblocks[w]) prior_block_dx(blk[ln], pose_c, sb_c, calib_of(p, w, true), S.dx);
       __syncwarp();
       const double* J0 = p.prior_J0 + (size_t)w * p.Pr * p.Pr; const double* r0p = p.prior_r0 + (size_t)w * p.Pr;
       for (int row = ln; row < n; row += 32) { double s2 = r0p[row]; for (int c = 0; c < n; c++) s2 += J0[row * p.Pr + c] * S.dx[c]; accx[0] += 0.5 * s2 * s2; }
@@ -789,6 +623,11 @@ __global__ void __launch_bounds__(256) k_decide(KP p, int w0) {
     for (int i = t; i < F * 7; i += blockDim.x) poseW[i] = pose_c[i];
     for (int i = t; i < F * 9; i += blockDim.x) sbW[i] = sb_c[i];
     for (int l = t; l < nlm; l += blockDim.x) p.invdep[(size_t)w * p.Lm + l] = p.invdep_c[(size_t)w * p.Lm + l];
+    if (p.wcal) {
+      if (t < 7) p.exw[(size_t)w * 7 + t] = p.exw_c[(size_t)w * 7 + t];
+      else if (t < 10) p.sxw[(size_t)w * 3 + t - 7] = p.sxw_c[(size_t)w * 3 + t - 7];
+      else if (t == 10) p.tdw[w] = p.tdw_c[w];
+    }
   }
 }
 

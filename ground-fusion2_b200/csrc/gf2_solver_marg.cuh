@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(kMargThreads) k_marg_build(KP p, int w0, MargP
     const int nb = p.prior_nblocks[w];
     if (t < nb) {
       const gf2_prior_block& b = blk[t];
-      prior_block_dx(b, pose, sb, s.dx);
+      prior_block_dx(b, pose, sb, calib_of(p, w, false), s.dx);
       int col = -1, ls = (b.kind == GF2_BLK_POSE || b.kind == GF2_BLK_EX_POSE || b.kind == GF2_BLK_EX_WHEEL) ? 6 : (b.kind == GF2_BLK_SPEEDBIAS ? 9 : 1);
       if (mp.mode == 0) {
         if (b.kind == GF2_BLK_POSE && b.index == 0) { col = 0; s.mtouched[0] = 1; }

@@ -109,20 +109,30 @@ __global__ void __launch_bounds__(kNonvisThreads, 2) k_nonvis(KP p, int w0) {
       __syncwarp();
     }
   }
-  if (p.wheel) {  // WheelFactor: 6 residuals, pose_i / pose_j blocks (calibration constant)
+  if (p.wheel) {  // WheelFactor: 6 residuals, pose_i / pose_j blocks; with free calibration blocks (p.wcal) also their columns
     for (int k = wid; k < F - 1; k += nw) {
       const gf2_wheel_preint& pre = p.wheel[(size_t)w * (F - 1) + k];
       double* Hout = p.wheel_H + ((size_t)w * (F - 1) + k) * 108;
       double* gout = p.wheel_g + ((size_t)w * (F - 1) + k) * 12;
-      if (!pre.valid || pre.sum_dt > 10.0) { for (int i = lane; i < 108; i += 32) Hout[i] = 0.0; if (lane < 12) gout[lane] = 0.0; continue; }
-      double* J = scratch[wid];
+      double* Hc = p.wcal ? p.wheel_Hc + ((size_t)w * (F - 1) + k) * 220 : nullptr;
+      double* gc = p.wcal ? p.wheel_gc + ((size_t)w * (F - 1) + k) * 10 : nullptr;
+      if (!pre.valid || pre.sum_dt > 10.0) {
+        for (int i = lane; i < 108; i += 32) Hout[i] = 0.0;
+        if (lane < 12) gout[lane] = 0.0;
+        if (Hc) { for (int i = lane; i < 220; i += 32) Hc[i] = 0.0; if (lane < 10) gc[lane] = 0.0; }
+        continue;
+      }
+      double* J = scratch[wid];   // 6 x 12 [pose_i | pose_j]
       double* r = J + 72;
+      double* Jc = J + 80;        // 6 x 10 [ex_wheel 6 | sx | sy | sw | td_wheel]
       __syncwarp();
       if (lane == 0) wheel_raw(pre, pose + 7 * k, pose + 7 * (k + 1), p.exw + (size_t)w * 7, p.sxw + (size_t)w * 3, p.tdw[w], r, J);
+      else if (lane == 1 && p.wcal) wheel_calib_jacobians_masked(pre, pose + 7 * k, pose + 7 * (k + 1), p.exw + (size_t)w * 7, p.sxw + (size_t)w * 3, p.tdw[w], p.wcal, Jc);
       __syncwarp();
       const double* sq = p.wheel_sqrt + ((size_t)w * (F - 1) + k) * 36;
       if (lane < 12) { for (int a = 0; a < 6; a++) { double acc = 0; for (int kk = a; kk < 6; kk++) acc += sq[a * 6 + kk] * J[kk * 12 + lane]; J[a * 12 + lane] = acc; } }
       else if (lane == 12) { for (int a = 0; a < 6; a++) { double acc = 0; for (int kk = a; kk < 6; kk++) acc += sq[a * 6 + kk] * r[kk]; r[a] = acc; } }
+      else if (lane >= 16 && lane < 26 && p.wcal) { const int c = lane - 16; for (int a = 0; a < 6; a++) { double acc = 0; for (int kk = a; kk < 6; kk++) acc += sq[a * 6 + kk] * Jc[kk * 10 + c]; Jc[a * 10 + c] = acc; } }
       __syncwarp();
       if (lane == 0) { double c = 0; for (int a = 0; a < 6; a++) c += r[a] * r[a]; cost += 0.5 * c; }
       for (int idx = lane; idx < 108; idx += 32) {  // 6x6 blocks (i,i), (j,i), (j,j)
@@ -132,13 +142,22 @@ __global__ void __launch_bounds__(kNonvisThreads, 2) k_nonvis(KP p, int w0) {
         Hout[idx] = acc;
       }
       if (lane < 12) { double acc = 0; for (int rr = 0; rr < 6; rr++) acc += J[rr * 12 + lane] * r[rr]; gout[lane] = acc; }
+      if (Hc) {
+        for (int idx = lane; idx < 220; idx += 32) {
+          double acc = 0;
+          if (idx < 120) { const int a = (idx % 60) / 6, b = idx % 6 + (idx >= 60 ? 6 : 0); for (int rr = 0; rr < 6; rr++) acc += Jc[rr * 10 + a] * J[rr * 12 + b]; }
+          else { const int a = (idx - 120) / 10, b = (idx - 120) % 10; for (int rr = 0; rr < 6; rr++) acc += Jc[rr * 10 + a] * Jc[rr * 10 + b]; }
+          Hc[idx] = acc;
+        }
+        if (lane < 10) { double acc = 0; for (int rr = 0; rr < 6; rr++) acc += Jc[rr * 10 + lane] * r[rr]; gc[lane] = acc; }
+      }
       __syncwarp();
     }
   }
   const int n = p.prior_rows ? p.prior_rows[w] : 0;
   if (n > 0) {
     const gf2_prior_block* blk = p.prior_blocks + (size_t)w * (2 * F + 8);
-    if (t < p.prior_nblocks[w]) prior_block_dx(blk[t], pose, sb, dx);
+    if (t < p.prior_nblocks[w]) prior_block_dx(blk[t], pose, sb, calib_of(p, w, false), dx);
     __syncthreads();
     const double* J0 = p.prior_J0 + (size_t)w * p.Pr * p.Pr;
     const double* r0 = p.prior_r0 + (size_t)w * p.Pr;
@@ -162,14 +181,19 @@ __global__ void __launch_bounds__(kNonvisThreads, 2) k_nonvis(KP p, int w0) {
 constexpr int kNearBlk = 15 * kBS, kFarBlk = 6 * kBS;
 
 constexpr int kNBlkPairsS = kMaxF * (kMaxF + 1) / 2;
-static_assert(kSolveThreads >= 15 * kMaxF, "one thread per tangent dimension in the assembly");
+// Free wheel calibration blocks (KP::wcal) add ONE block row after the frames: "frame" F with tangent layout [ex_wheel 6 | sx sy sw |
+// td_wheel | 5 unused]. A wheel factor couples it to the pose rows of two frames, the factorisation fills the rest, so all its
+// blocks (F, J) are stored with 15 rows (12 more near blocks: 139 KB of shared memory, one window per SM in that mode). Constant
+// sub-blocks and the unused entries are decoupled unit diagonals.
+constexpr int kMaxFx = kMaxF + 1;
+static_assert(kSolveThreads >= 15 * kMaxFx, "one thread per tangent dimension in the assembly");
 
 struct Solve2Shared {
-  double g[kMaxF * 16], gs[kMaxF * 16], Hd[kMaxF * 16], s[kMaxF * 16], e[kMaxF * 16], u[kMaxF * 16], z[kMaxF * 16];
-  double yu[kMaxF * 16], fw[kMaxF * 16];  // L^T u and the forward-substitution result (= L^T z)
+  double g[kMaxFx * 16], gs[kMaxFx * 16], Hd[kMaxFx * 16], s[kMaxFx * 16], e[kMaxFx * 16], u[kMaxFx * 16], z[kMaxFx * 16];
+  double yu[kMaxFx * 16], fw[kMaxFx * 16];  // L^T u and the forward-substitution result (= L^T z)
   double red[8 * 32];
-  double dinv[kMaxF * 16];  // reciprocal diagonal of every factored diagonal block
-  int boff[kMaxF * kMaxF];  // offset of block (I, J), J <= I
+  double dinv[kMaxFx * 16];  // reciprocal diagonal of every factored diagonal block
+  int boff[kMaxFx * kMaxFx];  // offset of block (I, J), J <= I
   int blin[kMaxF * (kMaxF + 1) / 2];  // offset of block number I (I + 1) / 2 + J (the order k_linearize writes Svis in)
   int flag;
   int pad_;
@@ -177,7 +201,7 @@ struct Solve2Shared {
 };
 
 __host__ __device__ __forceinline__ int solve2_matrix_doubles(int F) { return (2 * F - 1) * kNearBlk + ((F - 1) * (F - 2) / 2) * kFarBlk; }
-__device__ __forceinline__ int brows(int I, int J) { return (I - J >= 2) ? 6 : 15; }
+__host__ __device__ __forceinline__ int solve2_matrix_doubles(int F, int wcal) { return solve2_matrix_doubles(F) + (wcal ? (F + 1) * kNearBlk : 0); }
 
 // C (rc rows) -= X (rx rows) * Y (ry rows)^T over k = 0..15 on the fp64 tensor cores, one warp; rows beyond a block's own
 // are never read (predicated to zero) or written. c may alias x.
@@ -271,8 +295,12 @@ __global__ void __launch_bounds__(kSolveThreads, 2) k_solve2(KP p, int w0) {
   Solve2Shared& S = *reinterpret_cast<Solve2Shared*>(smem_raw);
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5, nt = blockDim.x, nwarp = nt >> 5;
   const int F = p.F, D = p.D, NV = 6 * F;
-  const int NB = F * (F + 1) / 2;
-  const int NA = solve2_matrix_doubles(F);
+  const int Fc = p.wcal ? F : -1;            // block row of the free wheel calibration (none: -1)
+  const int Fx = F + (p.wcal ? 1 : 0), Dx = 15 * Fx;
+  const int NB = F * (F + 1) / 2, NBx = Fx * (Fx + 1) / 2;
+  const int NA = solve2_matrix_doubles(F, p.wcal);
+  auto brows = [&](int I, int J) -> int { return (I != Fc && I - J >= 2) ? 6 : 15; };
+  auto calib_live = [&](int c) -> bool { return c < 6 ? (p.wcal & 1) : c < 9 ? (p.wcal & 2) : c == 9 ? (p.wcal & 4) : false; };
   double* A = S.A;
 #ifdef GF2_PHASE_CLOCKS
   long long pc[16]; int npc = 0;
@@ -281,13 +309,14 @@ __global__ void __launch_bounds__(kSolveThreads, 2) k_solve2(KP p, int w0) {
 #define GF2_PC() do {} while (0)
 #endif
   GF2_PC();
-  if (t < NB) {  // block offsets, row-major over the lower triangle
+  if (t < NBx) {  // block offsets, row-major over the lower triangle (the calibration row, if any, comes last: all near blocks)
     int I = 0; while ((I + 1) * (I + 2) / 2 <= t) I++;
     const int J = t - I * (I + 1) / 2;
     int off = 0;
     for (int i = 0; i < I; i++) off += (i >= 2 ? (i - 1) * kFarBlk : 0) + (i >= 1 ? 2 : 1) * kNearBlk;
-    off += (J <= I - 2) ? J * kFarBlk : ((I >= 2 ? (I - 1) * kFarBlk : 0) + (J - (I >= 1 ? I - 1 : 0)) * kNearBlk);
-    S.boff[I * kMaxF + J] = off; S.blin[t] = off;
+    if (I == Fc) off += J * kNearBlk;
+    else off += (J <= I - 2) ? J * kFarBlk : ((I >= 2 ? (I - 1) * kFarBlk : 0) + (J - (I >= 1 ? I - 1 : 0)) * kNearBlk);
+    S.boff[I * kMaxFx + J] = off; if (t < NB) S.blin[t] = off;
   }
   // ---- assembly. Every global load of the visual and IMU parts is issued before anything waits on one (the per-element
   // load -> shared-memory update loops this replaces cost 40k cycles of exposed DRAM latency per window)
@@ -315,12 +344,12 @@ __global__ void __launch_bounds__(kSolveThreads, 2) k_solve2(KP p, int w0) {
   }
   GF2_PC();
   for (int i = t; i < NA; i += nt) A[i] = 0.0;
-  for (int i = t; i < F * 16; i += nt) { S.g[i] = 0.0; S.gs[i] = 0.0; S.Hd[i] = 0.0; S.z[i] = 0.0; S.u[i] = 0.0; }
+  for (int i = t; i < Fx * 16; i += nt) { S.g[i] = 0.0; S.gs[i] = 0.0; S.Hd[i] = 0.0; S.z[i] = 0.0; S.u[i] = 0.0; }
   __syncthreads();
   GF2_PC();
-  auto bidx2 = [&](int I, int J) -> int { return S.boff[I * kMaxF + J]; };
+  auto bidx2 = [&](int I, int J) -> int { return S.boff[I * kMaxFx + J]; };
   // element (i, j), j <= i, global tangent indices; rows a far block does not store read as zero / are never written
-  auto stored = [&](int i, int j) -> bool { const int I = i / 15, J = j / 15; return (I - J < 2) || (i - 15 * I) < 6; };
+  auto stored = [&](int i, int j) -> bool { const int I = i / 15, J = j / 15; return (I - J < 2) || (i - 15 * I) < 6 || I == Fc; };
   auto Ael2 = [&](int i, int j) -> double& { const int I = i / 15, J = j / 15; return A[bidx2(I, J) + (i - 15 * I) * kBS + (j - 15 * J)]; };
   // visual Schur complement (blocked 6x6 layout written by k_linearize: coalesced read, pose part of each block)
 #pragma unroll
@@ -386,25 +415,45 @@ __global__ void __launch_bounds__(kSolveThreads, 2) k_solve2(KP p, int w0) {
       if (K < F - 1) v += gw[K * 12 + r];
       S.g[15 * K + r] += v;
     }
+    if (p.wcal) {  // calibration block row: (calib, pose_K) from the factors K (as pose_i) and K-1 (as pose_j); (calib, calib) summed
+      const double* Hc = p.wheel_Hc + (size_t)w * (F - 1) * 220;
+      const double* gc = p.wheel_gc + (size_t)w * (F - 1) * 10;
+      for (int idx = t; idx < F * 60; idx += nt) {
+        const int K = idx / 60, e = idx % 60;
+        double v = 0.0;
+        if (K < F - 1) v += Hc[K * 220 + e];
+        if (K > 0) v += Hc[(K - 1) * 220 + 60 + e];
+        A[bidx2(F, K) + (e / 6) * kBS + e % 6] += v;
+      }
+      for (int idx = t; idx < 100; idx += nt) {
+        const int a = idx / 10, b = idx % 10;
+        double v = 0.0;
+        for (int K = 0; K < F - 1; K++) v += Hc[K * 220 + 120 + idx];
+        if (b <= a) A[bidx2(F, F) + a * kBS + b] += v;
+        if (a == b) S.Hd[15 * F + a] += v;
+      }
+      if (t < 10) { double v = 0.0; for (int K = 0; K < F - 1; K++) v += gc[K * 10 + t]; S.g[15 * F + t] += v; }
+    }
     __syncthreads();
   }
   if (t == 0) { st.cost_vis = p.c_lin[(size_t)w * 4]; st.gmax_l = p.c_gmax[w]; st.x_cost = st.cost_vis + p.cost_nv[w]; if (st.iteration == 0) st.initial_cost = st.x_cost; }
   if (p.Sfull) {
-    double* Sf = p.Sfull + (size_t)w * D * D;
-    for (int idx = t; idx < D * D; idx += nt) {
-      const int a = idx / D, b = idx % D; const int hi = a >= b ? a : b, lo = a >= b ? b : a;
+    double* Sf = p.Sfull + (size_t)w * p.Ds * p.Ds;   // Dx x Dx, packed at the front of the window's slot
+    for (int idx = t; idx < Dx * Dx; idx += nt) {
+      const int a = idx / Dx, b = idx % Dx; const int hi = a >= b ? a : b, lo = a >= b ? b : a;
       Sf[idx] = stored(hi, lo) ? Ael2(hi, lo) : 0.0;
     }
-    for (int i = t; i < D; i += nt) p.gfull[(size_t)w * D + i] = S.g[i] - S.gs[i];  // reduced gradient (rhs)
+    for (int i = t; i < Dx; i += nt) p.gfull[(size_t)w * p.Ds + i] = S.g[i] - S.gs[i];  // reduced gradient (rhs)
   }
   GF2_PC();
   // ---- Jacobi scaling (iteration 0), dogleg diagonal, gradient quantities
   const double mu = st.mu;
   double sums[3] = {0, 0, 0};  // dlg2, uEu, -
   double gmax = 0.0;
-  for (int i = t; i < D; i += nt) {
+  for (int i = t; i < Dx; i += nt) {
+    if (i >= D && !calib_live(i - D)) { S.s[i] = 1.0; S.e[i] = 0.0; S.u[i] = 0.0; S.g[i] = 0.0; continue; }  // constant / unused calibration entry
     double sc;
-    if (st.iteration == 0) { sc = 1.0 / (1.0 + sqrt(S.Hd[i])); p.sx[(size_t)w * D + i] = sc; } else sc = p.sx[(size_t)w * D + i];
+    if (st.iteration == 0) { sc = 1.0 / (1.0 + sqrt(S.Hd[i])); p.sx[(size_t)w * p.Ds + i] = sc; } else sc = p.sx[(size_t)w * p.Ds + i];
     const double d2 = fmin(fmax(sc * sc * S.Hd[i], 1e-6), 1e32);
     const double e = d2 / (sc * sc);
     const double u = sc * sc * S.g[i] / d2;
@@ -418,9 +467,18 @@ __global__ void __launch_bounds__(kSolveThreads, 2) k_solve2(KP p, int w0) {
     Q4 q = ldq(x + 3); Q4 qn = qnormalized(qmul(q, deltaQ(mk3(-gg[3], -gg[4], -gg[5]))));
     gmax = fmax(gmax, fmax(fmax(fabs(q.x - qn.x), fabs(q.y - qn.y)), fmax(fabs(q.z - qn.z), fabs(q.w - qn.w))));
     for (int k = 6; k < 15; k++) gmax = fmax(gmax, fabs(gg[k]));
+  } else if (t == F && p.wcal) {
+    const double* gg = &S.g[15 * F];
+    if (p.wcal & 1) {
+      const double* x = p.exw + (size_t)w * 7;
+      for (int k = 0; k < 3; k++) gmax = fmax(gmax, fabs(gg[k]));
+      Q4 q = ldq(x + 3); Q4 qn = qnormalized(qmul(q, deltaQ(mk3(-gg[3], -gg[4], -gg[5]))));
+      gmax = fmax(gmax, fmax(fmax(fabs(q.x - qn.x), fabs(q.y - qn.y)), fmax(fabs(q.z - qn.z), fabs(q.w - qn.w))));
+    }
+    for (int k = 6; k < 10; k++) if (calib_live(k)) gmax = fmax(gmax, fabs(gg[k]));
   }
   __syncthreads();
-  for (int i = t; i < D; i += nt) Ael2(i, i) += mu * S.e[i];
+  for (int i = t; i < Dx; i += nt) { if (i >= D && !calib_live(i - D)) Ael2(i, i) = 1.0; else Ael2(i, i) += mu * S.e[i]; }
   __syncthreads();
   block_sum<3>(sums, S.red);
   gmax = warp_max(gmax);
@@ -440,20 +498,23 @@ __global__ void __launch_bounds__(kSolveThreads, 2) k_solve2(KP p, int w0) {
   auto factor_diag = [&](int K) { if (factor_diag_block(A + bidx2(K, K), &S.dinv[16 * K], lane) && lane == 0) S.flag = 1; };  // by warp 0
   // right-hand side g - g_schur, kept per block with stride 16; it rides along the factorisation as one more row of every
   // panel (forward substitution for free): after block step K, S.fw[15 K ..] = (L^-1 rhs)_K
-  for (int i = t; i < D; i += nt) S.z[16 * (i / 15) + i % 15] = S.g[i] - S.gs[i];
+  for (int i = t; i < Dx; i += nt) S.z[16 * (i / 15) + i % 15] = S.g[i] - S.gs[i];
   if (wid == 0) factor_diag(0);
   __syncthreads();
 #ifdef GF2_PHASE_CLOCKS
   long long cp_panel = 0, cp_w0 = 0, cp_trail = 0, cq0, cq1, cq2, cq3;
 #endif
-  for (int K = 0; K < F && !S.flag; K++) {
+  for (int K = 0; K < Fx && !S.flag; K++) {
 #ifdef GF2_PHASE_CLOCKS
     cq0 = clock64();
 #endif
     const double* Akk = A + bidx2(K, K);
     // panel: X L_KK^T = A_IK, one thread per stored row of the block column (15 rows of the near block, 6 of each far one)
-    const int prow = (K + 1 < F ? 15 : 0) + 6 * (F - 2 - K > 0 ? F - 2 - K : 0);
-    const int pI = t < 15 ? K + 1 : K + 2 + (t - 15) / 6, prr = t < 15 ? t : (t - 15) % 6;
+    // plus the 15 rows of the calibration block row, if there is one below
+    const int nNear = K + 1 < F ? 15 : 0, nFar = 6 * (F - 2 - K > 0 ? F - 2 - K : 0), nCal = (Fc >= 0 && K < Fc) ? 15 : 0;
+    const int prow = nNear + nFar + nCal;
+    const int pI = t < nNear ? K + 1 : t < nNear + nFar ? K + 2 + (t - nNear) / 6 : Fc;
+    const int prr = t < nNear ? t : t < nNear + nFar ? (t - nNear) % 6 : t - nNear - nFar;
     if (t < prow) { double* row = A + bidx2(pI, K) + prr * kBS; panel_row(row, Akk, &S.dinv[16 * K], row); }
     else if (t == prow) panel_row(&S.z[16 * K], Akk, &S.dinv[16 * K], &S.fw[15 * K]);  // the right-hand-side row
     __syncthreads();
@@ -470,7 +531,7 @@ __global__ void __launch_bounds__(kSolveThreads, 2) k_solve2(KP p, int w0) {
 #endif
     // trailing update on the fp64 tensor cores: A_IJ -= L_IK L_JK^T for K < J <= I
     {
-      const int m = F - 1 - K;
+      const int m = Fx - 1 - K;
       const int npairs = m * (m + 1) / 2;
       if (wid == 0) {
         if (npairs > 0) { block_mma(A + bidx2(K + 1, K + 1), A + bidx2(K + 1, K), A + bidx2(K + 1, K), 15, 15, 15, lane); __syncwarp(); factor_diag(K + 1); }
@@ -504,10 +565,10 @@ __global__ void __launch_bounds__(kSolveThreads, 2) k_solve2(KP p, int w0) {
   }
   GF2_PC();
   // ---- yu = L^T u (needs the diagonal blocks as factored, before they are overwritten by their inverses)
-  for (int col = t; col < D; col += nt) {
+  for (int col = t; col < Dx; col += nt) {
     const int J = col / 15, c = col % 15;
     double yu = 0;
-    for (int I = J; I < F; I++) {
+    for (int I = J; I < Fx; I++) {
       const double* L = A + bidx2(I, J) + c;
       const int nr = brows(I, J);
       for (int r = 0; r < nr; r++) yu += L[r * kBS] * S.u[15 * I + r];
@@ -517,7 +578,7 @@ __global__ void __launch_bounds__(kSolveThreads, 2) k_solve2(KP p, int w0) {
   __syncthreads();
   GF2_PC();
   // ---- inverses of the diagonal blocks IN PLACE, all K in parallel (lane = column of L^-1, forward substitution down the rows)
-  for (int K = wid; K < F; K += nwarp) {
+  for (int K = wid; K < Fx; K += nwarp) {
     double* Akk = A + bidx2(K, K);
     double x[15];
     if (lane < 15) {
@@ -538,9 +599,9 @@ __global__ void __launch_bounds__(kSolveThreads, 2) k_solve2(KP p, int w0) {
   GF2_PC();
   // ---- z = L^-T fw: backward block substitution (the forward half was done inside the factorisation); the block solve by
   // warp 0, the column updates by one thread per column. z kept per block with stride 16.
-  for (int i = t; i < D; i += nt) S.z[16 * (i / 15) + i % 15] = S.fw[i];
+  for (int i = t; i < Dx; i += nt) S.z[16 * (i / 15) + i % 15] = S.fw[i];
   __syncthreads();
-  for (int K = F - 1; K >= 0; K--) {
+  for (int K = Fx - 1; K >= 0; K--) {
     if (wid == 0) {  // z_K = L_KK^-T z_K (explicit inverse)
       const double* Li = A + bidx2(K, K);
       double v = 0;
@@ -556,7 +617,7 @@ __global__ void __launch_bounds__(kSolveThreads, 2) k_solve2(KP p, int w0) {
       const int J = t / 15, c = t % 15;
       const double* Lc = A + bidx2(K, J) + c;
       double acc = 0.0;
-      if (K - J >= 2) {
+      if (brows(K, J) == 6) {
 #pragma unroll
         for (int r = 0; r < 6; r++) acc += Lc[r * kBS] * S.z[16 * K + r];
       } else {
@@ -571,18 +632,18 @@ __global__ void __launch_bounds__(kSolveThreads, 2) k_solve2(KP p, int w0) {
   // quadratic forms of the model cost change through the factor: u^T S' u = |L^T u|^2, u^T S' z = (L^T u) . (L^T z),
   // z^T S' z = |L^T z|^2 with L^T z = the forward-substitution result
   double s3[3] = {0, 0, 0};  // uSu, uSz, zSz
-  for (int col = t; col < D; col += nt) { const double yu = S.yu[col], yz = S.fw[col]; s3[0] += yu * yu; s3[1] += yu * yz; s3[2] += yz * yz; }
+  for (int col = t; col < Dx; col += nt) { const double yu = S.yu[col], yz = S.fw[col]; s3[0] += yu * yu; s3[1] += yu * yz; s3[2] += yz * yz; }
   block_sum<3>(s3, S.red);
   if (t == 0) { st.uSu = s3[0]; st.uSz = s3[1]; st.zSz = s3[2]; }
   double s2[4] = {0, 0, 0, 0};  // gn2, gz, zEz, uEz
-  for (int i = t; i < D; i += nt) {
+  for (int i = t; i < Dx; i += nt) {
     const double z = S.z[16 * (i / 15) + i % 15], sc = S.s[i], e = S.e[i];
     const double d2 = e * sc * sc;
     s2[0] += d2 * z * z / (sc * sc);
     s2[1] += S.g[i] * z;
     s2[2] += e * z * z;
     s2[3] += e * S.u[i] * z;
-    p.zx[(size_t)w * D + i] = z; p.ux[(size_t)w * D + i] = S.u[i]; p.ex_diag[(size_t)w * D + i] = e;
+    p.zx[(size_t)w * p.Ds + i] = z; p.ux[(size_t)w * p.Ds + i] = S.u[i]; p.ex_diag[(size_t)w * p.Ds + i] = e;
   }
   block_sum<4>(s2, S.red);
   if (t == 0) { st.gn2_x = s2[0]; st.gz_x = s2[1]; st.zEz_x = s2[2]; st.uEz_x = s2[3]; st.lin_valid = 1; }

@@ -309,8 +309,10 @@ int gf2_linearize(gf2_solver* h, int first, int n, const gf2_solve_opts* opts);
 int gf2_reduced_dim(gf2_solver* h, const gf2_solve_opts* opts);
 /* Reduced camera system of the last linearisation: S [n][D][D] (full symmetric, row-major, WITHOUT
  * the mu*diag regularisation), g [n][D] (reduced gradient J^T r after eliminating landmarks),
- * cost [n] = 0.5 * sum rho(|r|^2). Tangent order: per frame [pose 6 | speed-bias 9], then the free
- * blocks among ex-pose 6, td 1, ex-wheel 6, sx sy sw 3, td-wheel 1. */
+ * cost [n] = 0.5 * sum rho(|r|^2). D = gf2_reduced_dim(h, opts) of the options last linearised with.
+ * Tangent order: per frame [pose 6 | speed-bias 9]; when a wheel calibration block is free
+ * (const_mask lacks GF2_CONST_EX_WHEEL / _WHEEL_INTRINSIC / _TD_WHEEL) one more block of 15:
+ * [ex-wheel 6 | sx sy sw | td-wheel | 5 unused], rows/columns of constant sub-blocks are zero. */
 int gf2_get_reduced_system(gf2_solver* h, int first, int n, double* S, double* g, double* cost);
 
 int gf2_get_states(gf2_solver* h, int first, int n, double* para_pose, double* para_speedbias, double* ex_pose,

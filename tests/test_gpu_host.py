@@ -268,6 +268,6 @@ def test_feature_tracker_prediction_and_remove_outliers():
         got = {int(r[0]): r for r in out[:n]}
         assert sorted(got) == sorted(ids)
         for k2, i in enumerate(ids):
-            assert int(got[i][9]) == cnt[k2] and np.abs(got[i][4:6] - pts[k2]).max() <= 1e-4
+            assert int(got[i][9]) == cnt[k2] and np.abs(got[i][4:6] - pts[k2]).max() <= 1e-3   # LK tolerance, accumulated over the chained frames
     assert fallbacks == [None, False, True, False]
     L.gf2h_tracker_destroy(t)

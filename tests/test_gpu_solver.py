@@ -245,3 +245,100 @@ def test_wheel_preintegration_kernel_matches_oracle(gf2, oracle, synth):
     ref_p = w0["para_pose"]; scale_p = np.abs(ref_p).max()
     assert np.abs(st["para_pose"] - ref_p).max() <= 1e-4 * scale_p
     s.close()
+
+
+@pytest.mark.parametrize("free,nl,planes", [("exw", 300, 0), ("exw", 1000, 5000), ("exw+td", 200, 500), ("all", 300, 0)])
+def test_free_wheel_calibration_matches_oracle(gf2, oracle, synth, free, nl, planes):
+    """estimate_wheel_extrinsic: 1 (gc_test / groundchallenge / idc_rs / m2dgrp .yaml) frees para_Ex_Pose_wheel once the window is full
+    (VE/estimator/estimator.cpp:3063-3094); estimate_wheel_intrinsic / estimate_td_wheel free sx sy sw / td_wheel (:3095-3110, :3160).
+    The free blocks form one more block row of the reduced system: [ex_wheel 6 | sx sy sw | td_wheel | 5 unused]."""
+    abi = gf2.abi
+    n = 2
+    w = synth.make_windows(n, config_id=4, n_landmarks=nl, wheel=True, n_planes=planes)
+    oracle.imu_preintegrate(w); oracle.wheel_preintegrate(w)
+    w["sxsysw"][1] = [1.01, 0.99, 1.02]; w["td_wheel"][0] = 0.003
+    mask = abi.CONST_EX_POSE | abi.CONST_TD
+    live = list(range(165)) + list(range(165, 171))
+    if free == "exw":
+        mask |= abi.CONST_WHEEL_INTRINSIC | abi.CONST_TD_WHEEL
+    elif free == "exw+td":
+        mask |= abi.CONST_WHEEL_INTRINSIC; live += [174]
+    else:
+        live += [171, 172, 173, 174]
+    opts = abi.default_opts(const_mask=mask)
+    s = _solver4(gf2, w, n)
+    s.upload(w, preintegrate="records")
+    S, g, cost = s.linearize(opts, n)
+    assert S.shape[1:] == (180, 180)
+    dead = [i for i in range(180) if i not in live]
+    for i in range(n):
+        So, go, co, _, _ = oracle.linearize_window(w, i, opts)
+        assert So.shape == (len(live), len(live))
+        assert abs(cost[i] - co) <= 1e-12 * co
+        assert np.abs(S[i][np.ix_(live, live)] - So).max() <= 1e-10 * np.abs(So).max()
+        assert np.abs(g[i][live] - go).max() <= 1e-10 * np.abs(go).max()
+        assert not S[i][dead].any() and not S[i][:, dead].any() and not g[i][dead].any()
+    s.upload(w, preintegrate="records")
+    summ = s.solve(opts, n)
+    got = s.get_states(n)
+    wo = _copy(w)
+    so = oracle.solve_batch(wo, opts, n_threads=2)
+    assert (summ["iterations"] == so["iterations"]).all() and (summ["termination"] == so["termination"]).all()
+    assert (summ["successful_steps"] == so["successful_steps"]).all()
+    assert np.abs(summ["initial_cost"] - so["initial_cost"]).max() <= 1e-12 * so["initial_cost"].max()
+    assert (np.abs(summ["final_cost"] - so["final_cost"]) <= 1e-6 * so["final_cost"]).all()
+    scale = np.abs(wo["para_pose"][..., :3]).max()
+    assert np.abs(got["para_pose"][..., :3] - wo["para_pose"][..., :3]).max() <= 1e-4 * scale
+    assert np.abs(got["para_pose"][..., 3:] - wo["para_pose"][..., 3:]).max() <= 1e-4
+    # calibration blocks: weakly observable on a planar arc (cond(S) ~ 1e14), so judged relative to how far the solve moved them
+    for key in ("ex_pose_wheel", "sxsysw", "td_wheel"):
+        moved = np.abs(wo[key] - w[key]).max()
+        assert np.abs(got[key] - wo[key]).max() <= 1e-3 * moved + 1e-9, key
+    assert np.abs(wo["ex_pose_wheel"] - w["ex_pose_wheel"]).max() > 1e-3          # the extrinsic did move
+    if free == "exw":
+        assert np.array_equal(got["sxsysw"], w["sxsysw"]) and np.array_equal(got["td_wheel"], w["td_wheel"])   # constant blocks untouched
+    assert np.abs(np.linalg.norm(got["ex_pose_wheel"][:, 3:], axis=-1) - 1).max() < 1e-14
+    s.close()
+
+
+def test_prior_with_free_wheel_extrinsic_chain(gf2, oracle, synth):
+    """solve (free body_T_wheel) -> marginalize (the wheel factor of frame 0 puts body_T_wheel into the prior with a non-zero Jacobian)
+    -> next window solved with the device-resident prior and the extrinsic still free == the oracle doing the same on the host."""
+    abi = gf2.abi
+    n = 2
+    mask = abi.CONST_EX_POSE | abi.CONST_TD | abi.CONST_WHEEL_INTRINSIC | abi.CONST_TD_WHEEL
+    opts = abi.default_opts(const_mask=mask)
+    w = synth.make_windows(n, config_id=4, n_landmarks=300, wheel=True, prior="anchor")
+    oracle.imu_preintegrate(w); oracle.wheel_preintegrate(w)
+    s = gf2.Solver(n, w["n_frames"], w["max_landmarks"], w["max_obs"], use_wheel=True)
+    s.upload(w, preintegrate="records")
+    s.solve(opts, n)
+    st = s.get_states(n); lam = s.get_landmarks(n)
+    status, _ = s.marginalize(opts, mode=0)
+    assert (status == 0).all(), status
+    w2 = synth.make_windows(n, config_id=4, n_landmarks=300, wheel=True, prior="anchor", first_window=50)
+    oracle.imu_preintegrate(w2); oracle.wheel_preintegrate(w2)
+    # the calibration state carries over from the first solve (it is one physical quantity)
+    w2["ex_pose_wheel"][...] = st["ex_pose_wheel"]
+    s.set_states(w2); s.set_landmarks(w2); s.set_imu(w2["imu"]); s.set_wheel(w2["wheel"])
+    summ = s.solve(opts, n)
+    got = s.get_states(n)
+    for key in ("para_pose", "para_speedbias", "ex_pose_wheel"):
+        w[key][...] = st[key]
+    w["inv_depth"][...] = lam
+    for i in range(n):
+        ref = oracle.marginalize_window(w, i, opts, mode=0)
+        nn = ref["n"]; nb = len(ref["blocks"])
+        assert any(b["kind"] == abi.BLK_EX_WHEEL for b in ref["blocks"])
+        w2["prior_rows"][i] = nn; w2["prior_nblocks"][i] = nb
+        w2["prior_J0"][i] = 0; w2["prior_J0"][i, :nn, :nn] = ref["J0"]; w2["prior_r0"][i] = 0; w2["prior_r0"][i, :nn] = ref["r0"]
+        w2["prior_blocks"][i, :nb] = ref["blocks"]
+    start = w2["ex_pose_wheel"].copy()
+    so = oracle.solve_batch(w2, opts)
+    assert (summ["iterations"] == so["iterations"]).all()
+    assert (np.abs(summ["final_cost"] - so["final_cost"]) <= 1e-6 * so["final_cost"]).all()
+    scale = np.abs(w2["para_pose"]).max()
+    assert np.abs(got["para_pose"] - w2["para_pose"]).max() <= 1e-4 * scale
+    moved = np.abs(w2["ex_pose_wheel"] - start).max()
+    assert np.abs(got["ex_pose_wheel"] - w2["ex_pose_wheel"]).max() <= 1e-3 * moved + 1e-9
+    s.close()
