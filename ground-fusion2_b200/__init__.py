@@ -44,6 +44,7 @@ ABI_SYMBOLS = [
     "gf2_get_landmarks", "gf2_comm_init", "gf2_comm_unique_id", "gf2_last_timing", "gf2_tracker_create",
     "gf2_tracker_destroy", "gf2_tracker_track", "gf2_tracker_track_fb", "gf2_tracker_last_timing",
     "gf2_tracker_track_image", "gf2_tracker_detect", "gf2_tracker_min_eigen_map", "gf2_detect_select",
+    "gf2_tracker_equalize", "gf2_tracker_set_equalize", "gf2_tracker_get_image",
 ]
 
 
@@ -360,6 +361,22 @@ class Tracker:
         _check(lib().gf2_tracker_detect(self.h, S, _p(im), C.c_size_t(self.cfg.width), _p(mk), _p(mc), C.c_double(quality_level), C.c_double(min_distance),
                                         _p(out), _p(n)))
         return [out[s, :n[s]].copy() for s in range(S)]
+
+    def equalize(self, img, clip_limit=40.0, tiles=(8, 8)):
+        """cv2.createCLAHE(clip_limit, tiles).apply(img) for [H, W] or [S, H, W] uint8 images -> uint8 [S, H, W]."""
+        im, _ = self._imgs(img)
+        out = np.zeros_like(im)
+        _check(lib().gf2_tracker_equalize(self.h, im.shape[0], _p(im), C.c_size_t(self.cfg.width), C.c_double(clip_limit), int(tiles[0]), int(tiles[1]), _p(out)))
+        return out
+
+    def set_equalize(self, clip_limit=40.0, tiles=(8, 8)):
+        """Equalise every uploaded image on the device before it is tracked / searched (EQUALIZE of the reference's node)."""
+        _check(lib().gf2_tracker_set_equalize(self.h, C.c_double(clip_limit), int(tiles[0]), int(tiles[1])))
+
+    def get_image(self, n_streams=1):
+        out = np.zeros((n_streams, self.cfg.height, self.cfg.width), np.uint8)
+        _check(lib().gf2_tracker_get_image(self.h, n_streams, _p(out)))
+        return out
 
     def min_eigen_map(self, img):
         """cv::cornerMinEigenVal(img, 3, 3) of [H, W] or [S, H, W] uint8 images -> float32 [S, H, W]."""

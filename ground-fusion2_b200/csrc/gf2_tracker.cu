@@ -262,6 +262,8 @@ struct gf2_tracker {
   float *d_cov = nullptr, *d_eig = nullptr; uint8_t *d_mask = nullptr, *d_det_img = nullptr; unsigned* d_vmax = nullptr;
   unsigned long long* d_keys = nullptr; int32_t *d_count = nullptr, *d_want = nullptr; int key_cap = 0;
   std::vector<unsigned long long> h_keys; std::vector<int32_t> h_count;
+  // CLAHE of every uploaded image (gf2_tracker_set_equalize); the LUT buffer is allocated on first use
+  double eq_clip = 0.0; int eq_tx = 8, eq_ty = 8; uint8_t* d_lut = nullptr; int lut_tiles = 0;
   std::vector<void*> allocs;
   cudaEvent_t ev[4];
   double timing[8];
@@ -269,10 +271,30 @@ struct gf2_tracker {
 
 #define GF2T_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return gf2::fail(GF2_ERR_CUDA, "%s: %s", #x, cudaGetErrorString(e_)); } while (0)
 
+// cv::createCLAHE(clip, Size(tx, ty))->apply in place on n_streams device images of the tracker's size
+static int clahe_inplace(gf2_tracker* h, uint8_t* d_img, int n_streams, double clip, int tx, int ty) {
+  const int W = h->cfg.width, H = h->cfg.height;
+  if (tx < 1 || ty < 1 || W % tx || H % ty) return gf2::fail(GF2_ERR_UNSUPPORTED, "CLAHE tile grid %dx%d does not divide the image %dx%d (cv pads by reflection there; not built)", tx, ty, W, H);
+  if (!h->d_lut || h->lut_tiles < tx * ty) {
+    uint8_t* p = nullptr;
+    if (cudaMalloc((void**)&p, (size_t)h->cfg.max_streams * tx * ty * 256) != cudaSuccess) return gf2::fail(GF2_ERR_CUDA, "CLAHE LUT allocation failed");
+    h->allocs.push_back(p); h->d_lut = p; h->lut_tiles = tx * ty;
+  }
+  const int area = (W / tx) * (H / ty);
+  int clip_i = 0;
+  if (clip > 0.0) { clip_i = (int)(clip * area / 256); if (clip_i < 1) clip_i = 1; }   // clahe.cpp: static_cast<int>(clipLimit * tileSizeTotal / histSize), max 1
+  k_clahe_lut<<<dim3(tx * ty, n_streams), 256, 0, h->stream>>>(d_img, W, H, (size_t)W * H, tx, ty, clip_i, h->d_lut);
+  dim3 b(32, 8), g((W + 31) / 32, (H + 7) / 8, n_streams);
+  k_clahe_apply<<<g, b, 0, h->stream>>>(d_img, W, H, (size_t)W * H, tx, ty, h->d_lut);
+  GF2T_CUDA(cudaGetLastError());
+  return GF2_OK;
+}
+
 static int build_pyramid(gf2_tracker* h, int slot, int n_streams, const uint8_t* host_img, size_t stride, bool derivs_upto_all, int deriv_levels) {
   Pyr& P = h->pyr[slot];
   const int W = h->cfg.width, H = h->cfg.height;
   GF2T_CUDA(cudaMemcpy2DAsync(P.img[0], W, host_img, stride, W, (size_t)H * n_streams, cudaMemcpyHostToDevice, h->stream));
+  if (h->eq_clip > 0.0) { int rc = clahe_inplace(h, P.img[0], n_streams, h->eq_clip, h->eq_tx, h->eq_ty); if (rc) return rc; }
   for (int l = 1; l <= h->cfg.max_level; l++) {
     dim3 b(32, 8), g((P.w[l] + 31) / 32, (P.h[l] + 7) / 8, n_streams);
     k_pyrdown<<<g, b, 0, h->stream>>>(P.img[l - 1], P.w[l - 1], P.h[l - 1], P.w[l - 1], P.img[l], P.w[l], P.h[l], h->img_stride[l], h->img_stride[l - 1]);
@@ -471,6 +493,7 @@ static int detect_eig(gf2_tracker* h, int n_streams, const uint8_t* img, size_t 
   const uint8_t* d_img;
   if (img) {
     GF2T_CUDA(cudaMemcpy2DAsync(h->d_det_img, W, img, stride, W, (size_t)H * n_streams, cudaMemcpyHostToDevice, h->stream));
+    if (h->eq_clip > 0.0) { int rc = clahe_inplace(h, h->d_det_img, n_streams, h->eq_clip, h->eq_tx, h->eq_ty); if (rc) return rc; }
     d_img = h->d_det_img;
   } else {
     if (!h->have_prev) return gf2::fail(GF2_ERR_INVALID, "img == NULL but no image is cached from an earlier gf2_tracker_track* call");
@@ -544,6 +567,35 @@ int gf2_tracker_detect(gf2_tracker* h, int n_streams, const uint8_t* img, size_t
   cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]); h->timing[4] = ms;  // upload + detector kernels
   h->timing[3] = 3.0;
   h->timing[5] = (double)total;                                       // candidates moved to the host
+  return GF2_OK;
+}
+
+int gf2_tracker_set_equalize(gf2_tracker* h, double clip_limit, int tiles_x, int tiles_y) {
+  if (!h) return gf2::fail(GF2_ERR_INVALID, "null handle");
+  if (clip_limit > 0.0 && (tiles_x < 1 || tiles_y < 1 || h->cfg.width % tiles_x || h->cfg.height % tiles_y))
+    return gf2::fail(GF2_ERR_UNSUPPORTED, "CLAHE tile grid %dx%d does not divide the image %dx%d (cv pads by reflection there; not built)", tiles_x, tiles_y, h->cfg.width, h->cfg.height);
+  h->eq_clip = clip_limit > 0.0 ? clip_limit : 0.0; h->eq_tx = tiles_x; h->eq_ty = tiles_y;
+  return GF2_OK;
+}
+
+int gf2_tracker_equalize(gf2_tracker* h, int n_streams, const uint8_t* img, size_t stride, double clip_limit, int tiles_x, int tiles_y, uint8_t* out) {
+  if (!img || !out) return gf2::fail(GF2_ERR_INVALID, "null argument");
+  { int rc = detect_check(h, n_streams, img, stride); if (rc) return rc; }
+  const int W = h->cfg.width, H = h->cfg.height;
+  GF2T_CUDA(cudaMemcpy2DAsync(h->d_det_img, W, img, stride, W, (size_t)H * n_streams, cudaMemcpyHostToDevice, h->stream));
+  { int rc = clahe_inplace(h, h->d_det_img, n_streams, clip_limit, tiles_x, tiles_y); if (rc) return rc; }
+  GF2T_CUDA(cudaMemcpyAsync(out, h->d_det_img, (size_t)W * H * n_streams, cudaMemcpyDeviceToHost, h->stream));
+  GF2T_CUDA(cudaStreamSynchronize(h->stream));
+  return GF2_OK;
+}
+
+int gf2_tracker_get_image(gf2_tracker* h, int n_streams, uint8_t* out) {
+  if (!h || !out) return gf2::fail(GF2_ERR_INVALID, "null argument");
+  if (n_streams < 1 || n_streams > h->cfg.max_streams) return gf2::fail(GF2_ERR_INVALID, "n_streams %d outside [1, %d]", n_streams, h->cfg.max_streams);
+  if (!h->have_prev) return gf2::fail(GF2_ERR_INVALID, "no image is cached from an earlier gf2_tracker_track* call");
+  cudaSetDevice(h->cfg.device);
+  GF2T_CUDA(cudaMemcpyAsync(out, h->pyr[h->cur_slot].img[0], (size_t)h->cfg.width * h->cfg.height * n_streams, cudaMemcpyDeviceToHost, h->stream));
+  GF2T_CUDA(cudaStreamSynchronize(h->stream));
   return GF2_OK;
 }
 

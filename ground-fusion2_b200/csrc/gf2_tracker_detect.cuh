@@ -109,3 +109,70 @@ __global__ void __launch_bounds__(256) k_gftt_nms(const float* __restrict__ eig,
   const int slot = atomicAdd(&count[s], 1);
   if (slot < cap) keys[(size_t)s * cap + slot] = ((unsigned long long)gftt_ordered(v) << 32) | (unsigned)(y * W + x);
 }
+
+// ------------------------------------------------------------------------------------------------ CLAHE
+// cv::createCLAHE(clipLimit, tileGridSize)->apply for 8-bit images (VE/rosNodeTest.cpp:271-276, `equalize: 1` in m3dgr.yaml):
+//   k_clahe_lut    one CTA per (tile, stream): histogram, clip at max(int(clipLimit * tileArea / 256), 1), redistribution (batch + the
+//                  strided residual), LUT = saturate(cvRound(float(cumsum) * (255.f / tileArea)))
+//   k_clahe_apply  per pixel: bilinear blend of the four neighbouring tile LUTs in float32 with cv's operation order (no contraction)
+// In place on the image buffer (the LUT kernel has read every pixel before the apply kernel starts).
+__global__ void __launch_bounds__(256) k_clahe_lut(const uint8_t* __restrict__ img, int W, int H, size_t img_stride, int tiles_x, int tiles_y, int clip_limit,
+                                                    uint8_t* __restrict__ lut /* [stream][tiles_y * tiles_x][256] */) {
+  __shared__ int hist[256];
+  __shared__ int wsum[8];
+  __shared__ int s_clipped;
+  const int t = threadIdx.x, tile = blockIdx.x, s = blockIdx.y;
+  const int tw = W / tiles_x, th = H / tiles_y, tx = tile % tiles_x, ty = tile / tiles_x;
+  hist[t] = 0;
+  if (t == 0) s_clipped = 0;
+  __syncthreads();
+  const uint8_t* S = img + (size_t)s * img_stride + (size_t)(ty * th) * W + tx * tw;
+  for (int i = t; i < tw * th; i += 256) { const int y = i / tw, x = i - y * tw; atomicAdd(&hist[S[(size_t)y * W + x]], 1); }
+  __syncthreads();
+  int h = hist[t];
+  if (clip_limit > 0) {
+    if (h > clip_limit) { atomicAdd(&s_clipped, h - clip_limit); h = clip_limit; }
+    __syncthreads();
+    const int clipped = s_clipped;
+    const int batch = clipped / 256;
+    int residual = clipped - batch * 256;
+    h += batch;
+    if (residual != 0) {  // for (i = 0; i < 256 && residual > 0; i += step, residual--) hist[i]++
+      const int step = max(256 / residual, 1);
+      if (t % step == 0 && t / step < residual) h++;
+    }
+  }
+  // inclusive prefix sum over the 256 bins
+  int v = h;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int n = __shfl_up_sync(0xffffffffu, v, o); if ((t & 31) >= o) v += n; }
+  if ((t & 31) == 31) wsum[t >> 5] = v;
+  __syncthreads();
+  int base = 0;
+  for (int k = 0; k < (t >> 5); k++) base += wsum[k];
+  const int sum = v + base;
+  const float lut_scale = __fdiv_rn(255.f, (float)(tw * th));
+  int r = __float2int_rn(__fmul_rn((float)sum, lut_scale));
+  r = r < 0 ? 0 : (r > 255 ? 255 : r);
+  lut[((size_t)s * tiles_x * tiles_y + tile) * 256 + t] = (uint8_t)r;
+}
+
+__global__ void __launch_bounds__(256) k_clahe_apply(uint8_t* __restrict__ img, int W, int H, size_t img_stride, int tiles_x, int tiles_y,
+                                                      const uint8_t* __restrict__ lut) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y, s = blockIdx.z;
+  if (x >= W || y >= H) return;
+  const float inv_tw = __fdiv_rn(1.f, (float)(W / tiles_x)), inv_th = __fdiv_rn(1.f, (float)(H / tiles_y));
+  const float txf = __fsub_rn(__fmul_rn((float)x, inv_tw), 0.5f), tyf = __fsub_rn(__fmul_rn((float)y, inv_th), 0.5f);
+  int tx1 = (int)floorf(txf), ty1 = (int)floorf(tyf);
+  int tx2 = tx1 + 1, ty2 = ty1 + 1;
+  const float xa = __fsub_rn(txf, (float)tx1), xa1 = __fsub_rn(1.f, xa), ya = __fsub_rn(tyf, (float)ty1), ya1 = __fsub_rn(1.f, ya);
+  tx1 = max(tx1, 0); tx2 = min(tx2, tiles_x - 1); ty1 = max(ty1, 0); ty2 = min(ty2, tiles_y - 1);
+  uint8_t* px = img + (size_t)s * img_stride + (size_t)y * W + x;
+  const int v = *px;
+  const uint8_t* L = lut + (size_t)s * tiles_x * tiles_y * 256 + v;
+  const float l11 = L[(ty1 * tiles_x + tx1) * 256], l12 = L[(ty1 * tiles_x + tx2) * 256], l21 = L[(ty2 * tiles_x + tx1) * 256], l22 = L[(ty2 * tiles_x + tx2) * 256];
+  const float top = __fadd_rn(__fmul_rn(l11, xa1), __fmul_rn(l12, xa)), bot = __fadd_rn(__fmul_rn(l21, xa1), __fmul_rn(l22, xa));
+  const float res = __fadd_rn(__fmul_rn(top, ya1), __fmul_rn(bot, ya));
+  int r = __float2int_rn(res);
+  *px = (uint8_t)(r < 0 ? 0 : (r > 255 ? 255 : r));
+}

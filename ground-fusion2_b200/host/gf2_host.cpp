@@ -112,7 +112,7 @@ bool readParameters(const std::string& config_file, Parameters& P) {  // keys an
   Yaml y;
   if (!y.load(config_file)) return false;
   P.USE_IMU = (int)y.num("imu"); P.USE_WHEEL = (int)y.num("wheel");
-  P.MAX_CNT = (int)y.num("max_cnt"); P.MIN_DIST = (int)y.num("min_dist"); P.F_THRESHOLD = y.num("F_threshold"); P.FLOW_BACK = (int)y.num("flow_back");
+  P.MAX_CNT = (int)y.num("max_cnt"); P.MIN_DIST = (int)y.num("min_dist"); P.F_THRESHOLD = y.num("F_threshold"); P.FLOW_BACK = (int)y.num("flow_back"); P.EQUALIZE = (int)y.num("equalize");
   P.ACC_N = y.num("acc_n"); P.ACC_W = y.num("acc_w"); P.GYR_N = y.num("gyr_n"); P.GYR_W = y.num("gyr_w"); P.G_NORM = y.num("g_norm");
   P.SOLVER_TIME = y.num("max_solver_time"); P.NUM_ITERATIONS = (int)y.num("max_num_iterations");
   P.MIN_PARALLAX = y.num("keyframe_parallax") / FOCAL_LENGTH;  // :351-352
@@ -339,7 +339,7 @@ void Estimator::optimization() {
 FeatureTracker::FeatureTracker() {}
 FeatureTracker::~FeatureTracker() { if (trk) gf2_tracker_destroy(trk); }
 void FeatureTracker::readIntrinsicParameter(const Parameters& p) {
-  row = p.ROW; col = p.COL; MAX_CNT = p.MAX_CNT; MIN_DIST = p.MIN_DIST; FLOW_BACK = p.FLOW_BACK;
+  row = p.ROW; col = p.COL; MAX_CNT = p.MAX_CNT; MIN_DIST = p.MIN_DIST; FLOW_BACK = p.FLOW_BACK; EQUALIZE = p.EQUALIZE;
   fx = p.fx; fy = p.fy; cx = p.cx; cy = p.cy; k1 = p.k1; k2 = p.k2; p1 = p.p1; p2 = p.p2;
 }
 static inline int cvRound(double v) { return (int)std::nearbyint(v); }
@@ -444,6 +444,8 @@ std::map<int, std::vector<std::pair<int, std::vector<double>>>> FeatureTracker::
     gf2_tracker_cfg c; memset(&c, 0, sizeof(c));
     c.device = 0; c.width = col; c.height = row; c.max_pts = std::max(MAX_CNT, 8); c.win = 21; c.max_level = 3; c.max_iters = 30; c.max_streams = 1; c.eps = 0.01; c.min_eig = 1e-4;
     if (gf2_tracker_create(&c, &trk) != GF2_OK) { last_error = gf2_last_error(); trk = nullptr; return featureFrame; }
+    // EQUALIZE: the node's cv::createCLAHE()->apply (VE/rosNodeTest.cpp:271-276) moves onto the device, fused into the upload
+    if (EQUALIZE && gf2_tracker_set_equalize(trk, 40.0, 8, 8) != GF2_OK) { last_error = gf2_last_error(); return featureFrame; }
   }
   if (prev_pts.size() > 0) {
     int32_t n = (int32_t)prev_pts.size();
@@ -462,6 +464,7 @@ std::map<int, std::vector<std::pair<int, std::vector<double>>>> FeatureTracker::
     }
     int rc = gf2_tracker_track_image(trk, 1, nullptr, cur_img.data(), (size_t)col, &n, pin.data(), ppred.empty() ? nullptr : ppred.data(), FLOW_BACK, pout.data(), status.data(), 3);
     if (rc != GF2_OK) { last_error = gf2_last_error(); return featureFrame; }
+    if (EQUALIZE && gf2_tracker_get_image(trk, 1, cur_img.data()) != GF2_OK) { last_error = gf2_last_error(); return featureFrame; }  // cur_img as tracked
     for (int i = 0; i < n; i++) cur_pts[i] = {pout[2 * i], pout[2 * i + 1]};
     for (int i = 0; i < n; i++) {
       if (status[i] && !inBorder(cur_pts[i])) status[i] = 0;
@@ -476,6 +479,7 @@ std::map<int, std::vector<std::pair<int, std::vector<double>>>> FeatureTracker::
     int32_t n0 = 0; const size_t cap = (size_t)std::max(MAX_CNT, 8);  // the ABI moves max_pts-sized point arrays
     std::vector<float> dummy_in(cap * 2, 0.f), dummy_out(cap * 2, 0.f); std::vector<uint8_t> st(cap, 0);
     if (gf2_tracker_track(trk, 1, cur_img.data(), cur_img.data(), (size_t)col, &n0, dummy_in.data(), dummy_out.data(), st.data(), nullptr, 0, 3) != GF2_OK) { last_error = gf2_last_error(); return featureFrame; }
+    if (EQUALIZE && gf2_tracker_get_image(trk, 1, cur_img.data()) != GF2_OK) { last_error = gf2_last_error(); return featureFrame; }
   }
   for (auto& n : track_cnt) n++;
   setMask();
@@ -587,6 +591,7 @@ void* gf2h_tracker_create(int rows, int cols, int max_cnt, int min_dist, const d
   t->readIntrinsicParameter(p); return t;
 }
 void gf2h_tracker_destroy(void* t) { delete (FeatureTracker*)t; }
+void gf2h_tracker_set_equalize(void* t, int on) { ((FeatureTracker*)t)->EQUALIZE = on; }   // before the first image
 void gf2h_tracker_set_detector(void* t, FeatureTracker::Detector d, void* user) { ((FeatureTracker*)t)->setDetector(d, user); }
 void gf2h_tracker_set_prediction(void* t, int n, const int* ids, const double* xyz) {
   std::map<int, Vector3d> m; for (int i = 0; i < n; i++) m[ids[i]] = {xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]};

@@ -40,7 +40,7 @@ Matrix3d transpose(const Matrix3d& a);
 struct Parameters {
   double ACC_N = 0.1, ACC_W = 0.001, GYR_N = 0.01, GYR_W = 0.0001, G_NORM = 9.81007;
   double SOLVER_TIME = 0.04; int NUM_ITERATIONS = 8;
-  int ESTIMATE_EXTRINSIC = 0, ESTIMATE_TD = 0, USE_IMU = 1, USE_WHEEL = 0, MAX_CNT = 150, MIN_DIST = 30, FLOW_BACK = 1, ROW = 480, COL = 640;
+  int ESTIMATE_EXTRINSIC = 0, ESTIMATE_TD = 0, USE_IMU = 1, USE_WHEEL = 0, EQUALIZE = 0, MAX_CNT = 150, MIN_DIST = 30, FLOW_BACK = 1, ROW = 480, COL = 640;
   double TD = 0.0, F_THRESHOLD = 1.0, MIN_PARALLAX = 10.0 / FOCAL_LENGTH;
   Matrix3d RIC; Vector3d TIC;
   double fx = 0, fy = 0, cx = 0, cy = 0, k1 = 0, k2 = 0, p1 = 0, p2 = 0;  // camodocal PINHOLE (GF/config/realsense/color.yaml)
@@ -168,7 +168,7 @@ class FeatureTracker {
   std::vector<Point2f> ptsVelocity(const std::vector<int>& ids, const std::vector<Point2f>& pts, std::map<int, Point2f>& cur_id_pts, std::map<int, Point2f>& prev_id_pts);  // :810-847
   const char* lastError() const { return last_error.c_str(); }
 
-  int row = 480, col = 640, MAX_CNT = 150, MIN_DIST = 30, FLOW_BACK = 1;
+  int row = 480, col = 640, MAX_CNT = 150, MIN_DIST = 30, FLOW_BACK = 1, EQUALIZE = 0;
   double fx = 0, fy = 0, cx = 0, cy = 0, k1 = 0, k2 = 0, p1 = 0, p2 = 0;
   std::vector<uint8_t> mask, cur_img;
   std::vector<Point2f> n_pts, prev_pts, cur_pts, cur_un_pts, prev_un_pts, pts_velocity, predict_pts;

@@ -403,6 +403,22 @@ int gf2_detect_select(const uint64_t* keys, int n, int width, int height, int ma
 /* cv::cornerMinEigenVal(img, eig, 3, 3): the detector's score map, eig [n_streams][height][width] float (parity checks). */
 int gf2_tracker_min_eigen_map(gf2_tracker* h, int n_streams, const uint8_t* img, size_t stride, float* eig);
 
+/* cv::createCLAHE(clip_limit, Size(tiles_x, tiles_y))->apply(img, out) for 8-bit images: what getImageFromMsg does when
+ * EQUALIZE is set (VE/rosNodeTest.cpp:271-276; `equalize: 1` in config/realsense/m3dgr.yaml:16; cv defaults 40.0, 8x8).
+ * Bit-exact with cv2. The tile grid must divide the image size (cv pads by reflection otherwise: GF2_ERR_UNSUPPORTED).
+ * clip_limit <= 0 means no clipping, as in cv. */
+int gf2_tracker_equalize(gf2_tracker* h, int n_streams, const uint8_t* img, size_t stride, double clip_limit,
+                         int tiles_x, int tiles_y, uint8_t* out);
+
+/* The same equalisation fused into the front end: after this call every image uploaded by gf2_tracker_track*,
+ * gf2_tracker_detect and gf2_tracker_min_eigen_map is replaced ON THE DEVICE by its CLAHE before anything reads it, so the
+ * node's cv::CLAHE call (and one host pass over the image) disappears. clip_limit <= 0 switches it off again. */
+int gf2_tracker_set_equalize(gf2_tracker* h, double clip_limit, int tiles_x, int tiles_y);
+
+/* The `cur` images of the last gf2_tracker_track* call as the device holds them (equalised if set): trackImage reads
+ * cur_img on the host for its grey > 250 test (feature_tracker.cpp:160-167). out: [n_streams][height][width]. */
+int gf2_tracker_get_image(gf2_tracker* h, int n_streams, uint8_t* out);
+
 int gf2_tracker_last_timing(gf2_tracker* h, double out[8]);
 
 #ifdef __cplusplus

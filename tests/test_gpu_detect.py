@@ -96,3 +96,31 @@ def test_prediction_path_and_per_stream_fallback(gf2):
     b, sb = t.track_fb(prev, cur, pts)
     assert np.array_equal(a, b) and np.array_equal(sa, sb)
     t.close()
+
+
+def test_clahe_bit_exact_and_fused_into_the_front_end(gf2, gold):
+    """cv::createCLAHE()->apply of the node (VE/rosNodeTest.cpp:271-276, equalize: 1 in m3dgr.yaml) on the device: bit-exact with the cv2
+    golden vectors; switched on inside the tracker, track + detect see the equalised images without a host round trip."""
+    import clahe_oracle
+    from test_clahe_oracle import check_against_golden
+    t = gf2.Tracker(640, 480, max_pts=300, max_streams=2)
+    check_against_golden(lambda img, clip, tiles: t.equalize(img, clip, tiles)[0])
+    both = t.equalize(np.stack([gold["imgs"][0], gold["imgs"][2]]))
+    assert np.array_equal(both[0], clahe_oracle.apply(gold["imgs"][0])) and np.array_equal(both[1], clahe_oracle.apply(gold["imgs"][2]))
+    with pytest.raises(gf2.Gf2Error, match="does not divide"):
+        t.equalize(gold["imgs"][0], 40.0, (7, 8))
+    # fused: the same result as equalising on the host first
+    prev, cur, pts = lk.synthetic_pair(3, shift=(3.0, 1.0))
+    dark = lambda im: (im // 3 + 20).astype(np.uint8)   # low contrast: CLAHE changes it a lot
+    pe, ce = clahe_oracle.apply(dark(prev)), clahe_oracle.apply(dark(cur))
+    ref_out, ref_ok = t.track_fb(pe, ce, pts)
+    ref_new = t.detect(ce, 40)
+    t.set_equalize(40.0, (8, 8))
+    out, ok = t.track_fb(dark(prev), dark(cur), pts)
+    assert np.array_equal(out, ref_out) and np.array_equal(ok, ref_ok)
+    assert np.array_equal(t.get_image(1)[0], ce)
+    assert np.array_equal(t.detect(None, 40)[0], ref_new[0])          # on the cached (equalised) image
+    assert np.array_equal(t.detect(dark(cur), 40)[0], ref_new[0])     # on an uploaded image: equalised on the way in
+    t.set_equalize(0.0)
+    assert not np.array_equal(t.detect(dark(cur), 40)[0], ref_new[0])
+    t.close()
