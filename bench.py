@@ -159,6 +159,45 @@ def run_lk(gf2, synth, streams=64, steps=10, cv2_seconds=2.0):
             line["cpu_baseline"] = {"value": n / (time.perf_counter() - t0), "unit": "frame pairs/s", "kind": "reference", "sample": f"cv2 {cv2.__version__} calcOpticalFlowPyrLK x2, all threads, one stream, {cv2_seconds:.0f} s"}
         except ImportError:
             pass
+    # detector stage of trackImage (CLAHE of the node + goodFeaturesToTrack, feature_tracker.cpp:198) on the same streams: steady state,
+    # mask = MIN_DIST circles around the tracked points, 40 new corners wanted per stream
+    mask = np.full((streams, 480, 640), 255, np.uint8)
+    yy, xx = np.mgrid[:480, :640]
+    for s in range(min(streams, len(base))):
+        for p_ in base[s][2][:npts:2]:
+            mask[s][(xx - int(p_[0])) ** 2 + (yy - int(p_[1])) ** 2 <= 900] = 0
+    for s in range(len(base), streams):
+        mask[s] = mask[s % len(base)]
+    t.set_equalize(40.0, (8, 8))
+    for _ in range(2):
+        t.detect(cur, 40, mask=mask)
+    det_ms = 0.0; t0 = time.perf_counter()
+    for _ in range(steps):
+        corners = t.detect(cur, 40, mask=mask); det_ms += t.last_timing()["detect_ms"]
+    wall_d = time.perf_counter() - t0
+    t1.set_equalize(40.0, (8, 8))
+    one_d = []
+    for _ in range(10):
+        t0 = time.perf_counter(); t1.detect(cur[0], 40, mask=mask[0]); one_d.append((time.perf_counter() - t0) * 1e3)
+    # algorithmic bytes per frame: image read twice (CLAHE histogram + apply), written once, mask read, score map written + read once
+    bytes_det = 640 * 480 * (3 + 1 + 8)
+    line["detect"] = {"metric": "CLAHE + goodFeaturesToTrack frames/sec (640x480, 8x8 tiles, 40 new corners, mask)", "value": streams * steps / wall_d, "unit": "frames/s",
+                      "device_ms_per_batch": det_ms / steps, "single_stream_ms_per_frame": float(np.median(one_d)), "corners_per_frame": float(np.mean([len(c) for c in corners])),
+                      "roofline": {"bound": "hbm", "kernel": "k_gftt_cov + k_gftt_eig + k_gftt_nms + k_clahe_*", "achieved": bytes_det * streams / (det_ms / steps / 1e3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                   "frac": bytes_det * streams / (det_ms / steps / 1e3) / 1e9 / peaks["hbm_gbs"], "algorithmic_bytes_per_frame": bytes_det,
+                                   "note": "device_ms includes the H2D upload of image + mask; the column running sum of k_gftt_eig is sequential by construction (cv's rounding history)"}}
+    if cv2_seconds > 0:
+        try:
+            import cv2
+            cv2.setNumThreads(0)
+            cl = cv2.createCLAHE()
+            t0 = time.perf_counter(); n = 0
+            while time.perf_counter() - t0 < cv2_seconds:
+                s = n % len(base)
+                cv2.goodFeaturesToTrack(cl.apply(base[s][1]), 40, 0.01, 30, mask=mask[s]); n += 1
+            line["detect"]["cpu_baseline"] = {"value": n / (time.perf_counter() - t0), "unit": "frames/s", "kind": "reference", "sample": f"cv2 {cv2.__version__} CLAHE + goodFeaturesToTrack, all threads, one stream, {cv2_seconds:.0f} s"}
+        except ImportError:
+            pass
     t.close(); t1.close()
     return line
 

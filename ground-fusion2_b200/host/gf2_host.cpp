@@ -118,6 +118,21 @@ bool readParameters(const std::string& config_file, Parameters& P) {  // keys an
   P.MIN_PARALLAX = y.num("keyframe_parallax") / FOCAL_LENGTH;  // :351-352
   P.ESTIMATE_EXTRINSIC = (int)y.num("estimate_extrinsic"); P.ESTIMATE_TD = (int)y.num("estimate_td"); P.TD = y.num("td");
   P.ROW = (int)y.num("image_height"); P.COL = (int)y.num("image_width");
+  P.ONLY_INITIAL_WITH_WHEEL = (int)y.num("only_initial_with_wheel");
+  if (P.USE_WHEEL) {  // parameters.cpp:234-335
+    P.VEL_N_wheel = y.num("wheel_velocity_noise_sigma"); P.GYR_N_wheel = y.num("wheel_gyro_noise_sigma");
+    P.ESTIMATE_EXTRINSIC_WHEEL = (int)y.num("estimate_wheel_extrinsic"); P.EXTRINSIC_TYPE_WHEEL = (int)y.num("extrinsic_type_wheel");
+    P.ESTIMATE_INTRINSIC_WHEEL = (int)y.num("estimate_wheel_intrinsic");
+    if (y.scalars.count("sx")) P.SX = y.num("sx"); if (y.scalars.count("sy")) P.SY = y.num("sy"); if (y.scalars.count("sw")) P.SW = y.num("sw");
+    auto iw = y.matrices.find("body_T_wheel");
+    if (iw != y.matrices.end() && iw->second.size() == 16) {
+      const std::vector<double>& T = iw->second;
+      Matrix3d R; for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) R.m[r * 3 + c] = T[r * 4 + c];
+      P.RIO = toRotationMatrix(normalized(quatFromMatrix(R)));  // QIO.normalize() (:272-275)
+      P.TIO = {T[3], T[7], T[11]};
+    }
+  }
+  P.TD_WHEEL = y.num("td_wheel"); P.ESTIMATE_TD_WHEEL = (int)y.num("estimate_td_wheel");
   auto it = y.matrices.find("body_T_cam0");
   if (it != y.matrices.end() && it->second.size() == 16) {
     const std::vector<double>& T = it->second;
@@ -181,11 +196,17 @@ Estimator::Estimator() { clearState(); memset(&last_summary, 0, sizeof(last_summ
 Estimator::~Estimator() {
   if (gf2) gf2_solver_destroy(gf2);
   for (auto& p : pre_integrations) { delete p; p = nullptr; }
+  for (auto& p : pre_integrations_wheel) { delete p; p = nullptr; }
 }
-void Estimator::setParameter(const Parameters& p) { P = p; tic[0] = p.TIC; ric[0] = p.RIC; td = p.TD; }
+void Estimator::setParameter(const Parameters& p) {
+  P = p; tic[0] = p.TIC; ric[0] = p.RIC; td = p.TD;
+  tio = p.TIO; rio = p.RIO; sx = p.SX; sy = p.SY; sw = p.SW; td_wheel = p.TD_WHEEL;
+}
 void Estimator::clearState() {
   for (int i = 0; i <= WINDOW_SIZE; i++) { Rs[i] = Matrix3d(); Ps[i] = Vector3d(); Vs[i] = Vector3d(); Bas[i] = Vector3d(); Bgs[i] = Vector3d(); delete pre_integrations[i]; pre_integrations[i] = nullptr; }
+  for (auto& p : pre_integrations_wheel) { delete p; p = nullptr; }
   f_manager.feature.clear(); last_marginalization_info = MarginalizationPrior(); failure_occur = false; openExEstimation = false;
+  openExWheelEstimation = false; openIxEstimation = false;
 }
 
 void Estimator::vector2double() {
@@ -205,6 +226,12 @@ void Estimator::vector2double() {
   const std::vector<double> dep = f_manager.getDepthVector();
   for (int i = 0; i < f_manager.getFeatureCount(); i++) para_Feature[i][0] = dep[i];
   para_Td[0][0] = td;
+  // wheel blocks (estimator.cpp:2378-2390)
+  para_Ex_Pose_wheel[0][0] = tio.x; para_Ex_Pose_wheel[0][1] = tio.y; para_Ex_Pose_wheel[0][2] = tio.z;
+  const Quaterniond qw = quatFromMatrix(rio);
+  para_Ex_Pose_wheel[0][3] = qw.x; para_Ex_Pose_wheel[0][4] = qw.y; para_Ex_Pose_wheel[0][5] = qw.z; para_Ex_Pose_wheel[0][6] = qw.w;
+  para_Ix_sx_wheel[0][0] = sx; para_Ix_sy_wheel[0][0] = sy; para_Ix_sw_wheel[0][0] = sw;
+  para_Td_wheel[0][0] = td_wheel;
 }
 
 void Estimator::double2vector() {
@@ -237,6 +264,12 @@ void Estimator::double2vector() {
   for (int i = 0; i < f_manager.getFeatureCount(); i++) dep[i] = para_Feature[i][0];
   f_manager.setDepth(dep);
   if (P.USE_IMU) td = para_Td[0][0];
+  if (P.USE_WHEEL) {  // estimator.cpp:2584-2606
+    tio = {para_Ex_Pose_wheel[0][0], para_Ex_Pose_wheel[0][1], para_Ex_Pose_wheel[0][2]};
+    rio = toRotationMatrix(normalized({para_Ex_Pose_wheel[0][6], para_Ex_Pose_wheel[0][3], para_Ex_Pose_wheel[0][4], para_Ex_Pose_wheel[0][5]}));
+    sx = para_Ix_sx_wheel[0][0]; sy = para_Ix_sy_wheel[0][0]; sw = para_Ix_sw_wheel[0][0];
+    td_wheel = para_Td_wheel[0][0];
+  }
 }
 
 void Estimator::optimization() {
@@ -247,9 +280,12 @@ void Estimator::optimization() {
     gf2_solver_cfg cfg; memset(&cfg, 0, sizeof(cfg));
     cfg.device = 0; cfg.max_windows = 1; cfg.n_frames = WINDOW_SIZE + 1; cfg.max_landmarks = NUM_OF_F; cfg.max_obs = NUM_OF_F * (WINDOW_SIZE + 1);
     cfg.max_imu_samples = 64; cfg.max_prior_rows = GF2_MAX_PRIOR_DIM;
+    cfg.use_wheel = (P.USE_WHEEL && !P.ONLY_INITIAL_WITH_WHEEL) ? 1 : 0; cfg.max_wheel_samples = cfg.use_wheel ? 32 : 0;
     if (gf2_solver_create(&cfg, &gf2) != GF2_OK) { last_error = gf2_last_error(); gf2 = nullptr; return; }
   }
   if (F != WINDOW_SIZE + 1) { last_error = "gf2host::Estimator::optimization handles the steady state frame_count == WINDOW_SIZE"; return; }
+  const bool wheel_on = P.USE_WHEEL && !P.ONLY_INITIAL_WITH_WHEEL;   // estimator.cpp:3063, 3181
+  double sxsysw[3] = {para_Ix_sx_wheel[0][0], para_Ix_sy_wheel[0][0], para_Ix_sw_wheel[0][0]};
   // landmark table in getDepthVector order (used_num >= 4, estimator.cpp:3330-3358)
   std::vector<int32_t> start, len; std::vector<uint8_t> fixed; std::vector<gf2_obs> obs; std::vector<double> frame_td(F, td);
   for (auto& it_per_id : f_manager.feature) {
@@ -266,7 +302,7 @@ void Estimator::optimization() {
   int32_t n_lm = (int32_t)start.size();
   std::vector<double> invdep(NUM_OF_F, 1.0); for (int i = 0; i < n_lm; i++) invdep[i] = para_Feature[i][0];
   start.resize(NUM_OF_F, 0); len.resize(NUM_OF_F, 0); fixed.resize(NUM_OF_F, 0); obs.resize((size_t)NUM_OF_F * (WINDOW_SIZE + 1));
-  int rc = gf2_set_states(gf2, 0, 1, &para_Pose[0][0], &para_SpeedBias[0][0], para_Ex_Pose[0], para_Td[0], nullptr, nullptr, nullptr);
+  int rc = gf2_set_states(gf2, 0, 1, &para_Pose[0][0], &para_SpeedBias[0][0], para_Ex_Pose[0], para_Td[0], wheel_on ? para_Ex_Pose_wheel[0] : nullptr, wheel_on ? sxsysw : nullptr, wheel_on ? para_Td_wheel[0] : nullptr);
   if (rc == GF2_OK) rc = gf2_set_landmarks(gf2, 0, 1, &n_lm, invdep.data(), start.data(), len.data(), fixed.data(), obs.data(), frame_td.data());
   // raw IMU samples of every interval -> device preintegration (IntegrationBase::push_back chain)
   if (rc == GF2_OK && P.USE_IMU) {
@@ -282,6 +318,27 @@ void Estimator::optimization() {
     }
     const double noise[4] = {P.ACC_N, P.GYR_N, P.ACC_W, P.GYR_W};
     rc = gf2_imu_preintegrate(gf2, 0, 1, smp.data(), ns.data(), first.data(), bias.data(), noise);
+  }
+  // raw wheel samples of every interval -> device preintegration (WheelIntegrationBase::push_back chain), estimator.cpp:3181-3212
+  if (rc == GF2_OK && wheel_on) {
+    std::vector<gf2_wheel_sample> smp((size_t)(F - 1) * 32); std::vector<int32_t> ns(F - 1, 0); std::vector<double> first((F - 1) * 6, 0.0), lin((F - 1) * 4, 0.0);
+    for (int j = 1; j < F; j++) {
+      const WheelIntegrationBase* pi = pre_integrations_wheel[j];
+      if (!pi) { last_error = "pre_integrations_wheel[j] missing"; return; }
+      const int n = (int)std::min<size_t>(pi->dt_buf.size(), 32);
+      ns[j - 1] = n;
+      for (int k = 0; k < n; k++) { gf2_wheel_sample& o = smp[(size_t)(j - 1) * 32 + k]; o.dt = pi->dt_buf[k]; o.vel[0] = pi->vel_buf[k].x; o.vel[1] = pi->vel_buf[k].y; o.vel[2] = pi->vel_buf[k].z; o.gyr[0] = pi->gyr_buf[k].x; o.gyr[1] = pi->gyr_buf[k].y; o.gyr[2] = pi->gyr_buf[k].z; }
+      double* f6 = &first[(j - 1) * 6]; f6[0] = pi->linearized_vel.x; f6[1] = pi->linearized_vel.y; f6[2] = pi->linearized_vel.z; f6[3] = pi->linearized_gyr.x; f6[4] = pi->linearized_gyr.y; f6[5] = pi->linearized_gyr.z;
+      double* l4 = &lin[(j - 1) * 4]; l4[0] = pi->linearized_sx; l4[1] = pi->linearized_sy; l4[2] = pi->linearized_sw; l4[3] = pi->linearized_td;
+    }
+    const double noise[2] = {P.VEL_N_wheel, P.GYR_N_wheel};
+    rc = gf2_wheel_preintegrate(gf2, 0, 1, smp.data(), ns.data(), first.data(), lin.data(), noise);
+    if (rc == GF2_OK && wdetect && wheelanomaly) {  // "wheel anomaly, skip optimization" (:3195-3199): no wheel factor enters the problem
+      std::vector<gf2_wheel_preint> rec(F - 1);
+      rc = gf2_get_wheel(gf2, 0, 1, rec.data());
+      for (auto& r : rec) r.valid = 0;
+      if (rc == GF2_OK) rc = gf2_set_wheel(gf2, 0, 1, rec.data());
+    }
   }
   if (rc == GF2_OK) {
     const MarginalizationPrior& mp = last_marginalization_info;
@@ -299,20 +356,26 @@ void Estimator::optimization() {
     const double v0 = std::sqrt(Vs[0].x * Vs[0].x + Vs[0].y * Vs[0].y + Vs[0].z * Vs[0].z);
     if ((P.ESTIMATE_EXTRINSIC && frame_count == WINDOW_SIZE && v0 > 0.2) || openExEstimation) openExEstimation = true; else o.const_mask |= GF2_CONST_EX_POSE;
     if (!P.ESTIMATE_TD || v0 < 0.2) o.const_mask |= GF2_CONST_TD;
-    o.const_mask |= GF2_CONST_EX_WHEEL | GF2_CONST_WHEEL_INTRINSIC | GF2_CONST_TD_WHEEL;
+    // wheel calibration blocks (estimator.cpp:3063-3110, 3160-3161); extrinsic_type_wheel 0 = ADJUST_WHEEL_ALL (every shipped config)
+    if (wheel_on && P.ESTIMATE_EXTRINSIC_WHEEL && P.EXTRINSIC_TYPE_WHEEL != 0) { last_error = "extrinsic_type_wheel != 0 (PoseSubsetParameterization with constant components) is not built"; return; }
+    if ((wheel_on && P.ESTIMATE_EXTRINSIC_WHEEL && frame_count == WINDOW_SIZE && v0 > 0.2) || openExWheelEstimation) openExWheelEstimation = true; else o.const_mask |= GF2_CONST_EX_WHEEL;
+    if ((wheel_on && P.ESTIMATE_INTRINSIC_WHEEL && frame_count == WINDOW_SIZE && v0 > 0.2) || openIxEstimation) openIxEstimation = true; else o.const_mask |= GF2_CONST_WHEEL_INTRINSIC;
+    if (!P.ESTIMATE_TD_WHEEL || v0 < 0.2) o.const_mask |= GF2_CONST_TD_WHEEL;
     o.max_time_s = 0;  // SOLVER_TIME is a wall-clock cap: machine dependent, not reproduced
     rc = gf2_solve(gf2, 0, 1, &o, &last_summary);
   }
-  if (rc == GF2_OK) rc = gf2_get_states(gf2, 0, 1, &para_Pose[0][0], &para_SpeedBias[0][0], para_Ex_Pose[0], para_Td[0], nullptr, nullptr, nullptr);
+  if (rc == GF2_OK) rc = gf2_get_states(gf2, 0, 1, &para_Pose[0][0], &para_SpeedBias[0][0], para_Ex_Pose[0], para_Td[0], wheel_on ? para_Ex_Pose_wheel[0] : nullptr, wheel_on ? sxsysw : nullptr, wheel_on ? para_Td_wheel[0] : nullptr);
   if (rc == GF2_OK) { rc = gf2_get_landmarks(gf2, 0, 1, invdep.data()); for (int i = 0; i < n_lm; i++) para_Feature[i][0] = invdep[i]; }
   if (rc != GF2_OK) { last_error = gf2_last_error(); return; }  // the reference logs and carries on (no exceptions)
+  if (wheel_on) { para_Ix_sx_wheel[0][0] = sxsysw[0]; para_Ix_sy_wheel[0][0] = sxsysw[1]; para_Ix_sw_wheel[0][0] = sxsysw[2]; }
   double2vector();
 
   // ---- marginalization (estimator.cpp:3394-3690): runs at the states double2vector() left (yaw / position re-anchored),
   // re-packed by vector2double() exactly as the reference does at :3399 / :3603
   vector2double();
   for (int i = 0; i < n_lm; i++) invdep[i] = para_Feature[i][0];
-  rc = gf2_set_states(gf2, 0, 1, &para_Pose[0][0], &para_SpeedBias[0][0], para_Ex_Pose[0], para_Td[0], nullptr, nullptr, nullptr);
+  sxsysw[0] = para_Ix_sx_wheel[0][0]; sxsysw[1] = para_Ix_sy_wheel[0][0]; sxsysw[2] = para_Ix_sw_wheel[0][0];
+  rc = gf2_set_states(gf2, 0, 1, &para_Pose[0][0], &para_SpeedBias[0][0], para_Ex_Pose[0], para_Td[0], wheel_on ? para_Ex_Pose_wheel[0] : nullptr, wheel_on ? sxsysw : nullptr, wheel_on ? para_Td_wheel[0] : nullptr);
   if (rc == GF2_OK) rc = gf2_set_landmarks(gf2, 0, 1, &n_lm, invdep.data(), start.data(), len.data(), fixed.data(), obs.data(), frame_td.data());
   int32_t st = 0, m = 0;
   gf2_solve_opts o; memset(&o, 0, sizeof(o));
@@ -557,6 +620,26 @@ void gf2h_new_interval(void* e, int j, const double* acc0, const double* gyr0, c
   E->pre_integrations[j] = new IntegrationBase({acc0[0], acc0[1], acc0[2]}, {gyr0[0], gyr0[1], gyr0[2]}, {ba[0], ba[1], ba[2]}, {bg[0], bg[1], bg[2]});
 }
 void gf2h_push_imu(void* e, int j, double dt, const double* acc, const double* gyr) { ((Estimator*)e)->pre_integrations[j]->push_back(dt, {acc[0], acc[1], acc[2]}, {gyr[0], gyr[1], gyr[2]}); }
+// wheel: calibration {tio 3, rio 9 row-major, sx, sy, sw, td_wheel} and flags {use_wheel, estimate_extrinsic, estimate_intrinsic, estimate_td, vel_n, gyr_n}
+void gf2h_set_wheel_parameters(void* e, const double* calib16, const double* flags6) {
+  Estimator* E = (Estimator*)e; Parameters p = E->P;
+  p.TIO = {calib16[0], calib16[1], calib16[2]}; for (int i = 0; i < 9; i++) p.RIO.m[i] = calib16[3 + i];
+  p.SX = calib16[12]; p.SY = calib16[13]; p.SW = calib16[14]; p.TD_WHEEL = calib16[15];
+  p.USE_WHEEL = (int)flags6[0]; p.ESTIMATE_EXTRINSIC_WHEEL = (int)flags6[1]; p.ESTIMATE_INTRINSIC_WHEEL = (int)flags6[2]; p.ESTIMATE_TD_WHEEL = (int)flags6[3];
+  p.VEL_N_wheel = flags6[4]; p.GYR_N_wheel = flags6[5];
+  E->P = p; E->tio = p.TIO; E->rio = p.RIO; E->sx = p.SX; E->sy = p.SY; E->sw = p.SW; E->td_wheel = p.TD_WHEEL;
+}
+void gf2h_get_wheel_states(void* e, double* calib16, int* open_flags2) {
+  Estimator* E = (Estimator*)e;
+  calib16[0] = E->tio.x; calib16[1] = E->tio.y; calib16[2] = E->tio.z; for (int i = 0; i < 9; i++) calib16[3 + i] = E->rio.m[i];
+  calib16[12] = E->sx; calib16[13] = E->sy; calib16[14] = E->sw; calib16[15] = E->td_wheel;
+  open_flags2[0] = E->openExWheelEstimation; open_flags2[1] = E->openIxEstimation;
+}
+void gf2h_new_wheel_interval(void* e, int j, const double* vel0, const double* gyr0) {
+  Estimator* E = (Estimator*)e; delete E->pre_integrations_wheel[j];
+  E->pre_integrations_wheel[j] = new WheelIntegrationBase({vel0[0], vel0[1], vel0[2]}, {gyr0[0], gyr0[1], gyr0[2]}, E->sx, E->sy, E->sw, E->td_wheel);
+}
+void gf2h_push_wheel(void* e, int j, double dt, const double* vel, const double* gyr) { ((Estimator*)e)->pre_integrations_wheel[j]->push_back(dt, {vel[0], vel[1], vel[2]}, {gyr[0], gyr[1], gyr[2]}); }
 void gf2h_set_prior(void* e, int n, const double* J0, const double* r0, int nblocks, const gf2_prior_block* blocks) {
   MarginalizationPrior& mp = ((Estimator*)e)->last_marginalization_info;
   mp.valid = n > 0; mp.n = n; mp.linearized_jacobians.assign(J0, J0 + (size_t)n * n); mp.linearized_residuals.assign(r0, r0 + n); mp.blocks.assign(blocks, blocks + nblocks);

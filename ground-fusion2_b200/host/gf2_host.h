@@ -43,6 +43,10 @@ struct Parameters {
   int ESTIMATE_EXTRINSIC = 0, ESTIMATE_TD = 0, USE_IMU = 1, USE_WHEEL = 0, EQUALIZE = 0, MAX_CNT = 150, MIN_DIST = 30, FLOW_BACK = 1, ROW = 480, COL = 640;
   double TD = 0.0, F_THRESHOLD = 1.0, MIN_PARALLAX = 10.0 / FOCAL_LENGTH;
   Matrix3d RIC; Vector3d TIC;
+  // wheel odometer (parameters.cpp:181-194, 234-335, 501-502)
+  int ONLY_INITIAL_WITH_WHEEL = 0, ESTIMATE_EXTRINSIC_WHEEL = 0, ESTIMATE_INTRINSIC_WHEEL = 0, ESTIMATE_TD_WHEEL = 0, EXTRINSIC_TYPE_WHEEL = 0;
+  double VEL_N_wheel = 0.01, GYR_N_wheel = 0.004, SX = 1.0, SY = 1.0, SW = 1.0, TD_WHEEL = 0.0;
+  Matrix3d RIO; Vector3d TIO;
   double fx = 0, fy = 0, cx = 0, cy = 0, k1 = 0, k2 = 0, p1 = 0, p2 = 0;  // camodocal PINHOLE (GF/config/realsense/color.yaml)
 };
 // Reads the OpenCV-FileStorage YAML dialect of GF/config/realsense/m3dgr.yaml (+ the camera file named by cam0_calib);
@@ -61,6 +65,21 @@ class IntegrationBase {
   double sum_dt = 0.0;
   std::vector<double> dt_buf;
   std::vector<Vector3d> acc_buf, gyr_buf;
+};
+
+// Raw-sample buffer of one wheel preintegration interval (WheelIntegrationBase::push_back, VE/factor/wheel_integration_base.h:41-48);
+// the integration itself is gf2_wheel_preintegrate on the device.
+class WheelIntegrationBase {
+ public:
+  WheelIntegrationBase(const Vector3d& _vel_0, const Vector3d& _gyr_0, double _sx, double _sy, double _sw, double _td)
+      : vel_0(_vel_0), gyr_0(_gyr_0), linearized_vel(_vel_0), linearized_gyr(_gyr_0), linearized_sx(_sx), linearized_sy(_sy), linearized_sw(_sw), linearized_td(_td) {}
+  void push_back(double dt, const Vector3d& vel, const Vector3d& gyr) { dt_buf.push_back(dt); vel_buf.push_back(vel); gyr_buf.push_back(gyr); sum_dt += dt; vel_0 = vel; gyr_0 = gyr; }
+  Vector3d vel_0, gyr_0;
+  const Vector3d linearized_vel, linearized_gyr;
+  double linearized_sx, linearized_sy, linearized_sw, linearized_td;
+  double sum_dt = 0.0;
+  std::vector<double> dt_buf;
+  std::vector<Vector3d> vel_buf, gyr_buf;
 };
 
 class FeaturePerFrame {  // VE/estimator/feature_manager.h:28-62
@@ -129,6 +148,11 @@ class Estimator {
   double td = 0.0;
   int frame_count = WINDOW_SIZE;
   bool openExEstimation = false, failure_occur = false;
+  // wheel odometer states (estimator.h: tio, rio, sx, sy, sw, td_wheel; estimator.cpp:3063-3118, 3181-3212)
+  Vector3d tio; Matrix3d rio; double sx = 1.0, sy = 1.0, sw = 1.0, td_wheel = 0.0;
+  bool openExWheelEstimation = false, openIxEstimation = false, wdetect = false, wheelanomaly = false;
+  WheelIntegrationBase* pre_integrations_wheel[WINDOW_SIZE + 1] = {nullptr};
+  double para_Ex_Pose_wheel[1][7], para_Ix_sx_wheel[1][1], para_Ix_sy_wheel[1][1], para_Ix_sw_wheel[1][1], para_Td_wheel[1][1];
   Matrix3d last_R0; Vector3d last_P0;
   FeatureManager f_manager;
   IntegrationBase* pre_integrations[WINDOW_SIZE + 1] = {nullptr};

@@ -271,3 +271,69 @@ def test_feature_tracker_prediction_and_remove_outliers():
             assert int(got[i][9]) == cnt[k2] and np.abs(got[i][4:6] - pts[k2]).max() <= 1e-3   # LK tolerance, accumulated over the chained frames
     assert fallbacks == [None, False, True, False]
     L.gf2h_tracker_destroy(t)
+
+
+def test_estimator_optimization_with_wheel_and_free_wheel_extrinsic(gf2, oracle):
+    """wheel: 1, estimate_wheel_extrinsic: 1, extrinsic_type_wheel: 0 (gc_test / groundchallenge / idc_rs / m2dgrp .yaml): the C++ mirror
+    buffers the wheel samples, frees para_Ex_Pose_wheel once the window is full and |Vs[0]| > 0.2 (estimator.cpp:3063-3094), solves,
+    writes tio / rio back (double2vector :2584-2606) and marginalizes with the wheel factor of frame 0."""
+    synth = importlib.import_module("gf2_b200.synth")
+    abi = gf2.abi
+    L = H.lib()
+    nl = 300
+    w = synth.make_windows(1, config_id=4, n_landmarks=nl, wheel=True, n_planes=0)
+    e = C.c_void_p(L.gf2h_estimator_create())
+    R = np.stack([_R(w["para_pose"][0, i, 3:]) for i in range(11)])
+    P = w["para_pose"][0, :, :3]; sb = w["para_speedbias"][0]
+    L.gf2h_set_frame_states(e, H.p(H.frame_states(P, R, sb[:, :3], sb[:, 3:6], sb[:, 6:9])))
+    L.gf2h_set_extrinsic(e, H.p(w["ex_pose"][0, :3].copy()), H.p(_R(w["ex_pose"][0, 3:])), C.c_double(0.0), C.c_double(synth.G_NORM), H.p(w["imu_noise"]))
+    calib = np.concatenate([w["ex_pose_wheel"][0, :3], _R(w["ex_pose_wheel"][0, 3:]).ravel(), w["sxsysw"][0], [w["td_wheel"][0]]])
+    L.gf2h_set_wheel_parameters(e, H.p(calib), H.p(np.array([1.0, 1.0, 0.0, 0.0, w["wheel_noise"][0], w["wheel_noise"][1]])))
+    start = w["start_frame"][0, :nl]; tlen = w["track_len"][0, :nl]; beg = np.concatenate([[0], np.cumsum(tlen)[:-1]])
+    for f in range(11):
+        ids = np.array([l for l in range(nl) if start[l] <= f < start[l] + tlen[l]], np.int32)
+        pts = np.zeros((len(ids), 8))
+        for k, l in enumerate(ids):
+            o = w["obs"][0][beg[l] + f - start[l]]
+            pts[k] = [o["x"], o["y"], 1.0, 0, 0, o["vx"], o["vy"], -2.4]
+        L.gf2h_add_image(e, f, len(ids), H.p(ids), H.p(pts), C.c_double(0.0))
+    L.gf2h_set_depths(e, nl, H.p(np.arange(nl, dtype=np.int32)), H.p(1.0 / w["inv_depth"][0, :nl]), None)
+    for j in range(1, 11):
+        first = w["imu_first"][0, j - 1]; lb = w["imu_lin_bias"][0, j - 1]
+        L.gf2h_new_interval(e, j, H.p(first[:3].copy()), H.p(first[3:].copy()), H.p(lb[:3].copy()), H.p(lb[3:].copy()))
+        for s in w["imu_samples"][0, j - 1]:
+            L.gf2h_push_imu(e, j, C.c_double(s["dt"]), H.p(s["acc"].copy()), H.p(s["gyr"].copy()))
+        wf = w["wheel_first"][0, j - 1]
+        L.gf2h_new_wheel_interval(e, j, H.p(wf[:3].copy()), H.p(wf[3:].copy()))
+        for s in w["wheel_samples"][0, j - 1][: int(w["wheel_n"][0, j - 1])]:
+            L.gf2h_push_wheel(e, j, C.c_double(s["dt"]), H.p(s["vel"].copy()), H.p(s["gyr"].copy()))
+    n = int(w["prior_rows"][0])
+    L.gf2h_set_prior(e, n, H.p(w["prior_J0"][0, :n, :n].copy()), H.p(w["prior_r0"][0, :n].copy()), int(w["prior_nblocks"][0]), H.p(w["prior_blocks"][0]))
+    assert np.linalg.norm(sb[0, :3]) > 0.2          # the reference's excitation gate
+    summ = np.zeros(1, abi.SUMMARY)
+    rc = L.gf2h_optimization(e, H.p(summ))
+    assert rc == 0, L.gf2h_last_error(e)
+    out = np.zeros((11, 21)); L.gf2h_get_frame_states(e, H.p(out))
+    cal = np.zeros(16); flags = np.zeros(2, np.int32); L.gf2h_get_wheel_states(e, H.p(cal), H.p(flags))
+    assert flags[0] == 1 and flags[1] == 0                              # openExWheelEstimation latched, intrinsics stay fixed
+    # oracle: same window, body_T_wheel free
+    oracle.imu_preintegrate(w); oracle.wheel_preintegrate(w)
+    wo = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in w.items()}
+    opts = abi.default_opts(const_mask=abi.CONST_EX_POSE | abi.CONST_TD | abi.CONST_WHEEL_INTRINSIC | abi.CONST_TD_WHEEL)
+    so = oracle.solve_batch(wo, opts)
+    assert summ["iterations"][0] == so["iterations"][0] and abs(summ["final_cost"][0] - so["final_cost"][0]) < 1e-6 * so["final_cost"][0]
+    Ps, Rs, Vs = _double2vector(P[0], R[0], wo["para_pose"][0], wo["para_speedbias"][0])
+    assert np.abs(out[:, 0:3] - Ps).max() < 1e-4 * np.abs(Ps).max()
+    assert np.abs(out[:, 3:12].reshape(11, 3, 3) - Rs).max() < 1e-4
+    moved = np.abs(wo["ex_pose_wheel"][0] - w["ex_pose_wheel"][0]).max()
+    assert moved > 1e-3
+    assert np.abs(cal[:3] - wo["ex_pose_wheel"][0, :3]).max() <= 1e-3 * moved + 1e-9              # tio written back
+    assert np.abs(cal[3:12].reshape(3, 3) - _R(wo["ex_pose_wheel"][0, 3:])).max() <= 1e-3 * moved + 1e-9
+    assert np.array_equal(cal[12:], np.concatenate([w["sxsysw"][0], [w["td_wheel"][0]]]))            # constant blocks untouched
+    # the prior produced inside optimization() keeps body_T_wheel (+ sx sy sw td_wheel): 6 + 9 + 9*6... = 86 rows as in test_gpu_marg
+    nn = C.c_int(0); nb = C.c_int(0); stt = C.c_int(0)
+    J0 = np.zeros(96 * 96); r0 = np.zeros(96); blocks = np.zeros(30, abi.PRIOR_BLOCK)
+    assert L.gf2h_get_prior(e, C.byref(nn), H.p(J0), H.p(r0), C.byref(nb), H.p(blocks), C.byref(stt)) == 1 and stt.value == 0
+    kinds = set(int(b["kind"]) for b in blocks[:nb.value])
+    assert {abi.BLK_EX_WHEEL, abi.BLK_SX, abi.BLK_SY, abi.BLK_SW, abi.BLK_TD_WHEEL} <= kinds and nn.value == 86
+    L.gf2h_estimator_destroy(e)
