@@ -45,6 +45,7 @@ ABI_SYMBOLS = [
     "gf2_tracker_destroy", "gf2_tracker_track", "gf2_tracker_track_fb", "gf2_tracker_last_timing",
     "gf2_tracker_track_image", "gf2_tracker_detect", "gf2_tracker_min_eigen_map", "gf2_detect_select",
     "gf2_tracker_equalize", "gf2_tracker_set_equalize", "gf2_tracker_get_image",
+    "gf2_lio_create", "gf2_lio_destroy", "gf2_lio_set_map", "gf2_lio_build_factors", "gf2_lio_last_timing",
 ]
 
 
@@ -389,3 +390,47 @@ class Tracker:
         t = np.zeros(8)
         _check(lib().gf2_tracker_last_timing(self.h, _p(t)))
         return {"total_ms": t[0], "pyramid_ms": t[1], "lk_ms": t[2], "launches": int(t[3]), "detect_ms": t[4], "candidates": int(t[5])}
+
+
+class Lio:
+    """LIO factor construction: lidarodom::addSurfCostFactor (searchNeighbors + computeNeighborhoodDistribution + the residual gate,
+    LIO/liw/lio/lidarodom.cpp:887-1165) over a snapshot of the voxel map."""
+
+    def __init__(self, max_voxels, max_keypoints, max_points_per_voxel=20, device=0):
+        cfg = abi.LioCfg()
+        cfg.device = device; cfg.max_voxels = max_voxels; cfg.max_points_per_voxel = max_points_per_voxel; cfg.max_keypoints = max_keypoints
+        self.cfg = cfg
+        self.h = C.c_void_p()
+        _check(lib().gf2_lio_create(C.byref(cfg), C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            lib().gf2_lio_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_map(self, keys, n_points, points):
+        """keys [n, 3] int16, n_points [n] int32, points [n, max_points_per_voxel, 3] float64 (insertion order)."""
+        keys = np.ascontiguousarray(keys, np.int16); n_points = np.ascontiguousarray(n_points, np.int32); points = np.ascontiguousarray(points, np.float64)
+        assert points.shape[1] == self.cfg.max_points_per_voxel
+        _check(lib().gf2_lio_set_map(self.h, len(keys), _p(keys), _p(n_points), _p(points)))
+
+    def build_factors(self, keypoints, opts, want_neighbors=False):
+        """Returns (factors [n] abi.PLANE, alpha [n], neighbors or None, n_neighbors or None)."""
+        kp = np.ascontiguousarray(keypoints, abi.LIO_KEYPOINT)
+        cap = max(int(opts.max_num_residuals), 1)
+        fac = np.zeros(cap, abi.PLANE); alpha = np.zeros(cap); n = C.c_int32(0)
+        nb = np.zeros((len(kp), opts.max_number_neighbors, 3)) if want_neighbors else None
+        nn = np.zeros(len(kp), np.int32) if want_neighbors else None
+        _check(lib().gf2_lio_build_factors(self.h, len(kp), _p(kp), C.byref(opts), _p(fac), _p(alpha), C.byref(n), _p(nb), _p(nn)))
+        return fac[:n.value].copy(), alpha[:n.value].copy(), nb, nn
+
+    def last_timing(self):
+        t = np.zeros(8)
+        _check(lib().gf2_lio_last_timing(self.h, _p(t)))
+        return {"total_ms": t[0], "kernel_ms": t[1], "voxels": int(t[2]), "keypoints": int(t[3])}

@@ -59,6 +59,42 @@ SUMMARY = np.dtype([("initial_cost", "f8"), ("final_cost", "f8"), ("iterations",
                     ("termination", "i4"), ("pad_", "i4")], align=True)
 
 
+LIO_KEYPOINT = np.dtype([("raw_point", "f8", 3), ("point", "f8", 3), ("alpha_time", "f8")], align=True)
+ICP_CT_POINT_TO_PLANE, ICP_POINT_TO_PLANE = 0, 1
+
+
+class LioCfg(C.Structure):
+    _fields_ = [("device", C.c_int32), ("max_voxels", C.c_int32), ("max_points_per_voxel", C.c_int32), ("max_keypoints", C.c_int32)]
+
+
+class LioOpts(C.Structure):
+    _fields_ = [("size_voxel_map", C.c_double), ("max_dist_to_plane_icp", C.c_double), ("power_planarity", C.c_double),
+                ("weight_alpha", C.c_double), ("weight_neighborhood", C.c_double), ("nb_voxels_visited", C.c_int32),
+                ("threshold_voxel_capacity", C.c_int32), ("max_number_neighbors", C.c_int32), ("min_number_neighbors", C.c_int32),
+                ("num_closest_neighbors", C.c_int32), ("max_num_residuals", C.c_int32), ("icp_model", C.c_int32), ("pad_", C.c_int32),
+                ("translation_begin", C.c_double * 3), ("rotation", C.c_double * 4), ("translation", C.c_double * 3),
+                ("R_IL", C.c_double * 9), ("t_IL", C.c_double * 3)]
+
+
+def default_lio_opts(**kw):
+    """odometry options of LIO/config/m3dgr.yaml (size_voxel_map 0.2, 20 neighbours, max_dist_to_plane_icp 0.3, power_planarity 2,
+    weights 0.9 / 0.1, voxel_neighborhood 1, max_num_residuals 2000, CT_POINT_TO_PLANE), identity frame state."""
+    o = LioOpts()
+    o.size_voxel_map = 0.2; o.max_dist_to_plane_icp = 0.3; o.power_planarity = 2.0; o.weight_alpha = 0.9; o.weight_neighborhood = 0.1
+    o.nb_voxels_visited = 1; o.threshold_voxel_capacity = 1; o.max_number_neighbors = 20; o.min_number_neighbors = 20
+    o.num_closest_neighbors = 1; o.max_num_residuals = 2000; o.icp_model = ICP_CT_POINT_TO_PLANE
+    o.rotation[3] = 1.0
+    for i in (0, 4, 8):
+        o.R_IL[i] = 1.0
+    for k, v in kw.items():
+        if isinstance(v, (list, tuple, np.ndarray)):
+            for i, x in enumerate(np.asarray(v, np.float64).ravel()):
+                getattr(o, k)[i] = float(x)
+        else:
+            setattr(o, k, v)
+    return o
+
+
 class TrackerCfg(C.Structure):
     _fields_ = [("device", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("max_pts", C.c_int32),
                 ("win", C.c_int32), ("max_level", C.c_int32), ("max_iters", C.c_int32), ("max_streams", C.c_int32),

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libgf2_b200.so")
-SOURCES = ["gf2_solver.cu", "gf2_tracker.cu"]
+SOURCES = ["gf2_solver.cu", "gf2_tracker.cu", "gf2_lio.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "--expt-relaxed-constexpr", "-Xptxas", "-v", "-shared", "-lcudart", "-ldl"]
 

@@ -291,3 +291,61 @@ def image_pair(seed=0, w=640, h=480, shift=(3.3, -2.1), n_pts=300):
             pts.append((x + ix + 0.25 * ((x + y) % 3), y + iy + 0.125 * ((x * 7 + y) % 5)))
     pts = np.array(pts[:n_pts], np.float32)
     return prev, cur, pts
+
+
+def lio_scene(seed=0, n_map_points=60000, n_keypoints=3000, size_voxel_map=0.2, max_points_per_voxel=20, min_distance_points=0.05):
+    """Synthetic LIO scene: a room (ground, four walls, a box) sampled with 1 cm noise and inserted into a voxel map with the rules
+    of lidarodom::addPointToMap (LIO/liw/lio/lidarodom.cpp:1167-1213: at most max_points_per_voxel per voxel, new points at least
+    min_distance_points from those already there); keypoints of a new scan on the same surfaces (2 cm noise), some off-surface
+    (rejected by the point-to-plane gate) and some in unmapped space (too few neighbours). Returns a dict with the map snapshot
+    (keys, n_points, points), the keypoints (abi.LIO_KEYPOINT) and the frame state used to express them."""
+    rng = np.random.default_rng(4000 + seed)
+
+    def surface(n):
+        which = rng.integers(0, 6, n)
+        u, v = rng.uniform(-1, 1, n), rng.uniform(-1, 1, n)
+        p = np.zeros((n, 3))
+        for k in range(n):
+            w_ = which[k]
+            if w_ == 0: p[k] = (6 * u[k], 5 * v[k], 0.0)                       # ground
+            elif w_ == 1: p[k] = (6.0, 5 * u[k], 1.5 + 1.5 * v[k])             # walls
+            elif w_ == 2: p[k] = (-6.0, 5 * u[k], 1.5 + 1.5 * v[k])
+            elif w_ == 3: p[k] = (6 * u[k], 5.0, 1.5 + 1.5 * v[k])
+            elif w_ == 4: p[k] = (6 * u[k], -5.0, 1.5 + 1.5 * v[k])
+            else: p[k] = (2.0 + 0.5 * u[k], 1.0 + 0.5 * v[k], 1.0)             # box top
+        return p
+
+    pts = surface(n_map_points) + rng.normal(0, 0.01, (n_map_points, 3))
+    vox = {}
+    order = []
+    for p in pts:   # addPointToMap with min_num_points = 0
+        key = tuple(int(c / size_voxel_map) for c in p)    # short(point / voxel_size): truncation toward zero
+        blk = vox.get(key)
+        if blk is None:
+            vox[key] = [p]; order.append(key)
+        elif len(blk) < max_points_per_voxel:
+            d2 = min(10 * size_voxel_map * size_voxel_map, min(float(((q - p) ** 2).sum()) for q in blk))
+            if d2 > min_distance_points * min_distance_points:
+                blk.append(p)
+    perm = rng.permutation(len(order))     # the hash map has no meaningful order: hand the voxels over shuffled
+    keys = np.array([order[i] for i in perm], np.int16)
+    n_points = np.array([len(vox[order[i]]) for i in perm], np.int32)
+    points = np.zeros((len(order), max_points_per_voxel, 3))
+    for j, i in enumerate(perm):
+        points[j, :n_points[j]] = np.array(vox[order[i]])
+    # frame state: the sensor 1.2 m above the ground, slightly rotated
+    yaw = 0.3 + 0.1 * seed
+    q = np.array([0.0, 0.0, np.sin(yaw / 2), np.cos(yaw / 2)])
+    R = np.array([[np.cos(yaw), -np.sin(yaw), 0], [np.sin(yaw), np.cos(yaw), 0], [0, 0, 1.0]])
+    t = np.array([0.5, -0.3, 1.2])
+    world = surface(n_keypoints) + rng.normal(0, 0.02, (n_keypoints, 3))
+    off = rng.random(n_keypoints) < 0.10
+    world[off] += rng.normal(0, 0.35, (int(off.sum()), 3))                     # off-surface points
+    far = rng.random(n_keypoints) < 0.03
+    world[far] = rng.uniform(-3, 3, (int(far.sum()), 3)) + np.array([0, 0, 12.0])   # unmapped space
+    kp = np.zeros(n_keypoints, abi.LIO_KEYPOINT)
+    kp["point"] = world
+    kp["raw_point"] = (world - t) @ R          # R^T (p - t)
+    kp["alpha_time"] = rng.random(n_keypoints)
+    return {"keys": keys, "n_points": n_points, "points": points, "keypoints": kp, "rotation": q, "translation": t,
+            "translation_begin": t - np.array([0.05, 0.0, 0.0]), "size_voxel_map": size_voxel_map, "max_points_per_voxel": max_points_per_voxel}

@@ -421,6 +421,65 @@ int gf2_tracker_get_image(gf2_tracker* h, int n_streams, uint8_t* out);
 
 int gf2_tracker_last_timing(gf2_tracker* h, double out[8]);
 
+/* ---------------------------------------------------------------- LIO factor construction */
+/* lidarodom::addSurfCostFactor (LIO/liw/lio/lidarodom.cpp:929-1071) for one scan: per keypoint the voxel-hash nearest-neighbour
+ * search searchNeighbors (:1087-1165), the neighbourhood statistics computeNeighborhoodDistribution (:887-927: barycentre,
+ * covariance, normal = eigenvector of the smallest eigenvalue, planarity a2D), the weights and the point-to-plane gate, in
+ * keypoint order with the max_num_residuals cap. The output records are the constructor arguments of CTLidarPlaneNormFactor /
+ * LidarPlaneNormFactor (LIO/liw/lidarFactor.cpp:13-16, 52-56). The voxel map itself (addPointToMap, :1167-1213) stays with the
+ * caller, who hands over a snapshot. */
+typedef struct gf2_lio gf2_lio;
+
+typedef struct gf2_lio_cfg {
+  int32_t device;
+  int32_t max_voxels;           /* capacity of the map snapshot */
+  int32_t max_points_per_voxel; /* max_num_points_in_voxel (20) */
+  int32_t max_keypoints;
+} gf2_lio_cfg;
+
+typedef struct gf2_lio_keypoint { /* point3D (LIO/common/cloudMap.hpp:17-32): the fields the path reads */
+  double raw_point[3];
+  double point[3];
+  double alpha_time;
+} gf2_lio_keypoint;
+
+enum { GF2_ICP_CT_POINT_TO_PLANE = 0, GF2_ICP_POINT_TO_PLANE = 1 };
+
+typedef struct gf2_lio_opts {         /* lidarodom options (lidarodom.h:33-52) + the frame state the function reads */
+  double size_voxel_map;              /* 0.2 */
+  double max_dist_to_plane_icp;       /* 0.3 */
+  double power_planarity;             /* 2.0 */
+  double weight_alpha;                /* 0.9 */
+  double weight_neighborhood;         /* 0.1 */
+  int32_t nb_voxels_visited;          /* frame_id < init_num_frames ? 2 : voxel_neighborhood (1) */
+  int32_t threshold_voxel_capacity;   /* frame_id < init_num_frames ? 1 : threshold_voxel_occupancy */
+  int32_t max_number_neighbors;       /* 20, <= 32 */
+  int32_t min_number_neighbors;       /* 20 */
+  int32_t num_closest_neighbors;      /* 1 */
+  int32_t max_num_residuals;          /* 2000 */
+  int32_t icp_model;                  /* GF2_ICP_* */
+  int32_t pad_;
+  double translation_begin[3];        /* p_frame->p_state->translation_begin: orients the normal (:939) */
+  double rotation[4];                 /* p_state->rotation  [x y z w] (POINT_TO_PLANE: point_end, :1040-1042) */
+  double translation[3];              /* p_state->translation */
+  double R_IL[9];                     /* TIL_ = [R_IL | t_IL], row-major: location = TIL_ * raw_point (:988) */
+  double t_IL[3];
+} gf2_lio_opts;
+
+int gf2_lio_create(const gf2_lio_cfg* cfg, gf2_lio** out);
+void gf2_lio_destroy(gf2_lio* h);
+/* Snapshot of the voxelHashMap (tsl::robin_map<voxel, voxelBlock>, cloudMap.hpp:34-83): n_voxels entries in any order,
+ * keys [n][3] (short x, y, z), n_points [n], points [n][max_points_per_voxel][3] in insertion order. Duplicate keys are rejected. */
+int gf2_lio_set_map(gf2_lio* h, int n_voxels, const int16_t* keys, const int32_t* n_points, const double* points);
+/* out_factors [max_num_residuals]: p_body = raw_point (CT) or point_end (POINT_TO_PLANE), normal = nvec, offset =
+ * -nvec . neighbour, weight, frame = index of the keypoint (the reference's valid_keypoints); out_alpha [max_num_residuals] =
+ * kp.alpha_time; out_neighbors (nullable) [n_keypoints][max_number_neighbors][3] + out_n_neighbors [n_keypoints]: the sorted
+ * neighbour lists (what searchNeighbors returns); *n_out residuals written. */
+int gf2_lio_build_factors(gf2_lio* h, int n_keypoints, const gf2_lio_keypoint* keypoints, const gf2_lio_opts* opts,
+                          gf2_plane* out_factors, double* out_alpha, int32_t* n_out, double* out_neighbors,
+                          int32_t* out_n_neighbors);
+int gf2_lio_last_timing(gf2_lio* h, double out[8]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -188,3 +188,19 @@ def prior_information(prior, n_frames=11):
     Hs = prior["J0"].T @ prior["J0"]; gs = prior["J0"].T @ prior["r0"]
     H[np.ix_(cols, cols)] = Hs; g[cols] = gs
     return H, g, x0
+
+
+def lio_build_factors(scene, opts, want_neighbors=False):
+    """lidarodom::addSurfCostFactor restated (gf2o_lio.cpp) on a synth.lio_scene dict. Returns (factors, alpha, neighbors, n_neighbors)."""
+    from gf2_loader import load
+    abi = load().abi
+    kp = np.ascontiguousarray(scene["keypoints"]); keys = np.ascontiguousarray(scene["keys"], np.int16)
+    npts = np.ascontiguousarray(scene["n_points"], np.int32); pts = np.ascontiguousarray(scene["points"], np.float64)
+    cap = max(int(opts.max_num_residuals), 1)
+    fac = np.zeros(cap, abi.PLANE); alpha = np.zeros(cap)
+    nb = np.zeros((len(kp), opts.max_number_neighbors, 3)) if want_neighbors else None
+    nn = np.full(len(kp), -1, np.int32) if want_neighbors else None
+    n = lib.gf2o_lio_build_factors(len(keys), _p(keys), _p(npts), _p(pts), int(pts.shape[1]), len(kp), _p(kp), C.byref(opts), _p(fac), _p(alpha), _p(nb), _p(nn))
+    if n < 0:
+        raise RuntimeError("a2D is NaN (the reference throws)")
+    return fac[:n].copy(), alpha[:n].copy(), nb, nn
