@@ -283,9 +283,10 @@ int gf2_lio_build_factors(gf2_lio* h, int n_keypoints, const gf2_lio_keypoint* k
   const double R[9] = {1 - 2 * (qy * qy + qz * qz), 2 * (qx * qy - qz * qw), 2 * (qx * qz + qy * qw), 2 * (qx * qy + qz * qw), 1 - 2 * (qx * qx + qz * qz), 2 * (qy * qz - qx * qw),
                        2 * (qx * qz - qy * qw), 2 * (qy * qz + qx * qw), 1 - 2 * (qx * qx + qy * qy)};
   int num = 0;
-  for (int k = 0; k < n_keypoints && num < o->max_num_residuals; k++) {
+  bool full = false;   // the reference tests the cap AFTER pushing a residual (:1058-1061): at least one gets through
+  for (int k = 0; k < n_keypoints && !full; k++) {
     if (h->h_cnt[k] < 0) return gf2::fail(GF2_ERR_INVALID, "keypoint %d: planarity a2D is NaN (the reference throws here, lidarodom.cpp:921-924)", k);
-    for (int c = 0; c < h->h_cnt[k] && num < o->max_num_residuals; c++) {
+    for (int c = 0; c < h->h_cnt[k] && !full; c++) {
       const LioRec& r = h->h_rec[(size_t)k * kLioMaxClosest + c];
       gf2_plane& f = out_factors[num];
       memset(&f, 0, sizeof(f));
@@ -301,6 +302,7 @@ int gf2_lio_build_factors(gf2_lio* h, int n_keypoints, const gf2_lio_keypoint* k
       }
       out_alpha[num] = kp.alpha_time;
       num++;
+      if (num >= o->max_num_residuals) full = true;
     }
   }
   *n_out = num;

@@ -471,8 +471,8 @@ void gf2_lio_destroy(gf2_lio* h);
 /* Snapshot of the voxelHashMap (tsl::robin_map<voxel, voxelBlock>, cloudMap.hpp:34-83): n_voxels entries in any order,
  * keys [n][3] (short x, y, z), n_points [n], points [n][max_points_per_voxel][3] in insertion order. Duplicate keys are rejected. */
 int gf2_lio_set_map(gf2_lio* h, int n_voxels, const int16_t* keys, const int32_t* n_points, const double* points);
-/* out_factors [max_num_residuals]: p_body = raw_point (CT) or point_end (POINT_TO_PLANE), normal = nvec, offset =
- * -nvec . neighbour, weight, frame = index of the keypoint (the reference's valid_keypoints); out_alpha [max_num_residuals] =
+/* out_factors [max(max_num_residuals, 1)] (the reference tests the cap after pushing): p_body = raw_point (CT) or point_end (POINT_TO_PLANE), normal = nvec, offset =
+ * -nvec . neighbour, weight, frame = index of the keypoint (the reference's valid_keypoints); out_alpha [same] =
  * kp.alpha_time; out_neighbors (nullable) [n_keypoints][max_number_neighbors][3] + out_n_neighbors [n_keypoints]: the sorted
  * neighbour lists (what searchNeighbors returns); *n_out residuals written. */
 int gf2_lio_build_factors(gf2_lio* h, int n_keypoints, const gf2_lio_keypoint* keypoints, const gf2_lio_opts* opts,
