@@ -190,7 +190,7 @@ def prior_information(prior, n_frames=11):
     return H, g, x0
 
 
-def lio_build_factors(scene, opts, want_neighbors=False):
+def lio_build_factors(scene, opts, want_neighbors=False, timing=None):
     """lidarodom::addSurfCostFactor restated (gf2o_lio.cpp) on a synth.lio_scene dict. Returns (factors, alpha, neighbors, n_neighbors)."""
     from gf2_loader import load
     abi = load().abi
@@ -200,7 +200,10 @@ def lio_build_factors(scene, opts, want_neighbors=False):
     fac = np.zeros(cap, abi.PLANE); alpha = np.zeros(cap)
     nb = np.zeros((len(kp), opts.max_number_neighbors, 3)) if want_neighbors else None
     nn = np.full(len(kp), -1, np.int32) if want_neighbors else None
-    n = lib.gf2o_lio_build_factors(len(keys), _p(keys), _p(npts), _p(pts), int(pts.shape[1]), len(kp), _p(kp), C.byref(opts), _p(fac), _p(alpha), _p(nb), _p(nn))
+    secs = C.c_double(0.0)
+    n = lib.gf2o_lio_build_factors(len(keys), _p(keys), _p(npts), _p(pts), int(pts.shape[1]), len(kp), _p(kp), C.byref(opts), _p(fac), _p(alpha), _p(nb), _p(nn), C.byref(secs))
+    if timing is not None:
+        timing["loop_seconds"] = secs.value   # the keypoint loop alone: the voxel map is rebuilt per call and excluded
     if n < 0:
         raise RuntimeError("a2D is NaN (the reference throws)")
     return fac[:n].copy(), alpha[:n].copy(), nb, nn

@@ -5,6 +5,7 @@
 // (eigenvalues ascending; the eigenvector of a simple eigenvalue is unique up to sign and the sign is fixed by :939-940).
 // Parity unpinned (the reference holds no known-answer test for this function); pinned instead against an independent numpy
 // restatement (brute-force neighbour search + numpy.linalg.eigh) in tests/test_oracle_lio.py.
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <queue>
@@ -55,7 +56,7 @@ extern "C" {
 // returns the number of residuals; arrays as in gf2_lio_build_factors (out_neighbors / out_n_neighbors nullable)
 int gf2o_lio_build_factors(int n_voxels, const int16_t* keys, const int32_t* n_points, const double* points, int max_points_per_voxel, int n_keypoints,
                            const gf2_lio_keypoint* keypoints, const gf2_lio_opts* o, gf2_plane* out_factors, double* out_alpha, double* out_neighbors,
-                           int32_t* out_n_neighbors) {
+                           int32_t* out_n_neighbors, double* loop_seconds /* nullable: time of the keypoint loop alone (map build excluded) */) {
   Map map;
   for (int v = 0; v < n_voxels; v++) {
     std::vector<P3>& blk = map[Vox{keys[3 * v], keys[3 * v + 1], keys[3 * v + 2]}];
@@ -70,6 +71,8 @@ int gf2o_lio_build_factors(int n_voxels, const int16_t* keys, const int32_t* n_p
   const double R[9] = {1 - 2 * (qy * qy + qz * qz), 2 * (qx * qy - qz * qw), 2 * (qx * qz + qy * qw), 2 * (qx * qy + qz * qw), 1 - 2 * (qx * qx + qz * qz), 2 * (qy * qz - qx * qw),
                        2 * (qx * qz - qy * qw), 2 * (qy * qz + qx * qw), 1 - 2 * (qx * qx + qy * qy)};
   int num_residuals = 0;
+  const auto t_loop0 = std::chrono::steady_clock::now();
+  struct Stop { std::chrono::steady_clock::time_point t0; double* out; ~Stop() { if (out) *out = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); } } stop{t_loop0, loop_seconds};
   for (int k = 0; k < n_keypoints; ++k) {
     const gf2_lio_keypoint& kp = keypoints[k];
     const P3 pt = {kp.point[0], kp.point[1], kp.point[2]};
