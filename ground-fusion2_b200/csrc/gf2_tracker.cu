@@ -285,7 +285,9 @@ static int clahe_inplace(gf2_tracker* h, uint8_t* d_img, int n_streams, double c
   if (clip > 0.0) { clip_i = (int)(clip * area / 256); if (clip_i < 1) clip_i = 1; }   // clahe.cpp: static_cast<int>(clipLimit * tileSizeTotal / histSize), max 1
   k_clahe_lut<<<dim3(tx * ty, n_streams), 256, 0, h->stream>>>(d_img, W, H, (size_t)W * H, tx, ty, clip_i, h->d_lut);
   dim3 b(32, 8), g((W + 31) / 32, (H + 7) / 8, n_streams);
-  k_clahe_apply<<<g, b, 0, h->stream>>>(d_img, W, H, (size_t)W * H, tx, ty, h->d_lut);
+  const volatile float one = 1.f;   // keep the two divisions in IEEE single precision exactly as cv computes inv_tw / inv_th
+  const float inv_tw = one / (float)(W / tx), inv_th = one / (float)(H / ty);
+  k_clahe_apply<<<g, b, 0, h->stream>>>(d_img, W, H, (size_t)W * H, tx, ty, inv_tw, inv_th, h->d_lut);
   GF2T_CUDA(cudaGetLastError());
   return GF2_OK;
 }

@@ -47,7 +47,7 @@ __device__ __forceinline__ GfttRow gftt_row_sum(const float* __restrict__ C, siz
 }
 
 // one thread per image column; eig [stream][H][W]; vmax [stream] ordered-float maximum over the masked pixels
-constexpr int kGfttUnroll = 4;
+constexpr int kGfttUnroll = 8;   // rows of loads in flight per thread (the column walk is latency bound: 552 -> see profiles/)
 __global__ void __launch_bounds__(64) k_gftt_eig(const float* __restrict__ cov, const uint8_t* __restrict__ mask, int W, int H, float* __restrict__ eig,
                                                   unsigned* __restrict__ vmax) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x, s = blockIdx.y;
@@ -157,11 +157,12 @@ __global__ void __launch_bounds__(256) k_clahe_lut(const uint8_t* __restrict__ i
   lut[((size_t)s * tiles_x * tiles_y + tile) * 256 + t] = (uint8_t)r;
 }
 
-__global__ void __launch_bounds__(256) k_clahe_apply(uint8_t* __restrict__ img, int W, int H, size_t img_stride, int tiles_x, int tiles_y,
+// inv_tw = 1.f / tile width, inv_th = 1.f / tile height: IEEE divisions done once on the host (two fp32 divisions per pixel were a third
+// of the kernel's instructions)
+__global__ void __launch_bounds__(256) k_clahe_apply(uint8_t* __restrict__ img, int W, int H, size_t img_stride, int tiles_x, int tiles_y, float inv_tw, float inv_th,
                                                       const uint8_t* __restrict__ lut) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y, s = blockIdx.z;
   if (x >= W || y >= H) return;
-  const float inv_tw = __fdiv_rn(1.f, (float)(W / tiles_x)), inv_th = __fdiv_rn(1.f, (float)(H / tiles_y));
   const float txf = __fsub_rn(__fmul_rn((float)x, inv_tw), 0.5f), tyf = __fsub_rn(__fmul_rn((float)y, inv_th), 0.5f);
   int tx1 = (int)floorf(txf), ty1 = (int)floorf(tyf);
   int tx2 = tx1 + 1, ty2 = ty1 + 1;
