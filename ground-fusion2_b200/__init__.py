@@ -40,7 +40,7 @@ ABI_SYMBOLS = [
     "gf2_solver_set_stream", "gf2_snapshot_states", "gf2_restore_states", "gf2_host_alloc", "gf2_host_free",
     "gf2_imu_preintegrate_resident", "gf2_get_trace",
     "gf2_set_landmarks", "gf2_set_imu", "gf2_imu_preintegrate", "gf2_get_imu", "gf2_set_wheel", "gf2_wheel_preintegrate", "gf2_get_wheel", "gf2_set_prior",
-    "gf2_set_planes", "gf2_marginalize", "gf2_get_prior", "gf2_last_marginalize_ms", "gf2_solve", "gf2_linearize", "gf2_reduced_dim", "gf2_get_reduced_system", "gf2_get_states",
+    "gf2_set_planes", "gf2_set_plane_alpha", "gf2_marginalize", "gf2_get_prior", "gf2_last_marginalize_ms", "gf2_solve", "gf2_linearize", "gf2_reduced_dim", "gf2_get_reduced_system", "gf2_get_states",
     "gf2_get_landmarks", "gf2_comm_init", "gf2_comm_unique_id", "gf2_last_timing", "gf2_tracker_create",
     "gf2_tracker_destroy", "gf2_tracker_track", "gf2_tracker_track_fb", "gf2_tracker_last_timing",
     "gf2_tracker_track_image", "gf2_tracker_detect", "gf2_tracker_min_eigen_map", "gf2_detect_select",
@@ -179,6 +179,8 @@ class Solver:
 
     def set_planes(self, w, first=0):
         _check(lib().gf2_set_planes(self.h, first, w["n_planes"].shape[0], _p(w["n_planes"]), _p(w["planes"])))
+        if w.get("plane_alpha") is not None:   # alpha_time of the CTLidarPlaneNormFactor records (ct == 1)
+            _check(lib().gf2_set_plane_alpha(self.h, first, w["n_planes"].shape[0], _p(np.ascontiguousarray(w["plane_alpha"], np.float64))))
 
     def upload(self, w, first=0, preintegrate="auto"):
         """Everything a synth window dict holds. preintegrate: 'device' (raw samples -> kernel), 'records' (w['imu'])."""

@@ -18,7 +18,7 @@ WHEEL_PREINT = np.dtype([("sum_dt", "f8"), ("delta_p", "f8", 3), ("delta_q", "f8
                          ("lin_vel", "f8", 3), ("lin_gyr", "f8", 3), ("vel_1", "f8", 3), ("gyr_1", "f8", 3),
                          ("jacobian", "f8", 18), ("covariance", "f8", 36), ("valid", "i4"), ("pad_", "i4")], align=True)
 PLANE = np.dtype([("p_body", "f8", 3), ("normal", "f8", 3), ("offset", "f8"), ("weight", "f8"),
-                  ("frame", "i4"), ("pad_", "i4")], align=True)
+                  ("frame", "i4"), ("ct", "i4")], align=True)
 PRIOR_BLOCK = np.dtype([("kind", "i4"), ("index", "i4"), ("offset", "i4"), ("pad_", "i4"), ("x0", "f8", 9)], align=True)
 
 BLK_POSE, BLK_SPEEDBIAS, BLK_EX_POSE, BLK_TD, BLK_EX_WHEEL, BLK_SX, BLK_SY, BLK_SW, BLK_TD_WHEEL = range(9)

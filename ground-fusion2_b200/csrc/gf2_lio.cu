@@ -290,7 +290,7 @@ int gf2_lio_build_factors(gf2_lio* h, int n_keypoints, const gf2_lio_keypoint* k
       const LioRec& r = h->h_rec[(size_t)k * kLioMaxClosest + c];
       gf2_plane& f = out_factors[num];
       memset(&f, 0, sizeof(f));
-      f.normal[0] = r.normal[0]; f.normal[1] = r.normal[1]; f.normal[2] = r.normal[2]; f.offset = r.offset; f.weight = r.weight; f.frame = k;
+      f.normal[0] = r.normal[0]; f.normal[1] = r.normal[1]; f.normal[2] = r.normal[2]; f.offset = r.offset; f.weight = r.weight; f.frame = k; f.ct = (o->icp_model == GF2_ICP_CT_POINT_TO_PLANE) ? 1 : 0;
       const gf2_lio_keypoint& kp = keypoints[k];
       if (o->icp_model == GF2_ICP_CT_POINT_TO_PLANE) { f.p_body[0] = kp.raw_point[0]; f.p_body[1] = kp.raw_point[1]; f.p_body[2] = kp.raw_point[2]; }
       else {

@@ -323,7 +323,7 @@ int gf2_solver_create(const gf2_solver_cfg* cfg, gf2_solver** out) {
   }
   A(k.prior_rows, int32_t, B); A(k.prior_nblocks, int32_t, B); A(k.prior_J0, double, (size_t)B * k.Pr * k.Pr); A(k.prior_r0, double, (size_t)B * k.Pr);
   A(k.prior_blocks, gf2_prior_block, (size_t)B * (2 * F + 8)); A(k.prior_H, double, (size_t)B * k.Pr * k.Pr); A(k.prior_map, int32_t, (size_t)B * k.Pr);
-  if (Pm > 0) { A(k.n_planes, int32_t, B); A(k.planes, gf2_plane, (size_t)B * Pm); }
+  if (Pm > 0) { A(k.n_planes, int32_t, B); A(k.planes, gf2_plane, (size_t)B * Pm); A(k.plane_alpha, double, (size_t)B * Pm); }
   A(k.Svis, double, (size_t)B * kNVMax * kNVMax); A(k.gvis, double, (size_t)B * kNVP); A(k.gschur, double, (size_t)B * kNVP); A(k.Udiag, double, (size_t)B * kNVMax);
   A(k.lm_v, double, (size_t)B * Lm); A(k.lm_g, double, (size_t)B * Lm); A(k.lm_s, double, (size_t)B * Lm); A(k.lm_z, double, (size_t)B * Lm);
   A(k.sx, double, (size_t)B * k.Ds); A(k.zx, double, (size_t)B * k.Ds); A(k.ux, double, (size_t)B * k.Ds); A(k.ex_diag, double, (size_t)B * k.Ds);
@@ -569,9 +569,19 @@ int gf2_set_planes(gf2_solver* h, int first, int n, const int32_t* n_planes, con
   for (int w = 0; w < n; w++) for (int q = 0; q < n_planes[w]; q++) {
     const int f = planes[(size_t)w * k.Pm + q].frame;
     if (f < 0 || f >= k.F) return gf2::fail(GF2_ERR_INVALID, "window %d plane %d: frame %d outside [0, %d)", first + w, q, f, k.F);
+    if (planes[(size_t)w * k.Pm + q].ct && f + 1 >= k.F) return gf2::fail(GF2_ERR_INVALID, "window %d plane %d: a CT plane of frame %d needs the end pose %d", first + w, q, f, f + 1);
   }
-  if ((k.Pm + 31) / 32 + k.F > kMaxPlaneTasks) return gf2::fail(GF2_ERR_INVALID, "max_planes %d exceeds the task capacity", k.Pm);
+  if ((k.Pm + 31) / 32 + 2 * k.F > kMaxPlaneTasks) return gf2::fail(GF2_ERR_INVALID, "max_planes %d exceeds the task capacity", k.Pm);
   h->has_planes = true;
+  return GF2_OK;
+}
+
+int gf2_set_plane_alpha(gf2_solver* h, int first, int n, const double* alpha) {
+  GF2_TRY(check_range(h, first, n));
+  const KP& k = h->kp;
+  if (k.Pm <= 0) return gf2::fail(GF2_ERR_INVALID, "solver created with max_planes = 0");
+  if (!alpha) return gf2::fail(GF2_ERR_INVALID, "null argument");
+  H2D((double*)k.plane_alpha + (size_t)first * k.Pm, alpha, sizeof(double) * n * k.Pm);
   return GF2_OK;
 }
 

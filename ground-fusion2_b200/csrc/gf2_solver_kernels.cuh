@@ -75,6 +75,7 @@ struct KP {  // kernel parameters (device pointers are window-major with the str
   // planes
   const int32_t* n_planes;
   const gf2_plane* planes;
+  const double* plane_alpha;   // [nW][Pm] alpha_time of the ct == 1 planes (CTLidarPlaneNormFactor)
   // work
   double *Svis, *gvis, *gschur, *Udiag;  // [nW][66*66], [nW][72], [nW][72], [nW][66]
   double *lm_v, *lm_g, *lm_s, *lm_z; // [nW][Lm]

@@ -252,6 +252,55 @@ __device__ __forceinline__ double plane_residual(const gf2_plane& pl, const Fram
   return sw * (dot(n, pw) + pl.offset);
 }
 
+// Eigen's QuaternionBase::slerp (the call of LIO/liw/lidarFactor.cpp:67,81)
+__device__ __forceinline__ Q4 eigen_slerp(Q4 a, double t, Q4 b) {
+  const double one = 1.0 - 2.220446049250313e-16;
+  const double d = a.w * b.w + a.x * b.x + a.y * b.y + a.z * b.z, absD = fabs(d);
+  double s0, s1;
+  if (absD >= one) { s0 = 1.0 - t; s1 = t; }
+  else { const double theta = acos(absD), st = sin(theta); s0 = sin((1.0 - t) * theta) / st; s1 = sin(t * theta) / st; }
+  if (d < 0) s1 = -s1;
+  Q4 r; r.w = s0 * a.w + s1 * b.w; r.x = s0 * a.x + s1 * b.x; r.y = s0 * a.y + s1 * b.y; r.z = s0 * a.z + s1 * b.z;
+  return r;
+}
+__device__ __forceinline__ M3 inv3x3(const M3& a) {
+  const double* m = a.m;
+  const double c0 = m[4] * m[8] - m[5] * m[7], c1 = m[5] * m[6] - m[3] * m[8], c2 = m[3] * m[7] - m[4] * m[6];
+  const double id = 1.0 / (m[0] * c0 + m[1] * c1 + m[2] * c2);
+  M3 r;
+  r.m[0] = c0 * id; r.m[1] = (m[2] * m[7] - m[1] * m[8]) * id; r.m[2] = (m[1] * m[5] - m[2] * m[4]) * id;
+  r.m[3] = c1 * id; r.m[4] = (m[0] * m[8] - m[2] * m[6]) * id; r.m[5] = (m[2] * m[3] - m[0] * m[5]) * id;
+  r.m[6] = c2 * id; r.m[7] = (m[1] * m[6] - m[0] * m[7]) * id; r.m[8] = (m[0] * m[4] - m[1] * m[3]) * id;
+  return r;
+}
+// CTLidarPlaneNormFactor (LIO/liw/lidarFactor.cpp:58-123) attached to the window poses pose_b (begin) and pose_e (end): residual and
+// the 1x12 tangent Jacobian [t_begin 3 | q_begin 3 | t_end 3 | q_end 3]. The rotation blocks are the reference's formulas verbatim
+// (first order in the begin-end rotation difference).
+__device__ double ct_plane_residual(const gf2_plane& pl, double alpha, const double* pose_b, const double* pose_e, double sqrt_info, double* J /*12 or null*/) {
+  const V3 p = ld3(pl.p_body), n = ld3(pl.normal);
+  const V3 tb = ld3(pose_b), te = ld3(pose_e);
+  const Q4 qb = ldq(pose_b + 3), qe = ldq(pose_e + 3);
+  const Q4 qs = qnormalized(eigen_slerp(qb, alpha, qe));
+  const V3 ts = tb * (1.0 - alpha) + te * alpha;
+  const M3 Rs = toR(qs);
+  const V3 pw = mul(Rs, p) + ts;
+  const double sw = sqrt_info * pl.weight;
+  if (J) {
+    const V3 jrs = -1.0 * mulT(mul(Rs, skew(p)), n) * pl.weight;   // -(n^T R_slerp [p]x) * weight as a column
+    const Q4 rd = qmul(qinv(qb), qe);
+    Q4 id; id.w = 1.0; id.x = 0.0; id.y = 0.0; id.z = 0.0;
+    const Q4 rds = eigen_slerp(id, alpha, rd);
+    const M3 jsb = mulT(toR(rds), sub(eye3(), scale(mul(QleftBR(rds), inv3x3(QleftBR(rd))), alpha)));
+    const M3 jse = scale(mul(QrightBR(rds), inv3x3(QrightBR(rd))), alpha);
+    const V3 jb = mulT(jsb, jrs), je = mulT(jse, jrs);           // (jrs^T M)^T = M^T jrs
+    J[0] = sw * n.x * (1.0 - alpha); J[1] = sw * n.y * (1.0 - alpha); J[2] = sw * n.z * (1.0 - alpha);
+    J[3] = sqrt_info * jb.x; J[4] = sqrt_info * jb.y; J[5] = sqrt_info * jb.z;
+    J[6] = sw * n.x * alpha; J[7] = sw * n.y * alpha; J[8] = sw * n.z * alpha;
+    J[9] = sqrt_info * je.x; J[10] = sqrt_info * je.y; J[11] = sqrt_info * je.z;
+  }
+  return sw * (dot(n, pw) + pl.offset);
+}
+
 // 0.5 * |sqrt_info * r|^2 by one thread
 __device__ __forceinline__ double imu_cost(const double* sq /*15x15 upper*/, const double* r) {
   double c = 0;
@@ -515,7 +564,13 @@ __global__ void __launch_bounds__(288, 2) k_cand_eval(KP p, int w0) {
   if (p.planes && t < 256) {  // LiDAR plane residuals at the candidate
     const int np = p.n_planes[w];
     const gf2_plane* pls = p.planes + (size_t)w * p.Pm;
-    for (int q = t; q < np; q += 256) { const double r = plane_residual(pls[q], S.fr[pls[q].frame], p.lidar_sqrt_info, nullptr); acc[0] += 0.5 * r * r; }
+    const double* palpha = p.plane_alpha ? p.plane_alpha + (size_t)w * p.Pm : nullptr;
+    for (int q = t; q < np; q += 256) {
+      const int f = pls[q].frame;
+      const double r = pls[q].ct ? ct_plane_residual(pls[q], palpha ? palpha[q] : 0.0, pose_c + 7 * f, pose_c + 7 * (f + 1), p.lidar_sqrt_info, nullptr)
+                                 : plane_residual(pls[q], S.fr[f], p.lidar_sqrt_info, nullptr);
+      acc[0] += 0.5 * r * r;
+    }
   }
   // IMU / wheel factors and the prior at the candidate: warp 8 alone, concurrently with the landmark warps
   if (t >= 256) {

@@ -30,7 +30,7 @@ constexpr int kMaxPlaneTasks = 192;  // planes: up to ~5.8k per window in tasks 
 __global__ void k_tasks(KP p, int w0) {
   const int w = w0 + blockIdx.x;
   const int t = threadIdx.x, F = p.F;
-  __shared__ int cnt[kMaxF], ofs[kMaxF + 1];
+  __shared__ int cnt[2 * kMaxF], ofs[2 * kMaxF + 1];
   const int nlm = p.nlm[w];
   const int32_t* start = p.start + (size_t)w * p.Lm;
   if (t < F) { int c = 0; for (int l = 0; l < nlm; l++) c += (start[l] == t); cnt[t] = c; }
@@ -56,16 +56,16 @@ __global__ void k_tasks(KP p, int w0) {
     for (int l = 0; l < nlm; l++) if (start[l] == t) info[o++] = make_int4(l, tlen[l], obeg[l], fixed[l] != 0);
   }
   if (!p.planes) return;
-  // LiDAR plane factors grouped by frame, tasks of <= 32 planes
+  // LiDAR plane factors grouped by key = 2 * frame + ct (LidarPlaneNormFactor / CTLidarPlaneNormFactor), tasks of <= 32 planes
   __syncthreads();
   const int np = p.n_planes[w];
   const gf2_plane* pls = p.planes + (size_t)w * p.Pm;
-  if (t < F) { int c = 0; for (int q = 0; q < np; q++) c += (pls[q].frame == t); cnt[t] = c; }
+  if (t < 2 * F) { int c = 0; for (int q = 0; q < np; q++) c += (2 * pls[q].frame + (pls[q].ct ? 1 : 0) == t); cnt[t] = c; }
   __syncthreads();
   if (t == 0) {
     int o = 0, nt = 0;
     int32_t* tf = p.ptask_first + (size_t)w * kMaxPlaneTasks; int32_t* tc = p.ptask_cnt + (size_t)w * kMaxPlaneTasks; int32_t* ts = p.ptask_frame + (size_t)w * kMaxPlaneTasks;
-    for (int s = 0; s < F; s++) {
+    for (int s = 0; s < 2 * F; s++) {
       ofs[s] = o;
       for (int c = 0; c < cnt[s] && nt < kMaxPlaneTasks; c += 32) { tf[nt] = o + c; tc[nt] = min(32, cnt[s] - c); ts[nt] = s; nt++; }
       o += cnt[s];
@@ -73,7 +73,7 @@ __global__ void k_tasks(KP p, int w0) {
     p.nptasks[w] = nt;
   }
   __syncthreads();
-  if (t < F) { int32_t* perm = p.pperm + (size_t)w * p.Pm; int o = ofs[t]; for (int q = 0; q < np; q++) if (pls[q].frame == t) perm[o++] = q; }
+  if (t < 2 * F) { int32_t* perm = p.pperm + (size_t)w * p.Pm; int o = ofs[t]; for (int q = 0; q < np; q++) if (2 * pls[q].frame + (pls[q].ct ? 1 : 0) == t) perm[o++] = q; }
 }
 
 // ------------------------------------------------------------------------------------------------ k_linearize
@@ -529,10 +529,8 @@ __global__ void __launch_bounds__(kLinThreads, 2) k_linearize(KP p, int w0) {
     const int npt = p.nptasks[w];
     const gf2_plane* pls = p.planes + (size_t)w * p.Pm;
     const int32_t* pperm = p.pperm + (size_t)w * p.Pm;
-    for (int q = wid; q < npt; q += kLinWarps) {
-      const int f = p.ptask_frame[(size_t)w * kMaxPlaneTasks + q], cnt = p.ptask_cnt[(size_t)w * kMaxPlaneTasks + q], first = p.ptask_first[(size_t)w * kMaxPlaneTasks + q];
-      double Jp[6] = {0, 0, 0, 0, 0, 0}, r = 0.0;
-      if (lane < cnt) { r = plane_residual(pls[pperm[first + lane]], S.fr[f], p.lidar_sqrt_info, Jp); cost_acc += 0.5 * r * r; }
+    // [J | r]^T [J | r] of one 6-dim pose block summed over the warp's planes -> diagonal block (f, f) and gradient
+    auto accum_diag = [&](int f, const double* Jp, double r) {
       double m[32];
       {
         int c = 0;
@@ -554,6 +552,36 @@ __global__ void __launch_bounds__(kLinThreads, 2) k_linearize(KP p, int w0) {
         atomicAdd(&B[a * 6 + b], tot);
         if (a != b) atomicAdd(&B[b * 6 + a], tot);
       } else if (lane < 27) atomicAdd(&S.g[6 * f + lane - 21], tot);
+    };
+    const double* poseW = p.pose + (size_t)w * F * 7;
+    const double* palpha = p.plane_alpha ? p.plane_alpha + (size_t)w * p.Pm : nullptr;
+    for (int q = wid; q < npt; q += kLinWarps) {
+      const int key = p.ptask_frame[(size_t)w * kMaxPlaneTasks + q], cnt = p.ptask_cnt[(size_t)w * kMaxPlaneTasks + q], first = p.ptask_first[(size_t)w * kMaxPlaneTasks + q];
+      const int f = key >> 1;
+      if (!(key & 1)) {  // LidarPlaneNormFactor on the pose of frame f
+        double Jp[6] = {0, 0, 0, 0, 0, 0}, r = 0.0;
+        if (lane < cnt) { r = plane_residual(pls[pperm[first + lane]], S.fr[f], p.lidar_sqrt_info, Jp); cost_acc += 0.5 * r * r; }
+        accum_diag(f, Jp, r);
+      } else {           // CTLidarPlaneNormFactor between the poses of frames f (begin) and f + 1 (end): blocks (f,f), (f,f+1), (f+1,f+1)
+        double Jc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, r = 0.0;
+        if (lane < cnt) {
+          const int pi = pperm[first + lane];
+          r = ct_plane_residual(pls[pi], palpha ? palpha[pi] : 0.0, poseW + 7 * f, poseW + 7 * (f + 1), p.lidar_sqrt_info, Jc);
+          cost_acc += 0.5 * r * r;
+        }
+        accum_diag(f, Jc, r);
+        accum_diag(f + 1, Jc + 6, r);
+        double* B = &S.U[ublk(f, f + 1, F)];   // rows: frame f, columns: frame f + 1
+#pragma unroll
+        for (int pass = 0; pass < 2; pass++) {
+          double m[32];
+#pragma unroll
+          for (int e = 0; e < 32; e++) { const int idx = 32 * pass + e; m[e] = idx < 36 ? Jc[idx / 6] * Jc[6 + idx % 6] : 0.0; }
+          const double tot = butterfly32(m, lane);
+          const int idx = 32 * pass + lane;
+          if (idx < 36) atomicAdd(&B[idx], tot);
+        }
+      }
     }
     __syncthreads();
   }

@@ -75,7 +75,7 @@ def _heading_R(psi):
     return R
 
 
-def make_windows(n_windows, config_id=2, n_landmarks=1000, n_frames=11, wheel=False, n_planes=0, first_window=0,
+def make_windows(n_windows, config_id=2, n_landmarks=1000, n_frames=11, wheel=False, n_planes=0, ct_fraction=0.0, first_window=0,
                  sorted_landmarks=True, prior="anchor", speed=1.0, yaw_rate=0.2, frame_dt=0.1, imu_hz=200, wheel_hz=50,
                  pixel_noise=0.5, max_landmarks=None, max_obs=None, prior_weight=1.0, prior_stride=None):
     """Return a dict of window-major arrays for `n_windows` windows (W10-F1000 when n_landmarks = 1000).
@@ -128,6 +128,8 @@ def make_windows(n_windows, config_id=2, n_landmarks=1000, n_frames=11, wheel=Fa
     if n_planes:
         out["n_planes"] = np.full(n_windows, n_planes, np.int32)
         out["planes"] = np.zeros((n_windows, n_planes), abi.PLANE)
+        if ct_fraction > 0:   # CTLidarPlaneNormFactor records (ct == 1): alpha_time per plane
+            out["plane_alpha"] = np.zeros((n_windows, n_planes))
     P = prior_stride or abi.MAX_PRIOR_DIM
     out["prior_stride"] = P
     out["prior_rows"] = np.zeros(n_windows, np.int32); out["prior_nblocks"] = np.zeros(n_windows, np.int32)
@@ -229,6 +231,16 @@ def make_windows(n_windows, config_id=2, n_landmarks=1000, n_frames=11, wheel=Fa
                 dist = np.einsum("ij,ij->i", nrm[which], pw) + off[which]
                 pw = pw - dist[:, None] * nrm[which] + rng.normal(0, 0.02, (cnt, 1)) * nrm[which]
                 pb = np.einsum("ji,nj->ni", gtR[f], pw - gtp[f])
+                if ct_fraction > 0 and f < F - 1:
+                    # continuous-time factors: the point was measured at the pose interpolated between frames f and f + 1
+                    from scipy.spatial.transform import Rotation, Slerp
+                    is_ct = rng.random(cnt) < ct_fraction
+                    alpha = np.where(is_ct, rng.random(cnt), 0.0)
+                    sl = Slerp([0.0, 1.0], Rotation.from_matrix(np.stack([gtR[f], gtR[f + 1]])))
+                    Ri = sl(alpha).as_matrix(); ti = gtp[f][None] * (1 - alpha[:, None]) + gtp[f + 1][None] * alpha[:, None]
+                    pb_ct = np.einsum("nji,nj->ni", Ri, pw - ti)
+                    pb = np.where(is_ct[:, None], pb_ct, pb)
+                    pl["ct"][idx:idx + cnt] = is_ct.astype(np.int32); out["plane_alpha"][wi, idx:idx + cnt] = alpha
                 pl["p_body"][idx:idx + cnt] = pb; pl["normal"][idx:idx + cnt] = nrm[which]; pl["offset"][idx:idx + cnt] = off[which]
                 pl["weight"][idx:idx + cnt] = 1.0; pl["frame"][idx:idx + cnt] = f
                 idx += cnt

@@ -109,16 +109,21 @@ typedef struct gf2_wheel_preint {
   int32_t pad_;
 } gf2_wheel_preint;
 
-/* One LiDAR point-to-plane factor, LidarPlaneNormFactor (LIO/liw/lidarFactor.cpp:13-50), attached
- * to the window pose of `frame` (synthetic composition of BASELINE.json config 4).
- * residual = sqrt_info * weight * (normal . (R p_body + t) + offset). */
+/* One LiDAR point-to-plane factor attached to window poses (synthetic composition of BASELINE.json config 4).
+ * ct == 0: LidarPlaneNormFactor (LIO/liw/lidarFactor.cpp:13-50) on the pose of `frame`:
+ *          residual = sqrt_info * weight * (normal . (R p_body + t) + offset).
+ * ct == 1: CTLidarPlaneNormFactor (LIO/liw/lidarFactor.cpp:52-123, the factor of `icpmodel: CT_POINT_TO_PLANE`, every LIO config):
+ *          begin pose = window pose `frame`, end pose = window pose `frame + 1`, the point is transformed by the pose
+ *          interpolated at alpha_time (slerp / lerp); alpha_time comes from gf2_set_plane_alpha. The reference's rotation
+ *          Jacobians of this factor are first-order in the begin-end rotation difference; they are reproduced as written.
+ * p_body is expressed in the body frame (q_il / t_il of the factor's constructor already applied). */
 typedef struct gf2_plane {
   double p_body[3];
   double normal[3];
   double offset;
   double weight;
   int32_t frame;
-  int32_t pad_;
+  int32_t ct;
 } gf2_plane;
 
 /* Parameter-block kinds a marginalization prior can keep
@@ -298,6 +303,9 @@ double gf2_last_marginalize_ms(gf2_solver* h);
 
 /* LiDAR plane factors: n_planes [n], planes [n][max_planes] sorted or not by frame. */
 int gf2_set_planes(gf2_solver* h, int first, int n, const int32_t* n_planes, const gf2_plane* planes);
+/* alpha_time of the CTLidarPlaneNormFactor records (ct == 1): alpha [n][max_planes], entry q belongs to plane q of the window
+ * (entries of ct == 0 planes are ignored). Call after gf2_set_planes; without it alpha_time is 0 (the begin pose). */
+int gf2_set_plane_alpha(gf2_solver* h, int first, int n, const double* alpha);
 
 /* Solve windows [first, first+n) (ceres::Solve with DENSE_SCHUR + traditional DOGLEG semantics).
  * Synchronous. summaries may be NULL. */

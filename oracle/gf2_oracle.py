@@ -27,7 +27,7 @@ class Window(C.Structure):
                 ("prior_nblocks", C.c_int32), ("use_wheel", C.c_int32), ("prior_stride", C.c_int32), ("pad_", C.c_int32)] + [(n, C.c_void_p) for n in (
                     "para_pose", "para_speedbias", "ex_pose", "td", "ex_pose_wheel", "sxsysw", "td_wheel", "inv_depth",
                     "start_frame", "track_len", "fixed", "obs", "frame_td", "imu", "wheel", "prior_J0", "prior_r0",
-                    "prior_blocks", "planes")]
+                    "prior_blocks", "planes", "plane_alpha")]
 
 
 class Batch(C.Structure):
@@ -35,7 +35,7 @@ class Batch(C.Structure):
                [(n, C.c_void_p) for n in ("para_pose", "para_speedbias", "ex_pose", "td", "ex_pose_wheel", "sxsysw", "td_wheel",
                                           "inv_depth", "n_landmarks", "start_frame", "track_len", "fixed", "obs", "frame_td",
                                           "imu", "wheel", "prior_rows", "prior_J0", "prior_r0", "prior_nblocks", "prior_blocks",
-                                          "n_planes", "planes")]
+                                          "n_planes", "planes", "plane_alpha")]
 
 
 assert lib.gf2o_sizeof(4) == C.sizeof(Window) and lib.gf2o_sizeof(5) == C.sizeof(Batch)
@@ -54,7 +54,7 @@ def make_batch(w, keep):
     b.prior_stride = int(w["prior_J0"].shape[1]) if w.get("prior_J0") is not None else 96
     for name in ("para_pose", "para_speedbias", "ex_pose", "td", "ex_pose_wheel", "sxsysw", "td_wheel", "inv_depth",
                  "n_landmarks", "start_frame", "track_len", "fixed", "obs", "frame_td", "imu", "wheel", "prior_rows",
-                 "prior_J0", "prior_r0", "prior_nblocks", "prior_blocks", "n_planes", "planes"):
+                 "prior_J0", "prior_r0", "prior_nblocks", "prior_blocks", "n_planes", "planes", "plane_alpha"):
         a = w.get(name)
         if a is not None:
             a = np.ascontiguousarray(a); w[name] = a; keep.append(a)
@@ -102,7 +102,7 @@ def linearize_window(w, i, opts, max_dim=256):
 
 
 def factor_eval(kind, consts, params, extra=None, want_jac=True):
-    sizes = {0: (2, [7, 7, 7, 1, 1]), 1: (15, [7, 9, 7, 9]), 2: (6, [7, 7, 7, 1, 1, 1, 1]), 3: (1, [3, 4]), 4: (1, [3, 4, 3, 4]), 5: (1, [7])}[kind]
+    sizes = {0: (2, [7, 7, 7, 1, 1]), 1: (15, [7, 9, 7, 9]), 2: (6, [7, 7, 7, 1, 1, 1, 1]), 3: (1, [3, 4]), 4: (1, [3, 4, 3, 4]), 5: (1, [7]), 6: (1, [7, 7])}[kind]
     nres, blocks = sizes
     params = np.ascontiguousarray(params, dtype=np.float64)
     assert params.size == sum(blocks)

@@ -624,4 +624,19 @@ bool LidarPlanePoseFactor::Evaluate(double const* const* parameters, double* res
   return true;
 }
 
+CTLidarPlanePoseFactor::CTLidarPlanePoseFactor(const V3& kp, const V3& nv, double off, double alpha, double w) : inner(kp, nv, off, alpha, w) {
+  block_sizes = {7, 7}; num_residuals = 1;
+}
+bool CTLidarPlanePoseFactor::Evaluate(double const* const* parameters, double* residuals, double** jacobians) const {
+  const double* p[4] = {parameters[0], parameters[0] + 3, parameters[1], parameters[1] + 3};
+  double jtb[3], jqb[4], jte[3], jqe[4];
+  double* J[4] = {jtb, jqb, jte, jqe};
+  inner.Evaluate(p, residuals, jacobians ? J : nullptr);
+  if (jacobians) {
+    if (jacobians[0]) { for (int i = 0; i < 3; i++) { jacobians[0][i] = jtb[i]; jacobians[0][3 + i] = jqb[i]; } jacobians[0][6] = 0.0; }
+    if (jacobians[1]) { for (int i = 0; i < 3; i++) { jacobians[1][i] = jte[i]; jacobians[1][3 + i] = jqe[i]; } jacobians[1][6] = 0.0; }
+  }
+  return true;
+}
+
 }  // namespace gf2o

@@ -125,4 +125,12 @@ struct LidarPlanePoseFactor : CostFunction {
   bool Evaluate(double const* const* parameters, double* residuals, double** jacobians) const override;
 };
 
+// CTLidarPlaneNormFactor attached to two VINS 7-block poses (begin = window pose f, end = window pose f + 1): blocks {7, 7},
+// Jacobians 1x7 = [J_t | J_q(3) | 0] each.
+struct CTLidarPlanePoseFactor : CostFunction {
+  CTLidarPlaneNormFactor inner;
+  CTLidarPlanePoseFactor(const V3& kp, const V3& nv, double off, double alpha, double w);
+  bool Evaluate(double const* const* parameters, double* residuals, double** jacobians) const override;
+};
+
 }  // namespace gf2o

@@ -113,7 +113,7 @@ int gf2o_lio_build_factors(int n_voxels, const int16_t* keys, const int32_t* n_p
       { const double nn = std::sqrt(nv[0] * nv[0] + nv[1] * nv[1] + nv[2] * nv[2]); for (double& c : nv) c /= nn; }
       f.normal[0] = nv[0]; f.normal[1] = nv[1]; f.normal[2] = nv[2];
       f.offset = -(nv[0] * nbs[i].x + nv[1] * nbs[i].y + nv[2] * nbs[i].z);
-      f.weight = weight; f.frame = k;
+      f.weight = weight; f.frame = k; f.ct = (o->icp_model == GF2_ICP_CT_POINT_TO_PLANE) ? 1 : 0;
       if (o->icp_model == GF2_ICP_CT_POINT_TO_PLANE) { f.p_body[0] = kp.raw_point[0]; f.p_body[1] = kp.raw_point[1]; f.p_body[2] = kp.raw_point[2]; }
       else {  // point_end = R^-1 kp.point - R^-1 translation
         const double a[3] = {R[0] * pt.x + R[3] * pt.y + R[6] * pt.z, R[1] * pt.x + R[4] * pt.y + R[7] * pt.z, R[2] * pt.x + R[5] * pt.y + R[8] * pt.z};

@@ -43,6 +43,7 @@ typedef struct gf2o_window {
   const double* prior_r0;
   const gf2_prior_block* prior_blocks;
   const gf2_plane* planes;
+  const double* plane_alpha;     /* [n_planes] alpha_time of the ct == 1 planes, or NULL */
 } gf2o_window;
 
 }  // extern "C"
@@ -129,6 +130,13 @@ void buildWindow(const gf2o_window& w, const gf2_solve_opts& o, BuiltWindow& bw)
   // LiDAR planes (BASELINE.json config 4 composition)
   for (int k = 0; k < w.n_planes; k++) {
     const gf2_plane& pl = w.planes[k];
+    if (pl.ct) {  // CTLidarPlaneNormFactor between the window poses frame (begin) and frame + 1 (end)
+      CTLidarPlaneNormFactor::sqrt_info = o.lidar_sqrt_info;
+      bw.factors.emplace_back(new CTLidarPlanePoseFactor(v3(pl.p_body[0], pl.p_body[1], pl.p_body[2]), v3(pl.normal[0], pl.normal[1], pl.normal[2]), pl.offset,
+                                                         w.plane_alpha ? w.plane_alpha[k] : 0.0, pl.weight));
+      P.AddResidualBlock(bw.factors.back().get(), false, {id_pose[pl.frame], id_pose[pl.frame + 1]});
+      continue;
+    }
     bw.factors.emplace_back(new LidarPlanePoseFactor(v3(pl.p_body[0], pl.p_body[1], pl.p_body[2]), v3(pl.normal[0], pl.normal[1], pl.normal[2]), pl.offset, pl.weight));
     P.AddResidualBlock(bw.factors.back().get(), false, {id_pose[pl.frame]});
   }
@@ -208,6 +216,7 @@ typedef struct gf2o_batch {
   const gf2_wheel_preint* wheel;
   const int32_t* prior_rows; const double *prior_J0, *prior_r0; const int32_t* prior_nblocks; const gf2_prior_block* prior_blocks;
   const int32_t* n_planes; const gf2_plane* planes;
+  const double* plane_alpha;   /* [n_windows][max_planes] or NULL */
 } gf2o_batch;
 
 static void windowOf(const gf2o_batch& b, int i, gf2o_window& w) {
@@ -229,7 +238,7 @@ static void windowOf(const gf2o_batch& b, int i, gf2o_window& w) {
     w.prior_stride = b.prior_stride; w.prior_J0 = b.prior_J0 + (size_t)i * b.prior_stride * b.prior_stride; w.prior_r0 = b.prior_r0 + (size_t)i * b.prior_stride;
     w.prior_blocks = b.prior_blocks + (size_t)i * (2 * F + 8);
   }
-  if (b.n_planes && b.max_planes > 0) { w.n_planes = b.n_planes[i]; w.planes = b.planes + (size_t)i * b.max_planes; }
+  if (b.n_planes && b.max_planes > 0) { w.n_planes = b.n_planes[i]; w.planes = b.planes + (size_t)i * b.max_planes; w.plane_alpha = b.plane_alpha ? b.plane_alpha + (size_t)i * b.max_planes : nullptr; }
 }
 
 int gf2o_batch_window(const gf2o_batch* b, int i, gf2o_window* w) { windowOf(*b, i, *w); return 0; }
@@ -276,6 +285,7 @@ int gf2o_factor_eval(int kind, const void* consts, const double* extra, const do
     case 3: LidarPlaneNormFactor::sqrt_info = c[8]; f.reset(new LidarPlaneNormFactor(v3(c[0], c[1], c[2]), v3(c[3], c[4], c[5]), c[6], c[7])); break;
     case 4: CTLidarPlaneNormFactor::sqrt_info = c[9]; f.reset(new CTLidarPlaneNormFactor(v3(c[0], c[1], c[2]), v3(c[3], c[4], c[5]), c[6], c[7], c[8])); break;
     case 5: LidarPlaneNormFactor::sqrt_info = c[8]; f.reset(new LidarPlanePoseFactor(v3(c[0], c[1], c[2]), v3(c[3], c[4], c[5]), c[6], c[7])); break;
+    case 6: CTLidarPlaneNormFactor::sqrt_info = c[9]; f.reset(new CTLidarPlanePoseFactor(v3(c[0], c[1], c[2]), v3(c[3], c[4], c[5]), c[6], c[7], c[8])); break;
     default: return -1;
   }
   std::vector<const double*> pp; std::vector<double*> jj; size_t po = 0, jo = 0;

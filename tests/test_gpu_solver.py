@@ -342,3 +342,38 @@ def test_prior_with_free_wheel_extrinsic_chain(gf2, oracle, synth):
     moved = np.abs(w2["ex_pose_wheel"] - start).max()
     assert np.abs(got["ex_pose_wheel"] - w2["ex_pose_wheel"]).max() <= 1e-3 * moved + 1e-9
     s.close()
+
+
+@pytest.mark.parametrize("nl,planes,ct_fraction", [(300, 1000, 0.5), (1000, 5000, 1.0), (200, 333, 0.3)])
+def test_ct_lidar_plane_factors_match_oracle(gf2, oracle, synth, nl, planes, ct_fraction):
+    """CTLidarPlaneNormFactor (LIO/liw/lidarFactor.cpp:52-123, the factor of icpmodel: CT_POINT_TO_PLANE) in the sweep: begin / end pose =
+    window poses f / f + 1, alpha_time per plane; mixed with LidarPlaneNormFactor records in the same window."""
+    n = 2
+    w = synth.make_windows(n, config_id=4, n_landmarks=nl, wheel=True, n_planes=planes, ct_fraction=ct_fraction)
+    assert 0 < int(w["planes"]["ct"].sum()) and (w["planes"]["frame"][w["planes"]["ct"] == 1] < 10).all()
+    oracle.imu_preintegrate(w); oracle.wheel_preintegrate(w)
+    s = _solver4(gf2, w, n)
+    s.upload(w, preintegrate="records")
+    opts = gf2.abi.default_opts()
+    S, g, cost = s.linearize(opts, n)
+    for i in range(n):
+        So, go, co, _, _ = oracle.linearize_window(w, i, opts)
+        assert abs(cost[i] - co) <= 1e-12 * co
+        assert np.abs(S[i] - So).max() <= 1e-10 * np.abs(So).max()
+        assert np.abs(g[i] - go).max() <= 1e-10 * np.abs(go).max()
+    s.upload(w, preintegrate="records")
+    summ = s.solve(opts, n)
+    got = s.get_states(n)
+    wo = _copy(w)
+    so = oracle.solve_batch(wo, opts, n_threads=2)
+    assert (summ["iterations"] == so["iterations"]).all() and (summ["termination"] == so["termination"]).all()
+    assert (summ["successful_steps"] == so["successful_steps"]).all()
+    assert (np.abs(summ["final_cost"] - so["final_cost"]) <= 1e-6 * so["final_cost"]).all()
+    scale = np.abs(wo["para_pose"][..., :3]).max()
+    assert np.abs(got["para_pose"][..., :3] - wo["para_pose"][..., :3]).max() <= 1e-4 * scale
+    assert np.abs(got["para_pose"][..., 3:] - wo["para_pose"][..., 3:]).max() <= 1e-4
+    # a CT plane on the last frame has no end pose
+    bad = _copy(w); bad["planes"]["frame"][0, 0] = 10; bad["planes"]["ct"][0, 0] = 1
+    with pytest.raises(gf2.Gf2Error, match="needs the end pose"):
+        s.set_planes(bad)
+    s.close()

@@ -121,3 +121,35 @@ def test_sym_eigen_matches_numpy(oracle):
     oracle.lib.gf2o_sym_eigen(40, oracle._p(np.ascontiguousarray(A)), oracle._p(ev), oracle._p(V))
     assert np.allclose(ev, np.linalg.eigvalsh(A), rtol=1e-10, atol=1e-10 * ev.max())
     assert np.abs(V @ np.diag(ev) @ V.T - A).max() < 1e-9 * np.abs(A).max()
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_ct_lidar_plane_factor_translation_exact_rotation_first_order(oracle, seed):
+    """CTLidarPlaneNormFactor (LIO/liw/lidarFactor.cpp:58-123). The reference ships no test for it (test_analytic_factor.cpp covers only
+    the non-CT factor). Its translation Jacobians are exact; its rotation Jacobians are first order in the begin-end rotation difference
+    (restated verbatim): their error against finite differences is O(|delta|) (1e-6 at 1e-4 rad, < 1 % at 0.05 rad), which this test pins so that a transcription error would show."""
+    rng = np.random.default_rng(seed)
+    nv = rng.normal(size=3); nv /= np.linalg.norm(nv)
+    alpha = rng.uniform(0.1, 0.9)
+    consts = np.concatenate([rng.normal(size=3), nv, [0.3, alpha, 0.8, 31.6]])
+    tb = rng.normal(size=3); qb = random_unit_quat(rng)
+    for delta, tol in ((1e-4, 1e-6), (0.05, 1e-2)):
+        te = tb + rng.normal(size=3) * 0.1; qe = plus(qb, rng.normal(size=3) * delta, "quat4")
+        blocks = [tb, qb, te, qe]; kinds = ["vec", "quat4", "vec", "quat4"]
+        res, J = oracle.factor_eval(4, consts, np.concatenate(blocks))
+        Jn = numeric_jacobians(lambda bl: oracle.factor_eval(4, consts, np.concatenate(bl), want_jac=False)[0], blocks, kinds)
+        for i in (0, 2):
+            assert np.abs(J[i] - Jn[i]).max() < 1e-8 * max(1.0, np.abs(Jn[i]).max())
+        for i in (1, 3):
+            assert np.abs(J[i][:, :3] - Jn[i]).max() < tol * max(1.0, np.abs(Jn[i]).max()) and J[i][0, 3] == 0.0
+        # the two-pose wrapper used in the window composition carries the same numbers in 7-blocks
+        r7, J7 = oracle.factor_eval(6, consts, np.concatenate([tb, qb, te, qe]))
+        assert r7[0] == res[0]
+        assert np.array_equal(J7[0][0, :3], J[0][0]) and np.array_equal(J7[0][0, 3:6], J[1][0, :3]) and J7[0][0, 6] == 0.0
+        assert np.array_equal(J7[1][0, :3], J[2][0]) and np.array_equal(J7[1][0, 3:6], J[3][0, :3]) and J7[1][0, 6] == 0.0
+        # alpha = 0 / 1 reduce to the begin / end pose
+    for a, (t, q) in ((0.0, (tb, qb)), (1.0, (te, qe))):
+        c = consts.copy(); c[7] = a
+        r_ct = oracle.factor_eval(4, c, np.concatenate([tb, qb, te, qe]), want_jac=False)[0]
+        r_pl = oracle.factor_eval(3, np.concatenate([c[:7], [c[8], c[9]]]), np.concatenate([t, q]), want_jac=False)[0]
+        assert abs(r_ct[0] - r_pl[0]) < 1e-12 * max(1.0, abs(r_pl[0]))
