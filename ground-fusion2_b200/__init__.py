@@ -46,6 +46,7 @@ ABI_SYMBOLS = [
     "gf2_tracker_track_image", "gf2_tracker_detect", "gf2_tracker_min_eigen_map", "gf2_detect_select",
     "gf2_tracker_equalize", "gf2_tracker_set_equalize", "gf2_tracker_get_image",
     "gf2_lio_create", "gf2_lio_destroy", "gf2_lio_set_map", "gf2_lio_build_factors", "gf2_lio_last_timing",
+    "gf2_lio_add_points", "gf2_lio_map_size", "gf2_lio_get_map",
 ]
 
 
@@ -422,6 +423,19 @@ class Lio:
         assert points.shape[1] == self.cfg.max_points_per_voxel
         _check(lib().gf2_lio_set_map(self.h, len(keys), _p(keys), _p(n_points), _p(points)))
 
+    def add_points(self, points, size_voxel_map=0.2, min_distance_points=0.05, min_num_points=0):
+        """lidarodom::map_incremental: addPointToMap for the points [n, 3] of a scan in order, on the device-resident map."""
+        pts = np.ascontiguousarray(points, np.float64)
+        _check(lib().gf2_lio_add_points(self.h, len(pts), _p(pts), C.c_double(size_voxel_map), C.c_double(min_distance_points), int(min_num_points)))
+
+    def get_map(self):
+        """Snapshot of the device map (keys [n, 3] int16 ascending, n_points [n], points [n, M, 3])."""
+        n = C.c_int32(0)
+        _check(lib().gf2_lio_map_size(self.h, C.byref(n)))
+        keys = np.zeros((n.value, 3), np.int16); npts = np.zeros(n.value, np.int32); pts = np.zeros((n.value, self.cfg.max_points_per_voxel, 3))
+        _check(lib().gf2_lio_get_map(self.h, _p(keys), _p(npts), _p(pts)))
+        return keys, npts, pts
+
     def build_factors(self, keypoints, opts, want_neighbors=False):
         """Returns (factors [n] abi.PLANE, alpha [n], neighbors or None, n_neighbors or None)."""
         kp = np.ascontiguousarray(keypoints, abi.LIO_KEYPOINT)
@@ -435,4 +449,4 @@ class Lio:
     def last_timing(self):
         t = np.zeros(8)
         _check(lib().gf2_lio_last_timing(self.h, _p(t)))
-        return {"total_ms": t[0], "kernel_ms": t[1], "voxels": int(t[2]), "keypoints": int(t[3])}
+        return {"total_ms": t[0], "kernel_ms": t[1], "voxels": int(t[2]), "keypoints": int(t[3]), "new_voxels": int(t[4])}

@@ -11,6 +11,7 @@
 // The residual records are compacted in keypoint order with the max_num_residuals cap on the host (integer bookkeeping, like the
 // reference's sequential loop). The voxel map itself (addPointToMap) stays with the caller; gf2_lio_set_map takes a snapshot.
 #include <cuda_runtime.h>
+#include <cub/cub.cuh>
 #include <math.h>
 #include <stdint.h>
 #include <string.h>
@@ -177,6 +178,60 @@ __global__ void __launch_bounds__(32 * kLioWarps) k_lio_factors(LioArgs a) {
   a.cnt[k] = c;
 }
 
+// ---- map maintenance (addPointToMap, :1167-1213)
+__global__ void k_lio_point_keys(int n, const double* __restrict__ pts, double size, unsigned long long* __restrict__ keys, int32_t* __restrict__ idx) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int kx = (short)(int)(pts[3 * i] / size), ky = (short)(int)(pts[3 * i + 1] / size), kz = (short)(int)(pts[3 * i + 2] / size);
+  keys[i] = lio_key(kx, ky, kz); idx[i] = i;
+}
+
+// sorted scan positions; the thread at the head of a run of equal keys inserts the run's points in scan order
+__global__ void k_lio_insert(int n, const unsigned long long* __restrict__ skeys, const int32_t* __restrict__ sidx, const double* __restrict__ pts, int n_voxels,
+                             const unsigned long long* __restrict__ tkeys, const int32_t* __restrict__ tvox, int max_voxels, int M, double size, double min_dist,
+                             int min_num_points, int32_t* __restrict__ n_points, double* __restrict__ vpoints, unsigned long long* __restrict__ new_keys,
+                             int32_t* __restrict__ n_new /* [0]: new voxels, [1]: overflow flag */) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned long long key = skeys[i];
+  if (i > 0 && skeys[i - 1] == key) return;   // not a run head
+  int slot = -1;
+  { int lo = 0, hi = n_voxels;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (tkeys[mid] < key) lo = mid + 1; else hi = mid; }
+    if (lo < n_voxels && tkeys[lo] == key) slot = tvox[lo]; }
+  int count = slot >= 0 ? n_points[slot] : 0;
+  for (int j = i; j < n && skeys[j] == key; j++) {
+    const double* p = pts + 3 * (size_t)sidx[j];
+    if (slot < 0) {
+      if (min_num_points > 0) return;          // voxel missing and new voxels are not created in this mode: the whole run is dropped
+      const int k = atomicAdd(&n_new[0], 1);
+      if (n_voxels + k >= max_voxels) { n_new[1] = 1; return; }
+      slot = n_voxels + k; new_keys[k] = key; count = 0;
+      double* q = vpoints + ((size_t)slot * M) * 3;
+      q[0] = p[0]; q[1] = p[1]; q[2] = p[2]; count = 1;   // voxelBlock block(max); block.AddPoint(point)
+      continue;
+    }
+    if (count >= M) break;                      // IsFull: nothing else of this run can enter
+    double dmin = 10.0 * size * size;
+    const double* q = vpoints + ((size_t)slot * M) * 3;
+    for (int c = 0; c < count; c++) {
+      const double dx = q[3 * c] - p[0], dy = q[3 * c + 1] - p[1], dz = q[3 * c + 2] - p[2];
+      const double d2 = dx * dx + dy * dy + dz * dz;
+      if (d2 < dmin) dmin = d2;
+    }
+    if (dmin > min_dist * min_dist && (min_num_points <= 0 || count >= min_num_points)) {
+      double* w = vpoints + ((size_t)slot * M + count) * 3;
+      w[0] = p[0]; w[1] = p[1]; w[2] = p[2]; count++;
+    }
+  }
+  if (slot >= 0) n_points[slot] = count;
+}
+
+__global__ void k_lio_append_table(int n_old, int n_new, const unsigned long long* __restrict__ new_keys, unsigned long long* __restrict__ tkeys, int32_t* __restrict__ tvox) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_new) { tkeys[n_old + i] = new_keys[i]; tvox[n_old + i] = n_old + i; }
+}
+
 }  // namespace gf2
 
 using namespace gf2;
@@ -187,6 +242,9 @@ struct gf2_lio {
   unsigned long long* d_keys; int32_t *d_vox, *d_npts; double* d_points;
   gf2_lio_keypoint* d_kp; int32_t* d_cnt; LioRec* d_rec; double* d_nb; int32_t* d_nnb;
   int n_voxels = 0;
+  // map maintenance scratch (allocated by the first gf2_lio_add_points)
+  int scan_cap = 0; double* d_scan = nullptr; unsigned long long *d_pk = nullptr, *d_pk2 = nullptr, *d_newk = nullptr, *d_tk2 = nullptr;
+  int32_t *d_pi = nullptr, *d_pi2 = nullptr, *d_tv2 = nullptr, *d_nnew = nullptr; void* d_tmp = nullptr; size_t tmp_bytes = 0;
   std::vector<void*> allocs;
   std::vector<int32_t> h_cnt; std::vector<LioRec> h_rec;
   cudaEvent_t ev[3];
@@ -248,6 +306,83 @@ int gf2_lio_set_map(gf2_lio* h, int n_voxels, const int16_t* keys, const int32_t
   }
   GF2L_CUDA(cudaStreamSynchronize(h->stream));   // sk / sv are locals
   h->n_voxels = n_voxels;
+  return GF2_OK;
+}
+
+int gf2_lio_add_points(gf2_lio* h, int n, const double* points, double size_voxel_map, double min_distance_points, int min_num_points) {
+  if (!h || (n > 0 && !points)) return gf2::fail(GF2_ERR_INVALID, "null argument");
+  if (n < 0 || !(size_voxel_map > 0.0) || min_distance_points < 0.0) return gf2::fail(GF2_ERR_INVALID, "bad argument");
+  if (n == 0) return GF2_OK;
+  cudaSetDevice(h->cfg.device);
+  const int V = h->cfg.max_voxels;
+  if (n > h->scan_cap) {   // scratch grows to the largest scan seen
+    auto alloc = [&](void** p, size_t bytes) { if (cudaMalloc(p, bytes) != cudaSuccess) return false; h->allocs.push_back(*p); return true; };
+    const size_t cap = (size_t)n + n / 4 + 1024;
+    size_t t1 = 0, t2 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, t1, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (int32_t*)nullptr, (int32_t*)nullptr, (int)cap, 0, 48, h->stream);
+    cub::DeviceRadixSort::SortPairs(nullptr, t2, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (int32_t*)nullptr, (int32_t*)nullptr, V, 0, 48, h->stream);
+    const size_t tb = t1 > t2 ? t1 : t2;
+    bool ok = alloc((void**)&h->d_scan, sizeof(double) * 3 * cap) && alloc((void**)&h->d_pk, 8 * cap) && alloc((void**)&h->d_pk2, 8 * cap) && alloc((void**)&h->d_pi, 4 * cap) && alloc((void**)&h->d_pi2, 4 * cap) &&
+              alloc(&h->d_tmp, tb);
+    if (ok && !h->d_newk) ok = alloc((void**)&h->d_newk, 8 * (size_t)V) && alloc((void**)&h->d_tk2, 8 * (size_t)V) && alloc((void**)&h->d_tv2, 4 * (size_t)V) && alloc((void**)&h->d_nnew, 8);
+    if (!ok) { h->scan_cap = 0; return gf2::fail(GF2_ERR_CUDA, "LIO map scratch allocation failed"); }
+    h->scan_cap = (int)cap; h->tmp_bytes = tb;
+  }
+  cudaEventRecord(h->ev[0], h->stream);
+  GF2L_CUDA(cudaMemcpyAsync(h->d_scan, points, sizeof(double) * 3 * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+  GF2L_CUDA(cudaMemsetAsync(h->d_nnew, 0, 8, h->stream));
+  cudaEventRecord(h->ev[1], h->stream);
+  k_lio_point_keys<<<(n + 255) / 256, 256, 0, h->stream>>>(n, h->d_scan, size_voxel_map, h->d_pk, h->d_pi);
+  size_t tb = h->tmp_bytes;
+  GF2L_CUDA(cub::DeviceRadixSort::SortPairs(h->d_tmp, tb, h->d_pk, h->d_pk2, h->d_pi, h->d_pi2, n, 0, 48, h->stream));   // LSD radix sort: stable, scan order kept inside a voxel
+  k_lio_insert<<<(n + 127) / 128, 128, 0, h->stream>>>(n, h->d_pk2, h->d_pi2, h->d_scan, h->n_voxels, h->d_keys, h->d_vox, V, h->cfg.max_points_per_voxel, size_voxel_map,
+                                                       min_distance_points, min_num_points, h->d_npts, h->d_points, h->d_newk, h->d_nnew);
+  GF2L_CUDA(cudaGetLastError());
+  int32_t nn[2] = {0, 0};
+  GF2L_CUDA(cudaMemcpyAsync(nn, h->d_nnew, 8, cudaMemcpyDeviceToHost, h->stream));
+  GF2L_CUDA(cudaStreamSynchronize(h->stream));
+  if (nn[1] || h->n_voxels + nn[0] > V) return gf2::fail(GF2_ERR_INVALID, "voxel map capacity %d exceeded (%d voxels + %d new)", V, h->n_voxels, nn[0]);
+  if (nn[0] > 0) {   // the new voxels join the sorted key table: append, then sort the table again (48-bit keys)
+    k_lio_append_table<<<(nn[0] + 255) / 256, 256, 0, h->stream>>>(h->n_voxels, nn[0], h->d_newk, h->d_keys, h->d_vox);
+    const int total = h->n_voxels + nn[0];
+    tb = h->tmp_bytes;
+    GF2L_CUDA(cub::DeviceRadixSort::SortPairs(h->d_tmp, tb, h->d_keys, h->d_tk2, h->d_vox, h->d_tv2, total, 0, 48, h->stream));
+    GF2L_CUDA(cudaMemcpyAsync(h->d_keys, h->d_tk2, 8 * (size_t)total, cudaMemcpyDeviceToDevice, h->stream));
+    GF2L_CUDA(cudaMemcpyAsync(h->d_vox, h->d_tv2, 4 * (size_t)total, cudaMemcpyDeviceToDevice, h->stream));
+    h->n_voxels = total;
+  }
+  cudaEventRecord(h->ev[2], h->stream);
+  GF2L_CUDA(cudaStreamSynchronize(h->stream));
+  float ms; memset(h->timing, 0, sizeof(h->timing));
+  cudaEventElapsedTime(&ms, h->ev[0], h->ev[2]); h->timing[0] = ms;
+  cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]); h->timing[1] = ms;
+  h->timing[2] = h->n_voxels; h->timing[3] = n; h->timing[4] = nn[0];
+  return GF2_OK;
+}
+
+int gf2_lio_map_size(gf2_lio* h, int32_t* n_voxels) {
+  if (!h || !n_voxels) return gf2::fail(GF2_ERR_INVALID, "null argument");
+  *n_voxels = h->n_voxels;
+  return GF2_OK;
+}
+
+int gf2_lio_get_map(gf2_lio* h, int16_t* keys, int32_t* n_points, double* points) {
+  if (!h || !keys || !n_points || !points) return gf2::fail(GF2_ERR_INVALID, "null argument");
+  const int n = h->n_voxels, M = h->cfg.max_points_per_voxel;
+  if (n == 0) return GF2_OK;
+  cudaSetDevice(h->cfg.device);
+  std::vector<unsigned long long> tk(n); std::vector<int32_t> tv(n), np(n); std::vector<double> pts((size_t)n * M * 3);
+  GF2L_CUDA(cudaMemcpyAsync(tk.data(), h->d_keys, 8 * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+  GF2L_CUDA(cudaMemcpyAsync(tv.data(), h->d_vox, 4 * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+  GF2L_CUDA(cudaMemcpyAsync(np.data(), h->d_npts, 4 * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+  GF2L_CUDA(cudaMemcpyAsync(pts.data(), h->d_points, sizeof(double) * 3 * (size_t)n * M, cudaMemcpyDeviceToHost, h->stream));
+  GF2L_CUDA(cudaStreamSynchronize(h->stream));
+  for (int i = 0; i < n; i++) {   // ascending key order
+    const int s = tv[i];
+    keys[3 * i] = (int16_t)((int)((tk[i] >> 32) & 0xffff) - 32768); keys[3 * i + 1] = (int16_t)((int)((tk[i] >> 16) & 0xffff) - 32768); keys[3 * i + 2] = (int16_t)((int)(tk[i] & 0xffff) - 32768);
+    n_points[i] = np[s];
+    memcpy(points + (size_t)i * M * 3, pts.data() + (size_t)s * M * 3, sizeof(double) * 3 * M);
+  }
   return GF2_OK;
 }
 

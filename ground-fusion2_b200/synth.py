@@ -305,6 +305,55 @@ def image_pair(seed=0, w=640, h=480, shift=(3.3, -2.1), n_pts=300):
     return prev, cur, pts
 
 
+def _lio_surface(rng, n):
+    """Points on a room: ground, four walls, a box top."""
+    which = rng.integers(0, 6, n)
+    u, v = rng.uniform(-1, 1, n), rng.uniform(-1, 1, n)
+    p = np.zeros((n, 3))
+    for k in range(n):
+        w_ = which[k]
+        if w_ == 0: p[k] = (6 * u[k], 5 * v[k], 0.0)                       # ground
+        elif w_ == 1: p[k] = (6.0, 5 * u[k], 1.5 + 1.5 * v[k])             # walls
+        elif w_ == 2: p[k] = (-6.0, 5 * u[k], 1.5 + 1.5 * v[k])
+        elif w_ == 3: p[k] = (6 * u[k], 5.0, 1.5 + 1.5 * v[k])
+        elif w_ == 4: p[k] = (6 * u[k], -5.0, 1.5 + 1.5 * v[k])
+        else: p[k] = (2.0 + 0.5 * u[k], 1.0 + 0.5 * v[k], 1.0)             # box top
+    return p
+
+
+def lio_scan(seed, n, noise=0.01):
+    """n world points of one synthetic scan (surface samples + noise), in scan order."""
+    rng = np.random.default_rng(9000 + seed)
+    return _lio_surface(rng, n) + rng.normal(0, noise, (n, 3))
+
+
+def voxel_map_insert(vox, pts, size_voxel_map=0.2, max_points_per_voxel=20, min_distance_points=0.05, min_num_points=0):
+    """lidarodom::addPointToMap (LIO/liw/lio/lidarodom.cpp:1167-1213) for the points of a scan in order; vox: dict voxel key -> list of
+    points (insertion order). Used to generate map snapshots and as the sequential statement the device insertion is compared with."""
+    for p in pts:
+        key = tuple(int(c / size_voxel_map) for c in p)    # short(point / voxel_size): truncation toward zero
+        blk = vox.get(key)
+        if blk is None:
+            if min_num_points <= 0:
+                vox[key] = [p.copy()]
+        elif len(blk) < max_points_per_voxel:
+            d2 = min(10 * size_voxel_map * size_voxel_map, min(float(((q - p) ** 2).sum()) for q in blk))
+            if d2 > min_distance_points * min_distance_points and (min_num_points <= 0 or len(blk) >= min_num_points):
+                blk.append(p.copy())
+    return vox
+
+
+def voxel_map_arrays(vox, max_points_per_voxel=20, order=None):
+    """(keys [n, 3] int16, n_points [n], points [n, M, 3]) of a voxel dict, in the given key order (default: dict order)."""
+    order = list(vox) if order is None else order
+    keys = np.array(order, np.int16).reshape(-1, 3)
+    n_points = np.array([len(vox[k]) for k in order], np.int32)
+    points = np.zeros((len(order), max_points_per_voxel, 3))
+    for j, k in enumerate(order):
+        points[j, :n_points[j]] = np.array(vox[k])
+    return keys, n_points, points
+
+
 def lio_scene(seed=0, n_map_points=60000, n_keypoints=3000, size_voxel_map=0.2, max_points_per_voxel=20, min_distance_points=0.05):
     """Synthetic LIO scene: a room (ground, four walls, a box) sampled with 1 cm noise and inserted into a voxel map with the rules
     of lidarodom::addPointToMap (LIO/liw/lio/lidarodom.cpp:1167-1213: at most max_points_per_voxel per voxel, new points at least
@@ -312,39 +361,12 @@ def lio_scene(seed=0, n_map_points=60000, n_keypoints=3000, size_voxel_map=0.2, 
     (rejected by the point-to-plane gate) and some in unmapped space (too few neighbours). Returns a dict with the map snapshot
     (keys, n_points, points), the keypoints (abi.LIO_KEYPOINT) and the frame state used to express them."""
     rng = np.random.default_rng(4000 + seed)
-
-    def surface(n):
-        which = rng.integers(0, 6, n)
-        u, v = rng.uniform(-1, 1, n), rng.uniform(-1, 1, n)
-        p = np.zeros((n, 3))
-        for k in range(n):
-            w_ = which[k]
-            if w_ == 0: p[k] = (6 * u[k], 5 * v[k], 0.0)                       # ground
-            elif w_ == 1: p[k] = (6.0, 5 * u[k], 1.5 + 1.5 * v[k])             # walls
-            elif w_ == 2: p[k] = (-6.0, 5 * u[k], 1.5 + 1.5 * v[k])
-            elif w_ == 3: p[k] = (6 * u[k], 5.0, 1.5 + 1.5 * v[k])
-            elif w_ == 4: p[k] = (6 * u[k], -5.0, 1.5 + 1.5 * v[k])
-            else: p[k] = (2.0 + 0.5 * u[k], 1.0 + 0.5 * v[k], 1.0)             # box top
-        return p
-
+    surface = lambda n: _lio_surface(rng, n)
     pts = surface(n_map_points) + rng.normal(0, 0.01, (n_map_points, 3))
-    vox = {}
-    order = []
-    for p in pts:   # addPointToMap with min_num_points = 0
-        key = tuple(int(c / size_voxel_map) for c in p)    # short(point / voxel_size): truncation toward zero
-        blk = vox.get(key)
-        if blk is None:
-            vox[key] = [p]; order.append(key)
-        elif len(blk) < max_points_per_voxel:
-            d2 = min(10 * size_voxel_map * size_voxel_map, min(float(((q - p) ** 2).sum()) for q in blk))
-            if d2 > min_distance_points * min_distance_points:
-                blk.append(p)
+    vox = voxel_map_insert({}, pts, size_voxel_map, max_points_per_voxel, min_distance_points, 0)
+    order = list(vox)
     perm = rng.permutation(len(order))     # the hash map has no meaningful order: hand the voxels over shuffled
-    keys = np.array([order[i] for i in perm], np.int16)
-    n_points = np.array([len(vox[order[i]]) for i in perm], np.int32)
-    points = np.zeros((len(order), max_points_per_voxel, 3))
-    for j, i in enumerate(perm):
-        points[j, :n_points[j]] = np.array(vox[order[i]])
+    keys, n_points, points = voxel_map_arrays(vox, max_points_per_voxel, [order[i] for i in perm])
     # frame state: the sensor 1.2 m above the ground, slightly rotated
     yaw = 0.3 + 0.1 * seed
     q = np.array([0.0, 0.0, np.sin(yaw / 2), np.cos(yaw / 2)])

@@ -479,6 +479,18 @@ void gf2_lio_destroy(gf2_lio* h);
 /* Snapshot of the voxelHashMap (tsl::robin_map<voxel, voxelBlock>, cloudMap.hpp:34-83): n_voxels entries in any order,
  * keys [n][3] (short x, y, z), n_points [n], points [n][max_points_per_voxel][3] in insertion order. Duplicate keys are rejected. */
 int gf2_lio_set_map(gf2_lio* h, int n_voxels, const int16_t* keys, const int32_t* n_points, const double* points);
+/* Device-resident map maintenance: lidarodom::addPointToMap (LIO/liw/lio/lidarodom.cpp:1167-1213) for the n points of a scan IN ORDER
+ * (map_incremental, :1226-1237): a point goes into the voxel short(p / size_voxel_map); an existing voxel takes it if it is not
+ * full (max_points_per_voxel), the point is farther than min_distance_points from every point already there and the voxel holds at
+ * least min_num_points points (when min_num_points > 0); a missing voxel is created only when min_num_points <= 0. Points interact
+ * only inside a voxel, so the scan is sorted by voxel key (stable) and one thread walks each voxel's points in scan order: the
+ * result equals the sequential loop. The map then stays on the device for gf2_lio_build_factors (no snapshot upload). */
+int gf2_lio_add_points(gf2_lio* h, int n, const double* points /* [n][3] */, double size_voxel_map, double min_distance_points,
+                       int min_num_points);
+/* Number of voxels held / snapshot of the device map in the layout of gf2_lio_set_map (voxels in ascending key order). */
+int gf2_lio_map_size(gf2_lio* h, int32_t* n_voxels);
+int gf2_lio_get_map(gf2_lio* h, int16_t* keys, int32_t* n_points, double* points);
+
 /* out_factors [max(max_num_residuals, 1)] (the reference tests the cap after pushing): p_body = raw_point (CT) or point_end (POINT_TO_PLANE), normal = nvec, offset =
  * -nvec . neighbour, weight, frame = index of the keypoint (the reference's valid_keypoints); out_alpha [same] =
  * kp.alpha_time; out_neighbors (nullable) [n_keypoints][max_number_neighbors][3] + out_n_neighbors [n_keypoints]: the sorted

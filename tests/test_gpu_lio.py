@@ -70,3 +70,42 @@ def test_lio_residual_cap_small_neighbourhoods_and_edge_cases(gf2, oracle, synth
     with pytest.raises(gf2.Gf2Error, match="max_number_neighbors"):
         h.build_factors(scene["keypoints"], _opts(gf2, scene, max_number_neighbors=64))
     h.close()
+
+
+def test_device_resident_map_equals_sequential_add_point_to_map(gf2, oracle, synth):
+    """gf2_lio_add_points == lidarodom::addPointToMap over the scan in order (LIO/liw/lio/lidarodom.cpp:1167-1237): three scans, the last
+    with min_num_points = 3 (no new voxels, only voxels that already hold 3 points grow); the device map must hold exactly the same
+    points in the same per-voxel order, and factors built on it must equal the oracle's on the downloaded snapshot."""
+    scans = [synth.lio_scan(0, 30000), synth.lio_scan(1, 20000), synth.lio_scan(2, 25000, noise=0.03)]
+    mins = [0, 0, 3]
+    vox = {}
+    h = gf2.Lio(max_voxels=40000, max_keypoints=2000)
+    sizes = []
+    for pts, mn in zip(scans, mins):
+        synth.voxel_map_insert(vox, pts, 0.2, 20, 0.05, mn)
+        h.add_points(pts, 0.2, 0.05, mn)
+        sizes.append((len(vox), h.last_timing()["voxels"], h.last_timing()["new_voxels"]))
+    assert sizes[0][0] == sizes[0][1] == sizes[0][2] and sizes[1][0] == sizes[1][1] and sizes[2][2] == 0 and sizes[2][1] == sizes[1][1]
+    keys, npts, pts = h.get_map()
+    assert len(keys) == len(vox)
+    assert (np.diff(keys[:, 0].astype(np.int64) * 2 ** 32 + keys[:, 1].astype(np.int64) * 2 ** 16 + keys[:, 2].astype(np.int64)) > 0).all()   # ascending keys
+    grew = 0
+    for k, n, p in zip(keys.tolist(), npts, pts):
+        ref = np.array(vox[tuple(k)])
+        assert n == len(ref) and np.array_equal(p[:n], ref), k          # same points, same insertion order, bit-equal
+        grew += n > 1
+    assert grew > 1000 and npts.max() == 20                                 # voxels filled up to the capacity
+    # factors on the resident map == oracle on its snapshot
+    scene = synth.lio_scene(5, n_map_points=1000, n_keypoints=2000)
+    scene.update(keys=keys, n_points=npts, points=pts)
+    o = _opts(gf2, scene, max_num_residuals=100000)
+    fac, alpha, nbs, nn = h.build_factors(scene["keypoints"], o, want_neighbors=True)
+    rf, ra, rnbs, rnn = oracle.lio_build_factors(scene, o, want_neighbors=True)
+    assert np.array_equal(nn, rnn) and all(np.array_equal(nbs[k, :nn[k]], rnbs[k, :nn[k]]) for k in range(len(nn)))
+    _compare(fac, alpha, rf, ra)
+    assert len(fac) > 500
+    # capacity overflow is reported, not silently dropped
+    small = gf2.Lio(max_voxels=100, max_keypoints=8)
+    with pytest.raises(gf2.Gf2Error, match="capacity"):
+        small.add_points(scans[0])
+    small.close(); h.close()
