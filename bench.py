@@ -224,6 +224,21 @@ def run_lio(gf2, synth, steps=10, with_cpu=True):
             "residuals": int(len(fac)), "kernel_ms": k_ms / steps, "call_ms": wall * 1e3,
             "roofline": {"bound": "hbm", "kernel": "k_lio_factors", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
                          "note": "latency bound: 750 warps per scan, 20 dependent arg-min rounds each; the candidate points are L2 resident"}}
+    # map maintenance on the device-resident map: addPointToMap for 30k-point scans (the third scan lands in a populated map)
+    hm = gf2.Lio(max_voxels=60000, max_keypoints=8)
+    scans = [synth.lio_scan(s_, 30000) for s_ in range(4)]
+    for sc in scans[:3]:
+        hm.add_points(sc)
+    t0 = time.perf_counter(); hm.add_points(scans[3]); add_wall = time.perf_counter() - t0
+    tm = hm.last_timing()
+    line["map_insert"] = {"metric": "addPointToMap points/sec (30k-point scan into a populated device-resident map)", "value": 30000 / add_wall, "unit": "points/s",
+                          "device_ms": tm["kernel_ms"], "call_ms": add_wall * 1e3, "voxels": tm["voxels"], "new_voxels": tm["new_voxels"]}
+    if with_cpu:
+        vox = {}
+        synth.voxel_map_insert(vox, scans[0][:3000])
+        t0 = time.perf_counter(); synth.voxel_map_insert(vox, scans[1][:3000]); dt = time.perf_counter() - t0
+        line["map_insert"]["cpu_baseline"] = {"value": 3000 / dt, "unit": "points/s", "kind": "port", "cores": 1, "sample": "Python statement of addPointToMap, 3000 points (an interpreted baseline: indicative only)"}
+    hm.close()
     if with_cpu:
         import gf2_oracle as orc
         t0 = time.perf_counter(); n = 0; loop_s = 0.0
