@@ -123,7 +123,9 @@ bool readParameters(const std::string& config_file, Parameters& P) {  // keys an
     P.VEL_N_wheel = y.num("wheel_velocity_noise_sigma"); P.GYR_N_wheel = y.num("wheel_gyro_noise_sigma");
     P.ESTIMATE_EXTRINSIC_WHEEL = (int)y.num("estimate_wheel_extrinsic"); P.EXTRINSIC_TYPE_WHEEL = (int)y.num("extrinsic_type_wheel");
     P.ESTIMATE_INTRINSIC_WHEEL = (int)y.num("estimate_wheel_intrinsic");
-    if (y.scalars.count("sx")) P.SX = y.num("sx"); if (y.scalars.count("sy")) P.SY = y.num("sy"); if (y.scalars.count("sw")) P.SW = y.num("sw");
+    if (y.scalars.count("sx")) P.SX = y.num("sx");
+    if (y.scalars.count("sy")) P.SY = y.num("sy");
+    if (y.scalars.count("sw")) P.SW = y.num("sw");
     auto iw = y.matrices.find("body_T_wheel");
     if (iw != y.matrices.end() && iw->second.size() == 16) {
       const std::vector<double>& T = iw->second;
@@ -191,6 +193,164 @@ void FeatureManager::addFeatures(int frame_count, const std::map<int, std::vecto
   }
 }
 
+// feature_manager.cpp:57-116
+bool FeatureManager::addFeatureCheckParallax(int frame_count, const std::map<int, std::vector<std::pair<int, std::vector<double>>>>& image, double td) {
+  double parallax_sum = 0; int parallax_num = 0;
+  last_track_num = 0; last_average_parallax = 0; new_feature_num = 0; long_track_num = 0;
+  for (auto& id_pts : image) {
+    FeaturePerFrame f_per_fra(id_pts.second[0].second.data(), td);
+    const int feature_id = id_pts.first;
+    auto it = std::find_if(feature.begin(), feature.end(), [feature_id](const FeaturePerId& f) { return f.feature_id == feature_id; });
+    if (it == feature.end()) { feature.push_back(FeaturePerId(feature_id, frame_count)); feature.back().feature_per_frame.push_back(f_per_fra); new_feature_num++; }
+    else { it->feature_per_frame.push_back(f_per_fra); last_track_num++; if (it->feature_per_frame.size() >= 4) long_track_num++; }
+  }
+  if (frame_count < 2 || last_track_num < 20 || long_track_num < 40 || new_feature_num > 0.5 * last_track_num) return true;
+  for (auto& it_per_id : feature)
+    if (it_per_id.start_frame <= frame_count - 2 && it_per_id.start_frame + int(it_per_id.feature_per_frame.size()) - 1 >= frame_count - 1) {
+      parallax_sum += compensatedParallax2(it_per_id, frame_count); parallax_num++;
+    }
+  if (parallax_num == 0) return true;
+  last_average_parallax = parallax_sum / parallax_num * FOCAL_LENGTH;
+  return parallax_sum / parallax_num >= MIN_PARALLAX;
+}
+// :978-1011 (the rotation compensation is commented out in the reference: p_i_comp = p_i)
+double FeatureManager::compensatedParallax2(const FeaturePerId& it_per_id, int frame_count) const {
+  const FeaturePerFrame& frame_i = it_per_id.feature_per_frame[frame_count - 2 - it_per_id.start_frame];
+  const FeaturePerFrame& frame_j = it_per_id.feature_per_frame[frame_count - 1 - it_per_id.start_frame];
+  double ans = 0;
+  const double u_j = frame_j.point.x, v_j = frame_j.point.y;
+  const Vector3d p_i = frame_i.point, p_i_comp = p_i;
+  const double dep_i = p_i.z, u_i = p_i.x / dep_i, v_i = p_i.y / dep_i, du = u_i - u_j, dv = v_i - v_j;
+  const double dep_i_comp = p_i_comp.z, u_i_comp = p_i_comp.x / dep_i_comp, v_i_comp = p_i_comp.y / dep_i_comp, du_comp = u_i_comp - u_j, dv_comp = v_i_comp - v_j;
+  ans = std::max(ans, std::sqrt(std::min(du * du + dv * dv, du_comp * du_comp + dv_comp * dv_comp)));
+  return ans;
+}
+void FeatureManager::removeOutlier(const std::set<int>& outlierIndex) {   // :801-816
+  for (auto it = feature.begin(), it_next = feature.begin(); it != feature.end(); it = it_next) {
+    it_next++;
+    if (outlierIndex.find(it->feature_id) != outlierIndex.end()) feature.erase(it);
+  }
+}
+void FeatureManager::removeBackShiftDepth(const Matrix3d& marg_R, const Vector3d& marg_P, const Matrix3d& new_R, const Vector3d& new_P) {   // :818-856
+  for (auto it = feature.begin(), it_next = feature.begin(); it != feature.end(); it = it_next) {
+    it_next++;
+    if (it->start_frame != 0) it->start_frame--;
+    else {
+      const Vector3d uv_i = it->feature_per_frame[0].point;
+      it->feature_per_frame.erase(it->feature_per_frame.begin());
+      if (it->feature_per_frame.size() < 2) { feature.erase(it); continue; }
+      const Vector3d pts_i = {uv_i.x * it->estimated_depth, uv_i.y * it->estimated_depth, uv_i.z * it->estimated_depth};
+      const Vector3d r = mul(marg_R, pts_i), w_pts_i = {r.x + marg_P.x, r.y + marg_P.y, r.z + marg_P.z};
+      const Vector3d pts_j = mul(transpose(new_R), Vector3d{w_pts_i.x - new_P.x, w_pts_i.y - new_P.y, w_pts_i.z - new_P.z});
+      const double dep_j = pts_j.z;
+      it->estimated_depth = dep_j > 0 ? dep_j : INIT_DEPTH;
+    }
+  }
+}
+void FeatureManager::removeBack() {   // :858-874
+  for (auto it = feature.begin(), it_next = feature.begin(); it != feature.end(); it = it_next) {
+    it_next++;
+    if (it->start_frame != 0) it->start_frame--;
+    else { it->feature_per_frame.erase(it->feature_per_frame.begin()); if (it->feature_per_frame.size() == 0) feature.erase(it); }
+  }
+}
+void FeatureManager::removeFront(int frame_count) {   // :914-934
+  for (auto it = feature.begin(), it_next = feature.begin(); it != feature.end(); it = it_next) {
+    it_next++;
+    if (it->start_frame == frame_count) it->start_frame--;
+    else {
+      const int j = WINDOW_SIZE - 1 - it->start_frame;
+      if (it->endFrame() < frame_count - 1) continue;
+      it->feature_per_frame.erase(it->feature_per_frame.begin() + j);
+      if (it->feature_per_frame.size() == 0) feature.erase(it);
+    }
+  }
+}
+namespace {
+// right singular vector of the smallest singular value of an m x 4 matrix = eigenvector of the smallest eigenvalue of A^T A
+// (Eigen::JacobiSVD(...).matrixV().rightCols<1>() in the reference, up to the sign, which the caller divides out)
+void smallestRightSingularVector4(const std::vector<double>& A /* m x 4 row-major */, double v[4]) {
+  double M[16] = {0}, V[16];
+  const size_t m = A.size() / 4;
+  for (size_t r = 0; r < m; r++) for (int a = 0; a < 4; a++) for (int b = 0; b < 4; b++) M[a * 4 + b] += A[r * 4 + a] * A[r * 4 + b];
+  for (int i = 0; i < 16; i++) V[i] = (i % 5 == 0) ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < 100; sweep++) {
+    double off = 0, dg = 0;
+    for (int r = 0; r < 4; r++) for (int c = 0; c < 4; c++) (r == c ? dg : off) += M[r * 4 + c] * M[r * 4 + c];
+    if (off <= 1e-32 * (dg + 1e-300)) break;
+    for (int p = 0; p < 4; p++) for (int q = p + 1; q < 4; q++) {
+      const double apq = M[p * 4 + q]; if (apq == 0.0) continue;
+      const double tau = (M[q * 4 + q] - M[p * 4 + p]) / (2.0 * apq);
+      const double t = (tau >= 0 ? 1.0 : -1.0) / (std::fabs(tau) + std::sqrt(1.0 + tau * tau)), c = 1.0 / std::sqrt(1.0 + t * t), s = t * c;
+      for (int k = 0; k < 4; k++) { const double a = M[k * 4 + p], b = M[k * 4 + q]; M[k * 4 + p] = c * a - s * b; M[k * 4 + q] = s * a + c * b; }
+      for (int k = 0; k < 4; k++) { const double a = M[p * 4 + k], b = M[q * 4 + k]; M[p * 4 + k] = c * a - s * b; M[q * 4 + k] = s * a + c * b; }
+      for (int k = 0; k < 4; k++) { const double a = V[k * 4 + p], b = V[k * 4 + q]; V[k * 4 + p] = c * a - s * b; V[k * 4 + q] = s * a + c * b; }
+    }
+  }
+  int best = 0; for (int i = 1; i < 4; i++) if (M[i * 5] < M[best * 5]) best = i;
+  for (int k = 0; k < 4; k++) v[k] = V[k * 4 + best];
+}
+inline Vector3d add3(const Vector3d& a, const Vector3d& b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+inline Vector3d sub3(const Vector3d& a, const Vector3d& b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+}  // namespace
+void FeatureManager::triangulate(int, const Vector3d Ps[], const Matrix3d Rs[], const Vector3d tic[], const Matrix3d ric[]) {   // :669-724
+  for (auto& it_per_id : feature) {
+    if (it_per_id.estimated_depth > 0) continue;
+    it_per_id.used_num = (int)it_per_id.feature_per_frame.size();
+    if (it_per_id.used_num < 4) continue;
+    const int imu_i = it_per_id.start_frame; int imu_j = imu_i - 1;
+    std::vector<double> svd_A;
+    const Vector3d t0 = add3(Ps[imu_i], mul(Rs[imu_i], tic[0])); const Matrix3d R0 = mul(Rs[imu_i], ric[0]);
+    for (auto& it_per_frame : it_per_id.feature_per_frame) {
+      imu_j++;
+      const Vector3d t1 = add3(Ps[imu_j], mul(Rs[imu_j], tic[0])); const Matrix3d R1 = mul(Rs[imu_j], ric[0]);
+      const Vector3d t = mul(transpose(R0), sub3(t1, t0)); const Matrix3d R = mul(transpose(R0), R1);
+      const Matrix3d Rt = transpose(R); const Vector3d mt = mul(Rt, t);
+      const double P[12] = {Rt.m[0], Rt.m[1], Rt.m[2], -mt.x, Rt.m[3], Rt.m[4], Rt.m[5], -mt.y, Rt.m[6], Rt.m[7], Rt.m[8], -mt.z};
+      const Vector3d p = it_per_frame.point; const double n = std::sqrt(p.x * p.x + p.y * p.y + p.z * p.z);
+      const double f[3] = {p.x / n, p.y / n, p.z / n};
+      for (int c = 0; c < 4; c++) svd_A.push_back(f[0] * P[8 + c] - f[2] * P[c]);
+      for (int c = 0; c < 4; c++) svd_A.push_back(f[1] * P[8 + c] - f[2] * P[4 + c]);
+    }
+    double v[4]; smallestRightSingularVector4(svd_A, v);
+    it_per_id.estimated_depth = v[2] / v[3];
+    it_per_id.estimate_flag = 2;
+    if (it_per_id.estimated_depth < 0.1) { it_per_id.estimated_depth = INIT_DEPTH; it_per_id.estimate_flag = 0; }
+  }
+}
+void FeatureManager::triangulateWithDepth(int, const Vector3d Ps[], const Matrix3d Rs[], const Vector3d tic[], const Matrix3d ric[]) {   // :726-799
+  for (auto& it_per_id : feature) {
+    it_per_id.used_num = (int)it_per_id.feature_per_frame.size();
+    if (it_per_id.used_num < 4) continue;
+    if (it_per_id.estimated_depth > 0) continue;
+    const int start_frame = it_per_id.start_frame;
+    std::vector<double> verified_depths;
+    const Vector3d tr = add3(Ps[start_frame], mul(Rs[start_frame], tic[0])); const Matrix3d Rr = mul(Rs[start_frame], ric[0]);
+    const int n = (int)it_per_id.feature_per_frame.size();
+    for (int i = 0; i < n; i++) {
+      const Vector3d t0 = add3(Ps[start_frame + i], mul(Rs[start_frame + i], tic[0])); const Matrix3d R0 = mul(Rs[start_frame + i], ric[0]);
+      const FeaturePerFrame& fi = it_per_id.feature_per_frame[i];
+      if (fi.depth < 0.1 || fi.depth > depth_threshold) continue;
+      const Vector3d point0 = {fi.point.x * fi.depth, fi.point.y * fi.depth, fi.point.z * fi.depth};
+      const Vector3d t2r = mul(transpose(Rr), sub3(t0, tr)); const Matrix3d R2r = mul(transpose(Rr), R0);
+      for (int j = 0; j < n; j++) {
+        if (i == j) continue;
+        const Vector3d t1 = add3(Ps[start_frame + j], mul(Rs[start_frame + j], tic[0])); const Matrix3d R1 = mul(Rs[start_frame + j], ric[0]);
+        const Vector3d t20 = mul(transpose(R0), sub3(t1, t0)); const Matrix3d R20 = mul(transpose(R0), R1);
+        const Vector3d pp = sub3(mul(transpose(R20), point0), mul(transpose(R20), t20));
+        const FeaturePerFrame& fj = it_per_id.feature_per_frame[j];
+        const double rx = fj.point.x - pp.x / pp.z, ry = fj.point.y - pp.y / pp.z;
+        if (std::sqrt(rx * rx + ry * ry) < 10.0 / 460) { const Vector3d point_r = add3(mul(R2r, point0), t2r); verified_depths.push_back(point_r.z); }
+      }
+    }
+    if (verified_depths.empty()) continue;
+    double depth_sum = 0.0; for (double d : verified_depths) depth_sum += d;
+    it_per_id.estimated_depth = depth_sum / verified_depths.size();
+    it_per_id.estimate_flag = 1;
+    if (it_per_id.estimated_depth < 0.1) { it_per_id.estimated_depth = INIT_DEPTH; it_per_id.estimate_flag = 0; }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ Estimator
 Estimator::Estimator() { clearState(); memset(&last_summary, 0, sizeof(last_summary)); }
 Estimator::~Estimator() {
@@ -201,6 +361,7 @@ Estimator::~Estimator() {
 void Estimator::setParameter(const Parameters& p) {
   P = p; tic[0] = p.TIC; ric[0] = p.RIC; td = p.TD;
   tio = p.TIO; rio = p.RIO; sx = p.SX; sy = p.SY; sw = p.SW; td_wheel = p.TD_WHEEL;
+  f_manager.MIN_PARALLAX = p.MIN_PARALLAX;
 }
 void Estimator::clearState() {
   for (int i = 0; i <= WINDOW_SIZE; i++) { Rs[i] = Matrix3d(); Ps[i] = Vector3d(); Vs[i] = Vector3d(); Bas[i] = Vector3d(); Bgs[i] = Vector3d(); delete pre_integrations[i]; pre_integrations[i] = nullptr; }
@@ -396,6 +557,163 @@ void Estimator::optimization() {
     for (int r = 0; r < rows; r++) for (int c = 0; c < rows; c++) mp.linearized_jacobians[(size_t)r * rows + c] = J0[(size_t)r * GF2_MAX_PRIOR_DIM + c];
     mp.blocks.assign(blocks.begin(), blocks.begin() + nb);
   }  // GF2_MARG_UNCHANGED / DEGENERATE / UNSUPPORTED: the previous prior stays (block indices untouched, as at :3599)
+}
+
+// ---- measurement processing around the solve (steady state) -------------------------------------------------------------------------
+void Estimator::processIMU(double, double dt, const Vector3d& linear_acceleration, const Vector3d& angular_velocity) {   // estimator.cpp:795-836
+  if (!first_imu) { first_imu = true; acc_0 = linear_acceleration; gyr_0 = angular_velocity; }
+  if (!pre_integrations[frame_count]) pre_integrations[frame_count] = new IntegrationBase(acc_0, gyr_0, Bas[frame_count], Bgs[frame_count]);
+  if (frame_count != 0) pre_integrations[frame_count]->push_back(dt, linear_acceleration, angular_velocity);   // dt_buf / *_buf live inside the buffer class
+  acc_0 = linear_acceleration; gyr_0 = angular_velocity;
+}
+void Estimator::processWheel(double, double dt, const Vector3d& linear_velocity, const Vector3d& angular_velocity) {   // :837-896
+  if (!first_wheel) { first_wheel = true; vel_0_wheel = linear_velocity; gyr_0_wheel = angular_velocity; }
+  if (!pre_integrations_wheel[frame_count]) pre_integrations_wheel[frame_count] = new WheelIntegrationBase(vel_0_wheel, gyr_0_wheel, sx, sy, sw, td_wheel);
+  if (frame_count != 0) {
+    pre_integrations_wheel[frame_count]->push_back(dt, linear_velocity, angular_velocity);
+    const int j = frame_count;
+    const Vector3d un_gyr = {0.5 * (gyr_0_wheel.x + angular_velocity.x), 0.5 * (gyr_0_wheel.y + angular_velocity.y), 0.5 * (gyr_0_wheel.z + angular_velocity.z)};
+    const Vector3d un_vel_0 = mul(Rs[j], latest_vel_wheel_0);
+    // dead reckoning of the newest frame (systemstationary == false): Rs[j] *= deltaQ(un_gyr dt), Vs[j] = (Rs[j] v + un_vel_0) / 2, Ps[j] += dt Vs[j]
+    Rs[j] = mul(Rs[j], toRotationMatrix(normalized({1.0, un_gyr.x * dt / 2.0, un_gyr.y * dt / 2.0, un_gyr.z * dt / 2.0})));
+    const Vector3d rv = mul(Rs[j], linear_velocity);
+    Vs[j] = {0.5 * (rv.x + un_vel_0.x), 0.5 * (rv.y + un_vel_0.y), 0.5 * (rv.z + un_vel_0.z)};
+    Ps[j] = {Ps[j].x + dt * Vs[j].x, Ps[j].y + dt * Vs[j].y, Ps[j].z + dt * Vs[j].z};
+    latest_vel_wheel_0 = linear_velocity;
+  }
+  vel_0_wheel = linear_velocity; gyr_0_wheel = angular_velocity;
+}
+
+static double reprojectionError(const Matrix3d& Ri, const Vector3d& Pi, const Matrix3d& rici, const Vector3d& tici, const Matrix3d& Rj, const Vector3d& Pj,
+                                const Matrix3d& ricj, const Vector3d& ticj, double depth, const Vector3d& uvi, const Vector3d& uvj, double* err3d) {   // :3950-3969
+  const Vector3d a = mul(rici, Vector3d{depth * uvi.x, depth * uvi.y, depth * uvi.z});
+  const Vector3d b = mul(Ri, Vector3d{a.x + tici.x, a.y + tici.y, a.z + tici.z});
+  const Vector3d pts_w = {b.x + Pi.x, b.y + Pi.y, b.z + Pi.z};
+  const Vector3d c = mul(transpose(Rj), Vector3d{pts_w.x - Pj.x, pts_w.y - Pj.y, pts_w.z - Pj.z});
+  const Vector3d pts_cj = mul(transpose(ricj), Vector3d{c.x - ticj.x, c.y - ticj.y, c.z - ticj.z});
+  if (err3d) { const double dx = pts_cj.x - uvj.x, dy = pts_cj.y - uvj.y, dz = pts_cj.z - uvj.z; *err3d = std::sqrt(dx * dx + dy * dy + dz * dz) / depth; }
+  const double rx = pts_cj.x / pts_cj.z - uvj.x, ry = pts_cj.y / pts_cj.z - uvj.y;
+  return std::sqrt(rx * rx + ry * ry);
+}
+void Estimator::outliersRejection(std::set<int>& removeIndex) {   // :3971-4028
+  for (auto& it_per_id : f_manager.feature) {
+    double err = 0; int errCnt = 0;
+    it_per_id.used_num = (int)it_per_id.feature_per_frame.size();
+    if (it_per_id.used_num < 4) continue;
+    const int imu_i = it_per_id.start_frame; int imu_j = imu_i - 1;
+    const Vector3d pts_i = it_per_id.feature_per_frame[0].point; const double depth = it_per_id.estimated_depth;
+    for (auto& it_per_frame : it_per_id.feature_per_frame) {
+      imu_j++;
+      if (imu_i != imu_j) { err += reprojectionError(Rs[imu_i], Ps[imu_i], ric[0], tic[0], Rs[imu_j], Ps[imu_j], ric[0], tic[0], depth, pts_i, it_per_frame.point, nullptr); errCnt++; }
+    }
+    const double ave_err = err / errCnt;
+    if (ave_err * FOCAL_LENGTH > 3) removeIndex.insert(it_per_id.feature_id);
+  }
+}
+void Estimator::movingConsistencyCheckW(std::set<int>& removeIndex) {   // :4030-4074
+  for (auto& it_per_id : f_manager.feature) {
+    it_per_id.used_num = (int)it_per_id.feature_per_frame.size();
+    if (!(it_per_id.used_num >= 2 && it_per_id.start_frame < WINDOW_SIZE - 2)) continue;
+    const double depth = it_per_id.estimated_depth;
+    if (depth < 0) continue;
+    double err = 0, err3D = 0; int errCnt = 0;
+    const int wheel_i = it_per_id.start_frame; int wheel_j = wheel_i - 1;
+    const Vector3d pts_i = it_per_id.feature_per_frame[0].point;
+    for (auto& it_per_frame : it_per_id.feature_per_frame) {
+      wheel_j++;
+      if (wheel_i != wheel_j) {
+        double e3 = 0;
+        err += reprojectionError(Rs[wheel_i], Ps[wheel_i], ric[0], tic[0], Rs[wheel_j], Ps[wheel_j], ric[0], tic[0], depth, pts_i, it_per_frame.point, &e3);
+        err3D += e3; errCnt++;
+      }
+    }
+    if (errCnt > 0 && (FOCAL_LENGTH * err / errCnt > 10 || err3D / errCnt > 2.0)) removeIndex.insert(it_per_id.feature_id);
+  }
+}
+void Estimator::getPoseInWorldFrame(int index, double T[16]) const {   // :3901-3913
+  for (int i = 0; i < 16; i++) T[i] = (i % 5 == 0) ? 1.0 : 0.0;
+  for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) T[r * 4 + c] = Rs[index].m[r * 3 + c];
+  T[3] = Ps[index].x; T[7] = Ps[index].y; T[11] = Ps[index].z;
+}
+std::map<int, Vector3d> Estimator::predictPtsInNextFrame() const {   // :3915-3948: constant-velocity pose, landmarks of the newest frame into its camera
+  std::map<int, Vector3d> predictPts;
+  if (frame_count < 2) return predictPts;
+  // nextT = curT * (prevT^-1 * curT)
+  const Matrix3d Rc = Rs[frame_count], Rp = Rs[frame_count - 1]; const Vector3d Pc = Ps[frame_count], Pp = Ps[frame_count - 1];
+  const Matrix3d Rrel = mul(transpose(Rp), Rc); const Vector3d trel = mul(transpose(Rp), Vector3d{Pc.x - Pp.x, Pc.y - Pp.y, Pc.z - Pp.z});
+  const Matrix3d Rn = mul(Rc, Rrel); const Vector3d rn = mul(Rc, trel), Pn = {rn.x + Pc.x, rn.y + Pc.y, rn.z + Pc.z};
+  for (auto& it_per_id : f_manager.feature) {
+    if (!(it_per_id.estimated_depth > 0)) continue;
+    const int firstIndex = it_per_id.start_frame, lastIndex = it_per_id.start_frame + (int)it_per_id.feature_per_frame.size() - 1;
+    if ((int)it_per_id.feature_per_frame.size() >= 2 && lastIndex == frame_count) {
+      const double depth = it_per_id.estimated_depth; const Vector3d p0 = it_per_id.feature_per_frame[0].point;
+      const Vector3d a = mul(ric[0], Vector3d{depth * p0.x, depth * p0.y, depth * p0.z}), pts_j = {a.x + tic[0].x, a.y + tic[0].y, a.z + tic[0].z};
+      const Vector3d b = mul(Rs[firstIndex], pts_j), pts_w = {b.x + Ps[firstIndex].x, b.y + Ps[firstIndex].y, b.z + Ps[firstIndex].z};
+      const Vector3d pts_local = mul(transpose(Rn), Vector3d{pts_w.x - Pn.x, pts_w.y - Pn.y, pts_w.z - Pn.z});
+      predictPts[it_per_id.feature_id] = mul(transpose(ric[0]), Vector3d{pts_local.x - tic[0].x, pts_local.y - tic[0].y, pts_local.z - tic[0].z});
+    }
+  }
+  return predictPts;
+}
+void Estimator::slideWindow() {   // :3700-3857 (GNSS buffers and all_image_frame belong to subsystems outside this build)
+  if (marginalization_flag == MARGIN_OLD) {
+    back_R0 = Rs[0]; back_P0 = Ps[0];
+    if (frame_count == WINDOW_SIZE) {
+      for (int i = 0; i < WINDOW_SIZE; i++) {
+        Headers[i] = Headers[i + 1];
+        std::swap(Rs[i], Rs[i + 1]); std::swap(Ps[i], Ps[i + 1]);
+        if (P.USE_IMU) { std::swap(pre_integrations[i], pre_integrations[i + 1]); std::swap(Vs[i], Vs[i + 1]); std::swap(Bas[i], Bas[i + 1]); std::swap(Bgs[i], Bgs[i + 1]); }
+        if (P.USE_WHEEL) std::swap(pre_integrations_wheel[i], pre_integrations_wheel[i + 1]);
+      }
+      Headers[WINDOW_SIZE] = Headers[WINDOW_SIZE - 1]; Ps[WINDOW_SIZE] = Ps[WINDOW_SIZE - 1]; Rs[WINDOW_SIZE] = Rs[WINDOW_SIZE - 1];
+      if (P.USE_IMU) {
+        Vs[WINDOW_SIZE] = Vs[WINDOW_SIZE - 1]; Bas[WINDOW_SIZE] = Bas[WINDOW_SIZE - 1]; Bgs[WINDOW_SIZE] = Bgs[WINDOW_SIZE - 1];
+        delete pre_integrations[WINDOW_SIZE];
+        pre_integrations[WINDOW_SIZE] = new IntegrationBase(acc_0, gyr_0, Bas[WINDOW_SIZE], Bgs[WINDOW_SIZE]);
+      }
+      if (P.USE_WHEEL) { delete pre_integrations_wheel[WINDOW_SIZE]; pre_integrations_wheel[WINDOW_SIZE] = new WheelIntegrationBase(vel_0_wheel, gyr_0_wheel, sx, sy, sw, td_wheel); }
+      slideWindowOld();
+    }
+  } else if (frame_count == WINDOW_SIZE) {
+    Headers[frame_count - 1] = Headers[frame_count]; Ps[frame_count - 1] = Ps[frame_count]; Rs[frame_count - 1] = Rs[frame_count];
+    if (P.USE_IMU) {
+      const IntegrationBase* src = pre_integrations[frame_count];
+      for (size_t i = 0; src && i < src->dt_buf.size(); i++) pre_integrations[frame_count - 1]->push_back(src->dt_buf[i], src->acc_buf[i], src->gyr_buf[i]);
+      Vs[frame_count - 1] = Vs[frame_count]; Bas[frame_count - 1] = Bas[frame_count]; Bgs[frame_count - 1] = Bgs[frame_count];
+      delete pre_integrations[WINDOW_SIZE];
+      pre_integrations[WINDOW_SIZE] = new IntegrationBase(acc_0, gyr_0, Bas[WINDOW_SIZE], Bgs[WINDOW_SIZE]);
+    }
+    if (P.USE_WHEEL) {
+      const WheelIntegrationBase* src = pre_integrations_wheel[frame_count];
+      for (size_t i = 0; src && i < src->dt_buf.size(); i++) pre_integrations_wheel[frame_count - 1]->push_back(src->dt_buf[i], src->vel_buf[i], src->gyr_buf[i]);
+      delete pre_integrations_wheel[WINDOW_SIZE];
+      pre_integrations_wheel[WINDOW_SIZE] = new WheelIntegrationBase(vel_0_wheel, gyr_0_wheel, sx, sy, sw, td_wheel);
+    }
+    slideWindowNew();
+  }
+}
+void Estimator::slideWindowNew() { sum_of_front++; f_manager.removeFront(frame_count); }   // :3859-3868
+void Estimator::slideWindowOld() {   // :3870-3899 with solver_flag == NON_LINEAR (shift_depth)
+  sum_of_back++;
+  const Matrix3d R0 = mul(back_R0, ric[0]), R1 = mul(Rs[0], ric[0]);
+  const Vector3d a = mul(back_R0, tic[0]), b = mul(Rs[0], tic[0]);
+  f_manager.removeBackShiftDepth(R0, {back_P0.x + a.x, back_P0.y + a.y, back_P0.z + a.z}, R1, {Ps[0].x + b.x, Ps[0].y + b.y, Ps[0].z + b.z});
+}
+// processImage, the `else // not ini` branch (:1133-1215): keyframe decision, depth initialisation, solve + marginalization, moving-consistency
+// outlier removal, window slide. failureDetection / GNSS / line features / the image-frame map of the initialiser are outside this build.
+void Estimator::processImage(const std::map<int, std::vector<std::pair<int, std::vector<double>>>>& image, double header) {
+  marginalization_flag = f_manager.addFeatureCheckParallax(frame_count, image, td) ? MARGIN_OLD : MARGIN_SECOND_NEW;   // :900-911
+  Headers[frame_count] = header;
+  if (DEPTH) f_manager.triangulateWithDepth(frame_count, Ps, Rs, tic, ric);
+  f_manager.triangulate(frame_count, Ps, Rs, tic, ric);
+  std::set<int> removeIndex;
+  if (USE_MCC) { movingConsistencyCheckW(removeIndex); f_manager.removeOutlier(removeIndex); }
+  optimization();
+  if (!last_error.empty()) return;
+  if (!USE_MCC) { std::set<int> idx; movingConsistencyCheckW(idx); f_manager.removeOutlier(idx); }
+  slideWindow();
+  f_manager.removeFailures();
+  last_R0 = Rs[0]; last_P0 = Ps[0];
 }
 
 // ------------------------------------------------------------------------------------------------ FeatureTracker
@@ -640,6 +958,67 @@ void gf2h_new_wheel_interval(void* e, int j, const double* vel0, const double* g
   E->pre_integrations_wheel[j] = new WheelIntegrationBase({vel0[0], vel0[1], vel0[2]}, {gyr0[0], gyr0[1], gyr0[2]}, E->sx, E->sy, E->sw, E->td_wheel);
 }
 void gf2h_push_wheel(void* e, int j, double dt, const double* vel, const double* gyr) { ((Estimator*)e)->pre_integrations_wheel[j]->push_back(dt, {vel[0], vel[1], vel[2]}, {gyr[0], gyr[1], gyr[2]}); }
+// ---- FeatureManager bookkeeping / window glue (CPU-only logic: tests/test_host_cpu.py drives it without a device)
+static std::map<int, std::vector<std::pair<int, std::vector<double>>>> image_of(int n, const int* ids, const double* pts8) {
+  std::map<int, std::vector<std::pair<int, std::vector<double>>>> image;
+  for (int i = 0; i < n; i++) image[ids[i]].emplace_back(0, std::vector<double>(pts8 + 8 * i, pts8 + 8 * i + 8));
+  return image;
+}
+int gf2h_add_feature_check_parallax(void* e, int frame_count, int n, const int* ids, const double* pts8, double td, double* stats4) {
+  FeatureManager& fm = ((Estimator*)e)->f_manager;
+  const bool key = fm.addFeatureCheckParallax(frame_count, image_of(n, ids, pts8), td);
+  if (stats4) { stats4[0] = fm.last_track_num; stats4[1] = fm.new_feature_num; stats4[2] = fm.long_track_num; stats4[3] = fm.last_average_parallax; }
+  return key ? 1 : 0;
+}
+void gf2h_set_min_parallax(void* e, double v) { ((Estimator*)e)->f_manager.MIN_PARALLAX = v; }
+void gf2h_remove_back(void* e) { ((Estimator*)e)->f_manager.removeBack(); }
+void gf2h_remove_front(void* e, int frame_count) { ((Estimator*)e)->f_manager.removeFront(frame_count); }
+void gf2h_remove_failures(void* e) { ((Estimator*)e)->f_manager.removeFailures(); }
+void gf2h_remove_outlier(void* e, int n, const int* ids) { ((Estimator*)e)->f_manager.removeOutlier(std::set<int>(ids, ids + n)); }
+void gf2h_remove_back_shift_depth(void* e, const double* mR, const double* mP, const double* nR, const double* nP) {
+  Matrix3d a, b; for (int i = 0; i < 9; i++) { a.m[i] = mR[i]; b.m[i] = nR[i]; }
+  ((Estimator*)e)->f_manager.removeBackShiftDepth(a, {mP[0], mP[1], mP[2]}, b, {nP[0], nP[1], nP[2]});
+}
+void gf2h_triangulate(void* e, int with_depth) {
+  Estimator* E = (Estimator*)e;
+  if (with_depth) E->f_manager.triangulateWithDepth(E->frame_count, E->Ps, E->Rs, E->tic, E->ric); else E->f_manager.triangulate(E->frame_count, E->Ps, E->Rs, E->tic, E->ric);
+}
+int gf2h_feature_obs(void* e, int feature_id, int max_n, double* out8, int* estimate_flag) {   // rows [x y z u v vx vy depth] of one landmark's track
+  for (auto& f : ((Estimator*)e)->f_manager.feature) if (f.feature_id == feature_id) {
+    int k = 0;
+    for (auto& pf : f.feature_per_frame) { if (k >= max_n) break; double* o = out8 + 8 * k++; o[0] = pf.point.x; o[1] = pf.point.y; o[2] = pf.point.z; o[3] = pf.uv[0]; o[4] = pf.uv[1]; o[5] = pf.velocity[0]; o[6] = pf.velocity[1]; o[7] = pf.depth; }
+    if (estimate_flag) *estimate_flag = f.estimate_flag;
+    return k;
+  }
+  return -1;
+}
+int gf2h_check_outliers(void* e, int which /* 0 outliersRejection, 1 movingConsistencyCheckW */, int max_n, int* ids) {
+  std::set<int> idx; if (which) ((Estimator*)e)->movingConsistencyCheckW(idx); else ((Estimator*)e)->outliersRejection(idx);
+  int k = 0; for (int i : idx) if (k < max_n) ids[k++] = i;
+  return (int)idx.size();
+}
+int gf2h_predict_pts(void* e, int max_n, int* ids, double* xyz) {
+  auto m = ((Estimator*)e)->predictPtsInNextFrame(); int k = 0;
+  for (auto& kv : m) if (k < max_n) { ids[k] = kv.first; xyz[3 * k] = kv.second.x; xyz[3 * k + 1] = kv.second.y; xyz[3 * k + 2] = kv.second.z; k++; }
+  return (int)m.size();
+}
+void gf2h_set_flags(void* e, int use_imu, int use_wheel, int depth, int use_mcc) { Estimator* E = (Estimator*)e; E->P.USE_IMU = use_imu; E->P.USE_WHEEL = use_wheel; E->DEPTH = depth != 0; E->USE_MCC = use_mcc != 0; }
+void gf2h_process_imu(void* e, double t, double dt, const double* acc, const double* gyr) { ((Estimator*)e)->processIMU(t, dt, {acc[0], acc[1], acc[2]}, {gyr[0], gyr[1], gyr[2]}); }
+void gf2h_process_wheel(void* e, double t, double dt, const double* vel, const double* gyr) { ((Estimator*)e)->processWheel(t, dt, {vel[0], vel[1], vel[2]}, {gyr[0], gyr[1], gyr[2]}); }
+void gf2h_slide_window(void* e) { ((Estimator*)e)->slideWindow(); }
+void gf2h_set_headers(void* e, const double* h11) { for (int i = 0; i <= WINDOW_SIZE; i++) ((Estimator*)e)->Headers[i] = h11[i]; }
+void gf2h_get_headers(void* e, double* h11, int* counters2) { Estimator* E = (Estimator*)e; for (int i = 0; i <= WINDOW_SIZE; i++) h11[i] = E->Headers[i]; counters2[0] = E->sum_of_back; counters2[1] = E->sum_of_front; }
+int gf2h_interval_samples(void* e, int j, int wheel, int max_n, double* dt) {   // dt_buf of pre_integrations[j] / pre_integrations_wheel[j]
+  Estimator* E = (Estimator*)e; const std::vector<double>* b = nullptr;
+  if (wheel) { if (E->pre_integrations_wheel[j]) b = &E->pre_integrations_wheel[j]->dt_buf; } else if (E->pre_integrations[j]) b = &E->pre_integrations[j]->dt_buf;
+  if (!b) return -1;
+  for (size_t i = 0; i < b->size() && (int)i < max_n; i++) dt[i] = (*b)[i];
+  return (int)b->size();
+}
+int gf2h_process_image(void* e, int n, const int* ids, const double* pts8, double header) {
+  Estimator* E = (Estimator*)e; E->processImage(image_of(n, ids, pts8), header);
+  return E->lastError()[0] ? -1 : (E->marginalization_flag == Estimator::MARGIN_OLD ? 0 : 1);
+}
 void gf2h_set_prior(void* e, int n, const double* J0, const double* r0, int nblocks, const gf2_prior_block* blocks) {
   MarginalizationPrior& mp = ((Estimator*)e)->last_marginalization_info;
   mp.valid = n > 0; mp.n = n; mp.linearized_jacobians.assign(J0, J0 + (size_t)n * n); mp.linearized_residuals.assign(r0, r0 + n); mp.blocks.assign(blocks, blocks + nblocks);

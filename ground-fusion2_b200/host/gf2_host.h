@@ -113,6 +113,20 @@ class FeatureManager {
   void setDepth(const std::vector<double>& x);   // :249-267
   void removeFailures();                         // :269-278
   void clearDepth();                             // :280-284
+  // keyframe decision + table update of one image (feature_manager.cpp:57-116); true = the second newest frame is a keyframe (MARGIN_OLD)
+  bool addFeatureCheckParallax(int frame_count, const std::map<int, std::vector<std::pair<int, std::vector<double>>>>& image, double td);
+  double compensatedParallax2(const FeaturePerId& it_per_id, int frame_count) const;   // :978-1011
+  void removeOutlier(const std::set<int>& outlierIndex);                               // :801-816
+  void removeBackShiftDepth(const Matrix3d& marg_R, const Vector3d& marg_P, const Matrix3d& new_R, const Vector3d& new_P);  // :818-856
+  void removeBack();                                                                   // :858-874
+  void removeFront(int frame_count);                                                   // :914-934
+  // depth initialisation of landmarks without one (estimated_depth <= 0, >= 4 observations): :669-724 (SVD over the track) and
+  // :726-799 (RGB-D: mean of the depth measurements that reproject within 10/460 into the other frames)
+  void triangulate(int frameCnt, const Vector3d Ps[], const Matrix3d Rs[], const Vector3d tic[], const Matrix3d ric[]);
+  void triangulateWithDepth(int frameCnt, const Vector3d Ps[], const Matrix3d Rs[], const Vector3d tic[], const Matrix3d ric[]);
+  int last_track_num = 0, new_feature_num = 0, long_track_num = 0;
+  double last_average_parallax = 0.0, MIN_PARALLAX = 10.0 / FOCAL_LENGTH, INIT_DEPTH = 5.0;
+  int depth_threshold = 3;
   // append the observations of one image in the reference's container: map<id, vector<pair<cam, 8-vector>>> (cam 0 only)
   void addFeatures(int frame_count, const std::map<int, std::vector<std::pair<int, std::vector<double>>>>& image, double td);  // :67-88 (list insertion part)
 };
@@ -134,6 +148,22 @@ class Estimator {
   void clearState();
   void vector2double();   // estimator.cpp:2337-2414
   void double2vector();   // estimator.cpp:2501-2630 (yaw / position re-anchoring to frame 0, setDepth)
+  // measurement processing around the solve (steady state, solver_flag == NON_LINEAR)
+  void processIMU(double t, double dt, const Vector3d& linear_acceleration, const Vector3d& angular_velocity);   // :795-836 (sample buffering)
+  void processWheel(double t, double dt, const Vector3d& linear_velocity, const Vector3d& angular_velocity);     // :837-896 (buffering + dead reckoning of the newest frame)
+  void processImage(const std::map<int, std::vector<std::pair<int, std::vector<double>>>>& image, double header);  // :897-1216, the `else // not ini` branch
+  void slideWindow();      // :3700-3857
+  void slideWindowNew();   // :3859-3868
+  void slideWindowOld();   // :3870-3899
+  void outliersRejection(std::set<int>& removeIndex);          // :3971-4028
+  void movingConsistencyCheckW(std::set<int>& removeIndex);    // :4030-4074
+  void getPoseInWorldFrame(int index, double T[16]) const;     // :3901-3913 (row-major 4x4)
+  std::map<int, Vector3d> predictPtsInNextFrame() const;       // :3915-3948 (the map handed to FeatureTracker::setPrediction)
+  double Headers[WINDOW_SIZE + 1] = {0};
+  Matrix3d back_R0; Vector3d back_P0;
+  int sum_of_back = 0, sum_of_front = 0;
+  bool first_imu = false, first_wheel = false, DEPTH = false, USE_MCC = false;
+  Vector3d acc_0, gyr_0, vel_0_wheel, gyr_0_wheel, latest_vel_wheel_0;
   void optimization();    // estimator.cpp:2951-3693: the ceres::Problem build + ceres::Solve (gf2_solve), then the
                           // marginalization of the oldest / second-newest frame (gf2_marginalize) into last_marginalization_info
   enum MarginalizationFlag { MARGIN_OLD = 0, MARGIN_SECOND_NEW = 1 };  // estimator.h:60-64

@@ -136,3 +136,232 @@ def test_set_mask_filled_circle_matches_cv2():
     assert len(kept) == 4   # the 5th point lies inside the 4th's disk
     # the C++ fillCircle is tested against cv2.circle on the GPU box in tests/test_gpu_host.py (trackImage exports its mask)
     L.gf2h_tracker_destroy(t)
+
+
+# ---------------------------------------------------------------------------------------------------- window glue
+class PyFeatureManager:
+    """Plain-Python restatement of the FeatureManager bookkeeping (VE/estimator/feature_manager.cpp:57-116, 801-934, 978-1011):
+    list of [feature_id, start_frame, [obs8...], depth] in insertion order. Index work: compared exactly with the C++ mirror."""
+    WINDOW_SIZE = 10
+    FOCAL = 460.0
+
+    def __init__(self, min_parallax):
+        self.f = []; self.min_parallax = min_parallax
+
+    def add_check_parallax(self, frame_count, ids, pts):
+        last_track = new = long_track = 0
+        for i, p in sorted(zip(ids, pts), key=lambda t: t[0]):
+            it = next((x for x in self.f if x[0] == i), None)
+            if it is None:
+                self.f.append([i, frame_count, [p], -1.0]); new += 1
+            else:
+                it[2].append(p); last_track += 1
+                long_track += len(it[2]) >= 4
+        self.stats = (last_track, new, long_track)
+        if frame_count < 2 or last_track < 20 or long_track < 40 or new > 0.5 * last_track:
+            return True
+        ps, pn = 0.0, 0
+        for fid, s, obs, _ in self.f:
+            if s <= frame_count - 2 and s + len(obs) - 1 >= frame_count - 1:
+                a, b = obs[frame_count - 2 - s], obs[frame_count - 1 - s]
+                du, dv = a[0] / a[2] - b[0], a[1] / a[2] - b[1]
+                ps += max(0.0, np.sqrt(min(du * du + dv * dv, du * du + dv * dv))); pn += 1
+        return True if pn == 0 else ps / pn >= self.min_parallax
+
+    def remove_back(self):
+        keep = []
+        for it in self.f:
+            if it[1] != 0:
+                it[1] -= 1; keep.append(it)
+            else:
+                it[2].pop(0)
+                if len(it[2]): keep.append(it)
+        self.f = keep
+
+    def remove_back_shift_depth(self, mR, mP, nR, nP, init_depth=5.0):
+        keep = []
+        for it in self.f:
+            if it[1] != 0:
+                it[1] -= 1; keep.append(it); continue
+            uv = np.array(it[2].pop(0)[:3])
+            if len(it[2]) < 2: continue
+            pj = nR.T @ (mR @ (uv * it[3]) + mP - nP)
+            it[3] = pj[2] if pj[2] > 0 else init_depth
+            keep.append(it)
+        self.f = keep
+
+    def remove_front(self, frame_count):
+        keep = []
+        for it in self.f:
+            if it[1] == frame_count:
+                it[1] -= 1; keep.append(it); continue
+            j = self.WINDOW_SIZE - 1 - it[1]
+            if it[1] + len(it[2]) - 1 < frame_count - 1:
+                keep.append(it); continue
+            it[2].pop(j)
+            if len(it[2]): keep.append(it)
+        self.f = keep
+
+    def remove_outlier(self, ids):
+        self.f = [it for it in self.f if it[0] not in set(ids)]
+
+
+def _table(L, e, n_max=4000):
+    ids = np.zeros(n_max, np.int32); st = np.zeros(n_max, np.int32); ln = np.zeros(n_max, np.int32); dep = np.zeros(n_max); flg = np.zeros(n_max, np.int32)
+    n = L.gf2h_feature_table(e, n_max, H.p(ids), H.p(st), H.p(ln), H.p(dep), H.p(flg))
+    return ids[:n].tolist(), st[:n].tolist(), ln[:n].tolist(), dep[:n]
+
+
+def _same(L, e, py):
+    ids, st, ln, dep = _table(L, e)
+    assert ids == [it[0] for it in py.f] and st == [it[1] for it in py.f] and ln == [len(it[2]) for it in py.f]
+    return dep
+
+
+def test_feature_manager_bookkeeping_matches_restatement():
+    """addFeatureCheckParallax (keyframe decision), removeBack / removeBackShiftDepth / removeFront / removeOutlier over a simulated
+    sequence of 40 frames with feature births and deaths: table order, start frames, track lengths and keyframe flags identical."""
+    L = H.lib()
+    L.gf2h_feature_obs.restype = C.c_int
+    rng = np.random.default_rng(12)
+    e = C.c_void_p(L.gf2h_estimator_create())
+    minpar = 10.0 / 460.0
+    L.gf2h_set_min_parallax(e, C.c_double(minpar))
+    py = PyFeatureManager(minpar)
+    alive = {}; next_id = 0; frame_count = 0; flags = []
+    for step in range(40):
+        for i in list(alive):                                        # deaths
+            if rng.random() < 0.08: del alive[i]
+        for _ in range(int(rng.integers(0, 12)) + (60 if step == 0 else 0)):   # births
+            alive[next_id] = rng.uniform(-0.5, 0.5, 2); next_id += 1
+        move = rng.uniform(0.0, 0.06) * (step % 3 != 0)              # some frames barely move -> MARGIN_SECOND_NEW
+        ids = np.array(sorted(alive), np.int32)
+        pts = np.zeros((len(ids), 8))
+        for k, i in enumerate(ids):
+            alive[i] = alive[i] + move * rng.normal(size=2) * 0.5 + move
+            pts[k] = [alive[i][0], alive[i][1], 1.0, 320 + 460 * alive[i][0], 240 + 460 * alive[i][1], 0.1, -0.2, rng.uniform(0.5, 4.0)]
+        stats = np.zeros(4)
+        key = L.gf2h_add_feature_check_parallax(e, frame_count, len(ids), H.p(ids), H.p(pts), C.c_double(0.0), H.p(stats))
+        pkey = py.add_check_parallax(frame_count, ids.tolist(), [p.tolist() for p in pts])
+        assert bool(key) == pkey and tuple(int(x) for x in stats[:3]) == py.stats
+        flags.append(pkey)
+        _same(L, e, py)
+        if frame_count < 10:
+            frame_count += 1; continue
+        if step % 7 == 3:                                            # outlier removal of a few ids
+            drop = ids[::9].astype(np.int32)
+            L.gf2h_remove_outlier(e, len(drop), H.p(drop)); py.remove_outlier(drop.tolist())
+            for i in drop.tolist(): alive.pop(i, None)
+        if pkey:
+            if step % 2:                                             # solver_flag == NON_LINEAR path with depth shifting
+                allids = np.array([it[0] for it in py.f], np.int32); deps = rng.uniform(1.0, 6.0, len(allids))
+                L.gf2h_set_depths(e, len(allids), H.p(allids), H.p(deps), None)
+                for it, d in zip(py.f, deps): it[3] = d
+                th = 0.05; mR = np.eye(3); nR = np.array([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1.0]])
+                mP = np.zeros(3); nP = np.array([0.1, 0.0, 2.0 if step % 4 == 1 else 0.05])   # sometimes behind the new camera -> INIT_DEPTH
+                L.gf2h_remove_back_shift_depth(e, H.p(mR), H.p(mP), H.p(nR), H.p(nP)); py.remove_back_shift_depth(mR, mP, nR, nP)
+                dep = _same(L, e, py)
+                assert np.abs(dep - np.array([it[3] for it in py.f])).max() < 1e-12
+            else:
+                L.gf2h_remove_back(e); py.remove_back()
+        else:
+            L.gf2h_remove_front(e, frame_count); py.remove_front(frame_count)
+        _same(L, e, py)
+    assert 5 < sum(flags) < 40 and len(py.f) > 20                  # both marginalization flags occurred
+    # the stored observation rows survive the erasures intact
+    fid = py.f[len(py.f) // 2][0]; out = np.zeros((16, 8)); fl = C.c_int(0)
+    n = L.gf2h_feature_obs(e, fid, 16, H.p(out), C.byref(fl))
+    assert n == len(py.f[len(py.f) // 2][2]) and np.array_equal(out[:n], np.array(py.f[len(py.f) // 2][2]))
+    L.gf2h_estimator_destroy(e)
+
+
+def _look_at_frames(rng, n=11):
+    """camera-forward (+z) body frames moving along x with a small yaw; returns (P [n,3], R [n,3,3])"""
+    P = np.stack([np.array([0.15 * i, 0.02 * np.sin(i), 0.0]) for i in range(n)])
+    R = []
+    for i in range(n):
+        a = 0.02 * i
+        R.append(np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]]))
+    return P, np.stack(R)
+
+
+def test_triangulate_outlier_checks_prediction_and_slide_window():
+    """triangulate (SVD over the track) / triangulateWithDepth recover the true depth; movingConsistencyCheckW / outliersRejection flag
+    exactly the corrupted landmarks; predictPtsInNextFrame follows the constant-velocity formula; slideWindow moves states, headers and
+    sample buffers as estimator.cpp:3700-3899 does (MARGIN_OLD and MARGIN_SECOND_NEW)."""
+    L = H.lib()
+    rng = np.random.default_rng(3)
+    e = C.c_void_p(L.gf2h_estimator_create())
+    P, R = _look_at_frames(rng)
+    L.gf2h_set_frame_states(e, H.p(H.frame_states(P, R, np.tile([1.5, 0, 0], (11, 1)), np.zeros((11, 3)), np.zeros((11, 3)))))
+    L.gf2h_set_extrinsic(e, H.p(np.zeros(3)), H.p(np.eye(3)), C.c_double(0.0), C.c_double(9.8), H.p(np.array([0.1, 0.01, 1e-3, 1e-4])))
+    nl = 60
+    Xw = np.stack([rng.uniform(-0.5, 2.0, nl), rng.uniform(-0.6, 0.6, nl), rng.uniform(1.6, 2.7, nl)], -1)   # within depth_threshold = 3 m
+    start = rng.integers(0, 5, nl)
+    for f in range(11):
+        ids = np.array([l for l in range(nl) if start[l] <= f], np.int32)
+        pts = np.zeros((len(ids), 8))
+        for k, l in enumerate(ids):
+            pc = R[f].T @ (Xw[l] - P[f])
+            pts[k] = [pc[0] / pc[2], pc[1] / pc[2], 1.0, 0, 0, 0, 0, pc[2] if l % 2 == 0 else 0.0]   # odd landmarks: no depth measurement
+        L.gf2h_add_image(e, f, len(ids), H.p(ids), H.p(pts), C.c_double(0.0))
+    true_depth = np.array([(R[start[l]].T @ (Xw[l] - P[start[l]]))[2] for l in range(nl)])
+    L.gf2h_set_flags(e, 1, 0, 1, 0)
+    L.gf2h_triangulate(e, 1)                                                   # RGB-D: even landmarks get the verified depth (flag 1)
+    def by_id():
+        ids, st, ln, dep = _table(L, e)
+        order = np.argsort(ids)
+        return np.array(ids)[order].tolist(), np.array(st)[order].tolist(), dep[order]
+    ids, st, dep = by_id()
+    assert ids == list(range(nl)) and st == start.tolist()
+    even = np.arange(nl) % 2 == 0
+    assert np.abs(dep[even] - true_depth[even]).max() < 1e-9 and (dep[~even] == -1.0).all()
+    L.gf2h_triangulate(e, 0)                                                   # the rest by SVD triangulation (flag 2)
+    ids, st, dep = by_id()
+    assert np.abs(dep - true_depth).max() < 1e-6
+    out = np.zeros((16, 8)); fl = C.c_int(0)
+    L.gf2h_feature_obs(e, 1, 16, H.p(out), C.byref(fl)); assert fl.value == 2
+    L.gf2h_feature_obs(e, 0, 16, H.p(out), C.byref(fl)); assert fl.value == 1
+    # corrupt three depths: far too deep -> large reprojection error
+    bad = np.array([5, 17, 33], np.int32)
+    L.gf2h_set_depths(e, 3, H.p(bad), H.p(true_depth[bad] * np.array([6.0, 0.15, 5.0])), None)
+    got = np.zeros(64, np.int32)
+    n = L.gf2h_check_outliers(e, 0, 64, H.p(got)); assert sorted(got[:n].tolist()) == bad.tolist()           # outliersRejection: > 3 px mean
+    n = L.gf2h_check_outliers(e, 1, 64, H.p(got)); assert set(got[:n].tolist()) <= set(bad.tolist()) and n >= 1   # movingConsistencyCheckW: > 10 px or 3-D ratio > 2
+    L.gf2h_set_depths(e, 3, H.p(bad), H.p(true_depth[bad]), None)
+    # prediction: landmarks seen in the newest frame, expressed in the constant-velocity next camera frame
+    pid = np.zeros(nl, np.int32); pxyz = np.zeros((nl, 3))
+    n = L.gf2h_predict_pts(e, nl, H.p(pid), H.p(pxyz)); assert n == nl
+    Tc = np.eye(4); Tc[:3, :3] = R[10]; Tc[:3, 3] = P[10]; Tp = np.eye(4); Tp[:3, :3] = R[9]; Tp[:3, 3] = P[9]
+    Tn = Tc @ (np.linalg.inv(Tp) @ Tc)
+    ref = (Tn[:3, :3].T @ (Xw[pid[:n]] - Tn[:3, 3]).T).T
+    assert np.abs(pxyz[:n] - ref).max() < 1e-6
+    # slideWindow, MARGIN_OLD: states / headers shift down, the newest is duplicated, interval buffers follow their frames
+    hdr = np.arange(11) * 0.1 + 5.0; L.gf2h_set_headers(e, H.p(hdr))
+    for j in range(1, 11):
+        L.gf2h_new_interval(e, j, H.p(np.zeros(3)), H.p(np.zeros(3)), H.p(np.zeros(3)), H.p(np.zeros(3)))
+        for s in range(j):                                                     # interval j holds j samples of dt = 0.001 j
+            L.gf2h_push_imu(e, j, C.c_double(0.001 * j), H.p(np.zeros(3)), H.p(np.zeros(3)))
+    L.gf2h_set_marginalization_flag(e, 0)
+    L.gf2h_slide_window(e)
+    st2 = np.zeros((11, 21)); L.gf2h_get_frame_states(e, H.p(st2))
+    assert np.array_equal(st2[:10, :3], P[1:]) and np.array_equal(st2[10, :3], P[10])
+    h2 = np.zeros(11); cnt = np.zeros(2, np.int32); L.gf2h_get_headers(e, H.p(h2), H.p(cnt))
+    assert np.array_equal(h2[:10], hdr[1:]) and h2[10] == hdr[10] and cnt.tolist() == [1, 0]
+    dt = np.zeros(32)
+    assert [L.gf2h_interval_samples(e, j, 0, 32, H.p(dt)) for j in range(1, 11)] == [2, 3, 4, 5, 6, 7, 8, 9, 10, 0]   # interval j+1 moved to j; a fresh one at 10
+    ids2, st_2, ln2, dep2 = _table(L, e)
+    assert all(s >= 0 for s in st_2) and len(ids2) <= nl
+    # depths of landmarks that started in the dropped frame are re-expressed in their new first frame
+    for i, s_old, d_new in zip(ids2, [start[i] for i in ids2], dep2):
+        if s_old == 0:
+            assert abs(d_new - (R[1].T @ (Xw[i] - P[1]))[2]) < 1e-6
+    # MARGIN_SECOND_NEW: the newest frame replaces the second newest, its samples are appended to the previous interval
+    for s in range(3):
+        L.gf2h_push_imu(e, 10, C.c_double(0.5), H.p(np.zeros(3)), H.p(np.zeros(3)))
+    L.gf2h_set_marginalization_flag(e, 1)
+    before = L.gf2h_interval_samples(e, 9, 0, 32, H.p(dt))
+    L.gf2h_slide_window(e)
+    assert L.gf2h_interval_samples(e, 9, 0, 32, H.p(dt)) == before + 3 and L.gf2h_interval_samples(e, 10, 0, 32, H.p(dt)) == 0
+    L.gf2h_get_headers(e, H.p(h2), H.p(cnt)); assert cnt.tolist() == [1, 1]
+    L.gf2h_estimator_destroy(e)
