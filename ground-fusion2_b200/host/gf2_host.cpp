@@ -463,6 +463,14 @@ void Estimator::optimization() {
   int32_t n_lm = (int32_t)start.size();
   std::vector<double> invdep(NUM_OF_F, 1.0); for (int i = 0; i < n_lm; i++) invdep[i] = para_Feature[i][0];
   start.resize(NUM_OF_F, 0); len.resize(NUM_OF_F, 0); fixed.resize(NUM_OF_F, 0); obs.resize((size_t)NUM_OF_F * (WINDOW_SIZE + 1));
+  if (capture) {
+    memcpy(cap.pose, para_Pose, sizeof(cap.pose)); memcpy(cap.sb, para_SpeedBias, sizeof(cap.sb)); memcpy(cap.ex, para_Ex_Pose[0], sizeof(cap.ex)); cap.td = para_Td[0][0];
+    for (int i = 0; i < F; i++) cap.frame_td[i] = frame_td[i];
+    cap.n_lm = n_lm; cap.start.assign(start.begin(), start.begin() + n_lm); cap.len.assign(len.begin(), len.begin() + n_lm); cap.fixed.assign(fixed.begin(), fixed.begin() + n_lm);
+    cap.invdep.assign(invdep.begin(), invdep.begin() + n_lm);
+    size_t no = 0; for (int i = 0; i < n_lm; i++) no += (size_t)len[i];
+    cap.obs.assign(obs.begin(), obs.begin() + no);
+  }
   int rc = gf2_set_states(gf2, 0, 1, &para_Pose[0][0], &para_SpeedBias[0][0], para_Ex_Pose[0], para_Td[0], wheel_on ? para_Ex_Pose_wheel[0] : nullptr, wheel_on ? sxsysw : nullptr, wheel_on ? para_Td_wheel[0] : nullptr);
   if (rc == GF2_OK) rc = gf2_set_landmarks(gf2, 0, 1, &n_lm, invdep.data(), start.data(), len.data(), fixed.data(), obs.data(), frame_td.data());
   // raw IMU samples of every interval -> device preintegration (IntegrationBase::push_back chain)
@@ -478,6 +486,7 @@ void Estimator::optimization() {
       double* b6 = &bias[(j - 1) * 6]; b6[0] = pi->linearized_ba.x; b6[1] = pi->linearized_ba.y; b6[2] = pi->linearized_ba.z; b6[3] = pi->linearized_bg.x; b6[4] = pi->linearized_bg.y; b6[5] = pi->linearized_bg.z;
     }
     const double noise[4] = {P.ACC_N, P.GYR_N, P.ACC_W, P.GYR_W};
+    if (capture) { cap.imu_samples = smp; cap.imu_n = ns; cap.imu_first = first; cap.imu_bias = bias; }
     rc = gf2_imu_preintegrate(gf2, 0, 1, smp.data(), ns.data(), first.data(), bias.data(), noise);
   }
   // raw wheel samples of every interval -> device preintegration (WheelIntegrationBase::push_back chain), estimator.cpp:3181-3212
@@ -508,6 +517,7 @@ void Estimator::optimization() {
     std::vector<gf2_prior_block> blocks(2 * F + 8); memset(blocks.data(), 0, sizeof(gf2_prior_block) * blocks.size());
     for (int r = 0; r < rows; r++) { r0[r] = mp.linearized_residuals[r]; for (int c = 0; c < rows; c++) J0[(size_t)r * GF2_MAX_PRIOR_DIM + c] = mp.linearized_jacobians[(size_t)r * rows + c]; }
     for (int b = 0; b < nb && b < (int)blocks.size(); b++) blocks[b] = mp.blocks[b];
+    if (capture) { cap.prior_rows = rows; cap.prior_nblocks = rows > 0 ? nb : 0; cap.prior_J0 = J0; cap.prior_r0 = r0; cap.prior_blocks = blocks; }
     rc = gf2_set_prior(gf2, 0, 1, &rows, J0.data(), r0.data(), &nb, blocks.data());
   }
   if (rc == GF2_OK) {
@@ -523,12 +533,14 @@ void Estimator::optimization() {
     if ((wheel_on && P.ESTIMATE_INTRINSIC_WHEEL && frame_count == WINDOW_SIZE && v0 > 0.2) || openIxEstimation) openIxEstimation = true; else o.const_mask |= GF2_CONST_WHEEL_INTRINSIC;
     if (!P.ESTIMATE_TD_WHEEL || v0 < 0.2) o.const_mask |= GF2_CONST_TD_WHEEL;
     o.max_time_s = 0;  // SOLVER_TIME is a wall-clock cap: machine dependent, not reproduced
+    if (capture) { cap.const_mask = o.const_mask; cap.marg_mode = marginalization_flag == MARGIN_OLD ? 0 : 1; }
     rc = gf2_solve(gf2, 0, 1, &o, &last_summary);
   }
   if (rc == GF2_OK) rc = gf2_get_states(gf2, 0, 1, &para_Pose[0][0], &para_SpeedBias[0][0], para_Ex_Pose[0], para_Td[0], wheel_on ? para_Ex_Pose_wheel[0] : nullptr, wheel_on ? sxsysw : nullptr, wheel_on ? para_Td_wheel[0] : nullptr);
   if (rc == GF2_OK) { rc = gf2_get_landmarks(gf2, 0, 1, invdep.data()); for (int i = 0; i < n_lm; i++) para_Feature[i][0] = invdep[i]; }
   if (rc != GF2_OK) { last_error = gf2_last_error(); return; }  // the reference logs and carries on (no exceptions)
   if (wheel_on) { para_Ix_sx_wheel[0][0] = sxsysw[0]; para_Ix_sy_wheel[0][0] = sxsysw[1]; para_Ix_sw_wheel[0][0] = sxsysw[2]; }
+  if (capture) { memcpy(cap.pose_out, para_Pose, sizeof(cap.pose_out)); memcpy(cap.sb_out, para_SpeedBias, sizeof(cap.sb_out)); cap.invdep_out.assign(invdep.begin(), invdep.begin() + n_lm); }
   double2vector();
 
   // ---- marginalization (estimator.cpp:3394-3690): runs at the states double2vector() left (yaw / position re-anchored),
@@ -536,6 +548,7 @@ void Estimator::optimization() {
   vector2double();
   for (int i = 0; i < n_lm; i++) invdep[i] = para_Feature[i][0];
   sxsysw[0] = para_Ix_sx_wheel[0][0]; sxsysw[1] = para_Ix_sy_wheel[0][0]; sxsysw[2] = para_Ix_sw_wheel[0][0];
+  if (capture) { memcpy(cap.pose_marg, para_Pose, sizeof(cap.pose_marg)); memcpy(cap.sb_marg, para_SpeedBias, sizeof(cap.sb_marg)); cap.invdep_marg.assign(invdep.begin(), invdep.begin() + n_lm); }
   rc = gf2_set_states(gf2, 0, 1, &para_Pose[0][0], &para_SpeedBias[0][0], para_Ex_Pose[0], para_Td[0], wheel_on ? para_Ex_Pose_wheel[0] : nullptr, wheel_on ? sxsysw : nullptr, wheel_on ? para_Td_wheel[0] : nullptr);
   if (rc == GF2_OK) rc = gf2_set_landmarks(gf2, 0, 1, &n_lm, invdep.data(), start.data(), len.data(), fixed.data(), obs.data(), frame_td.data());
   int32_t st = 0, m = 0;
@@ -1014,6 +1027,30 @@ int gf2h_interval_samples(void* e, int j, int wheel, int max_n, double* dt) {   
   if (!b) return -1;
   for (size_t i = 0; i < b->size() && (int)i < max_n; i++) dt[i] = (*b)[i];
   return (int)b->size();
+}
+void gf2h_set_imu0(void* e, const double* acc, const double* gyr) {   // the sample the next interval starts from (acc_0 / gyr_0 of processIMU)
+  Estimator* E = (Estimator*)e; E->first_imu = true; E->acc_0 = {acc[0], acc[1], acc[2]}; E->gyr_0 = {gyr[0], gyr[1], gyr[2]};
+}
+void gf2h_set_capture(void* e, int on) { ((Estimator*)e)->capture = on != 0; }
+// sizes: [n_lm, n_obs, prior_rows, prior_nblocks, const_mask, marg_mode]
+void gf2h_capture_sizes(void* e, int* s6) {
+  const Estimator::Capture& c = ((Estimator*)e)->cap;
+  s6[0] = c.n_lm; s6[1] = (int)c.obs.size(); s6[2] = c.prior_rows; s6[3] = c.prior_nblocks; s6[4] = (int)c.const_mask; s6[5] = c.marg_mode;
+}
+void gf2h_capture_get(void* e, double* pose, double* sb, double* ex_td8, double* frame_td, int32_t* start, int32_t* len, uint8_t* fixed, double* invdep, gf2_obs* obs,
+                      gf2_imu_sample* imu_samples /*[10][64]*/, int32_t* imu_n, double* imu_first, double* imu_bias, double* prior_J0 /* [96][96] */, double* prior_r0,
+                      gf2_prior_block* prior_blocks, double* pose_out, double* sb_out, double* invdep_out, double* pose_marg, double* sb_marg, double* invdep_marg) {
+  const Estimator::Capture& c = ((Estimator*)e)->cap;
+  memcpy(pose, c.pose, sizeof(c.pose)); memcpy(sb, c.sb, sizeof(c.sb)); memcpy(ex_td8, c.ex, sizeof(c.ex)); ex_td8[7] = c.td; memcpy(frame_td, c.frame_td, sizeof(c.frame_td));
+  for (int i = 0; i < c.n_lm; i++) { start[i] = c.start[i]; len[i] = c.len[i]; fixed[i] = c.fixed[i]; invdep[i] = c.invdep[i]; invdep_out[i] = c.invdep_out[i]; invdep_marg[i] = c.invdep_marg[i]; }
+  for (size_t i = 0; i < c.obs.size(); i++) obs[i] = c.obs[i];
+  for (size_t i = 0; i < c.imu_samples.size(); i++) imu_samples[i] = c.imu_samples[i];
+  for (size_t i = 0; i < c.imu_n.size(); i++) imu_n[i] = c.imu_n[i];
+  for (size_t i = 0; i < c.imu_first.size(); i++) { imu_first[i] = c.imu_first[i]; imu_bias[i] = c.imu_bias[i]; }
+  for (size_t i = 0; i < c.prior_J0.size(); i++) prior_J0[i] = c.prior_J0[i];
+  for (size_t i = 0; i < c.prior_r0.size(); i++) prior_r0[i] = c.prior_r0[i];
+  for (size_t i = 0; i < c.prior_blocks.size(); i++) prior_blocks[i] = c.prior_blocks[i];
+  memcpy(pose_out, c.pose_out, sizeof(c.pose_out)); memcpy(sb_out, c.sb_out, sizeof(c.sb_out)); memcpy(pose_marg, c.pose_marg, sizeof(c.pose_marg)); memcpy(sb_marg, c.sb_marg, sizeof(c.sb_marg));
 }
 int gf2h_process_image(void* e, int n, const int* ids, const double* pts8, double header) {
   Estimator* E = (Estimator*)e; E->processImage(image_of(n, ids, pts8), header);

@@ -159,6 +159,18 @@ class Estimator {
   void movingConsistencyCheckW(std::set<int>& removeIndex);    // :4030-4074
   void getPoseInWorldFrame(int index, double T[16]) const;     // :3901-3913 (row-major 4x4)
   std::map<int, Vector3d> predictPtsInNextFrame() const;       // :3915-3948 (the map handed to FeatureTracker::setPrediction)
+  // Test hook: when capture is set, optimization() keeps a copy of everything it hands to the C ABI and of what comes back, so that a
+  // replay can be checked step by step against the CPU oracle on identical inputs (tests/test_gpu_replay.py).
+  struct Capture {
+    double pose[(WINDOW_SIZE + 1) * 7], sb[(WINDOW_SIZE + 1) * 9], ex[7], td, frame_td[WINDOW_SIZE + 1];
+    int32_t n_lm = 0; std::vector<int32_t> start, len; std::vector<uint8_t> fixed; std::vector<double> invdep; std::vector<gf2_obs> obs;
+    std::vector<gf2_imu_sample> imu_samples; std::vector<int32_t> imu_n; std::vector<double> imu_first, imu_bias;
+    int32_t prior_rows = 0, prior_nblocks = 0; std::vector<double> prior_J0, prior_r0; std::vector<gf2_prior_block> prior_blocks;
+    uint32_t const_mask = 0; int32_t marg_mode = 0;
+    double pose_out[(WINDOW_SIZE + 1) * 7], sb_out[(WINDOW_SIZE + 1) * 9]; std::vector<double> invdep_out;   // straight from gf2_get_states / gf2_get_landmarks
+    double pose_marg[(WINDOW_SIZE + 1) * 7], sb_marg[(WINDOW_SIZE + 1) * 9]; std::vector<double> invdep_marg;  // the states gf2_marginalize ran at
+  };
+  bool capture = false; Capture cap;
   double Headers[WINDOW_SIZE + 1] = {0};
   Matrix3d back_R0; Vector3d back_P0;
   int sum_of_back = 0, sum_of_front = 0;

@@ -383,3 +383,61 @@ def lio_scene(seed=0, n_map_points=60000, n_keypoints=3000, size_voxel_map=0.2, 
     kp["alpha_time"] = rng.random(n_keypoints)
     return {"keys": keys, "n_points": n_points, "points": points, "keypoints": kp, "rotation": q, "translation": t,
             "translation_begin": t - np.array([0.05, 0.0, 0.0]), "size_voxel_map": size_voxel_map, "max_points_per_voxel": max_points_per_voxel}
+
+
+def feature_stream(seed=0, n_frames=45, target_features=150, speed=1.0, yaw_rate=0.2, frame_dt=0.1, imu_hz=200, pixel_noise=0.5,
+                   max_life=30, depth_range=(1.5, 12.0)):
+    """A synthetic stream for the steady-state replay (BASELINE.json config 5 shape, visual-inertial part): a planar arc like
+    make_windows, IMU samples at imu_hz with the m3dgr noise / bias, and per frame the feature map processImage receives:
+    id -> [x, y, 1, u, v, vx, vy, depth] (float32-representable x, y, velocities by finite difference, RGB-D depth below 4 m, 0 = invalid).
+    Landmarks are born in the current frustum whenever fewer than target_features are visible (what the detector would do), live at
+    most max_life frames and die when they leave the image. Returns a dict with frames, imu intervals and ground truth."""
+    rng = np.random.Generator(np.random.PCG64(BASE_SEED + 5000 + seed))
+    Ric = BODY_T_CAM0[:3, :3]; tic = BODY_T_CAM0[:3, 3]
+    n_imu = int(round(frame_dt * imu_hz)); dt = 1.0 / imu_hz
+    psi0 = 0.3; p0 = np.array([1.0, -2.0, 0.4])
+    ba = np.array([0.02, -0.01, 0.015]); bg = np.array([0.002, -0.001, 0.0015])
+    t_imu = np.arange(0, (n_frames - 1) * n_imu + 1) * dt
+    psi = psi0 + yaw_rate * t_imu
+    px = p0[0] + speed / yaw_rate * (np.sin(psi) - np.sin(psi0)); py = p0[1] - speed / yaw_rate * (np.cos(psi) - np.cos(psi0))
+    pos = np.stack([px, py, np.full_like(px, p0[2])], -1)
+    vel = np.stack([speed * np.cos(psi), speed * np.sin(psi), np.zeros_like(psi)], -1)
+    acc_w = np.stack([-speed * yaw_rate * np.sin(psi), speed * yaw_rate * np.cos(psi), np.zeros_like(psi)], -1)
+    Rwb = _heading_R(psi)
+    acc_b = np.einsum("nji,nj->ni", Rwb, acc_w + np.array([0, 0, G_NORM])) + ba + rng.normal(0, ACC_N, acc_w.shape)
+    gyr_b = np.tile(np.array([0.0, -yaw_rate, 0.0]), (len(psi), 1)) + bg + rng.normal(0, GYR_N, acc_w.shape)
+    fidx = np.arange(n_frames) * n_imu
+    gtR = Rwb[fidx]; gtp = pos[fidx]; gtv = vel[fidx]
+    Rwc = gtR @ Ric; twc = gtp + np.einsum("nij,j->ni", gtR, tic)
+    imu = []
+    for k in range(n_frames - 1):
+        s0 = fidx[k]
+        smp = np.zeros(n_imu, abi.IMU_SAMPLE); smp["dt"] = dt; smp["acc"] = acc_b[s0 + 1:s0 + 1 + n_imu]; smp["gyr"] = gyr_b[s0 + 1:s0 + 1 + n_imu]
+        imu.append({"first": np.concatenate([acc_b[s0], gyr_b[s0]]), "samples": smp})
+    lm = {}       # id -> (Xw, birth frame)
+    prev_xy = {}
+    next_id = 0
+    frames = []
+    for f in range(n_frames):
+        def project(X):
+            pc = (X - twc[f]) @ Rwc[f]
+            return pc, FX * pc[..., 0] / pc[..., 2] + CX, FY * pc[..., 1] / pc[..., 2] + CY
+        for i in list(lm):                                  # deaths: out of the image, too close / behind, too old
+            pc, u, v = project(lm[i][0])
+            if not (pc[2] > 0.5 and 5 < u < W_IMG - 5 and 5 < v < H_IMG - 5) or f - lm[i][1] >= max_life:
+                del lm[i]; prev_xy.pop(i, None)
+        while len(lm) < target_features:                    # births in the current frustum
+            u = rng.uniform(20, W_IMG - 20); v = rng.uniform(20, H_IMG - 20); d = rng.uniform(*depth_range)
+            lm[next_id] = (Rwc[f] @ np.array([(u - CX) / FX * d, (v - CY) / FY * d, d]) + twc[f], f); next_id += 1
+        ids = np.array(sorted(lm), np.int32)
+        pts = np.zeros((len(ids), 8))
+        for k, i in enumerate(ids):
+            pc, u, v = project(lm[i][0])
+            xn = np.float32(pc[0] / pc[2] + rng.normal(0, pixel_noise) / FX); yn = np.float32(pc[1] / pc[2] + rng.normal(0, pixel_noise) / FY)
+            vx, vy = (np.float32((xn - prev_xy[i][0]) / np.float32(frame_dt)), np.float32((yn - prev_xy[i][1]) / np.float32(frame_dt))) if i in prev_xy else (0.0, 0.0)
+            depth = pc[2] * (1.0 + rng.normal(0, 0.005)) if pc[2] < 4.0 else 0.0
+            pts[k] = [xn, yn, 1.0, FX * xn + CX, FY * yn + CY, vx, vy, depth]
+            prev_xy[i] = (xn, yn)
+        frames.append({"ids": ids, "pts": pts, "header": 100.0 + f * frame_dt})
+    return {"frames": frames, "imu": imu, "gt_p": gtp, "gt_R": gtR, "gt_v": gtv, "ba": ba, "bg": bg, "ric": Ric, "tic": tic,
+            "imu_noise": np.array([ACC_N, GYR_N, ACC_W, GYR_W]), "n_frames": n_frames, "landmarks_total": next_id}

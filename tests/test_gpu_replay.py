@@ -1,0 +1,112 @@
+"""Steady-state replay (first slice; BASELINE.json config 5 shape, visual-inertial part) through the C++ mirror's
+Estimator::processIMU / processImage: keyframe decision, depth initialisation, device solve + marginalization, outlier check, window slide,
+for a synthetic feature stream. Every step is checked against the CPU oracle on IDENTICAL inputs (the estimator's capture hook hands over
+what it sent to the C ABI and what came back), and the trajectory against ground truth."""
+import ctypes as C
+import importlib
+import time
+
+import numpy as np
+import pytest
+
+import host_py as H
+
+pytestmark = pytest.mark.gpu
+
+
+def _capture(L, e, abi):
+    s6 = np.zeros(6, np.int32); L.gf2h_capture_sizes(e, H.p(s6))
+    n_lm, n_obs, rows, nb, const_mask, marg_mode = [int(x) for x in s6]
+    c = dict(n_lm=n_lm, n_obs=n_obs, rows=rows, nb=nb, const_mask=const_mask, marg_mode=marg_mode,
+             pose=np.zeros((11, 7)), sb=np.zeros((11, 9)), ex_td=np.zeros(8), frame_td=np.zeros(11), start=np.zeros(max(n_lm, 1), np.int32), len=np.zeros(max(n_lm, 1), np.int32),
+             fixed=np.zeros(max(n_lm, 1), np.uint8), invdep=np.zeros(max(n_lm, 1)), obs=np.zeros(max(n_obs, 1), abi.OBS), imu_samples=np.zeros((10, 64), abi.IMU_SAMPLE),
+             imu_n=np.zeros(10, np.int32), imu_first=np.zeros((10, 6)), imu_bias=np.zeros((10, 6)), J0=np.zeros((96, 96)), r0=np.zeros(96), blocks=np.zeros(30, abi.PRIOR_BLOCK),
+             pose_out=np.zeros((11, 7)), sb_out=np.zeros((11, 9)), invdep_out=np.zeros(max(n_lm, 1)), pose_marg=np.zeros((11, 7)), sb_marg=np.zeros((11, 9)), invdep_marg=np.zeros(max(n_lm, 1)))
+    L.gf2h_capture_get(e, *[H.p(c[k]) for k in ("pose", "sb", "ex_td", "frame_td", "start", "len", "fixed", "invdep", "obs", "imu_samples", "imu_n", "imu_first", "imu_bias",
+                                                 "J0", "r0", "blocks", "pose_out", "sb_out", "invdep_out", "pose_marg", "sb_marg", "invdep_marg")])
+    return c
+
+
+def _oracle_window(c, noise, abi):
+    n, no = c["n_lm"], c["n_obs"]
+    Lm, Om = max(n, 1), max(no, 1)
+    w = {"n_frames": 11, "max_landmarks": Lm, "max_obs": Om, "para_pose": c["pose"][None].copy(), "para_speedbias": c["sb"][None].copy(), "ex_pose": c["ex_td"][None, :7].copy(),
+         "td": c["ex_td"][7:8].copy(), "inv_depth": c["invdep"][None].copy(), "n_landmarks": np.array([n], np.int32), "start_frame": c["start"][None].copy(),
+         "track_len": c["len"][None].copy(), "fixed": c["fixed"][None].copy(), "obs": c["obs"][None].copy(), "frame_td": c["frame_td"][None].copy(),
+         "imu_samples": c["imu_samples"][None].copy(), "imu_n": c["imu_n"][None].copy(), "imu_first": c["imu_first"][None].copy(), "imu_lin_bias": c["imu_bias"][None].copy(),
+         "imu_noise": noise, "prior_rows": np.array([c["rows"]], np.int32), "prior_J0": c["J0"][None].copy(), "prior_r0": c["r0"][None].copy(),
+         "prior_nblocks": np.array([c["nb"]], np.int32), "prior_blocks": c["blocks"][None].copy()}
+    return w
+
+
+def test_steady_state_replay_matches_oracle_step_by_step(gf2, oracle):
+    synth = importlib.import_module("gf2_b200.synth")
+    abi = gf2.abi
+    L = H.lib()
+    st = synth.feature_stream(0, n_frames=34)
+    e = C.c_void_p(L.gf2h_estimator_create())
+    L.gf2h_set_extrinsic(e, H.p(st["tic"].copy()), H.p(st["ric"].copy()), C.c_double(0.0), C.c_double(synth.G_NORM), H.p(st["imu_noise"]))
+    L.gf2h_set_flags(e, 1, 0, 1, 0)                       # IMU, no wheel, RGB-D depth initialisation, moving-consistency check after the solve
+    L.gf2h_set_min_parallax(e, C.c_double(10.0 / 460.0))
+    rng = np.random.default_rng(1)
+    P = st["gt_p"][:11].copy() + rng.normal(0, 0.01, (11, 3)); R = st["gt_R"][:11].copy(); V = st["gt_v"][:11].copy()
+    P[10] = P[9]; R[10] = R[9]; V[10] = V[9]              # what slideWindow leaves in the newest slot (estimator.cpp:3746-3754)
+    L.gf2h_set_frame_states(e, H.p(H.frame_states(P, R, V, np.zeros((11, 3)), np.zeros((11, 3)))))
+    for f in range(10):
+        fr = st["frames"][f]
+        L.gf2h_add_image(e, f, len(fr["ids"]), H.p(fr["ids"]), H.p(fr["pts"]), C.c_double(0.0))
+    for j in range(1, 10):
+        iv = st["imu"][j - 1]
+        L.gf2h_new_interval(e, j, H.p(iv["first"][:3].copy()), H.p(iv["first"][3:].copy()), H.p(np.zeros(3)), H.p(np.zeros(3)))
+        for s in iv["samples"]:
+            L.gf2h_push_imu(e, j, C.c_double(s["dt"]), H.p(s["acc"].copy()), H.p(s["gyr"].copy()))
+    L.gf2h_set_imu0(e, H.p(st["imu"][9]["first"][:3].copy()), H.p(st["imu"][9]["first"][3:].copy()))
+    pose = np.zeros((11, 7)); sbv = np.zeros((11, 9)); exv = np.zeros(7)
+    L.gf2h_vector2double(e, H.p(pose), H.p(sbv), H.p(exv))
+    blk = np.zeros(1, abi.PRIOR_BLOCK); blk["kind"] = abi.BLK_POSE; blk["x0"][0, :7] = pose[0]
+    L.gf2h_set_prior(e, 6, H.p(np.eye(6) * 100.0), H.p(np.zeros(6)), 1, H.p(blk))      # anchor on the oldest pose until the first marginalization
+    L.gf2h_set_capture(e, 1)
+    flags, errs, worst = [], [], 0.0
+    t_proc = 0.0
+    for k in range(10, st["n_frames"]):
+        for s in st["imu"][k - 1]["samples"]:
+            L.gf2h_process_imu(e, C.c_double(0.0), C.c_double(s["dt"]), H.p(s["acc"].copy()), H.p(s["gyr"].copy()))
+        fr = st["frames"][k]
+        t0 = time.perf_counter()
+        flag = L.gf2h_process_image(e, len(fr["ids"]), H.p(fr["ids"]), H.p(fr["pts"]), C.c_double(fr["header"]))
+        t_proc += time.perf_counter() - t0
+        assert flag >= 0, L.gf2h_last_error(e)
+        flags.append(flag)
+        # ---- this step against the oracle on identical inputs
+        c = _capture(L, e, abi)
+        assert c["n_lm"] > 50 and c["marg_mode"] == flag
+        opts = abi.default_opts(const_mask=c["const_mask"])
+        w = _oracle_window(c, st["imu_noise"], abi)
+        oracle.imu_preintegrate(w)
+        oracle.solve_batch(w, opts)
+        scale = np.abs(w["para_pose"][0, :, :3]).max()
+        d_pos = np.abs(c["pose_out"][:, :3] - w["para_pose"][0, :, :3]).max() / scale
+        d_rot = np.abs(c["pose_out"][:, 3:] - w["para_pose"][0, :, 3:]).max()
+        worst = max(worst, d_pos, d_rot)
+        assert d_pos <= 1e-4 and d_rot <= 1e-4, (k, d_pos, d_rot)                      # BASELINE.json tolerance on pose states
+        assert np.abs(c["sb_out"] - w["para_speedbias"][0]).max() <= 1e-4 * max(1.0, np.abs(w["para_speedbias"]).max())
+        # marginalization at the states the estimator used
+        wm = _oracle_window(c, st["imu_noise"], abi)
+        wm["para_pose"][0] = c["pose_marg"]; wm["para_speedbias"][0] = c["sb_marg"]; wm["inv_depth"][0, :c["n_lm"]] = c["invdep_marg"][:c["n_lm"]]
+        oracle.imu_preintegrate(wm)
+        ref = oracle.marginalize_window(wm, 0, opts, mode=flag)
+        nn = C.c_int(0); nb = C.c_int(0); stt = C.c_int(0)
+        J0 = np.zeros(96 * 96); r0 = np.zeros(96); blocks = np.zeros(30, abi.PRIOR_BLOCK)
+        L.gf2h_get_prior(e, C.byref(nn), H.p(J0), H.p(r0), C.byref(nb), H.p(blocks), C.byref(stt))
+        assert stt.value == ref["status"], (k, stt.value, ref["status"])
+        if ref["status"] == 0:
+            got = {"n": nn.value, "J0": J0[:nn.value ** 2].reshape(nn.value, nn.value), "r0": r0[:nn.value], "blocks": blocks[:nb.value]}
+            Hg, gg, _ = oracle.prior_information(got, 11); Hr, gr, _ = oracle.prior_information(ref, 11)
+            assert got["n"] == ref["n"] and np.abs(Hg - Hr).max() <= 1e-7 * np.abs(Hr).max(), (k, np.abs(Hg - Hr).max() / np.abs(Hr).max())
+        # ---- trajectory against ground truth: the newest frame sits at index 9 after the slide
+        out = np.zeros((11, 21)); L.gf2h_get_frame_states(e, H.p(out))
+        errs.append(np.linalg.norm(out[9, :3] - st["gt_p"][k]))
+    assert 0 in flags                                                                   # keyframes happened (MARGIN_OLD)
+    assert max(errs) < 0.15 and np.mean(errs[-10:]) < 0.10, (max(errs), errs[-10:])     # no drift blow-up over the replay (1 m/s, 0.5 px noise)
+    print(f"replay: {len(flags)} frames, {flags.count(0)} keyframes, {len(flags) / t_proc:.1f} frames/s through processImage, max position error {max(errs):.3f} m, worst oracle deviation {worst:.2e}")
+    L.gf2h_estimator_destroy(e)
