@@ -6,6 +6,7 @@
 #include <cstdlib>
 
 namespace gf2host {
+constexpr int kMaxImuSamples = 256;   // per preintegration interval (MARGIN_SECOND_NEW merges intervals)
 
 // ------------------------------------------------------------------------------------------------ small math
 Matrix3d mul(const Matrix3d& a, const Matrix3d& b) {
@@ -440,7 +441,7 @@ void Estimator::optimization() {
   if (!gf2) {
     gf2_solver_cfg cfg; memset(&cfg, 0, sizeof(cfg));
     cfg.device = 0; cfg.max_windows = 1; cfg.n_frames = WINDOW_SIZE + 1; cfg.max_landmarks = NUM_OF_F; cfg.max_obs = NUM_OF_F * (WINDOW_SIZE + 1);
-    cfg.max_imu_samples = 64; cfg.max_prior_rows = GF2_MAX_PRIOR_DIM;
+    cfg.max_imu_samples = kMaxImuSamples; cfg.max_prior_rows = GF2_MAX_PRIOR_DIM;
     cfg.use_wheel = (P.USE_WHEEL && !P.ONLY_INITIAL_WITH_WHEEL) ? 1 : 0; cfg.max_wheel_samples = cfg.use_wheel ? 32 : 0;
     if (gf2_solver_create(&cfg, &gf2) != GF2_OK) { last_error = gf2_last_error(); gf2 = nullptr; return; }
   }
@@ -475,13 +476,14 @@ void Estimator::optimization() {
   if (rc == GF2_OK) rc = gf2_set_landmarks(gf2, 0, 1, &n_lm, invdep.data(), start.data(), len.data(), fixed.data(), obs.data(), frame_td.data());
   // raw IMU samples of every interval -> device preintegration (IntegrationBase::push_back chain)
   if (rc == GF2_OK && P.USE_IMU) {
-    std::vector<gf2_imu_sample> smp((size_t)(F - 1) * 64); std::vector<int32_t> ns(F - 1, 0); std::vector<double> first((F - 1) * 6, 0.0), bias((F - 1) * 6, 0.0);
+    std::vector<gf2_imu_sample> smp((size_t)(F - 1) * kMaxImuSamples); std::vector<int32_t> ns(F - 1, 0); std::vector<double> first((F - 1) * 6, 0.0), bias((F - 1) * 6, 0.0);
     for (int j = 1; j < F; j++) {
       const IntegrationBase* pi = pre_integrations[j];
       if (!pi) { last_error = "pre_integrations[j] missing"; return; }
-      const int n = (int)std::min<size_t>(pi->dt_buf.size(), 64);
+      if (pi->dt_buf.size() > (size_t)kMaxImuSamples) { last_error = "an IMU interval holds more samples than the device buffer (kMaxImuSamples)"; return; }
+      const int n = (int)pi->dt_buf.size();
       ns[j - 1] = n;
-      for (int s = 0; s < n; s++) { gf2_imu_sample& o = smp[(size_t)(j - 1) * 64 + s]; o.dt = pi->dt_buf[s]; o.acc[0] = pi->acc_buf[s].x; o.acc[1] = pi->acc_buf[s].y; o.acc[2] = pi->acc_buf[s].z; o.gyr[0] = pi->gyr_buf[s].x; o.gyr[1] = pi->gyr_buf[s].y; o.gyr[2] = pi->gyr_buf[s].z; }
+      for (int s = 0; s < n; s++) { gf2_imu_sample& o = smp[(size_t)(j - 1) * kMaxImuSamples + s]; o.dt = pi->dt_buf[s]; o.acc[0] = pi->acc_buf[s].x; o.acc[1] = pi->acc_buf[s].y; o.acc[2] = pi->acc_buf[s].z; o.gyr[0] = pi->gyr_buf[s].x; o.gyr[1] = pi->gyr_buf[s].y; o.gyr[2] = pi->gyr_buf[s].z; }
       double* f6 = &first[(j - 1) * 6]; f6[0] = pi->linearized_acc.x; f6[1] = pi->linearized_acc.y; f6[2] = pi->linearized_acc.z; f6[3] = pi->linearized_gyr.x; f6[4] = pi->linearized_gyr.y; f6[5] = pi->linearized_gyr.z;
       double* b6 = &bias[(j - 1) * 6]; b6[0] = pi->linearized_ba.x; b6[1] = pi->linearized_ba.y; b6[2] = pi->linearized_ba.z; b6[3] = pi->linearized_bg.x; b6[4] = pi->linearized_bg.y; b6[5] = pi->linearized_bg.z;
     }
@@ -1038,7 +1040,7 @@ void gf2h_capture_sizes(void* e, int* s6) {
   s6[0] = c.n_lm; s6[1] = (int)c.obs.size(); s6[2] = c.prior_rows; s6[3] = c.prior_nblocks; s6[4] = (int)c.const_mask; s6[5] = c.marg_mode;
 }
 void gf2h_capture_get(void* e, double* pose, double* sb, double* ex_td8, double* frame_td, int32_t* start, int32_t* len, uint8_t* fixed, double* invdep, gf2_obs* obs,
-                      gf2_imu_sample* imu_samples /*[10][64]*/, int32_t* imu_n, double* imu_first, double* imu_bias, double* prior_J0 /* [96][96] */, double* prior_r0,
+                      gf2_imu_sample* imu_samples /*[10][kMaxImuSamples]*/, int32_t* imu_n, double* imu_first, double* imu_bias, double* prior_J0 /* [96][96] */, double* prior_r0,
                       gf2_prior_block* prior_blocks, double* pose_out, double* sb_out, double* invdep_out, double* pose_marg, double* sb_marg, double* invdep_marg) {
   const Estimator::Capture& c = ((Estimator*)e)->cap;
   memcpy(pose, c.pose, sizeof(c.pose)); memcpy(sb, c.sb, sizeof(c.sb)); memcpy(ex_td8, c.ex, sizeof(c.ex)); ex_td8[7] = c.td; memcpy(frame_td, c.frame_td, sizeof(c.frame_td));

@@ -19,7 +19,7 @@ def _capture(L, e, abi):
     n_lm, n_obs, rows, nb, const_mask, marg_mode = [int(x) for x in s6]
     c = dict(n_lm=n_lm, n_obs=n_obs, rows=rows, nb=nb, const_mask=const_mask, marg_mode=marg_mode,
              pose=np.zeros((11, 7)), sb=np.zeros((11, 9)), ex_td=np.zeros(8), frame_td=np.zeros(11), start=np.zeros(max(n_lm, 1), np.int32), len=np.zeros(max(n_lm, 1), np.int32),
-             fixed=np.zeros(max(n_lm, 1), np.uint8), invdep=np.zeros(max(n_lm, 1)), obs=np.zeros(max(n_obs, 1), abi.OBS), imu_samples=np.zeros((10, 64), abi.IMU_SAMPLE),
+             fixed=np.zeros(max(n_lm, 1), np.uint8), invdep=np.zeros(max(n_lm, 1)), obs=np.zeros(max(n_obs, 1), abi.OBS), imu_samples=np.zeros((10, 256), abi.IMU_SAMPLE),
              imu_n=np.zeros(10, np.int32), imu_first=np.zeros((10, 6)), imu_bias=np.zeros((10, 6)), J0=np.zeros((96, 96)), r0=np.zeros(96), blocks=np.zeros(30, abi.PRIOR_BLOCK),
              pose_out=np.zeros((11, 7)), sb_out=np.zeros((11, 9)), invdep_out=np.zeros(max(n_lm, 1)), pose_marg=np.zeros((11, 7)), sb_marg=np.zeros((11, 9)), invdep_marg=np.zeros(max(n_lm, 1)))
     L.gf2h_capture_get(e, *[H.p(c[k]) for k in ("pose", "sb", "ex_td", "frame_td", "start", "len", "fixed", "invdep", "obs", "imu_samples", "imu_n", "imu_first", "imu_bias",
