@@ -386,11 +386,12 @@ def lio_scene(seed=0, n_map_points=60000, n_keypoints=3000, size_voxel_map=0.2, 
 
 
 def feature_stream(seed=0, n_frames=45, target_features=150, speed=1.0, yaw_rate=0.2, frame_dt=0.1, imu_hz=200, pixel_noise=0.5,
-                   max_life=30, depth_range=(1.5, 12.0)):
+                   max_life=30, depth_range=(1.5, 12.0), pause=None):
     """A synthetic stream for the steady-state replay (BASELINE.json config 5 shape, visual-inertial part): a planar arc like
     make_windows, IMU samples at imu_hz with the m3dgr noise / bias, and per frame the feature map processImage receives:
     id -> [x, y, 1, u, v, vx, vy, depth] (float32-representable x, y, velocities by finite difference, RGB-D depth below 4 m, 0 = invalid).
-    Landmarks are born in the current frustum whenever fewer than target_features are visible (what the detector would do), live at
+    pause = (first_frame, last_frame): the robot brakes to a stop and starts again (cosine ramps of 3 frames), which produces the
+    low-parallax frames that make the estimator marginalize the second newest frame. Landmarks are born in the current frustum whenever fewer than target_features are visible (what the detector would do), live at
     most max_life frames and die when they leave the image. Returns a dict with frames, imu intervals and ground truth."""
     rng = np.random.Generator(np.random.PCG64(BASE_SEED + 5000 + seed))
     Ric = BODY_T_CAM0[:3, :3]; tic = BODY_T_CAM0[:3, 3]
@@ -398,14 +399,26 @@ def feature_stream(seed=0, n_frames=45, target_features=150, speed=1.0, yaw_rate
     psi0 = 0.3; p0 = np.array([1.0, -2.0, 0.4])
     ba = np.array([0.02, -0.01, 0.015]); bg = np.array([0.002, -0.001, 0.0015])
     t_imu = np.arange(0, (n_frames - 1) * n_imu + 1) * dt
-    psi = psi0 + yaw_rate * t_imu
-    px = p0[0] + speed / yaw_rate * (np.sin(psi) - np.sin(psi0)); py = p0[1] - speed / yaw_rate * (np.cos(psi) - np.cos(psi0))
+    # speed profile v(t) = speed * g(t) along a circular arc of curvature kappa = yaw_rate / speed (arc length s = integral of v)
+    g = np.ones_like(t_imu); gd = np.zeros_like(t_imu)
+    if pause is not None:
+        ramp = 3 * frame_dt; t1, t2 = pause[0] * frame_dt, pause[1] * frame_dt
+        down = (t_imu >= t1 - ramp) & (t_imu < t1); up = (t_imu > t2) & (t_imu <= t2 + ramp)
+        g[down] = 0.5 * (1 + np.cos(np.pi * (t_imu[down] - (t1 - ramp)) / ramp)); gd[down] = -0.5 * np.pi / ramp * np.sin(np.pi * (t_imu[down] - (t1 - ramp)) / ramp)
+        g[up] = 0.5 * (1 - np.cos(np.pi * (t_imu[up] - t2) / ramp)); gd[up] = 0.5 * np.pi / ramp * np.sin(np.pi * (t_imu[up] - t2) / ramp)
+        g[(t_imu >= t1) & (t_imu <= t2)] = 0.0
+    kappa = yaw_rate / speed
+    v_t = speed * g
+    s_arc = np.concatenate([[0.0], np.cumsum(0.5 * (v_t[1:] + v_t[:-1]) * dt)])
+    psi = psi0 + kappa * s_arc
+    px = p0[0] + (np.sin(psi) - np.sin(psi0)) / kappa; py = p0[1] - (np.cos(psi) - np.cos(psi0)) / kappa
     pos = np.stack([px, py, np.full_like(px, p0[2])], -1)
-    vel = np.stack([speed * np.cos(psi), speed * np.sin(psi), np.zeros_like(psi)], -1)
-    acc_w = np.stack([-speed * yaw_rate * np.sin(psi), speed * yaw_rate * np.cos(psi), np.zeros_like(psi)], -1)
+    tang = np.stack([np.cos(psi), np.sin(psi), np.zeros_like(psi)], -1); nrm_ = np.stack([-np.sin(psi), np.cos(psi), np.zeros_like(psi)], -1)
+    vel = v_t[:, None] * tang
+    acc_w = (speed * gd)[:, None] * tang + (v_t * v_t * kappa)[:, None] * nrm_
     Rwb = _heading_R(psi)
     acc_b = np.einsum("nji,nj->ni", Rwb, acc_w + np.array([0, 0, G_NORM])) + ba + rng.normal(0, ACC_N, acc_w.shape)
-    gyr_b = np.tile(np.array([0.0, -yaw_rate, 0.0]), (len(psi), 1)) + bg + rng.normal(0, GYR_N, acc_w.shape)
+    gyr_b = np.stack([np.zeros_like(psi), -kappa * v_t, np.zeros_like(psi)], -1) + bg + rng.normal(0, GYR_N, acc_w.shape)
     fidx = np.arange(n_frames) * n_imu
     gtR = Rwb[fidx]; gtp = pos[fidx]; gtv = vel[fidx]
     Rwc = gtR @ Ric; twc = gtp + np.einsum("nij,j->ni", gtR, tic)

@@ -43,7 +43,7 @@ def test_steady_state_replay_matches_oracle_step_by_step(gf2, oracle):
     synth = importlib.import_module("gf2_b200.synth")
     abi = gf2.abi
     L = H.lib()
-    st = synth.feature_stream(0, n_frames=34)
+    st = synth.feature_stream(0, n_frames=38, pause=(20, 24))     # the robot stops for a few frames: MARGIN_SECOND_NEW steps
     e = C.c_void_p(L.gf2h_estimator_create())
     L.gf2h_set_extrinsic(e, H.p(st["tic"].copy()), H.p(st["ric"].copy()), C.c_double(0.0), C.c_double(synth.G_NORM), H.p(st["imu_noise"]))
     L.gf2h_set_flags(e, 1, 0, 1, 0)                       # IMU, no wheel, RGB-D depth initialisation, moving-consistency check after the solve
@@ -67,14 +67,14 @@ def test_steady_state_replay_matches_oracle_step_by_step(gf2, oracle):
     L.gf2h_set_prior(e, 6, H.p(np.eye(6) * 100.0), H.p(np.zeros(6)), 1, H.p(blk))      # anchor on the oldest pose until the first marginalization
     L.gf2h_set_capture(e, 1)
     flags, errs, worst = [], [], 0.0
-    t_proc = 0.0
+    t_steps = []
     for k in range(10, st["n_frames"]):
         for s in st["imu"][k - 1]["samples"]:
             L.gf2h_process_imu(e, C.c_double(0.0), C.c_double(s["dt"]), H.p(s["acc"].copy()), H.p(s["gyr"].copy()))
         fr = st["frames"][k]
         t0 = time.perf_counter()
         flag = L.gf2h_process_image(e, len(fr["ids"]), H.p(fr["ids"]), H.p(fr["pts"]), C.c_double(fr["header"]))
-        t_proc += time.perf_counter() - t0
+        t_steps.append(time.perf_counter() - t0)
         assert flag >= 0, L.gf2h_last_error(e)
         flags.append(flag)
         # ---- this step against the oracle on identical inputs
@@ -106,7 +106,8 @@ def test_steady_state_replay_matches_oracle_step_by_step(gf2, oracle):
         # ---- trajectory against ground truth: the newest frame sits at index 9 after the slide
         out = np.zeros((11, 21)); L.gf2h_get_frame_states(e, H.p(out))
         errs.append(np.linalg.norm(out[9, :3] - st["gt_p"][k]))
-    assert 0 in flags                                                                   # keyframes happened (MARGIN_OLD)
+    assert 0 in flags and 1 in flags                                                    # both MARGIN_OLD and MARGIN_SECOND_NEW steps happened
     assert max(errs) < 0.15 and np.mean(errs[-10:]) < 0.10, (max(errs), errs[-10:])     # no drift blow-up over the replay (1 m/s, 0.5 px noise)
-    print(f"replay: {len(flags)} frames, {flags.count(0)} keyframes, {len(flags) / t_proc:.1f} frames/s through processImage, max position error {max(errs):.3f} m, worst oracle deviation {worst:.2e}")
+    print(f"replay: {len(flags)} frames, {flags.count(0)} keyframes, first processImage {t_steps[0] * 1e3:.1f} ms (handle creation), then median {np.median(t_steps[1:]) * 1e3:.2f} ms "
+          f"= {1.0 / np.median(t_steps[1:]):.0f} frames/s, max position error {max(errs):.3f} m, worst oracle deviation {worst:.2e}")
     L.gf2h_estimator_destroy(e)
