@@ -250,6 +250,58 @@ def run_lio(gf2, synth, steps=10, with_cpu=True):
     return line
 
 
+def run_replay(gf2, synth, with_cpu=True):
+    """BASELINE.json config 5 shape, visual-inertial part: a synthetic feature + IMU stream through the C++ mirror's
+    Estimator::processIMU / processImage (keyframe decision, depth initialisation, device solve + marginalization, outlier check, slide),
+    one window at a time as the reference's node runs it: a LATENCY figure (frames/s of one robot), not a batched throughput."""
+    import ctypes as C
+    L = C.CDLL(os.path.join(ROOT, "ground-fusion2_b200", "libgf2_host.so"))
+    L.gf2h_estimator_create.restype = C.c_void_p; L.gf2h_last_error.restype = C.c_char_p
+    P_ = lambda a: np.ascontiguousarray(a).ctypes.data_as(C.c_void_p)
+    st = synth.feature_stream(1, n_frames=70, pause=(30, 34))
+    e = C.c_void_p(L.gf2h_estimator_create())
+    L.gf2h_set_extrinsic(e, P_(st["tic"].copy()), P_(st["ric"].copy()), C.c_double(0.0), C.c_double(synth.G_NORM), P_(st["imu_noise"]))
+    L.gf2h_set_flags(e, 1, 0, 1, 0); L.gf2h_set_min_parallax(e, C.c_double(10.0 / 460.0))
+    Pp = st["gt_p"][:11].copy(); R = st["gt_R"][:11].copy(); V = st["gt_v"][:11].copy(); Pp[10] = Pp[9]; R[10] = R[9]; V[10] = V[9]
+    fs = np.zeros((11, 21)); fs[:, 0:3] = Pp; fs[:, 3:12] = R.reshape(11, 9); fs[:, 12:15] = V
+    L.gf2h_set_frame_states(e, P_(fs))
+    for f in range(10):
+        fr = st["frames"][f]; L.gf2h_add_image(e, f, len(fr["ids"]), P_(fr["ids"]), P_(fr["pts"]), C.c_double(0.0))
+    for j in range(1, 10):
+        iv = st["imu"][j - 1]
+        L.gf2h_new_interval(e, j, P_(iv["first"][:3].copy()), P_(iv["first"][3:].copy()), P_(np.zeros(3)), P_(np.zeros(3)))
+        for s_ in iv["samples"]:
+            L.gf2h_push_imu(e, j, C.c_double(s_["dt"]), P_(s_["acc"].copy()), P_(s_["gyr"].copy()))
+    L.gf2h_set_imu0(e, P_(st["imu"][9]["first"][:3].copy()), P_(st["imu"][9]["first"][3:].copy()))
+    pose = np.zeros((11, 7)); sbv = np.zeros((11, 9)); exv = np.zeros(7); L.gf2h_vector2double(e, P_(pose), P_(sbv), P_(exv))
+    blk = np.zeros(1, gf2.abi.PRIOR_BLOCK); blk["kind"] = gf2.abi.BLK_POSE; blk["x0"][0, :7] = pose[0]
+    L.gf2h_set_prior(e, 6, P_(np.eye(6) * 100.0), P_(np.zeros(6)), 1, P_(blk))
+    steps, flags, errs = [], [], []
+    for k in range(10, st["n_frames"]):
+        for s_ in st["imu"][k - 1]["samples"]:
+            L.gf2h_process_imu(e, C.c_double(0.0), C.c_double(s_["dt"]), P_(s_["acc"].copy()), P_(s_["gyr"].copy()))
+        fr = st["frames"][k]
+        t0 = time.perf_counter()
+        flag = L.gf2h_process_image(e, len(fr["ids"]), P_(fr["ids"]), P_(fr["pts"]), C.c_double(fr["header"]))
+        steps.append(time.perf_counter() - t0)
+        if flag < 0:
+            raise RuntimeError("replay: " + L.gf2h_last_error(e).decode())
+        flags.append(flag)
+        out = np.zeros((11, 21)); L.gf2h_get_frame_states(e, P_(out)); errs.append(float(np.linalg.norm(out[9, :3] - st["gt_p"][k])))
+    L.gf2h_estimator_destroy(e)
+    med = float(np.median(steps[1:]))
+    line = {"metric": "replay frames/sec through Estimator::processImage (one window at a time: single-robot latency)", "value": 1.0 / med, "unit": "frames/s",
+            "frames": len(flags), "keyframes": flags.count(0), "median_ms_per_frame": med * 1e3, "first_frame_ms": steps[0] * 1e3,
+            "max_position_error_m": max(errs), "features_per_frame": 150}
+    if with_cpu:
+        import gf2_oracle as orc
+        w = synth.make_windows(1, n_landmarks=150)
+        orc.imu_preintegrate(w)
+        t0 = time.perf_counter(); orc.solve_batch(w, gf2.abi.default_opts()); orc.marginalize_window(w, 0, gf2.abi.default_opts(), mode=0); dt_ = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": 1.0 / dt_, "unit": "frames/s", "cores": 1, "kind": "port", "sample": "restated solve + marginalization of one 150-landmark window (the glue around them is negligible)"}
+    return line
+
+
 def run_reference(args, rank, world):
     """Restated-reference CPU baseline: oracle solve (same algorithm as ceres::Solve with the reference's options) on
     all host threads, each step a bounded sample of the same workload."""
@@ -451,9 +503,10 @@ def main():
     if rank == 0 and not args.no_lk:
         lk_line = run_lk(gf2, synth, streams=64, steps=10, cv2_seconds=0.0 if args.no_cpu_baseline else 2.0)
 
-    lio_line = None
+    lio_line = replay_line = None
     if rank == 0 and not args.no_lk:
         lio_line = run_lio(gf2, synth, steps=10, with_cpu=not args.no_cpu_baseline)
+        replay_line = run_replay(gf2, synth, with_cpu=not args.no_cpu_baseline)
 
     if rank == 0:
         peaks, which = measured_peaks()
@@ -476,7 +529,7 @@ def main():
                          "algorithmic_bytes_per_launch": BYTES_SWEEP * B, "avg_launch_ms": lin_avg_ms},
             "reduced_solve": {"kernels": "k_nonvis + k_solve2", "avg_ms_per_iteration": solve_ms / n_lin, "bound": "serial pivot chain (latency), not the tensor pipe",
                               "dmma_pipe_pct_ncu": NCU_DMMA_PCT, "source": "profiles/ncu_full_solver_kernels_B4096_r1.csv"},
-            "marginalize": marg, "lk": lk_line, "lio": lio_line,
+            "marginalize": marg, "lk": lk_line, "lio": lio_line, "replay": replay_line,
             "phase_ms_per_step": {"linearize": lin_ms / args.steps, "reduced_solve": solve_ms / args.steps, "backsub_candidate": step_ms / args.steps,
                                   "solve_total": total_ms / args.steps},
         }
