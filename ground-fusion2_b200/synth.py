@@ -385,15 +385,8 @@ def lio_scene(seed=0, n_map_points=60000, n_keypoints=3000, size_voxel_map=0.2, 
             "translation_begin": t - np.array([0.05, 0.0, 0.0]), "size_voxel_map": size_voxel_map, "max_points_per_voxel": max_points_per_voxel}
 
 
-def feature_stream(seed=0, n_frames=45, target_features=150, speed=1.0, yaw_rate=0.2, frame_dt=0.1, imu_hz=200, pixel_noise=0.5,
-                   max_life=30, depth_range=(1.5, 12.0), pause=None):
-    """A synthetic stream for the steady-state replay (BASELINE.json config 5 shape, visual-inertial part): a planar arc like
-    make_windows, IMU samples at imu_hz with the m3dgr noise / bias, and per frame the feature map processImage receives:
-    id -> [x, y, 1, u, v, vx, vy, depth] (float32-representable x, y, velocities by finite difference, RGB-D depth below 4 m, 0 = invalid).
-    pause = (first_frame, last_frame): the robot brakes to a stop and starts again (cosine ramps of 3 frames), which produces the
-    low-parallax frames that make the estimator marginalize the second newest frame. Landmarks are born in the current frustum whenever fewer than target_features are visible (what the detector would do), live at
-    most max_life frames and die when they leave the image. Returns a dict with frames, imu intervals and ground truth."""
-    rng = np.random.Generator(np.random.PCG64(BASE_SEED + 5000 + seed))
+def _arc_trajectory(rng, n_frames, speed, yaw_rate, frame_dt, imu_hz, pause):
+    """Ground truth of the replay streams: planar arc with an optional stop, IMU samples with the m3dgr noise / bias."""
     Ric = BODY_T_CAM0[:3, :3]; tic = BODY_T_CAM0[:3, 3]
     n_imu = int(round(frame_dt * imu_hz)); dt = 1.0 / imu_hz
     psi0 = 0.3; p0 = np.array([1.0, -2.0, 0.4])
@@ -427,6 +420,20 @@ def feature_stream(seed=0, n_frames=45, target_features=150, speed=1.0, yaw_rate
         s0 = fidx[k]
         smp = np.zeros(n_imu, abi.IMU_SAMPLE); smp["dt"] = dt; smp["acc"] = acc_b[s0 + 1:s0 + 1 + n_imu]; smp["gyr"] = gyr_b[s0 + 1:s0 + 1 + n_imu]
         imu.append({"first": np.concatenate([acc_b[s0], gyr_b[s0]]), "samples": smp})
+    return {"gtp": gtp, "gtR": gtR, "gtv": gtv, "Rwc": Rwc, "twc": twc, "imu": imu, "ba": ba, "bg": bg, "Ric": Ric, "tic": tic}
+
+
+def feature_stream(seed=0, n_frames=45, target_features=150, speed=1.0, yaw_rate=0.2, frame_dt=0.1, imu_hz=200, pixel_noise=0.5,
+                   max_life=30, depth_range=(1.5, 12.0), pause=None):
+    """A synthetic stream for the steady-state replay (BASELINE.json config 5 shape, visual-inertial part): a planar arc like
+    make_windows, IMU samples at imu_hz with the m3dgr noise / bias, and per frame the feature map processImage receives:
+    id -> [x, y, 1, u, v, vx, vy, depth] (float32-representable x, y, velocities by finite difference, RGB-D depth below 4 m, 0 = invalid).
+    pause = (first_frame, last_frame): the robot brakes to a stop and starts again (cosine ramps of 3 frames), which produces the
+    low-parallax frames that make the estimator marginalize the second newest frame. Landmarks are born in the current frustum whenever fewer than target_features are visible (what the detector would do), live at
+    most max_life frames and die when they leave the image. Returns a dict with frames, imu intervals and ground truth."""
+    rng = np.random.Generator(np.random.PCG64(BASE_SEED + 5000 + seed))
+    tr = _arc_trajectory(rng, n_frames, speed, yaw_rate, frame_dt, imu_hz, pause)
+    gtp, gtR, gtv, Rwc, twc, imu, ba, bg, Ric, tic = (tr[k] for k in ("gtp", "gtR", "gtv", "Rwc", "twc", "imu", "ba", "bg", "Ric", "tic"))
     lm = {}       # id -> (Xw, birth frame)
     prev_xy = {}
     next_id = 0
@@ -454,3 +461,47 @@ def feature_stream(seed=0, n_frames=45, target_features=150, speed=1.0, yaw_rate
         frames.append({"ids": ids, "pts": pts, "header": 100.0 + f * frame_dt})
     return {"frames": frames, "imu": imu, "gt_p": gtp, "gt_R": gtR, "gt_v": gtv, "ba": ba, "bg": bg, "ric": Ric, "tic": tic,
             "imu_noise": np.array([ACC_N, GYR_N, ACC_W, GYR_W]), "n_frames": n_frames, "landmarks_total": next_id}
+
+
+def render_stream(seed=0, n_frames=40, speed=1.0, yaw_rate=0.2, frame_dt=0.1, imu_hz=200, pause=None, room=(9.0, 9.0, 3.0), texel=0.015):
+    """RGB-D + IMU stream of a camera moving inside a textured box room (BASELINE.json config 5 shape without wheel / LiDAR / GNSS): the
+    same arc and IMU model as feature_stream; every frame is ray-cast against the six walls (band-limited random texture, bilinear
+    lookup) into a 640x480 uint8 image and a uint16 depth image in millimetres (z-depth, as an RGB-D camera reports it). The scene is
+    geometrically consistent, so features tracked in the images are real 3-D points. Returns a dict with images, depths, imu, ground truth."""
+    rng = np.random.Generator(np.random.PCG64(BASE_SEED + 7000 + seed))
+    tr = _arc_trajectory(rng, n_frames, speed, yaw_rate, frame_dt, imu_hz, pause)
+    hx, hy, hz = room                                   # walls at x = +-hx, y = +-hy, floor z = 0... the camera height is 0.4 m: floor z = -0.6, ceiling hz
+    lo = np.array([-hx, -hy, -0.6]); hi = np.array([hx, hy, hz])
+    n_u = int(2 * max(hx, hy) / texel) + 64; n_v = int(2 * max(hx, hy) / texel) + 64
+    tex = rng.normal(size=(n_v, n_u)).astype(np.float32)
+    k = np.exp(-0.5 * (np.arange(-7, 8) / 2.5) ** 2).astype(np.float32); k /= k.sum()
+    tex = np.apply_along_axis(lambda r: np.convolve(r, k, mode="same"), 1, tex)
+    tex = np.apply_along_axis(lambda c: np.convolve(c, k, mode="same"), 0, tex)
+    tex = ((tex - tex.mean()) / tex.std()).astype(np.float32)
+    vv, uu = np.mgrid[0:H_IMG, 0:W_IMG].astype(np.float64)
+    dc = np.stack([(uu - CX) / FX, (vv - CY) / FY, np.ones_like(uu)], -1)          # camera rays, z = 1
+    images, depths = [], []
+    for f in range(n_frames):
+        dw = dc @ tr["Rwc"][f].T                                                    # world rays
+        o = tr["twc"][f]
+        best_t = np.full(uu.shape, np.inf); best_a = np.zeros(uu.shape, np.int32); best_side = np.zeros(uu.shape, np.int32)
+        for axis in range(3):
+            for side, plane in enumerate((lo[axis], hi[axis])):
+                with np.errstate(divide="ignore", invalid="ignore"):
+                    t = (plane - o[axis]) / dw[..., axis]
+                ok = (t > 1e-6) & (t < best_t)
+                best_t = np.where(ok, t, best_t); best_a = np.where(ok, axis, best_a); best_side = np.where(ok, side, best_side)
+        hit = o + dw * best_t[..., None]
+        # texture coordinates: the two axes other than the plane's normal, shifted per wall so that walls do not repeat each other
+        a1 = np.where(best_a == 0, 1, 0); a2 = np.where(best_a == 2, 1, 2)
+        c1 = np.take_along_axis(hit, a1[..., None], -1)[..., 0]; c2 = np.take_along_axis(hit, a2[..., None], -1)[..., 0]
+        tu = (c1 + max(hx, hy)) / texel + 17.0 * (2 * best_a + best_side); tv = (c2 + max(hx, hy)) / texel + 11.0 * (2 * best_a + best_side)
+        tu = np.clip(tu, 0, n_u - 2.001); tv = np.clip(tv, 0, n_v - 2.001)
+        u0 = np.floor(tu).astype(np.int64); v0 = np.floor(tv).astype(np.int64); au = tu - u0; av = tv - v0
+        val = tex[v0, u0] * (1 - au) * (1 - av) + tex[v0, u0 + 1] * au * (1 - av) + tex[v0 + 1, u0] * (1 - au) * av + tex[v0 + 1, u0 + 1] * au * av
+        img = np.clip(128 + 45 * val + rng.normal(0, 1.5, val.shape), 0, 255).astype(np.uint8)
+        images.append(img)
+        depths.append(np.clip(np.rint(best_t * 1000.0), 0, 65535).astype(np.uint16))   # rays have z = 1 in the camera frame: t is the z-depth
+    return {"images": images, "depths": depths, "imu": tr["imu"], "gt_p": tr["gtp"], "gt_R": tr["gtR"], "gt_v": tr["gtv"], "ba": tr["ba"], "bg": tr["bg"],
+            "ric": tr["Ric"], "tic": tr["tic"], "imu_noise": np.array([ACC_N, GYR_N, ACC_W, GYR_W]), "n_frames": n_frames,
+            "headers": 100.0 + np.arange(n_frames) * frame_dt, "intrinsics": np.array([FX, FY, CX, CY, 0.0, 0.0, 0.0, 0.0])}

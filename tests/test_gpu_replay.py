@@ -111,3 +111,73 @@ def test_steady_state_replay_matches_oracle_step_by_step(gf2, oracle):
     print(f"replay: {len(flags)} frames, {flags.count(0)} keyframes, first processImage {t_steps[0] * 1e3:.1f} ms (handle creation), then median {np.median(t_steps[1:]) * 1e3:.2f} ms "
           f"= {1.0 / np.median(t_steps[1:]):.0f} frames/s, max position error {max(errs):.3f} m, worst oracle deviation {worst:.2e}")
     L.gf2h_estimator_destroy(e)
+
+
+def test_rgbd_imu_stream_end_to_end_images_in_poses_out(gf2, oracle):
+    """The whole mirrored pipeline on a geometrically consistent synthetic RGB-D + IMU stream (a camera moving inside a textured room,
+    ray-cast per frame): FeatureTracker::trackImage (CLAHE, LK + reverse check, detector on the device; depth lookup) feeds
+    Estimator::processImage (device solve + marginalization, window glue). Checked: every solve against the oracle on identical inputs,
+    feature bookkeeping sanity, and the estimated trajectory against ground truth."""
+    synth = importlib.import_module("gf2_b200.synth")
+    abi = gf2.abi
+    L = H.lib()
+    st = synth.render_stream(0, n_frames=36, pause=(22, 25))
+    t = C.c_void_p(L.gf2h_tracker_create(480, 640, 150, 30, H.p(st["intrinsics"])))
+    L.gf2h_tracker_set_equalize(t, 1)
+    e = C.c_void_p(L.gf2h_estimator_create())
+    L.gf2h_set_extrinsic(e, H.p(st["tic"].copy()), H.p(st["ric"].copy()), C.c_double(0.0), C.c_double(synth.G_NORM), H.p(st["imu_noise"]))
+    L.gf2h_set_flags(e, 1, 0, 1, 0)
+    L.gf2h_set_min_parallax(e, C.c_double(10.0 / 460.0))
+    rng = np.random.default_rng(2)
+    P = st["gt_p"][:11].copy() + rng.normal(0, 0.01, (11, 3)); R = st["gt_R"][:11].copy(); V = st["gt_v"][:11].copy()
+    P[10] = P[9]; R[10] = R[9]; V[10] = V[9]
+    L.gf2h_set_frame_states(e, H.p(H.frame_states(P, R, V, np.zeros((11, 3)), np.zeros((11, 3)))))
+
+    def track(k):
+        out = np.zeros((200, 10))
+        n = L.gf2h_tracker_track(t, C.c_double(st["headers"][k]), H.p(st["images"][k]), H.p(st["depths"][k]), 200, H.p(out))
+        assert n > 60, (k, n, L.gf2h_tracker_last_error(t))
+        order = np.argsort(out[:n, 0])
+        return out[:n, 0][order].astype(np.int32), np.ascontiguousarray(out[:n, 1:9][order]), out[:n, 9][order]
+
+    for k in range(10):
+        ids, pts, cnt = track(k)
+        L.gf2h_add_image(e, k, len(ids), H.p(ids), H.p(pts), C.c_double(0.0))
+    for j in range(1, 10):
+        iv = st["imu"][j - 1]
+        L.gf2h_new_interval(e, j, H.p(iv["first"][:3].copy()), H.p(iv["first"][3:].copy()), H.p(np.zeros(3)), H.p(np.zeros(3)))
+        for s in iv["samples"]:
+            L.gf2h_push_imu(e, j, C.c_double(s["dt"]), H.p(s["acc"].copy()), H.p(s["gyr"].copy()))
+    L.gf2h_set_imu0(e, H.p(st["imu"][9]["first"][:3].copy()), H.p(st["imu"][9]["first"][3:].copy()))
+    pose = np.zeros((11, 7)); sbv = np.zeros((11, 9)); exv = np.zeros(7)
+    L.gf2h_vector2double(e, H.p(pose), H.p(sbv), H.p(exv))
+    blk = np.zeros(1, abi.PRIOR_BLOCK); blk["kind"] = abi.BLK_POSE; blk["x0"][0, :7] = pose[0]
+    L.gf2h_set_prior(e, 6, H.p(np.eye(6) * 100.0), H.p(np.zeros(6)), 1, H.p(blk))
+    L.gf2h_set_capture(e, 1)
+    flags, errs, n_lm, long_tracks, worst = [], [], [], [], 0.0
+    for k in range(10, st["n_frames"]):
+        for s in st["imu"][k - 1]["samples"]:
+            L.gf2h_process_imu(e, C.c_double(0.0), C.c_double(s["dt"]), H.p(s["acc"].copy()), H.p(s["gyr"].copy()))
+        ids, pts, cnt = track(k)
+        long_tracks.append(int((cnt >= 4).sum()))
+        flag = L.gf2h_process_image(e, len(ids), H.p(ids), H.p(pts), C.c_double(st["headers"][k]))
+        assert flag >= 0, L.gf2h_last_error(e)
+        flags.append(flag)
+        c = _capture(L, e, abi)
+        n_lm.append(c["n_lm"])
+        opts = abi.default_opts(const_mask=c["const_mask"])
+        w = _oracle_window(c, st["imu_noise"], abi)
+        oracle.imu_preintegrate(w)
+        oracle.solve_batch(w, opts)
+        scale = np.abs(w["para_pose"][0, :, :3]).max()
+        d = max(np.abs(c["pose_out"][:, :3] - w["para_pose"][0, :, :3]).max() / scale, np.abs(c["pose_out"][:, 3:] - w["para_pose"][0, :, 3:]).max())
+        worst = max(worst, d)
+        assert d <= 1e-4, (k, d)
+        out = np.zeros((11, 21)); L.gf2h_get_frame_states(e, H.p(out))
+        errs.append(np.linalg.norm(out[9, :3] - st["gt_p"][k]))
+    assert min(n_lm) > 40 and min(long_tracks) > 40                                    # the front end keeps enough long tracks alive
+    assert 0 in flags
+    assert max(errs) < 0.15, (max(errs), errs)
+    print(f"rgbd+imu replay: {len(flags)} frames, {flags.count(0)} keyframes, landmarks in the solve {min(n_lm)}..{max(n_lm)}, max position error {max(errs):.3f} m, "
+          f"worst oracle deviation {worst:.2e}")
+    L.gf2h_tracker_destroy(t); L.gf2h_estimator_destroy(e)
