@@ -45,6 +45,7 @@ struct KP {  // kernel parameters (device pointers are window-major with the str
   // wcal bit 0: body_T_wheel free, bit 1: sx sy sw free, bit 2: td_wheel free. They form one more block row "frame F" of the
   // reduced system with tangent layout [ex_wheel 6 | sx sy sw | td_wheel | 5 unused]. Ds = 15 (F + 1): row stride of sx/zx/ux/ex_diag.
   int wcal, Ds;
+  uint32_t wsub;   // PoseSubsetParameterization of the wheel extrinsic: tangent components whose delta Plus zeroes (their columns stay in the system)
   uint32_t const_mask;
   double huber, sqrt_info_px, g_norm, lidar_sqrt_info;
   double ftol, gtol, ptol;

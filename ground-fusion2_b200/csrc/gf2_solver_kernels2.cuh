@@ -508,6 +508,7 @@ __global__ void __launch_bounds__(288, 2) k_cand_eval(KP p, int w0) {
     const double* zx = p.zx + (size_t)w * p.Ds + 15 * F; const double* ux = p.ux + (size_t)w * p.Ds + 15 * F;
     double dl[10];
     for (int k = 0; k < 10; k++) dl[k] = -(a * ux[k] + b * zx[k]);
+    for (int k = 0; k < 6; k++) if ((p.wsub >> k) & 1u) dl[k] = 0.0;   // PoseSubsetParameterization::Plus (pose_subset_parameterization.cpp:29-33)
     const double* x = p.exw + (size_t)w * 7; double* xc = p.exw_c + (size_t)w * 7;
     if (p.wcal & 1) {
       for (int k = 0; k < 3; k++) { xc[k] = x[k] + dl[k]; accx[1] += dl[k] * dl[k]; accx[2] += x[k] * x[k]; }

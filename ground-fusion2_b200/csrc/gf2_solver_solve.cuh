@@ -468,7 +468,8 @@ __global__ void __launch_bounds__(kSolveThreads, 2) k_solve2(KP p, int w0) {
     gmax = fmax(gmax, fmax(fmax(fabs(q.x - qn.x), fabs(q.y - qn.y)), fmax(fabs(q.z - qn.z), fabs(q.w - qn.w))));
     for (int k = 6; k < 15; k++) gmax = fmax(gmax, fabs(gg[k]));
   } else if (t == F && p.wcal) {
-    const double* gg = &S.g[15 * F];
+    double gg[10];
+    for (int k = 0; k < 10; k++) gg[k] = (k < 6 && ((p.wsub >> k) & 1u)) ? 0.0 : S.g[15 * F + k];   // Plus of the subset parameterization ignores these
     if (p.wcal & 1) {
       const double* x = p.exw + (size_t)w * 7;
       for (int k = 0; k < 3; k++) gmax = fmax(gmax, fabs(gg[k]));

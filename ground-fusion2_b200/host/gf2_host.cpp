@@ -530,7 +530,8 @@ void Estimator::optimization() {
     if ((P.ESTIMATE_EXTRINSIC && frame_count == WINDOW_SIZE && v0 > 0.2) || openExEstimation) openExEstimation = true; else o.const_mask |= GF2_CONST_EX_POSE;
     if (!P.ESTIMATE_TD || v0 < 0.2) o.const_mask |= GF2_CONST_TD;
     // wheel calibration blocks (estimator.cpp:3063-3110, 3160-3161); extrinsic_type_wheel 0 = ADJUST_WHEEL_ALL (every shipped config)
-    if (wheel_on && P.ESTIMATE_EXTRINSIC_WHEEL && P.EXTRINSIC_TYPE_WHEEL != 0) { last_error = "extrinsic_type_wheel != 0 (PoseSubsetParameterization with constant components) is not built"; return; }
+    { static const uint32_t kSubset[5] = {0x00u, 0x38u, 0x07u, 0x04u, 0x3cu};   // ALL, TRANSLATION, ROTATION, NO_Z, NO_ROTATION_NO_Z (:3069-3089)
+      o.wheel_ext_const_components = (wheel_on && P.ESTIMATE_EXTRINSIC_WHEEL && P.EXTRINSIC_TYPE_WHEEL >= 0 && P.EXTRINSIC_TYPE_WHEEL <= 4) ? kSubset[P.EXTRINSIC_TYPE_WHEEL] : 0u; }
     if ((wheel_on && P.ESTIMATE_EXTRINSIC_WHEEL && frame_count == WINDOW_SIZE && v0 > 0.2) || openExWheelEstimation) openExWheelEstimation = true; else o.const_mask |= GF2_CONST_EX_WHEEL;
     if ((wheel_on && P.ESTIMATE_INTRINSIC_WHEEL && frame_count == WINDOW_SIZE && v0 > 0.2) || openIxEstimation) openIxEstimation = true; else o.const_mask |= GF2_CONST_WHEEL_INTRINSIC;
     if (!P.ESTIMATE_TD_WHEEL || v0 < 0.2) o.const_mask |= GF2_CONST_TD_WHEEL;

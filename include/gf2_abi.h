@@ -192,7 +192,13 @@ typedef struct gf2_solve_opts {
   double function_tolerance;   /* 1e-6 */
   double gradient_tolerance;   /* 1e-10 */
   double parameter_tolerance;  /* 1e-8 */
-  double reserved_[6];
+  /* PoseSubsetParameterization of para_Ex_Pose_wheel (estimator.cpp:3069-3089, VE/factor/pose_subset_parameterization.cpp): bit k set =
+   * tangent component k (0..2 translation, 3..5 rotation) is held by zeroing its delta in Plus while its column stays in the linear
+   * system (the reference's ComputeJacobian is [I6; 0] regardless). extrinsic_type_wheel 0 (ALL) = 0, 1 (TRANSLATION) = 0x38,
+   * 2 (ROTATION) = 0x07, 3 (NO_Z) = 0x04, 4 (NO_ROTATION_NO_Z) = 0x3c. */
+  uint32_t wheel_ext_const_components;
+  uint32_t pad_;
+  double reserved_[5];
 } gf2_solve_opts;
 
 enum { /* gf2_solve_summary.termination */

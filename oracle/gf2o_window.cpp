@@ -77,6 +77,7 @@ void buildWindow(const gf2o_window& w, const gf2_solve_opts& o, BuiltWindow& bw)
   if (w.use_wheel) {  // :3063-3118
     id_exw = P.AddParameterBlock(w.ex_pose_wheel, 7, true);
     if (o.const_mask & GF2_CONST_EX_WHEEL) P.SetParameterBlockConstant(id_exw);
+    for (int k = 0; k < 6; k++) P.blocks[id_exw].subset_mask[k] = ((o.wheel_ext_const_components >> k) & 1u) != 0;   // PoseSubsetParameterization
     id_sx = P.AddParameterBlock(w.sxsysw + 0, 1); id_sy = P.AddParameterBlock(w.sxsysw + 1, 1); id_sw = P.AddParameterBlock(w.sxsysw + 2, 1);
     if (o.const_mask & GF2_CONST_WHEEL_INTRINSIC) { P.SetParameterBlockConstant(id_sx); P.SetParameterBlockConstant(id_sy); P.SetParameterBlockConstant(id_sw); }
     id_tdw = P.AddParameterBlock(w.td_wheel, 1);

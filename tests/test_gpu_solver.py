@@ -247,7 +247,7 @@ def test_wheel_preintegration_kernel_matches_oracle(gf2, oracle, synth):
     s.close()
 
 
-@pytest.mark.parametrize("free,nl,planes", [("exw", 300, 0), ("exw", 1000, 5000), ("exw+td", 200, 500), ("all", 300, 0)])
+@pytest.mark.parametrize("free,nl,planes", [("exw", 300, 0), ("exw", 1000, 5000), ("exw+td", 200, 500), ("all", 300, 0), ("exw-noz", 300, 0), ("exw-rot", 200, 0)])
 def test_free_wheel_calibration_matches_oracle(gf2, oracle, synth, free, nl, planes):
     """estimate_wheel_extrinsic: 1 (gc_test / groundchallenge / idc_rs / m2dgrp .yaml) frees para_Ex_Pose_wheel once the window is full
     (VE/estimator/estimator.cpp:3063-3094); estimate_wheel_intrinsic / estimate_td_wheel free sx sy sw / td_wheel (:3095-3110, :3160).
@@ -259,13 +259,18 @@ def test_free_wheel_calibration_matches_oracle(gf2, oracle, synth, free, nl, pla
     w["sxsysw"][1] = [1.01, 0.99, 1.02]; w["td_wheel"][0] = 0.003
     mask = abi.CONST_EX_POSE | abi.CONST_TD
     live = list(range(165)) + list(range(165, 171))
-    if free == "exw":
+    subset = 0
+    if free.startswith("exw-"):   # PoseSubsetParameterization: extrinsic_type_wheel 3 (NO_Z) / 2 (ROTATION): deltas zeroed in Plus, columns stay
+        subset = {"exw-noz": 0x04, "exw-rot": 0x07}[free]
+        mask |= abi.CONST_WHEEL_INTRINSIC | abi.CONST_TD_WHEEL
+    elif free == "exw":
         mask |= abi.CONST_WHEEL_INTRINSIC | abi.CONST_TD_WHEEL
     elif free == "exw+td":
         mask |= abi.CONST_WHEEL_INTRINSIC; live += [174]
     else:
         live += [171, 172, 173, 174]
     opts = abi.default_opts(const_mask=mask)
+    opts.wheel_ext_const_components = subset
     s = _solver4(gf2, w, n)
     s.upload(w, preintegrate="records")
     S, g, cost = s.linearize(opts, n)
@@ -297,6 +302,10 @@ def test_free_wheel_calibration_matches_oracle(gf2, oracle, synth, free, nl, pla
     assert np.abs(wo["ex_pose_wheel"] - w["ex_pose_wheel"]).max() > 1e-3          # the extrinsic did move
     if free == "exw":
         assert np.array_equal(got["sxsysw"], w["sxsysw"]) and np.array_equal(got["td_wheel"], w["td_wheel"])   # constant blocks untouched
+    if free == "exw-noz":
+        assert np.array_equal(got["ex_pose_wheel"][:, 2], w["ex_pose_wheel"][:, 2]) and np.array_equal(wo["ex_pose_wheel"][:, 2], w["ex_pose_wheel"][:, 2])   # z held
+    if free == "exw-rot":
+        assert np.array_equal(got["ex_pose_wheel"][:, :3], w["ex_pose_wheel"][:, :3])                          # translation held, rotation moved
     assert np.abs(np.linalg.norm(got["ex_pose_wheel"][:, 3:], axis=-1) - 1).max() < 1e-14
     s.close()
 
