@@ -365,3 +365,38 @@ def test_triangulate_outlier_checks_prediction_and_slide_window():
     assert L.gf2h_interval_samples(e, 9, 0, 32, H.p(dt)) == before + 3 and L.gf2h_interval_samples(e, 10, 0, 32, H.p(dt)) == 0
     L.gf2h_get_headers(e, H.p(h2), H.p(cnt)); assert cnt.tolist() == [1, 1]
     L.gf2h_estimator_destroy(e)
+
+
+def test_synthetic_streams_are_self_consistent(gf2, oracle):
+    """The replay inputs (tests/test_gpu_replay.py, bench.py) are only as good as their ground truth: (1) the IMU samples of feature_stream,
+    preintegrated by the oracle, explain the ground-truth motion through the pause (whitened IMUFactor residual ~ noise level); (2) the
+    ray-cast RGB-D frames are geometrically consistent: a pixel's depth, lifted to 3-D and reprojected into the next frame, lands on a
+    pixel whose depth agrees."""
+    synth = importlib.import_module("gf2_b200.synth")
+    abi = gf2.abi
+    st = synth.feature_stream(3, n_frames=16, pause=(8, 10))
+    noise = st["imu_noise"]
+    worst = 0.0
+    for k in range(15):
+        rec = np.zeros(1, abi.IMU_PREINT)
+        smp = np.ascontiguousarray(st["imu"][k]["samples"]); first = np.ascontiguousarray(st["imu"][k]["first"]); lb = np.concatenate([st["ba"], st["bg"]])
+        oracle.lib.gf2o_imu_preintegrate(oracle._p(smp), len(smp), oracle._p(first), oracle._p(lb), oracle._p(noise), oracle._p(rec))
+        pi = np.concatenate([st["gt_p"][k], synth.quat_from_R(st["gt_R"][k])]); pj = np.concatenate([st["gt_p"][k + 1], synth.quat_from_R(st["gt_R"][k + 1])])
+        sbi = np.concatenate([st["gt_v"][k], st["ba"], st["bg"]]); sbj = np.concatenate([st["gt_v"][k + 1], st["ba"], st["bg"]])
+        r, _ = oracle.factor_eval(1, rec, np.concatenate([pi, sbi, pj, sbj]), extra=[synth.G_NORM], want_jac=False)
+        worst = max(worst, np.abs(r).max())
+    assert worst < 6.0, worst        # whitened residuals: a few sigma (sensor noise + trapezoid integration of the ground truth)
+    rs = synth.render_stream(1, n_frames=3)
+    fx, fy, cx, cy = rs["intrinsics"][:4]
+    Rwc = rs["gt_R"] @ rs["ric"]; twc = rs["gt_p"] + np.einsum("nij,j->ni", rs["gt_R"], rs["tic"])
+    rng = np.random.default_rng(0)
+    us = rng.integers(40, 600, 400); vs = rng.integers(40, 440, 400)
+    z0 = rs["depths"][0][vs, us].astype(np.float64) / 1000.0
+    Xw = (np.stack([(us - cx) / fx * z0, (vs - cy) / fy * z0, z0], -1) @ Rwc[0].T) + twc[0]
+    pc = (Xw - twc[1]) @ Rwc[1]
+    u1 = fx * pc[:, 0] / pc[:, 2] + cx; v1 = fy * pc[:, 1] / pc[:, 2] + cy
+    ok = (u1 > 2) & (u1 < 637) & (v1 > 2) & (v1 < 477)
+    z1 = rs["depths"][1][np.rint(v1[ok]).astype(int), np.rint(u1[ok]).astype(int)].astype(np.float64) / 1000.0
+    rel = np.abs(z1 - pc[ok, 2]) / pc[ok, 2]
+    assert ok.sum() > 300 and np.median(rel) < 2e-3 and (rel < 0.02).mean() > 0.9     # the few misses sit on wall / floor edges
+    assert 30 < rs["images"][0].std() < 60
