@@ -250,6 +250,57 @@ def run_lio(gf2, synth, steps=10, with_cpu=True):
     return line
 
 
+def run_replay_rgbd(gf2, synth):
+    """The same loop fed by IMAGES: a ray-cast RGB-D + IMU stream through FeatureTracker::trackImage (CLAHE, LK + reverse check, detector on the
+    device) and Estimator::processImage — BASELINE.json config 5 shape without wheel / LiDAR / GNSS; per-frame latency of one robot."""
+    import ctypes as C
+    L = C.CDLL(os.path.join(ROOT, "ground-fusion2_b200", "libgf2_host.so"))
+    L.gf2h_estimator_create.restype = C.c_void_p; L.gf2h_tracker_create.restype = C.c_void_p; L.gf2h_last_error.restype = C.c_char_p
+    P_ = lambda a: np.ascontiguousarray(a).ctypes.data_as(C.c_void_p)
+    st = synth.render_stream(2, n_frames=50, pause=(30, 33))
+    t = C.c_void_p(L.gf2h_tracker_create(480, 640, 150, 30, P_(st["intrinsics"]))); L.gf2h_tracker_set_equalize(t, 1)
+    e = C.c_void_p(L.gf2h_estimator_create())
+    L.gf2h_set_extrinsic(e, P_(st["tic"].copy()), P_(st["ric"].copy()), C.c_double(0.0), C.c_double(synth.G_NORM), P_(st["imu_noise"]))
+    L.gf2h_set_flags(e, 1, 0, 1, 0); L.gf2h_set_min_parallax(e, C.c_double(10.0 / 460.0))
+    Pp = st["gt_p"][:11].copy(); R = st["gt_R"][:11].copy(); V = st["gt_v"][:11].copy(); Pp[10] = Pp[9]; R[10] = R[9]; V[10] = V[9]
+    fs = np.zeros((11, 21)); fs[:, 0:3] = Pp; fs[:, 3:12] = R.reshape(11, 9); fs[:, 12:15] = V
+    L.gf2h_set_frame_states(e, P_(fs))
+
+    def track(k):
+        out = np.zeros((200, 10))
+        n = L.gf2h_tracker_track(t, C.c_double(st["headers"][k]), P_(st["images"][k]), P_(st["depths"][k]), 200, P_(out))
+        if n < 0:
+            raise RuntimeError("tracker failed")
+        order = np.argsort(out[:n, 0])
+        return out[:n, 0][order].astype(np.int32), np.ascontiguousarray(out[:n, 1:9][order])
+    for k in range(10):
+        ids, pts = track(k); L.gf2h_add_image(e, k, len(ids), P_(ids), P_(pts), C.c_double(0.0))
+    for j in range(1, 10):
+        iv = st["imu"][j - 1]
+        L.gf2h_new_interval(e, j, P_(iv["first"][:3].copy()), P_(iv["first"][3:].copy()), P_(np.zeros(3)), P_(np.zeros(3)))
+        for s_ in iv["samples"]:
+            L.gf2h_push_imu(e, j, C.c_double(s_["dt"]), P_(s_["acc"].copy()), P_(s_["gyr"].copy()))
+    L.gf2h_set_imu0(e, P_(st["imu"][9]["first"][:3].copy()), P_(st["imu"][9]["first"][3:].copy()))
+    pose = np.zeros((11, 7)); sbv = np.zeros((11, 9)); exv = np.zeros(7); L.gf2h_vector2double(e, P_(pose), P_(sbv), P_(exv))
+    blk = np.zeros(1, gf2.abi.PRIOR_BLOCK); blk["kind"] = gf2.abi.BLK_POSE; blk["x0"][0, :7] = pose[0]
+    L.gf2h_set_prior(e, 6, P_(np.eye(6) * 100.0), P_(np.zeros(6)), 1, P_(blk))
+    t_track, t_proc, flags, errs = [], [], [], []
+    for k in range(10, st["n_frames"]):
+        for s_ in st["imu"][k - 1]["samples"]:
+            L.gf2h_process_imu(e, C.c_double(0.0), C.c_double(s_["dt"]), P_(s_["acc"].copy()), P_(s_["gyr"].copy()))
+        t0 = time.perf_counter(); ids, pts = track(k); t1 = time.perf_counter()
+        flag = L.gf2h_process_image(e, len(ids), P_(ids), P_(pts), C.c_double(st["headers"][k])); t2 = time.perf_counter()
+        if flag < 0:
+            raise RuntimeError("replay: " + L.gf2h_last_error(e).decode())
+        t_track.append(t1 - t0); t_proc.append(t2 - t1); flags.append(flag)
+        out = np.zeros((11, 21)); L.gf2h_get_frame_states(e, P_(out)); errs.append(float(np.linalg.norm(out[9, :3] - st["gt_p"][k])))
+    L.gf2h_tracker_destroy(t); L.gf2h_estimator_destroy(e)
+    med = float(np.median(np.array(t_track[1:]) + np.array(t_proc[1:])))
+    return {"metric": "RGB-D + IMU replay frames/sec, images in -> poses out (trackImage + processImage, one robot)", "value": 1.0 / med, "unit": "frames/s", "frames": len(flags),
+            "keyframes": flags.count(0), "keyframes_per_s": flags.count(0) / float(np.sum(t_track[1:]) + np.sum(t_proc[1:])) if len(flags) > 1 else None,
+            "median_track_ms": float(np.median(t_track[1:])) * 1e3, "median_process_ms": float(np.median(t_proc[1:])) * 1e3, "max_position_error_m": max(errs)}
+
+
 def run_replay(gf2, synth, with_cpu=True):
     """BASELINE.json config 5 shape, visual-inertial part: a synthetic feature + IMU stream through the C++ mirror's
     Estimator::processIMU / processImage (keyframe decision, depth initialisation, device solve + marginalization, outlier check, slide),
@@ -507,6 +558,7 @@ def main():
     if rank == 0 and not args.no_lk:
         lio_line = run_lio(gf2, synth, steps=10, with_cpu=not args.no_cpu_baseline)
         replay_line = run_replay(gf2, synth, with_cpu=not args.no_cpu_baseline)
+        replay_line["rgbd"] = run_replay_rgbd(gf2, synth)
 
     if rank == 0:
         peaks, which = measured_peaks()

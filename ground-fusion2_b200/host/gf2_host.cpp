@@ -671,6 +671,18 @@ std::map<int, Vector3d> Estimator::predictPtsInNextFrame() const {   // :3915-39
   }
   return predictPts;
 }
+std::string Estimator::tumLine(double stamp) const {   // visualization.cpp:371-385
+  const Quaterniond q = quatFromMatrix(Rs[WINDOW_SIZE]);
+  char buf[256];
+  snprintf(buf, sizeof(buf), "%.9f %.9f %.9f %.9f %.9f %.9f %.9f %.9f\n", stamp, Ps[WINDOW_SIZE].x, Ps[WINDOW_SIZE].y, Ps[WINDOW_SIZE].z, q.x, q.y, q.z, q.w);
+  return buf;
+}
+bool Estimator::appendTum(const std::string& path, double stamp) const {
+  FILE* f = fopen(path.c_str(), "a");
+  if (!f) return false;
+  const std::string l = tumLine(stamp); fputs(l.c_str(), f); fclose(f);
+  return true;
+}
 void Estimator::slideWindow() {   // :3700-3857 (GNSS buffers and all_image_frame belong to subsystems outside this build)
   if (marginalization_flag == MARGIN_OLD) {
     back_R0 = Rs[0]; back_P0 = Ps[0];
@@ -1031,6 +1043,7 @@ int gf2h_interval_samples(void* e, int j, int wheel, int max_n, double* dt) {   
   for (size_t i = 0; i < b->size() && (int)i < max_n; i++) dt[i] = (*b)[i];
   return (int)b->size();
 }
+int gf2h_append_tum(void* e, const char* path, double stamp) { return ((Estimator*)e)->appendTum(path, stamp) ? 0 : -1; }
 void gf2h_set_imu0(void* e, const double* acc, const double* gyr) {   // the sample the next interval starts from (acc_0 / gyr_0 of processIMU)
   Estimator* E = (Estimator*)e; E->first_imu = true; E->acc_0 = {acc[0], acc[1], acc[2]}; E->gyr_0 = {gyr[0], gyr[1], gyr[2]};
 }

@@ -159,6 +159,9 @@ class Estimator {
   void movingConsistencyCheckW(std::set<int>& removeIndex);    // :4030-4074
   void getPoseInWorldFrame(int index, double T[16]) const;     // :3901-3913 (row-major 4x4)
   std::map<int, Vector3d> predictPtsInNextFrame() const;       // :3915-3948 (the map handed to FeatureTracker::setPrediction)
+  // pubOdometry's result line (VE/utility/visualization.cpp:315-387): "stamp x y z qx qy qz qw" of Ps / Rs[WINDOW_SIZE], fixed, 9 decimals (TUM format)
+  std::string tumLine(double stamp) const;
+  bool appendTum(const std::string& path, double stamp) const;
   // Test hook: when capture is set, optimization() keeps a copy of everything it hands to the C ABI and of what comes back, so that a
   // replay can be checked step by step against the CPU oracle on identical inputs (tests/test_gpu_replay.py).
   struct Capture {

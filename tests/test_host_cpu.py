@@ -400,3 +400,22 @@ def test_synthetic_streams_are_self_consistent(gf2, oracle):
     rel = np.abs(z1 - pc[ok, 2]) / pc[ok, 2]
     assert ok.sum() > 300 and np.median(rel) < 2e-3 and (rel < 0.02).mean() > 0.9     # the few misses sit on wall / floor edges
     assert 30 < rs["images"][0].std() < 60
+
+
+def test_tum_trajectory_line(tmp_path):
+    """pubOdometry's result file (VE/utility/visualization.cpp:371-385): 'stamp x y z qx qy qz qw', fixed notation, 9 decimals, newest frame."""
+    L = H.lib()
+    e = C.c_void_p(L.gf2h_estimator_create())
+    P = np.arange(33, dtype=np.float64).reshape(11, 3) * 0.125; R = np.tile(np.eye(3), (11, 1, 1))
+    a = 0.3; R[10] = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1.0]])
+    L.gf2h_set_frame_states(e, H.p(H.frame_states(P, R, np.zeros((11, 3)), np.zeros((11, 3)), np.zeros((11, 3)))))
+    path = str(tmp_path / "vio.txt").encode()
+    assert L.gf2h_append_tum(e, path, C.c_double(1700000000.123456789)) == 0 and L.gf2h_append_tum(e, path, C.c_double(2.5)) == 0
+    lines = open(path.decode()).read().splitlines()
+    assert len(lines) == 2
+    v = lines[0].split()
+    assert len(v) == 8 and all(len(x.split(".")[1]) == 9 for x in v)
+    assert v[0] == "1700000000.123456717" or abs(float(v[0]) - 1700000000.123456789) < 1e-6      # double precision of the stamp
+    assert np.allclose([float(x) for x in v[1:4]], P[10]) and np.allclose([float(x) for x in v[4:]], [0, 0, np.sin(a / 2), np.cos(a / 2)], atol=1e-9)
+    assert L.gf2h_append_tum(e, b"/nonexistent_dir/x.txt", C.c_double(0.0)) == -1
+    L.gf2h_estimator_destroy(e)
