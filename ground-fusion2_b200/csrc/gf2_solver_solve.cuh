@@ -451,7 +451,9 @@ __global__ void __launch_bounds__(kSolveThreads, 2) k_solve2(KP p, int w0) {
   double sums[3] = {0, 0, 0};  // dlg2, uEu, -
   double gmax = 0.0;
   for (int i = t; i < Dx; i += nt) {
-    if (i >= D && !calib_live(i - D)) { S.s[i] = 1.0; S.e[i] = 0.0; S.u[i] = 0.0; S.g[i] = 0.0; continue; }  // constant / unused calibration entry
+    // constant / unused calibration entry: S.g[i] is zero by construction (no Jacobian column, no prior column) and is NOT written here —
+    // thread F reads the calibration gradient below without a barrier in between
+    if (i >= D && !calib_live(i - D)) { S.s[i] = 1.0; S.e[i] = 0.0; S.u[i] = 0.0; continue; }
     double sc;
     if (st.iteration == 0) { sc = 1.0 / (1.0 + sqrt(S.Hd[i])); p.sx[(size_t)w * p.Ds + i] = sc; } else sc = p.sx[(size_t)w * p.Ds + i];
     const double d2 = fmin(fmax(sc * sc * S.Hd[i], 1e-6), 1e32);
