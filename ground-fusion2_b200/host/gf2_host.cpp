@@ -575,6 +575,58 @@ void Estimator::optimization() {
   }  // GF2_MARG_UNCHANGED / DEGENERATE / UNSUPPORTED: the previous prior stays (block indices untouched, as at :3599)
 }
 
+// ---- measurement queues (estimator.cpp:324-372, 422-545, 554-763) ---------------------------------------------------------------------
+void Estimator::inputIMU(double t, const Vector3d& a, const Vector3d& g) { accBuf.push({t, a}); gyrBuf.push({t, g}); }            // fastPredictIMU / publishers: outside this build
+void Estimator::inputWheel(double t, const Vector3d& v, const Vector3d& g) { wheelVelBuf.push({t, v}); wheelGyrBuf.push({t, g}); }
+void Estimator::inputFeature(double t, const FeatureFrame& f) { featureBuf.push({t, f}); }
+bool Estimator::IMUAvailable(double t) const { return !accBuf.empty() && t <= accBuf.back().first; }
+bool Estimator::WheelAvailable(double t) const { return !wheelVelBuf.empty() && t <= wheelVelBuf.back().first; }
+static bool takeInterval(std::queue<std::pair<double, Vector3d>>& A, std::queue<std::pair<double, Vector3d>>& B, double t0, double t1,
+                         std::vector<std::pair<double, Vector3d>>& av, std::vector<std::pair<double, Vector3d>>& bv) {   // :422-455 / :456-526
+  if (A.empty()) return false;
+  if (!(t1 <= A.back().first)) return false;                      // "wait for imu"
+  while (A.front().first <= t0) { A.pop(); B.pop(); }
+  while (A.front().first < t1) { av.push_back(A.front()); A.pop(); bv.push_back(B.front()); B.pop(); }
+  av.push_back(A.front()); bv.push_back(B.front());              // the first sample at or after t1 stays queued for the next interval
+  return true;
+}
+bool Estimator::getIMUInterval(double t0, double t1, std::vector<std::pair<double, Vector3d>>& av, std::vector<std::pair<double, Vector3d>>& gv) { return takeInterval(accBuf, gyrBuf, t0, t1, av, gv); }
+bool Estimator::getWheelInterval(double t0, double t1, std::vector<std::pair<double, Vector3d>>& vv, std::vector<std::pair<double, Vector3d>>& gv) { return takeInterval(wheelVelBuf, wheelGyrBuf, t0, t1, vv, gv); }
+int Estimator::processMeasurements() {
+  int consumed = 0;
+  while (!featureBuf.empty()) {
+    const std::pair<double, FeatureFrame>& feature = featureBuf.front();
+    curTime = feature.first + td; curTime_wheel = curTime - td_wheel;
+    const bool wheel_on = P.USE_WHEEL != 0;
+    if (P.USE_IMU && !IMUAvailable(feature.first + td)) break;                      // MULTIPLE_THREAD == 0: return and wait
+    if (wheel_on && !WheelAvailable(feature.first + td - td_wheel)) break;
+    std::vector<std::pair<double, Vector3d>> accVector, gyrVector, velWheelVector, gyrWheelVector;
+    if (P.USE_IMU) getIMUInterval(prevTime, curTime, accVector, gyrVector);
+    const FeatureFrame image = feature.second; const double header = feature.first;
+    featureBuf.pop();
+    if (wheel_on) getWheelInterval(prevTime_wheel, curTime_wheel, velWheelVector, gyrWheelVector);
+    for (size_t i = 0; i < accVector.size(); i++) {   // :640-651: the first and the last sample are cut at the image times
+      double dt;
+      if (i == 0) dt = accVector[i].first - prevTime;
+      else if (i == accVector.size() - 1) dt = curTime - accVector[i - 1].first;
+      else dt = accVector[i].first - accVector[i - 1].first;
+      processIMU(accVector[i].first, dt, accVector[i].second, gyrVector[i].second);
+    }
+    for (size_t i = 0; i < velWheelVector.size(); i++) {
+      double dt;
+      if (i == 0) dt = velWheelVector[i].first - prevTime_wheel;
+      else if (i == velWheelVector.size() - 1) dt = curTime_wheel - velWheelVector[i - 1].first;
+      else dt = velWheelVector[i].first - velWheelVector[i - 1].first;
+      processWheel(velWheelVector[i].first, dt, velWheelVector[i].second, gyrWheelVector[i].second);
+    }
+    processImage(image, header);
+    prevTime = curTime; prevTime_wheel = curTime_wheel;
+    consumed++;
+    if (!last_error.empty()) break;
+  }
+  return consumed;
+}
+
 // ---- measurement processing around the solve (steady state) -------------------------------------------------------------------------
 void Estimator::processIMU(double, double dt, const Vector3d& linear_acceleration, const Vector3d& angular_velocity) {   // estimator.cpp:795-836
   if (!first_imu) { first_imu = true; acc_0 = linear_acceleration; gyr_0 = angular_velocity; }
@@ -736,9 +788,11 @@ void Estimator::processImage(const std::map<int, std::vector<std::pair<int, std:
   f_manager.triangulate(frame_count, Ps, Rs, tic, ric);
   std::set<int> removeIndex;
   if (USE_MCC) { movingConsistencyCheckW(removeIndex); f_manager.removeOutlier(removeIndex); }
-  optimization();
-  if (!last_error.empty()) return;
-  if (!USE_MCC) { std::set<int> idx; movingConsistencyCheckW(idx); f_manager.removeOutlier(idx); }
+  if (solve_enabled) {
+    optimization();
+    if (!last_error.empty()) return;
+    if (!USE_MCC) { std::set<int> idx; movingConsistencyCheckW(idx); f_manager.removeOutlier(idx); }
+  }
   slideWindow();
   f_manager.removeFailures();
   last_R0 = Rs[0]; last_P0 = Ps[0];
@@ -1047,6 +1101,13 @@ int gf2h_append_tum(void* e, const char* path, double stamp) { return ((Estimato
 void gf2h_set_imu0(void* e, const double* acc, const double* gyr) {   // the sample the next interval starts from (acc_0 / gyr_0 of processIMU)
   Estimator* E = (Estimator*)e; E->first_imu = true; E->acc_0 = {acc[0], acc[1], acc[2]}; E->gyr_0 = {gyr[0], gyr[1], gyr[2]};
 }
+void gf2h_set_solve_enabled(void* e, int on) { ((Estimator*)e)->solve_enabled = on != 0; }
+void gf2h_input_imu(void* e, double t, const double* acc, const double* gyr) { ((Estimator*)e)->inputIMU(t, {acc[0], acc[1], acc[2]}, {gyr[0], gyr[1], gyr[2]}); }
+void gf2h_input_wheel(void* e, double t, const double* vel, const double* gyr) { ((Estimator*)e)->inputWheel(t, {vel[0], vel[1], vel[2]}, {gyr[0], gyr[1], gyr[2]}); }
+void gf2h_input_feature(void* e, double t, int n, const int* ids, const double* pts8) { ((Estimator*)e)->inputFeature(t, image_of(n, ids, pts8)); }
+void gf2h_set_prev_time(void* e, double prev, double prev_wheel) { ((Estimator*)e)->prevTime = prev; ((Estimator*)e)->prevTime_wheel = prev_wheel; }
+int gf2h_process_measurements(void* e) { return ((Estimator*)e)->processMeasurements(); }
+int gf2h_queue_sizes(void* e, int* s3) { Estimator* E = (Estimator*)e; s3[0] = (int)E->accBuf.size(); s3[1] = (int)E->wheelVelBuf.size(); s3[2] = (int)E->featureBuf.size(); return 0; }
 void gf2h_set_capture(void* e, int on) { ((Estimator*)e)->capture = on != 0; }
 // sizes: [n_lm, n_obs, prior_rows, prior_nblocks, const_mask, marg_mode]
 void gf2h_capture_sizes(void* e, int* s6) {

@@ -13,6 +13,7 @@
 #include <cstdint>
 #include <list>
 #include <map>
+#include <queue>
 #include <set>
 #include <string>
 #include <utility>
@@ -148,6 +149,21 @@ class Estimator {
   void clearState();
   void vector2double();   // estimator.cpp:2337-2414
   void double2vector();   // estimator.cpp:2501-2630 (yaw / position re-anchoring to frame 0, setDepth)
+  // measurement queues and the consumer loop (estimator.cpp:324-372 inputIMU / inputWheel, :422-545 interval extraction, :554-763
+  // processMeasurements with MULTIPLE_THREAD == 0: one pass, returns when a stream has to be waited for)
+  typedef std::map<int, std::vector<std::pair<int, std::vector<double>>>> FeatureFrame;
+  void inputIMU(double t, const Vector3d& linearAcceleration, const Vector3d& angularVelocity);
+  void inputWheel(double t, const Vector3d& linearVelocity, const Vector3d& angularVelocity);
+  void inputFeature(double t, const FeatureFrame& featureFrame);   // what inputImage pushes after trackImage (:232-236)
+  bool IMUAvailable(double t) const;
+  bool WheelAvailable(double t) const;
+  bool getIMUInterval(double t0, double t1, std::vector<std::pair<double, Vector3d>>& accVector, std::vector<std::pair<double, Vector3d>>& gyrVector);
+  bool getWheelInterval(double t0, double t1, std::vector<std::pair<double, Vector3d>>& velVector, std::vector<std::pair<double, Vector3d>>& gyrVector);
+  int processMeasurements();   // returns the number of images consumed
+  std::queue<std::pair<double, Vector3d>> accBuf, gyrBuf, wheelVelBuf, wheelGyrBuf;
+  std::queue<std::pair<double, FeatureFrame>> featureBuf;
+  double prevTime = -1.0, curTime = 0.0, prevTime_wheel = -1.0, curTime_wheel = 0.0;
+  bool solve_enabled = true;   // test hook: false = processImage keeps all bookkeeping but skips optimization() (CPU-only tests of the glue)
   // measurement processing around the solve (steady state, solver_flag == NON_LINEAR)
   void processIMU(double t, double dt, const Vector3d& linear_acceleration, const Vector3d& angular_velocity);   // :795-836 (sample buffering)
   void processWheel(double t, double dt, const Vector3d& linear_velocity, const Vector3d& angular_velocity);     // :837-896 (buffering + dead reckoning of the newest frame)

@@ -419,3 +419,52 @@ def test_tum_trajectory_line(tmp_path):
     assert np.allclose([float(x) for x in v[1:4]], P[10]) and np.allclose([float(x) for x in v[4:]], [0, 0, np.sin(a / 2), np.cos(a / 2)], atol=1e-9)
     assert L.gf2h_append_tum(e, b"/nonexistent_dir/x.txt", C.c_double(0.0)) == -1
     L.gf2h_estimator_destroy(e)
+
+
+def test_process_measurements_interval_extraction_and_sample_timing():
+    """processMeasurements (estimator.cpp:554-763, MULTIPLE_THREAD == 0) with the solve switched off: images wait until IMU and wheel
+    samples cover them (IMUAvailable / WheelAvailable), getIMUInterval / getWheelInterval hand over the samples in (prevTime, curTime) plus
+    the first one at or after curTime (which also stays queued), and the first / last dt are cut at the image times (:640-651) so that
+    every interval sums to exactly the image spacing."""
+    L = H.lib()
+    e = C.c_void_p(L.gf2h_estimator_create())
+    P = np.zeros((11, 3)); R = np.tile(np.eye(3), (11, 1, 1))
+    L.gf2h_set_frame_states(e, H.p(H.frame_states(P, R, np.zeros((11, 3)), np.zeros((11, 3)), np.zeros((11, 3)))))
+    L.gf2h_set_extrinsic(e, H.p(np.zeros(3)), H.p(np.eye(3)), C.c_double(0.0), C.c_double(9.8), H.p(np.array([0.1, 0.01, 1e-3, 1e-4])))
+    L.gf2h_set_flags(e, 1, 1, 0, 0)
+    L.gf2h_set_solve_enabled(e, 0)
+    imu_t = 0.9513 + 0.005 * np.arange(80)          # 200 Hz, not aligned with the images
+    whl_t = 0.9441 + 0.02 * np.arange(22)           # 50 Hz
+    img_t = [1.0, 1.1, 1.2, 1.3]
+    L.gf2h_set_prev_time(e, C.c_double(0.95), C.c_double(0.95))
+    ids = np.arange(5, dtype=np.int32); pts = np.tile([0.1, 0.2, 1.0, 300, 200, 0, 0, 2.0], (5, 1)).astype(np.float64)
+    for tt in img_t:
+        L.gf2h_input_feature(e, C.c_double(tt), 5, H.p(ids), H.p(pts))
+    zero = np.zeros(3)
+    for tt in imu_t[:25]:                              # IMU up to 1.0713: covers image 1.0 only
+        L.gf2h_input_imu(e, C.c_double(tt), H.p(zero), H.p(zero))
+    assert L.gf2h_process_measurements(e) == 0         # no wheel sample yet: WheelAvailable fails, nothing consumed
+    for tt in whl_t[:4]:                               # wheel up to 1.0041
+        L.gf2h_input_wheel(e, C.c_double(tt), H.p(zero), H.p(zero))
+    assert L.gf2h_process_measurements(e) == 1         # image 1.0 consumed, 1.1 waits for IMU
+    dt = np.zeros(64)
+    n = L.gf2h_interval_samples(e, 9, 0, 64, H.p(dt))   # few tracks -> MARGIN_OLD: the interval of the newest frame moved to slot 9
+    sel = imu_t[(imu_t > 0.95) & (imu_t < 1.0)]; nxt = imu_t[imu_t >= 1.0][0]
+    exp = np.concatenate([[sel[0] - 0.95], np.diff(sel), [1.0 - sel[-1]]])
+    assert n == len(sel) + 1 and np.array_equal(dt[:n], exp) and abs(dt[:n].sum() - 0.05) < 1e-15
+    nw = L.gf2h_interval_samples(e, 9, 1, 64, H.p(dt))
+    selw = whl_t[(whl_t > 0.95) & (whl_t < 1.0)]
+    assert nw == len(selw) + 1 and np.array_equal(dt[:nw], np.concatenate([[selw[0] - 0.95], np.diff(selw), [1.0 - selw[-1]]]))
+    q = np.zeros(3, np.int32); L.gf2h_queue_sizes(e, H.p(q))
+    assert q[2] == 3 and q[0] == int((imu_t[:25] >= nxt).sum())           # the sample at / after curTime stays queued for the next interval
+    for tt in imu_t[25:]:
+        L.gf2h_input_imu(e, C.c_double(tt), H.p(zero), H.p(zero))
+    for tt in whl_t[4:]:
+        L.gf2h_input_wheel(e, C.c_double(tt), H.p(zero), H.p(zero))
+    assert L.gf2h_process_measurements(e) == 3         # everything that is covered now
+    n = L.gf2h_interval_samples(e, 9, 0, 64, H.p(dt))   # the last interval (1.2, 1.3]
+    sel = imu_t[(imu_t > 1.2) & (imu_t < 1.3)]
+    assert n == len(sel) + 1 and abs(dt[:n].sum() - 0.1) < 1e-12 and abs(dt[0] - (sel[0] - 1.2)) < 1e-15 and abs(dt[n - 1] - (1.3 - sel[-1])) < 1e-15
+    h = np.zeros(11); cnt = np.zeros(2, np.int32); L.gf2h_get_headers(e, H.p(h), H.p(cnt))
+    assert cnt.tolist() == [4, 0] and h[9] == 1.3 and h[8] == 1.2
+    L.gf2h_estimator_destroy(e)
