@@ -354,7 +354,18 @@ void FeatureManager::triangulateWithDepth(int, const Vector3d Ps[], const Matrix
 
 // ------------------------------------------------------------------------------------------------ Estimator
 Estimator::Estimator() { clearState(); memset(&last_summary, 0, sizeof(last_summary)); }
+bool ImagePairSynchronizer::next(double* time, int* handle0, int* handle1) {   // rosNodeTest.cpp:395-428
+  while (!img0_buf.empty() && !img1_buf.empty()) {
+    const double time0 = img0_buf.front().first, time1 = img1_buf.front().first;
+    if (time0 < time1 - 0.003) { img0_buf.pop(); thrown0++; }
+    else if (time0 > time1 + 0.003) { img1_buf.pop(); thrown1++; }
+    else { *time = time0; *handle0 = img0_buf.front().second; *handle1 = img1_buf.front().second; img0_buf.pop(); img1_buf.pop(); return true; }
+  }
+  return false;
+}
+
 Estimator::~Estimator() {
+  delete featureTracker;
   if (gf2) gf2_solver_destroy(gf2);
   for (auto& p : pre_integrations) { delete p; p = nullptr; }
   for (auto& p : pre_integrations_wheel) { delete p; p = nullptr; }
@@ -363,6 +374,16 @@ void Estimator::setParameter(const Parameters& p) {
   P = p; tic[0] = p.TIC; ric[0] = p.RIC; td = p.TD;
   tio = p.TIO; rio = p.RIO; sx = p.SX; sy = p.SY; sw = p.SW; td_wheel = p.TD_WHEEL;
   f_manager.MIN_PARALLAX = p.MIN_PARALLAX;
+  if (!featureTracker) featureTracker = new FeatureTracker();
+  featureTracker->readIntrinsicParameter(p);
+}
+void Estimator::inputImage(double t, const uint8_t* _img, const uint16_t* _img1) {   // estimator.cpp:213-242
+  inputImageCnt++;
+  if (!featureTracker) { last_error = "setParameter has not been called"; return; }
+  FeatureFrame featureFrame = featureTracker->trackImage(t, _img, _img1);
+  if (featureTracker->lastError()[0]) { last_error = featureTracker->lastError(); return; }
+  if (MULTIPLE_THREAD) { if (inputImageCnt % 2 == 0) featureBuf.push({t, featureFrame}); }
+  else { featureBuf.push({t, featureFrame}); processMeasurements(); }
 }
 void Estimator::clearState() {
   for (int i = 0; i <= WINDOW_SIZE; i++) { Rs[i] = Matrix3d(); Ps[i] = Vector3d(); Vs[i] = Vector3d(); Bas[i] = Vector3d(); Bgs[i] = Vector3d(); delete pre_integrations[i]; pre_integrations[i] = nullptr; }
@@ -791,7 +812,11 @@ void Estimator::processImage(const std::map<int, std::vector<std::pair<int, std:
   if (solve_enabled) {
     optimization();
     if (!last_error.empty()) return;
-    if (!USE_MCC) { std::set<int> idx; movingConsistencyCheckW(idx); f_manager.removeOutlier(idx); }
+    if (!USE_MCC) { removeIndex.clear(); movingConsistencyCheckW(removeIndex); f_manager.removeOutlier(removeIndex); }
+    if (!MULTIPLE_THREAD && featureTracker) {   // :1185-1189
+      featureTracker->removeOutliers(removeIndex);
+      featureTracker->setPrediction(predictPtsInNextFrame());
+    }
   }
   slideWindow();
   f_manager.removeFailures();
@@ -1101,6 +1126,27 @@ int gf2h_append_tum(void* e, const char* path, double stamp) { return ((Estimato
 void gf2h_set_imu0(void* e, const double* acc, const double* gyr) {   // the sample the next interval starts from (acc_0 / gyr_0 of processIMU)
   Estimator* E = (Estimator*)e; E->first_imu = true; E->acc_0 = {acc[0], acc[1], acc[2]}; E->gyr_0 = {gyr[0], gyr[1], gyr[2]};
 }
+// single-threaded public API of the reference: setParameter -> inputIMU / inputImage
+void gf2h_set_tracker_parameters(void* e, int rows, int cols, int max_cnt, int min_dist, int equalize, const double* intr8) {
+  Estimator* E = (Estimator*)e; Parameters p = E->P;
+  p.ROW = rows; p.COL = cols; p.MAX_CNT = max_cnt; p.MIN_DIST = min_dist; p.FLOW_BACK = 1; p.EQUALIZE = equalize;
+  p.fx = intr8[0]; p.fy = intr8[1]; p.cx = intr8[2]; p.cy = intr8[3]; p.k1 = intr8[4]; p.k2 = intr8[5]; p.p1 = intr8[6]; p.p2 = intr8[7];
+  p.TIC = E->tic[0]; p.RIC = E->ric[0]; p.TD = E->td; p.TIO = E->tio; p.RIO = E->rio; p.SX = E->sx; p.SY = E->sy; p.SW = E->sw; p.TD_WHEEL = E->td_wheel;
+  p.MIN_PARALLAX = E->f_manager.MIN_PARALLAX;
+  E->setParameter(p);
+}
+int gf2h_input_image(void* e, double t, const uint8_t* img, const uint16_t* depth) {
+  Estimator* E = (Estimator*)e; E->inputImage(t, img, depth);
+  return E->lastError()[0] ? -1 : (E->marginalization_flag == Estimator::MARGIN_OLD ? 0 : 1);
+}
+// the tracker's current feature table rows [id, x, y, 1, u, v, vx, vy, depth, track_cnt] (used to fill the first window in the replay test)
+int gf2h_estimator_track_only(void* e, double t, const uint8_t* img, const uint16_t* depth, int max_n, double* out10);
+void* gf2h_sync_create() { return new ImagePairSynchronizer(); }
+void gf2h_sync_destroy(void* s) { delete (ImagePairSynchronizer*)s; }
+void gf2h_sync_push(void* s, int which, double t, int handle) { if (which) ((ImagePairSynchronizer*)s)->push1(t, handle); else ((ImagePairSynchronizer*)s)->push0(t, handle); }
+int gf2h_sync_next(void* s, double* t, int* h0, int* h1, int* thrown2) {
+  ImagePairSynchronizer* S = (ImagePairSynchronizer*)s; const bool ok = S->next(t, h0, h1); thrown2[0] = S->thrown0; thrown2[1] = S->thrown1; return ok ? 1 : 0;
+}
 void gf2h_set_solve_enabled(void* e, int on) { ((Estimator*)e)->solve_enabled = on != 0; }
 void gf2h_input_imu(void* e, double t, const double* acc, const double* gyr) { ((Estimator*)e)->inputIMU(t, {acc[0], acc[1], acc[2]}, {gyr[0], gyr[1], gyr[2]}); }
 void gf2h_input_wheel(void* e, double t, const double* vel, const double* gyr) { ((Estimator*)e)->inputWheel(t, {vel[0], vel[1], vel[2]}, {gyr[0], gyr[1], gyr[2]}); }
@@ -1185,6 +1231,10 @@ int gf2h_tracker_track(void* t, double time, const uint8_t* img, const uint16_t*
     o[0] = T->ids[i]; for (int c = 0; c < 8; c++) o[1 + c] = v[c]; o[9] = T->track_cnt[i];
   }
   return k;
+}
+int gf2h_estimator_track_only(void* e, double t, const uint8_t* img, const uint16_t* depth, int max_n, double* out10) {
+  Estimator* E = (Estimator*)e; if (!E->featureTracker) return -1;
+  return gf2h_tracker_track(E->featureTracker, t, img, depth, max_n, out10);
 }
 int gf2h_tracker_mask(void* t, uint8_t* out) { FeatureTracker* T = (FeatureTracker*)t; memcpy(out, T->mask.data(), T->mask.size()); return (int)T->mask.size(); }
 const char* gf2h_tracker_last_error(void* t) { return ((FeatureTracker*)t)->lastError(); }

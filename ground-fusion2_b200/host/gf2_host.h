@@ -141,6 +141,20 @@ struct MarginalizationPrior {
   std::vector<gf2_prior_block> blocks;       // keep_block_size / idx / data with the block each one maps to
 };
 
+class FeatureTracker;
+
+// sync_process of the node for the RGB-D configuration (VE/rosNodeTest.cpp:305-598, the non-YOLO branch :395-428): colour and depth messages are
+// paired when their stamps differ by at most 3 ms; the older unmatched head is thrown away.
+class ImagePairSynchronizer {
+ public:
+  void push0(double t, int handle) { img0_buf.push({t, handle}); }
+  void push1(double t, int handle) { img1_buf.push({t, handle}); }
+  bool next(double* time, int* handle0, int* handle1);   // one pass of the loop body; false = nothing to pair yet
+  int thrown0 = 0, thrown1 = 0;
+ private:
+  std::queue<std::pair<double, int>> img0_buf, img1_buf;
+};
+
 class Estimator {
  public:
   Estimator();
@@ -155,6 +169,12 @@ class Estimator {
   void inputIMU(double t, const Vector3d& linearAcceleration, const Vector3d& angularVelocity);
   void inputWheel(double t, const Vector3d& linearVelocity, const Vector3d& angularVelocity);
   void inputFeature(double t, const FeatureFrame& featureFrame);   // what inputImage pushes after trackImage (:232-236)
+  // estimator.cpp:213-242 with MULTIPLE_THREAD == 0: trackImage on the device, push, processMeasurements; after the solve the tracker gets
+  // removeOutliers + the prediction for the next frame (:1185-1189). _img: ROW x COL bytes, _img1: depth in millimetres or null.
+  void inputImage(double t, const uint8_t* _img, const uint16_t* _img1 = nullptr);
+  FeatureTracker* featureTracker = nullptr;   // owned; created by setParameter
+  int inputImageCnt = 0;
+  bool MULTIPLE_THREAD = false;
   bool IMUAvailable(double t) const;
   bool WheelAvailable(double t) const;
   bool getIMUInterval(double t0, double t1, std::vector<std::pair<double, Vector3d>>& accVector, std::vector<std::pair<double, Vector3d>>& gyrVector);

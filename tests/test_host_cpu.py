@@ -468,3 +468,21 @@ def test_process_measurements_interval_extraction_and_sample_timing():
     h = np.zeros(11); cnt = np.zeros(2, np.int32); L.gf2h_get_headers(e, H.p(h), H.p(cnt))
     assert cnt.tolist() == [4, 0] and h[9] == 1.3 and h[8] == 1.2
     L.gf2h_estimator_destroy(e)
+
+
+def test_image_pair_synchronizer():
+    """sync_process for RGB-D (VE/rosNodeTest.cpp:395-428): colour / depth stamps within 3 ms pair up, the older unmatched head is dropped."""
+    L = H.lib(); L.gf2h_sync_create.restype = C.c_void_p
+    s = C.c_void_p(L.gf2h_sync_create())
+    t0 = [0.100, 0.200, 0.300, 0.400, 0.500]           # colour
+    t1 = [0.0995, 0.2031, 0.3029, 0.4000, 0.6000]      # depth: 2nd is 3.1 ms late (no match), 3rd 2.9 ms late (match)
+    for i, t in enumerate(t0): L.gf2h_sync_push(s, 0, C.c_double(t), i)
+    for i, t in enumerate(t1): L.gf2h_sync_push(s, 1, C.c_double(t), 100 + i)
+    got = []; thrown = np.zeros(2, np.int32)
+    while True:
+        t = C.c_double(0); h0 = C.c_int(0); h1 = C.c_int(0)
+        if not L.gf2h_sync_next(s, C.byref(t), C.byref(h0), C.byref(h1), H.p(thrown)): break
+        got.append((round(t.value, 4), h0.value, h1.value))
+    # 0.2 colour is older than 0.2031 - 3 ms -> thrown; then 0.3 colour vs 0.2031 depth: depth is older -> thrown; 0.3 / 0.3029 pair; 0.5 colour is thrown against 0.6 depth
+    assert got == [(0.1, 0, 100), (0.3, 2, 102), (0.4, 3, 103)] and thrown.tolist() == [2, 1]
+    L.gf2h_sync_destroy(s)
