@@ -801,7 +801,8 @@ void Estimator::slideWindowOld() {   // :3870-3899 with solver_flag == NON_LINEA
   f_manager.removeBackShiftDepth(R0, {back_P0.x + a.x, back_P0.y + a.y, back_P0.z + a.z}, R1, {Ps[0].x + b.x, Ps[0].y + b.y, Ps[0].z + b.z});
 }
 // processImage, the `else // not ini` branch (:1133-1215): keyframe decision, depth initialisation, solve + marginalization, moving-consistency
-// outlier removal, window slide. failureDetection / GNSS / line features / the image-frame map of the initialiser are outside this build.
+// outlier removal, window slide. failureDetection() returns false on its first line in the reference (:2910), so nothing is lost by not calling it;
+// GNSS / line features / the image-frame map of the initialiser are outside this build.
 void Estimator::processImage(const std::map<int, std::vector<std::pair<int, std::vector<double>>>>& image, double header) {
   marginalization_flag = f_manager.addFeatureCheckParallax(frame_count, image, td) ? MARGIN_OLD : MARGIN_SECOND_NEW;   // :900-911
   Headers[frame_count] = header;
