@@ -6,6 +6,7 @@
 #include <cstdlib>
 
 namespace gf2host {
+constexpr int kMaxWheelSamples = 64;  // per wheel preintegration interval
 constexpr int kMaxImuSamples = 256;   // per preintegration interval (MARGIN_SECOND_NEW merges intervals)
 
 // ------------------------------------------------------------------------------------------------ small math
@@ -463,7 +464,7 @@ void Estimator::optimization() {
     gf2_solver_cfg cfg; memset(&cfg, 0, sizeof(cfg));
     cfg.device = 0; cfg.max_windows = 1; cfg.n_frames = WINDOW_SIZE + 1; cfg.max_landmarks = NUM_OF_F; cfg.max_obs = NUM_OF_F * (WINDOW_SIZE + 1);
     cfg.max_imu_samples = kMaxImuSamples; cfg.max_prior_rows = GF2_MAX_PRIOR_DIM;
-    cfg.use_wheel = (P.USE_WHEEL && !P.ONLY_INITIAL_WITH_WHEEL) ? 1 : 0; cfg.max_wheel_samples = cfg.use_wheel ? 32 : 0;
+    cfg.use_wheel = (P.USE_WHEEL && !P.ONLY_INITIAL_WITH_WHEEL) ? 1 : 0; cfg.max_wheel_samples = cfg.use_wheel ? kMaxWheelSamples : 0;
     if (gf2_solver_create(&cfg, &gf2) != GF2_OK) { last_error = gf2_last_error(); gf2 = nullptr; return; }
   }
   if (F != WINDOW_SIZE + 1) { last_error = "gf2host::Estimator::optimization handles the steady state frame_count == WINDOW_SIZE"; return; }
@@ -514,17 +515,19 @@ void Estimator::optimization() {
   }
   // raw wheel samples of every interval -> device preintegration (WheelIntegrationBase::push_back chain), estimator.cpp:3181-3212
   if (rc == GF2_OK && wheel_on) {
-    std::vector<gf2_wheel_sample> smp((size_t)(F - 1) * 32); std::vector<int32_t> ns(F - 1, 0); std::vector<double> first((F - 1) * 6, 0.0), lin((F - 1) * 4, 0.0);
+    std::vector<gf2_wheel_sample> smp((size_t)(F - 1) * kMaxWheelSamples); std::vector<int32_t> ns(F - 1, 0); std::vector<double> first((F - 1) * 6, 0.0), lin((F - 1) * 4, 0.0);
     for (int j = 1; j < F; j++) {
       const WheelIntegrationBase* pi = pre_integrations_wheel[j];
       if (!pi) { last_error = "pre_integrations_wheel[j] missing"; return; }
-      const int n = (int)std::min<size_t>(pi->dt_buf.size(), 32);
+      if (pi->dt_buf.size() > (size_t)kMaxWheelSamples) { last_error = "a wheel interval holds more samples than the device buffer (kMaxWheelSamples)"; return; }
+      const int n = (int)pi->dt_buf.size();
       ns[j - 1] = n;
-      for (int k = 0; k < n; k++) { gf2_wheel_sample& o = smp[(size_t)(j - 1) * 32 + k]; o.dt = pi->dt_buf[k]; o.vel[0] = pi->vel_buf[k].x; o.vel[1] = pi->vel_buf[k].y; o.vel[2] = pi->vel_buf[k].z; o.gyr[0] = pi->gyr_buf[k].x; o.gyr[1] = pi->gyr_buf[k].y; o.gyr[2] = pi->gyr_buf[k].z; }
+      for (int k = 0; k < n; k++) { gf2_wheel_sample& o = smp[(size_t)(j - 1) * kMaxWheelSamples + k]; o.dt = pi->dt_buf[k]; o.vel[0] = pi->vel_buf[k].x; o.vel[1] = pi->vel_buf[k].y; o.vel[2] = pi->vel_buf[k].z; o.gyr[0] = pi->gyr_buf[k].x; o.gyr[1] = pi->gyr_buf[k].y; o.gyr[2] = pi->gyr_buf[k].z; }
       double* f6 = &first[(j - 1) * 6]; f6[0] = pi->linearized_vel.x; f6[1] = pi->linearized_vel.y; f6[2] = pi->linearized_vel.z; f6[3] = pi->linearized_gyr.x; f6[4] = pi->linearized_gyr.y; f6[5] = pi->linearized_gyr.z;
       double* l4 = &lin[(j - 1) * 4]; l4[0] = pi->linearized_sx; l4[1] = pi->linearized_sy; l4[2] = pi->linearized_sw; l4[3] = pi->linearized_td;
     }
     const double noise[2] = {P.VEL_N_wheel, P.GYR_N_wheel};
+    if (capture) { cap.wheel_samples = smp; cap.wheel_n = ns; cap.wheel_first = first; cap.wheel_lin = lin; }
     rc = gf2_wheel_preintegrate(gf2, 0, 1, smp.data(), ns.data(), first.data(), lin.data(), noise);
     if (rc == GF2_OK && wdetect && wheelanomaly) {  // "wheel anomaly, skip optimization" (:3195-3199): no wheel factor enters the problem
       std::vector<gf2_wheel_preint> rec(F - 1);
@@ -557,14 +560,17 @@ void Estimator::optimization() {
     if ((wheel_on && P.ESTIMATE_INTRINSIC_WHEEL && frame_count == WINDOW_SIZE && v0 > 0.2) || openIxEstimation) openIxEstimation = true; else o.const_mask |= GF2_CONST_WHEEL_INTRINSIC;
     if (!P.ESTIMATE_TD_WHEEL || v0 < 0.2) o.const_mask |= GF2_CONST_TD_WHEEL;
     o.max_time_s = 0;  // SOLVER_TIME is a wall-clock cap: machine dependent, not reproduced
-    if (capture) { cap.const_mask = o.const_mask; cap.marg_mode = marginalization_flag == MARGIN_OLD ? 0 : 1; }
+    if (capture) {
+      cap.const_mask = o.const_mask; cap.marg_mode = marginalization_flag == MARGIN_OLD ? 0 : 1; cap.use_wheel = wheel_on ? 1 : 0;
+      memcpy(cap.exw, para_Ex_Pose_wheel[0], sizeof(cap.exw)); memcpy(cap.sxsysw, sxsysw, sizeof(cap.sxsysw)); cap.tdw = para_Td_wheel[0][0];
+    }
     rc = gf2_solve(gf2, 0, 1, &o, &last_summary);
   }
   if (rc == GF2_OK) rc = gf2_get_states(gf2, 0, 1, &para_Pose[0][0], &para_SpeedBias[0][0], para_Ex_Pose[0], para_Td[0], wheel_on ? para_Ex_Pose_wheel[0] : nullptr, wheel_on ? sxsysw : nullptr, wheel_on ? para_Td_wheel[0] : nullptr);
   if (rc == GF2_OK) { rc = gf2_get_landmarks(gf2, 0, 1, invdep.data()); for (int i = 0; i < n_lm; i++) para_Feature[i][0] = invdep[i]; }
   if (rc != GF2_OK) { last_error = gf2_last_error(); return; }  // the reference logs and carries on (no exceptions)
   if (wheel_on) { para_Ix_sx_wheel[0][0] = sxsysw[0]; para_Ix_sy_wheel[0][0] = sxsysw[1]; para_Ix_sw_wheel[0][0] = sxsysw[2]; }
-  if (capture) { memcpy(cap.pose_out, para_Pose, sizeof(cap.pose_out)); memcpy(cap.sb_out, para_SpeedBias, sizeof(cap.sb_out)); cap.invdep_out.assign(invdep.begin(), invdep.begin() + n_lm); }
+  if (capture) { memcpy(cap.exw_out, para_Ex_Pose_wheel[0], sizeof(cap.exw_out)); memcpy(cap.pose_out, para_Pose, sizeof(cap.pose_out)); memcpy(cap.sb_out, para_SpeedBias, sizeof(cap.sb_out)); cap.invdep_out.assign(invdep.begin(), invdep.begin() + n_lm); }
   double2vector();
 
   // ---- marginalization (estimator.cpp:3394-3690): runs at the states double2vector() left (yaw / position re-anchored),
@@ -1175,6 +1181,17 @@ void gf2h_capture_get(void* e, double* pose, double* sb, double* ex_td8, double*
   for (size_t i = 0; i < c.prior_r0.size(); i++) prior_r0[i] = c.prior_r0[i];
   for (size_t i = 0; i < c.prior_blocks.size(); i++) prior_blocks[i] = c.prior_blocks[i];
   memcpy(pose_out, c.pose_out, sizeof(c.pose_out)); memcpy(sb_out, c.sb_out, sizeof(c.sb_out)); memcpy(pose_marg, c.pose_marg, sizeof(c.pose_marg)); memcpy(sb_marg, c.sb_marg, sizeof(c.sb_marg));
+}
+// wheel part of the capture: returns use_wheel; calib12 = [ex_wheel 7 | sx sy sw | td_wheel | -], exw_out 7 = para_Ex_Pose_wheel after the solve
+int gf2h_capture_get_wheel(void* e, gf2_wheel_sample* samples /*[10][kMaxWheelSamples = 64]*/, int32_t* n, double* first, double* lin, double* calib12, double* exw_out) {
+  const Estimator::Capture& c = ((Estimator*)e)->cap;
+  for (size_t i = 0; i < c.wheel_samples.size(); i++) samples[i] = c.wheel_samples[i];
+  for (size_t i = 0; i < c.wheel_n.size(); i++) n[i] = c.wheel_n[i];
+  for (size_t i = 0; i < c.wheel_first.size(); i++) first[i] = c.wheel_first[i];
+  for (size_t i = 0; i < c.wheel_lin.size(); i++) lin[i] = c.wheel_lin[i];
+  memcpy(calib12, c.exw, sizeof(c.exw)); calib12[7] = c.sxsysw[0]; calib12[8] = c.sxsysw[1]; calib12[9] = c.sxsysw[2]; calib12[10] = c.tdw; calib12[11] = 0.0;
+  memcpy(exw_out, c.exw_out, sizeof(c.exw_out));
+  return c.use_wheel;
 }
 int gf2h_process_image(void* e, int n, const int* ids, const double* pts8, double header) {
   Estimator* E = (Estimator*)e; E->processImage(image_of(n, ids, pts8), header);

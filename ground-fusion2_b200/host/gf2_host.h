@@ -206,6 +206,8 @@ class Estimator {
     std::vector<gf2_imu_sample> imu_samples; std::vector<int32_t> imu_n; std::vector<double> imu_first, imu_bias;
     int32_t prior_rows = 0, prior_nblocks = 0; std::vector<double> prior_J0, prior_r0; std::vector<gf2_prior_block> prior_blocks;
     uint32_t const_mask = 0; int32_t marg_mode = 0;
+    int32_t use_wheel = 0; std::vector<gf2_wheel_sample> wheel_samples; std::vector<int32_t> wheel_n; std::vector<double> wheel_first, wheel_lin;
+    double exw[7], sxsysw[3], tdw, exw_out[7];
     double pose_out[(WINDOW_SIZE + 1) * 7], sb_out[(WINDOW_SIZE + 1) * 9]; std::vector<double> invdep_out;   // straight from gf2_get_states / gf2_get_landmarks
     double pose_marg[(WINDOW_SIZE + 1) * 7], sb_marg[(WINDOW_SIZE + 1) * 9]; std::vector<double> invdep_marg;  // the states gf2_marginalize ran at
   };

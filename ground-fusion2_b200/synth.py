@@ -385,7 +385,7 @@ def lio_scene(seed=0, n_map_points=60000, n_keypoints=3000, size_voxel_map=0.2, 
             "translation_begin": t - np.array([0.05, 0.0, 0.0]), "size_voxel_map": size_voxel_map, "max_points_per_voxel": max_points_per_voxel}
 
 
-def _arc_trajectory(rng, n_frames, speed, yaw_rate, frame_dt, imu_hz, pause):
+def _arc_trajectory(rng, n_frames, speed, yaw_rate, frame_dt, imu_hz, pause, wheel_hz=0):
     """Ground truth of the replay streams: planar arc with an optional stop, IMU samples with the m3dgr noise / bias."""
     Ric = BODY_T_CAM0[:3, :3]; tic = BODY_T_CAM0[:3, 3]
     n_imu = int(round(frame_dt * imu_hz)); dt = 1.0 / imu_hz
@@ -420,11 +420,25 @@ def _arc_trajectory(rng, n_frames, speed, yaw_rate, frame_dt, imu_hz, pause):
         s0 = fidx[k]
         smp = np.zeros(n_imu, abi.IMU_SAMPLE); smp["dt"] = dt; smp["acc"] = acc_b[s0 + 1:s0 + 1 + n_imu]; smp["gyr"] = gyr_b[s0 + 1:s0 + 1 + n_imu]
         imu.append({"first": np.concatenate([acc_b[s0], gyr_b[s0]]), "samples": smp})
-    return {"gtp": gtp, "gtR": gtR, "gtv": gtv, "Rwc": Rwc, "twc": twc, "imu": imu, "ba": ba, "bg": bg, "Ric": Ric, "tic": tic}
+    out = {"gtp": gtp, "gtR": gtR, "gtv": gtv, "Rwc": Rwc, "twc": twc, "imu": imu, "ba": ba, "bg": bg, "Ric": Ric, "tic": tic}
+    if wheel_hz:   # wheel odometer (drawn after everything else so that the IMU / image streams do not depend on it). The odometer frame is
+        # ALIGNED with the body frame (R_io = I, a small lever arm): Estimator::processWheel dead-reckons the newest frame with the raw wheel
+        # velocity / yaw rate as if they were body quantities (estimator.cpp:871-876, the RIO factor is commented out there)
+        n_sub = imu_hz // wheel_hz; n_whl = n_imu // n_sub
+        out["Rio"] = np.eye(3); out["tio"] = np.array([0.0, 0.05, -0.1])
+        wheel = []
+        for k in range(n_frames - 1):
+            idx = fidx[k] + n_sub * np.arange(n_whl + 1)
+            vel_o = np.zeros((n_whl + 1, 3)); vel_o[:, 2] = v_t[idx]; gyr_o = np.zeros((n_whl + 1, 3)); gyr_o[:, 1] = -kappa * v_t[idx]   # body z forward, yaw about -y
+            vel_o += rng.normal(0, WHEEL_VEL_N, vel_o.shape); gyr_o += rng.normal(0, WHEEL_GYR_N, gyr_o.shape)
+            smp = np.zeros(n_whl, abi.WHEEL_SAMPLE); smp["dt"] = 1.0 / wheel_hz; smp["vel"] = vel_o[1:]; smp["gyr"] = gyr_o[1:]
+            wheel.append({"first": np.concatenate([vel_o[0], gyr_o[0]]), "samples": smp})
+        out["wheel"] = wheel
+    return out
 
 
 def feature_stream(seed=0, n_frames=45, target_features=150, speed=1.0, yaw_rate=0.2, frame_dt=0.1, imu_hz=200, pixel_noise=0.5,
-                   max_life=30, depth_range=(1.5, 12.0), pause=None):
+                   max_life=30, depth_range=(1.5, 12.0), pause=None, wheel_hz=0):
     """A synthetic stream for the steady-state replay (BASELINE.json config 5 shape, visual-inertial part): a planar arc like
     make_windows, IMU samples at imu_hz with the m3dgr noise / bias, and per frame the feature map processImage receives:
     id -> [x, y, 1, u, v, vx, vy, depth] (float32-representable x, y, velocities by finite difference, RGB-D depth below 4 m, 0 = invalid).
@@ -434,6 +448,10 @@ def feature_stream(seed=0, n_frames=45, target_features=150, speed=1.0, yaw_rate
     rng = np.random.Generator(np.random.PCG64(BASE_SEED + 5000 + seed))
     tr = _arc_trajectory(rng, n_frames, speed, yaw_rate, frame_dt, imu_hz, pause)
     gtp, gtR, gtv, Rwc, twc, imu, ba, bg, Ric, tic = (tr[k] for k in ("gtp", "gtR", "gtv", "Rwc", "twc", "imu", "ba", "bg", "Ric", "tic"))
+    wheel_part = {}
+    if wheel_hz:   # a second generator: the feature / IMU streams stay identical with and without the wheel stream
+        trw = _arc_trajectory(np.random.Generator(np.random.PCG64(BASE_SEED + 5000 + seed)), n_frames, speed, yaw_rate, frame_dt, imu_hz, pause, wheel_hz)
+        wheel_part = {"wheel": trw["wheel"], "rio": trw["Rio"], "tio": trw["tio"], "wheel_noise": np.array([WHEEL_VEL_N, WHEEL_GYR_N])}
     lm = {}       # id -> (Xw, birth frame)
     prev_xy = {}
     next_id = 0
@@ -460,7 +478,7 @@ def feature_stream(seed=0, n_frames=45, target_features=150, speed=1.0, yaw_rate
             prev_xy[i] = (xn, yn)
         frames.append({"ids": ids, "pts": pts, "header": 100.0 + f * frame_dt})
     return {"frames": frames, "imu": imu, "gt_p": gtp, "gt_R": gtR, "gt_v": gtv, "ba": ba, "bg": bg, "ric": Ric, "tic": tic,
-            "imu_noise": np.array([ACC_N, GYR_N, ACC_W, GYR_W]), "n_frames": n_frames, "landmarks_total": next_id}
+            "imu_noise": np.array([ACC_N, GYR_N, ACC_W, GYR_W]), "n_frames": n_frames, "landmarks_total": next_id, **wheel_part}
 
 
 def render_stream(seed=0, n_frames=40, speed=1.0, yaw_rate=0.2, frame_dt=0.1, imu_hz=200, pause=None, room=(9.0, 9.0, 3.0), texel=0.015):

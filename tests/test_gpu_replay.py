@@ -245,3 +245,84 @@ def test_public_single_thread_api_input_imu_input_image(gf2, oracle):
     assert 0 in flags and max(errs) < 0.25, (flags, max(errs))     # observed 0.12 m: with the prediction the tracks live longer, fewer keyframes
     print(f"inputIMU/inputImage replay: {len(flags)} frames, {flags.count(0)} keyframes, max position error {max(errs):.3f} m, worst oracle deviation {worst:.2e}")
     L.gf2h_estimator_destroy(e)
+
+
+def test_replay_with_wheel_odometer_and_free_wheel_extrinsic(gf2, oracle):
+    """wheel: 1, estimate_wheel_extrinsic: 1 (gc_test / groundchallenge / idc_rs / m2dgrp .yaml) in the loop: processWheel buffers the 50 Hz odometer
+    and dead-reckons the newest frame, the solve frees body_T_wheel (openExWheelEstimation), the marginalization keeps the wheel calibration blocks;
+    every step against the oracle on identical inputs (incl. the wheel samples), trajectory against ground truth."""
+    synth = importlib.import_module("gf2_b200.synth")
+    abi = gf2.abi
+    L = H.lib()
+    st = synth.feature_stream(0, n_frames=30, pause=(20, 23), wheel_hz=50)
+    e = C.c_void_p(L.gf2h_estimator_create())
+    L.gf2h_set_extrinsic(e, H.p(st["tic"].copy()), H.p(st["ric"].copy()), C.c_double(0.0), C.c_double(synth.G_NORM), H.p(st["imu_noise"]))
+    calib = np.concatenate([st["tio"], st["rio"].ravel(), [1.0, 1.0, 1.0, 0.0]])
+    L.gf2h_set_wheel_parameters(e, H.p(calib), H.p(np.array([1.0, 1.0, 0.0, 0.0, st["wheel_noise"][0], st["wheel_noise"][1]])))
+    L.gf2h_set_flags(e, 1, 1, 1, 0)
+    L.gf2h_set_min_parallax(e, C.c_double(10.0 / 460.0))
+    rng = np.random.default_rng(1)
+    P = st["gt_p"][:11].copy() + rng.normal(0, 0.01, (11, 3)); R = st["gt_R"][:11].copy(); V = st["gt_v"][:11].copy()
+    P[10] = P[9]; R[10] = R[9]; V[10] = V[9]
+    L.gf2h_set_frame_states(e, H.p(H.frame_states(P, R, V, np.zeros((11, 3)), np.zeros((11, 3)))))
+    for f in range(10):
+        fr = st["frames"][f]
+        L.gf2h_add_image(e, f, len(fr["ids"]), H.p(fr["ids"]), H.p(fr["pts"]), C.c_double(0.0))
+    for j in range(1, 10):
+        iv = st["imu"][j - 1]
+        L.gf2h_new_interval(e, j, H.p(iv["first"][:3].copy()), H.p(iv["first"][3:].copy()), H.p(np.zeros(3)), H.p(np.zeros(3)))
+        for s in iv["samples"]:
+            L.gf2h_push_imu(e, j, C.c_double(s["dt"]), H.p(s["acc"].copy()), H.p(s["gyr"].copy()))
+        wv = st["wheel"][j - 1]
+        L.gf2h_new_wheel_interval(e, j, H.p(wv["first"][:3].copy()), H.p(wv["first"][3:].copy()))
+        for s in wv["samples"]:
+            L.gf2h_push_wheel(e, j, C.c_double(s["dt"]), H.p(s["vel"].copy()), H.p(s["gyr"].copy()))
+    L.gf2h_set_imu0(e, H.p(st["imu"][9]["first"][:3].copy()), H.p(st["imu"][9]["first"][3:].copy()))
+    w0 = st["wheel"][9]["first"]
+    L.gf2h_process_wheel(e, C.c_double(0.0), C.c_double(0.0), H.p(w0[:3].copy()), H.p(w0[3:].copy()))   # the sample at the image time: sets vel_0 / gyr_0 of the next interval, dt = 0
+    pose = np.zeros((11, 7)); sbv = np.zeros((11, 9)); exv = np.zeros(7)
+    L.gf2h_vector2double(e, H.p(pose), H.p(sbv), H.p(exv))
+    blk = np.zeros(1, abi.PRIOR_BLOCK); blk["kind"] = abi.BLK_POSE; blk["x0"][0, :7] = pose[0]
+    L.gf2h_set_prior(e, 6, H.p(np.eye(6) * 100.0), H.p(np.zeros(6)), 1, H.p(blk))
+    L.gf2h_set_capture(e, 1)
+    flags, errs, worst, worst_cal = [], [], 0.0, 0.0
+    for k in range(10, st["n_frames"]):
+        for s in st["imu"][k - 1]["samples"]:
+            L.gf2h_process_imu(e, C.c_double(0.0), C.c_double(s["dt"]), H.p(s["acc"].copy()), H.p(s["gyr"].copy()))
+        for s in st["wheel"][k - 1]["samples"]:
+            L.gf2h_process_wheel(e, C.c_double(0.0), C.c_double(s["dt"]), H.p(s["vel"].copy()), H.p(s["gyr"].copy()))
+        fr = st["frames"][k]
+        flag = L.gf2h_process_image(e, len(fr["ids"]), H.p(fr["ids"]), H.p(fr["pts"]), C.c_double(fr["header"]))
+        assert flag >= 0, L.gf2h_last_error(e)
+        flags.append(flag)
+        c = _capture(L, e, abi)
+        ws = np.zeros((10, 64), abi.WHEEL_SAMPLE); wn = np.zeros(10, np.int32); wf = np.zeros((10, 6)); wl = np.zeros((10, 4)); cal = np.zeros(12); exw_out = np.zeros(7)
+        assert L.gf2h_capture_get_wheel(e, H.p(ws), H.p(wn), H.p(wf), H.p(wl), H.p(cal), H.p(exw_out)) == 1
+        assert not (c["const_mask"] & abi.CONST_EX_WHEEL) and (c["const_mask"] & abi.CONST_WHEEL_INTRINSIC)     # extrinsic free (|Vs[0]| > 0.2 latched), intrinsics fixed
+        opts = abi.default_opts(const_mask=c["const_mask"])
+        w = _oracle_window(c, st["imu_noise"], abi)
+        w.update(use_wheel=True, ex_pose_wheel=cal[None, :7].copy(), sxsysw=cal[None, 7:10].copy(), td_wheel=cal[10:11].copy(), wheel_samples=ws[None].copy(), wheel_n=wn[None].copy(),
+                 wheel_first=wf[None].copy(), wheel_lin=wl[None].copy(), wheel_noise=st["wheel_noise"])
+        oracle.imu_preintegrate(w); oracle.wheel_preintegrate(w)
+        start_cal = w["ex_pose_wheel"].copy()
+        oracle.solve_batch(w, opts)
+        scale = np.abs(w["para_pose"][0, :, :3]).max()
+        d = max(np.abs(c["pose_out"][:, :3] - w["para_pose"][0, :, :3]).max() / scale, np.abs(c["pose_out"][:, 3:] - w["para_pose"][0, :, 3:]).max())
+        worst = max(worst, d)
+        assert d <= 1e-4, (k, d)
+        moved = np.abs(w["ex_pose_wheel"] - start_cal).max()
+        dc = np.abs(exw_out - w["ex_pose_wheel"][0]).max()
+        worst_cal = max(worst_cal, dc / max(moved, 1e-12))
+        assert dc <= 1e-3 * moved + 1e-9, (k, dc, moved)
+        out = np.zeros((11, 21)); L.gf2h_get_frame_states(e, H.p(out))
+        errs.append(np.linalg.norm(out[9, :3] - st["gt_p"][k]))
+    cal16 = np.zeros(16); of = np.zeros(2, np.int32); L.gf2h_get_wheel_states(e, H.p(cal16), H.p(of))
+    assert of.tolist() == [1, 0] and 0 in flags and 1 in flags
+    assert max(errs) < 0.15, (max(errs), errs)
+    nn = C.c_int(0); nb = C.c_int(0); stt = C.c_int(0)
+    J0 = np.zeros(96 * 96); r0 = np.zeros(96); blocks = np.zeros(30, abi.PRIOR_BLOCK)
+    L.gf2h_get_prior(e, C.byref(nn), H.p(J0), H.p(r0), C.byref(nb), H.p(blocks), C.byref(stt))
+    assert abi.BLK_EX_WHEEL in set(int(b["kind"]) for b in blocks[:nb.value])                                 # the wheel calibration lives on in the prior
+    print(f"wheel replay: {len(flags)} frames, {flags.count(0)} keyframes, max position error {max(errs):.3f} m, worst oracle deviation {worst:.2e}, "
+          f"calibration deviation / motion {worst_cal:.2e}, |tio - truth| = {np.abs(cal16[:3] - st['tio']).max():.3f} m")
+    L.gf2h_estimator_destroy(e)
