@@ -603,7 +603,30 @@ void Estimator::optimization() {
 }
 
 // ---- measurement queues (estimator.cpp:324-372, 422-545, 554-763) ---------------------------------------------------------------------
-void Estimator::inputIMU(double t, const Vector3d& a, const Vector3d& g) { accBuf.push({t, a}); gyrBuf.push({t, g}); }            // fastPredictIMU / publishers: outside this build
+void Estimator::inputIMU(double t, const Vector3d& a, const Vector3d& g) {   // :324-352 (the publishers are outside this build)
+  accBuf.push({t, a}); gyrBuf.push({t, g});
+  if (latest_valid) fastPredictIMU(t, a, g);
+}
+void Estimator::fastPredictIMU(double t, const Vector3d& linear_acceleration, const Vector3d& angular_velocity) {   // :4076-4093
+  const double dt = t - latest_time; latest_time = t;
+  const Vector3d g = {0.0, 0.0, P.G_NORM};
+  auto sub = [](const Vector3d& a, const Vector3d& b) { return Vector3d{a.x - b.x, a.y - b.y, a.z - b.z}; };
+  const Vector3d un_acc_0 = sub(mul(latest_Q, sub(latest_acc_0, latest_Ba)), g);
+  const Vector3d un_gyr = sub(Vector3d{0.5 * (latest_gyr_0.x + angular_velocity.x), 0.5 * (latest_gyr_0.y + angular_velocity.y), 0.5 * (latest_gyr_0.z + angular_velocity.z)}, latest_Bg);
+  latest_Q = mul(latest_Q, toRotationMatrix(normalized({1.0, un_gyr.x * dt / 2.0, un_gyr.y * dt / 2.0, un_gyr.z * dt / 2.0})));   // latest_Q * Utility::deltaQ(un_gyr * dt)
+  const Vector3d un_acc_1 = sub(mul(latest_Q, sub(linear_acceleration, latest_Ba)), g);
+  const Vector3d un_acc = {0.5 * (un_acc_0.x + un_acc_1.x), 0.5 * (un_acc_0.y + un_acc_1.y), 0.5 * (un_acc_0.z + un_acc_1.z)};
+  latest_P = {latest_P.x + dt * latest_V.x + 0.5 * dt * dt * un_acc.x, latest_P.y + dt * latest_V.y + 0.5 * dt * dt * un_acc.y, latest_P.z + dt * latest_V.z + 0.5 * dt * dt * un_acc.z};
+  latest_V = {latest_V.x + dt * un_acc.x, latest_V.y + dt * un_acc.y, latest_V.z + dt * un_acc.z};
+  latest_acc_0 = linear_acceleration; latest_gyr_0 = angular_velocity;
+}
+void Estimator::updateLatestStates() {   // :4203-4228
+  latest_time = Headers[frame_count] + td;
+  latest_P = Ps[frame_count]; latest_Q = Rs[frame_count]; latest_V = Vs[frame_count]; latest_Ba = Bas[frame_count]; latest_Bg = Bgs[frame_count];
+  latest_acc_0 = acc_0; latest_gyr_0 = gyr_0; latest_valid = true;
+  std::queue<std::pair<double, Vector3d>> tmp_accBuf = accBuf, tmp_gyrBuf = gyrBuf;
+  while (!tmp_accBuf.empty()) { fastPredictIMU(tmp_accBuf.front().first, tmp_accBuf.front().second, tmp_gyrBuf.front().second); tmp_accBuf.pop(); tmp_gyrBuf.pop(); }
+}
 void Estimator::inputWheel(double t, const Vector3d& v, const Vector3d& g) { wheelVelBuf.push({t, v}); wheelGyrBuf.push({t, g}); }
 void Estimator::inputFeature(double t, const FeatureFrame& f) { featureBuf.push({t, f}); }
 bool Estimator::IMUAvailable(double t) const { return !accBuf.empty() && t <= accBuf.back().first; }
@@ -828,6 +851,7 @@ void Estimator::processImage(const std::map<int, std::vector<std::pair<int, std:
   slideWindow();
   f_manager.removeFailures();
   last_R0 = Rs[0]; last_P0 = Ps[0];
+  updateLatestStates();   // :1214
 }
 
 // ------------------------------------------------------------------------------------------------ FeatureTracker
@@ -1153,6 +1177,12 @@ void gf2h_sync_destroy(void* s) { delete (ImagePairSynchronizer*)s; }
 void gf2h_sync_push(void* s, int which, double t, int handle) { if (which) ((ImagePairSynchronizer*)s)->push1(t, handle); else ((ImagePairSynchronizer*)s)->push0(t, handle); }
 int gf2h_sync_next(void* s, double* t, int* h0, int* h1, int* thrown2) {
   ImagePairSynchronizer* S = (ImagePairSynchronizer*)s; const bool ok = S->next(t, h0, h1); thrown2[0] = S->thrown0; thrown2[1] = S->thrown1; return ok ? 1 : 0;
+}
+void gf2h_update_latest_states(void* e) { ((Estimator*)e)->updateLatestStates(); }
+void gf2h_get_latest(void* e, double* out16 /* time, P 3, R 9 row-major, V 3 */) {
+  Estimator* E = (Estimator*)e; out16[0] = E->latest_time; out16[1] = E->latest_P.x; out16[2] = E->latest_P.y; out16[3] = E->latest_P.z;
+  for (int i = 0; i < 9; i++) out16[4 + i] = E->latest_Q.m[i];
+  out16[13] = E->latest_V.x; out16[14] = E->latest_V.y; out16[15] = E->latest_V.z;
 }
 void gf2h_set_solve_enabled(void* e, int on) { ((Estimator*)e)->solve_enabled = on != 0; }
 void gf2h_input_imu(void* e, double t, const double* acc, const double* gyr) { ((Estimator*)e)->inputIMU(t, {acc[0], acc[1], acc[2]}, {gyr[0], gyr[1], gyr[2]}); }

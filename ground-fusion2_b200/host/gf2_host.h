@@ -180,6 +180,12 @@ class Estimator {
   bool getIMUInterval(double t0, double t1, std::vector<std::pair<double, Vector3d>>& accVector, std::vector<std::pair<double, Vector3d>>& gyrVector);
   bool getWheelInterval(double t0, double t1, std::vector<std::pair<double, Vector3d>>& velVector, std::vector<std::pair<double, Vector3d>>& gyrVector);
   int processMeasurements();   // returns the number of images consumed
+  // IMU-rate pose output: fastPredictIMU (estimator.cpp:4076-4093, mid-point propagation of the latest state with every inputIMU sample) and
+  // updateLatestStates (:4203-4228, re-anchor at the newest window state after each processImage and replay the queued samples)
+  void fastPredictIMU(double t, const Vector3d& linear_acceleration, const Vector3d& angular_velocity);
+  void updateLatestStates();
+  double latest_time = 0.0; Vector3d latest_P, latest_V, latest_Ba, latest_Bg, latest_acc_0, latest_gyr_0; Matrix3d latest_Q;   // latest_Q kept as a rotation matrix
+  bool latest_valid = false;
   std::queue<std::pair<double, Vector3d>> accBuf, gyrBuf, wheelVelBuf, wheelGyrBuf;
   std::queue<std::pair<double, FeatureFrame>> featureBuf;
   double prevTime = -1.0, curTime = 0.0, prevTime_wheel = -1.0, curTime_wheel = 0.0;

@@ -486,3 +486,44 @@ def test_image_pair_synchronizer():
     # 0.2 colour is older than 0.2031 - 3 ms -> thrown; then 0.3 colour vs 0.2031 depth: depth is older -> thrown; 0.3 / 0.3029 pair; 0.5 colour is thrown against 0.6 depth
     assert got == [(0.1, 0, 100), (0.3, 2, 102), (0.4, 3, 103)] and thrown.tolist() == [2, 1]
     L.gf2h_sync_destroy(s)
+
+
+def test_fast_predict_imu_and_update_latest_states():
+    """IMU-rate output pose: updateLatestStates re-anchors at the newest window state and replays the queued samples; every later inputIMU
+    propagates it with the mid-point rule of fastPredictIMU (estimator.cpp:4076-4093, 4203-4228). Checked against a numpy restatement."""
+    L = H.lib()
+    rng = np.random.default_rng(8)
+    e = C.c_void_p(L.gf2h_estimator_create())
+    g = 9.81
+    P = rng.normal(size=(11, 3)); R = np.tile(np.eye(3), (11, 1, 1)); V = rng.normal(size=(11, 3)); Ba = np.tile([0.01, -0.02, 0.03], (11, 1)); Bg = np.tile([0.001, 0.002, -0.001], (11, 1))
+    a = 0.4; R[10] = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1.0]])
+    L.gf2h_set_frame_states(e, H.p(H.frame_states(P, R, V, Ba, Bg)))
+    L.gf2h_set_extrinsic(e, H.p(np.zeros(3)), H.p(np.eye(3)), C.c_double(0.0), C.c_double(g), H.p(np.array([0.1, 0.01, 1e-3, 1e-4])))
+    hdr = np.arange(11) * 0.1 + 3.0; L.gf2h_set_headers(e, H.p(hdr))
+    acc0 = np.array([0.1, 0.2, 9.7]); gyr0 = np.array([0.01, -0.02, 0.3])
+    L.gf2h_set_imu0(e, H.p(acc0), H.p(gyr0))
+    ts = hdr[10] + 0.005 * np.arange(1, 31); acc = rng.normal(size=(30, 3)) * 0.3 + [0, 0, 9.8]; gyr = rng.normal(size=(30, 3)) * 0.2
+    for i in range(10):                                # queued before the re-anchoring: replayed by updateLatestStates
+        L.gf2h_input_imu(e, C.c_double(ts[i]), H.p(acc[i].copy()), H.p(gyr[i].copy()))
+    L.gf2h_update_latest_states(e)
+    for i in range(10, 30):                            # afterwards every sample propagates the latest state directly
+        L.gf2h_input_imu(e, C.c_double(ts[i]), H.p(acc[i].copy()), H.p(gyr[i].copy()))
+    out = np.zeros(16); L.gf2h_get_latest(e, H.p(out))
+
+    def dq(th):
+        q = np.array([1.0, th[0] / 2, th[1] / 2, th[2] / 2]); q /= np.linalg.norm(q); w, x, y, z = q
+        return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)], [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                         [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+    t, p, Rm, v, a0, g0 = hdr[10], P[10].copy(), R[10].copy(), V[10].copy(), acc0, gyr0
+    G = np.array([0, 0, g])
+    for i in range(30):
+        dt = ts[i] - t; t = ts[i]
+        ua0 = Rm @ (a0 - Ba[10]) - G
+        ug = 0.5 * (g0 + gyr[i]) - Bg[10]
+        Rm = Rm @ dq(ug * dt)
+        ua1 = Rm @ (acc[i] - Ba[10]) - G
+        ua = 0.5 * (ua0 + ua1)
+        p = p + dt * v + 0.5 * dt * dt * ua; v = v + dt * ua
+        a0, g0 = acc[i], gyr[i]
+    assert abs(out[0] - ts[-1]) < 1e-12 and np.abs(out[1:4] - p).max() < 1e-12 and np.abs(out[4:13].reshape(3, 3) - Rm).max() < 1e-12 and np.abs(out[13:16] - v).max() < 1e-12
+    L.gf2h_estimator_destroy(e)
