@@ -353,6 +353,9 @@ int gf2_solver_create(const gf2_solver_cfg* cfg, gf2_solver** out) {
   cudaFuncSetAttribute(k_linearize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LinShared));
   cudaFuncSetAttribute(k_solve2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(Solve2Shared) + sizeof(double) * solve2_matrix_doubles(F, 1)));
   cudaFuncSetAttribute(k_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * 450 * GF2_MAX_FRAMES));
+  // function attributes are per device: set here, after cudaSetDevice, for every handle (not once per process)
+  cudaFuncSetAttribute(k_marg_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(((sizeof(MargShared) + 15) & ~size_t(15)) + sizeof(double) * kMargTMax * kMargLD));
+  cudaFuncSetAttribute(k_marg_eig, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(((sizeof(EigShared) + 15) & ~size_t(15)) + sizeof(double) * 2 * kMargKMax * (kMargKMax | 1)));
   if (cudaGetLastError() != cudaSuccess) { gf2_solver_destroy(h); return gf2::fail(GF2_ERR_CUDA, "cudaFuncSetAttribute failed (is this an sm_100a device?)"); }
   *out = h;
   return GF2_OK;
@@ -542,13 +545,15 @@ int gf2_set_prior(gf2_solver* h, int first, int n, const int32_t* n_rows, const 
   if (!n_rows) { h->has_prior = false; return GF2_OK; }
   for (int w = 0; w < n; w++) {
     if (n_rows[w] < 0 || n_rows[w] > k.Pr) return gf2::fail(GF2_ERR_INVALID, "prior of window %d has %d rows (max %d)", first + w, n_rows[w], k.Pr);
+    if (n_rows[w] > 0 && (!n_blocks || !blocks || !J0 || !r0)) return gf2::fail(GF2_ERR_INVALID, "prior of window %d has rows but a null J0 / r0 / n_blocks / blocks array", first + w);
+    if (n_rows[w] > 0 && (n_blocks[w] < 1 || n_blocks[w] > 2 * k.F + 8)) return gf2::fail(GF2_ERR_INVALID, "prior of window %d has %d blocks", first + w, n_blocks[w]);
+    if (n_blocks && (n_blocks[w] < 0 || n_blocks[w] > 2 * k.F + 8)) return gf2::fail(GF2_ERR_INVALID, "prior of window %d has %d blocks", first + w, n_blocks[w]);
     // k_solve2 stores the speed-bias rows of frame I only against frames I-1 and I (structural zeros of S and of its Cholesky
     // factor): a prior that couples speed-bias k >= 2 to far frames would break that; the reference's priors keep speed-bias 0 only
     if (blocks && n_blocks) for (int b = 0; b < n_blocks[w]; b++) {
       const gf2_prior_block& pb = blocks[(size_t)w * (2 * k.F + 8) + b];
       if (pb.kind == GF2_BLK_SPEEDBIAS && pb.index >= 2) return gf2::fail(GF2_ERR_UNSUPPORTED, "prior of window %d keeps speed-bias %d (only 0 and 1 are supported)", first + w, pb.index);
     }
-    if (n_rows[w] > 0 && (n_blocks[w] < 1 || n_blocks[w] > 2 * k.F + 8)) return gf2::fail(GF2_ERR_INVALID, "prior of window %d has %d blocks", first + w, n_blocks[w]);
   }
   H2D(k.prior_rows + first, n_rows, sizeof(int32_t) * n);
   H2D(k.prior_nblocks + first, n_blocks, sizeof(int32_t) * n);
@@ -563,15 +568,16 @@ int gf2_set_planes(gf2_solver* h, int first, int n, const int32_t* n_planes, con
   GF2_TRY(check_range(h, first, n));
   const KP& k = h->kp;
   if (k.Pm <= 0) return gf2::fail(GF2_ERR_INVALID, "solver created with max_planes = 0");
+  if (!n_planes || !planes) return gf2::fail(GF2_ERR_INVALID, "null argument");
+  if ((k.Pm + 31) / 32 + 2 * k.F > kMaxPlaneTasks) return gf2::fail(GF2_ERR_INVALID, "max_planes %d exceeds the task capacity", k.Pm);
   for (int w = 0; w < n; w++) if (n_planes[w] < 0 || n_planes[w] > k.Pm) return gf2::fail(GF2_ERR_INVALID, "n_planes[%d] = %d exceeds capacity %d", w, n_planes[w], k.Pm);
-  H2D(k.n_planes + first, n_planes, sizeof(int32_t) * n);
-  H2D(k.planes + (size_t)first * k.Pm, planes, sizeof(gf2_plane) * n * k.Pm);
   for (int w = 0; w < n; w++) for (int q = 0; q < n_planes[w]; q++) {
     const int f = planes[(size_t)w * k.Pm + q].frame;
     if (f < 0 || f >= k.F) return gf2::fail(GF2_ERR_INVALID, "window %d plane %d: frame %d outside [0, %d)", first + w, q, f, k.F);
     if (planes[(size_t)w * k.Pm + q].ct && f + 1 >= k.F) return gf2::fail(GF2_ERR_INVALID, "window %d plane %d: a CT plane of frame %d needs the end pose %d", first + w, q, f, f + 1);
   }
-  if ((k.Pm + 31) / 32 + 2 * k.F > kMaxPlaneTasks) return gf2::fail(GF2_ERR_INVALID, "max_planes %d exceeds the task capacity", k.Pm);
+  H2D(k.n_planes + first, n_planes, sizeof(int32_t) * n);   // nothing is uploaded unless every record is valid
+  H2D(k.planes + (size_t)first * k.Pm, planes, sizeof(gf2_plane) * n * k.Pm);
   h->has_planes = true;
   return GF2_OK;
 }
@@ -588,6 +594,7 @@ int gf2_set_plane_alpha(gf2_solver* h, int first, int n, const double* alpha) {
 static int fill_kp(gf2_solver* h, const gf2_solve_opts* o, KP& k) {
   if (!o) return gf2::fail(GF2_ERR_INVALID, "null options");
   if (o->max_time_s != 0.0) return gf2::fail(GF2_ERR_INVALID, "max_time_s must be 0: the wall-clock cap is not reproduced");
+  if (o->initial_radius > 0 && o->initial_radius != 1e4) return gf2::fail(GF2_ERR_UNSUPPORTED, "initial_radius other than the Ceres default 1e4");
   if (o->max_iterations < 0 || o->max_iterations > 64) return gf2::fail(GF2_ERR_INVALID, "max_iterations %d out of range [0, 64]", o->max_iterations);
   const uint32_t need = GF2_CONST_EX_POSE | GF2_CONST_TD;
   if ((o->const_mask & need) != need) return gf2::fail(GF2_ERR_UNSUPPORTED, "free camera extrinsic / td blocks are not built yet (const_mask must hold EX_POSE|TD)");
@@ -617,13 +624,11 @@ static int run(gf2_solver* h, int first, int n, const gf2_solve_opts* opts, gf2_
   const int D = h->D;
   h->last_Dx = k.wcal ? k.Ds : h->D;
   const size_t sh_solve = sizeof(Solve2Shared) + sizeof(double) * solve2_matrix_doubles(k.F, k.wcal);
-  double initial_radius = opts->initial_radius > 0 ? opts->initial_radius : 1e4;
   int ne = 0;
   cudaEventRecord(h->ev[ne++], h->stream);
   k_prepare<<<n, 128, sizeof(double) * 450 * GF2_MAX_FRAMES, h->stream>>>(k, first);
   k_tasks<<<n, 32, 0, h->stream>>>(k, first);
   cudaEventRecord(h->ev[ne++], h->stream);
-  if (initial_radius != 1e4) return gf2::fail(GF2_ERR_UNSUPPORTED, "initial_radius other than the Ceres default 1e4");
   const int iters = only_linearize ? 1 : iterations;
   for (int it = 0; it < iters; it++) {
     k_linearize<<<n, kLinThreads, sizeof(LinShared), h->stream>>>(k, first);
@@ -756,12 +761,6 @@ int gf2_marginalize(gf2_solver* h, int first, int n, int32_t mode, const gf2_sol
   const size_t sh_build = ((sizeof(MargShared) + 15) & ~size_t(15)) + sizeof(double) * kMargTMax * kMargLD;
   const int Kc = 6 * (k.F - 1) + 16 + (k.use_wheel ? 10 : 0);
   const size_t sh_eig = ((sizeof(EigShared) + 15) & ~size_t(15)) + sizeof(double) * 2 * Kc * (Kc | 1);
-  static bool attr_done = false;
-  if (!attr_done) {
-    GF2_CUDA(cudaFuncSetAttribute(k_marg_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh_build));
-    GF2_CUDA(cudaFuncSetAttribute(k_marg_eig, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(((sizeof(EigShared) + 15) & ~size_t(15)) + sizeof(double) * 2 * kMargKMax * (kMargKMax | 1))));
-    attr_done = true;
-  }
   cudaEventRecord(h->ev[0], h->stream);
   k_prepare<<<n, 128, sizeof(double) * 450 * GF2_MAX_FRAMES, h->stream>>>(k, first);   // IMU sqrt_info, J0^T J0 of the old prior
   k_marg_build<<<n, kMargThreads, sh_build, h->stream>>>(k, first, mp);

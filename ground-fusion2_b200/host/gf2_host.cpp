@@ -120,6 +120,7 @@ bool readParameters(const std::string& config_file, Parameters& P) {  // keys an
   P.MIN_PARALLAX = y.num("keyframe_parallax") / FOCAL_LENGTH;  // :351-352
   P.ESTIMATE_EXTRINSIC = (int)y.num("estimate_extrinsic"); P.ESTIMATE_TD = (int)y.num("estimate_td"); P.TD = y.num("td");
   P.ROW = (int)y.num("image_height"); P.COL = (int)y.num("image_width");
+  P.USE_MCC = (int)y.num("use_mcc"); P.DEPTH = (int)y.num("depth");   // parameters.cpp:164,472 (absent key reads as 0, cv::FileNode semantics)
   P.ONLY_INITIAL_WITH_WHEEL = (int)y.num("only_initial_with_wheel");
   if (P.USE_WHEEL) {  // parameters.cpp:234-335
     P.VEL_N_wheel = y.num("wheel_velocity_noise_sigma"); P.GYR_N_wheel = y.num("wheel_gyro_noise_sigma");
@@ -375,6 +376,7 @@ void Estimator::setParameter(const Parameters& p) {
   P = p; tic[0] = p.TIC; ric[0] = p.RIC; td = p.TD;
   tio = p.TIO; rio = p.RIO; sx = p.SX; sy = p.SY; sw = p.SW; td_wheel = p.TD_WHEEL;
   f_manager.MIN_PARALLAX = p.MIN_PARALLAX;
+  USE_MCC = p.USE_MCC != 0; DEPTH = p.DEPTH != 0;
   if (!featureTracker) featureTracker = new FeatureTracker();
   featureTracker->readIntrinsicParameter(p);
 }
@@ -599,7 +601,12 @@ void Estimator::optimization() {
     mp.valid = true; mp.n = rows; mp.linearized_jacobians.resize((size_t)rows * rows); mp.linearized_residuals.assign(r0.begin(), r0.begin() + rows);
     for (int r = 0; r < rows; r++) for (int c = 0; c < rows; c++) mp.linearized_jacobians[(size_t)r * rows + c] = J0[(size_t)r * GF2_MAX_PRIOR_DIM + c];
     mp.blocks.assign(blocks.begin(), blocks.begin() + nb);
-  }  // GF2_MARG_UNCHANGED / DEGENERATE / UNSUPPORTED: the previous prior stays (block indices untouched, as at :3599)
+  } else if (st != GF2_MARG_UNCHANGED) {
+    // DEGENERATE / UNSUPPORTED / TOO_LARGE have no counterpart in the reference (it always produces a prior). Keeping the old prior while
+    // slideWindow() shifts the frames would attach pose k's prior to the former frame k + 1: stop instead of corrupting the estimate.
+    last_error = "gf2_marginalize: window status " + std::to_string(st) + " (no prior produced); estimation stopped";
+    last_marginalization_info = MarginalizationPrior();
+  }  // GF2_MARG_UNCHANGED: the previous prior stays (block indices untouched, as at :3599)
 }
 
 // ---- measurement queues (estimator.cpp:324-372, 422-545, 554-763) ---------------------------------------------------------------------
@@ -842,7 +849,9 @@ void Estimator::processImage(const std::map<int, std::vector<std::pair<int, std:
   if (solve_enabled) {
     optimization();
     if (!last_error.empty()) return;
-    if (!USE_MCC) { removeIndex.clear(); movingConsistencyCheckW(removeIndex); f_manager.removeOutlier(removeIndex); }
+    // :1175-1182: the reference declares a SECOND, inner `set<int> removeIndex` in this branch, so with use_mcc: 0 (m3dgr / m2dgr / HILTI22
+    // yaml) the tracker below receives the OUTER set, which is still empty: the feature manager drops the outliers, the tracker keeps them.
+    if (!USE_MCC) { std::set<int> removeIndexInner; movingConsistencyCheckW(removeIndexInner); f_manager.removeOutlier(removeIndexInner); }
     if (!MULTIPLE_THREAD && featureTracker) {   // :1185-1189
       featureTracker->removeOutliers(removeIndex);
       featureTracker->setPrediction(predictPtsInNextFrame());

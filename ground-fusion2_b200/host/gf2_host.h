@@ -41,6 +41,7 @@ Matrix3d transpose(const Matrix3d& a);
 struct Parameters {
   double ACC_N = 0.1, ACC_W = 0.001, GYR_N = 0.01, GYR_W = 0.0001, G_NORM = 9.81007;
   double SOLVER_TIME = 0.04; int NUM_ITERATIONS = 8;
+  int USE_MCC = 0, DEPTH = 0;   // parameters.cpp:164,472
   int ESTIMATE_EXTRINSIC = 0, ESTIMATE_TD = 0, USE_IMU = 1, USE_WHEEL = 0, EQUALIZE = 0, MAX_CNT = 150, MIN_DIST = 30, FLOW_BACK = 1, ROW = 480, COL = 640;
   double TD = 0.0, F_THRESHOLD = 1.0, MIN_PARALLAX = 10.0 / FOCAL_LENGTH;
   Matrix3d RIC; Vector3d TIC;

@@ -22,6 +22,34 @@ __global__ void k_dmma(double* out, int iters) {
   double s = 0; for (int i = 0; i < 8; i++) s += c[i][0] + c[i][1];
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
+// Do the fp64 FMA pipe and the fp64 tensor path share one datapath? Even warps issue DFMA, odd warps DMMA, in the same CTA.
+// If the two were independent pipes the combined rate would approach the sum of the two single rates.
+__global__ void k_mixed(double* out, int iters) {
+  const int wid = threadIdx.x >> 5;
+  double s = 0;
+  if (wid & 1) {
+    double c[8][2]; for (int i = 0; i < 8; i++) { c[i][0] = 0; c[i][1] = 0; }
+    double a = threadIdx.x * 1e-3, b = 1.0 + threadIdx.x * 1e-6;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+      for (int i = 0; i < 8; i++)
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c[i][0]), "+d"(c[i][1]) : "d"(a), "d"(b));
+    }
+    for (int i = 0; i < 8; i++) s += c[i][0] + c[i][1];
+  } else {
+    double a[8]; for (int i = 0; i < 8; i++) a[i] = threadIdx.x * 1e-3 + i;
+    const double b = 1.0000001, c = 1e-9;
+    // 16 DFMA warp-instructions carry the same 256 MACs per lane-row as ONE m8n8k4: 8 x 16 FMAs per iteration keeps the two halves in step
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+      for (int r = 0; r < 16; r++)
+#pragma unroll
+        for (int i = 0; i < 8; i++) a[i] = fma(a[i], b, c);
+    }
+    for (int i = 0; i < 8; i++) s += a[i];
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
 __global__ void k_atoms(double* out, int iters, int stride) {
   __shared__ double sm[2048];
   for (int i = threadIdx.x; i < 2048; i += blockDim.x) sm[i] = 0;
@@ -47,6 +75,12 @@ int main() {
     ms = timeit([&] { k_dmma<<<blocks, threads>>>(out, iters); });
     printf("DMMA  %2d warps/blk x4 blk/SM: %.2f TFLOP/s  (%.2f clk/mma/SM @1.9GHz)\n", warps, 2.0 * 256 * 8 * iters * (double)warps * blocks / ms / 1e9,
            ms * 1e-3 * 1.9e9 / (8.0 * iters * warps * 4));
+  }
+  for (int warps : {8, 16}) {
+    const int threads = warps * 32, blocks = 148 * 4, it2 = 4000;
+    float ms = timeit([&] { k_mixed<<<blocks, threads>>>(out, it2); });
+    const double fl_mma = 2.0 * 256 * 8 * it2 * (double)(warps / 2) * blocks, fl_fma = 2.0 * 8 * 16 * it2 * (double)(threads / 2) * blocks;
+    printf("MIXED %2d warps/blk (half DFMA, half DMMA, equal flops): DMMA %.2f + DFMA %.2f = %.2f TFLOP/s\n", warps, fl_mma / ms / 1e9, fl_fma / ms / 1e9, (fl_mma + fl_fma) / ms / 1e9);
   }
   for (int stride : {1, 0, 33}) {
     float ms = timeit([&] { k_atoms<<<148 * 2, 256>>>(out, 20000, stride); });
