@@ -105,19 +105,20 @@ GF2_HD M3 QleftQrightBR(Q4 a, Q4 b) {
 }
 
 #ifdef __CUDACC__
-// Branch-free reciprocal / reciprocal square root for normal, positive arguments (depths, squared norms): the 2^-23
-// hardware approximation refined by three Newton steps (about 1 ulp; the library versions carry special-case branches that
-// split the basic block the kernel wants to software-pipeline).
+// Branch-free reciprocal / reciprocal square root for normal, positive arguments (depths, squared norms): the hardware
+// approximation (measured 1e-6 relative, scripts/ubench/approx_accuracy.cu) refined by TWO Newton steps: 1e-6 -> 1e-12 -> 1.1e-16
+// (rcp) / 2.2e-16 (rsqrt), i.e. already at the rounding level, a third step changes nothing (profiles/ubench_approx_accuracy_r2.txt).
+// The library versions carry special-case branches that split the basic block the kernel wants to software-pipeline.
 __device__ __forceinline__ double fast_rcp(double x) {
   double r; asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
 #pragma unroll
-  for (int it = 0; it < 3; it++) { const double e = fma(-x, r, 1.0); r = fma(r, e, r); }
+  for (int it = 0; it < 2; it++) { const double e = fma(-x, r, 1.0); r = fma(r, e, r); }
   return r;
 }
 __device__ __forceinline__ double fast_rsqrt(double x) {
   double r; asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
 #pragma unroll
-  for (int it = 0; it < 3; it++) { const double e = fma(-x * r, r, 1.0); r = fma(0.5 * r, e, r); }
+  for (int it = 0; it < 2; it++) { const double e = fma(-x * r, r, 1.0); r = fma(0.5 * r, e, r); }
   return r;
 }
 #endif

@@ -86,6 +86,10 @@ constexpr int kNPairs = kMaxF * (kMaxF - 1) / 2;  // frame pairs i < j
 constexpr int kMomStride = 28;     // upper part (m <= n, m < 6, n < 7) of the 7x7 Gram matrix of Y = [Jx | Jx [d]x | r]
 constexpr int kYStride = 68;       // staging of Y^T per warp: [8][kYStride], rows 0..63 = the warp's residual rows, column 7 stays zero
 constexpr int kSchurSlots = 12;    // Schur tiles owned by a warp (11, 11, 11, 12)
+// SYRK tile grid: tile row a covers the rows r' = 8a .. 8a+7 of the END-ALIGNED index r' = r + kRowShift (r = tangent index 0..65, landmark
+// gradient at r = 66; r = 67 and r' < kRowShift are zero padding). Every landmark's support ends at the last frame, so a round whose
+// first host frame is i touches the tile rows a >= (6 i + kRowShift) / 8 only: 193 instead of 221 tile-rounds per W10-F1000 window.
+constexpr int kRowShift = 4;
 
 struct LinShared {
   FrameCtx fr[kMaxF];
@@ -143,39 +147,43 @@ __device__ __forceinline__ void syrk_tile(const double (&f)[9], double (&C)[kSch
   constexpr TileAB tl = tile_of(W, S);
   if constexpr (tl.a >= 0 && tl.a >= M) mma_f64(C[S][0], C[S][1], f[tl.a], f[tl.b]);
 }
+// row fragment of tile row I: WT[8 I + fq - kRowShift][k0 + fk]; the first kRowShift rows of tile row 0 are padding
 template <int M, int I>
-__device__ __forceinline__ void syrk_frag(double (&f)[9], const double* wb, const double* w8) {
-  if constexpr (I >= M) f[I] = (I == 8) ? *w8 : wb[I * 8 * kWTStride];
+__device__ __forceinline__ void syrk_frag(double (&f)[9], const double* wb, bool lo_ok) {
+  if constexpr (I >= M) {
+    if constexpr (I == 0) f[0] = lo_ok ? wb[0] : 0.0;
+    else f[I] = wb[I * 8 * kWTStride];
+  }
 }
 // one round: C[tile] += sum over the 128 landmark columns, tiles with a >= M only
 template <int W, int M>
-__device__ __forceinline__ void syrk_round(const double* wb /* &WT[fq][fk] */, const double* w8 /* row min(64 + fq, 67) */, double (&C)[kSchurSlots][2]) {
+__device__ __forceinline__ void syrk_round(const double* wb /* &WT[fq - kRowShift][fk] */, bool lo_ok, double (&C)[kSchurSlots][2]) {
 #pragma unroll 4
   for (int k0 = 0; k0 < kLinThreads; k0 += 4) {
     double f[9];
-    syrk_frag<M, 0>(f, wb + k0, w8 + k0); syrk_frag<M, 1>(f, wb + k0, w8 + k0); syrk_frag<M, 2>(f, wb + k0, w8 + k0);
-    syrk_frag<M, 3>(f, wb + k0, w8 + k0); syrk_frag<M, 4>(f, wb + k0, w8 + k0); syrk_frag<M, 5>(f, wb + k0, w8 + k0);
-    syrk_frag<M, 6>(f, wb + k0, w8 + k0); syrk_frag<M, 7>(f, wb + k0, w8 + k0); syrk_frag<M, 8>(f, wb + k0, w8 + k0);
+    syrk_frag<M, 0>(f, wb + k0, lo_ok); syrk_frag<M, 1>(f, wb + k0, lo_ok); syrk_frag<M, 2>(f, wb + k0, lo_ok);
+    syrk_frag<M, 3>(f, wb + k0, lo_ok); syrk_frag<M, 4>(f, wb + k0, lo_ok); syrk_frag<M, 5>(f, wb + k0, lo_ok);
+    syrk_frag<M, 6>(f, wb + k0, lo_ok); syrk_frag<M, 7>(f, wb + k0, lo_ok); syrk_frag<M, 8>(f, wb + k0, lo_ok);
     syrk_tile<W, M, 0>(f, C); syrk_tile<W, M, 1>(f, C); syrk_tile<W, M, 2>(f, C); syrk_tile<W, M, 3>(f, C);
     syrk_tile<W, M, 4>(f, C); syrk_tile<W, M, 5>(f, C); syrk_tile<W, M, 6>(f, C); syrk_tile<W, M, 7>(f, C);
     syrk_tile<W, M, 8>(f, C); syrk_tile<W, M, 9>(f, C); syrk_tile<W, M, 10>(f, C); syrk_tile<W, M, 11>(f, C);
   }
 }
 template <int W>
-__device__ __forceinline__ void syrk_warp(int a_min, const double* wb, const double* w8, double (&C)[kSchurSlots][2]) {
+__device__ __forceinline__ void syrk_warp(int a_min, const double* wb, bool lo_ok, double (&C)[kSchurSlots][2]) {
   switch (a_min) {
-    case 0: syrk_round<W, 0>(wb, w8, C); break;
-    case 1: syrk_round<W, 1>(wb, w8, C); break;
-    case 2: syrk_round<W, 2>(wb, w8, C); break;
-    case 3: syrk_round<W, 3>(wb, w8, C); break;
-    case 4: syrk_round<W, 4>(wb, w8, C); break;
-    case 5: syrk_round<W, 5>(wb, w8, C); break;
-    case 6: syrk_round<W, 6>(wb, w8, C); break;
-    case 7: syrk_round<W, 7>(wb, w8, C); break;
-    default: syrk_round<W, 8>(wb, w8, C); break;
+    case 0: syrk_round<W, 0>(wb, lo_ok, C); break;
+    case 1: syrk_round<W, 1>(wb, lo_ok, C); break;
+    case 2: syrk_round<W, 2>(wb, lo_ok, C); break;
+    case 3: syrk_round<W, 3>(wb, lo_ok, C); break;
+    case 4: syrk_round<W, 4>(wb, lo_ok, C); break;
+    case 5: syrk_round<W, 5>(wb, lo_ok, C); break;
+    case 6: syrk_round<W, 6>(wb, lo_ok, C); break;
+    case 7: syrk_round<W, 7>(wb, lo_ok, C); break;
+    default: syrk_round<W, 8>(wb, lo_ok, C); break;
   }
 }
-// accumulator tiles -> dense 72x72 (upper tiles) in shared memory
+// accumulator tiles -> dense 72x72 (upper tiles, end-aligned index) in shared memory
 template <int W, int S>
 __device__ __forceinline__ void syrk_store_tile(double* dense, const double (&C)[kSchurSlots][2], int fq, int fk) {
   constexpr TileAB tl = tile_of(W, S);
@@ -279,8 +287,8 @@ __global__ void __launch_bounds__(kLinThreads, 2) k_linearize(KP p, int w0) {
   for (int q = 0; q < kSchurSlots; q++) { C[q][0] = 0.0; C[q][1] = 0.0; }
   const int fq = lane >> 2, fk = lane & 3;  // fragment coordinates: row/col index 0..7, k index 0..3
   double* Yw = S.Y[wid];
-  const double* wb = &S.WT[fq * kWTStride + fk];
-  const double* w8 = &S.WT[min(64 + fq, kWTRows - 1) * kWTStride + fk];
+  const double* wb = &S.WT[(fq - kRowShift) * kWTStride + fk];
+  const bool lo_ok = fq >= kRowShift;
 
   // landmark record of a lane for one round, fetched ahead in two levels so that the dependent global loads are in flight
   // during the SYRK of earlier rounds: the packed table entry two rounds ahead, the landmark's state and first observations
@@ -316,7 +324,8 @@ __global__ void __launch_bounds__(kLinThreads, 2) k_linearize(KP p, int w0) {
     const int i = have_task ? S.task_start[task] : 0;
     const LaneLm cur = nxt;
     const bool have = cur.have;
-    const int row0 = 8 * ((6 * S.task_start[tbase]) >> 3);  // tiles left of the round's first host frame are skipped by the SYRK
+    const int a_min = (6 * S.task_start[tbase] + kRowShift) >> 3;  // tile rows above the round's first host frame are skipped by the SYRK
+    const int row0 = max(8 * a_min - kRowShift, 0);
     const int l = cur.l, L = cur.L, ob = cur.ob; const bool fx = cur.fx;
     LmCtx lc; lc.Xw = mk3(0, 0, 0); lc.dXdl = mk3(0, 0, 0);
     if (have) landmark_ctx(S.fr[i], S.cam, cur.oi, ftd[i], cur.lam, lc);
@@ -457,12 +466,11 @@ __global__ void __launch_bounds__(kLinThreads, 2) k_linearize(KP p, int w0) {
 #endif
     // Schur SYRK on the fp64 tensor cores: C[a-tile][b-tile] += sum_l Ws[l][a] * Ws[l][b]
     {
-      const int a_min = row0 >> 3;
       switch (wid) {
-        case 0: syrk_warp<0>(a_min, wb, w8, C); break;
-        case 1: syrk_warp<1>(a_min, wb, w8, C); break;
-        case 2: syrk_warp<2>(a_min, wb, w8, C); break;
-        default: syrk_warp<3>(a_min, wb, w8, C); break;
+        case 0: syrk_warp<0>(a_min, wb, lo_ok, C); break;
+        case 1: syrk_warp<1>(a_min, wb, lo_ok, C); break;
+        case 2: syrk_warp<2>(a_min, wb, lo_ok, C); break;
+        default: syrk_warp<3>(a_min, wb, lo_ok, C); break;
       }
     }
     __syncthreads();
@@ -596,11 +604,11 @@ __global__ void __launch_bounds__(kLinThreads, 2) k_linearize(KP p, int w0) {
     const int bj = blk - bi * (bi + 1) / 2;
     const int r = 6 * bi + e / 6, c = 6 * bj + e % 6;
     const int a = r <= c ? r : c, b = r <= c ? c : r;  // upper element (a <= b) of U and of the Schur tiles
-    Svis[idx] = S.U[ublk(a / 6, b / 6, F) + (a % 6) * 6 + (b % 6)] - S.WT[a * kNVP + b];
+    Svis[idx] = S.U[ublk(a / 6, b / 6, F) + (a % 6) * 6 + (b % 6)] - S.WT[(a + kRowShift) * kNVP + b + kRowShift];
   }
   for (int q = t; q < NV; q += kLinThreads) {
     p.gvis[(size_t)w * kNVP + q] = S.g[q];                       // full visual gradient J^T r (pose part)
-    p.gschur[(size_t)w * kNVP + q] = S.WT[q * kNVP + 66];         // sum_l w_l g_l / v'_l, subtracted to form the reduced rhs
+    p.gschur[(size_t)w * kNVP + q] = S.WT[(q + kRowShift) * kNVP + 66 + kRowShift];         // sum_l w_l g_l / v'_l, subtracted to form the reduced rhs
     p.Udiag[(size_t)w * kNVMax + q] = S.U[ublk(q / 6, q / 6, F) + (q % 6) * 7];
   }
   double red2[2] = {cost_acc, 0.0};
