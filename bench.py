@@ -353,6 +353,85 @@ def run_replay(gf2, synth, with_cpu=True):
     return line
 
 
+def run_config4(gf2, synth, torch, dist, rank, world, local, B, steps, warmup):
+    """BASELINE.json config 4: W10-F1000 + 10 wheel factors + 5,000 point-to-plane factors per window (IMU and wheel preintegrated on the
+    device). world == 1: the windows solved on one GPU. world > 1: the factor-sharded mode of SURVEY 8(e) — every rank holds all frame
+    states + IMU / wheel / prior factors of ALL B windows and the landmarks l mod N / planes k mod N; per linearisation ONE NCCL all-reduce
+    of the windows' 36.6 KB records (+ a MAX and two small SUMs per iteration); strong scaling over a fixed batch."""
+    shard = importlib.import_module("gf2_b200.shard")
+    abi = gf2.abi
+    distinct = min(B, 8)
+    base = synth.make_windows(distinct, config_id=4, n_landmarks=N_LM, wheel=True, n_planes=5000)
+    tile = lambda d: {k: (np.concatenate([v] * ((B + distinct - 1) // distinct))[:B] if isinstance(v, np.ndarray) and v.ndim >= 1 and v.shape[0] == distinct
+                          and k not in ("imu_noise", "wheel_noise") else v) for k, v in d.items()}
+    mk = lambda d: gf2.Solver(B, d["n_frames"], d["max_landmarks"], d["max_obs"], max_planes=d["max_planes"], max_imu_samples=d["n_imu_samples"],
+                              use_wheel=True, max_wheel_samples=d["n_wheel_samples"], device=local, max_prior_rows=d.get("prior_stride", 0))
+    opts = abi.default_opts()
+    stream = torch.cuda.current_stream()
+
+    def timed(s, n_steps):
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        nccl_ms = 0.0; iters = 0
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0.record(stream)
+        for _ in range(n_steps):
+            s.restore(B); summ = s.solve(opts, B)
+            nccl_ms += s.last_timing()["nccl_ms"]; iters += int(summ["iterations"].max())
+        e1.record(stream); torch.cuda.synchronize()
+        return e0.elapsed_time(e1), nccl_ms, iters, summ
+
+    mine = tile(shard.shard_windows(base, rank, world)) if world > 1 else tile(base)
+    s = mk(mine); s.set_stream(stream.cuda_stream)
+    if world > 1:
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.from_numpy(gf2.Solver.comm_unique_id()).cuda())
+        dist.broadcast(uid, 0)
+        s.comm_init(rank, world, uid.cpu().numpy())
+    s.upload(mine, preintegrate="device"); s.snapshot(B)
+    for _ in range(warmup):
+        s.restore(B); s.solve(opts, B)
+    ms, nccl_ms, iters, summ = timed(s, steps)
+    tt = torch.tensor([ms], device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms = float(tt.item())
+    st = s.get_states(B)
+    s.close()
+    line = {"metric": "solves/sec, BASELINE config 4 (W10-F1000 + 10 wheel + 5,000 point-to-plane factors, 8 iterations)", "value": B * steps / (ms / 1e3), "unit": "solves/s",
+            "windows": B, "distinct_windows": distinct, "n_gpus": world, "ms_per_step": ms / steps, "iterations_per_step": iters / steps,
+            "mode": "single GPU" if world == 1 else f"factor-sharded over {world} GPUs (landmarks l mod {world}, planes k mod {world}; frame states, IMU / wheel / prior replicated)",
+            "timing": "CUDA events on the launching stream, max over ranks; step = restore + solve, preintegration records resident"}
+    if world > 1:
+        it = max(iters / steps, 1.0)
+        line.update({"scaling": "strong",
+                     "nccl_ms_per_step_rank0": nccl_ms / steps, "nccl_share_rank0": nccl_ms / ms if rank == 0 else None,
+                     "allreduce_bytes_per_iteration": int(B * (4576 * 8 + 8 + 64 + 32)),
+                     "collectives_per_iteration": "1 SUM of B x 36,608 B records + 1 MAX (grouped) after the sweep, 1 SUM of B x 64 B after back-substitution, 1 SUM of B x 32 B after the candidate",
+                     "nccl_us_per_iteration_rank0": 1e3 * nccl_ms / steps / it})
+        if rank == 0:   # the same windows unsharded on rank 0's GPU alone: parity and the strong-scaling reference
+            full = tile(base)
+            ref = mk(full); ref.set_stream(stream.cuda_stream); ref.upload(full, preintegrate="device"); ref.snapshot(B)
+            for _ in range(2):
+                ref.restore(B); ref.solve(opts, B)
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(steps):
+                ref.restore(B); rsum = ref.solve(opts, B)
+            e1.record(stream); torch.cuda.synchronize()
+            ms1 = e0.elapsed_time(e1)
+            rst = ref.get_states(B); ref.close()
+            line["single_gpu"] = {"value": B * steps / (ms1 / 1e3), "ms_per_step": ms1 / steps}
+            line["speedup_vs_single_gpu"] = ms1 / ms
+            line["parity_vs_single_gpu"] = {"pose_max_abs_diff": float(np.abs(st["para_pose"] - rst["para_pose"]).max()),
+                                            "iterations_equal": bool((summ["iterations"] == rsum["iterations"]).all()),
+                                            "termination_equal": bool((summ["termination"] == rsum["termination"]).all())}
+        dist.barrier()
+    return line
+
+
 def run_reference(args, rank, world):
     """Restated-reference CPU baseline: oracle solve (same algorithm as ceres::Solve with the reference's options) on
     all host threads, each step a bounded sample of the same workload."""
@@ -404,6 +483,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-marginalize", action="store_true", help="skip the marginalization leg")
     ap.add_argument("--no-lk", action="store_true", help="skip the front-end (LK) leg")
+    ap.add_argument("--no-config4", action="store_true", help="skip the config-4 leg (wheel + LiDAR planes; factor-sharded over the ranks when N > 1)")
+    ap.add_argument("--config4-windows", type=int, default=512, help="windows of the config-4 leg (fixed total: strong scaling when N > 1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "gf2" else args.warmup
     rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
@@ -524,6 +605,11 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * B * args.steps / float(te.item())
 
+    # ------------------------------------------------------------ BASELINE config 4 (wheel + LiDAR planes): one GPU at N = 1, factor-sharded + NCCL at N > 1
+    cfg4 = None
+    if not args.no_config4:
+        cfg4 = run_config4(gf2, synth, torch, dist, rank, world, local, args.config4_windows, max(2, min(args.steps, 5)), 2)
+
     # ------------------------------------------------------------ marginalization leg, reported beside the metric
     marg = None
     if rank == 0 and not args.no_marginalize:
@@ -581,6 +667,7 @@ def main():
                          "algorithmic_bytes_per_launch": BYTES_SWEEP * B, "avg_launch_ms": lin_avg_ms},
             "reduced_solve": {"kernels": "k_nonvis + k_solve2", "avg_ms_per_iteration": solve_ms / n_lin, "bound": "serial pivot chain (latency), not the tensor pipe",
                               "dmma_pipe_pct_ncu": NCU_DMMA_PCT, "source": "profiles/ncu_full_solver_kernels_B4096_r1.csv"},
+            ("config4_sharded" if world > 1 else "config4"): cfg4,
             "marginalize": marg, "lk": lk_line, "lio": lio_line, "replay": replay_line,
             "phase_ms_per_step": {"linearize": lin_ms / args.steps, "reduced_solve": solve_ms / args.steps, "backsub_candidate": step_ms / args.steps,
                                   "solve_total": total_ms / args.steps},

@@ -254,7 +254,7 @@ class Solver:
     def last_timing(self):
         t = np.zeros(8)
         _check(lib().gf2_last_timing(self.h, _p(t)))
-        return {"total_ms": t[0], "linearize_ms": t[1], "solve_ms": t[2], "step_ms": t[3], "launches": int(t[4]), "linearize_launches": int(t[5]), "prepare_ms": t[6]}
+        return {"total_ms": t[0], "linearize_ms": t[1], "solve_ms": t[2], "step_ms": t[3], "launches": int(t[4]), "linearize_launches": int(t[5]), "prepare_ms": t[6], "nccl_ms": t[7]}
 
 
 def detect_select(idx, val, width, height, max_corners, min_distance):

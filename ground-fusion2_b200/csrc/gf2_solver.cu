@@ -263,6 +263,7 @@ struct gf2_solver {
   bool has_imu = false, has_wheel = false, has_prior = false, has_planes = false, dump_full = false;
   std::vector<int32_t> h_obeg;
   cudaEvent_t ev[4 * 64 + 3];
+  cudaEvent_t ev_nccl[6 * 64];   // pairs around the collectives of the factor-sharded mode (created by gf2_comm_init)
   double timing[8];
   WinState* h_state = nullptr;
 };
@@ -324,13 +325,13 @@ int gf2_solver_create(const gf2_solver_cfg* cfg, gf2_solver** out) {
   A(k.prior_rows, int32_t, B); A(k.prior_nblocks, int32_t, B); A(k.prior_J0, double, (size_t)B * k.Pr * k.Pr); A(k.prior_r0, double, (size_t)B * k.Pr);
   A(k.prior_blocks, gf2_prior_block, (size_t)B * (2 * F + 8)); A(k.prior_H, double, (size_t)B * k.Pr * k.Pr); A(k.prior_map, int32_t, (size_t)B * k.Pr);
   if (Pm > 0) { A(k.n_planes, int32_t, B); A(k.planes, gf2_plane, (size_t)B * Pm); A(k.plane_alpha, double, (size_t)B * Pm); }
-  A(k.Svis, double, (size_t)B * kNVMax * kNVMax); A(k.gvis, double, (size_t)B * kNVP); A(k.gschur, double, (size_t)B * kNVP); A(k.Udiag, double, (size_t)B * kNVMax);
+  A(k.Svis, double, (size_t)B * kVisRec);   // one record per window: Svis | gvis | gschur | Udiag | c_lin
   A(k.lm_v, double, (size_t)B * Lm); A(k.lm_g, double, (size_t)B * Lm); A(k.lm_s, double, (size_t)B * Lm); A(k.lm_z, double, (size_t)B * Lm);
   A(k.sx, double, (size_t)B * k.Ds); A(k.zx, double, (size_t)B * k.Ds); A(k.ux, double, (size_t)B * k.Ds); A(k.ex_diag, double, (size_t)B * k.Ds);
   A(k.imu_H, double, (size_t)B * (F - 1) * 675); A(k.imu_g, double, (size_t)B * (F - 1) * 30);
   A(k.prior_g, double, (size_t)B * k.Pr); A(k.cost_nv, double, B);
   A(k.trace, double, (size_t)B * 64 * 6);
-  A(k.c_lin, double, (size_t)B * 4); A(k.c_gmax, double, B); A(k.c_sums, double, (size_t)B * 8); A(k.c_cand, double, (size_t)B * 4);
+  A(k.c_gmax, double, B); A(k.c_sums, double, (size_t)B * 8); A(k.c_cand, double, (size_t)B * 4);
   if (Pm > 0) { A(k.pperm, int32_t, (size_t)B * Pm); A(k.ptask_first, int32_t, (size_t)B * kMaxPlaneTasks); A(k.ptask_cnt, int32_t, (size_t)B * kMaxPlaneTasks); A(k.ptask_frame, int32_t, (size_t)B * kMaxPlaneTasks); A(k.nptasks, int32_t, B); }
   if (cfg->use_wheel) {
     A(k.wheel_H, double, (size_t)B * (F - 1) * 108); A(k.wheel_g, double, (size_t)B * (F - 1) * 12);
@@ -346,6 +347,7 @@ int gf2_solver_create(const gf2_solver_cfg* cfg, gf2_solver** out) {
   }
 #undef A
   if (rc != GF2_OK) { gf2_solver_destroy(h); return rc; }
+  k.gvis = k.Svis + kNVMax * kNVMax; k.gschur = k.gvis + kNVP; k.Udiag = k.gschur + kNVP; k.c_lin = k.Udiag + kNVMax;
   cudaMemset((void*)k.prior_rows, 0, sizeof(int32_t) * B); cudaMemset((void*)k.prior_nblocks, 0, sizeof(int32_t) * B);
   for (auto& e : h->ev) cudaEventCreate(&e);
   cudaHostAlloc((void**)&h->h_state, sizeof(WinState) * B, cudaHostAllocDefault);
@@ -367,6 +369,7 @@ void gf2_solver_destroy(gf2_solver* h) {
   cudaStreamSynchronize(h->stream);
   for (void* p : h->allocs) cudaFree(p);
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+  for (auto& e : h->ev_nccl) if (e) cudaEventDestroy(e);
   if (h->h_state) cudaFreeHost(h->h_state);
   if (h->h_marg) cudaFreeHost(h->h_marg);
   if (h->nccl_comm && g_nccl.lib) g_nccl.CommDestroy(h->nccl_comm);
@@ -624,7 +627,7 @@ static int run(gf2_solver* h, int first, int n, const gf2_solve_opts* opts, gf2_
   const int D = h->D;
   h->last_Dx = k.wcal ? k.Ds : h->D;
   const size_t sh_solve = sizeof(Solve2Shared) + sizeof(double) * solve2_matrix_doubles(k.F, k.wcal);
-  int ne = 0;
+  int ne = 0, nn = 0;
   cudaEventRecord(h->ev[ne++], h->stream);
   k_prepare<<<n, 128, sizeof(double) * 450 * GF2_MAX_FRAMES, h->stream>>>(k, first);
   k_tasks<<<n, 32, 0, h->stream>>>(k, first);
@@ -632,15 +635,15 @@ static int run(gf2_solver* h, int first, int n, const gf2_solve_opts* opts, gf2_
   const int iters = only_linearize ? 1 : iterations;
   for (int it = 0; it < iters; it++) {
     k_linearize<<<n, kLinThreads, sizeof(LinShared), h->stream>>>(k, first);
-    if (h->nccl_comm) {  // one all-reduce of the visual reduced system + gradient per linearisation
+    if (h->nccl_comm) {
+      // ONE all-reduce of the windows' records [Svis | gvis | gschur | Udiag | visual cost] per linearisation (36.6 KB per window) + the
+      // max-norm of the landmark gradients (a MAX reduction cannot ride in the SUM buffer)
+      cudaEventRecord(h->ev_nccl[nn++], h->stream);
       g_nccl.GroupStart();
-      g_nccl.AllReduce(k.Svis + (size_t)first * kNVMax * kNVMax, k.Svis + (size_t)first * kNVMax * kNVMax, (size_t)n * kNVMax * kNVMax, kNcclFloat64, kNcclSum, h->nccl_comm, h->stream);
-      g_nccl.AllReduce(k.gvis + (size_t)first * kNVP, k.gvis + (size_t)first * kNVP, (size_t)n * kNVP, kNcclFloat64, kNcclSum, h->nccl_comm, h->stream);
-      g_nccl.AllReduce(k.gschur + (size_t)first * kNVP, k.gschur + (size_t)first * kNVP, (size_t)n * kNVP, kNcclFloat64, kNcclSum, h->nccl_comm, h->stream);
-      g_nccl.AllReduce(k.Udiag + (size_t)first * kNVMax, k.Udiag + (size_t)first * kNVMax, (size_t)n * kNVMax, kNcclFloat64, kNcclSum, h->nccl_comm, h->stream);
-      g_nccl.AllReduce(k.c_lin + (size_t)first * 4, k.c_lin + (size_t)first * 4, (size_t)n * 4, kNcclFloat64, kNcclSum, h->nccl_comm, h->stream);
+      g_nccl.AllReduce(k.Svis + (size_t)first * kVisRec, k.Svis + (size_t)first * kVisRec, (size_t)n * kVisRec, kNcclFloat64, kNcclSum, h->nccl_comm, h->stream);
       g_nccl.AllReduce(k.c_gmax + first, k.c_gmax + first, (size_t)n, kNcclFloat64, kNcclMax, h->nccl_comm, h->stream);
       g_nccl.GroupEnd();
+      cudaEventRecord(h->ev_nccl[nn++], h->stream);
     }
     cudaEventRecord(h->ev[ne++], h->stream);
     k_nonvis<<<n, kNonvisThreads, 0, h->stream>>>(k, first);
@@ -648,10 +651,18 @@ static int run(gf2_solver* h, int first, int n, const gf2_solve_opts* opts, gf2_
     cudaEventRecord(h->ev[ne++], h->stream);
     if (!only_linearize) {
       k_backsub<<<n, 256, 0, h->stream>>>(k, first);
-      if (h->nccl_comm) g_nccl.AllReduce(k.c_sums + (size_t)first * 8, k.c_sums + (size_t)first * 8, (size_t)n * 8, kNcclFloat64, kNcclSum, h->nccl_comm, h->stream);
+      if (h->nccl_comm) {
+        cudaEventRecord(h->ev_nccl[nn++], h->stream);
+        g_nccl.AllReduce(k.c_sums + (size_t)first * 8, k.c_sums + (size_t)first * 8, (size_t)n * 8, kNcclFloat64, kNcclSum, h->nccl_comm, h->stream);
+        cudaEventRecord(h->ev_nccl[nn++], h->stream);
+      }
       cudaEventRecord(h->ev[ne++], h->stream);
       k_cand_eval<<<n, 288, 0, h->stream>>>(k, first);
-      if (h->nccl_comm) g_nccl.AllReduce(k.c_cand + (size_t)first * 4, k.c_cand + (size_t)first * 4, (size_t)n * 4, kNcclFloat64, kNcclSum, h->nccl_comm, h->stream);
+      if (h->nccl_comm) {
+        cudaEventRecord(h->ev_nccl[nn++], h->stream);
+        g_nccl.AllReduce(k.c_cand + (size_t)first * 4, k.c_cand + (size_t)first * 4, (size_t)n * 4, kNcclFloat64, kNcclSum, h->nccl_comm, h->stream);
+        cudaEventRecord(h->ev_nccl[nn++], h->stream);
+      }
       k_decide<<<n, 256, 0, h->stream>>>(k, first);
       cudaEventRecord(h->ev[ne++], h->stream);
     }
@@ -672,6 +683,7 @@ static int run(gf2_solver* h, int first, int n, const gf2_solve_opts* opts, gf2_
   }
   h->timing[4] = 2 + iters * (only_linearize ? 3 : 6); h->timing[5] = iters;
   cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]); h->timing[6] = ms;  // k_prepare
+  for (int q = 0; q + 1 < nn; q += 2) { cudaEventElapsedTime(&ms, h->ev_nccl[q], h->ev_nccl[q + 1]); h->timing[7] += ms; }   // time inside the NCCL collectives (factor-sharded mode)
   if (summaries) for (int w = 0; w < n; w++) {
     const WinState& s = h->h_state[w];
     summaries[w].initial_cost = s.initial_cost; summaries[w].final_cost = s.x_cost; summaries[w].iterations = s.iteration;
@@ -811,6 +823,7 @@ int gf2_comm_init(gf2_solver* h, int rank, int nranks, const void* nccl_unique_i
   h->nccl_comm = nranks > 1 ? comm : nullptr;
   if (nranks == 1) g_nccl.CommDestroy(comm);
   h->comm_rank = rank; h->comm_size = nranks;
+  if (h->nccl_comm && !h->ev_nccl[0]) for (auto& e : h->ev_nccl) cudaEventCreate(&e);
   return GF2_OK;
 }
 int gf2_comm_unique_id(void* out) {

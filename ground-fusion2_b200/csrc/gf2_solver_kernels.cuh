@@ -24,6 +24,11 @@ constexpr int kMaxF = GF2_MAX_FRAMES;
 constexpr int kNVMax = 6 * kMaxF;          // 66 visual tangent dims
 constexpr int kNVP = 72;                   // padded to 9 mma tiles of 8; column 66 carries the landmark gradient
 constexpr int kSolveThreads = 256;
+// k_linearize's output record of one window, contiguous so that the factor-sharded mode all-reduces ONE buffer per linearisation
+// (SURVEY 8(e)): [Svis 66*66 | gvis 72 | gschur 72 | Udiag 66 | c_lin 4 | pad 6]; KP::Svis / gvis / gschur / Udiag / c_lin point at their
+// field of window 0 and are indexed with the stride kVisRec.
+constexpr int kVisRec = kNVMax * kNVMax + 2 * kNVP + kNVMax + 4 + 6;   // 4576 doubles = 36,608 B
+static_assert(kVisRec % 2 == 0, "record keeps 16-byte alignment");
 constexpr int kP = GF2_MAX_PRIOR_DIM;
 
 struct WinState {  // per-window trust-region state (DoglegStrategy + TrustRegionMinimizer members)
@@ -78,7 +83,7 @@ struct KP {  // kernel parameters (device pointers are window-major with the str
   const gf2_plane* planes;
   const double* plane_alpha;   // [nW][Pm] alpha_time of the ct == 1 planes (CTLidarPlaneNormFactor)
   // work
-  double *Svis, *gvis, *gschur, *Udiag;  // [nW][66*66], [nW][72], [nW][72], [nW][66]
+  double *Svis, *gvis, *gschur, *Udiag;  // fields of the per-window record of kVisRec doubles (see kVisRec)
   double *lm_v, *lm_g, *lm_s, *lm_z; // [nW][Lm]
   double *sx, *zx, *ux, *ex_diag;  // [nW][D] jacobi scale, GN step, u, e
   double *Sfull, *gfull;           // optional dump of the assembled reduced system [nW][D*D], [nW][D]
@@ -88,7 +93,7 @@ struct KP {  // kernel parameters (device pointers are window-major with the str
   int4* lminfo;                    // k_tasks: landmarks sorted by start frame, packed (index, track length, first observation, fixed)
   int32_t *task_first, *task_cnt, *task_start, *ntasks;  // k_tasks: warp tasks over that order
   // cross-rank scalars (factor-sharded mode all-reduces them; single GPU reads them straight back)
-  double *c_lin, *c_gmax, *c_sums, *c_cand;  // [nW][4] {visual cost}, [nW] max|g_l|, [nW][8] k_backsub sums, [nW][4] {cand visual cost, |dl|^2, |l|^2}
+  double *c_lin, *c_gmax, *c_sums, *c_cand;  // record field {visual cost} (stride kVisRec), [nW] max|g_l|, [nW][8] k_backsub sums, [nW][4] {cand visual cost, |dl|^2, |l|^2}
   double* trace;                   // [nW][64][6]: candidate cost, model change, rho, radius, step norm, decision
   WinState* st;
 };

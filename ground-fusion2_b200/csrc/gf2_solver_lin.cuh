@@ -594,7 +594,7 @@ __global__ void __launch_bounds__(kLinThreads, 2) k_linearize(KP p, int w0) {
     __syncthreads();
   }
   // S_vis = U - Schur, g_schur = Schur[:,66]
-  double* Svis = p.Svis + (size_t)w * kNVMax * kNVMax;
+  double* Svis = p.Svis + (size_t)w * kVisRec;
   // blocked output: lower block pairs (bi >= bj) in the order bi (bi + 1) / 2 + bj, each a row-major 6x6 block (the layout
   // k_solve2 assembles from); diagonal blocks are written symmetric from their upper triangle
   for (int idx = t; idx < (F * (F + 1) / 2) * 36; idx += kLinThreads) {
@@ -607,9 +607,9 @@ __global__ void __launch_bounds__(kLinThreads, 2) k_linearize(KP p, int w0) {
     Svis[idx] = S.U[ublk(a / 6, b / 6, F) + (a % 6) * 6 + (b % 6)] - S.WT[(a + kRowShift) * kNVP + b + kRowShift];
   }
   for (int q = t; q < NV; q += kLinThreads) {
-    p.gvis[(size_t)w * kNVP + q] = S.g[q];                       // full visual gradient J^T r (pose part)
-    p.gschur[(size_t)w * kNVP + q] = S.WT[(q + kRowShift) * kNVP + 66 + kRowShift];         // sum_l w_l g_l / v'_l, subtracted to form the reduced rhs
-    p.Udiag[(size_t)w * kNVMax + q] = S.U[ublk(q / 6, q / 6, F) + (q % 6) * 7];
+    p.gvis[(size_t)w * kVisRec + q] = S.g[q];                       // full visual gradient J^T r (pose part)
+    p.gschur[(size_t)w * kVisRec + q] = S.WT[(q + kRowShift) * kNVP + 66 + kRowShift];         // sum_l w_l g_l / v'_l, subtracted to form the reduced rhs
+    p.Udiag[(size_t)w * kVisRec + q] = S.U[ublk(q / 6, q / 6, F) + (q % 6) * 7];
   }
   double red2[2] = {cost_acc, 0.0};
   block_sum<2>(red2, S.red);
@@ -618,7 +618,7 @@ __global__ void __launch_bounds__(kLinThreads, 2) k_linearize(KP p, int w0) {
   __syncthreads();
   if (t == 0) {
     double gm = 0; for (int i2 = 0; i2 < kLinWarps; i2++) gm = fmax(gm, S.red[i2]);
-    p.c_lin[(size_t)w * 4] = red2[0]; p.c_gmax[w] = gm;
+    p.c_lin[(size_t)w * kVisRec] = red2[0]; p.c_gmax[w] = gm;
   }
 #ifdef GF2_PHASE_CLOCKS
   if (t == 0 && blockIdx.x == 300) printf("k_linearize clocks: init %lld step %lld syrk %lld tail %lld total %lld\n", lc_t1 - lc_t0 - lc_step - lc_syrk, lc_step, lc_syrk, clock64() - lc_t1, clock64() - lc_t0);

@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(kSolveThreads, 2) k_solve2(KP p, int w0) {
   // and never summed in flight (an accumulate-as-you-load chain waits one DRAM latency per element). Thread t < 225 owns
   // element e = t of every 15x15 IMU block; the visual blocks are spread over all threads.
   constexpr int kVisPT = (kNBlkPairsS * 36 + kSolveThreads - 1) / kSolveThreads;          // 10
-  const double* Svis = p.Svis + (size_t)w * kNVMax * kNVMax;
+  const double* Svis = p.Svis + (size_t)w * kVisRec;
   const double* Hw = p.imu ? p.imu_H + (size_t)w * (F - 1) * 675 : nullptr;
   const bool imu_on = Hw != nullptr && t < 225;
   double vis[kVisPT], hii[kMaxF - 1], hji[kMaxF - 1], hjj[kMaxF - 1];  // blocks (i,i), (j,i), (j,j) of IMU factor K
@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(kSolveThreads, 2) k_solve2(KP p, int w0) {
     hii[K] = on ? Hw[K * 675 + t] : 0.0; hji[K] = on ? Hw[K * 675 + 225 + t] : 0.0; hjj[K] = on ? Hw[K * 675 + 450 + t] : 0.0;
   }
   double gv = 0.0, gsv = 0.0, udv = 0.0, gimu = 0.0;
-  if (t < NV) { gv = p.gvis[(size_t)w * kNVP + t]; gsv = p.gschur[(size_t)w * kNVP + t]; udv = p.Udiag[(size_t)w * kNVMax + t]; }
+  if (t < NV) { gv = p.gvis[(size_t)w * kVisRec + t]; gsv = p.gschur[(size_t)w * kVisRec + t]; udv = p.Udiag[(size_t)w * kVisRec + t]; }
   if (p.imu && t < D) {
     const double* gw = p.imu_g + (size_t)w * (F - 1) * 30;
     const int K = t / 15, r = t % 15;
@@ -436,7 +436,7 @@ __global__ void __launch_bounds__(kSolveThreads, 2) k_solve2(KP p, int w0) {
     }
     __syncthreads();
   }
-  if (t == 0) { st.cost_vis = p.c_lin[(size_t)w * 4]; st.gmax_l = p.c_gmax[w]; st.x_cost = st.cost_vis + p.cost_nv[w]; if (st.iteration == 0) st.initial_cost = st.x_cost; }
+  if (t == 0) { st.cost_vis = p.c_lin[(size_t)w * kVisRec]; st.gmax_l = p.c_gmax[w]; st.x_cost = st.cost_vis + p.cost_nv[w]; if (st.iteration == 0) st.initial_cost = st.x_cost; }
   if (p.Sfull) {
     double* Sf = p.Sfull + (size_t)w * p.Ds * p.Ds;   // Dx x Dx, packed at the front of the window's slot
     for (int idx = t; idx < Dx * Dx; idx += nt) {

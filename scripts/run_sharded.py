@@ -22,15 +22,9 @@ distinct = min(B, 8)
 base = synth.make_windows(distinct, config_id=4, n_landmarks=args.landmarks, wheel=True, n_planes=args.planes)
 w = {k: (np.concatenate([v] * ((B + distinct - 1) // distinct))[:B] if isinstance(v, np.ndarray) and v.ndim >= 1 and v.shape[0] == distinct and k not in ("imu_noise", "wheel_noise") else v) for k, v in base.items()}
 
-def solver_for(d):
-    return gf2.Solver(B, d["n_frames"], d["max_landmarks"], d["max_obs"], max_planes=d["max_planes"], max_imu_samples=d["n_imu_samples"], use_wheel=True, device=local)
-
-# wheel preintegration records: device kernel not built yet -> records come from the caller; here a zero-motion-consistent
-# record is not available without the oracle, so the wheel factor is exercised in tests/ (oracle records) and left out here
-w["use_wheel"] = False
-def mk(d):
-    s = gf2.Solver(B, d["n_frames"], d["max_landmarks"], d["max_obs"], max_planes=d["max_planes"], max_imu_samples=d["n_imu_samples"], device=local)
-    return s
+def mk(d):   # config 4: IMU + wheel (both preintegrated on the device from raw samples) + projection + LiDAR plane factors
+    return gf2.Solver(B, d["n_frames"], d["max_landmarks"], d["max_obs"], max_planes=d["max_planes"], max_imu_samples=d["n_imu_samples"],
+                      use_wheel=True, max_wheel_samples=d["n_wheel_samples"], device=local)
 mine = shard.shard_windows(w, rank, world)
 s = mk(mine)
 uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
@@ -59,7 +53,7 @@ if rank == 0:
     rst = ref.get_states(B); rlam = ref.get_landmarks(B)
     lam_full = shard.gather_landmarks(w["n_landmarks"], [g.cpu().numpy() for g in gathered], world)
     out = {"n_gpus": world, "windows": B, "landmarks": args.landmarks, "planes": args.planes,
-           "sharded_ms": 1e3 * float(tt.item()), "single_gpu_ms": 1e3 * min(t1),
+           "sharded_ms": 1e3 * float(tt.item()), "single_gpu_ms": 1e3 * min(t1), "nccl_ms_rank0": s.last_timing()["nccl_ms"],
            "sharded_solves_per_s": B / float(tt.item()), "single_solves_per_s": B / min(t1),
            "pose_diff": float(np.abs(st["para_pose"] - rst["para_pose"]).max()), "speedbias_diff": float(np.abs(st["para_speedbias"] - rst["para_speedbias"]).max()),
            "inv_depth_diff": float(np.abs(lam_full - rlam).max()),

@@ -198,6 +198,38 @@ def test_bad_arguments_are_rejected(gf2, synth):
     s.close()
 
 
+def test_factor_shards_add_up_on_one_gpu(gf2, synth):
+    """The arithmetic the NCCL all-reduce of the factor-sharded mode relies on, checked WITHOUT NCCL on one GPU: the reduced systems of the
+    landmark / plane shards of a config-4 window (each with the replicated IMU / wheel / prior factors) add up to the unsharded one once the
+    replicated part is counted once; so do the costs. (The 2-GPU test below needs a 2-GPU box.)"""
+    shard = importlib.import_module("gf2_b200.shard")
+    n, R = 2, 3
+    w = synth.make_windows(n, config_id=4, n_landmarks=300, wheel=True, n_planes=700)
+    opts = gf2.abi.default_opts()
+
+    def lin(d):
+        s = gf2.Solver(n, d["n_frames"], d["max_landmarks"], d["max_obs"], max_planes=d["max_planes"], max_imu_samples=d["n_imu_samples"],
+                       use_wheel=True, max_wheel_samples=d["n_wheel_samples"])
+        s.upload(d, preintegrate="device")
+        out = s.linearize(opts, n)
+        s.close()
+        return out
+    S, g, c = lin(w)
+    empty = _copy(w); empty["n_landmarks"] = np.zeros(n, np.int32); empty["n_planes"] = np.zeros(n, np.int32)
+    S0, g0, c0 = lin(empty)
+    Ss = np.zeros_like(S); gs = np.zeros_like(g); cs = np.zeros_like(c); nl = 0
+    for r in range(R):
+        d = shard.shard_windows(w, r, R)
+        nl += int(d["n_landmarks"][0])
+        Sr, gr, cr = lin(d)
+        Ss += Sr; gs += gr; cs += cr
+    assert nl == 300
+    Ss -= (R - 1) * S0; gs -= (R - 1) * g0; cs -= (R - 1) * c0
+    assert np.abs(Ss - S).max() <= 1e-10 * np.abs(S).max()
+    assert np.abs(gs - g).max() <= 1e-10 * np.abs(g).max()
+    assert np.abs(cs - c).max() <= 1e-10 * np.abs(c).max()
+
+
 def test_factor_sharded_two_gpus_match_single_gpu(gf2):
     """landmarks/planes sharded over 2 GPUs with one NCCL all-reduce per linearisation == single-GPU solve.
     Needs 2 visible GPUs (skipped on the 1-GPU box; run with `gpurun --gpus 2 -- python -m pytest tests -m gpu -k sharded`)."""
@@ -210,7 +242,7 @@ def test_factor_sharded_two_gpus_match_single_gpu(gf2):
         pytest.skip("needs 2 GPUs")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29531",
-                          os.path.join(root, "scripts", "run_sharded.py"), "--windows", "8", "--landmarks", "400", "--planes", "800", "--steps", "1"],
+                          os.path.join(root, "scripts", "run_sharded.py"), "--windows", "8", "--landmarks", "400", "--planes", "800", "--steps", "1"],   # wheel factors included (device preintegration)
                          capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     out = _json.loads([ln for ln in res.stdout.splitlines() if ln.startswith("{")][-1])
