@@ -357,7 +357,8 @@ def run_config4(gf2, synth, torch, dist, rank, world, local, B, steps, warmup):
     """BASELINE.json config 4: W10-F1000 + 10 wheel factors + 5,000 point-to-plane factors per window (IMU and wheel preintegrated on the
     device). world == 1: the windows solved on one GPU. world > 1: the factor-sharded mode of SURVEY 8(e) — every rank holds all frame
     states + IMU / wheel / prior factors of ALL B windows and the landmarks l mod N / planes k mod N; per linearisation ONE NCCL all-reduce
-    of the windows' 36.6 KB records (+ a MAX and two small SUMs per iteration); strong scaling over a fixed batch."""
+    reduce-scatter of the windows' 36.6 KB records, the reduced solve sharded by WINDOW (each rank factorises B / N systems), one all-gather
+    of the steps (+ two small all-reduces per iteration); strong scaling over a fixed batch."""
     shard = importlib.import_module("gf2_b200.shard")
     abi = gf2.abi
     distinct = min(B, 8)
@@ -409,7 +410,7 @@ def run_config4(gf2, synth, torch, dist, rank, world, local, B, steps, warmup):
         line.update({"scaling": "strong",
                      "nccl_ms_per_step_rank0": nccl_ms / steps, "nccl_share_rank0": nccl_ms / ms if rank == 0 else None,
                      "allreduce_bytes_per_iteration": int(B * (4576 * 8 + 8 + 64 + 32)),
-                     "collectives_per_iteration": "1 SUM of B x 36,608 B records + 1 MAX (grouped) after the sweep, 1 SUM of B x 64 B after back-substitution, 1 SUM of B x 32 B after the candidate",
+                     "collectives_per_iteration": "after the sweep: reduce-scatter (SUM) of the B x 36,608 B window records + reduce-scatter (MAX) of B x 8 B, grouped; each rank then solves its B / N windows; all-gather of the steps and trust-region states (B x (2 x 1320 + 304) B); all-reduce of B x 64 B after back-substitution and of B x 32 B after the candidate",
                      "nccl_us_per_iteration_rank0": 1e3 * nccl_ms / steps / it})
         if rank == 0:   # the same windows unsharded on rank 0's GPU alone: parity and the strong-scaling reference
             full = tile(base)
@@ -484,7 +485,7 @@ def main():
     ap.add_argument("--no-marginalize", action="store_true", help="skip the marginalization leg")
     ap.add_argument("--no-lk", action="store_true", help="skip the front-end (LK) leg")
     ap.add_argument("--no-config4", action="store_true", help="skip the config-4 leg (wheel + LiDAR planes; factor-sharded over the ranks when N > 1)")
-    ap.add_argument("--config4-windows", type=int, default=512, help="windows of the config-4 leg (fixed total: strong scaling when N > 1)")
+    ap.add_argument("--config4-windows", type=int, default=1184, help="windows of the config-4 leg (fixed total: strong scaling when N > 1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "gf2" else args.warmup
     rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))

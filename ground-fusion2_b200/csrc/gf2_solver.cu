@@ -222,6 +222,8 @@ struct NcclApi {
   int (*GetUniqueId)(gf2_nccl_uid*) = nullptr;
   int (*CommInitRank)(void**, int, gf2_nccl_uid, int) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*ReduceScatter)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
   int (*GroupStart)() = nullptr;
   int (*GroupEnd)() = nullptr;
   int (*CommDestroy)(void*) = nullptr;
@@ -234,14 +236,16 @@ struct NcclApi {
     GetUniqueId = (int (*)(gf2_nccl_uid*))dlsym(lib, "ncclGetUniqueId");
     CommInitRank = (int (*)(void**, int, gf2_nccl_uid, int))dlsym(lib, "ncclCommInitRank");
     AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(lib, "ncclAllReduce");
+    ReduceScatter = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(lib, "ncclReduceScatter");
+    AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(lib, "ncclAllGather");
     GroupStart = (int (*)())dlsym(lib, "ncclGroupStart"); GroupEnd = (int (*)())dlsym(lib, "ncclGroupEnd");
     CommDestroy = (int (*)(void*))dlsym(lib, "ncclCommDestroy");
     GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
-    return GetUniqueId && CommInitRank && AllReduce && GroupStart && GroupEnd && CommDestroy;
+    return GetUniqueId && CommInitRank && AllReduce && ReduceScatter && AllGather && GroupStart && GroupEnd && CommDestroy;
   }
 };
 NcclApi g_nccl;
-constexpr int kNcclFloat64 = 8, kNcclSum = 0, kNcclMax = 2;  // ncclDataType_t / ncclRedOp_t values of nccl.h
+constexpr int kNcclFloat64 = 8, kNcclChar = 0, kNcclSum = 0, kNcclMax = 2;  // ncclDataType_t / ncclRedOp_t values of nccl.h
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------ handle
@@ -263,7 +267,7 @@ struct gf2_solver {
   bool has_imu = false, has_wheel = false, has_prior = false, has_planes = false, dump_full = false;
   std::vector<int32_t> h_obeg;
   cudaEvent_t ev[4 * 64 + 3];
-  cudaEvent_t ev_nccl[6 * 64];   // pairs around the collectives of the factor-sharded mode (created by gf2_comm_init)
+  cudaEvent_t ev_nccl[8 * 64];   // pairs around the collectives of the factor-sharded mode (created by gf2_comm_init)
   double timing[8];
   WinState* h_state = nullptr;
 };
@@ -635,19 +639,38 @@ static int run(gf2_solver* h, int first, int n, const gf2_solve_opts* opts, gf2_
   const int iters = only_linearize ? 1 : iterations;
   for (int it = 0; it < iters; it++) {
     k_linearize<<<n, kLinThreads, sizeof(LinShared), h->stream>>>(k, first);
+    // Factor-sharded mode, SURVEY 8(e). The sweep ran on this rank's landmarks / planes of ALL n windows. When n divides by the ranks the
+    // windows' records [Svis | gvis | gschur | Udiag | visual cost] (36.6 KB each) are REDUCE-SCATTERED: rank r receives the summed records of
+    // its n / N windows, assembles + factorises only those (k_nonvis, k_solve2: the reduced solve is sharded by window instead of being
+    // replicated), and the steps [zx | ux] + trust-region states are ALL-GATHERED: same bytes on the wire as one all-reduce, 1 / N of the solve
+    // work. Otherwise (and for the gf2_linearize dump): one all-reduce, every rank solves every window.
+    const bool rs = h->nccl_comm && !only_linearize && n % h->comm_size == 0;
+    const int n_own = rs ? n / h->comm_size : n, first_own = rs ? first + h->comm_rank * n_own : first;
     if (h->nccl_comm) {
-      // ONE all-reduce of the windows' records [Svis | gvis | gschur | Udiag | visual cost] per linearisation (36.6 KB per window) + the
-      // max-norm of the landmark gradients (a MAX reduction cannot ride in the SUM buffer)
       cudaEventRecord(h->ev_nccl[nn++], h->stream);
       g_nccl.GroupStart();
-      g_nccl.AllReduce(k.Svis + (size_t)first * kVisRec, k.Svis + (size_t)first * kVisRec, (size_t)n * kVisRec, kNcclFloat64, kNcclSum, h->nccl_comm, h->stream);
-      g_nccl.AllReduce(k.c_gmax + first, k.c_gmax + first, (size_t)n, kNcclFloat64, kNcclMax, h->nccl_comm, h->stream);
+      if (rs) {
+        g_nccl.ReduceScatter(k.Svis + (size_t)first * kVisRec, k.Svis + (size_t)first_own * kVisRec, (size_t)n_own * kVisRec, kNcclFloat64, kNcclSum, h->nccl_comm, h->stream);
+        g_nccl.ReduceScatter(k.c_gmax + first, k.c_gmax + first_own, (size_t)n_own, kNcclFloat64, kNcclMax, h->nccl_comm, h->stream);
+      } else {
+        g_nccl.AllReduce(k.Svis + (size_t)first * kVisRec, k.Svis + (size_t)first * kVisRec, (size_t)n * kVisRec, kNcclFloat64, kNcclSum, h->nccl_comm, h->stream);
+        g_nccl.AllReduce(k.c_gmax + first, k.c_gmax + first, (size_t)n, kNcclFloat64, kNcclMax, h->nccl_comm, h->stream);   // a MAX cannot ride in the SUM buffer
+      }
       g_nccl.GroupEnd();
       cudaEventRecord(h->ev_nccl[nn++], h->stream);
     }
     cudaEventRecord(h->ev[ne++], h->stream);
-    k_nonvis<<<n, kNonvisThreads, 0, h->stream>>>(k, first);
-    k_solve2<<<n, kSolveThreads, sh_solve, h->stream>>>(k, first);
+    k_nonvis<<<n_own, kNonvisThreads, 0, h->stream>>>(k, first_own);
+    k_solve2<<<n_own, kSolveThreads, sh_solve, h->stream>>>(k, first_own);
+    if (rs) {
+      cudaEventRecord(h->ev_nccl[nn++], h->stream);
+      g_nccl.GroupStart();
+      g_nccl.AllGather(k.zx + (size_t)first_own * k.Ds, k.zx + (size_t)first * k.Ds, (size_t)n_own * k.Ds, kNcclFloat64, h->nccl_comm, h->stream);
+      g_nccl.AllGather(k.ux + (size_t)first_own * k.Ds, k.ux + (size_t)first * k.Ds, (size_t)n_own * k.Ds, kNcclFloat64, h->nccl_comm, h->stream);
+      g_nccl.AllGather(k.st + first_own, k.st + first, (size_t)n_own * sizeof(WinState), kNcclChar, h->nccl_comm, h->stream);
+      g_nccl.GroupEnd();
+      cudaEventRecord(h->ev_nccl[nn++], h->stream);
+    }
     cudaEventRecord(h->ev[ne++], h->stream);
     if (!only_linearize) {
       k_backsub<<<n, 256, 0, h->stream>>>(k, first);
