@@ -301,6 +301,84 @@ def run_replay_rgbd(gf2, synth):
             "median_track_ms": float(np.median(t_track[1:])) * 1e3, "median_process_ms": float(np.median(t_proc[1:])) * 1e3, "max_position_error_m": max(errs)}
 
 
+def run_replay_full(gf2, synth):
+    """BASELINE.json config 5: the full-fusion replay — features (RGB-D shaped) + 200 Hz IMU + 50 Hz wheel odometer + a 32-line 10 Hz LiDAR
+    (GNSS is off in the shipped configs, gnss_enable: 0). Per frame: the scan's keypoints go through lidarodom::addSurfCostFactor on the device
+    (gf2_lio_build_factors: voxel kNN + PCA normals + gate) against the device-resident map at the predicted pose; the resulting point-to-plane
+    factors ride in the visual-inertial-wheel window on that frame's pose (Estimator::inputLidarPlanes -> gf2_set_planes, the config-4
+    composition); Estimator::processImage solves + marginalizes; the scan is added to the map at the solved pose (gf2_lio_add_points).
+    One robot, one window at a time: a latency figure."""
+    import ctypes as C
+    L = C.CDLL(os.path.join(ROOT, "ground-fusion2_b200", "libgf2_host.so"))
+    L.gf2h_estimator_create.restype = C.c_void_p; L.gf2h_last_error.restype = C.c_char_p
+    P_ = lambda a: np.ascontiguousarray(a).ctypes.data_as(C.c_void_p)
+    abi = gf2.abi
+    st = synth.feature_stream(3, n_frames=70, pause=(40, 43), wheel_hz=50)
+    lid = synth.lidar_scans(st["gt_p"], st["gt_R"], seed=3)
+    e = C.c_void_p(L.gf2h_estimator_create())
+    L.gf2h_set_extrinsic(e, P_(st["tic"].copy()), P_(st["ric"].copy()), C.c_double(0.0), C.c_double(synth.G_NORM), P_(st["imu_noise"]))
+    calib = np.concatenate([st["tio"], st["rio"].ravel(), [1.0, 1.0, 1.0, 0.0]])
+    L.gf2h_set_wheel_parameters(e, P_(calib), P_(np.array([1.0, 0.0, 0.0, 0.0, st["wheel_noise"][0], st["wheel_noise"][1]])))
+    L.gf2h_set_flags(e, 1, 1, 1, 0); L.gf2h_set_min_parallax(e, C.c_double(10.0 / 460.0))
+    Pp = st["gt_p"][:11].copy(); R = st["gt_R"][:11].copy(); V = st["gt_v"][:11].copy(); Pp[10] = Pp[9]; R[10] = R[9]; V[10] = V[9]
+    fs = np.zeros((11, 21)); fs[:, 0:3] = Pp; fs[:, 3:12] = R.reshape(11, 9); fs[:, 12:15] = V
+    L.gf2h_set_frame_states(e, P_(fs))
+    lio = gf2.Lio(max_voxels=200000, max_keypoints=4096)
+    for f in range(10):
+        fr = st["frames"][f]; L.gf2h_add_image(e, f, len(fr["ids"]), P_(fr["ids"]), P_(fr["pts"]), C.c_double(0.0))
+        lio.add_points(lid["scans"][f] @ st["gt_R"][f].T + st["gt_p"][f])          # map bootstrap at the initial window's poses
+    for j in range(1, 10):
+        iv = st["imu"][j - 1]
+        L.gf2h_new_interval(e, j, P_(iv["first"][:3].copy()), P_(iv["first"][3:].copy()), P_(np.zeros(3)), P_(np.zeros(3)))
+        for s_ in iv["samples"]:
+            L.gf2h_push_imu(e, j, C.c_double(s_["dt"]), P_(s_["acc"].copy()), P_(s_["gyr"].copy()))
+        wv = st["wheel"][j - 1]
+        L.gf2h_new_wheel_interval(e, j, P_(wv["first"][:3].copy()), P_(wv["first"][3:].copy()))
+        for s_ in wv["samples"]:
+            L.gf2h_push_wheel(e, j, C.c_double(s_["dt"]), P_(s_["vel"].copy()), P_(s_["gyr"].copy()))
+    L.gf2h_set_imu0(e, P_(st["imu"][9]["first"][:3].copy()), P_(st["imu"][9]["first"][3:].copy()))
+    w0 = st["wheel"][9]["first"]
+    L.gf2h_process_wheel(e, C.c_double(0.0), C.c_double(0.0), P_(w0[:3].copy()), P_(w0[3:].copy()))
+    pose = np.zeros((11, 7)); sbv = np.zeros((11, 9)); exv = np.zeros(7); L.gf2h_vector2double(e, P_(pose), P_(sbv), P_(exv))
+    blk = np.zeros(1, abi.PRIOR_BLOCK); blk["kind"] = abi.BLK_POSE; blk["x0"][0, :7] = pose[0]
+    L.gf2h_set_prior(e, 6, P_(np.eye(6) * 100.0), P_(np.zeros(6)), 1, P_(blk))
+    t_lio, t_proc, t_map, flags, errs, nres = [], [], [], [], [], []
+    for k in range(10, st["n_frames"]):
+        for s_ in st["imu"][k - 1]["samples"]:
+            L.gf2h_process_imu(e, C.c_double(0.0), C.c_double(s_["dt"]), P_(s_["acc"].copy()), P_(s_["gyr"].copy()))
+        for s_ in st["wheel"][k - 1]["samples"]:
+            L.gf2h_process_wheel(e, C.c_double(0.0), C.c_double(s_["dt"]), P_(s_["vel"].copy()), P_(s_["gyr"].copy()))
+        t0 = time.perf_counter()
+        out = np.zeros((11, 21)); L.gf2h_get_frame_states(e, P_(out))              # slot 10 = the newest frame, dead-reckoned by processWheel
+        Rp = out[10, 3:12].reshape(3, 3); Pn = out[10, :3]
+        scan = lid["scans"][k]
+        kp = np.zeros(len(scan[::6]), abi.LIO_KEYPOINT); kp["raw_point"] = scan[::6]; kp["point"] = scan[::6] @ Rp.T + Pn
+        q = synth.quat_from_R(Rp)
+        o = abi.default_lio_opts(icp_model=abi.ICP_POINT_TO_PLANE, max_num_residuals=480, rotation=q, translation=Pn, translation_begin=Pn)
+        fac, _, _, _ = lio.build_factors(kp, o)
+        L.gf2h_input_lidar_planes(e, len(fac), P_(fac), C.c_double(31.622776601683793))
+        t1 = time.perf_counter()
+        fr = st["frames"][k]
+        flag = L.gf2h_process_image(e, len(fr["ids"]), P_(fr["ids"]), P_(fr["pts"]), C.c_double(fr["header"]))
+        t2 = time.perf_counter()
+        if flag < 0:
+            raise RuntimeError("full replay: " + L.gf2h_last_error(e).decode())
+        L.gf2h_get_frame_states(e, P_(out))                                        # the newest frame sits in slot 9 after the slide
+        Rs_ = out[9, 3:12].reshape(3, 3); Ps_ = out[9, :3]
+        lio.add_points(scan @ Rs_.T + Ps_)
+        t3 = time.perf_counter()
+        t_lio.append(t1 - t0); t_proc.append(t2 - t1); t_map.append(t3 - t2); flags.append(flag); nres.append(len(fac))
+        errs.append(float(np.linalg.norm(Ps_ - st["gt_p"][k])))
+    L.gf2h_estimator_destroy(e); lio.close()
+    tot = np.array(t_lio[1:]) + np.array(t_proc[1:]) + np.array(t_map[1:])
+    kf = sum(1 for f_ in flags[1:] if f_ == 0)
+    return {"metric": "full-fusion replay keyframes/sec (features + IMU 200 Hz + wheel 50 Hz + 32-line LiDAR 10 Hz; one robot)", "value": kf / float(tot.sum()), "unit": "keyframes/s",
+            "frames": len(flags), "keyframes": flags.count(0), "frames_per_s": 1.0 / float(np.median(tot)), "median_ms_per_frame": float(np.median(tot)) * 1e3,
+            "median_lio_factor_ms": float(np.median(t_lio[1:])) * 1e3, "median_process_image_ms": float(np.median(t_proc[1:])) * 1e3, "median_map_insert_ms": float(np.median(t_map[1:])) * 1e3,
+            "lidar_points_per_scan": int(len(lid["scans"][0])), "lidar_residuals_per_frame": float(np.mean(nres)), "max_position_error_m": max(errs),
+            "note": "GNSS is disabled in every shipped config (gnss_enable: 0) and is not part of the stream"}
+
+
 def run_replay(gf2, synth, with_cpu=True):
     """BASELINE.json config 5 shape, visual-inertial part: a synthetic feature + IMU stream through the C++ mirror's
     Estimator::processIMU / processImage (keyframe decision, depth initialisation, device solve + marginalization, outlier check, slide),
@@ -646,6 +724,7 @@ def main():
         lio_line = run_lio(gf2, synth, steps=10, with_cpu=not args.no_cpu_baseline)
         replay_line = run_replay(gf2, synth, with_cpu=not args.no_cpu_baseline)
         replay_line["rgbd"] = run_replay_rgbd(gf2, synth)
+        replay_line["full_fusion"] = run_replay_full(gf2, synth)
 
     if rank == 0:
         peaks, which = measured_peaks()

@@ -465,7 +465,7 @@ void Estimator::optimization() {
   if (!gf2) {
     gf2_solver_cfg cfg; memset(&cfg, 0, sizeof(cfg));
     cfg.device = 0; cfg.max_windows = 1; cfg.n_frames = WINDOW_SIZE + 1; cfg.max_landmarks = NUM_OF_F; cfg.max_obs = NUM_OF_F * (WINDOW_SIZE + 1);
-    cfg.max_imu_samples = kMaxImuSamples; cfg.max_prior_rows = GF2_MAX_PRIOR_DIM;
+    cfg.max_imu_samples = kMaxImuSamples; cfg.max_prior_rows = GF2_MAX_PRIOR_DIM; cfg.max_planes = (WINDOW_SIZE + 1) * kMaxPlanesPerFrame;
     cfg.use_wheel = (P.USE_WHEEL && !P.ONLY_INITIAL_WITH_WHEEL) ? 1 : 0; cfg.max_wheel_samples = cfg.use_wheel ? kMaxWheelSamples : 0;
     if (gf2_solver_create(&cfg, &gf2) != GF2_OK) { last_error = gf2_last_error(); gf2 = nullptr; return; }
   }
@@ -538,6 +538,20 @@ void Estimator::optimization() {
       if (rc == GF2_OK) rc = gf2_set_wheel(gf2, 0, 1, rec.data());
     }
   }
+  // LiDAR plane factors of the frames in the window (config 4 / 5 composition), frame index = window slot
+  bool any_planes = false;
+  if (rc == GF2_OK) {
+    std::vector<gf2_plane> pl;
+    for (int f = 0; f < F; f++) for (gf2_plane q : lidar_planes[f]) { q.frame = f; q.ct = 0; pl.push_back(q); }
+    int32_t np = (int32_t)pl.size();
+    any_planes = np > 0 || planes_resident;
+    if (any_planes) {
+      pl.resize((size_t)(WINDOW_SIZE + 1) * kMaxPlanesPerFrame);
+      rc = gf2_set_planes(gf2, 0, 1, &np, pl.data());
+      planes_resident = np > 0;
+    }
+    if (capture) { cap.planes.assign(pl.begin(), pl.begin() + np); }
+  }
   if (rc == GF2_OK) {
     const MarginalizationPrior& mp = last_marginalization_info;
     int32_t rows = (mp.valid ? mp.n : 0), nb = (int32_t)mp.blocks.size();
@@ -550,7 +564,7 @@ void Estimator::optimization() {
   }
   if (rc == GF2_OK) {
     gf2_solve_opts o; memset(&o, 0, sizeof(o));
-    o.max_iterations = P.NUM_ITERATIONS; o.huber_delta = 1.0; o.sqrt_info_px = FOCAL_LENGTH / 1.5; o.g_norm = P.G_NORM; o.lidar_sqrt_info = 1.0;
+    o.max_iterations = P.NUM_ITERATIONS; o.huber_delta = 1.0; o.sqrt_info_px = FOCAL_LENGTH / 1.5; o.g_norm = P.G_NORM; o.lidar_sqrt_info = lidar_sqrt_info;
     // blocks held constant exactly when the reference calls SetParameterBlockConstant (estimator.cpp:3051-3060, 3158-3161)
     const double v0 = std::sqrt(Vs[0].x * Vs[0].x + Vs[0].y * Vs[0].y + Vs[0].z * Vs[0].z);
     if ((P.ESTIMATE_EXTRINSIC && frame_count == WINDOW_SIZE && v0 > 0.2) || openExEstimation) openExEstimation = true; else o.const_mask |= GF2_CONST_EX_POSE;
@@ -801,7 +815,9 @@ void Estimator::slideWindow() {   // :3700-3857 (GNSS buffers and all_image_fram
         std::swap(Rs[i], Rs[i + 1]); std::swap(Ps[i], Ps[i + 1]);
         if (P.USE_IMU) { std::swap(pre_integrations[i], pre_integrations[i + 1]); std::swap(Vs[i], Vs[i + 1]); std::swap(Bas[i], Bas[i + 1]); std::swap(Bgs[i], Bgs[i + 1]); }
         if (P.USE_WHEEL) std::swap(pre_integrations_wheel[i], pre_integrations_wheel[i + 1]);
+        std::swap(lidar_planes[i], lidar_planes[i + 1]);
       }
+      lidar_planes[WINDOW_SIZE].clear();   // the factors of the marginalized frame (now in the last slot) are dropped
       Headers[WINDOW_SIZE] = Headers[WINDOW_SIZE - 1]; Ps[WINDOW_SIZE] = Ps[WINDOW_SIZE - 1]; Rs[WINDOW_SIZE] = Rs[WINDOW_SIZE - 1];
       if (P.USE_IMU) {
         Vs[WINDOW_SIZE] = Vs[WINDOW_SIZE - 1]; Bas[WINDOW_SIZE] = Bas[WINDOW_SIZE - 1]; Bgs[WINDOW_SIZE] = Bgs[WINDOW_SIZE - 1];
@@ -826,8 +842,13 @@ void Estimator::slideWindow() {   // :3700-3857 (GNSS buffers and all_image_fram
       delete pre_integrations_wheel[WINDOW_SIZE];
       pre_integrations_wheel[WINDOW_SIZE] = new WheelIntegrationBase(vel_0_wheel, gyr_0_wheel, sx, sy, sw, td_wheel);
     }
+    lidar_planes[frame_count - 1] = std::move(lidar_planes[frame_count]); lidar_planes[frame_count].clear();   // the newest scan takes the second-newest slot
     slideWindowNew();
   }
+}
+void Estimator::inputLidarPlanes(const gf2_plane* planes, int n) {
+  n = std::min(n, kMaxPlanesPerFrame);
+  lidar_planes[frame_count].assign(planes, planes + std::max(n, 0));
 }
 void Estimator::slideWindowNew() { sum_of_front++; f_manager.removeFront(frame_count); }   // :3859-3868
 void Estimator::slideWindowOld() {   // :3870-3899 with solver_flag == NON_LINEAR (shift_depth)
@@ -1231,6 +1252,13 @@ int gf2h_capture_get_wheel(void* e, gf2_wheel_sample* samples /*[10][kMaxWheelSa
   memcpy(calib12, c.exw, sizeof(c.exw)); calib12[7] = c.sxsysw[0]; calib12[8] = c.sxsysw[1]; calib12[9] = c.sxsysw[2]; calib12[10] = c.tdw; calib12[11] = 0.0;
   memcpy(exw_out, c.exw_out, sizeof(c.exw_out));
   return c.use_wheel;
+}
+void gf2h_input_lidar_planes(void* e, int n, const gf2_plane* planes, double sqrt_info) { Estimator* E = (Estimator*)e; if (sqrt_info > 0) E->lidar_sqrt_info = sqrt_info; E->inputLidarPlanes(planes, n); }
+int gf2h_capture_get_planes(void* e, gf2_plane* out, int cap_n) {
+  const Estimator::Capture& c = ((Estimator*)e)->cap;
+  const int n = std::min((int)c.planes.size(), cap_n);
+  for (int i = 0; i < n; i++) out[i] = c.planes[i];
+  return (int)c.planes.size();
 }
 int gf2h_process_image(void* e, int n, const int* ids, const double* pts8, double header) {
   Estimator* E = (Estimator*)e; E->processImage(image_of(n, ids, pts8), header);

@@ -216,9 +216,20 @@ class Estimator {
     int32_t use_wheel = 0; std::vector<gf2_wheel_sample> wheel_samples; std::vector<int32_t> wheel_n; std::vector<double> wheel_first, wheel_lin;
     double exw[7], sxsysw[3], tdw, exw_out[7];
     double pose_out[(WINDOW_SIZE + 1) * 7], sb_out[(WINDOW_SIZE + 1) * 9]; std::vector<double> invdep_out;   // straight from gf2_get_states / gf2_get_landmarks
+    std::vector<gf2_plane> planes;   // the LiDAR plane factors handed to gf2_set_planes
     double pose_marg[(WINDOW_SIZE + 1) * 7], sb_marg[(WINDOW_SIZE + 1) * 9]; std::vector<double> invdep_marg;  // the states gf2_marginalize ran at
   };
   bool capture = false; Capture cap;
+  // LiDAR point-to-plane factors attached to window poses: the composition of BASELINE.json config 4 / 5 (in the reference the
+  // LIO residuals live in lidarodom's own per-scan problem, LIO/liw/lio/lidarodom.cpp:534-661; here the factors addSurfCostFactor builds for
+  // the scan of a frame, gf2_lio_build_factors, ride in the visual-inertial window on that frame's pose). inputLidarPlanes() attaches the
+  // factors of the NEWEST frame before its processImage(); slideWindow() moves them with their frame; the factors of a marginalized frame
+  // are dropped (they do not enter the prior).
+  static const int kMaxPlanesPerFrame = 480;   // 11 frames x 480 = 5,280 planes: within the solver's plane-task capacity (BASELINE config 4: 500 per frame, 5,000 per window)
+  std::vector<gf2_plane> lidar_planes[WINDOW_SIZE + 1];
+  double lidar_sqrt_info = 31.622776601683793;   // sqrt(1 / laser_point_cov), LIO/liw/lio/lidarodom.cpp:10,13
+  void inputLidarPlanes(const gf2_plane* planes, int n);
+  bool planes_resident = false;
   double Headers[WINDOW_SIZE + 1] = {0};
   Matrix3d back_R0; Vector3d back_P0;
   int sum_of_back = 0, sum_of_front = 0;

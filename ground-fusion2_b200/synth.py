@@ -437,6 +437,25 @@ def _arc_trajectory(rng, n_frames, speed, yaw_rate, frame_dt, imu_hz, pause, whe
     return out
 
 
+def lidar_scans(gt_p, gt_R, seed=0, lines=32, az_step_deg=0.6, fov_deg=(-16.0, 15.0), noise=0.01, margin=6.0, height=(0.0, 3.0)):
+    """A 32-line spinning LiDAR (BASELINE.json config 5: 32 lines, 10 Hz) at the frame poses of a replay stream, ray-cast against an axis-aligned
+    box room that encloses the trajectory with `margin` metres to spare (floor / ceiling at `height`): per frame the hit points in the BODY frame
+    (LiDAR frame == body frame, R_IL = I) in scan order (line-major), 1 cm range noise. World z is up; the robot moves in the plane."""
+    rng = np.random.Generator(np.random.PCG64(BASE_SEED + 8000 + seed))
+    lo = np.array([gt_p[:, 0].min() - margin, gt_p[:, 1].min() - margin, height[0]]); hi = np.array([gt_p[:, 0].max() + margin, gt_p[:, 1].max() + margin, height[1]])
+    az = np.deg2rad(np.arange(0.0, 360.0, az_step_deg)); el = np.deg2rad(np.linspace(fov_deg[0], fov_deg[1], lines))
+    d = np.stack([np.cos(el)[:, None] * np.cos(az)[None], np.cos(el)[:, None] * np.sin(az)[None], np.sin(el)[:, None] * np.ones_like(az)[None]], -1).reshape(-1, 3)
+    scans = []
+    for k in range(len(gt_p)):
+        o = gt_p[k]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            t = np.where(d > 0, (hi - o) / d, np.where(d < 0, (lo - o) / d, np.inf)).min(axis=1)
+        t = t + rng.normal(0, noise, t.shape)
+        pw = o + d * t[:, None]
+        scans.append(np.ascontiguousarray((pw - o) @ gt_R[k]))      # R_wb^T (p_w - P)
+    return {"scans": scans, "room": (lo, hi)}
+
+
 def feature_stream(seed=0, n_frames=45, target_features=150, speed=1.0, yaw_rate=0.2, frame_dt=0.1, imu_hz=200, pixel_noise=0.5,
                    max_life=30, depth_range=(1.5, 12.0), pause=None, wheel_hz=0):
     """A synthetic stream for the steady-state replay (BASELINE.json config 5 shape, visual-inertial part): a planar arc like

@@ -326,3 +326,94 @@ def test_replay_with_wheel_odometer_and_free_wheel_extrinsic(gf2, oracle):
     print(f"wheel replay: {len(flags)} frames, {flags.count(0)} keyframes, max position error {max(errs):.3f} m, worst oracle deviation {worst:.2e}, "
           f"calibration deviation / motion {worst_cal:.2e}, |tio - truth| = {np.abs(cal16[:3] - st['tio']).max():.3f} m")
     L.gf2h_estimator_destroy(e)
+
+
+def test_full_fusion_replay_lidar_planes_wheel_features(gf2, oracle):
+    """BASELINE.json config 5 shape: features + IMU + 50 Hz wheel odometer + a 32-line 10 Hz LiDAR. Per frame the scan's keypoints go through the
+    device's addSurfCostFactor (gf2_lio_build_factors) against the device-resident voxel map at the dead-reckoned pose, the point-to-plane factors
+    ride in the window on that frame's pose (Estimator::inputLidarPlanes -> gf2_set_planes, slid with the frames), processImage solves and
+    marginalizes, the scan is inserted into the map at the solved pose. Every solve against the oracle on identical inputs (planes included)."""
+    synth = importlib.import_module("gf2_b200.synth")
+    abi = gf2.abi
+    L = H.lib()
+    st = synth.feature_stream(3, n_frames=26, pause=(18, 20), wheel_hz=50)
+    lid = synth.lidar_scans(st["gt_p"], st["gt_R"], seed=3)
+    e = C.c_void_p(L.gf2h_estimator_create())
+    L.gf2h_set_extrinsic(e, H.p(st["tic"].copy()), H.p(st["ric"].copy()), C.c_double(0.0), C.c_double(synth.G_NORM), H.p(st["imu_noise"]))
+    calib = np.concatenate([st["tio"], st["rio"].ravel(), [1.0, 1.0, 1.0, 0.0]])
+    L.gf2h_set_wheel_parameters(e, H.p(calib), H.p(np.array([1.0, 0.0, 0.0, 0.0, st["wheel_noise"][0], st["wheel_noise"][1]])))
+    L.gf2h_set_flags(e, 1, 1, 1, 0)
+    L.gf2h_set_min_parallax(e, C.c_double(10.0 / 460.0))
+    rng = np.random.default_rng(4)
+    P = st["gt_p"][:11].copy() + rng.normal(0, 0.01, (11, 3)); R = st["gt_R"][:11].copy(); V = st["gt_v"][:11].copy()
+    P[10] = P[9]; R[10] = R[9]; V[10] = V[9]
+    L.gf2h_set_frame_states(e, H.p(H.frame_states(P, R, V, np.zeros((11, 3)), np.zeros((11, 3)))))
+    lio = gf2.Lio(max_voxels=200000, max_keypoints=4096)
+    for f in range(10):
+        fr = st["frames"][f]
+        L.gf2h_add_image(e, f, len(fr["ids"]), H.p(fr["ids"]), H.p(fr["pts"]), C.c_double(0.0))
+        lio.add_points(lid["scans"][f] @ st["gt_R"][f].T + st["gt_p"][f])
+    for j in range(1, 10):
+        iv = st["imu"][j - 1]
+        L.gf2h_new_interval(e, j, H.p(iv["first"][:3].copy()), H.p(iv["first"][3:].copy()), H.p(np.zeros(3)), H.p(np.zeros(3)))
+        for s in iv["samples"]:
+            L.gf2h_push_imu(e, j, C.c_double(s["dt"]), H.p(s["acc"].copy()), H.p(s["gyr"].copy()))
+        wv = st["wheel"][j - 1]
+        L.gf2h_new_wheel_interval(e, j, H.p(wv["first"][:3].copy()), H.p(wv["first"][3:].copy()))
+        for s in wv["samples"]:
+            L.gf2h_push_wheel(e, j, C.c_double(s["dt"]), H.p(s["vel"].copy()), H.p(s["gyr"].copy()))
+    L.gf2h_set_imu0(e, H.p(st["imu"][9]["first"][:3].copy()), H.p(st["imu"][9]["first"][3:].copy()))
+    w0 = st["wheel"][9]["first"]
+    L.gf2h_process_wheel(e, C.c_double(0.0), C.c_double(0.0), H.p(w0[:3].copy()), H.p(w0[3:].copy()))
+    pose = np.zeros((11, 7)); sbv = np.zeros((11, 9)); exv = np.zeros(7)
+    L.gf2h_vector2double(e, H.p(pose), H.p(sbv), H.p(exv))
+    blk = np.zeros(1, abi.PRIOR_BLOCK); blk["kind"] = abi.BLK_POSE; blk["x0"][0, :7] = pose[0]
+    L.gf2h_set_prior(e, 6, H.p(np.eye(6) * 100.0), H.p(np.zeros(6)), 1, H.p(blk))
+    L.gf2h_set_capture(e, 1)
+    L.gf2h_capture_get_planes.restype = C.c_int
+    flags, errs, worst, n_planes_seen = [], [], 0.0, []
+    for k in range(10, st["n_frames"]):
+        for s in st["imu"][k - 1]["samples"]:
+            L.gf2h_process_imu(e, C.c_double(0.0), C.c_double(s["dt"]), H.p(s["acc"].copy()), H.p(s["gyr"].copy()))
+        for s in st["wheel"][k - 1]["samples"]:
+            L.gf2h_process_wheel(e, C.c_double(0.0), C.c_double(s["dt"]), H.p(s["vel"].copy()), H.p(s["gyr"].copy()))
+        out = np.zeros((11, 21)); L.gf2h_get_frame_states(e, H.p(out))
+        Rp = out[10, 3:12].reshape(3, 3); Pn = out[10, :3]
+        assert np.linalg.norm(Pn - st["gt_p"][k]) < 0.2                                 # processWheel dead-reckoned the newest frame
+        scan = lid["scans"][k]
+        kp = np.zeros(len(scan[::6]), abi.LIO_KEYPOINT); kp["raw_point"] = scan[::6]; kp["point"] = scan[::6] @ Rp.T + Pn
+        o = abi.default_lio_opts(icp_model=abi.ICP_POINT_TO_PLANE, max_num_residuals=480, rotation=synth.quat_from_R(Rp), translation=Pn, translation_begin=Pn)
+        fac, _, _, _ = lio.build_factors(kp, o)
+        assert len(fac) > 200, len(fac)
+        L.gf2h_input_lidar_planes(e, len(fac), H.p(fac), C.c_double(31.622776601683793))
+        fr = st["frames"][k]
+        flag = L.gf2h_process_image(e, len(fr["ids"]), H.p(fr["ids"]), H.p(fr["pts"]), C.c_double(fr["header"]))
+        assert flag >= 0, L.gf2h_last_error(e)
+        flags.append(flag)
+        # ---- this solve against the oracle on identical inputs: landmarks, IMU + wheel samples, prior, planes
+        c = _capture(L, e, abi)
+        ws = np.zeros((10, 64), abi.WHEEL_SAMPLE); wn = np.zeros(10, np.int32); wf = np.zeros((10, 6)); wl = np.zeros((10, 4)); cal = np.zeros(12); exw_out = np.zeros(7)
+        assert L.gf2h_capture_get_wheel(e, H.p(ws), H.p(wn), H.p(wf), H.p(wl), H.p(cal), H.p(exw_out)) == 1
+        pl = np.zeros(11 * 480, abi.PLANE); npl = L.gf2h_capture_get_planes(e, H.p(pl), len(pl))
+        n_planes_seen.append(npl)
+        assert npl >= len(fac) and set(np.unique(pl["frame"][:npl])) <= set(range(11)) and (pl["frame"][:npl] == 10).sum() == len(fac)
+        opts = abi.default_opts(const_mask=c["const_mask"], lidar_sqrt_info=31.622776601683793)
+        w = _oracle_window(c, st["imu_noise"], abi)
+        w.update(use_wheel=True, ex_pose_wheel=cal[None, :7].copy(), sxsysw=cal[None, 7:10].copy(), td_wheel=cal[10:11].copy(), wheel_samples=ws[None].copy(), wheel_n=wn[None].copy(),
+                 wheel_first=wf[None].copy(), wheel_lin=wl[None].copy(), wheel_noise=st["wheel_noise"],
+                 max_planes=max(npl, 1), n_planes=np.array([npl], np.int32), planes=pl[None, :max(npl, 1)].copy())
+        oracle.imu_preintegrate(w); oracle.wheel_preintegrate(w)
+        oracle.solve_batch(w, opts)
+        scale = np.abs(w["para_pose"][0, :, :3]).max()
+        d = max(np.abs(c["pose_out"][:, :3] - w["para_pose"][0, :, :3]).max() / scale, np.abs(c["pose_out"][:, 3:] - w["para_pose"][0, :, 3:]).max())
+        worst = max(worst, d)
+        assert d <= 1e-4, (k, d)
+        L.gf2h_get_frame_states(e, H.p(out))
+        lio.add_points(scan @ out[9, 3:12].reshape(3, 3).T + out[9, :3])
+        errs.append(np.linalg.norm(out[9, :3] - st["gt_p"][k]))
+    assert 0 in flags and 1 in flags
+    assert max(n_planes_seen) > 3000                                                    # the window fills up with the scans' factors as it slides
+    assert max(errs) < 0.10, (max(errs), errs)
+    print(f"full-fusion replay: {len(flags)} frames, {flags.count(0)} keyframes, up to {max(n_planes_seen)} plane factors per window, "
+          f"max position error {max(errs):.3f} m, worst oracle deviation {worst:.2e}")
+    L.gf2h_estimator_destroy(e); lio.close()
