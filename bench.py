@@ -405,11 +405,14 @@ def run_replay(gf2, synth, with_cpu=True):
     pose = np.zeros((11, 7)); sbv = np.zeros((11, 9)); exv = np.zeros(7); L.gf2h_vector2double(e, P_(pose), P_(sbv), P_(exv))
     blk = np.zeros(1, gf2.abi.PRIOR_BLOCK); blk["kind"] = gf2.abi.BLK_POSE; blk["x0"][0, :7] = pose[0]
     L.gf2h_set_prior(e, 6, P_(np.eye(6) * 100.0), P_(np.zeros(6)), 1, P_(blk))
-    steps, flags, errs = [], [], []
+    steps, flags, errs, gaps = [], [], [], []
     for k in range(10, st["n_frames"]):
         for s_ in st["imu"][k - 1]["samples"]:
             L.gf2h_process_imu(e, C.c_double(0.0), C.c_double(s_["dt"]), P_(s_["acc"].copy()), P_(s_["gyr"].copy()))
         fr = st["frames"][k]
+        # the marginalization of the previous frame runs asynchronously on the device; a live 10 Hz stream leaves it 100 ms before the next
+        # image: wait for it OUTSIDE the latency clock (its duration is reported as background_marginalization_ms and counted in ms_per_frame)
+        tg = time.perf_counter(); L.gf2h_finish_marginalization(e); gaps.append(time.perf_counter() - tg)
         t0 = time.perf_counter()
         flag = L.gf2h_process_image(e, len(fr["ids"]), P_(fr["ids"]), P_(fr["pts"]), C.c_double(fr["header"]))
         steps.append(time.perf_counter() - t0)
@@ -418,9 +421,13 @@ def run_replay(gf2, synth, with_cpu=True):
         flags.append(flag)
         out = np.zeros((11, 21)); L.gf2h_get_frame_states(e, P_(out)); errs.append(float(np.linalg.norm(out[9, :3] - st["gt_p"][k])))
     L.gf2h_estimator_destroy(e)
-    med = float(np.median(steps[1:]))
+    med = float(np.median(np.array(steps[1:]) + np.array(gaps[2:] + [gaps[-1]])))   # device-busy time per frame: processImage + the marginalization that follows it
+    lat = float(np.median(steps[1:]))
     line = {"metric": "replay frames/sec through Estimator::processImage (one window at a time: single-robot latency)", "value": 1.0 / med, "unit": "frames/s",
-            "frames": len(flags), "keyframes": flags.count(0), "median_ms_per_frame": med * 1e3, "first_frame_ms": steps[0] * 1e3,
+            "frames": len(flags), "keyframes": flags.count(0), "median_ms_per_frame": med * 1e3, "median_process_image_latency_ms": lat * 1e3,
+            "background_marginalization_ms": float(np.median(gaps[2:])) * 1e3,
+            "latency_note": "processImage returns after the solve; the marginalization runs asynchronously on the device (the prior stays resident) and is complete long before the next image of a 10 Hz stream; median_ms_per_frame = latency + that background time (back-to-back throughput)",
+            "first_frame_ms": steps[0] * 1e3,
             "max_position_error_m": max(errs), "features_per_frame": 150}
     if with_cpu:
         import gf2_oracle as orc

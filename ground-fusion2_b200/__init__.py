@@ -40,7 +40,7 @@ ABI_SYMBOLS = [
     "gf2_solver_set_stream", "gf2_snapshot_states", "gf2_restore_states", "gf2_host_alloc", "gf2_host_free",
     "gf2_imu_preintegrate_resident", "gf2_get_trace",
     "gf2_set_landmarks", "gf2_set_imu", "gf2_imu_preintegrate", "gf2_get_imu", "gf2_set_wheel", "gf2_wheel_preintegrate", "gf2_get_wheel", "gf2_set_prior",
-    "gf2_set_planes", "gf2_set_plane_alpha", "gf2_marginalize", "gf2_get_prior", "gf2_last_marginalize_ms", "gf2_solve", "gf2_linearize", "gf2_reduced_dim", "gf2_get_reduced_system", "gf2_get_states",
+    "gf2_set_planes", "gf2_set_plane_alpha", "gf2_marginalize", "gf2_marginalize_async", "gf2_marginalize_wait", "gf2_get_prior", "gf2_last_marginalize_ms", "gf2_solve", "gf2_linearize", "gf2_reduced_dim", "gf2_get_reduced_system", "gf2_get_states",
     "gf2_get_landmarks", "gf2_comm_init", "gf2_comm_unique_id", "gf2_last_timing", "gf2_tracker_create",
     "gf2_tracker_destroy", "gf2_tracker_track", "gf2_tracker_track_fb", "gf2_tracker_last_timing",
     "gf2_tracker_track_image", "gf2_tracker_detect", "gf2_tracker_min_eigen_map", "gf2_detect_select",

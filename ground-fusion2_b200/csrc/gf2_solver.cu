@@ -267,6 +267,7 @@ struct gf2_solver {
   bool has_imu = false, has_wheel = false, has_prior = false, has_planes = false, dump_full = false;
   std::vector<int32_t> h_obeg;
   cudaEvent_t ev[4 * 64 + 3];
+  cudaEvent_t ev_marg[3] = {nullptr, nullptr, nullptr}; bool marg_pending = false;   // gf2_marginalize_async / _wait
   cudaEvent_t ev_nccl[8 * 64];   // pairs around the collectives of the factor-sharded mode (created by gf2_comm_init)
   double timing[8];
   WinState* h_state = nullptr;
@@ -354,6 +355,7 @@ int gf2_solver_create(const gf2_solver_cfg* cfg, gf2_solver** out) {
   k.gvis = k.Svis + kNVMax * kNVMax; k.gschur = k.gvis + kNVP; k.Udiag = k.gschur + kNVP; k.c_lin = k.Udiag + kNVMax;
   cudaMemset((void*)k.prior_rows, 0, sizeof(int32_t) * B); cudaMemset((void*)k.prior_nblocks, 0, sizeof(int32_t) * B);
   for (auto& e : h->ev) cudaEventCreate(&e);
+  for (auto& e : h->ev_marg) cudaEventCreate(&e);
   cudaHostAlloc((void**)&h->h_state, sizeof(WinState) * B, cudaHostAllocDefault);
   // opt in to large dynamic shared memory
   cudaFuncSetAttribute(k_linearize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LinShared));
@@ -374,6 +376,7 @@ void gf2_solver_destroy(gf2_solver* h) {
   for (void* p : h->allocs) cudaFree(p);
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
   for (auto& e : h->ev_nccl) if (e) cudaEventDestroy(e);
+  for (auto& e : h->ev_marg) if (e) cudaEventDestroy(e);
   if (h->h_state) cudaFreeHost(h->h_state);
   if (h->h_marg) cudaFreeHost(h->h_marg);
   if (h->nccl_comm && g_nccl.lib) g_nccl.CommDestroy(h->nccl_comm);
@@ -775,6 +778,11 @@ int gf2_get_landmarks(gf2_solver* h, int first, int n, double* inv_depth) {
 
 // ---------------------------------------------------------------------------------------------------------------------
 int gf2_marginalize(gf2_solver* h, int first, int n, int32_t mode, const gf2_solve_opts* opts, int32_t* status, int32_t* m_dims) {
+  GF2_TRY(gf2_marginalize_async(h, first, n, mode, opts));
+  return gf2_marginalize_wait(h, first, n, status, m_dims);
+}
+
+int gf2_marginalize_async(gf2_solver* h, int first, int n, int32_t mode, const gf2_solve_opts* opts) {
   GF2_TRY(check_range(h, first, n));
   if (!opts) return gf2::fail(GF2_ERR_INVALID, "null options");
   if (mode != GF2_MARGIN_OLD && mode != GF2_MARGIN_SECOND_NEW) return gf2::fail(GF2_ERR_INVALID, "mode %d", mode);
@@ -796,19 +804,30 @@ int gf2_marginalize(gf2_solver* h, int first, int n, int32_t mode, const gf2_sol
   const size_t sh_build = ((sizeof(MargShared) + 15) & ~size_t(15)) + sizeof(double) * kMargTMax * kMargLD;
   const int Kc = 6 * (k.F - 1) + 16 + (k.use_wheel ? 10 : 0);
   const size_t sh_eig = ((sizeof(EigShared) + 15) & ~size_t(15)) + sizeof(double) * 2 * Kc * (Kc | 1);
-  cudaEventRecord(h->ev[0], h->stream);
+  cudaEventRecord(h->ev_marg[0], h->stream);
   k_prepare<<<n, 128, sizeof(double) * 450 * GF2_MAX_FRAMES, h->stream>>>(k, first);   // IMU sqrt_info, J0^T J0 of the old prior
   k_marg_build<<<n, kMargThreads, sh_build, h->stream>>>(k, first, mp);
   k_marg_eig<<<n, kEigThreads, sh_eig, h->stream>>>(k, first, mp);
-  cudaEventRecord(h->ev[1], h->stream);
+  cudaEventRecord(h->ev_marg[1], h->stream);
   GF2_CUDA(cudaGetLastError());
   GF2_CUDA(cudaMemcpyAsync(h->h_marg, mp.status + first, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, h->stream));
   GF2_CUDA(cudaMemcpyAsync(h->h_marg + B, mp.mdim + first, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, h->stream));
-  GF2_CUDA(cudaStreamSynchronize(h->stream));
-  float ms = 0; cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
+  cudaEventRecord(h->ev_marg[2], h->stream);
+  h->has_prior = true;   // windows outside [first, first + n) keep prior_rows = 0 from creation unless gf2_set_prior filled them
+  h->marg_pending = true;
+  return GF2_OK;
+}
+
+int gf2_marginalize_wait(gf2_solver* h, int first, int n, int32_t* status, int32_t* m_dims) {
+  GF2_TRY(check_range(h, first, n));
+  if (n == 0) return GF2_OK;
+  if (!h->marg_pending || !h->h_marg) return gf2::fail(GF2_ERR_INVALID, "gf2_marginalize_wait without a pending gf2_marginalize_async");
+  const int B = h->cfg.max_windows;
+  GF2_CUDA(cudaEventSynchronize(h->ev_marg[2]));
+  h->marg_pending = false;
+  float ms = 0; cudaEventElapsedTime(&ms, h->ev_marg[0], h->ev_marg[1]);
   h->marg_ms = ms;
   for (int i = 0; i < n; i++) { if (status) status[i] = h->h_marg[i]; if (m_dims) m_dims[i] = h->h_marg[B + i]; }
-  h->has_prior = true;   // windows outside [first, first + n) keep prior_rows = 0 from creation unless gf2_set_prior filled them
   return GF2_OK;
 }
 

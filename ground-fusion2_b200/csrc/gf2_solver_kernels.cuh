@@ -229,43 +229,74 @@ __device__ __forceinline__ void mma_f64(double& d0, double& d1, double a, double
 // ------------------------------------------------------------------------------------------------ k_prepare
 // Once per solve: IMU/wheel sqrt_info = LLT(cov^-1).L^T (VE/factor/imu_factor.h:73, wheel_factor.h:85), prior
 // H = J0^T J0 and its column map, trust-region state reset, ambient norm of x.
+// sqrt_info = LLT(cov^-1).matrixL()^T (VE/factor/imu_factor.h:73, wheel_factor.h:85): Gauss-Jordan inverse with partial pivoting on the
+// augmented [cov | I] followed by the Cholesky factor of the inverse, ONE WARP per factor: lane c owns column c of the N x 2N augmented
+// matrix in shared memory. Every element goes through the same operations in the same order as a one-thread elimination would apply, so
+// the result does not depend on the lane count (a single thread per factor took 0.45 ms per 15 x 15 factor: the longest kernel of a
+// one-window solve).
 template <int N>
-__device__ void sqrt_info_from_cov(const double* cov, double* out /* N*N row-major, upper triangular */, double* scratch /* 2*N*N */) {
-  double* m = scratch;  // [N][2N] Gauss-Jordan with partial pivoting
-  for (int r = 0; r < N; r++) for (int c = 0; c < N; c++) { m[r * 2 * N + c] = cov[r * N + c]; m[r * 2 * N + N + c] = (r == c) ? 1.0 : 0.0; }
+__device__ void sqrt_info_from_cov_warp(const double* cov, double* out /* N*N row-major, upper triangular */, double* m /* shared scratch [N][2N] */) {
+  const int lane = threadIdx.x & 31;
+  constexpr int W = 2 * N;
+  static_assert(W <= 32, "one lane per column of the augmented matrix");
+  if (lane < W) for (int r = 0; r < N; r++) m[r * W + lane] = lane < N ? cov[r * N + lane] : (r == lane - N ? 1.0 : 0.0);
+  __syncwarp();
   for (int col = 0; col < N; col++) {
-    int piv = col; double best = fabs(m[col * 2 * N + col]);
-    for (int r = col + 1; r < N; r++) { double v = fabs(m[r * 2 * N + col]); if (v > best) { best = v; piv = r; } }
-    if (piv != col) for (int c = 0; c < 2 * N; c++) { double t = m[piv * 2 * N + c]; m[piv * 2 * N + c] = m[col * 2 * N + c]; m[col * 2 * N + c] = t; }
-    double d = m[col * 2 * N + col];
-    for (int c = 0; c < 2 * N; c++) m[col * 2 * N + c] /= d;
-    for (int r = 0; r < N; r++) if (r != col) { double f = m[r * 2 * N + col]; if (f != 0.0) for (int c = 0; c < 2 * N; c++) m[r * 2 * N + c] -= f * m[col * 2 * N + c]; }
+    // pivot: the row >= col with the largest |m[r][col]| (first one on ties, as a sequential scan with `>` finds)
+    double best = (lane >= col && lane < N) ? fabs(m[lane * W + col]) : -1.0; int piv = lane;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ob = __shfl_xor_sync(0xffffffffu, best, o); const int op = __shfl_xor_sync(0xffffffffu, piv, o);
+      if (ob > best || (ob == best && op < piv)) { best = ob; piv = op; }
+    }
+    if (lane < W) {
+      if (piv != col) { const double t = m[piv * W + lane]; m[piv * W + lane] = m[col * W + lane]; m[col * W + lane] = t; }
+    }
+    __syncwarp();
+    const double d = m[col * W + col];
+    __syncwarp();
+    if (lane < W) m[col * W + lane] /= d;
+    __syncwarp();
+    double f[N];
+#pragma unroll
+    for (int r = 0; r < N; r++) f[r] = m[r * W + col];   // read before lane `col` rewrites its own column
+    __syncwarp();
+    if (lane < W) {
+      const double pr = m[col * W + lane];
+#pragma unroll
+      for (int r = 0; r < N; r++) if (r != col && f[r] != 0.0) m[r * W + lane] -= f[r] * pr;
+    }
+    __syncwarp();
   }
-  // Cholesky of the inverse (lower), in place in the right half
+  // Cholesky of the inverse (lower), in place in the right half: column j by lanes i = j .. N-1
   for (int j = 0; j < N; j++) {
-    double d = m[j * 2 * N + N + j];
-    for (int k = 0; k < j; k++) d -= m[j * 2 * N + N + k] * m[j * 2 * N + N + k];
-    d = sqrt(d); m[j * 2 * N + N + j] = d;
-    for (int i = j + 1; i < N; i++) { double s = m[i * 2 * N + N + j]; for (int k = 0; k < j; k++) s -= m[i * 2 * N + N + k] * m[j * 2 * N + N + k]; m[i * 2 * N + N + j] = s / d; }
+    double dj = m[j * W + N + j];
+    for (int k = 0; k < j; k++) dj -= m[j * W + N + k] * m[j * W + N + k];
+    dj = sqrt(dj);
+    __syncwarp();
+    if (lane == j) m[j * W + N + j] = dj;
+    else if (lane > j && lane < N) { double sacc = m[lane * W + N + j]; for (int k = 0; k < j; k++) sacc -= m[lane * W + N + k] * m[j * W + N + k]; m[lane * W + N + j] = sacc / dj; }
+    __syncwarp();
   }
-  for (int r = 0; r < N; r++) for (int c = 0; c < N; c++) out[r * N + c] = (c >= r) ? m[c * 2 * N + N + r] : 0.0;
+  if (lane < N) for (int r = 0; r < N; r++) out[r * N + lane] = (lane >= r) ? m[lane * W + N + r] : 0.0;
+  __syncwarp();
 }
 
 __global__ void k_prepare(KP p, int w0) {
   const int w = w0 + blockIdx.x;
   const int F = p.F, t = threadIdx.x;
   extern __shared__ double sh[];
-  // IMU sqrt_info: one thread per factor, scratch in global-backed local arrays would spill; use shared: 2*225 doubles per factor
-  if (p.imu && t < F - 1) {
-    const gf2_imu_preint& rec = p.imu[(size_t)w * (F - 1) + t];
-    double* out = p.imu_sqrt + ((size_t)w * (F - 1) + t) * 225;
-    if (rec.valid && rec.sum_dt <= 10.0) sqrt_info_from_cov<15>(rec.covariance, out, sh + t * 450);
-  }
-  __syncthreads();
-  if (p.use_wheel && p.wheel && t < F - 1) {
-    const gf2_wheel_preint& rec = p.wheel[(size_t)w * (F - 1) + t];
-    double* out = p.wheel_sqrt + ((size_t)w * (F - 1) + t) * 36;
-    if (rec.valid && rec.sum_dt <= 10.0) sqrt_info_from_cov<6>(rec.covariance, out, sh + t * 72);
+  // IMU / wheel sqrt_info: one warp per factor (warp q handles the factors q, q + nwarps, ...), 450 doubles of shared scratch per warp
+  {
+    const int wid = t >> 5, nwarp = blockDim.x >> 5;
+    if (p.imu) for (int k = wid; k < F - 1; k += nwarp) {
+      const gf2_imu_preint& rec = p.imu[(size_t)w * (F - 1) + k];
+      if (rec.valid && rec.sum_dt <= 10.0) sqrt_info_from_cov_warp<15>(rec.covariance, p.imu_sqrt + ((size_t)w * (F - 1) + k) * 225, sh + wid * 450);
+    }
+    if (p.use_wheel && p.wheel) for (int k = wid; k < F - 1; k += nwarp) {
+      const gf2_wheel_preint& rec = p.wheel[(size_t)w * (F - 1) + k];
+      if (rec.valid && rec.sum_dt <= 10.0) sqrt_info_from_cov_warp<6>(rec.covariance, p.wheel_sqrt + ((size_t)w * (F - 1) + k) * 36, sh + wid * 450);
+    }
   }
   // prior: column map and H = J0^T J0
   const int n = p.prior_rows ? p.prior_rows[w] : 0;

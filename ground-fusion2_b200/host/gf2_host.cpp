@@ -391,6 +391,8 @@ void Estimator::inputImage(double t, const uint8_t* _img, const uint16_t* _img1)
 void Estimator::clearState() {
   for (int i = 0; i <= WINDOW_SIZE; i++) { Rs[i] = Matrix3d(); Ps[i] = Vector3d(); Vs[i] = Vector3d(); Bas[i] = Vector3d(); Bgs[i] = Vector3d(); delete pre_integrations[i]; pre_integrations[i] = nullptr; }
   for (auto& p : pre_integrations_wheel) { delete p; p = nullptr; }
+  if (marg_pending && gf2) { int32_t st_ = 0, m_ = 0; gf2_marginalize_wait(gf2, 0, 1, &st_, &m_); }
+  marg_pending = false; prior_on_device = false; host_prior_current = true;
   f_manager.feature.clear(); last_marginalization_info = MarginalizationPrior(); failure_occur = false; openExEstimation = false;
   openExWheelEstimation = false; openIxEstimation = false;
 }
@@ -460,6 +462,7 @@ void Estimator::double2vector() {
 
 void Estimator::optimization() {
   last_error.clear();
+  if (marg_pending) { finishMarginalization(capture); if (!last_error.empty()) return; }
   vector2double();
   const int F = frame_count + 1;
   if (!gf2) {
@@ -552,7 +555,8 @@ void Estimator::optimization() {
     }
     if (capture) { cap.planes.assign(pl.begin(), pl.begin() + np); }
   }
-  if (rc == GF2_OK) {
+  if (rc == GF2_OK && capture && !host_prior_current) { finishMarginalization(true); if (!last_error.empty()) return; }
+  if (rc == GF2_OK && (!prior_on_device || capture)) {   // otherwise the prior the last marginalization left on the device is the current one
     const MarginalizationPrior& mp = last_marginalization_info;
     int32_t rows = (mp.valid ? mp.n : 0), nb = (int32_t)mp.blocks.size();
     std::vector<double> J0((size_t)GF2_MAX_PRIOR_DIM * GF2_MAX_PRIOR_DIM, 0.0), r0(GF2_MAX_PRIOR_DIM, 0.0);
@@ -561,6 +565,7 @@ void Estimator::optimization() {
     for (int b = 0; b < nb && b < (int)blocks.size(); b++) blocks[b] = mp.blocks[b];
     if (capture) { cap.prior_rows = rows; cap.prior_nblocks = rows > 0 ? nb : 0; cap.prior_J0 = J0; cap.prior_r0 = r0; cap.prior_blocks = blocks; }
     rc = gf2_set_prior(gf2, 0, 1, &rows, J0.data(), r0.data(), &nb, blocks.data());
+    if (rc == GF2_OK) prior_on_device = true;
   }
   if (rc == GF2_OK) {
     gf2_solve_opts o; memset(&o, 0, sizeof(o));
@@ -597,30 +602,47 @@ void Estimator::optimization() {
   if (capture) { memcpy(cap.pose_marg, para_Pose, sizeof(cap.pose_marg)); memcpy(cap.sb_marg, para_SpeedBias, sizeof(cap.sb_marg)); cap.invdep_marg.assign(invdep.begin(), invdep.begin() + n_lm); }
   rc = gf2_set_states(gf2, 0, 1, &para_Pose[0][0], &para_SpeedBias[0][0], para_Ex_Pose[0], para_Td[0], wheel_on ? para_Ex_Pose_wheel[0] : nullptr, wheel_on ? sxsysw : nullptr, wheel_on ? para_Td_wheel[0] : nullptr);
   if (rc == GF2_OK) rc = gf2_set_landmarks(gf2, 0, 1, &n_lm, invdep.data(), start.data(), len.data(), fixed.data(), obs.data(), frame_td.data());
-  int32_t st = 0, m = 0;
   gf2_solve_opts o; memset(&o, 0, sizeof(o));
   o.max_iterations = P.NUM_ITERATIONS; o.huber_delta = 1.0; o.sqrt_info_px = FOCAL_LENGTH / 1.5; o.g_norm = P.G_NORM; o.lidar_sqrt_info = 1.0;
   o.const_mask = GF2_CONST_EX_POSE | GF2_CONST_TD | GF2_CONST_EX_WHEEL | GF2_CONST_WHEEL_INTRINSIC | GF2_CONST_TD_WHEEL;
-  if (rc == GF2_OK) rc = gf2_marginalize(gf2, 0, 1, marginalization_flag == MARGIN_OLD ? GF2_MARGIN_OLD : GF2_MARGIN_SECOND_NEW, &o, &st, &m);
+  if (rc == GF2_OK) rc = gf2_marginalize_async(gf2, 0, 1, marginalization_flag == MARGIN_OLD ? GF2_MARGIN_OLD : GF2_MARGIN_SECOND_NEW, &o);
   if (rc != GF2_OK) { last_error = gf2_last_error(); return; }
-  last_marginalization_status = st;
-  if (st == GF2_MARG_INVALID) { last_marginalization_info = MarginalizationPrior(); }   // valid = false
-  else if (st == 0) {
+  // The new prior replaces the device-resident one in stream order and is only needed by the NEXT frame's solve: with
+  // async_marginalization the call returns here (the kernels run while the node waits for the next image) and the prior never crosses
+  // PCIe; the status is collected at the start of the next optimization() or by whoever asks for the prior (gf2h_get_prior, capture).
+  marg_pending = true; prior_on_device = true; host_prior_current = false;
+  if (capture || !async_marginalization) finishMarginalization(true);
+}
+
+// Collects the status of the pending gf2_marginalize_async and (optionally) downloads the new prior into last_marginalization_info.
+void Estimator::finishMarginalization(bool download) {
+  const int F = WINDOW_SIZE + 1;
+  if (marg_pending) {
+    int32_t st = 0, m = 0;
+    marg_pending = false;
+    if (gf2_marginalize_wait(gf2, 0, 1, &st, &m) != GF2_OK) { last_error = gf2_last_error(); return; }
+    last_marginalization_status = st;
+    if (st == GF2_MARG_INVALID) { last_marginalization_info = MarginalizationPrior(); host_prior_current = true; }   // valid = false (the device prior was cleared too)
+    else if (st == GF2_MARG_UNCHANGED) { /* the previous prior stays on both sides (block indices untouched, as at :3599) */ }
+    else if (st != 0) {
+      // DEGENERATE / UNSUPPORTED / TOO_LARGE have no counterpart in the reference (it always produces a prior). Keeping the old prior while
+      // slideWindow() shifts the frames would attach pose k's prior to the former frame k + 1: stop instead of corrupting the estimate.
+      last_error = "gf2_marginalize: window status " + std::to_string(st) + " (no prior produced); estimation stopped";
+      last_marginalization_info = MarginalizationPrior(); host_prior_current = true; prior_on_device = false;
+      return;
+    }
+  }
+  if (download && !host_prior_current && prior_on_device && gf2) {
     int32_t rows = 0, nb = 0;
     std::vector<double> J0((size_t)GF2_MAX_PRIOR_DIM * GF2_MAX_PRIOR_DIM), r0(GF2_MAX_PRIOR_DIM);
     std::vector<gf2_prior_block> blocks(2 * F + 8);
-    rc = gf2_get_prior(gf2, 0, 1, &rows, J0.data(), r0.data(), &nb, blocks.data());
-    if (rc != GF2_OK) { last_error = gf2_last_error(); return; }
+    if (gf2_get_prior(gf2, 0, 1, &rows, J0.data(), r0.data(), &nb, blocks.data()) != GF2_OK) { last_error = gf2_last_error(); return; }
     MarginalizationPrior& mp = last_marginalization_info;
-    mp.valid = true; mp.n = rows; mp.linearized_jacobians.resize((size_t)rows * rows); mp.linearized_residuals.assign(r0.begin(), r0.begin() + rows);
+    mp.valid = rows > 0; mp.n = rows; mp.linearized_jacobians.resize((size_t)rows * rows); mp.linearized_residuals.assign(r0.begin(), r0.begin() + rows);
     for (int r = 0; r < rows; r++) for (int c = 0; c < rows; c++) mp.linearized_jacobians[(size_t)r * rows + c] = J0[(size_t)r * GF2_MAX_PRIOR_DIM + c];
-    mp.blocks.assign(blocks.begin(), blocks.begin() + nb);
-  } else if (st != GF2_MARG_UNCHANGED) {
-    // DEGENERATE / UNSUPPORTED / TOO_LARGE have no counterpart in the reference (it always produces a prior). Keeping the old prior while
-    // slideWindow() shifts the frames would attach pose k's prior to the former frame k + 1: stop instead of corrupting the estimate.
-    last_error = "gf2_marginalize: window status " + std::to_string(st) + " (no prior produced); estimation stopped";
-    last_marginalization_info = MarginalizationPrior();
-  }  // GF2_MARG_UNCHANGED: the previous prior stays (block indices untouched, as at :3599)
+    mp.blocks.assign(blocks.begin(), blocks.begin() + (rows > 0 ? nb : 0));
+    host_prior_current = true;
+  }
 }
 
 // ---- measurement queues (estimator.cpp:324-372, 422-545, 554-763) ---------------------------------------------------------------------
@@ -1265,7 +1287,9 @@ int gf2h_process_image(void* e, int n, const int* ids, const double* pts8, doubl
   return E->lastError()[0] ? -1 : (E->marginalization_flag == Estimator::MARGIN_OLD ? 0 : 1);
 }
 void gf2h_set_prior(void* e, int n, const double* J0, const double* r0, int nblocks, const gf2_prior_block* blocks) {
-  MarginalizationPrior& mp = ((Estimator*)e)->last_marginalization_info;
+  Estimator* E_ = (Estimator*)e; if (E_->marg_pending) E_->finishMarginalization(false);
+  E_->prior_on_device = false; E_->host_prior_current = true;   // the host copy is the truth now: uploaded by the next optimization()
+  MarginalizationPrior& mp = E_->last_marginalization_info;
   mp.valid = n > 0; mp.n = n; mp.linearized_jacobians.assign(J0, J0 + (size_t)n * n); mp.linearized_residuals.assign(r0, r0 + n); mp.blocks.assign(blocks, blocks + nblocks);
 }
 void gf2h_vector2double(void* e, double* pose /*11x7*/, double* sb /*11x9*/, double* ex /*7*/) {
@@ -1276,9 +1300,13 @@ void gf2h_double2vector(void* e, const double* pose, const double* sb, int n_fea
   for (int i = 0; i < n_feat; i++) E->para_Feature[i][0] = feat[i];
   E->double2vector();
 }
+// Blocks until the marginalization launched by the last processImage() is done (what the inter-frame gap of a live stream provides).
+int gf2h_finish_marginalization(void* e) { Estimator* E = (Estimator*)e; E->finishMarginalization(false); return E->lastError()[0] ? -1 : 0; }
+void gf2h_set_async_marginalization(void* e, int on) { ((Estimator*)e)->async_marginalization = on != 0; }
 void gf2h_set_marginalization_flag(void* e, int flag) { ((Estimator*)e)->marginalization_flag = flag ? Estimator::MARGIN_SECOND_NEW : Estimator::MARGIN_OLD; }
 int gf2h_get_prior(void* e, int* n, double* J0 /* n*n */, double* r0, int* nblocks, gf2_prior_block* blocks, int* status) {
-  Estimator* E = (Estimator*)e; const MarginalizationPrior& mp = E->last_marginalization_info;
+  Estimator* E = (Estimator*)e; E->finishMarginalization(true);   // collects a pending marginalization and fetches the device-resident prior
+  const MarginalizationPrior& mp = E->last_marginalization_info;
   *n = mp.valid ? mp.n : 0; *nblocks = (int)mp.blocks.size(); *status = E->last_marginalization_status;
   for (size_t i = 0; i < mp.linearized_jacobians.size(); i++) J0[i] = mp.linearized_jacobians[i];
   for (size_t i = 0; i < mp.linearized_residuals.size(); i++) r0[i] = mp.linearized_residuals[i];

@@ -240,6 +240,11 @@ class Estimator {
   enum MarginalizationFlag { MARGIN_OLD = 0, MARGIN_SECOND_NEW = 1 };  // estimator.h:60-64
   MarginalizationFlag marginalization_flag = MARGIN_OLD;
   int last_marginalization_status = 0;   // gf2_marginalize status of the last optimization()
+  // The prior lives on the device between frames: optimization() launches the marginalization asynchronously (gf2_marginalize_async) and
+  // returns after the solve; the status is collected by the next optimization() (or by gf2h_get_prior / the capture hook, which also
+  // download the prior into last_marginalization_info). async_marginalization = false restores the blocking behaviour.
+  bool async_marginalization = true, marg_pending = false, prior_on_device = false, host_prior_current = true;
+  void finishMarginalization(bool download);
   const char* lastError() const { return last_error.c_str(); }
 
   Parameters P;

@@ -301,6 +301,12 @@ enum { GF2_MARGIN_OLD = 0, GF2_MARGIN_SECOND_NEW = 1 };
 enum { GF2_MARG_INVALID = -1, GF2_MARG_UNCHANGED = -2, GF2_MARG_UNSUPPORTED = -3, GF2_MARG_DEGENERATE = -4, GF2_MARG_TOO_LARGE = -5 };
 int gf2_marginalize(gf2_solver* h, int first, int n, int32_t mode, const gf2_solve_opts* opts, int32_t* status,
                     int32_t* m_dims);
+/* The same in two halves, for callers that do not need the new prior before the next frame (one robot: the reference's node spends the
+ * time until the next image idle): gf2_marginalize_async launches the kernels on the handle's stream and returns; the new prior replaces
+ * the resident one in stream order, so a following gf2_solve already sees it. gf2_marginalize_wait blocks until those kernels are done and
+ * returns their status / m_dims (semantics as above). gf2_marginalize == async + wait. */
+int gf2_marginalize_async(gf2_solver* h, int first, int n, int32_t mode, const gf2_solve_opts* opts);
+int gf2_marginalize_wait(gf2_solver* h, int first, int n, int32_t* status, int32_t* m_dims);
 /* The resident prior (same layout as gf2_set_prior). */
 int gf2_get_prior(gf2_solver* h, int first, int n, int32_t* n_rows, double* J0, double* r0, int32_t* n_blocks,
                   gf2_prior_block* blocks);
