@@ -603,7 +603,7 @@ int gf2_set_plane_alpha(gf2_solver* h, int first, int n, const double* alpha) {
 
 static int fill_kp(gf2_solver* h, const gf2_solve_opts* o, KP& k) {
   if (!o) return gf2::fail(GF2_ERR_INVALID, "null options");
-  if (o->max_time_s != 0.0) return gf2::fail(GF2_ERR_INVALID, "max_time_s must be 0: the wall-clock cap is not reproduced");
+  if (!(o->max_time_s >= 0.0)) return gf2::fail(GF2_ERR_INVALID, "max_time_s must be >= 0 (0: no wall-clock cap)");
   if (o->initial_radius > 0 && o->initial_radius != 1e4) return gf2::fail(GF2_ERR_UNSUPPORTED, "initial_radius other than the Ceres default 1e4");
   if (o->max_iterations < 0 || o->max_iterations > 64) return gf2::fail(GF2_ERR_INVALID, "max_iterations %d out of range [0, 64]", o->max_iterations);
   const uint32_t need = GF2_CONST_EX_POSE | GF2_CONST_TD;
@@ -619,6 +619,7 @@ static int fill_kp(gf2_solver* h, const gf2_solve_opts* o, KP& k) {
   k.gtol = o->gradient_tolerance > 0 ? o->gradient_tolerance : 1e-10;
   k.ptol = o->parameter_tolerance > 0 ? o->parameter_tolerance : 1e-8;
   k.max_iterations = o->max_iterations;
+  k.max_time_ns = o->max_time_s > 0.0 ? (unsigned long long)(o->max_time_s * 1e9 + 0.5) : 0ull;
   k.imu = h->has_imu ? h->d_imu : nullptr;
   k.wheel = (h->cfg.use_wheel && h->has_wheel) ? h->d_wheel : nullptr;
   if (!h->has_prior) { k.prior_rows = nullptr; }

@@ -42,6 +42,7 @@ struct WinState {  // per-window trust-region state (DoglegStrategy + TrustRegio
   double uSz, zSz;                  // u^T S' z and z^T S' z through the Cholesky factor (k_solve2)
   double cost_vis;                  // from k_linearize
   int32_t iteration, successful, termination, active, reuse, invalid_count, lin_valid, pad_;
+  unsigned long long t_start_ns;    // %globaltimer at k_prepare: the solve's clock for max_solver_time_in_seconds
 };
 
 struct KP {  // kernel parameters (device pointers are window-major with the strides below)
@@ -55,6 +56,7 @@ struct KP {  // kernel parameters (device pointers are window-major with the str
   double huber, sqrt_info_px, g_norm, lidar_sqrt_info;
   double ftol, gtol, ptol;
   int max_iterations;
+  unsigned long long max_time_ns;   // ceres::Solver::Options::max_solver_time_in_seconds (0: no cap)
   // states (current / candidate)
   double *pose, *sb, *ex, *td, *exw, *sxw, *tdw, *invdep;
   double *pose_c, *sb_c, *invdep_c;
@@ -332,6 +334,8 @@ __global__ void k_prepare(KP p, int w0) {
     s.radius = 1e4; s.mu = 1e-8; s.x_cost = 0; s.cand_cost = 0; s.model_cost_change = 0; s.dogleg_step_norm = 0;
     s.iteration = 0; s.successful = 0; s.termination = GF2_TERM_NO_CONVERGENCE; s.active = 1; s.reuse = 0; s.invalid_count = 0; s.lin_valid = 0;
     s.initial_cost = 0; s.coef_a = 0; s.coef_b = 0; s.x_norm2 = 0;
+    unsigned long long now; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+    s.t_start_ns = now;
   }
 }
 

@@ -663,7 +663,13 @@ __global__ void __launch_bounds__(256) k_decide(KP p, int w0) {
       }
     }
     if (st.active) {
+      // TrustRegionMinimizer checks the iteration budget and then the wall clock after every iteration (MaxSolverTimeReached: "Maximum solver
+      // time reached", NO_CONVERGENCE). The clock is the device's %globaltimer since k_prepare of this solve: like the reference's, the number
+      // of iterations a capped solve runs depends on the machine.
+      unsigned long long now = 0;
+      if (p.max_time_ns) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
       if (st.iteration >= p.max_iterations) { st.active = 0; st.termination = GF2_TERM_NO_CONVERGENCE; }
+      else if (p.max_time_ns && now - st.t_start_ns >= p.max_time_ns) { st.active = 0; st.termination = GF2_TERM_NO_CONVERGENCE; }
       else if (st.radius <= 1e-32) { st.active = 0; st.termination = GF2_TERM_MIN_RADIUS; }
     }
     s_decision = decision;

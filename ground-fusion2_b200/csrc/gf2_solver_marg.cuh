@@ -364,8 +364,11 @@ __global__ void __launch_bounds__(kMargThreads) k_marg_build(KP p, int w0, MargP
         // landmark row: v, g_l, w over the touched columns, scaled by 1/sqrt(v)
         const double v = warp_sum(Jl[0] * Jl[0] + Jl[1] * Jl[1]);
         const double gl = warp_sum(Jl[0] * r[0] + Jl[1] * r[1]);
+        // v <= eps: the landmark's eigenvalue of Amm is truncated by the reference's pseudo-inverse (marginalization_factor.cpp:278-283).
+        // Its coupling to the frame block is bounded by |B_l|^2 <= v C_jj <= 1e-8 C_jj (Amm is positive semi-definite), so the landmark is an
+        // (almost) decoupled null direction: truncating it == not subtracting its Schur term; its factors' direct J^T J terms stay, as
+        // in the reference. (A robot turning on the spot gives exactly this: zero baseline, d r / d lambda = 0.)
         const bool okv = v > kMargEps;
-        if (!okv && lane == 0) s.bad = 2;
         const double isv = okv ? rsqrt(v) : 0.0;
         double q6[6];
 #pragma unroll

@@ -580,7 +580,9 @@ void Estimator::optimization() {
     if ((wheel_on && P.ESTIMATE_EXTRINSIC_WHEEL && frame_count == WINDOW_SIZE && v0 > 0.2) || openExWheelEstimation) openExWheelEstimation = true; else o.const_mask |= GF2_CONST_EX_WHEEL;
     if ((wheel_on && P.ESTIMATE_INTRINSIC_WHEEL && frame_count == WINDOW_SIZE && v0 > 0.2) || openIxEstimation) openIxEstimation = true; else o.const_mask |= GF2_CONST_WHEEL_INTRINSIC;
     if (!P.ESTIMATE_TD_WHEEL || v0 < 0.2) o.const_mask |= GF2_CONST_TD_WHEEL;
-    o.max_time_s = 0;  // SOLVER_TIME is a wall-clock cap: machine dependent, not reproduced
+    // options.max_solver_time_in_seconds = SOLVER_TIME (estimator.cpp:3373-3376; 0.04 s in the shipped configs): honoured on the device's clock.
+    // The parity-test hook (capture) runs without the cap: a capped solve is machine dependent by construction.
+    o.max_time_s = capture ? 0.0 : (marginalization_flag == MARGIN_OLD ? P.SOLVER_TIME * 4.0 / 5.0 : P.SOLVER_TIME);
     if (capture) {
       cap.const_mask = o.const_mask; cap.marg_mode = marginalization_flag == MARGIN_OLD ? 0 : 1; cap.use_wheel = wheel_on ? 1 : 0;
       memcpy(cap.exw, para_Ex_Pose_wheel[0], sizeof(cap.exw)); memcpy(cap.sxsysw, sxsysw, sizeof(cap.sxsysw)); cap.tdw = para_Td_wheel[0][0];

@@ -186,7 +186,8 @@ typedef struct gf2_solve_opts {
   double sqrt_info_px;     /* ProjectionTwoFrameOneCamFactor::sqrt_info = FOCAL_LENGTH/1.5 * I (estimator.cpp:193) */
   double g_norm;           /* G = (0,0,g_norm), parameters.cpp:223 */
   double lidar_sqrt_info;  /* LidarPlaneNormFactor::sqrt_info = sqrt(1/laser_point_cov) (lidarodom.cpp:10,13) */
-  double max_time_s;       /* must be 0: the wall-clock cap is machine dependent and is NOT reproduced */
+  double max_time_s;       /* options.max_solver_time_in_seconds (estimator.cpp:3373-3376): 0 = no cap; > 0: checked after every iteration against the
+                            * device clock since the start of the solve (termination NO_CONVERGENCE). Machine dependent, like the reference's. */
   /* Ceres 1.14 trust-region defaults; 0 selects the default */
   double initial_radius;       /* 1e4 */
   double function_tolerance;   /* 1e-6 */
@@ -294,8 +295,10 @@ int gf2_set_prior(gf2_solver* h, int first, int n, const int32_t* n_rows, const 
  * slideWindow the caller uploads the new states / landmarks and solves. status [n] (may be NULL):
  *   0 ok; GF2_MARG_INVALID: m == 0, prior cleared (valid = false, :205-210); GF2_MARG_UNCHANGED: SECOND_NEW without the
  *   second-newest pose in the old prior (estimator.cpp:3599), old prior kept; GF2_MARG_UNSUPPORTED: the old prior holds a
- *   block this build cannot keep; GF2_MARG_DEGENERATE: an eigenvalue of Amm is below eps = 1e-8 (the truncated
- *   pseudo-inverse of :281 would differ from the inverse), old prior kept; GF2_MARG_TOO_LARGE: n > max_prior_rows.
+ *   block this build cannot keep; GF2_MARG_DEGENERATE: the dropped FRAME block (pose 0 + speed-bias 0, 15 x 15 after the landmarks) has an
+ *   eigenvalue below eps = 1e-8, where the truncated pseudo-inverse of :281 differs from the inverse (landmarks whose own eigenvalue is
+ *   below eps — zero baseline, e.g. a robot turning on the spot — are truncated as the reference's pseudo-inverse truncates them and
+ *   do NOT raise this), old prior kept; GF2_MARG_TOO_LARGE: n > max_prior_rows.
  * m_dims [n] (may be NULL): the number of marginalized tangent dimensions m. */
 enum { GF2_MARGIN_OLD = 0, GF2_MARGIN_SECOND_NEW = 1 };
 enum { GF2_MARG_INVALID = -1, GF2_MARG_UNCHANGED = -2, GF2_MARG_UNSUPPORTED = -3, GF2_MARG_DEGENERATE = -4, GF2_MARG_TOO_LARGE = -5 };

@@ -204,3 +204,26 @@ def test_margin_old_edge_cases(gf2, oracle, synth):
     for i in range(n):
         assert oracle.marginalize_window(w, i, opts, mode=0)["status"] == -1
     s.close()
+
+
+def test_margin_old_truncates_uninformative_landmarks_like_the_pseudo_inverse(gf2, oracle, synth):
+    """A robot turning on the spot: zero baseline, d r / d lambda = 0 for every landmark, so their eigenvalues of Amm are below eps = 1e-8 and
+    MarginalizationInfo::marginalize() truncates them in its pseudo-inverse (marginalization_factor.cpp:278-283). The device drops exactly
+    those landmarks' Schur terms (status 0, not GF2_MARG_DEGENERATE) and must agree with the restated eigen-decomposition pseudo-inverse.
+    Window 1 is left untouched (informative landmarks) as the control."""
+    n = 2
+    w = synth.make_windows(n, n_landmarks=160, prior="anchor")
+    oracle.imu_preintegrate(w)
+    w["para_pose"][0, :, :3] = w["para_pose"][0, 0, :3]   # all camera centres coincide: no translation between the frames ...
+    w["ex_pose"][0, :3] = 0.0                             # ... and no lever arm
+    opts = gf2.abi.default_opts()
+    s = gf2.Solver(n, w["n_frames"], w["max_landmarks"], w["max_obs"])
+    s.upload(w, preintegrate="records")
+    status, m = s.marginalize(opts, mode=0)
+    assert (status == 0).all(), status
+    got = s.get_prior(n)
+    for i in range(n):
+        ref = oracle.marginalize_window(w, i, opts, mode=0)
+        assert ref["status"] == 0 and ref["m"] == m[i]
+        _check_prior(oracle, _prior_of(got, i), ref, w["n_frames"])
+    s.close()

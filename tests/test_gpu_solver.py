@@ -183,15 +183,41 @@ def test_edge_cases(gf2, oracle, synth):
     s.close()
 
 
+def test_max_solver_time_caps_the_iterations(gf2, synth):
+    """options.max_solver_time_in_seconds (estimator.cpp:3373-3376): checked after every iteration on the device clock. A cap far above the
+    solve's duration changes nothing; a cap of one nanosecond stops every window after its first iteration (NO_CONVERGENCE), with the
+    states of that first step applied."""
+    n = 4
+    w = synth.make_windows(n, n_landmarks=200)
+    s = _solver(gf2, w, n)
+    s.upload(w, preintegrate="device"); s.snapshot(n)
+    ref = s.solve(gf2.abi.default_opts(), n).copy(); st_ref = s.get_states(n)
+    o = gf2.abi.default_opts(); o.max_time_s = 10.0
+    s.restore(n); got = s.solve(o, n)
+    assert np.array_equal(got["iterations"], ref["iterations"]) and np.array_equal(got["final_cost"], ref["final_cost"])
+    assert np.array_equal(s.get_states(n)["para_pose"], st_ref["para_pose"])
+    o.max_time_s = 1e-9
+    s.restore(n); capped = s.solve(o, n)
+    assert (capped["iterations"] == 1).all() and (capped["termination"] == 0).all()  # GF2_TERM_NO_CONVERGENCE
+    assert (capped["final_cost"] < capped["initial_cost"]).all() and (capped["final_cost"] > ref["final_cost"]).all()
+    one = gf2.abi.default_opts(max_iterations=1)
+    s.restore(n); first = s.solve(one, n)
+    assert np.array_equal(first["final_cost"], capped["final_cost"])
+    s.close()
+
+
 def test_bad_arguments_are_rejected(gf2, synth):
     w = synth.make_windows(1, n_landmarks=20)
     s = _solver(gf2, w, 1)
     bad = _copy(w); bad["start_frame"][0, 0] = 9; bad["track_len"][0, 0] = 5
     with pytest.raises(gf2.Gf2Error, match="outside"):
         s.set_landmarks(bad)
-    o = gf2.abi.default_opts(); o.max_time_s = 0.04
+    o = gf2.abi.default_opts(); o.max_time_s = -1.0
     s.upload(w, preintegrate="device")
     with pytest.raises(gf2.Gf2Error, match="max_time_s"):
+        s.solve(o, 1)
+    o = gf2.abi.default_opts(); o.initial_radius = 10.0
+    with pytest.raises(gf2.Gf2Error, match="initial_radius"):
         s.solve(o, 1)
     with pytest.raises(gf2.Gf2Error, match="capacity"):
         s.solve(gf2.abi.default_opts(), 2)
