@@ -3,9 +3,17 @@
 //
 //   k_pyrdown   cv::pyrDown for 8-bit images (5x5 [1 4 6 4 1], BORDER_REFLECT_101, (sum + 128) >> 8)
 //   k_scharr    un-normalised 3x3 Scharr derivatives of the template pyramid, int16 (dx, dy) interleaved
-//   k_lk        one warp per point: all pyramid levels coarse -> fine in one launch; the 21x21 template (I, Ix, Iy) lives in
-//               registers (14 pixels per lane), window sums are exact int64 warp reductions, the 2x2 solve is float32 with
-//               the operation order of OpenCV's lkpyramid.cpp (no FMA contraction)
+//   k_lk        one warp per point: all pyramid levels coarse -> fine in one launch. Per level the warp stages three tiles in shared memory
+//               with bulk asynchronous copies (cp.async.bulk global -> shared, completion on the warp's mbarrier; SASS UBLKCP; every lane
+//               issues the 16-byte aligned row it owns): the 22-row footprint of the template in I, its Scharr derivatives, and a
+//               32-row search tile of J around the starting position (the window may move 5 px in every direction before the
+//               iteration leaves the tile). The template (I, Ix, Iy) then lives in registers (14 pixels per lane) and every iteration
+//               samples J out of the shared tile. Windows that overhang the image border (BORDER_REFLECT_101 / zero derivatives),
+//               iterations that leave the tile, and pyramid levels whose row pitch is not a multiple of 16 bytes take the direct global
+//               gather of the same arithmetic. (2-D tensor-map copies, cp.async.bulk.tensor, raise "illegal instruction" on this pool's
+//               boxes even from the CUDA programming guide's own sample — scripts/dbg/tma_probe*.cu — so the tiles are moved row by row.)
+//               Window sums are exact int64 warp reductions, the 2x2 solve is float32 with the operation order of OpenCV's
+//               lkpyramid.cpp (no FMA contraction)
 //   k_gftt_*    cv::goodFeaturesToTrack (feature_tracker.cpp:198): Sobel -> covariance planes -> 3x3 box sums with cv's running
 //               double column sum -> min eigenvalue (bit-exact with cv2.cornerMinEigenVal), masked maximum, threshold + 3x3
 //               non-maximum suppression -> candidate keys; the greedy min-distance selection runs on the host inside the
@@ -94,33 +102,108 @@ struct LkArgs {
   Pyr I, J;                   // template (prev) and search (next) pyramids, stream 0 base pointers
 };
 
-constexpr int kPix = 14;  // ceil(441 / 32)
+// Shared memory of a warp: the search tile of J (rows copied from the 16-byte aligned address at or below the wanted first pixel, so a row
+// holds up to 15 leading bytes of slack) and the template record of every window pixel.
+constexpr int kTileMargin = 5;                   // the search tile of J covers the 22 x 22 footprint moved by up to 5 px each way
+constexpr int kTileRows = 32, kTilePitch = 48;   // 32 = 21 + 1 + 2 * 5 pixels wanted per row, + 15 of slack, rounded to 48 bytes
+constexpr int kLkWarps = 4;
+constexpr int kPix = 14;                         // ceil(441 / 32) window pixels per lane
+struct __align__(128) LkWarpShared {
+  uint8_t J[kTileRows * kTilePitch];
+  short4 tmpl[32 * kPix];                        // per window pixel: I (x32), Ix, Iy, packed offset (oy << 8 | ox)
+};
 
-// Bilinear sample of a u8 image in the 5-extra-bit fixed point of cv::calcOpticalFlowPyrLK (CV_DESCALE(.., W_BITS1 - 5)).
-// `inside` is uniform over the warp: the window and its +1 neighbours lie in the image, so no BORDER_REFLECT_101 folding.
-__device__ __forceinline__ int lk_sample_u8(const uint8_t* __restrict__ im, int cols, int rows, int y, int x, bool inside, int w00, int w01, int w10, int w11) {
-  int a, b, c, d;
-  if (inside) { const uint8_t* q = im + y * cols + x; a = q[0]; b = q[1]; c = q[cols]; d = q[cols + 1]; }
-  else {
-    const int y0 = reflect101(y, rows), y1 = reflect101(y + 1, rows), x0 = reflect101(x, cols), x1 = reflect101(x + 1, cols);
-    a = im[(size_t)y0 * cols + x0]; b = im[(size_t)y0 * cols + x1]; c = im[(size_t)y1 * cols + x0]; d = im[(size_t)y1 * cols + x1];
-  }
+__device__ __forceinline__ uint32_t lk_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void lk_bulk_row(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(lk_smem_u32(dst)), "l"(src), "r"(bytes), "r"(lk_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void lk_mbar_expect(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(lk_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void lk_mbar_wait(unsigned long long* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(lk_smem_u32(bar)), "r"(parity) : "memory");
+}
+// Fixed-point bilinear sample (CV_DESCALE(.., W_BITS1 - 5)) of a u8 image: interior (four neighbouring bytes at `q`, row pitch `pitch`) and
+// the BORDER_REFLECT_101 version for windows that overhang the image (rare: kept out of line so that the hot loops stay small — the fully
+// inlined kernel was 11 k instructions and spent most of its time waiting for instruction fetches).
+__device__ __forceinline__ int lk_sample4(const uint8_t* __restrict__ q, int pitch, int w00, int w01, int w10, int w11) {
+  return ((int)q[0] * w00 + (int)q[1] * w01 + (int)q[pitch] * w10 + (int)q[pitch + 1] * w11 + (1 << (kWBits - 5 - 1))) >> (kWBits - 5);
+}
+__device__ __noinline__ int lk_sample_border(const uint8_t* __restrict__ im, int cols, int rows, int y, int x, int w00, int w01, int w10, int w11) {
+  const int y0 = reflect101(y, rows), y1 = reflect101(y + 1, rows), x0 = reflect101(x, cols), x1 = reflect101(x + 1, cols);
+  const int a = im[(size_t)y0 * cols + x0], b = im[(size_t)y0 * cols + x1], c = im[(size_t)y1 * cols + x0], d = im[(size_t)y1 * cols + x1];
   return (a * w00 + b * w01 + c * w10 + d * w11 + (1 << (kWBits - 5 - 1))) >> (kWBits - 5);
 }
+// derivative sample with the zero border of OpenCV's derivative buffer (BORDER_CONSTANT)
+__device__ __noinline__ void lk_deriv_border(const short2* __restrict__ dI, int cols, int rows, int y, int x, int w00, int w01, int w10, int w11, int& ix, int& iy) {
+  const bool yi0 = y >= 0 && y < rows, yi1 = y + 1 >= 0 && y + 1 < rows, xi0 = x >= 0 && x < cols, xi1 = x + 1 >= 0 && x + 1 < cols;
+  const short2 z = make_short2(0, 0);
+  const short2 d00 = (yi0 && xi0) ? dI[(size_t)y * cols + x] : z, d01 = (yi0 && xi1) ? dI[(size_t)y * cols + x + 1] : z;
+  const short2 d10 = (yi1 && xi0) ? dI[(size_t)(y + 1) * cols + x] : z, d11 = (yi1 && xi1) ? dI[(size_t)(y + 1) * cols + x + 1] : z;
+  ix = (d00.x * w00 + d01.x * w01 + d10.x * w10 + d11.x * w11 + (1 << (kWBits - 1))) >> kWBits;
+  iy = (d00.y * w00 + d01.y * w01 + d10.y * w10 + d11.y * w11 + (1 << (kWBits - 1))) >> kWBits;
+}
 
-__global__ void __launch_bounds__(128) k_lk(LkArgs a) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+// sum over the window of (J(q + .) - I) * (Ix, Iy) [mode 0] or |J(q + .) - I| [mode 1] at the window origin (inx, iny) of J
+template <int MODE>
+__device__ __forceinline__ void lk_window_sums(const LkWarpShared& W, const uint8_t* __restrict__ J, int cols, int rows, int win, int npx, int lane,
+                                               int inx, int iny, int v00, int v01, int v10, int v11, bool tJ, int jx0, int jy0, int sjx, int& q1, int& q2) {
+  q1 = 0; q2 = 0;
+  const int tx = inx - jx0, ty = iny - jy0;
+  if (tJ && tx >= 0 && ty >= 0 && tx <= 2 * kTileMargin && ty <= 2 * kTileMargin) {   // the window lies inside the staged tile
+    const uint8_t* tb = &W.J[ty * kTilePitch + sjx + tx];
+#pragma unroll 2
+    for (int m = 0; m < kPix; m++) {
+      const int idx = lane + 32 * m;
+      if (idx < npx) {
+        const short4 t = W.tmpl[idx];
+        const int diff = lk_sample4(tb + (t.w >> 8) * kTilePitch + (t.w & 0xff), kTilePitch, v00, v01, v10, v11) - t.x;
+        if (MODE == 0) { q1 += diff * t.y; q2 += diff * t.z; } else q1 += abs(diff);
+      }
+    }
+  } else {
+    const bool in_j = inx >= 0 && iny >= 0 && inx + win < cols && iny + win < rows;
+#pragma unroll 2
+    for (int m = 0; m < kPix; m++) {
+      const int idx = lane + 32 * m;
+      if (idx < npx) {
+        const short4 t = W.tmpl[idx];
+        const int y = iny + (t.w >> 8), x = inx + (t.w & 0xff);
+        const int diff = (in_j ? lk_sample4(J + (size_t)y * cols + x, cols, v00, v01, v10, v11) : lk_sample_border(J, cols, rows, y, x, v00, v01, v10, v11)) - t.x;
+        if (MODE == 0) { q1 += diff * t.y; q2 += diff * t.z; } else q1 += abs(diff);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(32 * kLkWarps) k_lk(const __grid_constant__ LkArgs a) {
+  __shared__ LkWarpShared wsh[kLkWarps];
+  __shared__ unsigned long long bars[kLkWarps];
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int s = warp / a.max_pts, i = warp % a.max_pts;
   if (s >= a.n_streams || i >= a.n_pts[s]) return;
   if (a.gate && !a.gate[s]) return;
+  LkWarpShared& W = wsh[wib];
+  unsigned long long* bar = &bars[wib];
+  if (lane == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(lk_smem_u32(bar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   const int win = a.win, npx = win * win;
+  for (int m = 0; m < kPix; m++) { const int idx = lane + 32 * m; const int oy = idx / win; W.tmpl[idx].w = (short)((oy << 8) | (idx - oy * win)); }
+  __syncwarp();
+  uint32_t phase = 0;
   const float half = (win - 1) * 0.5f;
   const float2 pp = reinterpret_cast<const float2*>(a.prev_pts)[(size_t)s * a.max_pts + i];
   float2 np = reinterpret_cast<float2*>(a.next_pts)[(size_t)s * a.max_pts + i];
   bool ok = true; float errv = 0.f;
-  int oy[kPix], ox[kPix];   // window pixel of (lane, m): the divisions by the runtime window size are done once
-#pragma unroll
-  for (int m = 0; m < kPix; m++) { const int idx = lane + 32 * m; oy[m] = idx / win; ox[m] = idx - oy[m] * win; }
+  const bool tile_geom = win + 1 + 2 * kTileMargin <= kTileRows;
   for (int level = a.max_level; level >= 0; level--) {
     const int cols = a.I.w[level], rows = a.I.h[level];
     const uint8_t* I = a.I.img[level] + (size_t)s * a.img_stride[level];
@@ -137,31 +220,42 @@ __global__ void __launch_bounds__(128) k_lk(LkArgs a) {
     const int ipx = (int)floorf(px), ipy = (int)floorf(py);
     if (ipx < -win || ipx >= cols || ipy < -win || ipy >= rows) { if (level == 0) { ok = false; errv = 0.f; } continue; }
     int w00, w01, w10, w11; lk_weights(px, py, ipx, ipy, w00, w01, w10, w11);
-    // template patch: intensity (x32), Ix, Iy as int16-range ints, kPix pixels per lane
-    int Iv[kPix], Ix[kPix], Iy[kPix];
-    // per-lane partial sums fit 32 bits: |Ix|, |Iy| <= 16 * 255 (Scharr), |J - I| <= 255 * 32, 14 pixels per lane
+    // ---- the search tile of J: lane r copies row r (16-byte aligned start), in flight while the template is extracted
+    const int jx0 = (int)floorf(__fsub_rn(nx, half)) - kTileMargin, jy0 = (int)floorf(__fsub_rn(ny, half)) - kTileMargin;
+    const int ajx = jx0 & ~15, sjx = jx0 - ajx;
+    const bool tJ = tile_geom && (cols & 15) == 0 && jx0 >= 0 && jy0 >= 0 && ajx + kTilePitch <= cols && jy0 + kTileRows <= rows;
+    __syncwarp();                                                 // every lane is done with the previous level's tile and template
+    if (tJ) {
+      if (lane == 0) lk_mbar_expect(bar, (uint32_t)(kTileRows * kTilePitch));
+      __syncwarp();
+      lk_bulk_row(&W.J[lane * kTilePitch], J + (size_t)(jy0 + lane) * cols + ajx, kTilePitch, bar);
+    }
+    // ---- template: intensity (x32), Ix, Iy as int16 per window pixel -> shared; per-lane partial sums fit 32 bits
+    //      (|Ix|, |Iy| <= 16 * 255 (Scharr), |J - I| <= 255 * 32, 14 pixels per lane)
     int p11 = 0, p12 = 0, p22 = 0;
     const bool in_t = ipx >= 0 && ipy >= 0 && ipx + win < cols && ipy + win < rows;
-#pragma unroll
+#pragma unroll 2
     for (int m = 0; m < kPix; m++) {
       const int idx = lane + 32 * m;
-      Iv[m] = 0; Ix[m] = 0; Iy[m] = 0;
       if (idx < npx) {
-        const int y = ipy + oy[m], x = ipx + ox[m];
-        Iv[m] = lk_sample_u8(I, cols, rows, y, x, in_t, w00, w01, w10, w11);
-        short2 d00, d01, d10, d11;
-        if (in_t) { const short2* q = dI + y * cols + x; d00 = q[0]; d01 = q[1]; d10 = q[cols]; d11 = q[cols + 1]; }
-        else {  // derivative buffers are zero outside the image (BORDER_CONSTANT)
-          const bool yi0 = y >= 0 && y < rows, yi1 = y + 1 >= 0 && y + 1 < rows, xi0 = x >= 0 && x < cols, xi1 = x + 1 >= 0 && x + 1 < cols;
-          const short2 z = make_short2(0, 0);
-          d00 = (yi0 && xi0) ? dI[(size_t)y * cols + x] : z; d01 = (yi0 && xi1) ? dI[(size_t)y * cols + x + 1] : z;
-          d10 = (yi1 && xi0) ? dI[(size_t)(y + 1) * cols + x] : z; d11 = (yi1 && xi1) ? dI[(size_t)(y + 1) * cols + x + 1] : z;
+        const int pk = W.tmpl[idx].w, y = ipy + (pk >> 8), x = ipx + (pk & 0xff);
+        int iv, ix, iy;
+        if (in_t) {
+          iv = lk_sample4(I + (size_t)y * cols + x, cols, w00, w01, w10, w11);
+          const short2* q = dI + (size_t)y * cols + x;
+          const short2 d00 = q[0], d01 = q[1], d10 = q[cols], d11 = q[cols + 1];
+          ix = (d00.x * w00 + d01.x * w01 + d10.x * w10 + d11.x * w11 + (1 << (kWBits - 1))) >> kWBits;
+          iy = (d00.y * w00 + d01.y * w01 + d10.y * w10 + d11.y * w11 + (1 << (kWBits - 1))) >> kWBits;
+        } else {
+          iv = lk_sample_border(I, cols, rows, y, x, w00, w01, w10, w11);
+          lk_deriv_border(dI, cols, rows, y, x, w00, w01, w10, w11, ix, iy);
         }
-        Ix[m] = (d00.x * w00 + d01.x * w01 + d10.x * w10 + d11.x * w11 + (1 << (kWBits - 1))) >> kWBits;
-        Iy[m] = (d00.y * w00 + d01.y * w01 + d10.y * w10 + d11.y * w11 + (1 << (kWBits - 1))) >> kWBits;
-        p11 += Ix[m] * Ix[m]; p12 += Ix[m] * Iy[m]; p22 += Iy[m] * Iy[m];
+        W.tmpl[idx] = make_short4((short)iv, (short)ix, (short)iy, (short)pk);
+        p11 += ix * ix; p12 += ix * iy; p22 += iy * iy;
       }
     }
+    if (tJ) { lk_mbar_wait(bar, phase); phase ^= 1u; }
+    __syncwarp();
     long long s11 = p11, s12 = p12, s22 = p22;
     s11 = warp_sum_ll(s11); s12 = warp_sum_ll(s12); s22 = warp_sum_ll(s22);
     const float FS = 1.f / (float)(1 << 20);
@@ -177,16 +271,8 @@ __global__ void __launch_bounds__(128) k_lk(LkArgs a) {
       const int inx = (int)floorf(nx), iny = (int)floorf(ny);
       if (inx < -win || inx >= cols || iny < -win || iny >= rows) { if (level == 0) ok = false; break; }
       int v00, v01, v10, v11; lk_weights(nx, ny, inx, iny, v00, v01, v10, v11);
-      int q1 = 0, q2 = 0;
-      const bool in_j = inx >= 0 && iny >= 0 && inx + win < cols && iny + win < rows;
-#pragma unroll
-      for (int m = 0; m < kPix; m++) {
-        const int idx = lane + 32 * m;
-        if (idx < npx) {
-          const int diff = lk_sample_u8(J, cols, rows, iny + oy[m], inx + ox[m], in_j, v00, v01, v10, v11) - Iv[m];
-          q1 += diff * Ix[m]; q2 += diff * Iy[m];
-        }
-      }
+      int q1, q2;
+      lk_window_sums<0>(W, J, cols, rows, win, npx, lane, inx, iny, v00, v01, v10, v11, tJ, jx0, jy0, sjx, q1, q2);
       long long sb1 = q1, sb2 = q2;
       sb1 = warp_sum_ll(sb1); sb2 = warp_sum_ll(sb2);
       const float b1 = __fmul_rn((float)sb1, FS), b2 = __fmul_rn((float)sb2, FS);
@@ -206,13 +292,8 @@ __global__ void __launch_bounds__(128) k_lk(LkArgs a) {
       const int inx = (int)floorf(fx), iny = (int)floorf(fy);
       if (inx < -win || inx >= cols || iny < -win || iny >= rows) { ok = false; errv = 0.f; continue; }
       int v00, v01, v10, v11; lk_weights(fx, fy, inx, iny, v00, v01, v10, v11);
-      int pe = 0;
-      const bool in_e = inx >= 0 && iny >= 0 && inx + win < cols && iny + win < rows;
-#pragma unroll
-      for (int m = 0; m < kPix; m++) {
-        const int idx = lane + 32 * m;
-        if (idx < npx) pe += abs(lk_sample_u8(J, cols, rows, iny + oy[m], inx + ox[m], in_e, v00, v01, v10, v11) - Iv[m]);
-      }
+      int pe, unused;
+      lk_window_sums<1>(W, J, cols, rows, win, npx, lane, inx, iny, v00, v01, v10, v11, tJ, jx0, jy0, sjx, pe, unused);
       long long se = pe;
       se = warp_sum_ll(se);
       errv = __fdiv_rn((float)se, (float)(32 * win * win));
@@ -366,7 +447,7 @@ static int lk_launch(gf2_tracker* h, int n_streams, int slotI, int slotJ, const 
   for (int l = 0; l < kMaxLevels; l++) { a.img_stride[l] = h->img_stride[l]; a.der_stride[l] = h->der_stride[l]; }
   a.I = h->pyr[slotI]; a.J = h->pyr[slotJ];
   const int warps = n_streams * h->cfg.max_pts;
-  k_lk<<<(warps + 3) / 4, 128, 0, h->stream>>>(a);
+  k_lk<<<(warps + kLkWarps - 1) / kLkWarps, 32 * kLkWarps, 0, h->stream>>>(a);
   GF2T_CUDA(cudaGetLastError());
   return GF2_OK;
 }
