@@ -31,13 +31,24 @@ for _p in (ROOT, os.path.join(ROOT, "oracle")):
 # algorithmic bytes of one Jacobian sweep of one W10-F1000 window
 N_OBS, N_LM, N_FRAMES, N_IMU, D_RED = 6500, 1000, 11, 10, 165
 PRIOR_STRIDE = 8   # row stride of the prior arrays (the anchor prior of this workload has 6 rows)
-# DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of one k_linearize launch per window, from the ncu --set full capture
-# summarised in profiles/ncu_full_solver_kernels_B4096_r1.csv (629.2 MB read + 135.2 MB written at 4096 windows)
-TRAFFIC_PER_WINDOW = 764.4e6 / 4096
-# fp64 tensor sub-pipe activity (sm__inst_executed_pipe_tensor_subpipe_dmma, % of peak) from the same capture: north_star asks for
-# tensor-pipe utilisation of the reduced solve next to the HBM fraction of the Jacobian sweep
-NCU_DMMA_PCT = {"k_linearize": 34.4, "k_solve2": 8.9}
+WORKLOAD = "W10-F1000 (11 frames, 1000 landmarks, 6500 projection + 10 IMU factors + anchor prior), 200 Hz IMU preintegration, 8 trust-region iterations, time cap off"
 BYTES_SWEEP = N_OBS * 20 + N_LM * 32 + N_FRAMES * 136 + 64 + N_IMU * 1456 + (D_RED * (D_RED + 1) // 2 + D_RED) * 8  # = 289,000
+
+
+def ncu_summary():
+    """Per-kernel numbers of the latest `ncu --set full` capture of this build, written by scripts/ncu_summarize.py into profiles/ (dated, with
+    the capture's command): DRAM bytes per launch, fp64 tensor sub-pipe activity, warps active. None when no summary is committed."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_summary_r2.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
+def bench_config(B, distinct, world, h2d_mb=None):
+    """The `config` object of the JSON line: identical for the gf2 arm and the reference arm (same workload, same batch definition)."""
+    return {"workload": WORKLOAD, "windows_per_gpu_per_step": B, "distinct_windows": distinct, "parallelism": f"window-dp{world} (no collective)",
+            "l2": "inputs larger than L2 (631 MB of window data per GPU at 4096 windows)"}
 
 
 def measured_peaks():
@@ -119,9 +130,11 @@ def make_batch(gf2, synth, B, distinct, first_window=0, pinned=True, prior_strid
 def run_lk(gf2, synth, streams=64, steps=10, cv2_seconds=2.0):
     """FeatureTracker::trackImage's LK stage (forward 4 levels + backward 2 levels + consistency check) on `streams`
     independent 640x480 frame pairs per launch; images cross PCIe every call (the tracker API takes host images)."""
-    base = [synth.image_pair(s % 8, shift=(2.0 + 0.3 * (s % 8), -1.0)) for s in range(min(streams, 8))]
-    prev = np.stack([base[s % len(base)][0] for s in range(streams)]); cur = np.stack([base[s % len(base)][1] for s in range(streams)])
-    npts = min(len(b[2]) for b in base)
+    base = [synth.image_pair(s % 8, shift=(2.0 + 0.3 * (s % 8), -1.0), n_pts=400) for s in range(min(streams, 8))]
+    npts = min(300, min(len(b[2]) for b in base))      # BASELINE config 3: 300 corners
+    prev = gf2.pinned_empty((streams, 480, 640), np.uint8); cur = gf2.pinned_empty((streams, 480, 640), np.uint8)   # host images in pinned memory: the upload runs at PCIe speed
+    for s in range(streams):
+        prev[s] = base[s % len(base)][0]; cur[s] = base[s % len(base)][1]
     pts = np.stack([base[s % len(base)][2][:npts] for s in range(streams)])
     t = gf2.Tracker(640, 480, max_pts=npts, max_streams=streams)
     for _ in range(3):
@@ -199,7 +212,37 @@ def run_lk(gf2, synth, streams=64, steps=10, cv2_seconds=2.0):
         except ImportError:
             pass
     t.close(); t1.close()
+    line["stream"] = run_lk_stream(gf2, synth)
     return line
+
+
+def run_lk_stream(gf2, synth, n_frames=300):
+    """BASELINE.json config 3 as a STREAM: 300 frames of a 640x480 30 Hz synthetic sequence through FeatureTracker::trackImage of the C++ mirror
+    (CLAHE off; forward 4-level LK + backward check on the device, border / status filtering, setMask, goodFeaturesToTrack top-up to
+    max_cnt = 300 corners with min_dist = 20 on the device, undistortion + velocities on the host): one stream, frame after frame — latency."""
+    import ctypes as C
+    L = C.CDLL(os.path.join(ROOT, "ground-fusion2_b200", "libgf2_host.so"))
+    L.gf2h_tracker_create.restype = C.c_void_p
+    P_ = lambda a: np.ascontiguousarray(a).ctypes.data_as(C.c_void_p)
+    imgs = synth.image_stream(0, n_frames)
+    K = np.array([607.8, 607.8, 328.8, 245.5, 0.0, 0.0, 0.0, 0.0])
+    t = C.c_void_p(L.gf2h_tracker_create(480, 640, 300, 20, P_(K)))
+    depth = np.zeros((480, 640), np.uint16)
+    out = np.zeros((400, 10)); ms = []; counts = []; ages = {}
+    for k in range(n_frames):
+        t0 = time.perf_counter()
+        n = L.gf2h_tracker_track(t, C.c_double(k / 30.0), P_(imgs[k]), P_(depth), 400, P_(out))
+        ms.append((time.perf_counter() - t0) * 1e3)
+        if n < 0:
+            raise RuntimeError("trackImage failed on the config-3 stream")
+        counts.append(n)
+        ids = out[:n, 0].astype(int)
+        ages = {i: ages.get(i, 0) + 1 for i in ids}
+    L.gf2h_tracker_destroy(t)
+    med = float(np.median(ms[5:]))
+    return {"metric": "FeatureTracker::trackImage frames/sec, one 640x480 stream of 300 frames, 300 corners (BASELINE config 3)", "value": 1e3 / med, "unit": "frames/s",
+            "frames": n_frames, "median_ms_per_frame": med, "p95_ms_per_frame": float(np.percentile(ms[5:], 95)), "real_time_factor_at_30hz": (1e3 / med) / 30.0,
+            "mean_features_per_frame": float(np.mean(counts)), "mean_track_age_frames": float(np.mean(list(ages.values()))) if ages else 0.0}
 
 
 def run_lio(gf2, synth, steps=10, with_cpu=True):
@@ -549,10 +592,10 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": "sliding-window solves/sec (10-frame, 1k-feat)", "value": val, "unit": "solves/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "W10-F1000 (11 frames, 1000 landmarks, 6500 projection + 10 IMU factors + anchor prior), 8 iterations, time cap off",
-                       "windows_per_step": n},
+            "config": bench_config(args.windows, min(args.distinct, args.windows), max(world, 1)),
             "cpu_baseline": {"value": val, "unit": "solves/s", "cores": T, "kind": "port",
-                             "sample": f"{n} windows/step x {args.steps} steps, restated-reference CPU baseline (Ceres unavailable), {T} threads over independent windows"},
+                             "sample": f"bounded sample of the workload: {n} windows/step x {args.steps} steps, restated-reference CPU baseline (Ceres unavailable; the restatement is pinned "
+                                       f"to the reference's own factor code, oracle/_ref), {T} threads over independent windows"},
             "e2e": {"value": val, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -738,22 +781,27 @@ def main():
         n_lin = lin_launches * args.steps
         lin_avg_ms = lin_ms / n_lin
         achieved = BYTES_SWEEP * B / (lin_avg_ms / 1e3) / 1e9
+        ncu = ncu_summary() or {}
+        klin = (ncu.get("kernels") or {}).get("k_linearize") or {}
+        traffic = klin.get("dram_bytes_per_window")
         line = {
             "metric": "sliding-window solves/sec (10-frame, 1k-feat)", "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "W10-F1000 (11 frames, 1000 landmarks, 6500 projection + 10 IMU factors + anchor prior), 200 Hz IMU preintegration on device, 8 trust-region iterations, time cap off",
-                       "windows_per_gpu_per_step": B, "distinct_windows": min(args.distinct, B), "parallelism": f"window-dp{world} (no collective)",
-                       "l2": "inputs larger than L2 (%.0f MB of window data per GPU)" % (h2d / 1e6), "converged_fraction": ok_frac},
+            "config": bench_config(B, min(args.distinct, B), world),
+            "converged_fraction": ok_frac,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "chunks": nch,
                     "timing": "host wall clock around the blocking ABI calls of all chunks + device synchronize"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k_linearize", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": achieved / peaks["hbm_gbs"], "traffic": TRAFFIC_PER_WINDOW * B, "traffic_source": "ncu --set full capture of k_linearize, profiles/ (per window x windows per launch)", "peak_source": which,
-                         "algorithmic_bytes_per_launch": BYTES_SWEEP * B, "avg_launch_ms": lin_avg_ms},
+                         "frac": achieved / peaks["hbm_gbs"], "traffic": (traffic * B if traffic else None),
+                         "traffic_source": (f"profiles/ncu_summary_r2.json ({ncu.get('captured')}, {ncu.get('command')}): dram__bytes_read.sum + dram__bytes_write.sum of one k_linearize launch per window x windows per launch" if traffic else None),
+                         "peak_source": which, "algorithmic_bytes_per_launch": BYTES_SWEEP * B, "avg_launch_ms": lin_avg_ms,
+                         "fp64_pipe": {"note": "DFMA and the fp64 mma share one datapath on this part (profiles/ubench_fp64_pipes_r2.txt: 12.1 + 24.3 = 36.4 TFLOP/s mixed); the kernel's real bound is its total fp64 work",
+                                       "dmma_pipe_pct_ncu": klin.get("dmma_pipe_pct"), "fp64_fma_pipe_pct_ncu": klin.get("fp64_pipe_pct"), "warps_active_pct_ncu": klin.get("warps_active_pct")}},
             "reduced_solve": {"kernels": "k_nonvis + k_solve2", "avg_ms_per_iteration": solve_ms / n_lin, "bound": "serial pivot chain (latency), not the tensor pipe",
-                              "dmma_pipe_pct_ncu": NCU_DMMA_PCT, "source": "profiles/ncu_full_solver_kernels_B4096_r1.csv"},
+                              "dmma_pipe_pct_ncu": ((ncu.get("kernels") or {}).get("k_solve2") or {}).get("dmma_pipe_pct"), "source": "profiles/ncu_summary_r2.json"},
             ("config4_sharded" if world > 1 else "config4"): cfg4,
             "marginalize": marg, "lk": lk_line, "lio": lio_line, "replay": replay_line,
             "phase_ms_per_step": {"linearize": lin_ms / args.steps, "reduced_solve": solve_ms / args.steps, "backsub_candidate": step_ms / args.steps,

@@ -437,6 +437,39 @@ def _arc_trajectory(rng, n_frames, speed, yaw_rate, frame_dt, imu_hz, pause, whe
     return out
 
 
+def image_stream(seed=0, n_frames=300, w=640, h=480, max_flow=4.0):
+    """BASELINE.json config 3 stream: one band-limited random texture seen through a smoothly varying similarity warp (translation <= max_flow
+    px per frame, slow rotation / zoom) + N(0, 2^2) intensity noise, 30 Hz. Uses cv2.warpAffine when cv2 is importable (1 ms per frame), the
+    numpy bilinear sampler otherwise. Returns uint8 [n_frames, h, w]."""
+    rng = np.random.default_rng(BASE_SEED + 9000 + seed)
+    pad = 256
+    big = rng.normal(size=(h + 2 * pad, w + 2 * pad)).astype(np.float32)
+    k = np.exp(-0.5 * (np.arange(-6, 7) / 2.0) ** 2).astype(np.float32); k /= k.sum()
+    big = np.apply_along_axis(lambda r: np.convolve(r, k, mode="same"), 1, big)
+    big = np.apply_along_axis(lambda c: np.convolve(c, k, mode="same"), 0, big)
+    big = ((big - big.mean()) / big.std()).astype(np.float32)
+    t = np.arange(n_frames)
+    dx = pad + 60.0 * np.sin(2 * np.pi * t / 97.0) * (max_flow / 3.9); dy = pad + 45.0 * np.sin(2 * np.pi * t / 71.0 + 0.7) * (max_flow / 4.0)
+    rot = 0.05 * np.sin(2 * np.pi * t / 151.0); zoom = 1.0 + 0.03 * np.sin(2 * np.pi * t / 113.0)
+    out = np.zeros((n_frames, h, w), np.uint8)
+    try:
+        import cv2
+    except ImportError:
+        cv2 = None
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    for f in range(n_frames):
+        c, s_ = zoom[f] * np.cos(rot[f]), zoom[f] * np.sin(rot[f])
+        M = np.array([[c, -s_, dx[f] + w / 2 - c * w / 2 + s_ * h / 2], [s_, c, dy[f] + h / 2 - s_ * w / 2 - c * h / 2]], np.float32)   # output pixel -> texture coordinate
+        if cv2 is not None:
+            v = cv2.warpAffine(big, M, (w, h), flags=cv2.INTER_LINEAR | cv2.WARP_INVERSE_MAP)
+        else:
+            xs = M[0, 0] * xx + M[0, 1] * yy + M[0, 2]; ys = M[1, 0] * xx + M[1, 1] * yy + M[1, 2]
+            x0 = np.floor(xs).astype(int); y0 = np.floor(ys).astype(int); ax = xs - x0; ay = ys - y0
+            v = big[y0, x0] * (1 - ax) * (1 - ay) + big[y0, x0 + 1] * ax * (1 - ay) + big[y0 + 1, x0] * (1 - ax) * ay + big[y0 + 1, x0 + 1] * ax * ay
+        out[f] = np.clip(128 + 45 * v + rng.normal(0, 2, v.shape), 0, 255).astype(np.uint8)
+    return out
+
+
 def lidar_scans(gt_p, gt_R, seed=0, lines=32, az_step_deg=0.6, fov_deg=(-16.0, 15.0), noise=0.01, margin=6.0, height=(0.0, 3.0)):
     """A 32-line spinning LiDAR (BASELINE.json config 5: 32 lines, 10 Hz) at the frame poses of a replay stream, ray-cast against an axis-aligned
     box room that encloses the trajectory with `margin` metres to spare (floor / ceiling at `height`): per frame the hit points in the BODY frame
