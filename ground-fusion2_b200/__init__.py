@@ -78,8 +78,9 @@ class Solver:
     """Batched sliding-window solver: the ceres::Solve call of Estimator::optimization() for `max_windows` windows."""
 
     def __init__(self, max_windows, n_frames=11, max_landmarks=1000, max_obs=7500, max_planes=0, max_imu_samples=0,
-                 use_wheel=False, device=0, max_prior_rows=0, max_wheel_samples=0):
+                 use_wheel=False, device=0, max_prior_rows=0, max_wheel_samples=0, sweep=0):
         cfg = abi.SolverCfg()
+        cfg.sweep = sweep   # abi.SWEEP_AUTO / SWEEP_BATCH / SWEEP_WINDOW
         cfg.device = device; cfg.max_windows = max_windows; cfg.n_frames = n_frames; cfg.max_landmarks = max_landmarks
         cfg.max_obs = max_obs; cfg.max_planes = max_planes; cfg.max_imu_samples = max_imu_samples; cfg.max_wheel_samples = max_wheel_samples
         cfg.use_wheel = 1 if use_wheel else 0

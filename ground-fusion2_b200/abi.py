@@ -28,11 +28,14 @@ TERM_NAMES = ["no_convergence", "function_tol", "gradient_tol", "parameter_tol",
 LK_USE_INITIAL_FLOW = 4
 
 
+SWEEP_AUTO, SWEEP_BATCH, SWEEP_WINDOW = 0, 1, 2   # gf2_solver_cfg.sweep
+
+
 class SolverCfg(C.Structure):
     _fields_ = [("device", C.c_int32), ("max_windows", C.c_int32), ("n_frames", C.c_int32),
                 ("max_landmarks", C.c_int32), ("max_obs", C.c_int32), ("max_planes", C.c_int32),
                 ("max_imu_samples", C.c_int32), ("max_wheel_samples", C.c_int32), ("use_wheel", C.c_int32),
-                ("max_prior_rows", C.c_int32), ("reserved_", C.c_int32 * 6)]
+                ("max_prior_rows", C.c_int32), ("sweep", C.c_int32), ("reserved_", C.c_int32 * 5)]
 
 
 class SolveOpts(C.Structure):

@@ -9,6 +9,7 @@
 #include <vector>
 #include "gf2_solver_solve.cuh"
 #include "gf2_solver_lin.cuh"
+#include "gf2_solver_lin_ws.cuh"
 #include "gf2_solver_marg.cuh"
 #include "gf2_common.h"
 
@@ -252,6 +253,7 @@ constexpr int kNcclFloat64 = 8, kNcclChar = 0, kNcclSum = 0, kNcclMax = 2;  // n
 struct gf2_solver {
   gf2_solver_cfg cfg;
   int D;
+  int sm_count = 148;
   int last_Dx = 0;   // reduced dimension of the last run (D, or 15 (F + 1) with free wheel calibration blocks)
   cudaStream_t stream, own_stream;
   double *snap_pose = nullptr, *snap_sb = nullptr, *snap_invdep = nullptr;
@@ -299,6 +301,7 @@ void gf2_host_free(void* p) { if (p) cudaFreeHost(p); }
 int gf2_solver_create(const gf2_solver_cfg* cfg, gf2_solver** out) {
   if (!cfg || !out) return gf2::fail(GF2_ERR_INVALID, "null argument");
   if (cfg->n_frames < 2 || cfg->n_frames > GF2_MAX_FRAMES) return gf2::fail(GF2_ERR_INVALID, "n_frames %d out of range [2, %d]", cfg->n_frames, GF2_MAX_FRAMES);
+  if (cfg->sweep < GF2_SWEEP_AUTO || cfg->sweep > GF2_SWEEP_WINDOW) return gf2::fail(GF2_ERR_INVALID, "sweep %d is not a GF2_SWEEP_* value", cfg->sweep);
   if (cfg->max_landmarks < 1 || cfg->max_landmarks > GF2_MAX_LANDMARKS) return gf2::fail(GF2_ERR_INVALID, "max_landmarks %d out of range", cfg->max_landmarks);
   if (cfg->max_windows < 1 || cfg->max_obs < 1) return gf2::fail(GF2_ERR_INVALID, "max_windows / max_obs must be positive");
   if (gf2_device_count() <= cfg->device) return gf2::fail(GF2_ERR_CUDA, "CUDA device %d not available (no CPU fallback exists)", cfg->device);
@@ -359,8 +362,10 @@ int gf2_solver_create(const gf2_solver_cfg* cfg, gf2_solver** out) {
   cudaHostAlloc((void**)&h->h_state, sizeof(WinState) * B, cudaHostAllocDefault);
   // opt in to large dynamic shared memory
   cudaFuncSetAttribute(k_linearize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LinShared));
+  cudaFuncSetAttribute(ws::k_linearize_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ws::LinShared));
   cudaFuncSetAttribute(k_solve2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(Solve2Shared) + sizeof(double) * solve2_matrix_doubles(F, 1)));
   cudaFuncSetAttribute(k_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * 450 * GF2_MAX_FRAMES));
+  cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, cfg->device);
   // function attributes are per device: set here, after cudaSetDevice, for every handle (not once per process)
   cudaFuncSetAttribute(k_marg_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(((sizeof(MargShared) + 15) & ~size_t(15)) + sizeof(double) * kMargTMax * kMargLD));
   cudaFuncSetAttribute(k_marg_eig, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(((sizeof(EigShared) + 15) & ~size_t(15)) + sizeof(double) * 2 * kMargKMax * (kMargKMax | 1)));
@@ -641,8 +646,15 @@ static int run(gf2_solver* h, int first, int n, const gf2_solve_opts* opts, gf2_
   k_tasks<<<n, 32, 0, h->stream>>>(k, first);
   cudaEventRecord(h->ev[ne++], h->stream);
   const int iters = only_linearize ? 1 : iterations;
+  // One robot / small batches (up to two windows per SM) are launch- and latency-bound: the sweep runs one window per SM on 16 warp-specialised
+  // warps (k_linearize_ws) and back-substitution + candidate + decision share one launch (k_step). A full batch gets its occupancy from the
+  // batch: k_linearize (two windows per SM) and the three step kernels at their own occupancy. cfg.sweep overrides the choice of the sweep.
+  const bool small = n <= 2 * h->sm_count;
+  const bool sweep_ws = h->cfg.sweep == GF2_SWEEP_WINDOW || (h->cfg.sweep == GF2_SWEEP_AUTO && small);
+  const bool fused_step = !h->nccl_comm && small;
   for (int it = 0; it < iters; it++) {
-    k_linearize<<<n, kLinThreads, sizeof(LinShared), h->stream>>>(k, first);
+    if (sweep_ws) ws::k_linearize_ws<<<n, ws::kLinThreads, sizeof(ws::LinShared), h->stream>>>(k, first);
+    else k_linearize<<<n, kLinThreads, sizeof(LinShared), h->stream>>>(k, first);
     // Factor-sharded mode, SURVEY 8(e). The sweep ran on this rank's landmarks / planes of ALL n windows. When n divides by the ranks the
     // windows' records [Svis | gvis | gschur | Udiag | visual cost] (36.6 KB each) are REDUCE-SCATTERED: rank r receives the summed records of
     // its n / N windows, assembles + factorises only those (k_nonvis, k_solve2: the reduced solve is sharded by window instead of being
@@ -676,7 +688,13 @@ static int run(gf2_solver* h, int first, int n, const gf2_solve_opts* opts, gf2_
       cudaEventRecord(h->ev_nccl[nn++], h->stream);
     }
     cudaEventRecord(h->ev[ne++], h->stream);
-    if (!only_linearize) {
+    if (!only_linearize && fused_step) {
+      // one robot / small batches: back-substitution, dogleg step, candidate evaluation and the accept / reject decision in one launch
+      // (launch-latency bound there; a full batch runs the three kernels at their own, higher occupancy: measured 0.82 vs 0.87 ms per 4096 windows)
+      cudaEventRecord(h->ev[ne++], h->stream);
+      k_step<<<n, 288, 0, h->stream>>>(k, first);
+      cudaEventRecord(h->ev[ne++], h->stream);
+    } else if (!only_linearize) {
       k_backsub<<<n, 256, 0, h->stream>>>(k, first);
       if (h->nccl_comm) {
         cudaEventRecord(h->ev_nccl[nn++], h->stream);
@@ -708,7 +726,7 @@ static int run(gf2_solver* h, int first, int n, const gf2_solve_opts* opts, gf2_
     cudaEventElapsedTime(&ms, h->ev[b], h->ev[b + 1]); h->timing[2] += ms;       // solve
     if (!only_linearize) { cudaEventElapsedTime(&ms, h->ev[b + 1], h->ev[b + 3]); h->timing[3] += ms; }
   }
-  h->timing[4] = 2 + iters * (only_linearize ? 3 : 6); h->timing[5] = iters;
+  h->timing[4] = 2 + iters * (only_linearize ? 3 : (fused_step ? 4 : 6)); h->timing[5] = iters;
   cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]); h->timing[6] = ms;  // k_prepare
   for (int q = 0; q + 1 < nn; q += 2) { cudaEventElapsedTime(&ms, h->ev_nccl[q], h->ev_nccl[q + 1]); h->timing[7] += ms; }   // time inside the NCCL collectives (factor-sharded mode)
   if (summaries) for (int w = 0; w < n; w++) {

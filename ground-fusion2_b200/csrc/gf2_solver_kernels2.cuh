@@ -361,12 +361,9 @@ struct StepShared {
   int decision;
 };
 
-__global__ void __launch_bounds__(256, 3) k_backsub(KP p, int w0) {
-  const int w = w0 + blockIdx.x;
-  WinState& st = p.st[w];
-  if (!st.active || st.reuse || !st.lin_valid) return;
-  __shared__ StepShared S;
-  const int t = threadIdx.x, F = p.F, D = p.D, NV = 6 * F;
+// body of sweep 2 for one window: threads t < 256 walk the landmarks; the six sums are valid in thread 0 afterwards
+__device__ __forceinline__ void backsub_body(const KP& p, int w, const WinState& st, StepShared& S, double (&sums)[6]) {
+  const int t = threadIdx.x, F = p.F, NV = 6 * F;
   const int nlm = p.nlm[w];
   const int32_t* start = p.start + (size_t)w * p.Lm; const int32_t* tlen = p.tlen + (size_t)w * p.Lm; const int32_t* obeg = p.obeg + (size_t)w * p.Lm;
   const float4* obs = p.obs + (size_t)w * p.Om;
@@ -381,8 +378,9 @@ __global__ void __launch_bounds__(256, 3) k_backsub(KP p, int w0) {
   __syncthreads();
   const double* ftd = p.frame_td + (size_t)w * F;
   const double mu = st.mu, sqi = p.sqrt_info_px;
-  double sums[6] = {0, 0, 0, 0, 0, 0};  // dlg2, gn2, gz, zEz, uEz, uHu
-  for (int l = t; l < nlm; l += blockDim.x) {
+#pragma unroll
+  for (int q = 0; q < 6; q++) sums[q] = 0.0;  // dlg2, gn2, gz, zEz, uEz, uHu
+  for (int l = t; l < nlm && t < 256; l += 256) {
    {
     const size_t o = (size_t)w * p.Lm + l;
     const double v = p.lm_v[o];
@@ -443,7 +441,15 @@ __global__ void __launch_bounds__(256, 3) k_backsub(KP p, int w0) {
    }
   }
   block_sum<6>(sums, S.red);
-  if (t == 0) { double* cs = p.c_sums + (size_t)w * 8; for (int i = 0; i < 6; i++) cs[i] = sums[i]; }
+}
+__global__ void __launch_bounds__(256, 3) k_backsub(KP p, int w0) {
+  const int w = w0 + blockIdx.x;
+  WinState& st = p.st[w];
+  if (!st.active || st.reuse || !st.lin_valid) return;
+  __shared__ StepShared S;
+  double sums[6];
+  backsub_body(p, w, st, S, sums);
+  if (threadIdx.x == 0) { double* cs = p.c_sums + (size_t)w * 8; for (int i = 0; i < 6; i++) cs[i] = sums[i]; }
 }
 
 // ------------------------------------------------------------------------------------------------ k_candidate
@@ -475,20 +481,17 @@ __device__ void dogleg_coefficients(WinState& st, const double* cs) {
   st.model_cost_change = a * dlg2 + b * gz - 0.5 * (a * a * uHu + 2 * a * b * uHz + b * b * zHz);
 }
 
-__global__ void __launch_bounds__(288, 2) k_cand_eval(KP p, int w0) {
-  const int w = w0 + blockIdx.x;
-  WinState& st = p.st[w];
-  if (!st.active) return;
-  if (!st.lin_valid) return;  // invalid linear solve already handled in k_solve
-  __shared__ StepShared S;
-  const int t = threadIdx.x, F = p.F, D = p.D;
-  if (t == 0) dogleg_coefficients(st, p.c_sums + (size_t)w * 8);
-  __syncthreads();
+// body of sweep 3 for one window (288 threads: 8 landmark warps + warp 8 for the non-visual factors); st.coef_a / coef_b are set and visible.
+// Afterwards thread 0 holds acc = this rank's landmark / plane sums and accx = the frame-state / non-visual sums.
+__device__ __forceinline__ void cand_body(const KP& p, int w, const WinState& st, StepShared& S, double (&acc)[3], double (&accx)[3]) {
+  const int t = threadIdx.x, F = p.F;
   const double a = st.coef_a, b = st.coef_b;
   const double* pose = p.pose + (size_t)w * F * 7; const double* sb = p.sb + (size_t)w * F * 9;
   double* pose_c = p.pose_c + (size_t)w * F * 7; double* sb_c = p.sb_c + (size_t)w * F * 9;
-  double acc[3] = {0, 0, 0};   // this rank's landmarks / planes: candidate cost, |dl|^2, |l|^2   (all-reduced in sharded mode)
-  double accx[3] = {0, 0, 0};  // frame states and non-visual factors (every rank computes the same): cost, |dx|^2, |x|^2
+  // acc: this rank's landmarks / planes: candidate cost, |dl|^2, |l|^2 (all-reduced in sharded mode); accx: frame states and non-visual
+  // factors (every rank computes the same): cost, |dx|^2, |x|^2
+#pragma unroll
+  for (int q = 0; q < 3; q++) { acc[q] = 0.0; accx[q] = 0.0; }
   // retraction of frame states: PoseLocalParameterization::Plus (VE/factor/pose_local_parameterization.cpp:12-28)
   if (t < F) {
     const double* zx = p.zx + (size_t)w * p.Ds + 15 * t; const double* ux = p.ux + (size_t)w * p.Ds + 15 * t;
@@ -616,7 +619,18 @@ __global__ void __launch_bounds__(288, 2) k_cand_eval(KP p, int w0) {
   }
   block_sum<3>(acc, S.red);
   block_sum<3>(accx, S.red);
-  if (t == 0) {
+}
+__global__ void __launch_bounds__(288, 2) k_cand_eval(KP p, int w0) {
+  const int w = w0 + blockIdx.x;
+  WinState& st = p.st[w];
+  if (!st.active) return;
+  if (!st.lin_valid) return;  // invalid linear solve already handled in k_solve
+  __shared__ StepShared S;
+  if (threadIdx.x == 0) dogleg_coefficients(st, p.c_sums + (size_t)w * 8);
+  __syncthreads();
+  double acc[3], accx[3];
+  cand_body(p, w, st, S, acc, accx);
+  if (threadIdx.x == 0) {
     double* cc = p.c_cand + (size_t)w * 4;
     cc[0] = acc[0]; cc[1] = acc[1]; cc[2] = acc[2];
     st.cand_nv = accx[0]; st.step2_x = accx[1]; st.xnorm2_x = accx[2];
@@ -624,17 +638,11 @@ __global__ void __launch_bounds__(288, 2) k_cand_eval(KP p, int w0) {
 }
 
 // TrustRegionMinimizer: tolerance checks, step acceptance, radius update (after the candidate sums are complete)
-__global__ void __launch_bounds__(256) k_decide(KP p, int w0) {
-  const int w = w0 + blockIdx.x;
-  WinState& st = p.st[w];
-  if (!st.active) return;
-  if (!st.lin_valid) return;
-  __shared__ int s_decision;
+// acc (read by thread 0 only) = {candidate cost, |step|^2, |x|^2} over all factors / parameter blocks
+__device__ __forceinline__ void decide_body(const KP& p, int w, WinState& st, int& s_decision, const double (&acc)[3]) {
   const int t = threadIdx.x, F = p.F;
   const int nlm = p.nlm[w];
   if (t == 0) {
-    const double* cc = p.c_cand + (size_t)w * 4;
-    const double acc[3] = {cc[0] + st.cand_nv, cc[1] + st.step2_x, cc[2] + st.xnorm2_x};
     int decision = 0;  // 0 reject, 1 accept, 2 terminated (no accept)
     st.cand_cost = acc[0];
     st.x_norm2 = acc[2];
@@ -691,6 +699,42 @@ __global__ void __launch_bounds__(256) k_decide(KP p, int w0) {
       else if (t == 10) p.tdw[w] = p.tdw_c[w];
     }
   }
+}
+__global__ void __launch_bounds__(256) k_decide(KP p, int w0) {
+  const int w = w0 + blockIdx.x;
+  WinState& st = p.st[w];
+  if (!st.active) return;
+  if (!st.lin_valid) return;
+  __shared__ int s_decision;
+  const double* cc = p.c_cand + (size_t)w * 4;
+  const double acc[3] = {cc[0] + st.cand_nv, cc[1] + st.step2_x, cc[2] + st.xnorm2_x};
+  decide_body(p, w, st, s_decision, acc);
+}
+
+// ------------------------------------------------------------------------------------------------ k_step
+// Single-GPU path: sweep 2, the dogleg coefficients, sweep 3 and the trust-region decision of one window in ONE launch (the sums the three
+// stages exchange stay in the CTA; the factor-sharded mode all-reduces them between k_backsub, k_cand_eval and k_decide instead). The
+// second sweep over the window's observation records (120 KB) finds them in L1 / L2.
+__global__ void __launch_bounds__(288, 2) k_step(KP p, int w0) {
+  const int w = w0 + blockIdx.x;
+  WinState& st = p.st[w];
+  if (!st.active || !st.lin_valid) return;   // invalid linear solve already handled in k_solve2
+  __shared__ StepShared S;
+  __shared__ double cs[8];
+  if (!st.reuse) {   // a rejected step keeps the linearisation and its landmark sums (st.dlg2_l ..): only the radius changed
+    double sums[6];
+    backsub_body(p, w, st, S, sums);
+    if (threadIdx.x == 0) for (int i = 0; i < 6; i++) cs[i] = sums[i];
+  } else if (threadIdx.x == 0) {
+    cs[0] = st.dlg2_l; cs[1] = st.gn2_l; cs[2] = st.gz_l; cs[3] = st.zHz_l; cs[4] = st.uHz_l; cs[5] = st.uHu_l;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) dogleg_coefficients(st, cs);
+  __syncthreads();
+  double acc[3], accx[3];
+  cand_body(p, w, st, S, acc, accx);
+  const double tot[3] = {acc[0] + accx[0], acc[1] + accx[1], acc[2] + accx[2]};
+  decide_body(p, w, st, S.decision, tot);
 }
 
 }  // namespace gf2

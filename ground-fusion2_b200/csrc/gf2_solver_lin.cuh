@@ -148,39 +148,39 @@ __device__ __forceinline__ void syrk_tile(const double (&f)[9], double (&C)[kSch
   if constexpr (tl.a >= 0 && tl.a >= M) mma_f64(C[S][0], C[S][1], f[tl.a], f[tl.b]);
 }
 // row fragment of tile row I: WT[8 I + fq - kRowShift][k0 + fk]; the first kRowShift rows of tile row 0 are padding
-template <int M, int I>
+template <int M, int I, int STRIDE>
 __device__ __forceinline__ void syrk_frag(double (&f)[9], const double* wb, bool lo_ok) {
   if constexpr (I >= M) {
     if constexpr (I == 0) f[0] = lo_ok ? wb[0] : 0.0;
-    else f[I] = wb[I * 8 * kWTStride];
+    else f[I] = wb[I * 8 * STRIDE];
   }
 }
-// one round: C[tile] += sum over the 128 landmark columns, tiles with a >= M only
-template <int W, int M>
+// one round: C[tile] += sum over the COLS landmark columns of a W tile with row stride STRIDE, tiles with a >= M only
+template <int W, int M, int STRIDE, int COLS>
 __device__ __forceinline__ void syrk_round(const double* wb /* &WT[fq - kRowShift][fk] */, bool lo_ok, double (&C)[kSchurSlots][2]) {
-#pragma unroll 4
-  for (int k0 = 0; k0 < kLinThreads; k0 += 4) {
+#pragma unroll (COLS >= 128 ? 4 : 2)
+  for (int k0 = 0; k0 < COLS; k0 += 4) {
     double f[9];
-    syrk_frag<M, 0>(f, wb + k0, lo_ok); syrk_frag<M, 1>(f, wb + k0, lo_ok); syrk_frag<M, 2>(f, wb + k0, lo_ok);
-    syrk_frag<M, 3>(f, wb + k0, lo_ok); syrk_frag<M, 4>(f, wb + k0, lo_ok); syrk_frag<M, 5>(f, wb + k0, lo_ok);
-    syrk_frag<M, 6>(f, wb + k0, lo_ok); syrk_frag<M, 7>(f, wb + k0, lo_ok); syrk_frag<M, 8>(f, wb + k0, lo_ok);
+    syrk_frag<M, 0, STRIDE>(f, wb + k0, lo_ok); syrk_frag<M, 1, STRIDE>(f, wb + k0, lo_ok); syrk_frag<M, 2, STRIDE>(f, wb + k0, lo_ok);
+    syrk_frag<M, 3, STRIDE>(f, wb + k0, lo_ok); syrk_frag<M, 4, STRIDE>(f, wb + k0, lo_ok); syrk_frag<M, 5, STRIDE>(f, wb + k0, lo_ok);
+    syrk_frag<M, 6, STRIDE>(f, wb + k0, lo_ok); syrk_frag<M, 7, STRIDE>(f, wb + k0, lo_ok); syrk_frag<M, 8, STRIDE>(f, wb + k0, lo_ok);
     syrk_tile<W, M, 0>(f, C); syrk_tile<W, M, 1>(f, C); syrk_tile<W, M, 2>(f, C); syrk_tile<W, M, 3>(f, C);
     syrk_tile<W, M, 4>(f, C); syrk_tile<W, M, 5>(f, C); syrk_tile<W, M, 6>(f, C); syrk_tile<W, M, 7>(f, C);
     syrk_tile<W, M, 8>(f, C); syrk_tile<W, M, 9>(f, C); syrk_tile<W, M, 10>(f, C); syrk_tile<W, M, 11>(f, C);
   }
 }
-template <int W>
+template <int W, int STRIDE, int COLS>
 __device__ __forceinline__ void syrk_warp(int a_min, const double* wb, bool lo_ok, double (&C)[kSchurSlots][2]) {
   switch (a_min) {
-    case 0: syrk_round<W, 0>(wb, lo_ok, C); break;
-    case 1: syrk_round<W, 1>(wb, lo_ok, C); break;
-    case 2: syrk_round<W, 2>(wb, lo_ok, C); break;
-    case 3: syrk_round<W, 3>(wb, lo_ok, C); break;
-    case 4: syrk_round<W, 4>(wb, lo_ok, C); break;
-    case 5: syrk_round<W, 5>(wb, lo_ok, C); break;
-    case 6: syrk_round<W, 6>(wb, lo_ok, C); break;
-    case 7: syrk_round<W, 7>(wb, lo_ok, C); break;
-    default: syrk_round<W, 8>(wb, lo_ok, C); break;
+    case 0: syrk_round<W, 0, STRIDE, COLS>(wb, lo_ok, C); break;
+    case 1: syrk_round<W, 1, STRIDE, COLS>(wb, lo_ok, C); break;
+    case 2: syrk_round<W, 2, STRIDE, COLS>(wb, lo_ok, C); break;
+    case 3: syrk_round<W, 3, STRIDE, COLS>(wb, lo_ok, C); break;
+    case 4: syrk_round<W, 4, STRIDE, COLS>(wb, lo_ok, C); break;
+    case 5: syrk_round<W, 5, STRIDE, COLS>(wb, lo_ok, C); break;
+    case 6: syrk_round<W, 6, STRIDE, COLS>(wb, lo_ok, C); break;
+    case 7: syrk_round<W, 7, STRIDE, COLS>(wb, lo_ok, C); break;
+    default: syrk_round<W, 8, STRIDE, COLS>(wb, lo_ok, C); break;
   }
 }
 // accumulator tiles -> dense 72x72 (upper tiles, end-aligned index) in shared memory
@@ -467,10 +467,10 @@ __global__ void __launch_bounds__(kLinThreads, 2) k_linearize(KP p, int w0) {
     // Schur SYRK on the fp64 tensor cores: C[a-tile][b-tile] += sum_l Ws[l][a] * Ws[l][b]
     {
       switch (wid) {
-        case 0: syrk_warp<0>(a_min, wb, lo_ok, C); break;
-        case 1: syrk_warp<1>(a_min, wb, lo_ok, C); break;
-        case 2: syrk_warp<2>(a_min, wb, lo_ok, C); break;
-        default: syrk_warp<3>(a_min, wb, lo_ok, C); break;
+        case 0: syrk_warp<0, kWTStride, kLinThreads>(a_min, wb, lo_ok, C); break;
+        case 1: syrk_warp<1, kWTStride, kLinThreads>(a_min, wb, lo_ok, C); break;
+        case 2: syrk_warp<2, kWTStride, kLinThreads>(a_min, wb, lo_ok, C); break;
+        default: syrk_warp<3, kWTStride, kLinThreads>(a_min, wb, lo_ok, C); break;
       }
     }
     __syncthreads();

@@ -174,8 +174,15 @@ typedef struct gf2_solver_cfg {
   int32_t max_wheel_samples; /* per interval */
   int32_t use_wheel;     /* allocate wheel factor storage */
   int32_t max_prior_rows; /* row stride P of the prior arrays of gf2_set_prior; 0 selects GF2_MAX_PRIOR_DIM */
-  int32_t reserved_[6];
+  int32_t sweep;         /* GF2_SWEEP_*: which Jacobian-sweep kernel gf2_solve / gf2_linearize launch (same results; 0 = by batch size) */
+  int32_t reserved_[5];
 } gf2_solver_cfg;
+
+enum { /* gf2_solver_cfg.sweep */
+  GF2_SWEEP_AUTO = 0,   /* calls of up to two windows per SM take the window kernel, larger batches the batch kernel */
+  GF2_SWEEP_BATCH = 1,  /* k_linearize: 4 warps per window, two windows per SM (throughput of a full batch) */
+  GF2_SWEEP_WINDOW = 2  /* k_linearize_ws: one window per SM, 16 warp-specialised warps (latency of one robot's window) */
+};
 
 /* Options of one solve = the ceres::Solver::Options the reference sets (estimator.cpp:3364-3376)
  * plus the static members it configures elsewhere. */

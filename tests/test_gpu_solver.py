@@ -21,8 +21,11 @@ def _copy(w):
     return {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in w.items()}
 
 
-def _solver(gf2, w, n):
-    return gf2.Solver(n, w["n_frames"], w["max_landmarks"], w["max_obs"], max_imu_samples=w["n_imu_samples"])
+def _solver(gf2, w, n, sweep=0):
+    return gf2.Solver(n, w["n_frames"], w["max_landmarks"], w["max_obs"], max_imu_samples=w["n_imu_samples"], sweep=sweep)
+
+
+SWEEPS = [1, 2]   # gf2_solver_cfg.sweep: GF2_SWEEP_BATCH (k_linearize), GF2_SWEEP_WINDOW (k_linearize_ws); AUTO picks by batch size
 
 
 def test_device_preintegration_matches_oracle(gf2, oracle, synth):
@@ -43,11 +46,12 @@ def test_device_preintegration_matches_oracle(gf2, oracle, synth):
     s.close()
 
 
+@pytest.mark.parametrize("sweep", SWEEPS)
 @pytest.mark.parametrize("nl,prior,sorted_lm", [(200, "anchor", True), (1000, "anchor", True), (300, "dense", True), (257, "anchor", False)])
-def test_linearize_matches_oracle(gf2, oracle, synth, nl, prior, sorted_lm):
+def test_linearize_matches_oracle(gf2, oracle, synth, nl, prior, sorted_lm, sweep):
     w = synth.make_windows(2, n_landmarks=nl, prior=prior, sorted_landmarks=sorted_lm)
     oracle.imu_preintegrate(w)
-    s = _solver(gf2, w, 2)
+    s = _solver(gf2, w, 2, sweep)
     s.upload(w, preintegrate="records")
     opts = gf2.abi.default_opts()
     S, g, cost = s.linearize(opts, 2)
@@ -61,12 +65,13 @@ def test_linearize_matches_oracle(gf2, oracle, synth, nl, prior, sorted_lm):
     s.close()
 
 
+@pytest.mark.parametrize("sweep", SWEEPS)
 @pytest.mark.parametrize("nl,prior", [(200, "anchor"), (1000, "anchor"), (300, "dense")])
-def test_solve_matches_oracle(gf2, oracle, synth, nl, prior):
+def test_solve_matches_oracle(gf2, oracle, synth, nl, prior, sweep):
     n = 3
     w = synth.make_windows(n, n_landmarks=nl, prior=prior)
     oracle.imu_preintegrate(w)
-    s = _solver(gf2, w, n)
+    s = _solver(gf2, w, n, sweep)
     s.upload(w, preintegrate="records")
     opts = gf2.abi.default_opts()
     summ = s.solve(opts, n)
@@ -91,20 +96,21 @@ def test_solve_matches_oracle(gf2, oracle, synth, nl, prior):
     s.close()
 
 
-def _solver4(gf2, w, n):
+def _solver4(gf2, w, n, sweep=0):
     return gf2.Solver(n, w["n_frames"], w["max_landmarks"], w["max_obs"], max_planes=w["max_planes"], max_imu_samples=w["n_imu_samples"],
-                      use_wheel=bool(w.get("use_wheel")))
+                      use_wheel=bool(w.get("use_wheel")), sweep=sweep)
 
 
+@pytest.mark.parametrize("sweep", SWEEPS)
 @pytest.mark.parametrize("nl,planes,wheel", [(300, 1000, True), (1000, 5000, True), (200, 0, True), (200, 777, False)])
-def test_config4_wheel_and_lidar_planes_match_oracle(gf2, oracle, synth, nl, planes, wheel):
+def test_config4_wheel_and_lidar_planes_match_oracle(gf2, oracle, synth, nl, planes, wheel, sweep):
     """BASELINE.json config 4 composition: visual + IMU + WheelFactor + LidarPlaneNormFactor on the window poses."""
     n = 2
     w = synth.make_windows(n, config_id=4, n_landmarks=nl, wheel=wheel, n_planes=planes)
     oracle.imu_preintegrate(w)
     if wheel:
         oracle.wheel_preintegrate(w)
-    s = _solver4(gf2, w, n)
+    s = _solver4(gf2, w, n, sweep)
     s.upload(w, preintegrate="records")
     opts = gf2.abi.default_opts()
     S, g, cost = s.linearize(opts, n)
@@ -403,7 +409,10 @@ def test_prior_with_free_wheel_extrinsic_chain(gf2, oracle, synth):
     start = w2["ex_pose_wheel"].copy()
     so = oracle.solve_batch(w2, opts)
     assert (summ["iterations"] == so["iterations"]).all()
-    assert (np.abs(summ["final_cost"] - so["final_cost"]) <= 1e-6 * so["final_cost"]).all()
+    # solve -> marginalize -> solve with a free, weakly observable extrinsic (cond(S) ~ 1e14): summation-order differences of 1e-16 in the
+    # first sweep grow to ~2e-6 of the final cost of the SECOND solve (measured: 2e-7 with k_linearize, 1.8e-6 with k_linearize_ws, whose
+    # tiles add the landmarks in another order); the single-solve tests above keep the 1e-6 bound
+    assert (np.abs(summ["final_cost"] - so["final_cost"]) <= 1e-5 * so["final_cost"]).all()
     scale = np.abs(w2["para_pose"]).max()
     assert np.abs(got["para_pose"] - w2["para_pose"]).max() <= 1e-4 * scale
     moved = np.abs(w2["ex_pose_wheel"] - start).max()
@@ -411,15 +420,16 @@ def test_prior_with_free_wheel_extrinsic_chain(gf2, oracle, synth):
     s.close()
 
 
+@pytest.mark.parametrize("sweep", SWEEPS)
 @pytest.mark.parametrize("nl,planes,ct_fraction", [(300, 1000, 0.5), (1000, 5000, 1.0), (200, 333, 0.3)])
-def test_ct_lidar_plane_factors_match_oracle(gf2, oracle, synth, nl, planes, ct_fraction):
+def test_ct_lidar_plane_factors_match_oracle(gf2, oracle, synth, nl, planes, ct_fraction, sweep):
     """CTLidarPlaneNormFactor (LIO/liw/lidarFactor.cpp:52-123, the factor of icpmodel: CT_POINT_TO_PLANE) in the sweep: begin / end pose =
     window poses f / f + 1, alpha_time per plane; mixed with LidarPlaneNormFactor records in the same window."""
     n = 2
     w = synth.make_windows(n, config_id=4, n_landmarks=nl, wheel=True, n_planes=planes, ct_fraction=ct_fraction)
     assert 0 < int(w["planes"]["ct"].sum()) and (w["planes"]["frame"][w["planes"]["ct"] == 1] < 10).all()
     oracle.imu_preintegrate(w); oracle.wheel_preintegrate(w)
-    s = _solver4(gf2, w, n)
+    s = _solver4(gf2, w, n, sweep)
     s.upload(w, preintegrate="records")
     opts = gf2.abi.default_opts()
     S, g, cost = s.linearize(opts, n)
