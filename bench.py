@@ -561,6 +561,28 @@ def run_config4(gf2, synth, torch, dist, rank, world, local, B, steps, warmup):
     return line
 
 
+def run_single_window(gf2, synth, device, reps=12):
+    """Latency of ONE window per call (one robot): the 8-iteration solve with the sweep kernel forced to the batch kernel (k_linearize: 4 warps per
+    window) and to the window kernel (k_linearize_ws: 16 warp-specialised warps per window, what GF2_SWEEP_AUTO picks at this size)."""
+    abi = gf2.abi
+    out = {"metric": "ms per 8-iteration solve of one window (device time, CUDA events), by sweep kernel", "unit": "ms"}
+    for nl in (1000, 150):
+        w = synth.make_windows(1, n_landmarks=nl, prior_stride=PRIOR_STRIDE)
+        rec = {}
+        for name, sweep in (("batch_kernel", abi.SWEEP_BATCH), ("window_kernel", abi.SWEEP_WINDOW)):
+            s = gf2.Solver(1, N_FRAMES, w["max_landmarks"], w["max_obs"], max_imu_samples=w["n_imu_samples"], device=device, max_prior_rows=PRIOR_STRIDE, sweep=sweep)
+            s.upload(w, preintegrate="device"); s.snapshot(1)
+            opts = abi.default_opts()
+            tot, lin = [], []
+            for _ in range(reps):
+                s.restore(1); s.solve(opts, 1)
+                t = s.last_timing(); tot.append(t["total_ms"]); lin.append(t["linearize_ms"] / max(t["linearize_launches"], 1))
+            s.close()
+            rec[name] = {"solve_ms": float(np.median(tot[2:])), "sweep_ms_per_iteration": float(np.median(lin[2:]))}
+        out[f"{nl}_landmarks"] = rec
+    return out
+
+
 def run_reference(args, rank, world):
     """Restated-reference CPU baseline: oracle solve (same algorithm as ceres::Solve with the reference's options) on
     all host threads, each step a bounded sample of the same workload."""
@@ -775,6 +797,7 @@ def main():
         replay_line = run_replay(gf2, synth, with_cpu=not args.no_cpu_baseline)
         replay_line["rgbd"] = run_replay_rgbd(gf2, synth)
         replay_line["full_fusion"] = run_replay_full(gf2, synth)
+        replay_line["single_window"] = run_single_window(gf2, synth, local)
 
     if rank == 0:
         peaks, which = measured_peaks()

@@ -42,7 +42,7 @@ class SolveOpts(C.Structure):
     _fields_ = [("max_iterations", C.c_int32), ("const_mask", C.c_uint32), ("huber_delta", C.c_double),
                 ("sqrt_info_px", C.c_double), ("g_norm", C.c_double), ("lidar_sqrt_info", C.c_double),
                 ("max_time_s", C.c_double), ("initial_radius", C.c_double), ("function_tolerance", C.c_double),
-                ("gradient_tolerance", C.c_double), ("parameter_tolerance", C.c_double), ("wheel_ext_const_components", C.c_uint32), ("pad_", C.c_uint32),
+                ("gradient_tolerance", C.c_double), ("parameter_tolerance", C.c_double), ("wheel_ext_const_components", C.c_uint32), ("marg_eig", C.c_uint32),
                 ("reserved_", C.c_double * 5)]
 
 

@@ -816,7 +816,7 @@ int gf2_marginalize_async(gf2_solver* h, int first, int n, int32_t mode, const g
     GF2_CUDA(cudaMallocHost((void**)&h->h_marg, sizeof(int32_t) * 2 * B));
   }
   MargP mp = h->marg;
-  mp.mode = mode;
+  mp.mode = mode; mp.eig = opts->marg_eig ? 1 : 0;
   mp.out_rows = const_cast<int32_t*>(h->kp.prior_rows); mp.out_nblocks = const_cast<int32_t*>(h->kp.prior_nblocks);
   mp.out_J0 = const_cast<double*>(h->kp.prior_J0); mp.out_r0 = const_cast<double*>(h->kp.prior_r0);
   mp.out_blocks = const_cast<gf2_prior_block*>(h->kp.prior_blocks);

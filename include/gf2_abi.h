@@ -205,7 +205,10 @@ typedef struct gf2_solve_opts {
    * system (the reference's ComputeJacobian is [I6; 0] regardless). extrinsic_type_wheel 0 (ALL) = 0, 1 (TRANSLATION) = 0x38,
    * 2 (ROTATION) = 0x07, 3 (NO_Z) = 0x04, 4 (NO_ROTATION_NO_Z) = 0x3c. */
   uint32_t wheel_ext_const_components;
-  uint32_t pad_;
+  /* gf2_marginalize: how the kept system A is factorised into the prior (linearized_jacobians, linearized_residuals), marginalization_factor.cpp:293-303.
+   * 0 = rank-revealing Cholesky, pivots <= eps dropped (J0 = L^T P^T; same J0^T J0 and J0^T r0 as the reference up to O(eps) = 1e-8 absolute);
+   * 1 = the reference's eigen-decomposition with its eps truncation, literally (a 12-sweep Jacobi solver: ~20x slower). */
+  uint32_t marg_eig;
   double reserved_[5];
 } gf2_solve_opts;
 

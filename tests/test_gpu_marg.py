@@ -17,6 +17,12 @@ def synth(gf2):
     return importlib.import_module("gf2_b200.synth")
 
 
+@pytest.fixture(params=[0, 1], ids=["cholesky", "eigen"])
+def marg_eig(request):
+    """gf2_solve_opts.marg_eig: 0 = rank-revealing Cholesky factor of the kept system (default), 1 = the reference's eigen-decomposition, literally."""
+    return request.param
+
+
 def _prior_of(pr, i):
     n = int(pr["prior_rows"][i]); nb = int(pr["prior_nblocks"][i])
     return {"n": n, "J0": pr["prior_J0"][i, :n, :n], "r0": pr["prior_r0"][i, :n], "blocks": pr["prior_blocks"][i, :nb]}
@@ -41,11 +47,11 @@ def _check_prior(oracle, got, ref, F):
 
 
 @pytest.mark.parametrize("prior,nl", [("anchor", 200), ("dense", 1000)])
-def test_margin_old_matches_oracle(gf2, oracle, synth, prior, nl):
+def test_margin_old_matches_oracle(gf2, oracle, synth, prior, nl, marg_eig):
     n = 5
     w = synth.make_windows(n, n_landmarks=nl, prior=prior)
     oracle.imu_preintegrate(w)
-    opts = gf2.abi.default_opts()
+    opts = gf2.abi.default_opts(); opts.marg_eig = marg_eig
     s = gf2.Solver(n, w["n_frames"], w["max_landmarks"], w["max_obs"])
     s.upload(w, preintegrate="records")
     s.solve(opts, n)
@@ -62,7 +68,7 @@ def test_margin_old_matches_oracle(gf2, oracle, synth, prior, nl):
     s.close()
 
 
-def test_margin_old_with_wheel_matches_oracle(gf2, oracle, synth):
+def test_margin_old_with_wheel_matches_oracle(gf2, oracle, synth, marg_eig):
     """config 4 composition: IMU + wheel + projection (+ planes, which never touch frame 0's dropped blocks... they do touch
     pose 0 but the reference does not marginalize LiDAR factors in the VINS window) -> the wheel factor's calibration blocks
     (body_T_wheel, sx, sy, sw, td_wheel) become kept blocks of the prior."""
@@ -70,7 +76,7 @@ def test_margin_old_with_wheel_matches_oracle(gf2, oracle, synth):
     w = synth.make_windows(n, config_id=4, n_landmarks=300, wheel=True, prior="dense")
     oracle.imu_preintegrate(w); oracle.wheel_preintegrate(w)
     w["sxsysw"][1] = [1.01, 0.99, 1.02]; w["td_wheel"][2] = 0.004
-    opts = gf2.abi.default_opts()
+    opts = gf2.abi.default_opts(); opts.marg_eig = marg_eig
     s = gf2.Solver(n, w["n_frames"], w["max_landmarks"], w["max_obs"], use_wheel=True)
     s.upload(w, preintegrate="records")
     s.solve(opts, n)
@@ -86,12 +92,12 @@ def test_margin_old_with_wheel_matches_oracle(gf2, oracle, synth):
     s.close()
 
 
-def test_prior_chain_stays_resident(gf2, oracle, synth):
+def test_prior_chain_stays_resident(gf2, oracle, synth, marg_eig):
     """solve -> marginalize -> (slide) -> solve again with the device-resident prior == oracle doing the same on the host."""
     n = 3
     w = synth.make_windows(n, n_landmarks=300, prior="anchor")
     oracle.imu_preintegrate(w)
-    opts = gf2.abi.default_opts()
+    opts = gf2.abi.default_opts(); opts.marg_eig = marg_eig
     s = gf2.Solver(n, w["n_frames"], w["max_landmarks"], w["max_obs"])
     s.upload(w, preintegrate="records")
     s.solve(opts, n)
@@ -119,10 +125,10 @@ def test_prior_chain_stays_resident(gf2, oracle, synth):
     s.close()
 
 
-def test_margin_second_new_matches_oracle(gf2, oracle, synth):
+def test_margin_second_new_matches_oracle(gf2, oracle, synth, marg_eig):
     n = 3
     w = synth.make_windows(n, n_landmarks=100, prior="dense")
-    opts = gf2.abi.default_opts()
+    opts = gf2.abi.default_opts(); opts.marg_eig = marg_eig
     oracle.imu_preintegrate(w)
     w["para_pose"][:, :, :3] += 0.01
     s = gf2.Solver(n, w["n_frames"], w["max_landmarks"], w["max_obs"])
@@ -145,12 +151,12 @@ def test_margin_second_new_matches_oracle(gf2, oracle, synth):
     s.close()
 
 
-def test_margin_old_edge_cases(gf2, oracle, synth):
+def test_margin_old_edge_cases(gf2, oracle, synth, marg_eig):
     """No landmark hosted in frame 0; no prior; no IMU -> m == 0 -> invalid prior (valid = false, marginalization_factor.cpp:205)."""
     n = 2
     w = synth.make_windows(n, n_landmarks=120, prior="anchor")
     oracle.imu_preintegrate(w)
-    opts = gf2.abi.default_opts()
+    opts = gf2.abi.default_opts(); opts.marg_eig = marg_eig
     # drop the frame-0 landmarks by compacting the landmark arrays
     for i in range(n):
         nl = int(w["n_landmarks"][i]); sel = np.where(w["start_frame"][i, :nl] != 0)[0]
@@ -206,7 +212,7 @@ def test_margin_old_edge_cases(gf2, oracle, synth):
     s.close()
 
 
-def test_margin_old_truncates_uninformative_landmarks_like_the_pseudo_inverse(gf2, oracle, synth):
+def test_margin_old_truncates_uninformative_landmarks_like_the_pseudo_inverse(gf2, oracle, synth, marg_eig):
     """A robot turning on the spot: zero baseline, d r / d lambda = 0 for every landmark, so their eigenvalues of Amm are below eps = 1e-8 and
     MarginalizationInfo::marginalize() truncates them in its pseudo-inverse (marginalization_factor.cpp:278-283). The device drops exactly
     those landmarks' Schur terms (status 0, not GF2_MARG_DEGENERATE) and must agree with the restated eigen-decomposition pseudo-inverse.
@@ -216,7 +222,7 @@ def test_margin_old_truncates_uninformative_landmarks_like_the_pseudo_inverse(gf
     oracle.imu_preintegrate(w)
     w["para_pose"][0, :, :3] = w["para_pose"][0, 0, :3]   # all camera centres coincide: no translation between the frames ...
     w["ex_pose"][0, :3] = 0.0                             # ... and no lever arm
-    opts = gf2.abi.default_opts()
+    opts = gf2.abi.default_opts(); opts.marg_eig = marg_eig
     s = gf2.Solver(n, w["n_frames"], w["max_landmarks"], w["max_obs"])
     s.upload(w, preintegrate="records")
     status, m = s.marginalize(opts, mode=0)
