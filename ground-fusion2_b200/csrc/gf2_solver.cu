@@ -20,9 +20,11 @@ namespace gf2 {
 // ------------------------------------------------------------------------------------------------ preintegration
 // IntegrationBase::push_back chain (VE/factor/integration_base.h:39-167): mid-point integration with the 15x15 jacobian
 // and covariance propagation  jacobian = F jacobian,  covariance = F covariance F^T + V noise V^T.
-// One warp per interval. Lane c (< 15) keeps column c of the jacobian and of the covariance in registers; F is block
-// sparse (identity + seven 3x3 blocks), so F x is eight 3x3 mat-vecs per column; F C F^T = F (F C)^T uses one transpose
-// through shared memory; V noise V^T comes from the 15x18 V staged in shared memory.
+// One HALF-warp per interval (two intervals per warp: the per-sample quantities every lane of an interval forms - mid-point integration,
+// the F and V blocks - cost a warp instruction each whether 16 or 32 lanes want them, so the second half-warp's interval rides for free;
+// round 2: 3.0 -> 1.6 ms per 40,960 intervals). Lane c (< 15) of the half keeps column c of the jacobian and of the covariance in
+// registers; F is block sparse (identity + seven 3x3 blocks), so F x is eight 3x3 mat-vecs per column; F C F^T = F (F C)^T uses one
+// transpose through shared memory; V noise V^T comes from the 15x18 V staged in shared memory.
 struct FBlocks { M3 f01, f03, f04, f11, f21, f23, f24; double dt; };
 
 __device__ __forceinline__ void apply_F(const FBlocks& F, double (&x)[15]) {
@@ -38,11 +40,13 @@ constexpr int kPreWarps = 4;
 __global__ void __launch_bounds__(32 * kPreWarps) k_imu_preintegrate(int n_intervals, int max_samples, const gf2_imu_sample* samples, const int32_t* n_samples,
                                                                       const double* first, const double* lin_bias, double acc_n, double gyr_n, double acc_w, double gyr_w,
                                                                       gf2_imu_preint* out) {
-  __shared__ double T[kPreWarps][15 * 16];
-  __shared__ double Vs[kPreWarps][15 * 18];
-  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int idx = blockIdx.x * kPreWarps + wid;
-  if (idx >= n_intervals) return;
+  __shared__ double T[2 * kPreWarps][15 * 16];
+  __shared__ double Vs[2 * kPreWarps][15 * 18];
+  const int hw = threadIdx.x >> 4, lane = threadIdx.x & 15;   // half-warp of the CTA, lane inside the half ("lane" below = column index)
+  const int idx_raw = blockIdx.x * 2 * kPreWarps + hw;
+  if (blockIdx.x * 2 * kPreWarps + (hw & ~1) >= n_intervals) return;   // the whole warp is past the end
+  const bool live = idx_raw < n_intervals;                              // the odd half of the last warp may have no interval: it shadows its neighbour
+  const int idx = live ? idx_raw : idx_raw - 1;
   const gf2_imu_sample* smp = samples + (size_t)idx * max_samples;
   V3 acc_0 = ld3(first + 6 * idx), gyr_0 = ld3(first + 6 * idx + 3);
   const V3 ba = ld3(lin_bias + 6 * idx), bg = ld3(lin_bias + 6 * idx + 3);
@@ -52,9 +56,12 @@ __global__ void __launch_bounds__(32 * kPreWarps) k_imu_preintegrate(int n_inter
   for (int r = 0; r < 15; r++) { jc[r] = (r == lane) ? 1.0 : 0.0; cc[r] = 0.0; }
   double sum_dt = 0;
   const double nz[6] = {acc_n * acc_n, gyr_n * gyr_n, acc_n * acc_n, gyr_n * gyr_n, acc_w * acc_w, gyr_w * gyr_w};
-  double* Tw = T[wid]; double* Vw = Vs[wid];
+  double* Tw = T[hw]; double* Vw = Vs[hw];
   const int ns = n_samples[idx];
-  for (int s = 0; s < ns; s++) {
+  const int ns_warp = max(ns, __shfl_xor_sync(0xffffffffu, ns, 16));   // the two halves step together; a half that has run out of samples idles
+  for (int s = 0; s < ns_warp; s++) {
+    const bool on = s < ns;
+    if (!on) { __syncwarp(); __syncwarp(); __syncwarp(); continue; }   // (keeps the warp-level barriers below matched)
     const double dt = smp[s].dt;
     const V3 acc_1 = ld3(smp[s].acc), gyr_1 = ld3(smp[s].gyr);
     // midPointIntegration, integration_base.h:72-81 (every lane, uniform)
@@ -82,7 +89,7 @@ __global__ void __launch_bounds__(32 * kPreWarps) k_imu_preintegrate(int n_inter
     F.f24 = scale(rRa1, -0.5 * dt * -dt);
     // V staged in shared memory (lanes 0..8 write the nine distinct 3x3 blocks' rows): [15][18]
     __syncwarp();
-    for (int i = lane; i < 270; i += 32) Vw[i] = 0.0;
+    for (int i = lane; i < 270; i += 16) Vw[i] = 0.0;
     __syncwarp();
     if (lane == 0) {
       put3(Vw, 18, 0, 0, dR, 0.25 * dt * dt);
@@ -121,6 +128,7 @@ __global__ void __launch_bounds__(32 * kPreWarps) k_imu_preintegrate(int n_inter
     dp = rp; dv = rv; dq = qnormalized(rq);
     sum_dt += dt; acc_0 = acc_1; gyr_0 = gyr_1;
   }
+  if (!live) return;
   gf2_imu_preint& o = out[idx];
   if (lane == 0) {
     o.sum_dt = sum_dt;
@@ -465,7 +473,7 @@ int gf2_imu_preintegrate(gf2_solver* h, int first, int n, const gf2_imu_sample* 
   H2D(h->d_imu_first + off * 6, first_sample, sizeof(double) * n * Fm1 * 6);
   H2D(h->d_imu_bias + off * 6, lin_bias, sizeof(double) * n * Fm1 * 6);
   const int total = n * Fm1;
-  k_imu_preintegrate<<<(total + kPreWarps - 1) / kPreWarps, 32 * kPreWarps, 0, h->stream>>>(total, ms, h->d_imu_samples + off * ms, h->d_imu_n + off, h->d_imu_first + off * 6,
+  k_imu_preintegrate<<<(total + 2 * kPreWarps - 1) / (2 * kPreWarps), 32 * kPreWarps, 0, h->stream>>>(total, ms, h->d_imu_samples + off * ms, h->d_imu_n + off, h->d_imu_first + off * 6,
                                                                h->d_imu_bias + off * 6, noise[0], noise[1], noise[2], noise[3], h->d_imu + off);
   GF2_CUDA(cudaGetLastError());
   h->has_imu = true;
@@ -477,7 +485,7 @@ int gf2_imu_preintegrate_resident(gf2_solver* h, int first, int n, const double 
   const int ms = h->cfg.max_imu_samples, Fm1 = h->kp.F - 1;
   if (ms <= 0) return gf2::fail(GF2_ERR_INVALID, "solver created with max_imu_samples = 0");
   const size_t off = (size_t)first * Fm1; const int total = n * Fm1;
-  k_imu_preintegrate<<<(total + kPreWarps - 1) / kPreWarps, 32 * kPreWarps, 0, h->stream>>>(total, ms, h->d_imu_samples + off * ms, h->d_imu_n + off, h->d_imu_first + off * 6,
+  k_imu_preintegrate<<<(total + 2 * kPreWarps - 1) / (2 * kPreWarps), 32 * kPreWarps, 0, h->stream>>>(total, ms, h->d_imu_samples + off * ms, h->d_imu_n + off, h->d_imu_first + off * 6,
                                                                h->d_imu_bias + off * 6, noise[0], noise[1], noise[2], noise[3], h->d_imu + off);
   GF2_CUDA(cudaGetLastError());
   h->has_imu = true;
