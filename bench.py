@@ -35,6 +35,15 @@ WORKLOAD = "W10-F1000 (11 frames, 1000 landmarks, 6500 projection + 10 IMU facto
 BYTES_SWEEP = N_OBS * 20 + N_LM * 32 + N_FRAMES * 136 + 64 + N_IMU * 1456 + (D_RED * (D_RED + 1) // 2 + D_RED) * 8  # = 289,000
 
 
+FP64_SM_CYCLES_PER_WINDOW = (39000 * 2 + 9500 * 16) / 4   # k_linearize: fp64 datapath time of one W10-F1000 window
+
+
+def fp64_bound_ms(B, clocks, n_sm=148):
+    """k_linearize's launch time if the SMs' fp64 datapath never idled: windows / SMs x cycles per window / SM clock."""
+    mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    return 1e3 * B / n_sm * FP64_SM_CYCLES_PER_WINDOW / (mhz * 1e6)
+
+
 def ncu_summary():
     """Per-kernel numbers of the latest `ncu --set full` capture of this build, written by scripts/ncu_summarize.py into profiles/ (dated, with
     the capture's command): DRAM bytes per launch, fp64 tensor sub-pipe activity, warps active. None when no summary is committed."""
@@ -518,7 +527,12 @@ def run_config4(gf2, synth, torch, dist, rank, world, local, B, steps, warmup):
         if rank == 0:
             uid.copy_(torch.from_numpy(gf2.Solver.comm_unique_id()).cuda())
         dist.broadcast(uid, 0)
-        s.comm_init(rank, world, uid.cpu().numpy())
+        # NCCL prints its version banner on stdout at the first communicator it creates; stdout carries the one JSON line, so send the banner to stderr
+        sys.stdout.flush(); saved = os.dup(1); os.dup2(2, 1)
+        try:
+            s.comm_init(rank, world, uid.cpu().numpy())
+        finally:
+            os.dup2(saved, 1); os.close(saved)
     s.upload(mine, preintegrate="device"); s.snapshot(B)
     for _ in range(warmup):
         s.restore(B); s.solve(opts, B)
@@ -821,8 +835,14 @@ def main():
                          "frac": achieved / peaks["hbm_gbs"], "traffic": (traffic * B if traffic else None),
                          "traffic_source": (f"profiles/ncu_summary_r2.json ({ncu.get('captured')}, {ncu.get('command')}): dram__bytes_read.sum + dram__bytes_write.sum of one k_linearize launch per window x windows per launch" if traffic else None),
                          "peak_source": which, "algorithmic_bytes_per_launch": BYTES_SWEEP * B, "avg_launch_ms": lin_avg_ms,
-                         "fp64_pipe": {"note": "DFMA and the fp64 mma share one datapath on this part (profiles/ubench_fp64_pipes_r2.txt: 12.1 + 24.3 = 36.4 TFLOP/s mixed); the kernel's real bound is its total fp64 work",
-                                       "dmma_pipe_pct_ncu": klin.get("dmma_pipe_pct"), "fp64_fma_pipe_pct_ncu": klin.get("fp64_pipe_pct"), "warps_active_pct_ncu": klin.get("warps_active_pct")}},
+                         "fp64_pipe": {"note": "DFMA and the fp64 mma share one datapath on this part (profiles/ubench_fp64_pipes_r2.txt: 12.1 + 24.3 = 36.4 TFLOP/s mixed; "
+                                               "profiles/ubench_fp64_latency_r2.txt: a DFMA holds a sub-partition's share for 2 cycles, an m8n8k4 DMMA for 16); the kernel's real bound is its total fp64 work",
+                                       "dmma_pipe_pct_ncu": klin.get("dmma_pipe_pct"), "fp64_fma_pipe_pct_ncu": klin.get("fp64_pipe_pct"), "warps_active_pct_ncu": klin.get("warps_active_pct"),
+                                       # per window (profiles/ncu_opcodes_k_linearize_r1.txt, same arithmetic): 39 k DP warp instructions x 2 + 9.5 k DMMA x 16 sub-partition cycles, 4 sub-partitions per SM
+                                       "datapath_sm_cycles_per_window": FP64_SM_CYCLES_PER_WINDOW,
+                                       "datapath_bound_ms_per_launch": fp64_bound_ms(B, clocks),
+                                       "datapath_utilisation": (fp64_bound_ms(B, clocks) / lin_avg_ms) if fp64_bound_ms(B, clocks) else None,
+                                       "hbm_frac_at_full_datapath": (BYTES_SWEEP * B / (fp64_bound_ms(B, clocks) / 1e3) / 1e9 / peaks["hbm_gbs"]) if fp64_bound_ms(B, clocks) else None}},
             "reduced_solve": {"kernels": "k_nonvis + k_solve2", "avg_ms_per_iteration": solve_ms / n_lin, "bound": "serial pivot chain (latency), not the tensor pipe",
                               "dmma_pipe_pct_ncu": ((ncu.get("kernels") or {}).get("k_solve2") or {}).get("dmma_pipe_pct"), "source": "profiles/ncu_summary_r2.json"},
             ("config4_sharded" if world > 1 else "config4"): cfg4,
