@@ -626,7 +626,8 @@ static int fill_kp(gf2_solver* h, const gf2_solve_opts* o, KP& k) {
   k.wcal = 0;
   if (h->cfg.use_wheel && h->has_wheel) k.wcal = ((o->const_mask & GF2_CONST_EX_WHEEL) ? 0 : 1) | ((o->const_mask & GF2_CONST_WHEEL_INTRINSIC) ? 0 : 2) | ((o->const_mask & GF2_CONST_TD_WHEEL) ? 0 : 4);
   k.wsub = o->wheel_ext_const_components & 0x3fu;
-  if (k.wcal && h->nccl_comm) return gf2::fail(GF2_ERR_UNSUPPORTED, "free wheel calibration blocks in factor-sharded mode are not built");
+  // (factor-sharded mode: the calibration block row is fed by the wheel factors and the prior only, which every rank holds; it rides in the
+  //  all-gathered steps [z | u] of stride Ds like the frame rows)
   k.const_mask = o->const_mask; k.huber = o->huber_delta; k.sqrt_info_px = o->sqrt_info_px; k.g_norm = o->g_norm; k.lidar_sqrt_info = o->lidar_sqrt_info;
   k.ftol = o->function_tolerance > 0 ? o->function_tolerance : 1e-6;
   k.gtol = o->gradient_tolerance > 0 ? o->gradient_tolerance : 1e-10;

@@ -12,6 +12,7 @@ from gf2_loader import load
 
 ap = argparse.ArgumentParser(); ap.add_argument("--windows", type=int, default=64); ap.add_argument("--landmarks", type=int, default=1000)
 ap.add_argument("--planes", type=int, default=5000); ap.add_argument("--steps", type=int, default=3)
+ap.add_argument("--free-wheel", action="store_true", help="body_T_wheel free (estimate_wheel_extrinsic: 1): one more block row of the reduced system")
 args = ap.parse_args()
 rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
@@ -33,6 +34,8 @@ if rank == 0:
 dist.broadcast(uid, 0)
 s.comm_init(rank, world, uid.cpu().numpy())
 opts = gf2.abi.default_opts()
+if args.free_wheel:
+    opts.const_mask = gf2.abi.CONST_EX_POSE | gf2.abi.CONST_TD | gf2.abi.CONST_WHEEL_INTRINSIC | gf2.abi.CONST_TD_WHEEL
 s.upload(mine, preintegrate="device"); s.snapshot(B)
 summ = s.solve(opts, B)   # warm-up
 times = []
@@ -56,7 +59,8 @@ if rank == 0:
            "sharded_ms": 1e3 * float(tt.item()), "single_gpu_ms": 1e3 * min(t1), "nccl_ms_rank0": s.last_timing()["nccl_ms"],
            "sharded_solves_per_s": B / float(tt.item()), "single_solves_per_s": B / min(t1),
            "pose_diff": float(np.abs(st["para_pose"] - rst["para_pose"]).max()), "speedbias_diff": float(np.abs(st["para_speedbias"] - rst["para_speedbias"]).max()),
-           "inv_depth_diff": float(np.abs(lam_full - rlam).max()),
+           "inv_depth_diff": float(np.abs(lam_full - rlam).max()), "free_wheel": bool(args.free_wheel),
+           "ex_wheel_diff": float(np.abs(st["ex_pose_wheel"] - rst["ex_pose_wheel"]).max()), "ex_wheel_moved": float(np.abs(rst["ex_pose_wheel"] - w["ex_pose_wheel"]).max()),
            "iterations_equal": bool((summ["iterations"] == rs["iterations"]).all()), "termination_equal": bool((summ["termination"] == rs["termination"]).all()),
            "final_cost_rel_diff": float((np.abs(summ["final_cost"] - rs["final_cost"]) / rs["final_cost"]).max())}
     print(json.dumps(out))

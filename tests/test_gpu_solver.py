@@ -262,8 +262,10 @@ def test_factor_shards_add_up_on_one_gpu(gf2, synth):
     assert np.abs(cs - c).max() <= 1e-10 * np.abs(c).max()
 
 
-def test_factor_sharded_two_gpus_match_single_gpu(gf2):
-    """landmarks/planes sharded over 2 GPUs with one NCCL all-reduce per linearisation == single-GPU solve.
+@pytest.mark.parametrize("free_wheel", [False, True])
+def test_factor_sharded_two_gpus_match_single_gpu(gf2, free_wheel):
+    """landmarks/planes sharded over 2 GPUs with one NCCL reduce-scatter per linearisation == single-GPU solve, with the wheel
+    extrinsic constant and free (the calibration block row rides in the all-gathered steps).
     Needs 2 visible GPUs (skipped on the 1-GPU box; run with `gpurun --gpus 2 -- python -m pytest tests -m gpu -k sharded`)."""
     import json as _json
     import os
@@ -274,11 +276,13 @@ def test_factor_sharded_two_gpus_match_single_gpu(gf2):
         pytest.skip("needs 2 GPUs")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29531",
-                          os.path.join(root, "scripts", "run_sharded.py"), "--windows", "8", "--landmarks", "400", "--planes", "800", "--steps", "1"],   # wheel factors included (device preintegration)
-                         capture_output=True, text=True, timeout=600)
+                          os.path.join(root, "scripts", "run_sharded.py"), "--windows", "8", "--landmarks", "400", "--planes", "800", "--steps", "1"]   # wheel factors included (device preintegration)
+                         + (["--free-wheel"] if free_wheel else []), capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     out = _json.loads([ln for ln in res.stdout.splitlines() if ln.startswith("{")][-1])
     assert out["iterations_equal"] and out["pose_diff"] < 1e-6
+    if free_wheel:
+        assert out["ex_wheel_moved"] > 0 and out["ex_wheel_diff"] <= 1e-6 * max(out["ex_wheel_moved"], 1e-3)
 
 
 @pytest.mark.gpu
