@@ -106,7 +106,8 @@ struct LinShared {
 };
 constexpr int kSumStride = 32;
 constexpr int kSumsOfs = kNVP * kNVP;  // scratch in WT after the sweep: dense 72x72 Schur tiles, then the per-frame un-rotated sums
-static_assert(kWTRows * kWTStride >= kSumsOfs + kMaxF * kSumStride, "scratch fits in WT");
+constexpr int kTermsOfs = kSumsOfs + kMaxF * kSumStride;   // then the F (F - 1) per-frame-pair terms of those sums
+static_assert(kWTRows * kWTStride >= kTermsOfs + kMaxF * (kMaxF - 1) * 30, "scratch fits in WT");
 
 __device__ __forceinline__ int ublk(int bi, int bj, int F) { return (bi * F - bi * (bi - 1) / 2 + (bj - bi)) * 36; }  // bi <= bj
 __device__ __forceinline__ int pidx(int i, int j, int F) { return i * (2 * F - i - 1) / 2 + (j - i - 1); }             // i < j
@@ -255,6 +256,36 @@ __device__ __forceinline__ void expand_diag_sums(const double* Mom, const FrameC
   } else {
     for (int c = 0; c < 9; c++) out[(grp == 1 ? 12 : 21) + c] = acc.m[c];
   }
+}
+
+// The same sums split by the other frame o, so that the F (F - 1) (frame, other frame) terms spread over the CTA instead of 3 F threads walking
+// F - 1 frame pairs each (those 33 threads were most of the kernel's tail): term of frame o in the un-rotated sums of frame f, all three
+// groups, in the layout of expand_diag_sums (30 doubles). expand_diag_reduce adds the terms of a frame in ascending o, the order of the
+// loop above: the result is the same to the last bit, and does not depend on the number of threads.
+constexpr int kDiagTerm = 30;
+__device__ __forceinline__ void expand_diag_term(const double* Mom, const FrameCtx* fr, int f, int o, int F, double* out /* kDiagTerm */) {
+  const bool irole = f < o;  // f is the host frame of the pair
+  const PairMom q = load_mom(Mom + (irole ? pidx(f, o, F) : pidx(o, f, F)) * kMomStride);
+  M3 pp, pt, tt; V3 gp, gt;
+  if (!irole) { pp = q.M0; gp = mk3(0, 0, 0) - q.h0; gt = q.h1; pt = q.M1; tt = q.M2; }
+  else {
+    const M3 C = skew(mk3(fr[o].P[0] - fr[f].P[0], fr[o].P[1] - fr[f].P[1], fr[o].P[2] - fr[f].P[2]));
+    pp = q.M0; gp = q.h0; gt = mk3(0, 0, 0) - (q.h1 + mulT(C, q.h0));
+    pt = add(q.M1, mul(q.M0, C));
+    const M3 CtM1 = mulT(C, q.M1); tt = add(add(q.M2, CtM1), add(transpose(CtM1), mulT(C, mul(q.M0, C))));
+  }
+  out[0] = pp.m[0]; out[1] = pp.m[1]; out[2] = pp.m[2]; out[3] = pp.m[4]; out[4] = pp.m[5]; out[5] = pp.m[8];
+  out[6] = gp.x; out[7] = gp.y; out[8] = gp.z; out[9] = gt.x; out[10] = gt.y; out[11] = gt.z;
+#pragma unroll
+  for (int c = 0; c < 9; c++) { out[12 + c] = pt.m[c]; out[21 + c] = tt.m[c]; }
+}
+// term index of (f, o), o != f
+__device__ __forceinline__ int diag_term_idx(int f, int o, int F) { return (f * (F - 1) + (o < f ? o : o - 1)) * kDiagTerm; }
+// entry e of the sums of frame f = the terms of all other frames, ascending
+__device__ __forceinline__ double expand_diag_reduce(const double* terms, int f, int e, int F) {
+  double acc = 0.0;
+  for (int o = 0; o < F; o++) if (o != f) acc += terms[diag_term_idx(f, o, F) + e];
+  return acc;
 }
 
 __global__ void __launch_bounds__(kLinThreads, 2) k_linearize(KP p, int w0) {
@@ -491,16 +522,21 @@ __global__ void __launch_bounds__(kLinThreads, 2) k_linearize(KP p, int w0) {
   }
   // frame-pair moments -> off-diagonal blocks (i, j) and the un-rotated per-frame sums
   {
-    const int npairs = F * (F - 1) / 2;
-    double* sums = S.WT + kSumsOfs;
-    for (int q = t; q < 3 * F + 4 * npairs; q += kLinThreads) {
-      if (q < 3 * F) { const int grp = q / F, f = q - grp * F; expand_diag_sums(S.Mom, S.fr, f, F, grp, sums + f * kSumStride); continue; }
-      const int q2 = q - 3 * F, pr = q2 >> 2, sub = q2 & 3;
+    const int npairs = F * (F - 1) / 2, nterms = F * (F - 1);
+    double* terms = S.WT + kTermsOfs;
+    for (int q = t; q < nterms + 4 * npairs; q += kLinThreads) {
+      if (q < nterms) { const int f = q / (F - 1), r = q - f * (F - 1), o = r < f ? r : r + 1; expand_diag_term(S.Mom, S.fr, f, o, F, terms + diag_term_idx(f, o, F)); continue; }
+      const int q2 = q - nterms, pr = q2 >> 2, sub = q2 & 3;
       int i = 0, rem = pr;
       while (rem >= F - 1 - i) { rem -= F - 1 - i; i++; }
       const int j = i + 1 + rem;
       expand_offdiag(&S.Mom[pr * kMomStride], S.fr[i], S.fr[j], sub, &S.U[ublk(i, j, F)]);
     }
+  }
+  __syncthreads();
+  {
+    double* sums = S.WT + kSumsOfs;
+    for (int q = t; q < F * kDiagTerm; q += kLinThreads) { const int f = q / kDiagTerm, e = q - f * kDiagTerm; sums[f * kSumStride + e] = expand_diag_reduce(S.WT + kTermsOfs, f, e, F); }
   }
   __syncthreads();
   // diagonal blocks (f, f) = [[PP, -PT Rf], [., Rf^T TT Rf]] and the gradient g_f = [GP ; Rf^T GT]

@@ -59,6 +59,7 @@ struct LinShared {
 static_assert(kStages == kPairs, "stage s is producer pair s's");
 static_assert(kStages * kWTRows * kWTStride >= kNVP * kNVP, "dense 72x72 Schur tiles fit in the stage ring");
 static_assert(sizeof(LinShared) <= 227 * 1024, "one CTA per SM");
+static_assert(sizeof(float4) * kPairs * kObsStage >= sizeof(double) * kMaxF * (kMaxF - 1) * kDiagTerm, "the per-frame-pair terms of the tail fit in the observation staging");
 
 // ---- synchronisation primitives (PTX): named barriers between warp groups, mbarriers for the stage ring and the bulk copies
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -340,16 +341,19 @@ __global__ void __launch_bounds__(kLinThreads, 1) k_linearize_ws(KP p, int w0) {
 
     // frame-pair moments -> off-diagonal blocks (i, j) and the un-rotated per-frame sums
     {
-      const int npairs = F * (F - 1) / 2;
-      for (int q = t; q < 3 * F + 4 * npairs; q += kProdThreads) {
-        if (q < 3 * F) { const int grp = q / F, f = q - grp * F; expand_diag_sums(S.Mom, S.fr, f, F, grp, S.sums + f * kSumStride); continue; }
-        const int q2 = q - 3 * F, pq = q2 >> 2, sub = q2 & 3;
+      const int npairs = F * (F - 1) / 2, nterms = F * (F - 1);
+      double* terms = reinterpret_cast<double*>(&S.sobs[0][0]);   // the observation staging is free: every producer is past its last task
+      for (int q = t; q < nterms + 4 * npairs; q += kProdThreads) {
+        if (q < nterms) { const int f = q / (F - 1), r = q - f * (F - 1), o = r < f ? r : r + 1; expand_diag_term(S.Mom, S.fr, f, o, F, terms + diag_term_idx(f, o, F)); continue; }
+        const int q2 = q - nterms, pq = q2 >> 2, sub = q2 & 3;
         int i = 0, rem = pq;
         while (rem >= F - 1 - i) { rem -= F - 1 - i; i++; }
         const int j = i + 1 + rem;
         expand_offdiag(&S.Mom[pq * kMomStride], S.fr[i], S.fr[j], sub, &S.U[ublk(i, j, F)]);
       }
     }
+    bar_sync(kBarProd, kProdThreads);
+    for (int q = t; q < F * kDiagTerm; q += kProdThreads) { const int f = q / kDiagTerm, e = q - f * kDiagTerm; S.sums[f * kSumStride + e] = expand_diag_reduce(reinterpret_cast<const double*>(&S.sobs[0][0]), f, e, F); }
     bar_sync(kBarProd, kProdThreads);
     // diagonal blocks (f, f) = [[PP, -PT Rf], [., Rf^T TT Rf]] and the gradient g_f = [GP ; Rf^T GT]
     for (int q = t; q < 42 * F; q += kProdThreads) {
