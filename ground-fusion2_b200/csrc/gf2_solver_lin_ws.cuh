@@ -4,7 +4,7 @@
 // that leaves the SM at four warps, and a window's sweep is a chain of 8 x (observation phase -> barrier -> SYRK -> barrier). This kernel
 // spends a whole SM on one window instead: 16 warps, split by role, connected by mbarriers (no CTA-wide barrier inside the sweep). Same
 // arithmetic per factor as k_linearize (moment form, Gram on the fp64 tensor cores, end-aligned SYRK tiles), same outputs; measured on
-// B200: one W10-F1000 window in half the time of k_linearize, a full 4096-window batch 8 % slower (profiles/README.md) - the launcher picks
+// B200: one W10-F1000 window in 0.062 ms instead of 0.091 ms, a full 4096-window batch 12 % slower (profiles/sweep_variants_r2.txt) - the launcher picks
 // by batch size.
 #pragma once
 #include "gf2_solver_lin.cuh"

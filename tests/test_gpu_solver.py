@@ -166,6 +166,34 @@ def test_solve_properties_full_size_batch(gf2, synth):
     s.close()
 
 
+def test_small_and_large_batch_paths_agree(gf2, synth):
+    """A call of <= 2 windows per SM takes k_linearize_ws + the fused k_step, a larger one k_linearize + k_backsub / k_cand_eval / k_decide.
+    The same three windows solved alone and at the front of a 320-window batch (a batch no B200 takes the small path for): identical
+    iteration counts and terminations, states within the 1e-6 the ill-conditioned windows allow; with the sweep kernel pinned to the batch
+    kernel in both calls only the step kernels differ (same bodies, same reduction order) and the results are bit-equal."""
+    base = synth.make_windows(3, n_landmarks=300)
+    N = 320
+    big = {k: (np.concatenate([v] * (N // 3 + 1))[:N] if isinstance(v, np.ndarray) and v.shape[:1] == (3,) else v) for k, v in base.items()}
+    opts = gf2.abi.default_opts()
+
+    def run(w, n, sweep):
+        s = _solver(gf2, w, n, sweep)
+        s.upload(w, preintegrate="device")
+        summ = s.solve(opts, n).copy(); st = s.get_states(n); lam = s.get_landmarks(n)
+        s.close()
+        return summ, st, lam
+    for sweep, exact in ((gf2.abi.SWEEP_BATCH, True), (gf2.abi.SWEEP_AUTO, False)):
+        s_small, x_small, l_small = run(base, 3, sweep)
+        s_big, x_big, l_big = run(big, N, sweep)
+        assert np.array_equal(s_small["iterations"], s_big["iterations"][:3]) and np.array_equal(s_small["termination"], s_big["termination"][:3])
+        if exact:
+            assert np.array_equal(x_small["para_pose"], x_big["para_pose"][:3]) and np.array_equal(l_small, l_big[:3])
+            assert np.array_equal(s_small["final_cost"], s_big["final_cost"][:3])
+        else:
+            assert np.allclose(x_small["para_pose"], x_big["para_pose"][:3], rtol=0, atol=1e-6)
+            assert np.allclose(s_small["final_cost"], s_big["final_cost"][:3], rtol=1e-6)
+
+
 def test_edge_cases(gf2, oracle, synth):
     """Empty window (no landmarks), a window with fixed landmarks, and zero iterations."""
     w = synth.make_windows(3, n_landmarks=120)
