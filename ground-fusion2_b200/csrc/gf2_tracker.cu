@@ -340,7 +340,7 @@ struct gf2_tracker {
   int32_t* d_npts; float *d_prev_pts, *d_next_pts, *d_rev_pts, *d_err; uint8_t *d_status, *d_rstatus;
   int32_t* d_gate;
   // detector (allocated by the first gf2_tracker_detect / gf2_tracker_min_eigen_map)
-  float *d_cov = nullptr, *d_eig = nullptr; uint8_t *d_mask = nullptr, *d_det_img = nullptr; unsigned* d_vmax = nullptr;
+  float* d_eig = nullptr; uint8_t *d_mask = nullptr, *d_det_img = nullptr; unsigned* d_vmax = nullptr;
   unsigned long long* d_keys = nullptr; int32_t *d_count = nullptr, *d_want = nullptr; int key_cap = 0;
   std::vector<unsigned long long> h_keys; std::vector<int32_t> h_count;
   // CLAHE of every uploaded image (gf2_tracker_set_equalize); the LUT buffer is allocated on first use
@@ -562,7 +562,7 @@ static int detect_alloc(gf2_tracker* h) {
   const int S = h->cfg.max_streams; const size_t plane = (size_t)h->cfg.width * h->cfg.height;
   h->key_cap = (int)(plane / 4);   // a 3x3 local maximum excludes its 8 neighbours unless they tie; overflow is reported, never truncated silently
   auto alloc = [&](void** p, size_t bytes) { if (cudaMalloc(p, bytes) != cudaSuccess) return false; h->allocs.push_back(*p); return true; };
-  const bool ok = alloc((void**)&h->d_cov, sizeof(float) * 3 * plane * S) && alloc((void**)&h->d_eig, sizeof(float) * plane * S) && alloc((void**)&h->d_mask, plane * S) &&
+  const bool ok = alloc((void**)&h->d_eig, sizeof(float) * plane * S) && alloc((void**)&h->d_mask, plane * S) &&
                   alloc((void**)&h->d_det_img, plane * S) && alloc((void**)&h->d_vmax, sizeof(unsigned) * S) && alloc((void**)&h->d_keys, sizeof(unsigned long long) * (size_t)h->key_cap * S) &&
                   alloc((void**)&h->d_count, sizeof(int32_t) * S) && alloc((void**)&h->d_want, sizeof(int32_t) * S);
   if (!ok) { h->d_eig = nullptr; return gf2::fail(GF2_ERR_CUDA, "detector allocation failed"); }
@@ -584,9 +584,7 @@ static int detect_eig(gf2_tracker* h, int n_streams, const uint8_t* img, size_t 
   }
   if (mask) GF2T_CUDA(cudaMemcpyAsync(h->d_mask, mask, plane * n_streams, cudaMemcpyHostToDevice, h->stream));
   GF2T_CUDA(cudaMemsetAsync(h->d_vmax, 0, sizeof(unsigned) * n_streams, h->stream));
-  dim3 b(32, 8), g((W + 31) / 32, (H + 7) / 8, n_streams);
-  k_gftt_cov<<<g, b, 0, h->stream>>>(d_img, W, H, plane, h->d_cov);
-  k_gftt_eig<<<dim3((W + 63) / 64, n_streams), 64, 0, h->stream>>>(h->d_cov, mask ? h->d_mask : nullptr, W, H, h->d_eig, h->d_vmax);
+  k_gftt_eig<<<dim3((W + 63) / 64, n_streams), 64, 0, h->stream>>>(d_img, plane, mask ? h->d_mask : nullptr, W, H, h->d_eig, h->d_vmax);
   GF2T_CUDA(cudaGetLastError());
   return GF2_OK;
 }

@@ -1,7 +1,7 @@
 // TEST INFRASTRUCTURE — host emulation of the detector kernels of ground-fusion2_b200/csrc/gf2_tracker_detect.cuh, one CUDA thread at a time, so that
 // the CPU-only suite can check their float32 / float64 operation order against the cv2-pinned numpy oracle without a GPU (tests/test_detect_emul.py).
 // It is compiled by the test with g++ -ffp-contract=off; it is not part of the product and nothing in the package references it. Only kernels whose
-// threads do not communicate are launched (k_gftt_cov, k_gftt_eig, k_gftt_nms); the warp reduction of the masked maximum is redone on the host.
+// threads do not communicate are launched (k_gftt_eig, k_gftt_nms); the warp reduction of the masked maximum is redone on the host.
 #include <math.h>
 #include <stdint.h>
 #include <string.h>
@@ -40,10 +40,8 @@ template <class F> static void launch(D3 g, D3 b, F f) {
     for (int tz = 0; tz < b.z; tz++) for (int ty = 0; ty < b.y; ty++) for (int tx = 0; tx < b.x; tx++) { blockIdx = {bx, by, bz}; threadIdx = {tx, ty, tz}; f(); }
 }
 extern "C" int detect_emul(const uint8_t* img, const uint8_t* mask, int W, int H, int S, const int32_t* want, double quality, float* eig, unsigned long long* keys, int cap, int32_t* count) {
-  std::vector<float> cov((size_t)3 * W * H * S);
   std::vector<unsigned> vmax(S, 0);
-  launch({(W + 31) / 32, (H + 7) / 8, S}, {32, 8, 1}, [&] { k_gftt_cov(img, W, H, (size_t)W * H, cov.data()); });
-  launch({(W + 63) / 64, S, 1}, {64, 1, 1}, [&] { k_gftt_eig(cov.data(), mask, W, H, eig, vmax.data()); });
+  launch({(W + 63) / 64, S, 1}, {64, 1, 1}, [&] { k_gftt_eig(img, (size_t)W * H, mask, W, H, eig, vmax.data()); });
   for (int s = 0; s < S; s++) { vmax[s] = 0; for (size_t i = 0; i < (size_t)W * H; i++) if (!mask || mask[(size_t)s * W * H + i]) vmax[s] = std::max(vmax[s], gftt_ordered(eig[(size_t)s * W * H + i])); }
   memset(count, 0, sizeof(int32_t) * S);
   launch({(W + 31) / 32, (H + 7) / 8, S}, {32, 8, 1}, [&] { k_gftt_nms(eig, mask, W, H, vmax.data(), quality, want, keys, cap, count); });
