@@ -375,6 +375,7 @@ int gf2_solver_create(const gf2_solver_cfg* cfg, gf2_solver** out) {
   cudaFuncSetAttribute(k_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * 450 * GF2_MAX_FRAMES));
   cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, cfg->device);
   // function attributes are per device: set here, after cudaSetDevice, for every handle (not once per process)
+  cudaFuncSetAttribute(k_marg_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(((sizeof(MargShared) + 15) & ~size_t(15)) + sizeof(double) * kMargTMax * kMargLD));
   cudaFuncSetAttribute(k_marg_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(((sizeof(MargShared) + 15) & ~size_t(15)) + sizeof(double) * kMargTMax * kMargLD));
   cudaFuncSetAttribute(k_marg_eig, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(((sizeof(EigShared) + 15) & ~size_t(15)) + sizeof(double) * 2 * kMargKMax * (kMargKMax | 1)));
   if (cudaGetLastError() != cudaSuccess) { gf2_solver_destroy(h); return gf2::fail(GF2_ERR_CUDA, "cudaFuncSetAttribute failed (is this an sm_100a device?)"); }
@@ -814,7 +815,6 @@ int gf2_marginalize_async(gf2_solver* h, int first, int n, int32_t mode, const g
   GF2_TRY(check_range(h, first, n));
   if (!opts) return gf2::fail(GF2_ERR_INVALID, "null options");
   if (mode != GF2_MARGIN_OLD && mode != GF2_MARGIN_SECOND_NEW) return gf2::fail(GF2_ERR_INVALID, "mode %d", mode);
-  if (h->nccl_comm) return gf2::fail(GF2_ERR_UNSUPPORTED, "marginalization in factor-sharded mode is not built (the frame-0 landmarks live on different ranks)");
   if (n == 0) return GF2_OK;
   KP k;
   GF2_TRY(fill_kp(h, opts, k));
@@ -824,8 +824,12 @@ int gf2_marginalize_async(gf2_solver* h, int first, int n, int32_t mode, const g
     GF2_TRY(dalloc<int32_t>(h, &h->marg.touched, (size_t)B * kMargBlocksMax)); GF2_TRY(dalloc<int32_t>(h, &h->marg.status, B)); GF2_TRY(dalloc<int32_t>(h, &h->marg.mdim, B));
     GF2_CUDA(cudaMallocHost((void**)&h->h_marg, sizeof(int32_t) * 2 * B));
   }
+  if (h->nccl_comm && !h->marg.stage_sum) {   // factor-sharded mode: the partial systems of the ranks meet in these buffers
+    GF2_TRY(dalloc<double>(h, &h->marg.stage_sum, (size_t)B * kMargStageSum)); GF2_TRY(dalloc<double>(h, &h->marg.stage_max, (size_t)B * kMargStageMax));
+  }
   MargP mp = h->marg;
   mp.mode = mode; mp.eig = opts->marg_eig ? 1 : 0;
+  mp.nranks = h->nccl_comm ? h->comm_size : 1; mp.rank = h->nccl_comm ? h->comm_rank : 0;
   mp.out_rows = const_cast<int32_t*>(h->kp.prior_rows); mp.out_nblocks = const_cast<int32_t*>(h->kp.prior_nblocks);
   mp.out_J0 = const_cast<double*>(h->kp.prior_J0); mp.out_r0 = const_cast<double*>(h->kp.prior_r0);
   mp.out_blocks = const_cast<gf2_prior_block*>(h->kp.prior_blocks);
@@ -835,6 +839,16 @@ int gf2_marginalize_async(gf2_solver* h, int first, int n, int32_t mode, const g
   cudaEventRecord(h->ev_marg[0], h->stream);
   k_prepare<<<n, 128, sizeof(double) * 450 * GF2_MAX_FRAMES, h->stream>>>(k, first);   // IMU sqrt_info, J0^T J0 of the old prior
   k_marg_build<<<n, kMargThreads, sh_build, h->stream>>>(k, first, mp);
+  if (h->nccl_comm) {
+    // every rank eliminated its own frame-0 landmarks (l mod N) into the window's [frame block | kept blocks] system: sum the partial
+    // systems (82.7 KB per window) and take the maximum of the flags, then every rank eliminates the frame block and factorises the same
+    // kept system: the new prior is replicated like the old one
+    g_nccl.GroupStart();
+    g_nccl.AllReduce(mp.stage_sum + (size_t)first * kMargStageSum, mp.stage_sum + (size_t)first * kMargStageSum, (size_t)n * kMargStageSum, kNcclFloat64, kNcclSum, h->nccl_comm, h->stream);
+    g_nccl.AllReduce(mp.stage_max + (size_t)first * kMargStageMax, mp.stage_max + (size_t)first * kMargStageMax, (size_t)n * kMargStageMax, kNcclFloat64, kNcclMax, h->nccl_comm, h->stream);
+    g_nccl.GroupEnd();
+    k_marg_finish<<<n, kMargThreads, sh_build, h->stream>>>(k, first, mp);
+  }
   k_marg_eig<<<n, kEigThreads, sh_eig, h->stream>>>(k, first, mp);
   cudaEventRecord(h->ev_marg[1], h->stream);
   GF2_CUDA(cudaGetLastError());

@@ -36,12 +36,21 @@ constexpr int kMargChunk = 32;                          // landmarks eliminated 
 constexpr int kMargNCMax = 13 + 6 * (kMaxF - 1);        // columns a frame-0 landmark can touch: pose0, poses 1..F-1, ex, td  (73)
 constexpr int kMargOwn = (kMargNCMax * (kMargNCMax + 1) / 2 + kMargNCMax + kMargThreads - 1) / kMargThreads;  // matrix entries per thread (11)
 constexpr double kMargEps = 1e-8;                       // MarginalizationInfo::eps, VE/factor/marginalization_factor.h:83
+constexpr int kMargStageSum = kMargTMax * kMargTMax + kMargTMax + 36 + 1;   // A (T x T, stride kMargTMax) | b | C6 | n_lm0
+constexpr int kMargStageMax = kMargBlocksMax + 2 + 1 + 1;                    // touched | mtouched | bad | record written
 
 enum { GF2_MARG_OK_ = 0, GF2_MARG_INVALID_ = -1, GF2_MARG_UNCHANGED_ = -2, GF2_MARG_UNSUPPORTED_ = -3, GF2_MARG_DEGENERATE_ = -4, GF2_MARG_TOO_LARGE_ = -5 };
 
 struct MargP {
   int mode;            // 0 MARGIN_OLD, 1 MARGIN_SECOND_NEW
   int eig;             // 0: rank-revealing Cholesky factor of the kept system (default), 1: the reference's eigen-decomposition, literally
+  // factor-sharded mode: the frame-0 landmarks of a window live on different ranks. k_marg_build stops after the landmark
+  // elimination and leaves the window's system [A | b | C6 | n_lm0] (SUM over the ranks) and flags (MAX) in the staging buffers; the ranks
+  // all-reduce them and k_marg_finish eliminates the frame block on the sums. The prior / IMU / wheel factors are replicated: rank 0 alone
+  // contributes their values (rank > 0 zeroes the system before its landmarks), every rank their flags.
+  int nranks, rank;
+  double* stage_sum;   // [nW][kMargStageSum]
+  double* stage_max;   // [nW][kMargStageMax]
   double* A;           // [nW][kMargKMax][kMargKMax] kept system after elimination
   double* b;           // [nW][kMargKMax]
   int32_t* touched;    // [nW][kMargBlocksMax] kept block touched by a factor
@@ -146,6 +155,64 @@ __device__ __forceinline__ void obs_jacobians_calib(const FrameCtx& fi, const Ca
   Jtd[1] = -(Jc[3] * (double)oi.z + Jc[4] * (double)oi.w) / inv_dep + sqrt_info * (double)oj.w;
 }
 
+// Second half of the marginalization of one window: the system [A | b] of the dropped frame block and the kept blocks is complete in
+// shared memory (upper triangle); symmetrise, eliminate the frame block, write the kept system for k_marg_eig.
+__device__ __forceinline__ void marg_finish_block(const KP& p, int w, const MargP& mp, MargShared& s, double* A, int T, int K) {
+  const int t = threadIdx.x;
+  // ---- symmetrise, then eliminate the frame-0 block (MARGIN_OLD: pose0 + sb0, MARGIN_SECOND_NEW: pose F-2)
+  for (int e = t; e < T * T; e += blockDim.x) { const int a = e / T, c = e % T; if (a > c) A[a * kMargLD + c] = A[c * kMargLD + a]; }
+  __syncthreads();
+  const int md = (mp.mode == 0 ? (s.mtouched[0] ? 6 : 0) + (s.mtouched[1] ? 9 : 0) : 6);
+  if (t == 0) {
+    int status = GF2_MARG_OK_;
+    if (s.bad == 1) status = GF2_MARG_UNSUPPORTED_;
+    else if (s.bad == 2) status = GF2_MARG_DEGENERATE_;
+    else if (md + s.n_lm0 == 0) status = GF2_MARG_INVALID_;
+    else {
+      // Cholesky of Y (the dropped frame block after the landmarks) and of its eps-shifted twin
+      for (int pass = 0; pass < 2 && status == GF2_MARG_OK_; pass++) {
+        for (int i = 0; i < kMargM; i++) for (int j = 0; j <= i; j++) {
+          const bool pi = mp.mode == 1 ? i < 6 : (i < 6 ? s.mtouched[0] : s.mtouched[1]) != 0;
+          const bool pj = mp.mode == 1 ? j < 6 : (j < 6 ? s.mtouched[0] : s.mtouched[1]) != 0;
+          double a = (pi && pj) ? A[i * kMargLD + j] : (i == j ? 1.0 : 0.0);   // absent dims: identity pivot, zero coupling
+          if (pass == 0 && pi && pj) { if (i == j) a -= kMargEps; if (i < 6) a -= s.C6[j][i]; }
+          s.Y[i][j] = a;
+        }
+        for (int j = 0; j < kMargM && status == GF2_MARG_OK_; j++) {
+          double d = s.Y[j][j]; for (int k = 0; k < j; k++) d -= s.Y[j][k] * s.Y[j][k];
+          if (!(d > 0.0)) { status = GF2_MARG_DEGENERATE_; break; }
+          d = sqrt(d); s.Y[j][j] = d;
+          for (int i = j + 1; i < kMargM; i++) { double v = s.Y[i][j]; for (int k = 0; k < j; k++) v -= s.Y[i][k] * s.Y[j][k]; s.Y[i][j] = v / d; }
+        }
+      }
+    }
+    mp.status[w] = status; mp.mdim[w] = md + s.n_lm0;
+    s.bad = status;
+  }
+  __syncthreads();
+  if (s.bad != GF2_MARG_OK_) return;
+  // Z = L^-1 [X | b_m], X = A[0:15, 15:T]; absent dropped dims have zero rows in X and an identity pivot
+  if (t <= K) {
+    double z[kMargM];
+    for (int i = 0; i < kMargM; i++) {
+      double v = (t < K) ? A[i * kMargLD + kMargM + t] : s.b[i];
+      for (int k = 0; k < i; k++) v -= s.Y[i][k] * z[k];
+      z[i] = v / s.Y[i][i];
+    }
+    for (int i = 0; i < kMargM; i++) s.Z[i][t] = z[i];
+  }
+  __syncthreads();
+  double* Ao = mp.A + (size_t)w * kMargKMax * kMargKMax;
+  for (int e = t; e < K * K; e += blockDim.x) {
+    const int a = e / K, c = e % K;
+    double v = A[(kMargM + a) * kMargLD + kMargM + c];
+    for (int k = 0; k < kMargM; k++) v -= s.Z[k][a] * s.Z[k][c];
+    Ao[a * kMargKMax + c] = v;
+  }
+  if (t < K) { double v = s.b[kMargM + t]; for (int k = 0; k < kMargM; k++) v -= s.Z[k][t] * s.Z[k][K]; mp.b[(size_t)w * kMargKMax + t] = v; }
+  if (t < kMargBlocksMax) mp.touched[(size_t)w * kMargBlocksMax + t] = s.touched[t];
+}
+
 __global__ void __launch_bounds__(kMargThreads) k_marg_build(KP p, int w0, MargP mp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   MargShared& s = *reinterpret_cast<MargShared*>(smem_raw);
@@ -209,7 +276,16 @@ __global__ void __launch_bounds__(kMargThreads) k_marg_build(KP p, int w0, MargP
   __syncthreads();
   if (mp.mode == 1 && !(n0 > 0 && s.mtouched[0])) {  // estimator.cpp:3599-3600: nothing to do, the old prior stays
     if (t == 0) { mp.status[w] = GF2_MARG_UNCHANGED_; mp.mdim[w] = 0; }
+    if (mp.nranks > 1) {   // (the same decision on every rank: the prior is replicated) no record for k_marg_finish
+      for (int i = t; i < kMargStageSum; i += blockDim.x) mp.stage_sum[(size_t)w * kMargStageSum + i] = 0.0;
+      for (int i = t; i < kMargStageMax; i += blockDim.x) mp.stage_max[(size_t)w * kMargStageMax + i] = 0.0;
+    }
     return;
+  }
+  if (mp.mode == 1 && mp.nranks > 1 && mp.rank > 0) {   // MARGIN_SECOND_NEW has replicated factors only: rank 0's values, everybody's flags
+    for (int i = t; i < kMargTMax * kMargLD; i += blockDim.x) A[i] = 0.0;
+    for (int i = t; i < kMargTMax; i += blockDim.x) s.b[i] = 0.0;
+    __syncthreads();
   }
 
   if (mp.mode == 0) {
@@ -276,6 +352,11 @@ __global__ void __launch_bounds__(kMargThreads) k_marg_build(KP p, int w0, MargP
     }
     __syncthreads();
 
+    if (mp.nranks > 1 && mp.rank > 0) {   // the replicated factors count once (rank 0); their flags stay
+      for (int i = t; i < kMargTMax * kMargLD; i += blockDim.x) A[i] = 0.0;
+      for (int i = t; i < kMargTMax; i += blockDim.x) s.b[i] = 0.0;
+      __syncthreads();
+    }
     // ---- projection factors of the landmarks hosted in frame 0 (estimator.cpp:3495-3528). One warp per landmark, one lane
     //      per observation. Each landmark is a 1x1 block of Amm coupled to pose 0 only, so it is eliminated on the spot:
     //      its scaled row w / sqrt(v) over the touched columns (and g_l / sqrt(v)) is staged in shared memory, and after
@@ -467,58 +548,39 @@ __global__ void __launch_bounds__(kMargThreads) k_marg_build(KP p, int w0, MargP
     __syncthreads();
   }
 
-  // ---- symmetrise, then eliminate the frame-0 block (MARGIN_OLD: pose0 + sb0, MARGIN_SECOND_NEW: pose F-2)
-  for (int e = t; e < T * T; e += blockDim.x) { const int a = e / T, c = e % T; if (a > c) A[a * kMargLD + c] = A[c * kMargLD + a]; }
-  __syncthreads();
-  const int md = (mp.mode == 0 ? (s.mtouched[0] ? 6 : 0) + (s.mtouched[1] ? 9 : 0) : 6);
-  if (t == 0) {
-    int status = GF2_MARG_OK_;
-    if (s.bad == 1) status = GF2_MARG_UNSUPPORTED_;
-    else if (s.bad == 2) status = GF2_MARG_DEGENERATE_;
-    else if (md + s.n_lm0 == 0) status = GF2_MARG_INVALID_;
-    else {
-      // Cholesky of Y (the dropped frame block after the landmarks) and of its eps-shifted twin
-      for (int pass = 0; pass < 2 && status == GF2_MARG_OK_; pass++) {
-        for (int i = 0; i < kMargM; i++) for (int j = 0; j <= i; j++) {
-          const bool pi = mp.mode == 1 ? i < 6 : (i < 6 ? s.mtouched[0] : s.mtouched[1]) != 0;
-          const bool pj = mp.mode == 1 ? j < 6 : (j < 6 ? s.mtouched[0] : s.mtouched[1]) != 0;
-          double a = (pi && pj) ? A[i * kMargLD + j] : (i == j ? 1.0 : 0.0);   // absent dims: identity pivot, zero coupling
-          if (pass == 0 && pi && pj) { if (i == j) a -= kMargEps; if (i < 6) a -= s.C6[j][i]; }
-          s.Y[i][j] = a;
-        }
-        for (int j = 0; j < kMargM && status == GF2_MARG_OK_; j++) {
-          double d = s.Y[j][j]; for (int k = 0; k < j; k++) d -= s.Y[j][k] * s.Y[j][k];
-          if (!(d > 0.0)) { status = GF2_MARG_DEGENERATE_; break; }
-          d = sqrt(d); s.Y[j][j] = d;
-          for (int i = j + 1; i < kMargM; i++) { double v = s.Y[i][j]; for (int k = 0; k < j; k++) v -= s.Y[i][k] * s.Y[j][k]; s.Y[i][j] = v / d; }
-        }
-      }
-    }
-    mp.status[w] = status; mp.mdim[w] = md + s.n_lm0;
-    s.bad = status;
+  if (mp.nranks > 1) {   // factor-sharded mode: hand the partial system to the all-reduce, k_marg_finish takes it from there
+    double* ss = mp.stage_sum + (size_t)w * kMargStageSum; double* sm = mp.stage_max + (size_t)w * kMargStageMax;
+    for (int e = t; e < kMargTMax * kMargTMax; e += blockDim.x) { const int a = e / kMargTMax, c = e % kMargTMax; ss[e] = (a <= c && c < T) ? A[a * kMargLD + c] : 0.0; }
+    for (int i = t; i < kMargTMax; i += blockDim.x) ss[kMargTMax * kMargTMax + i] = s.b[i];
+    if (t < 36) ss[kMargTMax * kMargTMax + kMargTMax + t] = (&s.C6[0][0])[t];
+    if (t == 0) ss[kMargTMax * kMargTMax + kMargTMax + 36] = (double)s.n_lm0;
+    if (t < kMargBlocksMax) sm[t] = (double)s.touched[t];
+    if (t < 2) sm[kMargBlocksMax + t] = (double)s.mtouched[t];
+    if (t == 0) { sm[kMargBlocksMax + 2] = (double)s.bad; sm[kMargBlocksMax + 3] = 1.0; }
+    return;
   }
+  marg_finish_block(p, w, mp, s, A, T, K);
+}
+
+// second half of k_marg_build in the factor-sharded mode: the all-reduced system of a window back into shared memory, then the elimination
+__global__ void __launch_bounds__(kMargThreads) k_marg_finish(KP p, int w0, MargP mp) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  MargShared& s = *reinterpret_cast<MargShared*>(smem_raw);
+  double* A = reinterpret_cast<double*>(smem_raw + ((sizeof(MargShared) + 15) & ~size_t(15)));
+  const int w = w0 + blockIdx.x, t = threadIdx.x;
+  const int F = p.F, NP = 6 * (F - 1), K = NP + 16 + (p.use_wheel ? 10 : 0), T = kMargM + K;
+  const double* ss = mp.stage_sum + (size_t)w * kMargStageSum; const double* sm = mp.stage_max + (size_t)w * kMargStageMax;
+  if (sm[kMargBlocksMax + 3] == 0.0) return;   // GF2_MARG_UNCHANGED on every rank (status written by k_marg_build)
+  for (int e = t; e < kMargTMax * kMargLD; e += blockDim.x) A[e] = 0.0;
   __syncthreads();
-  if (s.bad != GF2_MARG_OK_) return;
-  // Z = L^-1 [X | b_m], X = A[0:15, 15:T]; absent dropped dims have zero rows in X and an identity pivot
-  if (t <= K) {
-    double z[kMargM];
-    for (int i = 0; i < kMargM; i++) {
-      double v = (t < K) ? A[i * kMargLD + kMargM + t] : s.b[i];
-      for (int k = 0; k < i; k++) v -= s.Y[i][k] * z[k];
-      z[i] = v / s.Y[i][i];
-    }
-    for (int i = 0; i < kMargM; i++) s.Z[i][t] = z[i];
-  }
+  for (int e = t; e < kMargTMax * kMargTMax; e += blockDim.x) { const int a = e / kMargTMax, c = e % kMargTMax; if (a <= c) A[a * kMargLD + c] = ss[e]; }
+  for (int i = t; i < kMargTMax; i += blockDim.x) s.b[i] = ss[kMargTMax * kMargTMax + i];
+  if (t < 36) (&s.C6[0][0])[t] = ss[kMargTMax * kMargTMax + kMargTMax + t];
+  if (t < kMargBlocksMax) s.touched[t] = sm[t] != 0.0;
+  if (t < 2) s.mtouched[t] = sm[kMargBlocksMax + t] != 0.0;
+  if (t == 0) { s.n_lm0 = (int)(ss[kMargTMax * kMargTMax + kMargTMax + 36] + 0.5); s.bad = (int)sm[kMargBlocksMax + 2]; s.maxlen = 0; }
   __syncthreads();
-  double* Ao = mp.A + (size_t)w * kMargKMax * kMargKMax;
-  for (int e = t; e < K * K; e += blockDim.x) {
-    const int a = e / K, c = e % K;
-    double v = A[(kMargM + a) * kMargLD + kMargM + c];
-    for (int k = 0; k < kMargM; k++) v -= s.Z[k][a] * s.Z[k][c];
-    Ao[a * kMargKMax + c] = v;
-  }
-  if (t < K) { double v = s.b[kMargM + t]; for (int k = 0; k < kMargM; k++) v -= s.Z[k][t] * s.Z[k][K]; mp.b[(size_t)w * kMargKMax + t] = v; }
-  if (t < kMargBlocksMax) mp.touched[(size_t)w * kMargBlocksMax + t] = s.touched[t];
+  marg_finish_block(p, w, mp, s, A, T, K);
 }
 
 // --------------------------------------------------------------------------------------------------------------------

@@ -12,6 +12,7 @@ from gf2_loader import load
 
 ap = argparse.ArgumentParser(); ap.add_argument("--windows", type=int, default=64); ap.add_argument("--landmarks", type=int, default=1000)
 ap.add_argument("--planes", type=int, default=5000); ap.add_argument("--steps", type=int, default=3)
+ap.add_argument("--marginalize", action="store_true", help="after the solve: MARGIN_OLD on every rank (partial systems all-reduced), then a second solve with the resident prior")
 ap.add_argument("--free-wheel", action="store_true", help="body_T_wheel free (estimate_wheel_extrinsic: 1): one more block row of the reduced system")
 args = ap.parse_args()
 rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
@@ -45,6 +46,13 @@ for _ in range(args.steps):
     torch.cuda.synchronize(); times.append(time.perf_counter() - t0)
 tt = torch.tensor([min(times)], device="cuda"); dist.all_reduce(tt, op=dist.ReduceOp.MAX)
 st = s.get_states(B); lam = s.get_landmarks(B)
+marg = None
+if args.marginalize:   # every rank marginalizes its landmark shard; the new prior is the same on all ranks
+    mst, mm = s.marginalize(opts, 0, B)
+    pr = s.get_prior(B)
+    summ2 = s.solve(opts, B)          # the next solve uses the resident prior (same window data: the prior's frames are shifted by one, a consistency run only)
+    st2 = s.get_states(B)
+    marg = (mst, mm, pr, summ2, st2)
 lam_t = torch.from_numpy(lam).cuda(); gathered = [torch.zeros_like(lam_t) for _ in range(world)]
 dist.all_gather(gathered, lam_t)
 if rank == 0:
@@ -55,6 +63,22 @@ if rank == 0:
         ref.restore(B); torch.cuda.synchronize(); t0 = time.perf_counter(); rs = ref.solve(opts, B); torch.cuda.synchronize(); t1.append(time.perf_counter() - t0)
     rst = ref.get_states(B); rlam = ref.get_landmarks(B)
     lam_full = shard.gather_landmarks(w["n_landmarks"], [g.cpu().numpy() for g in gathered], world)
+    mout = {}
+    if marg is not None:
+        rmst, rmm = ref.marginalize(opts, 0, B)
+        rpr = ref.get_prior(B)
+        rs2 = ref.solve(opts, B); rst2 = ref.get_states(B)
+        mst, mm, pr, summ2, st2 = marg
+        hd = gd = 0.0
+        for i in range(B):
+            n = int(rpr["prior_rows"][i]); assert int(pr["prior_rows"][i]) == n
+            Jr, Js = rpr["prior_J0"][i, :n, :n], pr["prior_J0"][i, :n, :n]
+            Hr, Hs = Jr.T @ Jr, Js.T @ Js
+            gr, gs = Jr.T @ rpr["prior_r0"][i, :n], Js.T @ pr["prior_r0"][i, :n]
+            hd = max(hd, float(np.abs(Hs - Hr).max() / np.abs(Hr).max())); gd = max(gd, float(np.abs(gs - gr).max() / max(np.abs(gr).max(), 1e-300)))
+        mout = {"marg_status_equal": bool((mst == rmst).all() and (mst == 0).all()), "marg_m_equal": bool((mm == rmm).all()), "marg_H_rel_diff": hd, "marg_g_rel_diff": gd,
+                "marg_blocks_equal": bool(all(np.array_equal(pr["prior_blocks"][f], rpr["prior_blocks"][f]) for f in ("kind", "index", "offset"))),
+                "second_solve_pose_diff": float(np.abs(st2["para_pose"] - rst2["para_pose"]).max()), "second_solve_iterations_equal": bool((summ2["iterations"] == rs2["iterations"]).all())}
     out = {"n_gpus": world, "windows": B, "landmarks": args.landmarks, "planes": args.planes,
            "sharded_ms": 1e3 * float(tt.item()), "single_gpu_ms": 1e3 * min(t1), "nccl_ms_rank0": s.last_timing()["nccl_ms"],
            "sharded_solves_per_s": B / float(tt.item()), "single_solves_per_s": B / min(t1),
@@ -63,7 +87,10 @@ if rank == 0:
            "ex_wheel_diff": float(np.abs(st["ex_pose_wheel"] - rst["ex_pose_wheel"]).max()), "ex_wheel_moved": float(np.abs(rst["ex_pose_wheel"] - w["ex_pose_wheel"]).max()),
            "iterations_equal": bool((summ["iterations"] == rs["iterations"]).all()), "termination_equal": bool((summ["termination"] == rs["termination"]).all()),
            "final_cost_rel_diff": float((np.abs(summ["final_cost"] - rs["final_cost"]) / rs["final_cost"]).max())}
+    out.update(mout)
     print(json.dumps(out))
+    if mout:
+        assert mout["marg_status_equal"] and mout["marg_m_equal"] and mout["marg_blocks_equal"] and mout["marg_H_rel_diff"] <= 1e-8 and mout["marg_g_rel_diff"] <= 1e-5 and mout["second_solve_pose_diff"] < 1e-6, out
     assert out["iterations_equal"] and out["termination_equal"] and out["pose_diff"] < 1e-6 and out["inv_depth_diff"] < 1e-6, out
 s.close()
 dist.destroy_process_group()

@@ -313,6 +313,26 @@ def test_factor_sharded_two_gpus_match_single_gpu(gf2, free_wheel):
         assert out["ex_wheel_moved"] > 0 and out["ex_wheel_diff"] <= 1e-6 * max(out["ex_wheel_moved"], 1e-3)
 
 
+def test_factor_sharded_marginalization_two_gpus(gf2):
+    """gf2_marginalize in the factor-sharded mode: every rank eliminates its own frame-0 landmarks, the partial [frame block | kept blocks]
+    systems are all-reduced, every rank then holds the same new prior == the single-GPU one (J0^T J0 to 1e-8, J0^T r0, same blocks), and the
+    next sharded solve with that resident prior == the single-GPU one. Needs 2 visible GPUs."""
+    import json as _json
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29533",
+                          os.path.join(root, "scripts", "run_sharded.py"), "--windows", "8", "--landmarks", "400", "--planes", "800", "--steps", "1", "--marginalize"],
+                         capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    out = _json.loads([ln for ln in res.stdout.splitlines() if ln.startswith("{")][-1])
+    assert out["marg_status_equal"] and out["marg_H_rel_diff"] <= 1e-8 and out["second_solve_pose_diff"] < 1e-6
+
+
 @pytest.mark.gpu
 def test_wheel_preintegration_kernel_matches_oracle(gf2, oracle, synth):
     """k_wheel_preintegrate vs the restated WheelIntegrationBase::push_back chain (wheel_integration_base.h:41-178)."""
