@@ -653,7 +653,7 @@ static int run(gf2_solver* h, int first, int n, const gf2_solve_opts* opts, gf2_
   int ne = 0, nn = 0;
   cudaEventRecord(h->ev[ne++], h->stream);
   k_prepare<<<n, 128, sizeof(double) * 450 * GF2_MAX_FRAMES, h->stream>>>(k, first);
-  k_tasks<<<n, 32, 0, h->stream>>>(k, first);
+  k_tasks<<<n, kTaskThreads, 0, h->stream>>>(k, first);
   cudaEventRecord(h->ev[ne++], h->stream);
   const int iters = only_linearize ? 1 : iterations;
   // One robot / small batches (up to two windows per SM) are launch- and latency-bound: the sweep runs one window per SM on 16 warp-specialised

@@ -24,16 +24,22 @@ constexpr int kMaxTasks = 48;  // ceil(1000 / 32) + 11 partial tasks + slack
 constexpr int kMaxPlaneTasks = 192;  // planes: up to ~5.8k per window in tasks of 32 of the same frame
 
 // ------------------------------------------------------------------------------------------------ k_tasks
-// Deterministic counting sort of the landmark table by start frame -> perm, and the warp-task list. One thread per start
-// frame scans the table in order (the reference table is already sorted, VE/estimator/feature_manager.cpp:67-88; any
-// order is accepted).
-__global__ void k_tasks(KP p, int w0) {
+// Deterministic counting sort of the landmark table by start frame -> perm, and the warp-task list. One warp per start
+// frame scans the table in order, 32 entries per step (the reference table is already sorted, VE/estimator/feature_manager.cpp:67-88;
+// any order is accepted).
+constexpr int kTaskThreads = 128;
+__global__ void __launch_bounds__(kTaskThreads) k_tasks(KP p, int w0) {
   const int w = w0 + blockIdx.x;
-  const int t = threadIdx.x, F = p.F;
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5, nw = kTaskThreads / 32, F = p.F;
   __shared__ int cnt[2 * kMaxF], ofs[2 * kMaxF + 1];
   const int nlm = p.nlm[w];
   const int32_t* start = p.start + (size_t)w * p.Lm;
-  if (t < F) { int c = 0; for (int l = 0; l < nlm; l++) c += (start[l] == t); cnt[t] = c; }
+  // one warp per start frame, 32 table entries per step: counts and (below) ranks by ballot, in table order
+  for (int f = wid; f < F; f += nw) {
+    int c = 0;
+    for (int base = 0; base < nlm; base += 32) { const int l = base + lane; c += __popc(__ballot_sync(0xffffffffu, l < nlm && start[l] == f)); }
+    if (lane == 0) cnt[f] = c;
+  }
   __syncthreads();
   if (t == 0) {
     int o = 0, nt = 0;
@@ -49,18 +55,31 @@ __global__ void k_tasks(KP p, int w0) {
   __syncthreads();
   // packed record (landmark, track length, first observation, fixed) in sorted order: one load gives k_linearize everything
   // it needs to issue the dependent loads of a landmark
-  if (t < F) {
+  {
     int4* info = p.lminfo + (size_t)w * p.Lm; const int32_t* tlen = p.tlen + (size_t)w * p.Lm; const int32_t* obeg = p.obeg + (size_t)w * p.Lm;
     const uint8_t* fixed = p.fixed + (size_t)w * p.Lm;
-    int o = ofs[t];
-    for (int l = 0; l < nlm; l++) if (start[l] == t) info[o++] = make_int4(l, tlen[l], obeg[l], fixed[l] != 0);
+    for (int f = wid; f < F; f += nw) {
+      int o = ofs[f];
+      for (int base = 0; base < nlm; base += 32) {
+        const int l = base + lane;
+        const bool is = l < nlm && start[l] == f;
+        const unsigned bal = __ballot_sync(0xffffffffu, is);
+        if (is) info[o + __popc(bal & ((1u << lane) - 1u))] = make_int4(l, tlen[l], obeg[l], fixed[l] != 0);
+        o += __popc(bal);
+      }
+    }
   }
   if (!p.planes) return;
   // LiDAR plane factors grouped by key = 2 * frame + ct (LidarPlaneNormFactor / CTLidarPlaneNormFactor), tasks of <= 32 planes
   __syncthreads();
   const int np = p.n_planes[w];
   const gf2_plane* pls = p.planes + (size_t)w * p.Pm;
-  if (t < 2 * F) { int c = 0; for (int q = 0; q < np; q++) c += (2 * pls[q].frame + (pls[q].ct ? 1 : 0) == t); cnt[t] = c; }
+  auto key_of = [&](int q) { return 2 * pls[q].frame + (pls[q].ct ? 1 : 0); };
+  for (int s = wid; s < 2 * F; s += nw) {
+    int c = 0;
+    for (int base = 0; base < np; base += 32) { const int q = base + lane; c += __popc(__ballot_sync(0xffffffffu, q < np && key_of(q) == s)); }
+    if (lane == 0) cnt[s] = c;
+  }
   __syncthreads();
   if (t == 0) {
     int o = 0, nt = 0;
@@ -73,7 +92,19 @@ __global__ void k_tasks(KP p, int w0) {
     p.nptasks[w] = nt;
   }
   __syncthreads();
-  if (t < 2 * F) { int32_t* perm = p.pperm + (size_t)w * p.Pm; int o = ofs[t]; for (int q = 0; q < np; q++) if (2 * pls[q].frame + (pls[q].ct ? 1 : 0) == t) perm[o++] = q; }
+  {
+    int32_t* perm = p.pperm + (size_t)w * p.Pm;
+    for (int s = wid; s < 2 * F; s += nw) {
+      int o = ofs[s];
+      for (int base = 0; base < np; base += 32) {
+        const int q = base + lane;
+        const bool is = q < np && key_of(q) == s;
+        const unsigned bal = __ballot_sync(0xffffffffu, is);
+        if (is) perm[o + __popc(bal & ((1u << lane) - 1u))] = q;
+        o += __popc(bal);
+      }
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ k_linearize
