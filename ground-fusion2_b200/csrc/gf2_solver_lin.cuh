@@ -32,12 +32,16 @@ __global__ void __launch_bounds__(kTaskThreads) k_tasks(KP p, int w0) {
   const int w = w0 + blockIdx.x;
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5, nw = kTaskThreads / 32, F = p.F;
   __shared__ int cnt[2 * kMaxF], ofs[2 * kMaxF + 1];
+  __shared__ uint8_t key[kMaxPlaneTasks * 32];   // sort key of every table entry (start frame / 2 frame + ct), read from HBM once by the whole CTA
+  static_assert(kMaxPlaneTasks * 32 >= GF2_MAX_LANDMARKS, "key buffer holds the landmark table");
   const int nlm = p.nlm[w];
   const int32_t* start = p.start + (size_t)w * p.Lm;
+  for (int l = t; l < nlm; l += kTaskThreads) key[l] = (uint8_t)start[l];
+  __syncthreads();
   // one warp per start frame, 32 table entries per step: counts and (below) ranks by ballot, in table order
   for (int f = wid; f < F; f += nw) {
     int c = 0;
-    for (int base = 0; base < nlm; base += 32) { const int l = base + lane; c += __popc(__ballot_sync(0xffffffffu, l < nlm && start[l] == f)); }
+    for (int base = 0; base < nlm; base += 32) { const int l = base + lane; c += __popc(__ballot_sync(0xffffffffu, l < nlm && key[l] == f)); }
     if (lane == 0) cnt[f] = c;
   }
   __syncthreads();
@@ -62,7 +66,7 @@ __global__ void __launch_bounds__(kTaskThreads) k_tasks(KP p, int w0) {
       int o = ofs[f];
       for (int base = 0; base < nlm; base += 32) {
         const int l = base + lane;
-        const bool is = l < nlm && start[l] == f;
+        const bool is = l < nlm && key[l] == f;
         const unsigned bal = __ballot_sync(0xffffffffu, is);
         if (is) info[o + __popc(bal & ((1u << lane) - 1u))] = make_int4(l, tlen[l], obeg[l], fixed[l] != 0);
         o += __popc(bal);
@@ -72,9 +76,11 @@ __global__ void __launch_bounds__(kTaskThreads) k_tasks(KP p, int w0) {
   if (!p.planes) return;
   // LiDAR plane factors grouped by key = 2 * frame + ct (LidarPlaneNormFactor / CTLidarPlaneNormFactor), tasks of <= 32 planes
   __syncthreads();
-  const int np = p.n_planes[w];
+  const int np = min(p.n_planes[w], kMaxPlaneTasks * 32);
   const gf2_plane* pls = p.planes + (size_t)w * p.Pm;
-  auto key_of = [&](int q) { return 2 * pls[q].frame + (pls[q].ct ? 1 : 0); };
+  for (int q = t; q < np; q += kTaskThreads) key[q] = (uint8_t)(2 * pls[q].frame + (pls[q].ct ? 1 : 0));
+  __syncthreads();
+  auto key_of = [&](int q) { return (int)key[q]; };
   for (int s = wid; s < 2 * F; s += nw) {
     int c = 0;
     for (int base = 0; base < np; base += 32) { const int q = base + lane; c += __popc(__ballot_sync(0xffffffffu, q < np && key_of(q) == s)); }
