@@ -605,65 +605,69 @@ __global__ void __launch_bounds__(kLinThreads, 2) k_linearize(KP p, int w0) {
   }
   __syncthreads();
 
-  // LiDAR plane factors: tasks of <= 32 planes of one frame; [J | r]^T [J | r] (upper 21 + J^T r 6 = 27 sums) by a warp butterfly
+  // LiDAR plane factors: tasks of <= 32 planes of one key (frame, CT or not). The sums [J | r]^T [J | r] over a task's planes are a Gram matrix
+  // with K = 32: the lanes stage their row [J | r] (7 columns; 13 for a CT factor: begin pose, end pose, residual) transposed in shared memory
+  // and the warp forms the 8x8 tile(s) on the fp64 tensor cores (8 mma per tile), accumulating over CONSECUTIVE tasks of the same key in
+  // registers; the tile entries go to the pose blocks (f, f), (f, f + 1), (f + 1, f + 1) and the gradient by shared atomics only when the
+  // key changes. (A 27-value butterfly per block and task cost ~4x the instructions: 34 % of the sweep of a 5,000-plane window.)
   if (p.planes) {
     const int npt = p.nptasks[w];
     const gf2_plane* pls = p.planes + (size_t)w * p.Pm;
     const int32_t* pperm = p.pperm + (size_t)w * p.Pm;
-    // [J | r]^T [J | r] of one 6-dim pose block summed over the warp's planes -> diagonal block (f, f) and gradient
-    auto accum_diag = [&](int f, const double* Jp, double r) {
-      double m[32];
-      {
-        int c = 0;
-#pragma unroll
-        for (int a = 0; a < 6; a++)
-#pragma unroll
-          for (int b = a; b < 6; b++) m[c++] = Jp[a] * Jp[b];
-#pragma unroll
-        for (int a = 0; a < 6; a++) m[21 + a] = Jp[a] * r;
-#pragma unroll
-        for (int a = 27; a < 32; a++) m[a] = 0.0;
-      }
-      const double tot = butterfly32(m, lane);
-      double* B = &S.U[ublk(f, f, F)];
-      if (lane < 21) {
-        int a = 0, rem = lane;
-        while (rem >= 6 - a) { rem -= 6 - a; a++; }
-        const int b = a + rem;
-        atomicAdd(&B[a * 6 + b], tot);
-        if (a != b) atomicAdd(&B[b * 6 + a], tot);
-      } else if (lane < 27) atomicAdd(&S.g[6 * f + lane - 21], tot);
-    };
+    constexpr int kPS = 36;                                    // staging row stride (4 mod 16: conflict-free fragment loads)
+    double* stg = S.WT + kTermsOfs + wid * 13 * kPS;           // the frame-pair terms are summed: their space stages the planes
+    static_assert(kLinWarps * 13 * kPS <= kMaxF * (kMaxF - 1) * 30, "plane staging fits in the terms area");
     const double* poseW = p.pose + (size_t)w * F * 7;
     const double* palpha = p.plane_alpha ? p.plane_alpha + (size_t)w * p.Pm : nullptr;
+    double t00[2] = {0, 0}, t01[2] = {0, 0}, t11[2] = {0, 0};   // tiles (rows 0..7 x cols 0..7), (0..7 x 8..15), (8..15 x 8..15) of the Gram matrix
+    int cur_key = -1;
+    auto flush = [&]() {
+      if (cur_key < 0) return;
+      const int f = cur_key >> 1; const bool ct = cur_key & 1;
+      auto put = [&](int r, int c, double val) {   // entry (r, c), r <= c, of the Gram matrix of [J_f (6) | r] or [J_f (6) | J_f+1 (6) | r]
+        const int rc = ct ? 12 : 6;                // residual column
+        if (r >= rc || r > c) return;
+        if (c == rc) { atomicAdd(&S.g[6 * (f + r / 6) + r % 6], val); return; }
+        if (c > rc) return;
+        const int br = r / 6, bc = c / 6;          // block row / column: 0 = frame f, 1 = frame f + 1
+        double* B = &S.U[ublk(f + br, f + bc, F)];
+        atomicAdd(&B[(r % 6) * 6 + c % 6], val);
+        if (br == bc && r != c) atomicAdd(&B[(c % 6) * 6 + r % 6], val);   // diagonal blocks are kept full
+      };
+      put(fq, 2 * fk, t00[0]); put(fq, 2 * fk + 1, t00[1]);
+      if (ct) { put(fq, 8 + 2 * fk, t01[0]); put(fq, 9 + 2 * fk, t01[1]); put(8 + fq, 8 + 2 * fk, t11[0]); put(8 + fq, 9 + 2 * fk, t11[1]); }
+      t00[0] = t00[1] = t01[0] = t01[1] = t11[0] = t11[1] = 0.0;
+    };
     for (int q = wid; q < npt; q += kLinWarps) {
       const int key = p.ptask_frame[(size_t)w * kMaxPlaneTasks + q], cnt = p.ptask_cnt[(size_t)w * kMaxPlaneTasks + q], first = p.ptask_first[(size_t)w * kMaxPlaneTasks + q];
-      const int f = key >> 1;
-      if (!(key & 1)) {  // LidarPlaneNormFactor on the pose of frame f
-        double Jp[6] = {0, 0, 0, 0, 0, 0}, r = 0.0;
-        if (lane < cnt) { r = plane_residual(pls[pperm[first + lane]], S.fr[f], p.lidar_sqrt_info, Jp); cost_acc += 0.5 * r * r; }
-        accum_diag(f, Jp, r);
-      } else {           // CTLidarPlaneNormFactor between the poses of frames f (begin) and f + 1 (end): blocks (f,f), (f,f+1), (f+1,f+1)
-        double Jc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, r = 0.0;
-        if (lane < cnt) {
-          const int pi = pperm[first + lane];
-          r = ct_plane_residual(pls[pi], palpha ? palpha[pi] : 0.0, poseW + 7 * f, poseW + 7 * (f + 1), p.lidar_sqrt_info, Jc);
-          cost_acc += 0.5 * r * r;
-        }
-        accum_diag(f, Jc, r);
-        accum_diag(f + 1, Jc + 6, r);
-        double* B = &S.U[ublk(f, f + 1, F)];   // rows: frame f, columns: frame f + 1
+      const int f = key >> 1; const bool ct = key & 1;
+      if (key != cur_key) { flush(); cur_key = key; }
+      double Jc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, r = 0.0;
+      if (lane < cnt) {
+        const int pi = pperm[first + lane];
+        if (!ct) r = plane_residual(pls[pi], S.fr[f], p.lidar_sqrt_info, Jc);   // LidarPlaneNormFactor on the pose of frame f
+        else r = ct_plane_residual(pls[pi], palpha ? palpha[pi] : 0.0, poseW + 7 * f, poseW + 7 * (f + 1), p.lidar_sqrt_info, Jc);   // CTLidarPlaneNormFactor: poses f (begin), f + 1 (end)
+        cost_acc += 0.5 * r * r;
+      }
+      const int nc = ct ? 12 : 6;
+      __syncwarp();
 #pragma unroll
-        for (int pass = 0; pass < 2; pass++) {
-          double m[32];
+      for (int c = 0; c < 12; c++) if (c < nc) stg[c * kPS + lane] = Jc[c];
+      stg[nc * kPS + lane] = r;
+      __syncwarp();
+      const double* s0 = stg + fq * kPS + fk;
+      const bool ok0 = fq <= nc, ok1 = ct && 8 + fq <= nc;   // rows that exist (row nc = the residual column)
 #pragma unroll
-          for (int e = 0; e < 32; e++) { const int idx = 32 * pass + e; m[e] = idx < 36 ? Jc[idx / 6] * Jc[6 + idx % 6] : 0.0; }
-          const double tot = butterfly32(m, lane);
-          const int idx = 32 * pass + lane;
-          if (idx < 36) atomicAdd(&B[idx], tot);
+      for (int ks = 0; ks < 8; ks++) {
+        const double a0 = ok0 ? s0[4 * ks] : 0.0;
+        mma_f64(t00[0], t00[1], a0, a0);
+        if (ct) {   // warp-uniform
+          const double a1 = ok1 ? s0[8 * kPS + 4 * ks] : 0.0;
+          mma_f64(t01[0], t01[1], a0, a1); mma_f64(t11[0], t11[1], a1, a1);
         }
       }
     }
+    flush();
     __syncthreads();
   }
   // S_vis = U - Schur, g_schur = Schur[:,66]
