@@ -660,7 +660,9 @@ static int run(gf2_solver* h, int first, int n, const gf2_solve_opts* opts, gf2_
   // warps (k_linearize_ws) and back-substitution + candidate + decision share one launch (k_step). A full batch gets its occupancy from the
   // batch: k_linearize (two windows per SM) and the three step kernels at their own occupancy. cfg.sweep overrides the choice of the sweep.
   const bool small = n <= 2 * h->sm_count;
-  const bool sweep_ws = h->cfg.sweep == GF2_SWEEP_WINDOW || (h->cfg.sweep == GF2_SWEEP_AUTO && small);
+  // (the window kernel holds one window per SM: up to one window per SM it runs a single wave, 0.062 vs 0.091 ms; beyond that the batch
+  //  kernel's two windows per SM win)
+  const bool sweep_ws = h->cfg.sweep == GF2_SWEEP_WINDOW || (h->cfg.sweep == GF2_SWEEP_AUTO && n <= h->sm_count);
   const bool fused_step = !h->nccl_comm && small;
   for (int it = 0; it < iters; it++) {
     if (sweep_ws) ws::k_linearize_ws<<<n, ws::kLinThreads, sizeof(ws::LinShared), h->stream>>>(k, first);

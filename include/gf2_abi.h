@@ -179,7 +179,7 @@ typedef struct gf2_solver_cfg {
 } gf2_solver_cfg;
 
 enum { /* gf2_solver_cfg.sweep */
-  GF2_SWEEP_AUTO = 0,   /* calls of up to two windows per SM take the window kernel, larger batches the batch kernel */
+  GF2_SWEEP_AUTO = 0,   /* calls of up to one window per SM take the window kernel, larger batches the batch kernel */
   GF2_SWEEP_BATCH = 1,  /* k_linearize: 4 warps per window, two windows per SM (throughput of a full batch) */
   GF2_SWEEP_WINDOW = 2  /* k_linearize_ws: one window per SM, 16 warp-specialised warps (latency of one robot's window) */
 };

@@ -167,7 +167,7 @@ def test_solve_properties_full_size_batch(gf2, synth):
 
 
 def test_small_and_large_batch_paths_agree(gf2, synth):
-    """A call of <= 2 windows per SM takes k_linearize_ws + the fused k_step, a larger one k_linearize + k_backsub / k_cand_eval / k_decide.
+    """A call of <= 1 window per SM takes k_linearize_ws, one of <= 2 windows per SM the fused k_step; a larger one k_linearize + k_backsub / k_cand_eval / k_decide.
     The same three windows solved alone and at the front of a 320-window batch (a batch no B200 takes the small path for): identical
     iteration counts and terminations, states within the 1e-6 the ill-conditioned windows allow; with the sweep kernel pinned to the batch
     kernel in both calls only the step kernels differ (same bodies, same reduction order) and the results are bit-equal."""
