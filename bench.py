@@ -644,6 +644,7 @@ def main():
     ap.add_argument("--windows", type=int, default=4096, help="windows per GPU per step (batch B)")
     ap.add_argument("--distinct", type=int, default=64, help="distinct generated windows tiled to B")
     ap.add_argument("--e2e-chunks", type=int, default=4, help="chunks (handle + stream + host thread each) the e2e leg pipelines the batch over")
+    ap.add_argument("--e2e-obs", default="xy", choices=["xy", "full"], help="observation records of the e2e leg: positions only (8 B) or with velocities (16 B)")
     ap.add_argument("--impl", default="gf2", choices=["gf2", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-marginalize", action="store_true", help="skip the marginalization leg")
@@ -722,9 +723,15 @@ def main():
     ok_frac = float((summ["final_cost"] < 1e-3 * summ["initial_cost"]).mean())
 
     # ------------------------------------------------------------ end-to-end run through the ABI with host buffers
+    # Observations travel as positions only (gf2_set_observations_xy, 8 B instead of 16): ESTIMATE_TD = 0 and td == cur_td of every frame in
+    # this workload, so the velocities never enter the residual and the solve is bit-equal (tests/test_gpu_solver.py); --e2e-obs full sends the records.
+    xy_only = args.e2e_obs == "xy" and bool(np.all(w["td"][:, None] == w["frame_td"]))
+    if xy_only:
+        obs_xy = gf2.pinned_empty((B, w["max_obs"], 2), np.float32)
+        obs_xy[..., 0] = w["obs"]["x"]; obs_xy[..., 1] = w["obs"]["y"]
     h2d = sum(w[k].nbytes for k in ("para_pose", "para_speedbias", "ex_pose", "td", "n_landmarks", "inv_depth", "start_frame", "track_len",
-                                    "fixed", "obs", "frame_td", "imu_samples", "imu_n", "imu_first", "imu_lin_bias", "prior_rows",
-                                    "prior_J0", "prior_r0", "prior_nblocks", "prior_blocks"))
+                                    "fixed", "frame_td", "imu_samples", "imu_n", "imu_first", "imu_lin_bias", "prior_rows",
+                                    "prior_J0", "prior_r0", "prior_nblocks", "prior_blocks")) + (obs_xy.nbytes if xy_only else w["obs"].nbytes)
     d2h = sum(v.nbytes for v in out_states.values()) + out_lam.nbytes + summ.nbytes
 
     # The batch is cut into `--e2e-chunks` chunks; each chunk has its own handle + stream and is driven by its own host
@@ -738,6 +745,8 @@ def main():
         cs = gf2.Solver(hi - lo, N_FRAMES, w["max_landmarks"], w["max_obs"], max_imu_samples=w["n_imu_samples"], device=local,
                         max_prior_rows=w["prior_stride"])
         cw = {k: (v[lo:hi] if isinstance(v, np.ndarray) and v.ndim >= 1 and v.shape[0] == B and k != "imu_noise" else v) for k, v in w.items()}
+        if xy_only:
+            del cw["obs"]; cw["obs_xy"] = obs_xy[lo:hi]
         co = {k: v[lo:hi] for k, v in out_states.items()}
         chunks.append((cs, cw, co, out_lam[lo:hi], summ[lo:hi], hi - lo))
     from concurrent.futures import ThreadPoolExecutor
@@ -828,7 +837,7 @@ def main():
             "config": bench_config(B, min(args.distinct, B), world),
             "converged_fraction": ok_frac,
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "chunks": nch,
+            "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "chunks": nch, "observations": "positions only, 8 B (gf2_set_observations_xy; td == cur_td)" if xy_only else "full records, 16 B",
                     "timing": "host wall clock around the blocking ABI calls of all chunks + device synchronize"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k_linearize", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",

@@ -39,7 +39,7 @@ ABI_SYMBOLS = [
     "gf2_last_error", "gf2_abi_version", "gf2_device_count", "gf2_solver_create", "gf2_solver_destroy", "gf2_set_states",
     "gf2_solver_set_stream", "gf2_snapshot_states", "gf2_restore_states", "gf2_host_alloc", "gf2_host_free",
     "gf2_imu_preintegrate_resident", "gf2_get_trace",
-    "gf2_set_landmarks", "gf2_set_imu", "gf2_imu_preintegrate", "gf2_get_imu", "gf2_set_wheel", "gf2_wheel_preintegrate", "gf2_get_wheel", "gf2_set_prior",
+    "gf2_set_landmarks", "gf2_set_observations_xy", "gf2_set_imu", "gf2_imu_preintegrate", "gf2_get_imu", "gf2_set_wheel", "gf2_wheel_preintegrate", "gf2_get_wheel", "gf2_set_prior",
     "gf2_set_planes", "gf2_set_plane_alpha", "gf2_marginalize", "gf2_marginalize_async", "gf2_marginalize_wait", "gf2_get_prior", "gf2_last_marginalize_ms", "gf2_solve", "gf2_linearize", "gf2_reduced_dim", "gf2_get_reduced_system", "gf2_get_states",
     "gf2_get_landmarks", "gf2_comm_init", "gf2_comm_unique_id", "gf2_last_timing", "gf2_tracker_create",
     "gf2_tracker_destroy", "gf2_tracker_track", "gf2_tracker_track_fb", "gf2_tracker_last_timing",
@@ -109,10 +109,17 @@ class Solver:
                                     _p(w.get("ex_pose_wheel")), _p(w.get("sxsysw")), _p(w.get("td_wheel"))))
 
     def set_landmarks(self, w, first=0, n=None):
+        """w["obs"] (full records) or, without it, w["obs_xy"] ([n][max_obs][2] float32: positions only, half the bytes; valid while
+        td equals every frame's cur_td — see gf2_set_observations_xy)."""
         n = n if n is not None else w["para_pose"].shape[0]
-        assert w["inv_depth"].shape[1] == self.Lm and w["obs"].shape[1] == self.Om, "array strides must equal the solver capacities"
+        xy_only = "obs" not in w
+        ob = w["obs_xy"] if xy_only else w["obs"]
+        assert w["inv_depth"].shape[1] == self.Lm and ob.shape[1] == self.Om, "array strides must equal the solver capacities"
         _check(lib().gf2_set_landmarks(self.h, first, n, _p(w["n_landmarks"]), _p(w["inv_depth"]), _p(w["start_frame"]),
-                                       _p(w["track_len"]), _p(w["fixed"]), _p(w["obs"]), _p(w["frame_td"])))
+                                       _p(w["track_len"]), _p(w["fixed"]), None if xy_only else _p(ob), _p(w["frame_td"])))
+        if xy_only:
+            assert ob.dtype == np.float32 and ob.shape[2:] == (2,) and ob.flags.c_contiguous
+            _check(lib().gf2_set_observations_xy(self.h, first, n, _p(ob)))
 
     def set_imu(self, rec, first=0):
         _check(lib().gf2_set_imu(self.h, first, rec.shape[0], _p(rec)))

@@ -276,6 +276,7 @@ struct gf2_solver {
   void* nccl_comm = nullptr; int comm_rank = 0, comm_size = 1;
   bool has_imu = false, has_wheel = false, has_prior = false, has_planes = false, dump_full = false;
   std::vector<int32_t> h_obeg;
+  float2* d_xy = nullptr;   // staging of gf2_set_observations_xy (allocated on its first call)
   cudaEvent_t ev[4 * 64 + 3];
   cudaEvent_t ev_marg[3] = {nullptr, nullptr, nullptr}; bool marg_pending = false;   // gf2_marginalize_async / _wait
   cudaEvent_t ev_nccl[8 * 64];   // pairs around the collectives of the factor-sharded mode (created by gf2_comm_init)
@@ -427,7 +428,7 @@ int gf2_set_landmarks(gf2_solver* h, int first, int n, const int32_t* n_landmark
                       const int32_t* track_len, const uint8_t* fixed, const gf2_obs* obs, const double* frame_td) {
   GF2_TRY(check_range(h, first, n));
   const KP& k = h->kp; const int F = k.F, Lm = k.Lm, Om = k.Om;
-  if (!n_landmarks || !inv_depth || !start_frame || !track_len || !obs || !frame_td) return gf2::fail(GF2_ERR_INVALID, "null landmark array");
+  if (!n_landmarks || !inv_depth || !start_frame || !track_len || !frame_td) return gf2::fail(GF2_ERR_INVALID, "null landmark array");
   // validate + exclusive prefix sum of track_len on the host (index bookkeeping, bit-exact by construction)
   h->h_obeg.assign((size_t)n * Lm, 0);
   for (int w = 0; w < n; w++) {
@@ -451,6 +452,28 @@ int gf2_set_landmarks(gf2_solver* h, int first, int n, const int32_t* n_landmark
   H2D(k.obs + (size_t)first * Om, obs, sizeof(gf2_obs) * n * Om);
   H2D(k.frame_td + (size_t)first * F, frame_td, sizeof(double) * n * F);
   GF2_CUDA(cudaStreamSynchronize(h->stream));  // h_obeg is reused by the next call
+  return GF2_OK;
+}
+
+// Positions only: 8 B per observation over the bus instead of 16; the records on the device keep their layout (velocity 0).
+__global__ void k_expand_xy(const float2* __restrict__ xy, float4* __restrict__ obs, size_t count) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
+    const float2 p = xy[i];
+    obs[i] = make_float4(p.x, p.y, 0.f, 0.f);
+  }
+}
+
+int gf2_set_observations_xy(gf2_solver* h, int first, int n, const float* xy) {
+  GF2_TRY(check_range(h, first, n));
+  if (!xy) return gf2::fail(GF2_ERR_INVALID, "null observation array");
+  const KP& k = h->kp; const int Om = k.Om;
+  if (!h->d_xy) GF2_TRY(dalloc(h, &h->d_xy, (size_t)h->cfg.max_windows * Om));
+  const size_t count = (size_t)n * Om;
+  H2D(h->d_xy, xy, sizeof(float2) * count);
+  const int blocks = (int)std::min<size_t>((count + 255) / 256, (size_t)8 * h->sm_count);
+  k_expand_xy<<<blocks, 256, 0, h->stream>>>(h->d_xy, const_cast<float4*>(k.obs) + (size_t)first * Om, count);
+  GF2_CUDA(cudaGetLastError());
+  GF2_CUDA(cudaStreamSynchronize(h->stream));  // the staging area is reused by the next call
   return GF2_OK;
 }
 

@@ -269,6 +269,15 @@ int gf2_set_landmarks(gf2_solver* h, int first, int n, const int32_t* n_landmark
                       const int32_t* start_frame, const int32_t* track_len, const uint8_t* fixed,
                       const gf2_obs* obs, const double* frame_td);
 
+/* The same observations without their velocities: xy [n][max_obs][2] floats, 8 B per observation over the bus
+ * instead of 16 (the observations are 3/4 of the bytes a window uploads). The velocity enters the factor only as
+ * (td - td_i) * velocity (VE/factor/projectionTwoFrameOneCamFactor.cpp:53-54), which vanishes when td is not
+ * estimated and equals the cur_td of every frame (ESTIMATE_TD = 0, VE/estimator/estimator.cpp:3055-3061, the mode
+ * gf2_solve supports); the device records are written with velocity 0, so the results are bit-equal to the full
+ * records in that mode and differ as soon as td != frame_td. Pass obs = NULL to gf2_set_landmarks (table only,
+ * resident observations untouched) and call this for the observations. */
+int gf2_set_observations_xy(gf2_solver* h, int first, int n, const float* xy);
+
 /* IMU factors: record k of a window links frames k and k+1 ([n][F-1]). */
 int gf2_set_imu(gf2_solver* h, int first, int n, const gf2_imu_preint* preint);
 /* Same from raw samples, preintegrated on the device: samples [n][F-1][max_imu_samples],

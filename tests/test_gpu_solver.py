@@ -194,6 +194,37 @@ def test_small_and_large_batch_paths_agree(gf2, synth):
             assert np.allclose(s_small["final_cost"], s_big["final_cost"][:3], rtol=1e-6)
 
 
+def test_xy_only_observations_match_full_records(gf2, synth):
+    """gf2_set_observations_xy (positions only, half the H2D bytes): the velocity enters the residual only through (td - td_i) * v
+    (projectionTwoFrameOneCamFactor.cpp:53-54), so with td == cur_td of every frame (ESTIMATE_TD = 0) the solve is bit-equal to the one
+    on the full records; with td != cur_td the velocities matter and the two uploads must differ (the caller then needs the full records)."""
+    n = 3
+    opts = gf2.abi.default_opts()
+
+    def run(w, xy_only):
+        wv = dict(w)
+        if xy_only:
+            o = wv.pop("obs")
+            wv["obs_xy"] = np.ascontiguousarray(np.stack([o["x"], o["y"]], -1))
+        s = _solver(gf2, w, n)
+        s.upload(wv, preintegrate="device")
+        summ = s.solve(opts, n).copy(); st = s.get_states(n); lam = s.get_landmarks(n)
+        s.close()
+        return summ, st, lam
+    w = synth.make_windows(n, n_landmarks=200)
+    assert np.all(w["td"] == 0) and np.all(w["frame_td"] == 0) and np.any(w["obs"]["vx"] != 0)
+    a, b = run(w, False), run(w, True)
+    assert np.array_equal(a[0]["final_cost"], b[0]["final_cost"]) and np.array_equal(a[0]["iterations"], b[0]["iterations"])
+    assert np.array_equal(a[1]["para_pose"], b[1]["para_pose"]) and np.array_equal(a[2], b[2])
+    w2 = dict(w); w2["td"] = np.full(n, 0.02)
+    a, b = run(w2, False), run(w2, True)
+    assert not np.array_equal(a[1]["para_pose"], b[1]["para_pose"])
+    # table-only update leaves the resident observations alone; a null xy array is rejected
+    s = _solver(gf2, w, n); s.upload(w, preintegrate="device")
+    assert gf2.lib().gf2_set_observations_xy(s.h, 0, n, None) == -1   # GF2_ERR_INVALID
+    s.close()
+
+
 def test_edge_cases(gf2, oracle, synth):
     """Empty window (no landmarks), a window with fixed landmarks, and zero iterations."""
     w = synth.make_windows(3, n_landmarks=120)
